@@ -1,0 +1,150 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py
+
+Every array written here is an output of /root/reference code (imported through
+ref_harness.py) on seeded inputs; the inputs of the small op-level cases are stored beside
+the outputs, the stream case regenerates its frames from oracle.synth_frame (checksummed).
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_harness  # noqa: E402
+from oracle import stabstitch_oracle as O  # noqa: E402
+from oracle import weights as Wt  # noqa: E402
+
+STREAM_N, STREAM_H, STREAM_W = 9, 180, 320
+MESH_SCALE_S, MESH_SCALE_T = 20.0, 10.0
+
+
+def ops_case(m):
+    g = torch.Generator().manual_seed(1234)
+    out = {}
+    rn = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    S = m["spatial_network"]
+    # DLT + H2Mesh
+    src = torch.tensor([[0.0, 0.0], [480.0, 0.0], [0.0, 360.0], [480.0, 360.0]])[None].repeat(3, 1, 1)
+    dst = src + 30.0 * rn(3, 4, 2)
+    Hm = m["utils.torch_DLT"].tensor_DLT(src, dst)
+    out["dlt_src"], out["dlt_dst"], out["dlt_H"] = src, dst, Hm
+    out["h2mesh"] = S.H2Mesh(Hm, S.get_rigid_mesh(3, 360, 480))
+    # homography feature warp
+    U = rn(2, 8, 45, 60)
+    theta = torch.eye(3)[None].repeat(2, 1, 1) + 0.05 * rn(2, 3, 3)
+    out["homo_U"], out["homo_theta"] = U, theta
+    out["homo_out"] = m["utils.torch_homo_transform"].transformer(U, theta, (45, 60))
+    # cost volume
+    a, b = rn(1, 16, 12, 14), rn(1, 16, 12, 14)
+    out["cv_a"], out["cv_b"] = a, b
+    out["cv_sr5"] = S.SpatialNet.cost_volume(a, b, search_range=5, norm=False)
+    out["cv_sr3"] = S.SpatialNet.cost_volume(a, b, search_range=3, norm=False)
+    # CCL (needs the module only for extract_patches)
+    net = S.SpatialNet()
+    f1, f2 = rn(1, 32, 9, 11), rn(1, 32, 9, 11)
+    out["ccl_f1"], out["ccl_f2"] = f1, f2
+    out["ccl_out"] = net.CCL(f1, f2)
+    # TPS: point and image
+    rig = S.get_norm_mesh(S.get_rigid_mesh(2, 360, 480), 360, 480)
+    srcm = rig + 0.03 * rn(2, 63, 2)
+    pts = rig + 0.02 * rn(2, 63, 2)
+    out["tps_rigid"], out["tps_src"], out["tps_pts"] = rig, srcm, pts
+    out["tps_point_out"] = m["utils.torch_tps_transform_point"].transformer(pts, rig, srcm)
+    img = 127.5 * (1 + torch.tanh(torch.nn.functional.interpolate(rn(2, 3, 6, 8), size=(48, 64), mode="bicubic")))
+    out["tps_img"] = img
+    # view placed inside a wider canvas, like get_stable_sqe does
+    srcc = torch.stack([srcm[..., 0] * 0.55 + torch.tensor([-0.4, 0.4])[:, None], srcm[..., 1] * 0.9], 2)
+    out["tps_src_canvas"] = srcc
+    out["tps_warp_normal"] = m["utils.torch_tps_transform"].transformer(img, srcc, rig, (40, 100), mode="NORMAL")
+    out["tps_warp_fast"] = m["utils.torch_tps_transform"].transformer(img, srcc, rig, (40, 100), mode="FAST")
+    return {k: v.detach().numpy() for k, v in out.items()}
+
+
+def stream_case(m):
+    S, T, Sm, D = (m["spatial_network"], m["temporal_network"], m["smooth_network"], m["test_online_tra"])
+    tpp = m["utils.torch_tps_transform_point"]
+    sds = Wt.spatial_state_dict(mesh_scale=MESH_SCALE_S)
+    sdt = Wt.temporal_state_dict(mesh_scale=MESH_SCALE_T)
+    sdm = Wt.smooth_state_dict()
+    sn, tn, mn = S.SpatialNet().eval(), T.TemporalNet().eval(), Sm.SmoothNet().eval()
+    sn.load_state_dict(sds, strict=True)
+    tn.load_state_dict(sdt, strict=True)
+    mn.load_state_dict(sdm, strict=True)
+    N, H, W = STREAM_N, STREAM_H, STREAM_W
+    hr = [[O.synth_frame(t, v, H, W) for t in range(N)] for v in range(2)]
+    lr = [[O.lowres(x) for x in hr[v]] for v in range(2)]
+    out = {"hr_checksum": np.array([float(sum(x.double().sum() for x in hr[v])) for v in range(2)]),
+           "lr_checksum": np.array([float(sum(x.double().abs().sum() for x in lr[v])) for v in range(2)])}
+    # ---- mirrors the body of test_online_tra.test(), lines 284-399 ----
+    sm = [[], []]
+    fwd = []
+    for k in range(N):
+        fwd.append(sn(lr[0][k], lr[1][k]))
+        r = S.build_SpatialNet(sn, lr[0][k], lr[1][k])
+        sm[0].append(r["motion1"])
+        sm[1].append(r["motion2"])
+    tm = [T.build_TemporalNet(tn, lr[0])["motion_list"], T.build_TemporalNet(tn, lr[1])["motion_list"]]
+    rigid = D.get_rigid_mesh(1, 360, 480)
+    nrig = D.get_norm_mesh(rigid, 360, 480)
+    smesh, ts = [[], []], [[], []]
+    for v in range(2):
+        for k in range(N):
+            s = rigid + sm[v][k]
+            if k == 0:
+                t_ = sm[v][k].clone() * 0
+            else:
+                sp = rigid + sm[v][k - 1]
+                tmesh = rigid + tm[v][k]
+                moved = tpp.transformer(D.get_norm_mesh(tmesh, 360, 480), nrig, D.get_norm_mesh(sp, 360, 480))
+                t_ = D.recover_mesh(moved, 360, 480) - s
+            smesh[v].append(s)
+            ts[v].append(t_)
+    S1 = S2 = None
+    win0 = None
+    for k in range(N - 6):
+        a1 = ts[0][k:k + 7]
+        a1[0] = a1[0] * 0
+        a2 = ts[1][k:k + 7]
+        a2[0] = a2[0] * 0
+        o = Sm.build_SmoothNet(mn, a1, a2, smesh[0][k:k + 7], smesh[1][k:k + 7])
+        if k == 0:
+            S1, S2 = o["smooth_mesh1"], o["smooth_mesh2"]
+            win0 = o
+        else:
+            S1 = torch.cat((S1, o["smooth_mesh1"][:, -1:]), 1)
+            S2 = torch.cat((S2, o["smooth_mesh2"][:, -1:]), 1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        frames, ow, oh = D.get_stable_sqe(hr[0], hr[1], S1, S2, warp_mode="NORMAL", fusion_mode="AVERAGE")
+    out["offset_1"] = torch.cat([f[0] for f in fwd], 0)
+    out["offset_2_ref"] = torch.cat([f[1] for f in fwd], 0)
+    out["offset_2_tgt"] = torch.cat([f[2] for f in fwd], 0)
+    for v in range(2):
+        out["smotion%d" % (v + 1)] = torch.cat(sm[v], 0)
+        out["tmotion%d" % (v + 1)] = torch.cat(tm[v], 0)
+        out["tsmotion%d" % (v + 1)] = torch.cat(ts[v], 0)
+    for key in ("ori_path1", "smooth_path1", "ori_mesh1", "smooth_mesh1",
+                "ori_path2", "smooth_path2", "ori_mesh2", "smooth_mesh2"):
+        out["win0_" + key] = win0[key]
+    out["smooth_mesh1"], out["smooth_mesh2"] = S1, S2
+    out["canvas_hw"] = np.array([int(oh), int(ow)])
+    out["frame0"] = frames[0]
+    out["frame_last_rows8"] = frames[-1][::8]
+    return {k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
+
+
+if __name__ == "__main__":
+    torch.set_grad_enabled(False)
+    mods = ref_harness.load()
+    np.savez_compressed(os.path.join(HERE, "ops.npz"), **ops_case(mods))
+    np.savez_compressed(os.path.join(HERE, "stream_small.npz"), **stream_case(mods))
+    for f in ("ops.npz", "stream_small.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,101 @@
+"""Pin the CPU oracle (oracle/stabstitch_oracle.py) to the committed golden vectors, which
+are outputs of the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import torch
+
+from oracle import stabstitch_oracle as O
+from oracle import weights as Wt
+
+T = torch.from_numpy
+
+
+def close(a, b, tol):
+    a = a.detach().numpy() if torch.is_tensor(a) else a
+    assert a.shape == b.shape
+    assert np.abs(a - b).max() <= tol, np.abs(a - b).max()
+
+
+def test_dlt_h2mesh(golden_ops):
+    g = golden_ops
+    H = O.tensor_dlt(T(g["dlt_src"]), T(g["dlt_dst"]))
+    close(H, g["dlt_H"], 1e-5)
+    close(O.h2mesh(T(g["dlt_H"]), O.rigid_mesh(3, 360, 480)), g["h2mesh"], 1e-3)
+
+
+def test_homo_warp(golden_ops):
+    g = golden_ops
+    close(O.homo_warp(T(g["homo_U"]), T(g["homo_theta"]), (45, 60)), g["homo_out"], 1e-5)
+
+
+def test_cost_volume(golden_ops):
+    g = golden_ops
+    close(O.cost_volume(T(g["cv_a"]), T(g["cv_b"]), 5), g["cv_sr5"], 1e-6)
+    close(O.cost_volume(T(g["cv_a"]), T(g["cv_b"]), 3), g["cv_sr3"], 1e-6)
+
+
+def test_ccl(golden_ops):
+    g = golden_ops
+    close(O.ccl(T(g["ccl_f1"]), T(g["ccl_f2"])), g["ccl_out"], 1e-5)
+
+
+def test_ccl_known_answers():
+    # SURVEY.md 8c known-answer identities: CCL(f,f)=0, CCL(f, roll(f,(1,2)))=(2,1) interior
+    g = torch.Generator().manual_seed(5)
+    f = torch.randn(1, 64, 12, 16, generator=g)
+    assert O.ccl(f, f).abs().max() < 1e-5
+    fl = O.ccl(f, torch.roll(f, (1, 2), (2, 3)))[0, :, 3:-3, 3:-3]
+    assert (fl[0] - 2).abs().max() < 1e-3 and (fl[1] - 1).abs().max() < 1e-3
+
+
+def test_tps_point_and_warp(golden_ops):
+    g = golden_ops
+    close(O.tps_point(T(g["tps_pts"]), T(g["tps_rigid"]), T(g["tps_src"])), g["tps_point_out"], 1e-6)
+    w = O.tps_warp(T(g["tps_img"]), T(g["tps_src_canvas"]), T(g["tps_rigid"]), (40, 100), "NORMAL")
+    close(w, g["tps_warp_normal"], 1e-4)
+    w = O.tps_warp(T(g["tps_img"]), T(g["tps_src_canvas"]), T(g["tps_rigid"]), (40, 100), "FAST")
+    close(w, g["tps_warp_fast"], 1e-4)
+
+
+def test_tps_identity():
+    rig = O.norm_mesh(O.rigid_mesh(1, 360, 480), 360, 480)
+    close(O.tps_point(rig, rig, rig), rig.numpy(), 1e-5)
+    assert (O.tensor_dlt(torch.tensor([[[0., 0.], [4, 0], [0, 3], [4, 3]]]),
+                         torch.tensor([[[0., 0.], [4, 0], [0, 3], [4, 3]]])) - torch.eye(3)).abs().max() < 1e-5
+
+
+def test_fp64_arbiter_agrees(golden_ops):
+    g = golden_ops
+    src, tgt = T(g["tps_src_canvas"]), T(g["tps_rigid"])
+    ax, ay = O.tps_source_coords_fp64(src, tgt, 40, 100, 64, 48)
+    Tm = O.tps_solve(src, tgt)
+    xt = torch.linspace(-1, 1, 100)[None, :].expand(40, 100).reshape(-1)
+    yt = torch.linspace(-1, 1, 40)[:, None].expand(40, 100).reshape(-1)
+    xs, ys = O.tps_eval(Tm, src, xt, yt)
+    assert np.abs((xs.numpy().reshape(2, 40, 100) + 1) * 32 - ax).max() < 1e-3
+    assert np.abs((ys.numpy().reshape(2, 40, 100) + 1) * 24 - ay).max() < 1e-3
+
+
+def test_stream(golden_stream):
+    from tests.golden.make_golden import STREAM_N, STREAM_H, STREAM_W, MESH_SCALE_S, MESH_SCALE_T
+    g = golden_stream
+    N, H, W = STREAM_N, STREAM_H, STREAM_W
+    hr = [[O.synth_frame(t, v, H, W) for t in range(N)] for v in range(2)]
+    lr = [[O.lowres(x) for x in hr[v]] for v in range(2)]
+    cs = np.array([float(sum(x.double().sum() for x in hr[v])) for v in range(2)])
+    assert np.allclose(cs, g["hr_checksum"], rtol=1e-9), "synthetic frames differ from the fixture's"
+    with torch.no_grad():
+        out = O.stitch_stream(Wt.spatial_state_dict(mesh_scale=MESH_SCALE_S),
+                              Wt.temporal_state_dict(mesh_scale=MESH_SCALE_T), Wt.smooth_state_dict(),
+                              lr[0], lr[1], hr[0], hr[1])
+    close(torch.cat(out["smotion1"], 0), g["smotion1"], 2e-4)
+    close(torch.cat(out["smotion2"], 0), g["smotion2"], 2e-4)
+    close(torch.cat(out["tmotion1"], 0), g["tmotion1"], 2e-4)
+    close(torch.cat(out["tsmotion2"], 0), g["tsmotion2"], 5e-4)
+    close(out["smooth_mesh1"], g["smooth_mesh1"], 5e-4)
+    close(out["smooth_mesh2"], g["smooth_mesh2"], 5e-4)
+    assert tuple(g["canvas_hw"]) == out["canvas"]
+    d = np.abs(out["frames"][0] - g["frame0"])
+    # hard image edges flip single pixels when the mesh moves by 1e-5 px: bound the fraction
+    assert (d > 0.05).mean() < 1e-3, (d > 0.05).mean()
+    d = np.abs(out["frames"][-1][::8] - g["frame_last_rows8"])
+    assert (d > 0.05).mean() < 1e-3
