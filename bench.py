@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py - stitched frames/s of the StabStitch++ inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+A "step" is one pass of the whole hot path (SpatialNet, TemporalNet x2, tsmotion, SmoothNet
+windows, canvas, fused TPS resample + AVERAGE blend; test_online_tra.py:284-399 of the
+reference) over one chunk of `--frames` consecutive synthetic 720p frame pairs per GPU.
+N > 1 (under torchrun): the stream is sharded in time, rank r owns frames [r*F, (r+1)*F)
+(weak scaling); KB-sized mesh halo all-gather + canvas min/max all-reduce over NCCL.
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the
+same through ss2_stitch_stream_host with pinned HOST buffers (H2D + D2H inside the timed
+region); `roofline` = the fused resample+blend kernel's achieved algorithmic HBM GB/s against
+MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle port of the reference timed on this box's
+host cores on a bounded sample.  `--impl reference` times only that CPU port.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "stitched frames/sec at 720p pair"
+UNIT = "frames/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--frames", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--height", type=int, default=720)
+    ap.add_argument("--width", type=int, default=1280)
+    ap.add_argument("--tps", default="default", choices=["default", "exact", "lattice"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(self.NAMES, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference leg (the ONLY place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_sample(H, W, warp_frames=2):
+    """One bounded sample of the workload on the host cores: a 7-frame stream (one SmoothNet
+    window) through every network stage of the CPU oracle port, the resample+blend timed on
+    `warp_frames` of the 7 frames and scaled to 7.  Returns (frames/s, seconds spent)."""
+    import torch
+    from oracle import stabstitch_oracle as O
+    from stabstitch2_b200 import synthetic
+    n = 7
+    sds = _cached("sds", lambda: synthetic.spatial_state_dict(mesh_scale=20.0))
+    sdt = _cached("sdt", lambda: synthetic.temporal_state_dict(mesh_scale=10.0))
+    sdm = _cached("sdm", lambda: synthetic.smooth_state_dict())
+    hr = _cached("hr%dx%d" % (H, W), lambda: [[synthetic.synth_frame(k, v, H, W) for k in range(n)] for v in range(2)])
+    lr = _cached("lr%dx%d" % (H, W), lambda: [[synthetic.lowres(x) for x in hr[v]] for v in range(2)])
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        sm1, sm2 = [], []
+        for k in range(n):
+            a, b = O.build_spatial(sds, lr[0][k], lr[1][k])
+            sm1.append(a)
+            sm2.append(b)
+        tm1 = O.temporal_forward(sdt, lr[0])
+        tm2 = O.temporal_forward(sdt, lr[1])
+        smesh1, ts1 = O.tsmotion_prep(sm1, tm1)
+        smesh2, ts2 = O.tsmotion_prep(sm2, tm2)
+        S1, S2 = O.smooth_stream(sdm, smesh1, smesh2, ts1, ts2)
+        m1, m2, wmin, hmin, ow, oh = O.canvas(S1, S2, H, W)
+        t1 = time.perf_counter()
+        for k in range(warp_frames):
+            O.stable_frame(hr[0][k], hr[1][k], m1[:, k], m2[:, k], wmin, hmin, ow, oh)
+        t2 = time.perf_counter()
+    total = (t1 - t0) + (t2 - t1) * n / warp_frames
+    return n / total, t2 - t0
+
+
+_cache = {}
+
+
+def _cached(key, fn):
+    if key not in _cache:
+        _cache[key] = fn()
+    return _cache[key]
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the host cores.  The reference is
+    pure Python/PyTorch without packaging (no setup.py) and /root/reference does not exist on
+    the GPU box, so this arm times the CPU oracle port (oracle/stabstitch_oracle.py, pinned to
+    the reference's outputs by tests/golden) with every host thread torch can use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    H, W = args.height, args.width
+    for _ in range(args.warmup):
+        cpu_reference_sample(H, W, warp_frames=1)
+    vals, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        fps, _ = cpu_reference_sample(H, W, warp_frames=1)
+        vals.append(fps)
+    wall = time.perf_counter() - t0
+    # harmonic mean = total frames / total (scaled) time
+    value = len(vals) / sum(1.0 / v for v in vals)
+    sample = ("per step: 7-frame %dx%d stream (1 SmoothNet window) through all network stages; "
+              "resample+blend timed on 1 frame and scaled x7" % (H, W))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%dp synthetic pair stream, full Spatial+Temporal+Smooth+warp inference" % H,
+                       "height": H, "width": W},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from stabstitch2_b200 import _lib, pipeline, synthetic
+    from stabstitch2_b200.smooth_network import SmoothNet
+    from stabstitch2_b200.spatial_network import SpatialNet
+    from stabstitch2_b200.temporal_network import TemporalNet
+    from stabstitch2_b200.utils import torch_tps_transform as tt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tps = {"default": tt.DEFAULT_TPS, "exact": _lib.TPS_EXACT, "lattice": _lib.TPS_LATTICE}[args.tps]
+    H, W, F = args.height, args.width, args.frames
+    ctx = _lib.context()
+
+    s, t, m = SpatialNet().cuda().eval(), TemporalNet().cuda().eval(), SmoothNet().cuda().eval()
+    s.load_state_dict(synthetic.spatial_state_dict(mesh_scale=20.0), strict=True)
+    t.load_state_dict(synthetic.temporal_state_dict(mesh_scale=10.0), strict=True)
+    m.load_state_dict(synthetic.smooth_state_dict(), strict=True)
+
+    # this rank's chunk of the stream (+ the one-frame input halo TemporalNet needs on rank > 0)
+    f0 = rank * F
+    halo = 1 if rank > 0 else 0
+    hr1 = torch.cat([synthetic.synth_frame(k, 0, H, W) for k in range(f0 - halo, f0 + F)], 0)
+    hr2 = torch.cat([synthetic.synth_frame(k, 1, H, W) for k in range(f0 - halo, f0 + F)], 0)
+    lr1, lr2 = synthetic.lowres(hr1), synthetic.lowres(hr2)
+    hr1, hr2 = hr1[halo:].contiguous(), hr2[halo:].contiguous()
+    d_lr1, d_lr2, d_hr1, d_hr2 = lr1.cuda(), lr2.cuda(), hr1.cuda(), hr2.cuda()
+
+    def step():
+        if world == 1:
+            return pipeline.stitch_stream(s, t, m, d_lr1, d_lr2, d_hr1, d_hr2, tps=tps)[0]
+        return pipeline.stitch_stream_sharded(s, t, m, d_lr1, d_lr2, d_hr1, d_hr2, halo, tps=tps)[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        fused = step()
+    barrier()
+    Ho, Wo = int(fused.shape[2]), int(fused.shape[3])
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.launch_count(reset=True)
+    ctx.profile_enable(_lib.PROF_WARP, True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        fused = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count()
+    warp_ms, warp_n, warp_bytes = ctx.profile_read(_lib.PROF_WARP)
+    ctx.profile_enable(_lib.PROF_WARP, False)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tmax = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = world * F * args.steps / (ms / 1000.0)
+
+    # ---- e2e: HOST buffers through the C-ABI call, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        pins = [x.contiguous().pin_memory() for x in (lr1[halo:], lr2[halo:], hr1, hr2)]
+        out = torch.empty(F * 3 * Ho * Wo, dtype=torch.float32).pin_memory()
+        for _ in range(max(1, min(args.warmup, 2))):
+            pipeline.stitch_stream_host(s, t, m, *pins, out, tps=tps)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pipeline.stitch_stream_host(s, t, m, *pins, out, tps=tps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tmax = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dt = float(tmax.item())
+        e2e = {"value": world * F * args.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(sum(p.numel() for p in pins) * 4),
+               "d2h_bytes_per_step": int(F * 3 * Ho * Wo * 4 + 16),
+               "note": "per GPU; the whole stream is processed independently per rank in this leg" if world > 1 else
+                       "ss2_stitch_stream_host through pinned host buffers"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    achieved = (warp_bytes / warp_n) / (warp_ms / warp_n * 1e-3) / 1e9 if warp_n else None
+    roofline = {"bound": "hbm", "kernel": "tps_warp_blend (fused TPS resample + AVERAGE blend)",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": None,
+                "algorithmic_bytes_per_launch": warp_bytes / warp_n if warp_n else None,
+                "avg_launch_ms": warp_ms / warp_n if warp_n else None, "launches_timed": warp_n,
+                "share_of_step": warp_ms / ms if ms else None}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu_reference_sample(H, W, warp_frames=1)  # warm the CPU caches / lazy inits
+        fps, spent = cpu_reference_sample(H, W, warp_frames=2)
+        cpu = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "7-frame %dx%d stream (1 SmoothNet window) through all network stages of the CPU oracle "
+                         "port; resample+blend timed on 2 frames and scaled x3.5 (%.1f s of CPU work)" % (H, W, spent)}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%dp synthetic pair stream, full Spatial+Temporal+Smooth inference + fused TPS "
+                                   "resample/AVERAGE blend" % H, "height": H, "width": W, "canvas": [Ho, Wo],
+                       "frames_per_step_per_gpu": F, "net_input": [360, 480], "window": 7,
+                       "tps_field": "exact" if tps == _lib.TPS_EXACT else "lattice",
+                       "l2": "inputs larger than L2: %.0f MB of frames per step per GPU" % (F * 2 * 3 * H * W * 4 / 1e6),
+                       "parallelism": "temporal shards x%d" % world},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,190 @@
+/*
+ * ss2.h - C ABI of libss2.so: the B200-native (sm_100a) StabStitch++ inference hot path.
+ *
+ * The reference (nie-lang/StabStitch2) has no FFI: its boundary is the set of Python names
+ * its drivers import (Full_model_inference/Codes/test_online_tra.py:7-9,14-15,21-23).  The
+ * Python shim modules in stabstitch2_b200/ keep those names and call the entry points
+ * below through ctypes; each entry point cites the reference function it replaces
+ * (paths relative to /root/reference/Full_model_inference/Codes/).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types.
+ *  - every function returns 0 on success or a negative ss2_status; ss2_last_error(ctx)
+ *    gives the message.  Nothing exits or throws across the ABI.
+ *  - pointers named d_* are DEVICE pointers (caller-allocated, caller-owned); h_* are HOST
+ *    pointers.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - all entry points are asynchronous and stream-ordered unless documented otherwise.
+ *  - a context is bound to one device and is NOT thread-safe; distinct contexts are
+ *    independent (one per process/GPU in the multi-GPU layout).
+ *  - images are fp32 NCHW exactly like the reference tensors; meshes are fp32 [..,7,9,2]
+ *    with last dim (x, y) (grid_res.py:3-4 -> 63 control points).
+ */
+#ifndef SS2_H
+#define SS2_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ss2_ctx ss2_ctx;
+
+typedef enum {
+  SS2_OK = 0,
+  SS2_ERR_INVALID = -1,      /* bad argument / shape */
+  SS2_ERR_CUDA = -2,         /* CUDA runtime error (message has the cudaError string) */
+  SS2_ERR_NO_WEIGHTS = -3,   /* forward called before ss2_finalize_weights */
+  SS2_ERR_MISSING_KEY = -4,  /* a state-dict key the network needs was never loaded */
+  SS2_ERR_OOM = -5,
+  SS2_ERR_UNSUPPORTED = -6
+} ss2_status;
+
+enum { SS2_NET_SPATIAL = 0, SS2_NET_TEMPORAL = 1, SS2_NET_SMOOTH = 2 };
+enum { SS2_MODE_NORMAL = 0, SS2_MODE_FAST = 1 };   /* torch_tps_transform.py:151-162 */
+/* evaluation precision of the dense TPS field inside the resampler */
+enum { SS2_TPS_EXACT = 0,    /* all 63 radial terms per pixel (the reference's arithmetic) */
+       SS2_TPS_LATTICE = 1   /* far field interpolated on a per-tile lattice, near field exact */ };
+
+#define SS2_GRID_H 6
+#define SS2_GRID_W 8
+#define SS2_NPT 63
+#define SS2_WINDOW 7
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int ss2_create(int device, ss2_ctx** out);
+void ss2_destroy(ss2_ctx* ctx);
+const char* ss2_last_error(ss2_ctx* ctx);
+const char* ss2_version(void);
+/* number of kernel launches issued through this context since creation / last reset */
+int64_t ss2_launch_count(ss2_ctx* ctx, int reset);
+
+/* ---- in-library kernel timing (bench.py's roofline leg) -------------------------------- */
+/* While enabled, the launches of kernel class `which` are bracketed by CUDA events recorded on
+ * the launching stream.  ss2_profile_read synchronises those events and returns the summed
+ * duration (ms) and the number of launches since the last ss2_profile_enable. */
+enum { SS2_PROF_WARP = 0,   /* fused TPS resample + blend kernel */
+       SS2_PROF_CONV = 1,   /* implicit-GEMM convolution / linear kernels */
+       SS2_PROF_COUNT = 2 };
+int ss2_profile_enable(ss2_ctx* ctx, int which, int enable);
+int ss2_profile_read(ss2_ctx* ctx, int which, double* total_ms, int64_t* launches, double* work);
+
+/* ---- weights: replaces nn.Module.load_state_dict (test_online_tra.py:178-190) -------- */
+/* Copies one fp32 state-dict tensor (host memory) under its reference key name. */
+int ss2_load_tensor(ss2_ctx* ctx, int net_id, const char* key, const float* h_data,
+                    const int64_t* shape, int ndim);
+/* Folds eval-mode BatchNorm into the convolutions, re-packs to the kernels' layouts and
+ * uploads.  Synchronous.  Fails with SS2_ERR_MISSING_KEY naming the first absent key. */
+int ss2_finalize_weights(ss2_ctx* ctx, int net_id);
+
+/* ---- geometry --------------------------------------------------------------------------*/
+/* utils/torch_DLT.py:17 tensor_DLT: src,dst [bs,4,2] -> H [bs,3,3] */
+int ss2_dlt(ss2_ctx* ctx, const float* d_src, const float* d_dst, int bs, float* d_H, void* stream);
+/* utils/torch_homo_transform.py:6 transformer: U [bn,C,H,W], theta [bn,3,3] -> [bn,C,Ho,Wo] */
+int ss2_homo_warp(ss2_ctx* ctx, const float* d_U, const float* d_theta, int bn, int C, int H, int W,
+                  int Ho, int Wo, float* d_out, void* stream);
+/* utils/torch_tps_transform_point.py:6 transformer: point,source,target [bn,63,2] -> [bn,63,2] */
+int ss2_tps_point(ss2_ctx* ctx, const float* d_point, const float* d_source, const float* d_target,
+                  int bn, float* d_out, void* stream);
+/* utils/torch_tps_transform.py:7 transformer: U [bn,C,H,W], source,target [bn,63,2]
+ * -> [bn,C,Ho,Wo]; mode = SS2_MODE_NORMAL | SS2_MODE_FAST; tps = SS2_TPS_EXACT | _LATTICE */
+int ss2_tps_warp(ss2_ctx* ctx, const float* d_U, const float* d_source, const float* d_target,
+                 int bn, int C, int H, int W, int Ho, int Wo, int mode, int tps, float* d_out,
+                 void* stream);
+/* Fused resampler + AVERAGE blend: the body of the get_stable_sqe loop,
+ * test_online_tra.py:140-142.  img1,img2 [3,H,W] fp32; source [2,63,2] (view 1, view 2
+ * normalised canvas meshes); target [2,63,2]; out [3,Ho,Wo].  One launch for the TPS
+ * solves + one for warp/gather/blend.  `nframes` frames are processed in one call:
+ * img pointers are [nframes,3,H,W], source/target [nframes,2,63,2], out [nframes,3,Ho,Wo]. */
+int ss2_tps_warp_blend_avg(ss2_ctx* ctx, const float* d_img1, const float* d_img2,
+                           const float* d_source, const float* d_target, int nframes, int H, int W,
+                           int Ho, int Wo, int mode, int tps, float* d_out, void* stream);
+
+/* ---- correlation layers (NHWC activations) ---------------------------------------------- */
+/* SpatialNet.cost_volume / TemporalNet.cost_volume (spatial_network.py:333, norm=False):
+ * x1,x2 [B,H,W,128] -> out [B,H,W,CP], channels d = j*(2sr+1)+i, CP >= (2sr+1)^2, rest 0 */
+int ss2_cost_volume_nhwc(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B, int H, int W, int C,
+                         int sr, int CP, float* d_out, void* stream);
+/* SpatialNet.CCL (spatial_network.py:369): f1,f2 [B,H,W,C] -> flow [B,H,W,4] = (flow_w, flow_h, 0, 0) */
+int ss2_ccl_nhwc(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H, int W, int C,
+                 float* d_flow, void* stream);
+
+/* ---- networks ------------------------------------------------------------------------- */
+/* SpatialNet.forward, spatial_network.py:276: img1,img2 [bs,3,360,480] ->
+ * offset_1 [bs,8], offset_2_ref [bs,126], offset_2_tgt [bs,126] */
+int ss2_spatial_forward(ss2_ctx* ctx, const float* d_img1, const float* d_img2, int bs,
+                        float* d_offset1, float* d_offset2_ref, float* d_offset2_tgt, void* stream);
+/* build_SpatialNet, spatial_network.py:63: -> motion1, motion2 [bs,7,9,2] */
+int ss2_build_spatial(ss2_ctx* ctx, const float* d_img1, const float* d_img2, int bs,
+                      float* d_motion1, float* d_motion2, void* stream);
+/* the post-network tail of build_SpatialNet (spatial_network.py:68-115) on its own */
+int ss2_spatial_tail(ss2_ctx* ctx, const float* d_offset1, const float* d_offset2_ref,
+                     const float* d_offset2_tgt, int bs, int img_h, int img_w, float* d_motion1,
+                     float* d_motion2, void* stream);
+/* build_TemporalNet, temporal_network.py:23: frames [n,3,360,480] (consecutive frames of one
+ * view) -> motions [n,7,9,2]; motions[0] = 0, motions[k] = motion of frame k w.r.t. k-1 */
+int ss2_build_temporal(ss2_ctx* ctx, const float* d_frames, int n, float* d_motions, void* stream);
+/* tsmotion preparation, test_online_tra.py:309-347, one view: smotion,tmotion [n,7,9,2] ->
+ * smesh, tsmotion [n,7,9,2].  `first_is_stream_start` != 0 makes tsmotion[0] = 0 (k == 0
+ * branch); otherwise smotion_prev [7,9,2] (frame before the chunk) must be given. */
+int ss2_tsmotion(ss2_ctx* ctx, const float* d_smotion, const float* d_tmotion, int n,
+                 int first_is_stream_start, const float* d_smotion_prev, float* d_smesh,
+                 float* d_tsmotion, void* stream);
+/* build_SmoothNet over `nwin` consecutive sliding windows, smooth_network.py:23 +
+ * test_online_tra.py:359-392.  smesh*, tsmotion* [nwin+6,7,9,2] (frame-major); window w uses
+ * frames w..w+6; zero_first != 0 zeroes the tsmotion of each window's first frame (what the
+ * reference's driver does before the call, test_online_tra.py:361-365).  Outputs, each [nwin,7,7,9,2]:
+ * ori_path, smooth_path, ori_mesh, smooth_mesh for view 1 then view 2 (any may be NULL). */
+int ss2_build_smooth(ss2_ctx* ctx, const float* d_tsmotion1, const float* d_tsmotion2,
+                     const float* d_smesh1, const float* d_smesh2, int nwin, int zero_first,
+                     float* d_ori_path1, float* d_smooth_path1, float* d_ori_mesh1, float* d_smooth_mesh1,
+                     float* d_ori_path2, float* d_smooth_path2, float* d_ori_mesh2, float* d_smooth_mesh2,
+                     void* stream);
+
+/* ---- canvas (get_stable_sqe, test_online_tra.py:103-120) -------------------------------- */
+/* smooth meshes [n,7,9,2] @480x360 for both views -> d_minmax[4] = {xmin, xmax, ymin, ymax} of
+ * the hr-rescaled meshes (x*img_w/480, y*img_h/360).  Multi-GPU: all-reduce these 4 floats
+ * (min on 0,2; max on 1,3) before ss2_stable_frames. */
+int ss2_canvas_minmax(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh2, int n, int img_h,
+                      int img_w, float* d_minmax, void* stream);
+/* The whole get_stable_sqe loop (AVERAGE fusion) for n frames, given the global canvas:
+ * hr1,hr2 [n,3,H,W] fp32 0..255; smooth meshes [n,7,9,2] @480x360; minmax[4] on the HOST.
+ * out [n,3,Ho,Wo] with Ho=(int)(ymax-ymin), Wo=(int)(xmax-xmin) (fp32 subtraction, then
+ * truncation, as test_online_tra.py:119-120,140). */
+int ss2_stable_frames(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, const float* d_mesh1,
+                      const float* d_mesh2, int n, int H, int W, const float* h_minmax, int mode,
+                      int tps, float* d_out, void* stream);
+/* canvas size helper (host arithmetic identical to the kernels') */
+int ss2_canvas_size(const float* h_minmax, int* out_h, int* out_w);
+
+/* ---- whole stream, device resident ------------------------------------------------------- */
+/* smooth meshes of a stream from per-window SmoothNet outputs (test_online_tra.py:378-392):
+ * d_win_smooth [nwin,7,7,9,2].  with_head != 0: first window contributes its 7 meshes, every
+ * later one its last (nwin+6 frames out); with_head == 0: only the last mesh of each window
+ * (nwin frames out) - the form a non-first rank of a temporally sharded stream needs. */
+int ss2_assemble_smooth(ss2_ctx* ctx, const float* d_win_smooth, int nwin, int with_head, float* d_out,
+                        void* stream);
+/* SpatialNet + TemporalNet x2 + tsmotion + SmoothNet windows for one stream of n >= 7 frames
+ * (test_online_tra.py:284-392): lr1,lr2 [n,3,360,480] -> smooth meshes [n,7,9,2] per view.
+ * Optional raw outputs (may be NULL): smotion, tmotion [n,7,9,2] per view. */
+int ss2_stream_meshes(ss2_ctx* ctx, const float* d_lr1, const float* d_lr2, int n, float* d_smooth1,
+                      float* d_smooth2, float* d_smotion1, float* d_smotion2, float* d_tmotion1,
+                      float* d_tmotion2, void* stream);
+
+/* ---- whole stream through HOST buffers (the e2e call) ------------------------------------ */
+/* One video chunk, everything the reference's test() does between frame loading and video
+ * writing (test_online_tra.py:284-399, AVERAGE fusion): H2D of the inputs, SpatialNet,
+ * TemporalNet x2, tsmotion, SmoothNet windows, canvas, resample+blend, D2H of the frames.
+ *   h_lr1,h_lr2 [n,3,360,480] in [-1,1];  h_hr1,h_hr2 [n,3,H,W] 0..255 (pinned memory advised)
+ *   h_out: capacity `out_capacity` floats; receives n frames [3,Ho,Wo]; *out_h,*out_w set.
+ *   h_smooth_mesh1/2 (optional, [n,7,9,2]) receive the smoothed meshes.
+ * Synchronous (returns after the D2H finished). */
+int ss2_stitch_stream_host(ss2_ctx* ctx, const float* h_lr1, const float* h_lr2, const float* h_hr1,
+                           const float* h_hr2, int n, int H, int W, int mode, int tps, float* h_out,
+                           int64_t out_capacity, int* out_h, int* out_w, float* h_smooth_mesh1,
+                           float* h_smooth_mesh2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SS2_H */

@@ -1,0 +1,144 @@
+"""ctypes binding of libss2.so (include/ss2.h).  There is NO fallback: if the CUDA library
+is missing or a call fails, this raises."""
+import ctypes
+import os
+import threading
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libss2.so")
+
+NET_SPATIAL, NET_TEMPORAL, NET_SMOOTH = 0, 1, 2
+MODE = {"NORMAL": 0, "FAST": 1}
+TPS_EXACT, TPS_LATTICE = 0, 1
+PROF_WARP, PROF_CONV = 0, 1
+
+_vp, _i, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+_fp = ctypes.POINTER(ctypes.c_float)
+
+# name -> (restype, argtypes); every symbol declared in include/ss2.h
+SIGNATURES = {
+    "ss2_create": (_i, [_i, ctypes.POINTER(_vp)]),
+    "ss2_destroy": (None, [_vp]),
+    "ss2_last_error": (ctypes.c_char_p, [_vp]),
+    "ss2_version": (ctypes.c_char_p, []),
+    "ss2_launch_count": (_i64, [_vp, _i]),
+    "ss2_profile_enable": (_i, [_vp, _i, _i]),
+    "ss2_profile_read": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double)]),
+    "ss2_load_tensor": (_i, [_vp, _i, ctypes.c_char_p, _vp, ctypes.POINTER(_i64), _i]),
+    "ss2_finalize_weights": (_i, [_vp, _i]),
+    "ss2_dlt": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "ss2_homo_warp": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ss2_tps_point": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "ss2_tps_warp": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ss2_tps_warp_blend_avg": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ss2_cost_volume_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ss2_ccl_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ss2_spatial_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ss2_build_spatial": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ss2_spatial_tail": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "ss2_build_temporal": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "ss2_tsmotion": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "ss2_build_smooth": (_i, [_vp] + [_vp] * 4 + [_i, _i] + [_vp] * 8 + [_vp]),
+    "ss2_canvas_minmax": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ss2_stable_frames": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _fp, _i, _i, _vp, _vp]),
+    "ss2_canvas_size": (_i, [_fp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "ss2_assemble_smooth": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "ss2_stream_meshes": (_i, [_vp, _vp, _vp, _i] + [_vp] * 6 + [_vp]),
+    "ss2_stitch_stream_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64,
+                                    ctypes.POINTER(_i), ctypes.POINTER(_i), _vp, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_contexts = {}
+
+
+class SS2Error(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libss2.so and declare every prototype.  Works without a GPU (no CUDA call)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise SS2Error("libss2.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(stabstitch2_b200 has no CPU/PyTorch fallback)")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+class Context:
+    """One ss2_ctx per CUDA device (per process)."""
+
+    def __init__(self, device):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise SS2Error("stabstitch2_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = int(device)
+        h = _vp()
+        rc = self.lib.ss2_create(self.device, ctypes.byref(h))
+        if rc != 0:
+            raise SS2Error("ss2_create(device=%d) failed with %d" % (self.device, rc))
+        self.handle = h
+
+    def check(self, rc):
+        if rc != 0:
+            raise SS2Error("libss2 error %d: %s" % (rc, self.lib.ss2_last_error(self.handle).decode()))
+
+    def launch_count(self, reset=False):
+        return int(self.lib.ss2_launch_count(self.handle, 1 if reset else 0))
+
+    def profile_enable(self, which, enable=True):
+        self.check(self.lib.ss2_profile_enable(self.handle, which, 1 if enable else 0))
+
+    def profile_read(self, which):
+        ms, n, work = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+        self.check(self.lib.ss2_profile_read(self.handle, which, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(work)))
+        return ms.value, n.value, work.value
+
+    def load_state_dict(self, net_id, sd):
+        for key, t in sd.items():
+            if not torch.is_tensor(t) or not t.dtype.is_floating_point:
+                continue  # num_batches_tracked etc.
+            h = t.detach().to("cpu", torch.float32).contiguous()
+            shape = (ctypes.c_int64 * max(h.dim(), 1))(*h.shape)
+            self.check(self.lib.ss2_load_tensor(self.handle, net_id, key.encode(), h.data_ptr(), shape, h.dim()))
+        self.check(self.lib.ss2_finalize_weights(self.handle, net_id))
+
+
+def context(device=None):
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if isinstance(device, torch.device):
+        device = device.index if device.index is not None else torch.cuda.current_device()
+    with _lock:
+        pass
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]
+
+
+def dev_f32(t, device=None):
+    """contiguous fp32 CUDA view/copy of `t` (the reference calls .cuda() on everything)."""
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def ptr(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def cur_stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)

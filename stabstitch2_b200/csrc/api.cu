@@ -1,0 +1,265 @@
+// C ABI entry points of libss2.so that are not network forwards (see include/ss2.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+int ss2_fail(ss2_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+int ss2_ensure_arena(ss2_ctx* ctx, size_t bytes) {
+  if (ctx->arena.cap >= bytes) return SS2_OK;
+  // growing is rare (first call / larger batch): drain the device, then replace the slab
+  SS2_CUDA(ctx, cudaDeviceSynchronize());
+  if (ctx->arena.base) SS2_CUDA(ctx, cudaFree(ctx->arena.base));
+  ctx->arena.base = nullptr;
+  ctx->arena.cap = 0;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return ss2_fail(ctx, SS2_ERR_OOM, "cudaMalloc(%zu) for the workspace arena: %s", bytes, cudaGetErrorString(e));
+  ctx->arena.base = (char*)p;
+  ctx->arena.cap = bytes;
+  ctx->arena.off = 0;
+  return SS2_OK;
+}
+
+void ss2_prof_begin(ss2_ctx* ctx, int which, cudaStream_t st) {
+  ProfClass& p = ctx->prof[which];
+  if (!p.enabled) return;
+  if (p.used + 2 > p.pool.size()) {
+    for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); p.pool.push_back(e); }
+  }
+  cudaEventRecord(p.pool[p.used], st);
+}
+
+void ss2_prof_end(ss2_ctx* ctx, int which, cudaStream_t st, double work) {
+  ProfClass& p = ctx->prof[which];
+  if (!p.enabled) return;
+  cudaEventRecord(p.pool[p.used + 1], st);
+  p.used += 2;
+  p.work += work;
+}
+
+extern "C" {
+
+int ss2_profile_enable(ss2_ctx* ctx, int which, int enable) {
+  if (!ctx || which < 0 || which >= SS2_PROF_COUNT) return SS2_ERR_INVALID;
+  ctx->prof[which].enabled = enable != 0;
+  ctx->prof[which].used = 0;
+  ctx->prof[which].work = 0.0;
+  return SS2_OK;
+}
+
+int ss2_profile_read(ss2_ctx* ctx, int which, double* total_ms, int64_t* launches, double* work) {
+  if (!ctx || which < 0 || which >= SS2_PROF_COUNT) return SS2_ERR_INVALID;
+  ProfClass& p = ctx->prof[which];
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < p.used; i += 2) {
+    SS2_CUDA(ctx, cudaEventSynchronize(p.pool[i + 1]));
+    float ms = 0.f;
+    SS2_CUDA(ctx, cudaEventElapsedTime(&ms, p.pool[i], p.pool[i + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int64_t)(p.used / 2);
+  if (work) *work = p.work;
+  return SS2_OK;
+}
+
+const char* ss2_version(void) { return "ss2 0.1 (sm_100a)"; }
+
+int ss2_create(int device, ss2_ctx** out) {
+  if (!out) return SS2_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SS2_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return SS2_ERR_CUDA;
+  ss2_ctx* c = new ss2_ctx();
+  c->device = device;
+  const char* env = getenv("SS2_USE_TC");
+  if (env) c->use_tc = atoi(env);
+  *out = c;
+  return SS2_OK;
+}
+
+void ss2_destroy(ss2_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (void* p : ctx->owned) cudaFree(p);
+  if (ctx->arena.base) cudaFree(ctx->arena.base);
+  for (auto& kv : ctx->stream_bufs) cudaFree(kv.second.first);
+  for (auto& pc : ctx->prof) for (cudaEvent_t e : pc.pool) cudaEventDestroy(e);
+  delete ctx;
+}
+
+const char* ss2_last_error(ss2_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int64_t ss2_launch_count(ss2_ctx* ctx, int reset) {
+  if (!ctx) return -1;
+  int64_t n = ctx->launches;
+  if (reset) ctx->launches = 0;
+  return n;
+}
+
+int ss2_load_tensor(ss2_ctx* ctx, int net_id, const char* key, const float* h_data, const int64_t* shape, int ndim) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (net_id < 0 || net_id > 2 || !key || !h_data || ndim < 0 || ndim > 8 || (ndim > 0 && !shape))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_load_tensor: bad arguments");
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t n = t.numel();
+  if (n < 0) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_load_tensor: negative extent in '%s'", key);
+  t.data.assign(h_data, h_data + n);
+  ctx->host_weights[net_id][key] = std::move(t);
+  return SS2_OK;
+}
+
+int ss2_dlt(ss2_ctx* ctx, const float* d_src, const float* d_dst, int bs, float* d_H, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (bs < 0 || (bs > 0 && (!d_src || !d_dst || !d_H))) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_dlt: bad arguments");
+  return dlt_launch(ctx, d_src, d_dst, bs, d_H, (cudaStream_t)stream);
+}
+
+int ss2_homo_warp(ss2_ctx* ctx, const float* d_U, const float* d_theta, int bn, int C, int H, int W, int Ho, int Wo,
+                  float* d_out, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (bn < 0 || C <= 0 || H <= 0 || W <= 0 || Ho < 0 || Wo < 0 || (bn > 0 && (!d_U || !d_theta || !d_out)))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_homo_warp: bad arguments");
+  return homo_warp_nchw_launch(ctx, d_U, d_theta, bn, C, H, W, Ho, Wo, d_out, (cudaStream_t)stream);
+}
+
+int ss2_tps_point(ss2_ctx* ctx, const float* d_point, const float* d_source, const float* d_target, int bn,
+                  float* d_out, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (bn < 0 || (bn > 0 && (!d_point || !d_source || !d_target || !d_out)))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_tps_point: bad arguments");
+  if (bn == 0) return SS2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* T = nullptr;
+  SS2_CUDA(ctx, cudaMallocAsync((void**)&T, (size_t)bn * 2 * SS2_NSYS * sizeof(float), st));
+  int rc = tps_solve_launch(ctx, d_source, d_target, bn, T, st);
+  if (rc == SS2_OK) rc = tps_point_launch(ctx, d_point, d_source, T, bn, d_out, st);
+  cudaFreeAsync(T, st);
+  return rc;
+}
+
+int ss2_tps_warp(ss2_ctx* ctx, const float* d_U, const float* d_source, const float* d_target, int bn, int C, int H,
+                 int W, int Ho, int Wo, int mode, int tps, float* d_out, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (bn < 0 || C <= 0 || H <= 0 || W <= 0 || Ho < 0 || Wo < 0 || (mode != SS2_MODE_NORMAL && mode != SS2_MODE_FAST) ||
+      (bn > 0 && (!d_U || !d_source || !d_target || (!d_out && Ho * Wo > 0))))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_tps_warp: bad arguments");
+  if (bn == 0 || Ho == 0 || Wo == 0) return SS2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* T = nullptr;
+  SS2_CUDA(ctx, cudaMallocAsync((void**)&T, (size_t)bn * 2 * SS2_NSYS * sizeof(float), st));
+  int rc = tps_solve_launch(ctx, d_source, d_target, bn, T, st);
+  if (rc == SS2_OK) rc = tps_warp_launch(ctx, d_U, d_source, T, bn, C, H, W, Ho, Wo, mode, tps, d_out, st);
+  cudaFreeAsync(T, st);
+  return rc;
+}
+
+int ss2_tps_warp_blend_avg(ss2_ctx* ctx, const float* d_img1, const float* d_img2, const float* d_source,
+                           const float* d_target, int nframes, int H, int W, int Ho, int Wo, int mode, int tps,
+                           float* d_out, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (nframes < 0 || H <= 0 || W <= 0 || Ho < 0 || Wo < 0 || (mode != SS2_MODE_NORMAL && mode != SS2_MODE_FAST) ||
+      (nframes > 0 && (!d_img1 || !d_img2 || !d_source || !d_target || (!d_out && Ho * Wo > 0))))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_tps_warp_blend_avg: bad arguments");
+  if (nframes == 0 || Ho == 0 || Wo == 0) return SS2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* T = nullptr;
+  SS2_CUDA(ctx, cudaMallocAsync((void**)&T, (size_t)nframes * 2 * 2 * SS2_NSYS * sizeof(float), st));
+  int rc = tps_solve_launch(ctx, d_source, d_target, 2 * nframes, T, st);
+  if (rc == SS2_OK) rc = tps_warp_blend_launch(ctx, d_img1, d_img2, d_source, T, nframes, H, W, Ho, Wo, mode, tps, d_out, st);
+  cudaFreeAsync(T, st);
+  return rc;
+}
+
+int ss2_cost_volume_nhwc(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B, int H, int W, int C, int sr, int CP,
+                         float* d_out, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (B < 0 || H <= 0 || W <= 0 || sr < 0 || (B > 0 && (!d_x1 || !d_x2 || !d_out)))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_cost_volume_nhwc: bad arguments");
+  return cost_volume_launch(ctx, d_x1, d_x2, B, H, W, C, sr, CP, d_out, (cudaStream_t)stream);
+}
+
+int ss2_ccl_nhwc(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H, int W, int C, float* d_flow,
+                 void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (B < 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || (B > 0 && (!d_f1 || !d_f2 || !d_flow)))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_ccl_nhwc: bad arguments (C must be a multiple of 4)");
+  const size_t hw = (size_t)H * W, kp = (hw + 63) / 64 * 64;
+  SS2_TRY(ss2_ensure_arena(ctx, (size_t)B * (2 * hw * C + 9 * C * kp + hw * hw) * sizeof(float) + (1 << 20)));
+  ctx->arena.reset();
+  return ccl_launch(ctx, d_f1, d_f2, B, H, W, C, d_flow, (cudaStream_t)stream);
+}
+
+int ss2_tsmotion(ss2_ctx* ctx, const float* d_smotion, const float* d_tmotion, int n, int first_is_stream_start,
+                 const float* d_smotion_prev, float* d_smesh, float* d_tsmotion, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!d_smotion || !d_tmotion || !d_smesh || !d_tsmotion)) ||
+      (n > 0 && !first_is_stream_start && !d_smotion_prev))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_tsmotion: bad arguments");
+  if (n == 0) return SS2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* buf = nullptr;
+  const size_t m = (size_t)n * SS2_NPT * 2;
+  SS2_CUDA(ctx, cudaMallocAsync((void**)&buf, (4 * m + (size_t)n * 2 * SS2_NSYS) * sizeof(float), st));
+  float *point = buf, *source = buf + m, *target = buf + 2 * m, *moved = buf + 3 * m, *T = buf + 4 * m;
+  int rc = tsmotion_prep_launch(ctx, d_smotion, d_tmotion, n, first_is_stream_start, d_smotion_prev, d_smesh, point,
+                                source, target, st);
+  if (rc == SS2_OK) rc = tps_solve_launch(ctx, source, target, n, T, st);
+  if (rc == SS2_OK) rc = tps_point_launch(ctx, point, source, T, n, moved, st);
+  if (rc == SS2_OK) rc = tsmotion_finish_launch(ctx, moved, d_smesh, n, first_is_stream_start, d_tsmotion, st);
+  cudaFreeAsync(buf, st);
+  return rc;
+}
+
+int ss2_canvas_minmax(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh2, int n, int img_h, int img_w,
+                      float* d_minmax, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (n <= 0 || !d_mesh1 || !d_mesh2 || !d_minmax) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_canvas_minmax: bad arguments");
+  return canvas_minmax_launch(ctx, d_mesh1, d_mesh2, n, img_h, img_w, d_minmax, (cudaStream_t)stream);
+}
+
+int ss2_canvas_size(const float* h_minmax, int* out_h, int* out_w) {
+  if (!h_minmax || !out_h || !out_w) return SS2_ERR_INVALID;
+  const float ow = h_minmax[1] - h_minmax[0], oh = h_minmax[3] - h_minmax[2];
+  *out_w = (int)ow;  // torch .int(): truncation
+  *out_h = (int)oh;
+  return SS2_OK;
+}
+
+int ss2_stable_frames(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, const float* d_mesh1, const float* d_mesh2,
+                      int n, int H, int W, const float* h_minmax, int mode, int tps, float* d_out, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (n < 0 || H <= 0 || W <= 0 || !h_minmax || (n > 0 && (!d_hr1 || !d_hr2 || !d_mesh1 || !d_mesh2)))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stable_frames: bad arguments");
+  int Ho, Wo;
+  ss2_canvas_size(h_minmax, &Ho, &Wo);
+  if (Ho < 0 || Wo < 0) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stable_frames: negative canvas");
+  if (n == 0 || Ho == 0 || Wo == 0) return SS2_OK;
+  if (!d_out) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stable_frames: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float out_w = h_minmax[1] - h_minmax[0], out_h = h_minmax[3] - h_minmax[2];
+  float* buf = nullptr;
+  const size_t m = (size_t)n * 2 * SS2_NPT * 2;
+  SS2_CUDA(ctx, cudaMallocAsync((void**)&buf, (2 * m + (size_t)n * 2 * 2 * SS2_NSYS) * sizeof(float), st));
+  float *source = buf, *target = buf + m, *T = buf + 2 * m;
+  int rc = stable_meshes_launch(ctx, d_mesh1, d_mesh2, n, H, W, h_minmax[0], h_minmax[2], out_w, out_h, source, target, st);
+  if (rc == SS2_OK) rc = tps_solve_launch(ctx, source, target, 2 * n, T, st);
+  if (rc == SS2_OK) rc = tps_warp_blend_launch(ctx, d_hr1, d_hr2, source, T, n, H, W, Ho, Wo, mode, tps, d_out, st);
+  cudaFreeAsync(buf, st);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// Shared declarations for libss2.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ss2.h"
+
+#define SS2_NPT_PAD 64
+#define SS2_NSYS 66  // 63 control points + affine part
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// One convolution / linear layer, packed for the implicit-GEMM kernels:
+//   w [K = KD*KH*KW*CinP][CoutP] (CoutP = Cout rounded up to 64), bias [CoutP]
+struct ConvLayer {
+  float* w = nullptr;
+  float* bias = nullptr;  // may be null
+  int Cin = 0, CinP = 0, Cout = 0, CoutP = 0;
+  int KD = 1, KH = 1, KW = 1;
+  int sd = 1, sh = 1, sw = 1;  // strides
+  int pd = 0, ph = 0, pw = 0;  // paddings
+  void* tmap = nullptr;        // device copy of the CUtensorMap of w (tcgen05 path)
+};
+
+struct ResBlock {
+  ConvLayer c1, c2, down;
+  bool has_down = false;
+};
+
+struct Backbone {  // ResNet-18 up to layer3
+  ConvLayer stem;
+  ResBlock l1[2], l2[2], l3[2];
+};
+
+struct Regressor {
+  std::vector<ConvLayer> convs;
+  std::vector<int> pool_after;  // 1 if a 2x2 max-pool follows conv i
+  ConvLayer fc[3];
+};
+
+struct SpatialWeights {
+  bool ready = false;
+  Backbone bb;
+  Regressor r1, r2_ref, r2_tgt;
+};
+struct TemporalWeights {
+  bool ready = false;
+  Backbone bb;
+  Regressor r2;
+};
+struct SmoothWeights {
+  bool ready = false;
+  float* emb1_w = nullptr;  // [32][2]
+  float* emb1_b = nullptr;
+  float* emb3_w = nullptr;
+  float* emb3_b = nullptr;
+  ConvLayer conv3d[3];
+  float* dec_w = nullptr;  // [4][128]
+  float* dec_b = nullptr;
+};
+
+// Bump allocator over one cudaMalloc'd slab; reset at the start of every entry point.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  void* alloc(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    if (a + bytes > cap) return nullptr;
+    off = a + bytes;
+    return base + a;
+  }
+  void reset() { off = 0; }
+};
+
+struct ProfClass {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;   // start/stop pairs
+  size_t used = 0;
+  double work = 0.0;               // bytes or flops, accumulated by the launcher
+};
+
+struct ss2_ctx {
+  int device = 0;
+  std::string err;
+  int64_t launches = 0;
+  std::map<std::string, HostTensor> host_weights[3];
+  std::vector<void*> owned;  // device allocations freed at destroy
+  SpatialWeights spatial;
+  TemporalWeights temporal;
+  SmoothWeights smooth;
+  Arena arena;
+  std::map<std::string, std::pair<void*, size_t>> stream_bufs;  // named persistent device buffers
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_hr = nullptr, ev_chunk[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  ProfClass prof[SS2_PROF_COUNT];
+  int use_tc = 1;  // tcgen05 implicit-GEMM path for eligible layers
+};
+
+int ss2_fail(ss2_ctx* ctx, int code, const char* fmt, ...);
+int ss2_ensure_arena(ss2_ctx* ctx, size_t bytes);
+// profiling brackets: no-ops unless the class is enabled
+void ss2_prof_begin(ss2_ctx* ctx, int which, cudaStream_t st);
+void ss2_prof_end(ss2_ctx* ctx, int which, cudaStream_t st, double work);
+
+#define SS2_CUDA(ctx, call)                                                              \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return ss2_fail(ctx, SS2_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,      \
+                      cudaGetErrorString(e__));                                          \
+  } while (0)
+
+#define SS2_LAUNCH_CHECK(ctx)                                                            \
+  do {                                                                                   \
+    (ctx)->launches++;                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess)                                                              \
+      return ss2_fail(ctx, SS2_ERR_CUDA, "%s:%d launch: %s", __FILE__, __LINE__,         \
+                      cudaGetErrorString(e__));                                          \
+  } while (0)
+
+#define SS2_TRY(expr)              \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != SS2_OK) return rc__; \
+  } while (0)
+
+template <typename T>
+static inline T* arena_alloc(ss2_ctx* ctx, size_t n) {
+  return reinterpret_cast<T*>(ctx->arena.alloc(n * sizeof(T)));
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- kernels' host launchers (defined in the .cu files) ------------------------------------
+// tps.cu
+int tps_solve_launch(ss2_ctx* ctx, const float* d_source, const float* d_target, int bn, float* d_T,
+                     cudaStream_t st);
+int tps_point_launch(ss2_ctx* ctx, const float* d_point, const float* d_source, const float* d_T, int bn,
+                     float* d_out, cudaStream_t st);
+int tps_warp_launch(ss2_ctx* ctx, const float* d_U, const float* d_source, const float* d_T, int bn, int C,
+                    int H, int W, int Ho, int Wo, int mode, int tps, float* d_out, cudaStream_t st);
+int tps_warp_blend_launch(ss2_ctx* ctx, const float* d_img1, const float* d_img2, const float* d_source,
+                          const float* d_T, int nframes, int H, int W, int Ho, int Wo, int mode, int tps,
+                          float* d_out, cudaStream_t st);
+// geom.cu
+int dlt_launch(ss2_ctx* ctx, const float* d_src, const float* d_dst, int bs, float* d_H, cudaStream_t st);
+int homo_warp_nchw_launch(ss2_ctx* ctx, const float* d_U, const float* d_theta, int bn, int C, int H, int W,
+                          int Ho, int Wo, float* d_out, cudaStream_t st);
+int homo_warp_nhwc_launch(ss2_ctx* ctx, const float* d_U, const float* d_theta, int bn, int C, int H, int W,
+                          float* d_out, cudaStream_t st);
+int spatial_split_launch(ss2_ctx* ctx, const float* d_offset1, int bs, int img_h, int img_w,
+                         float* d_theta_ref, float* d_theta_tgt, cudaStream_t st);
+int spatial_tail_launch(ss2_ctx* ctx, const float* d_o1, const float* d_oref, const float* d_otgt, int bs,
+                        int img_h, int img_w, float* d_m1, float* d_m2, cudaStream_t st);
+int tsmotion_prep_launch(ss2_ctx* ctx, const float* d_smotion, const float* d_tmotion, int n, int first,
+                         const float* d_prev, float* d_smesh, float* d_point, float* d_source,
+                         float* d_target, cudaStream_t st);
+int tsmotion_finish_launch(ss2_ctx* ctx, const float* d_moved, const float* d_smesh, int n, int first,
+                           float* d_tsmotion, cudaStream_t st);
+int canvas_minmax_launch(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh2, int n, int img_h,
+                         int img_w, float* d_minmax, cudaStream_t st);
+int stable_meshes_launch(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh2, int n, int img_h,
+                         int img_w, float xmin, float ymin, float out_w, float out_h, float* d_source,
+                         float* d_target, cudaStream_t st);
+// conv.cu
+int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_in, int B, int D, int H, int W, float* d_out,
+                const float* d_residual, int relu, cudaStream_t st, int groups = 1, size_t w_group_stride = 0);
+void conv_out_dims(const ConvLayer& L, int D, int H, int W, int* Do, int* Ho, int* Wo);
+int maxpool_launch(ss2_ctx* ctx, const float* d_in, int B, int H, int W, int C, int k, int s, int p,
+                   float* d_out, cudaStream_t st);
+int nchw_to_nhwc4_launch(ss2_ctx* ctx, const float* d_in, int B, int C, int H, int W, float* d_out,
+                         cudaStream_t st);
+// corr.cu
+int cost_volume_launch(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B, int H, int W, int C, int sr,
+                       int CP, float* d_out, cudaStream_t st);
+int ccl_launch(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H, int W, int C, float* d_flow,
+               cudaStream_t st);
+// smooth.cu
+int smooth_embed_launch(ss2_ctx* ctx, const SmoothWeights& sw, const float* ts1, const float* ts2,
+                        const float* sm1, const float* sm2, int nwin, int zero_first, float* d_hidden, float* d_path1,
+                        float* d_path2, cudaStream_t st);
+int smooth_decode_launch(ss2_ctx* ctx, const SmoothWeights& sw, const float* d_hidden, const float* sm1,
+                         const float* sm2, const float* path1, const float* path2, int nwin, float* op1,
+                         float* sp1, float* om1, float* smm1, float* op2, float* sp2, float* om2, float* smm2,
+                         cudaStream_t st);

@@ -1,0 +1,297 @@
+// Convolution family as implicit GEMM over NHWC / NDHWC activations (fp32 SIMT path).
+//
+//   out[m][n] = act( sum_k A[m][k] * Wp[k][n] + bias[n] + residual[m][n] )
+//   m = (b, do, ho, wo) output position, k = (kd, kh, kw, cin), n = cout
+//
+// One kernel covers every dense layer of the three networks (reference paths under
+// Full_model_inference/Codes/): the ResNet-18 stem / BasicBlocks (spatial_network.py:123-139,
+// eval-mode BN folded into Wp/bias at pack time), the regressor 3x3 stacks and their Linear
+// heads (spatial_network.py:147-259, temporal_network.py:65-104; a Linear is a 1x1 conv on a
+// 1x1 map), the CCL correlation (per-sample filters, `groups`) and SmoothNet's Conv3d
+// (smooth_network.py:124-131).  This is the exact-fp32 path; conv_tc.cu holds the tcgen05
+// tensor-core version used for the large layers.
+#include <algorithm>
+
+#include "common.cuh"
+
+void conv_out_dims(const ConvLayer& L, int D, int H, int W, int* Do, int* Ho, int* Wo) {
+  *Do = (D + 2 * L.pd - L.KD) / L.sd + 1;
+  *Ho = (H + 2 * L.ph - L.KH) / L.sh + 1;
+  *Wo = (W + 2 * L.pw - L.KW) / L.sw + 1;
+}
+
+struct ConvParams {
+  const float* in;
+  const float* w;
+  const float* bias;
+  const float* residual;
+  float* out;
+  int B, D, H, W, Cin;       // Cin = padded input channels (multiple of 4)
+  int Do, Ho, Wo, Cout, CoutP;
+  int KD, KH, KW, sd, sh, sw, pd, ph, pw;
+  int M, K;
+  int relu;
+  size_t in_group_stride, w_group_stride, out_group_stride;  // blockIdx.z = group
+};
+
+#define BK 16
+
+template <int BM, int BN>
+__global__ void __launch_bounds__(256)
+conv_igemm_kernel(ConvParams P) {
+  constexpr int TM = BM / 16, TN = BN / 16;
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const float* in = P.in + blockIdx.z * P.in_group_stride;
+  const float* wgt = P.w + blockIdx.z * P.w_group_stride;
+  float* out = P.out + blockIdx.z * P.out_group_stride;
+  const float* residual = P.residual ? P.residual + blockIdx.z * P.out_group_stride : nullptr;
+
+  // A loader: each thread owns rows (tid/4 + 64*i) and the 4-wide k group (tid%4)
+  constexpr int AROWS = BM / 64;
+  const int a_kg = tid % 4;
+  int a_b[AROWS], a_d[AROWS], a_h[AROWS], a_w[AROWS];
+  bool a_ok[AROWS];
+#pragma unroll
+  for (int i = 0; i < AROWS; ++i) {
+    int m = m0 + tid / 4 + 64 * i;
+    a_ok[i] = m < P.M;
+    int mm = a_ok[i] ? m : 0;
+    int wo = mm % P.Wo; mm /= P.Wo;
+    int ho = mm % P.Ho; mm /= P.Ho;
+    int d_o = mm % P.Do; mm /= P.Do;
+    a_b[i] = mm;
+    a_d[i] = d_o * P.sd - P.pd;
+    a_h[i] = ho * P.sh - P.ph;
+    a_w[i] = wo * P.sw - P.pw;
+  }
+  // B loader: BK x BN floats = BK*BN/4 float4; 256 threads
+  constexpr int BVEC = BK * BN / 4 / 256;  // float4 per thread
+  float4 a_reg[AROWS];
+  float4 b_reg[BVEC > 0 ? BVEC : 1];
+
+  auto load_tile = [&](int kt) {
+    const int k = kt * BK + a_kg * 4;
+    int tap = k / P.Cin, c = k - tap * P.Cin;
+    int kw = tap % P.KW; tap /= P.KW;
+    int kh = tap % P.KH; tap /= P.KH;
+    int kd = tap;
+#pragma unroll
+    for (int i = 0; i < AROWS; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int d = a_d[i] + kd, h = a_h[i] + kh, w = a_w[i] + kw;
+      if (a_ok[i] && k < P.K && (unsigned)d < (unsigned)P.D && (unsigned)h < (unsigned)P.H &&
+          (unsigned)w < (unsigned)P.W) {
+        const size_t off = ((((size_t)a_b[i] * P.D + d) * P.H + h) * P.W + w) * P.Cin + c;
+        v = __ldg(reinterpret_cast<const float4*>(in + off));
+      }
+      a_reg[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < BVEC; ++i) {
+      const int e = tid + i * 256;
+      const int kr = e / (BN / 4), nc = (e % (BN / 4)) * 4;
+      const int kk = kt * BK + kr;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kk < P.K) v = __ldg(reinterpret_cast<const float4*>(wgt + (size_t)kk * P.CoutP + n0 + nc));
+      b_reg[i] = v;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < AROWS; ++i) {
+      const int r = tid / 4 + 64 * i;
+      As[buf][a_kg * 4 + 0][r] = a_reg[i].x;
+      As[buf][a_kg * 4 + 1][r] = a_reg[i].y;
+      As[buf][a_kg * 4 + 2][r] = a_reg[i].z;
+      As[buf][a_kg * 4 + 3][r] = a_reg[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < BVEC; ++i) {
+      const int e = tid + i * 256;
+      const int kr = e / (BN / 4), nc = (e % (BN / 4)) * 4;
+      *reinterpret_cast<float4*>(&Bs[buf][kr][nc]) = b_reg[i];
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nkt = (P.K + BK - 1) / BK;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nkt) load_tile(kt + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + i]);
+        a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN + j]);
+        b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nkt) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  // epilogue: bias, residual, ReLU; NHWC store (row m, contiguous couts)
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= P.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; j += 4) {
+      const int n = n0 + tx * TN + j;
+      if (n >= P.Cout) continue;
+      float v[4] = {acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]};
+      if (P.bias) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += __ldg(P.bias + n + q);  // bias is CoutP long
+      }
+      float* o = out + (size_t)m * P.Cout + n;
+      if (n + 3 < P.Cout && (P.Cout & 3) == 0) {
+        if (residual) {
+          const float4 r = __ldg(reinterpret_cast<const float4*>(residual + (size_t)m * P.Cout + n));
+          v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+        }
+        if (P.relu) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = fmaxf(v[q], 0.f);
+        }
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (n + q < P.Cout) {
+            float x = v[q];
+            if (residual) x += residual[(size_t)m * P.Cout + n + q];
+            if (P.relu) x = fmaxf(x, 0.f);
+            o[q] = x;
+          }
+        }
+      }
+    }
+  }
+}
+
+int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_in, int B, int D, int H, int W, float* d_out,
+                   const float* d_residual, int relu, cudaStream_t st, bool* handled);
+
+int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_in, int B, int D, int H, int W, float* d_out,
+                const float* d_residual, int relu, cudaStream_t st, int groups, size_t w_group_stride) {
+  ConvParams P;
+  P.in = d_in; P.w = L.w; P.bias = L.bias; P.residual = d_residual; P.out = d_out;
+  P.B = B; P.D = D; P.H = H; P.W = W; P.Cin = L.CinP;
+  conv_out_dims(L, D, H, W, &P.Do, &P.Ho, &P.Wo);
+  P.Cout = L.Cout; P.CoutP = L.CoutP;
+  P.KD = L.KD; P.KH = L.KH; P.KW = L.KW;
+  P.sd = L.sd; P.sh = L.sh; P.sw = L.sw; P.pd = L.pd; P.ph = L.ph; P.pw = L.pw;
+  P.M = B * P.Do * P.Ho * P.Wo;
+  P.K = L.KD * L.KH * L.KW * L.CinP;
+  P.relu = relu;
+  P.in_group_stride = (size_t)B * D * H * W * L.CinP;
+  P.w_group_stride = w_group_stride;
+  P.out_group_stride = (size_t)P.M * L.Cout;
+  if (P.M <= 0) return SS2_OK;
+  if ((L.CinP & 3) || (L.CoutP & 63)) return ss2_fail(ctx, SS2_ERR_INVALID, "conv: unpadded layer");
+  if (groups == 1 && ctx->use_tc) {
+    bool handled = false;
+    SS2_TRY(conv_tc_launch(ctx, L, d_in, B, D, H, W, d_out, d_residual, relu, st, &handled));
+    if (handled) return SS2_OK;
+  }
+  ss2_prof_begin(ctx, SS2_PROF_CONV, st);
+  if (P.M >= 128 * 148) {
+    dim3 grid(cdiv(P.M, 128), L.CoutP / 64, groups);
+    conv_igemm_kernel<128, 64><<<grid, 256, 0, st>>>(P);
+  } else {
+    dim3 grid(cdiv(P.M, 64), L.CoutP / 64, groups);
+    conv_igemm_kernel<64, 64><<<grid, 256, 0, st>>>(P);
+  }
+  // algorithmic flops: 2 * M * Cout * (taps * real Cin)
+  ss2_prof_end(ctx, SS2_PROF_CONV, st, 2.0 * P.M * (double)L.Cout * L.KD * L.KH * L.KW * L.Cin * groups);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// max pooling, NHWC, float4 over channels (C % 4 == 0); floor mode, -inf padding
+// ------------------------------------------------------------------------------------------
+__global__ void maxpool_nhwc_kernel(const float4* __restrict__ in, int B, int H, int W, int C4, int k, int s, int p,
+                                    int Ho, int Wo, float4* __restrict__ out) {
+  const size_t total = (size_t)B * Ho * Wo * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t t = i;
+    const int c = t % C4; t /= C4;
+    const int wo = t % Wo; t /= Wo;
+    const int ho = t % Ho; t /= Ho;
+    const int b = (int)t;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dh = 0; dh < k; ++dh) {
+      const int h = ho * s - p + dh;
+      if ((unsigned)h >= (unsigned)H) continue;
+      for (int dw = 0; dw < k; ++dw) {
+        const int w = wo * s - p + dw;
+        if ((unsigned)w >= (unsigned)W) continue;
+        const float4 v = __ldg(in + (((size_t)b * H + h) * W + w) * C4 + c);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    out[i] = m;
+  }
+}
+
+int maxpool_launch(ss2_ctx* ctx, const float* d_in, int B, int H, int W, int C, int k, int s, int p,
+                   float* d_out, cudaStream_t st) {
+  const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  const size_t total = (size_t)B * Ho * Wo * (C / 4);
+  if (total == 0) return SS2_OK;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  maxpool_nhwc_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(d_in), B, H, W, C / 4, k, s, p, Ho,
+                                             Wo, reinterpret_cast<float4*>(d_out));
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+
+// NCHW (C <= 4) -> NHWC with 4 channels (zero padded): the network input layout change
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ in, int B, int C, int HW, float4* __restrict__ out) {
+  const size_t total = (size_t)B * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / HW, p = i % HW;
+    const float* src = in + b * C * HW + p;
+    float4 v;
+    v.x = __ldg(src);
+    v.y = C > 1 ? __ldg(src + HW) : 0.f;
+    v.z = C > 2 ? __ldg(src + 2 * (size_t)HW) : 0.f;
+    v.w = C > 3 ? __ldg(src + 3 * (size_t)HW) : 0.f;
+    out[i] = v;
+  }
+}
+
+int nchw_to_nhwc4_launch(ss2_ctx* ctx, const float* d_in, int B, int C, int H, int W, float* d_out,
+                         cudaStream_t st) {
+  const size_t total = (size_t)B * H * W;
+  if (total == 0) return SS2_OK;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  nchw_to_nhwc4_kernel<<<blocks, 256, 0, st>>>(d_in, B, C, H * W, reinterpret_cast<float4*>(d_out));
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}

@@ -1,0 +1,152 @@
+// Correlation layers: the local cost volume (warp-shuffle channel reduction) and the global
+// contextual correlation layer (CCL) of SpatialNet.
+//
+// Reference behaviour restated (paths under Full_model_inference/Codes/):
+//   spatial_network.py:333-358 / temporal_network.py:149-174   cost_volume (norm=False)
+//   spatial_network.py:369-425                                 CCL
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// cost volume: cv[d] = leaky_relu_0.1( mean_c x1[c] * x2[c, y+j-sr, x+i-sr] ), d = j*(2sr+1)+i
+// NHWC, C = 128 (one float4 per lane).  One warp per output pixel: x1's channel vector stays
+// in registers, each displacement is one coalesced 512 B read of x2, 4 FMAs and a 5-step
+// butterfly; lane (d mod 32) keeps result d so the stores are coalesced 128 B rows.
+// Output has CP channels (>= (2sr+1)^2, zero filled) so the next conv sees a padded Cin.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cost_volume_kernel(const float4* __restrict__ x1, const float4* __restrict__ x2, int H, int W, int C4, int sr, int CP,
+                   float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * 8 + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (pix >= H * W) return;
+  const int y = pix / W, x = pix % W;
+  const size_t img = (size_t)b * H * W;
+  const bool act = lane < C4;  // C <= 128: one float4 per lane
+  const float4 a = act ? __ldg(x1 + (img + pix) * C4 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float inv_c = 1.0f / (float)(4 * C4);
+  const int k = 2 * sr + 1, nd = k * k;
+  float* o = out + (img + pix) * CP;
+  for (int d0 = 0; d0 < CP; d0 += 32) {
+    float keep = 0.f;
+    for (int dd = 0; dd < 32; ++dd) {
+      const int d = d0 + dd;
+      if (d >= nd) break;
+      const int j = d / k, i = d % k;
+      const int y2 = y + j - sr, x2c = x + i - sr;
+      float s = 0.f;
+      if ((unsigned)y2 < (unsigned)H && (unsigned)x2c < (unsigned)W) {  // warp-uniform branch
+        const float4 v = act ? __ldg(x2 + (img + (size_t)y2 * W + x2c) * C4 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s = fmaf(a.w, v.w, fmaf(a.z, v.z, fmaf(a.y, v.y, a.x * v.x)));
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+        s *= inv_c;
+        s = s > 0.f ? s : 0.1f * s;
+      }
+      if (lane == dd) keep = s;
+    }
+    if (d0 + lane < CP) o[d0 + lane] = keep;
+  }
+}
+
+int cost_volume_launch(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B, int H, int W, int C, int sr,
+                       int CP, float* d_out, cudaStream_t st) {
+  if (C <= 0 || C > 128 || (C & 3)) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "cost_volume: C must be a multiple of 4, <= 128 (got %d)", C);
+  if ((2 * sr + 1) * (2 * sr + 1) > CP || (CP & 31)) return ss2_fail(ctx, SS2_ERR_INVALID, "cost_volume: CP must be a multiple of 32 and >= (2sr+1)^2");
+  if (B <= 0) return SS2_OK;
+  dim3 grid(cdiv(H * W, 8), B);
+  cost_volume_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(d_x1),
+                                          reinterpret_cast<const float4*>(d_x2), H, W, C / 4, sr, CP, d_out);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// CCL
+//   1. L2-normalise both feature maps over C (F.normalize, eps 1e-12)
+//   2. every 3x3 patch of n2 becomes a correlation filter: Wp[b][(tap,c)][k], k = h2*W + w2
+//   3. match[b][p][k] = conv3x3(n1[b], Wp[b])           -> the implicit-GEMM conv kernel
+//   4. softmax_k(10*match) expectation of (k%W - w, k//W - h) -> flow (flow_w, flow_h, 0, 0)
+// ------------------------------------------------------------------------------------------
+__global__ void l2norm_nhwc_kernel(const float* __restrict__ in, int npix, int C, float* __restrict__ out) {
+  const int pix = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (pix >= npix) return;
+  const float* p = in + (size_t)pix * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) { const float v = p[c]; s = fmaf(v, v, s); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  for (int c = lane; c < C; c += 32) out[(size_t)pix * C + c] = p[c] * inv;
+}
+
+__global__ void ccl_filters_kernel(const float* __restrict__ n2, int H, int W, int C, int KP,
+                                   float* __restrict__ Wp) {
+  // grid: (cdiv(KP,128), 9*C, B) ; thread -> k
+  const int b = blockIdx.z, row = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= KP) return;
+  const int tap = row / C, c = row % C;
+  const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+  float v = 0.f;
+  if (k < H * W) {
+    const int h = k / W + dy, w = k % W + dx;
+    if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) v = __ldg(n2 + (((size_t)b * H + h) * W + w) * C + c);
+  }
+  Wp[((size_t)b * 9 * C + row) * KP + k] = v;
+}
+
+__global__ void ccl_softmax_flow_kernel(const float* __restrict__ match, int H, int W, float4* __restrict__ flow) {
+  const int HW = H * W;
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (pix >= HW) return;
+  const float* m = match + ((size_t)b * HW + pix) * HW;
+  float mx = -INFINITY;
+  for (int k = lane; k < HW; k += 32) mx = fmaxf(mx, m[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float ph = (float)(pix / W), pw = (float)(pix % W);
+  float se = 0.f, sh = 0.f, sw = 0.f;
+  for (int k = lane; k < HW; k += 32) {
+    const float e = expf(10.0f * m[k] - 10.0f * mx);
+    se += e;
+    sh = fmaf(e, (float)(k / W) - ph, sh);
+    sw = fmaf(e, (float)(k % W) - pw, sw);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    se += __shfl_xor_sync(0xffffffffu, se, o);
+    sh += __shfl_xor_sync(0xffffffffu, sh, o);
+    sw += __shfl_xor_sync(0xffffffffu, sw, o);
+  }
+  if (lane == 0) flow[(size_t)b * HW + pix] = make_float4(sw / se, sh / se, 0.f, 0.f);
+}
+
+int ccl_launch(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H, int W, int C, float* d_flow,
+               cudaStream_t st) {
+  if (B <= 0) return SS2_OK;
+  const int HW = H * W;
+  const int KP = (HW + 63) / 64 * 64;
+  float* n1 = arena_alloc<float>(ctx, (size_t)B * HW * C);
+  float* n2 = arena_alloc<float>(ctx, (size_t)B * HW * C);
+  float* Wp = arena_alloc<float>(ctx, (size_t)B * 9 * C * KP);
+  float* match = arena_alloc<float>(ctx, (size_t)B * HW * HW);
+  if (!n1 || !n2 || !Wp || !match) return ss2_fail(ctx, SS2_ERR_OOM, "ccl: workspace arena exhausted");
+  l2norm_nhwc_kernel<<<cdiv(B * HW, 8), 256, 0, st>>>(d_f1, B * HW, C, n1);
+  SS2_LAUNCH_CHECK(ctx);
+  l2norm_nhwc_kernel<<<cdiv(B * HW, 8), 256, 0, st>>>(d_f2, B * HW, C, n2);
+  SS2_LAUNCH_CHECK(ctx);
+  ccl_filters_kernel<<<dim3(cdiv(KP, 128), 9 * C, B), 128, 0, st>>>(n2, H, W, C, KP, Wp);
+  SS2_LAUNCH_CHECK(ctx);
+  ConvLayer L;
+  L.w = Wp; L.bias = nullptr;
+  L.Cin = L.CinP = C; L.Cout = HW; L.CoutP = KP;
+  L.KH = L.KW = 3; L.ph = L.pw = 1;
+  SS2_TRY(conv_launch(ctx, L, n1, 1, 1, H, W, match, nullptr, 0, st, B, (size_t)9 * C * KP));
+  ccl_softmax_flow_kernel<<<dim3(cdiv(HW, 8), B), 256, 0, st>>>(match, H, W, reinterpret_cast<float4*>(d_flow));
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}

@@ -1,0 +1,410 @@
+// Weight packing (state-dict -> kernel layouts, eval-mode BatchNorm folded) and the forward
+// graphs of SpatialNet, TemporalNet and SmoothNet.
+//
+// Reference behaviour restated (paths under Full_model_inference/Codes/):
+//   spatial_network.py:144-331   SpatialNet.__init__/forward
+//   temporal_network.py:62-147   TemporalNet.__init__/forward
+//   smooth_network.py:44-157     SmoothNet / MotionPrediction
+// State-dict key names: SURVEY.md Appendix B (verified by strict load into the reference).
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// packing
+// ------------------------------------------------------------------------------------------
+static const HostTensor* find(ss2_ctx* ctx, int net, const std::string& key) {
+  auto it = ctx->host_weights[net].find(key);
+  return it == ctx->host_weights[net].end() ? nullptr : &it->second;
+}
+
+static int upload(ss2_ctx* ctx, const std::vector<float>& h, float** d) {
+  void* p = nullptr;
+  SS2_CUDA(ctx, cudaMalloc(&p, h.size() * sizeof(float)));
+  ctx->owned.push_back(p);
+  SS2_CUDA(ctx, cudaMemcpy(p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *d = (float*)p;
+  return SS2_OK;
+}
+
+int conv_tc_prepare(ss2_ctx* ctx, ConvLayer& L);
+
+// conv weight [Cout,Cin,(KD,)KH,KW] (+ optional BN prefix, + optional bias key) -> ConvLayer.
+// `flatten_hw` > 0 packs a Linear that consumes an NCHW-flattened [C, flatten_hw] map whose
+// activations we hold as NHWC: input index (p*C + c) <- reference column (c*flatten_hw + p).
+static int pack_conv(ss2_ctx* ctx, int net, const std::string& wkey, const std::string& bnpfx,
+                     const std::string& bkey, int stride, int pad, int pad_d, int flatten_hw, ConvLayer* L) {
+  const HostTensor* w = find(ctx, net, wkey);
+  if (!w) return ss2_fail(ctx, SS2_ERR_MISSING_KEY, "missing state-dict key '%s'", wkey.c_str());
+  const int nd = (int)w->shape.size();
+  if (nd != 2 && nd != 4 && nd != 5) return ss2_fail(ctx, SS2_ERR_INVALID, "'%s': unexpected rank %d", wkey.c_str(), nd);
+  const int Cout = (int)w->shape[0];
+  int Cin = (int)w->shape[1];
+  int KD = 1, KH = 1, KW = 1;
+  if (nd == 4) { KH = (int)w->shape[2]; KW = (int)w->shape[3]; }
+  if (nd == 5) { KD = (int)w->shape[2]; KH = (int)w->shape[3]; KW = (int)w->shape[4]; }
+  std::vector<double> scale(Cout, 1.0), shift(Cout, 0.0);
+  bool has_bias = false;
+  if (!bnpfx.empty()) {
+    const HostTensor *g = find(ctx, net, bnpfx + ".weight"), *b = find(ctx, net, bnpfx + ".bias"),
+                     *m = find(ctx, net, bnpfx + ".running_mean"), *v = find(ctx, net, bnpfx + ".running_var");
+    if (!g || !b || !m || !v)
+      return ss2_fail(ctx, SS2_ERR_MISSING_KEY, "missing BatchNorm tensors under '%s'", bnpfx.c_str());
+    for (int o = 0; o < Cout; ++o) {
+      // F.batch_norm(eval): (x - mean) / sqrt(var + eps) * gamma + beta, eps = 1e-5
+      const double s = (double)g->data[o] / sqrt((double)v->data[o] + 1e-5);
+      scale[o] = s;
+      shift[o] = (double)b->data[o] - (double)m->data[o] * s;
+    }
+    has_bias = true;
+  }
+  if (!bkey.empty()) {
+    const HostTensor* b = find(ctx, net, bkey);
+    if (!b) return ss2_fail(ctx, SS2_ERR_MISSING_KEY, "missing state-dict key '%s'", bkey.c_str());
+    for (int o = 0; o < Cout; ++o) shift[o] += (double)b->data[o];
+    has_bias = true;
+  }
+  L->Cin = Cin; L->Cout = Cout;
+  L->CinP = (Cin + 3) / 4 * 4;
+  // channel-padded producers: cost volumes are emitted with 128 / 64 channels
+  if (Cin == 121) L->CinP = 128;
+  if (Cin == 49) L->CinP = 64;
+  L->CoutP = (Cout + 63) / 64 * 64;
+  L->KD = KD; L->KH = KH; L->KW = KW;
+  L->sd = 1; L->sh = L->sw = stride;
+  L->pd = pad_d; L->ph = L->pw = pad;
+  const int taps = KD * KH * KW;
+  std::vector<float> wp((size_t)taps * L->CinP * L->CoutP, 0.f);
+  for (int o = 0; o < Cout; ++o)
+    for (int c = 0; c < Cin; ++c)
+      for (int t = 0; t < taps; ++t) {
+        const double v = (double)w->data[((size_t)o * Cin + c) * taps + t] * scale[o];
+        size_t krow;
+        if (flatten_hw > 0) {
+          const int ch = c / flatten_hw, p = c % flatten_hw;  // reference column c = ch*hw + p
+          krow = (size_t)p * (Cin / flatten_hw) + ch;
+        } else {
+          krow = (size_t)t * L->CinP + c;
+        }
+        wp[krow * L->CoutP + o] = (float)v;
+      }
+  SS2_TRY(upload(ctx, wp, &L->w));
+  L->bias = nullptr;
+  if (has_bias) {
+    std::vector<float> bp(L->CoutP, 0.f);
+    for (int o = 0; o < Cout; ++o) bp[o] = (float)shift[o];
+    SS2_TRY(upload(ctx, bp, &L->bias));
+  }
+  return conv_tc_prepare(ctx, *L);
+}
+
+static int pack_block(ss2_ctx* ctx, int net, const std::string& pfx, int stride, ResBlock* b) {
+  SS2_TRY(pack_conv(ctx, net, pfx + ".conv1.weight", pfx + ".bn1", "", stride, 1, 0, 0, &b->c1));
+  SS2_TRY(pack_conv(ctx, net, pfx + ".conv2.weight", pfx + ".bn2", "", 1, 1, 0, 0, &b->c2));
+  b->has_down = find(ctx, net, pfx + ".downsample.0.weight") != nullptr;
+  if (b->has_down)
+    SS2_TRY(pack_conv(ctx, net, pfx + ".downsample.0.weight", pfx + ".downsample.1", "", stride, 0, 0, 0, &b->down));
+  return SS2_OK;
+}
+
+static int pack_backbone(ss2_ctx* ctx, int net, bool with_stage2, Backbone* bb) {
+  const std::string p1 = "feature_extractor_stage1", p2 = "feature_extractor_stage2";
+  SS2_TRY(pack_conv(ctx, net, p1 + ".0.weight", p1 + ".1", "", 2, 3, 0, 0, &bb->stem));
+  SS2_TRY(pack_block(ctx, net, p1 + ".4.0", 1, &bb->l1[0]));
+  SS2_TRY(pack_block(ctx, net, p1 + ".4.1", 1, &bb->l1[1]));
+  SS2_TRY(pack_block(ctx, net, p1 + ".5.0", 2, &bb->l2[0]));
+  SS2_TRY(pack_block(ctx, net, p1 + ".5.1", 1, &bb->l2[1]));
+  if (with_stage2) {
+    SS2_TRY(pack_block(ctx, net, p2 + ".0.0", 2, &bb->l3[0]));
+    SS2_TRY(pack_block(ctx, net, p2 + ".0.1", 1, &bb->l3[1]));
+  }
+  return SS2_OK;
+}
+
+static int pack_regressor(ss2_ctx* ctx, int net, const std::string& part1, const std::string& part2, int nconv,
+                          int final_hw, Regressor* r) {
+  static const int ids6[] = {0, 2, 5, 7, 10, 12}, ids8[] = {0, 2, 5, 7, 10, 12, 15, 17};
+  const int* ids = nconv == 6 ? ids6 : ids8;
+  r->convs.resize(nconv);
+  r->pool_after.assign(nconv, 0);
+  for (int i = 0; i < nconv; ++i) {
+    SS2_TRY(pack_conv(ctx, net, part1 + "." + std::to_string(ids[i]) + ".weight", "", "", 1, 1, 0, 0, &r->convs[i]));
+    r->pool_after[i] = (i % 2 == 1);
+  }
+  SS2_TRY(pack_conv(ctx, net, part2 + ".0.weight", "", part2 + ".0.bias", 1, 0, 0, final_hw, &r->fc[0]));
+  SS2_TRY(pack_conv(ctx, net, part2 + ".2.weight", "", part2 + ".2.bias", 1, 0, 0, 0, &r->fc[1]));
+  SS2_TRY(pack_conv(ctx, net, part2 + ".4.weight", "", part2 + ".4.bias", 1, 0, 0, 0, &r->fc[2]));
+  return SS2_OK;
+}
+
+static int upload_key(ss2_ctx* ctx, int net, const std::string& key, float** d) {
+  const HostTensor* t = find(ctx, net, key);
+  if (!t) return ss2_fail(ctx, SS2_ERR_MISSING_KEY, "missing state-dict key '%s'", key.c_str());
+  return upload(ctx, t->data, d);
+}
+
+extern "C" int ss2_finalize_weights(ss2_ctx* ctx, int net_id) {
+  if (!ctx) return SS2_ERR_INVALID;
+  SS2_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (net_id == SS2_NET_SPATIAL) {
+    SpatialWeights& s = ctx->spatial;
+    s.ready = false;
+    SS2_TRY(pack_backbone(ctx, net_id, true, &s.bb));
+    SS2_TRY(pack_regressor(ctx, net_id, "regressNet1_part1", "regressNet1_part2", 6, 2 * 3, &s.r1));
+    SS2_TRY(pack_regressor(ctx, net_id, "regressNet2_part1_ref", "regressNet2_part2_ref", 8, 2 * 3, &s.r2_ref));
+    SS2_TRY(pack_regressor(ctx, net_id, "regressNet2_part1_tgt", "regressNet2_part2_tgt", 8, 2 * 3, &s.r2_tgt));
+    s.ready = true;
+  } else if (net_id == SS2_NET_TEMPORAL) {
+    TemporalWeights& t = ctx->temporal;
+    t.ready = false;
+    SS2_TRY(pack_backbone(ctx, net_id, false, &t.bb));  // stage2 is in the checkpoint but unused
+    SS2_TRY(pack_regressor(ctx, net_id, "regressNet2_part1", "regressNet2_part2", 8, 2 * 3, &t.r2));
+    t.ready = true;
+  } else if (net_id == SS2_NET_SMOOTH) {
+    SmoothWeights& m = ctx->smooth;
+    m.ready = false;
+    const std::string p = "MotionPre.";
+    SS2_TRY(upload_key(ctx, net_id, p + "embedding1.0.weight", &m.emb1_w));
+    SS2_TRY(upload_key(ctx, net_id, p + "embedding1.0.bias", &m.emb1_b));
+    SS2_TRY(upload_key(ctx, net_id, p + "embedding3.0.weight", &m.emb3_w));
+    SS2_TRY(upload_key(ctx, net_id, p + "embedding3.0.bias", &m.emb3_b));
+    for (int i = 0; i < 3; ++i) {
+      const std::string k = p + "MotionConv3D." + std::to_string(2 * i);
+      SS2_TRY(pack_conv(ctx, net_id, k + ".weight", "", k + ".bias", 1, 1, 2, 0, &m.conv3d[i]));
+    }
+    SS2_TRY(upload_key(ctx, net_id, p + "decoding.0.weight", &m.dec_w));
+    SS2_TRY(upload_key(ctx, net_id, p + "decoding.0.bias", &m.dec_b));
+    m.ready = true;
+  } else {
+    return ss2_fail(ctx, SS2_ERR_INVALID, "unknown net id %d", net_id);
+  }
+  ctx->host_weights[net_id].clear();
+  SS2_CUDA(ctx, cudaDeviceSynchronize());
+  return SS2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward graphs.  Activations are NHWC fp32 carved from the context arena.
+// ------------------------------------------------------------------------------------------
+#define ARENA(ptr, T, n)                                                                        \
+  T* ptr = arena_alloc<T>(ctx, (size_t)(n));                                                    \
+  if (!ptr) return ss2_fail(ctx, SS2_ERR_OOM, "workspace arena exhausted at %s:%d", __FILE__, __LINE__)
+
+static int run_block(ss2_ctx* ctx, const ResBlock& b, const float* x, int NB, int H, int W, float** out, int* Ho,
+                     int* Wo, cudaStream_t st) {
+  int d, h, w;
+  conv_out_dims(b.c1, 1, H, W, &d, &h, &w);
+  ARENA(t1, float, (size_t)NB * h * w * b.c1.Cout);
+  SS2_TRY(conv_launch(ctx, b.c1, x, NB, 1, H, W, t1, nullptr, 1, st));
+  const float* idt = x;
+  if (b.has_down) {
+    ARENA(t2, float, (size_t)NB * h * w * b.down.Cout);
+    SS2_TRY(conv_launch(ctx, b.down, x, NB, 1, H, W, t2, nullptr, 0, st));
+    idt = t2;
+  }
+  ARENA(t3, float, (size_t)NB * h * w * b.c2.Cout);
+  SS2_TRY(conv_launch(ctx, b.c2, t1, NB, 1, h, w, t3, idt, 1, st));
+  *out = t3; *Ho = h; *Wo = w;
+  return SS2_OK;
+}
+
+// x: NCHW [NB,3,H,W] -> f64 [NB,H/8,W/8,128] (and f32 [NB,.,.,256] when stage2)
+static int run_backbone(ss2_ctx* ctx, const Backbone& bb, const float* x_nchw, int NB, int H, int W, bool stage2,
+                        float** f64, int* h64, int* w64, float** f32, int* h32, int* w32, cudaStream_t st) {
+  ARENA(x, float, (size_t)NB * H * W * 4);
+  SS2_TRY(nchw_to_nhwc4_launch(ctx, x_nchw, NB, 3, H, W, x, st));
+  int d, h, w;
+  conv_out_dims(bb.stem, 1, H, W, &d, &h, &w);
+  ARENA(s, float, (size_t)NB * h * w * 64);
+  SS2_TRY(conv_launch(ctx, bb.stem, x, NB, 1, H, W, s, nullptr, 1, st));
+  const int hp = (h + 2 - 3) / 2 + 1, wp = (w + 2 - 3) / 2 + 1;
+  ARENA(p, float, (size_t)NB * hp * wp * 64);
+  SS2_TRY(maxpool_launch(ctx, s, NB, h, w, 64, 3, 2, 1, p, st));
+  float* cur = p;
+  h = hp; w = wp;
+  SS2_TRY(run_block(ctx, bb.l1[0], cur, NB, h, w, &cur, &h, &w, st));
+  SS2_TRY(run_block(ctx, bb.l1[1], cur, NB, h, w, &cur, &h, &w, st));
+  SS2_TRY(run_block(ctx, bb.l2[0], cur, NB, h, w, &cur, &h, &w, st));
+  SS2_TRY(run_block(ctx, bb.l2[1], cur, NB, h, w, &cur, &h, &w, st));
+  *f64 = cur; *h64 = h; *w64 = w;
+  if (stage2) {
+    SS2_TRY(run_block(ctx, bb.l3[0], cur, NB, h, w, &cur, &h, &w, st));
+    SS2_TRY(run_block(ctx, bb.l3[1], cur, NB, h, w, &cur, &h, &w, st));
+    *f32 = cur; *h32 = h; *w32 = w;
+  }
+  return SS2_OK;
+}
+
+// x [NB,H,W,CinP] -> out [NB, fc[2].Cout]
+static int run_regressor(ss2_ctx* ctx, const Regressor& r, const float* x, int NB, int H, int W, float* out,
+                         cudaStream_t st) {
+  const float* cur = x;
+  int h = H, w = W;
+  for (size_t i = 0; i < r.convs.size(); ++i) {
+    const ConvLayer& L = r.convs[i];
+    ARENA(t, float, (size_t)NB * h * w * L.Cout);
+    SS2_TRY(conv_launch(ctx, L, cur, NB, 1, h, w, t, nullptr, 1, st));
+    cur = t;
+    if (r.pool_after[i]) {
+      const int hp = h / 2, wp = w / 2;
+      ARENA(q, float, (size_t)NB * hp * wp * L.Cout);
+      SS2_TRY(maxpool_launch(ctx, cur, NB, h, w, L.Cout, 2, 2, 0, q, st));
+      cur = q; h = hp; w = wp;
+    }
+  }
+  const int feat = h * w * r.convs.back().Cout;
+  if (feat != r.fc[0].Cin) return ss2_fail(ctx, SS2_ERR_INVALID, "regressor: %d features, Linear expects %d", feat, r.fc[0].Cin);
+  ARENA(a, float, (size_t)NB * r.fc[0].Cout);
+  SS2_TRY(conv_launch(ctx, r.fc[0], cur, NB, 1, 1, 1, a, nullptr, 1, st));
+  ARENA(b, float, (size_t)NB * r.fc[1].Cout);
+  SS2_TRY(conv_launch(ctx, r.fc[1], a, NB, 1, 1, 1, b, nullptr, 1, st));
+  SS2_TRY(conv_launch(ctx, r.fc[2], b, NB, 1, 1, 1, out, nullptr, 0, st));
+  return SS2_OK;
+}
+
+#define NET_IMG_H 360
+#define NET_IMG_W 480
+static const size_t kBytesPerImageBackbone = (size_t)48 << 20;   // generous bound, see DESIGN.md
+static const size_t kBytesPerPairHead = (size_t)40 << 20;
+
+static int spatial_chunk(ss2_ctx* ctx, const float* img1, const float* img2, int bs, int H, int W, float* o1,
+                         float* oref, float* otgt, cudaStream_t st) {
+  const SpatialWeights& S = ctx->spatial;
+  ctx->arena.reset();
+  // both views through the shared backbone as one batch of 2*bs images: [view1 | view2]
+  ARENA(both, float, (size_t)2 * bs * 3 * H * W);
+  SS2_CUDA(ctx, cudaMemcpyAsync(both, img1, (size_t)bs * 3 * H * W * 4, cudaMemcpyDeviceToDevice, st));
+  SS2_CUDA(ctx, cudaMemcpyAsync(both + (size_t)bs * 3 * H * W, img2, (size_t)bs * 3 * H * W * 4,
+                                cudaMemcpyDeviceToDevice, st));
+  float *f64, *f32;
+  int h64, w64, h32, w32;
+  SS2_TRY(run_backbone(ctx, S.bb, both, 2 * bs, H, W, true, &f64, &h64, &w64, &f32, &h32, &w32, st));
+  // stage 1: global correlation -> 4-point offsets
+  ARENA(flow, float, (size_t)bs * h32 * w32 * 4);
+  SS2_TRY(ccl_launch(ctx, f32, f32 + (size_t)bs * h32 * w32 * 256, bs, h32, w32, 256, flow, st));
+  SS2_TRY(run_regressor(ctx, S.r1, flow, bs, h32, w32, o1, st));
+  // homography split on the middle plane, warp both 1/8-scale feature maps
+  ARENA(theta, float, (size_t)2 * bs * 9);
+  SS2_TRY(spatial_split_launch(ctx, o1, bs, H, W, theta, theta + (size_t)bs * 9, st));
+  ARENA(warped, float, (size_t)2 * bs * h64 * w64 * 128);
+  SS2_TRY(homo_warp_nhwc_launch(ctx, f64, theta, 2 * bs, 128, h64, w64, warped, st));
+  // stage 2: two local cost volumes -> two mesh regressors
+  const size_t half = (size_t)bs * h64 * w64 * 128;
+  ARENA(cv, float, 2 * half);
+  SS2_TRY(cost_volume_launch(ctx, warped, warped + half, bs, h64, w64, 128, 5, 128, cv, st));
+  SS2_TRY(cost_volume_launch(ctx, warped + half, warped, bs, h64, w64, 128, 5, 128, cv + half, st));
+  SS2_TRY(run_regressor(ctx, S.r2_ref, cv, bs, h64, w64, oref, st));
+  SS2_TRY(run_regressor(ctx, S.r2_tgt, cv + half, bs, h64, w64, otgt, st));
+  return SS2_OK;
+}
+
+#define SPATIAL_CHUNK 16
+#define TEMPORAL_CHUNK 32
+#define SMOOTH_CHUNK 256
+
+extern "C" int ss2_spatial_forward(ss2_ctx* ctx, const float* d_img1, const float* d_img2, int bs,
+                                   float* d_offset1, float* d_offset2_ref, float* d_offset2_tgt, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (!ctx->spatial.ready) return ss2_fail(ctx, SS2_ERR_NO_WEIGHTS, "SpatialNet weights not finalized");
+  if (bs < 0 || (bs > 0 && (!d_img1 || !d_img2 || !d_offset1 || !d_offset2_ref || !d_offset2_tgt)))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_spatial_forward: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = NET_IMG_H, W = NET_IMG_W;
+  const int chunk = bs < SPATIAL_CHUNK ? bs : SPATIAL_CHUNK;
+  SS2_TRY(ss2_ensure_arena(ctx, (size_t)chunk * (2 * kBytesPerImageBackbone + kBytesPerPairHead) + ((size_t)64 << 20)));
+  for (int b0 = 0; b0 < bs; b0 += chunk) {
+    const int nb = bs - b0 < chunk ? bs - b0 : chunk;
+    const size_t io = (size_t)b0 * 3 * H * W;
+    SS2_TRY(spatial_chunk(ctx, d_img1 + io, d_img2 + io, nb, H, W, d_offset1 + (size_t)b0 * 8,
+                          d_offset2_ref + (size_t)b0 * 126, d_offset2_tgt + (size_t)b0 * 126, st));
+  }
+  return SS2_OK;
+}
+
+extern "C" int ss2_spatial_tail(ss2_ctx* ctx, const float* d_offset1, const float* d_offset2_ref,
+                                const float* d_offset2_tgt, int bs, int img_h, int img_w, float* d_motion1,
+                                float* d_motion2, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  return spatial_tail_launch(ctx, d_offset1, d_offset2_ref, d_offset2_tgt, bs, img_h, img_w, d_motion1, d_motion2,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int ss2_build_spatial(ss2_ctx* ctx, const float* d_img1, const float* d_img2, int bs, float* d_motion1,
+                                 float* d_motion2, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (bs <= 0) return bs == 0 ? SS2_OK : ss2_fail(ctx, SS2_ERR_INVALID, "negative batch");
+  // the three offset vectors live in a small persistent scratch (not the arena: chunks reset it)
+  float* off = nullptr;
+  SS2_CUDA(ctx, cudaMallocAsync((void**)&off, (size_t)bs * (8 + 126 + 126) * sizeof(float), (cudaStream_t)stream));
+  float *o1 = off, *oref = off + (size_t)bs * 8, *otgt = oref + (size_t)bs * 126;
+  int rc = ss2_spatial_forward(ctx, d_img1, d_img2, bs, o1, oref, otgt, stream);
+  if (rc == SS2_OK)
+    rc = spatial_tail_launch(ctx, o1, oref, otgt, bs, NET_IMG_H, NET_IMG_W, d_motion1, d_motion2, (cudaStream_t)stream);
+  cudaFreeAsync(off, (cudaStream_t)stream);
+  return rc;
+}
+
+// frames [n,3,360,480] of one view -> motions [n,7,9,2]; motions[0] = 0
+extern "C" int ss2_build_temporal(ss2_ctx* ctx, const float* d_frames, int n, float* d_motions, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (!ctx->temporal.ready) return ss2_fail(ctx, SS2_ERR_NO_WEIGHTS, "TemporalNet weights not finalized");
+  if (n < 0 || (n > 0 && (!d_frames || !d_motions))) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_build_temporal: bad arguments");
+  if (n == 0) return SS2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const TemporalWeights& T = ctx->temporal;
+  const int H = NET_IMG_H, W = NET_IMG_W;
+  SS2_CUDA(ctx, cudaMemsetAsync(d_motions, 0, (size_t)126 * sizeof(float), st));
+  const int chunk = (n < TEMPORAL_CHUNK ? n : TEMPORAL_CHUNK);
+  SS2_TRY(ss2_ensure_arena(ctx, (size_t)chunk * (kBytesPerImageBackbone + kBytesPerPairHead) + ((size_t)64 << 20)));
+  // chunk c covers frames [f0, f1): features of f0-1 are recomputed (1-frame halo) so chunks
+  // stay independent; motion k needs features of frames k-1 and k.
+  for (int f0 = 1; f0 < n; f0 += chunk - 1) {
+    const int f1 = (f0 + chunk - 1 < n) ? f0 + chunk - 1 : n;  // motions f0..f1-1
+    const int nimg = f1 - f0 + 1;                              // frames f0-1 .. f1-1
+    ctx->arena.reset();
+    float *f64, *f32 = nullptr;
+    int h64, w64, h32, w32;
+    SS2_TRY(run_backbone(ctx, T.bb, d_frames + (size_t)(f0 - 1) * 3 * H * W, nimg, H, W, false, &f64, &h64, &w64,
+                         &f32, &h32, &w32, st));
+    const int nm = nimg - 1;
+    ARENA(cv, float, (size_t)nm * h64 * w64 * 64);
+    SS2_TRY(cost_volume_launch(ctx, f64, f64 + (size_t)h64 * w64 * 128, nm, h64, w64, 128, 3, 64, cv, st));
+    SS2_TRY(run_regressor(ctx, T.r2, cv, nm, h64, w64, d_motions + (size_t)f0 * 126, st));
+    if (chunk == 1) break;
+  }
+  return SS2_OK;
+}
+
+extern "C" int ss2_build_smooth(ss2_ctx* ctx, const float* d_ts1, const float* d_ts2, const float* d_sm1,
+                                const float* d_sm2, int nwin, int zero_first, float* op1, float* sp1, float* om1, float* smm1,
+                                float* op2, float* sp2, float* om2, float* smm2, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (!ctx->smooth.ready) return ss2_fail(ctx, SS2_ERR_NO_WEIGHTS, "SmoothNet weights not finalized");
+  if (nwin < 0 || (nwin > 0 && (!d_ts1 || !d_ts2 || !d_sm1 || !d_sm2)))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_build_smooth: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const SmoothWeights& M = ctx->smooth;
+  const size_t per_win = (size_t)SS2_WINDOW * SS2_NPT * 128 * sizeof(float);
+  const int chunk = nwin < SMOOTH_CHUNK ? nwin : SMOOTH_CHUNK;
+  SS2_TRY(ss2_ensure_arena(ctx, (size_t)chunk * per_win * 5 + ((size_t)16 << 20)));
+  for (int w0 = 0; w0 < nwin; w0 += chunk) {
+    const int nw = nwin - w0 < chunk ? nwin - w0 : chunk;
+    ctx->arena.reset();
+    const size_t hid = (size_t)nw * SS2_WINDOW * SS2_NPT * 128;
+    ARENA(h0, float, hid);
+    ARENA(h1, float, hid);
+    ARENA(p1, float, (size_t)nw * SS2_WINDOW * SS2_NPT * 2);
+    ARENA(p2, float, (size_t)nw * SS2_WINDOW * SS2_NPT * 2);
+    const size_t fo = (size_t)w0 * SS2_NPT * 2;  // frame offset of the first window of the chunk
+    SS2_TRY(smooth_embed_launch(ctx, M, d_ts1 + fo, d_ts2 + fo, d_sm1 + fo, d_sm2 + fo, nw, zero_first, h0, p1, p2, st));
+    SS2_TRY(conv_launch(ctx, M.conv3d[0], h0, nw, SS2_WINDOW, SS2_GRID_H + 1, SS2_GRID_W + 1, h1, nullptr, 1, st));
+    SS2_TRY(conv_launch(ctx, M.conv3d[1], h1, nw, SS2_WINDOW, SS2_GRID_H + 1, SS2_GRID_W + 1, h0, nullptr, 1, st));
+    SS2_TRY(conv_launch(ctx, M.conv3d[2], h0, nw, SS2_WINDOW, SS2_GRID_H + 1, SS2_GRID_W + 1, h1, nullptr, 1, st));
+    const size_t oo = (size_t)w0 * SS2_WINDOW * SS2_NPT * 2;
+    auto at = [&](float* p) { return p ? p + oo : nullptr; };
+    SS2_TRY(smooth_decode_launch(ctx, M, h1, d_sm1 + fo, d_sm2 + fo, p1, p2, nw, at(op1), at(sp1), at(om1), at(smm1),
+                                 at(op2), at(sp2), at(om2), at(smm2), st));
+  }
+  return SS2_OK;
+}

@@ -1,0 +1,145 @@
+// Whole-stream entry points: everything the reference's test() does between frame loading
+// and video writing (Full_model_inference/Codes/test_online_tra.py:284-399, AVERAGE fusion),
+// as stream-ordered launches with a single 16-byte D2H (the data-dependent canvas size).
+#include "common.cuh"
+
+// smooth meshes of a stream from per-window outputs (test_online_tra.py:378-392):
+//   with_head:  S[k] = win0[k] for k < 7, S[k] = win_{k-6}[6] for k >= 7  (nwin+6 frames)
+//   otherwise:  S[i] = win_i[6]                                            (nwin frames)
+__global__ void assemble_smooth_kernel(const float* __restrict__ win, int nwin, int with_head, float* __restrict__ out) {
+  const int k = blockIdx.x, tid = threadIdx.x;
+  if (tid >= SS2_NPT * 2) return;
+  int w, t;
+  if (with_head) {
+    if (k < SS2_WINDOW) { w = 0; t = k; } else { w = k - (SS2_WINDOW - 1); t = SS2_WINDOW - 1; }
+  } else {
+    w = k; t = SS2_WINDOW - 1;
+  }
+  out[(size_t)k * SS2_NPT * 2 + tid] = win[((size_t)w * SS2_WINDOW + t) * SS2_NPT * 2 + tid];
+}
+
+static int named_buf(ss2_ctx* ctx, const char* name, size_t bytes, float** out) {
+  auto& e = ctx->stream_bufs[name];
+  if (e.second < bytes) {
+    if (e.first) { SS2_CUDA(ctx, cudaDeviceSynchronize()); SS2_CUDA(ctx, cudaFree(e.first)); e.first = nullptr; e.second = 0; }
+    void* p = nullptr;
+    cudaError_t err = cudaMalloc(&p, bytes);
+    if (err != cudaSuccess) return ss2_fail(ctx, SS2_ERR_OOM, "cudaMalloc(%zu) for '%s': %s", bytes, name, cudaGetErrorString(err));
+    e.first = p; e.second = bytes;
+  }
+  *out = (float*)e.first;
+  return SS2_OK;
+}
+
+extern "C" int ss2_assemble_smooth(ss2_ctx* ctx, const float* d_win_smooth, int nwin, int with_head, float* d_out,
+                                   void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (nwin <= 0 || !d_win_smooth || !d_out) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_assemble_smooth: bad arguments");
+  const int nf = with_head ? nwin + SS2_WINDOW - 1 : nwin;
+  assemble_smooth_kernel<<<nf, 128, 0, (cudaStream_t)stream>>>(d_win_smooth, nwin, with_head, d_out);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+
+// lr1, lr2 [n,3,360,480] device -> smooth meshes [n,7,9,2] x2 (+ optional raw outputs)
+extern "C" int ss2_stream_meshes(ss2_ctx* ctx, const float* d_lr1, const float* d_lr2, int n, float* d_smooth1,
+                                 float* d_smooth2, float* d_smotion1, float* d_smotion2, float* d_tmotion1,
+                                 float* d_tmotion2, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (n < SS2_WINDOW) return ss2_fail(ctx, SS2_ERR_INVALID, "a stream needs at least %d frames (got %d)", SS2_WINDOW, n);
+  if (!d_lr1 || !d_lr2 || !d_smooth1 || !d_smooth2) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stream_meshes: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t m = (size_t)n * SS2_NPT * 2;
+  const int nwin = n - (SS2_WINDOW - 1);
+  const size_t wm = (size_t)nwin * SS2_WINDOW * SS2_NPT * 2;
+  float* buf;
+  SS2_TRY(named_buf(ctx, "stream_meshes", (8 * m + 2 * wm) * sizeof(float), &buf));
+  float *sm1 = buf, *sm2 = buf + m, *tm1 = buf + 2 * m, *tm2 = buf + 3 * m;
+  float *mesh1 = buf + 4 * m, *mesh2 = buf + 5 * m, *ts1 = buf + 6 * m, *ts2 = buf + 7 * m;
+  float *w1 = buf + 8 * m, *w2 = w1 + wm;
+  SS2_TRY(ss2_build_spatial(ctx, d_lr1, d_lr2, n, sm1, sm2, stream));
+  SS2_TRY(ss2_build_temporal(ctx, d_lr1, n, tm1, stream));
+  SS2_TRY(ss2_build_temporal(ctx, d_lr2, n, tm2, stream));
+  SS2_TRY(ss2_tsmotion(ctx, sm1, tm1, n, 1, nullptr, mesh1, ts1, stream));
+  SS2_TRY(ss2_tsmotion(ctx, sm2, tm2, n, 1, nullptr, mesh2, ts2, stream));
+  SS2_TRY(ss2_build_smooth(ctx, ts1, ts2, mesh1, mesh2, nwin, 1, nullptr, nullptr, nullptr, w1, nullptr, nullptr, nullptr,
+                           w2, stream));
+  SS2_TRY(ss2_assemble_smooth(ctx, w1, nwin, 1, d_smooth1, stream));
+  SS2_TRY(ss2_assemble_smooth(ctx, w2, nwin, 1, d_smooth2, stream));
+  const size_t mb = m * sizeof(float);
+  if (d_smotion1) SS2_CUDA(ctx, cudaMemcpyAsync(d_smotion1, sm1, mb, cudaMemcpyDeviceToDevice, st));
+  if (d_smotion2) SS2_CUDA(ctx, cudaMemcpyAsync(d_smotion2, sm2, mb, cudaMemcpyDeviceToDevice, st));
+  if (d_tmotion1) SS2_CUDA(ctx, cudaMemcpyAsync(d_tmotion1, tm1, mb, cudaMemcpyDeviceToDevice, st));
+  if (d_tmotion2) SS2_CUDA(ctx, cudaMemcpyAsync(d_tmotion2, tm2, mb, cudaMemcpyDeviceToDevice, st));
+  return SS2_OK;
+}
+
+#define WARP_CHUNK 8
+
+extern "C" int ss2_stitch_stream_host(ss2_ctx* ctx, const float* h_lr1, const float* h_lr2, const float* h_hr1,
+                                      const float* h_hr2, int n, int H, int W, int mode, int tps, float* h_out,
+                                      int64_t out_capacity, int* out_h, int* out_w, float* h_smooth_mesh1,
+                                      float* h_smooth_mesh2) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (n < SS2_WINDOW) return ss2_fail(ctx, SS2_ERR_INVALID, "a stream needs at least %d frames (got %d)", SS2_WINDOW, n);
+  if (!h_lr1 || !h_lr2 || !h_hr1 || !h_hr2 || !h_out || !out_h || !out_w || H <= 0 || W <= 0)
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stitch_stream_host: bad arguments");
+  SS2_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->s_compute) {
+    SS2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+    SS2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+    SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_hr, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+  }
+  cudaStream_t sc = ctx->s_compute, sx = ctx->s_copy;
+  const size_t lrb = (size_t)n * 3 * 360 * 480 * sizeof(float), hrb = (size_t)n * 3 * H * W * sizeof(float);
+  const size_t mb = (size_t)n * SS2_NPT * 2 * sizeof(float);
+  float *lr1, *lr2, *hr1, *hr2, *small;
+  SS2_TRY(named_buf(ctx, "lr1", lrb, &lr1));
+  SS2_TRY(named_buf(ctx, "lr2", lrb, &lr2));
+  SS2_TRY(named_buf(ctx, "hr1", hrb, &hr1));
+  SS2_TRY(named_buf(ctx, "hr2", hrb, &hr2));
+  SS2_TRY(named_buf(ctx, "small", 2 * mb + 64, &small));
+  float *S1 = small, *S2 = small + (size_t)n * SS2_NPT * 2, *mm = S2 + (size_t)n * SS2_NPT * 2;
+  // network inputs first on the compute stream; the (much larger) hr frames on the copy stream
+  SS2_CUDA(ctx, cudaMemcpyAsync(lr1, h_lr1, lrb, cudaMemcpyHostToDevice, sc));
+  SS2_CUDA(ctx, cudaMemcpyAsync(lr2, h_lr2, lrb, cudaMemcpyHostToDevice, sc));
+  SS2_CUDA(ctx, cudaMemcpyAsync(hr1, h_hr1, hrb, cudaMemcpyHostToDevice, sx));
+  SS2_CUDA(ctx, cudaMemcpyAsync(hr2, h_hr2, hrb, cudaMemcpyHostToDevice, sx));
+  SS2_CUDA(ctx, cudaEventRecord(ctx->ev_hr, sx));
+  SS2_TRY(ss2_stream_meshes(ctx, lr1, lr2, n, S1, S2, nullptr, nullptr, nullptr, nullptr, sc));
+  SS2_TRY(canvas_minmax_launch(ctx, S1, S2, n, H, W, mm, sc));
+  float h_mm[4];
+  SS2_CUDA(ctx, cudaMemcpyAsync(h_mm, mm, sizeof(h_mm), cudaMemcpyDeviceToHost, sc));
+  if (h_smooth_mesh1) SS2_CUDA(ctx, cudaMemcpyAsync(h_smooth_mesh1, S1, mb, cudaMemcpyDeviceToHost, sc));
+  if (h_smooth_mesh2) SS2_CUDA(ctx, cudaMemcpyAsync(h_smooth_mesh2, S2, mb, cudaMemcpyDeviceToHost, sc));
+  SS2_CUDA(ctx, cudaStreamSynchronize(sc));  // the canvas size is data dependent
+  int Ho, Wo;
+  ss2_canvas_size(h_mm, &Ho, &Wo);
+  *out_h = Ho; *out_w = Wo;
+  if (Ho <= 0 || Wo <= 0) return ss2_fail(ctx, SS2_ERR_INVALID, "degenerate canvas %dx%d", Ho, Wo);
+  const size_t fpx = (size_t)3 * Ho * Wo;
+  if ((int64_t)(fpx * n) > out_capacity)
+    return ss2_fail(ctx, SS2_ERR_INVALID, "output needs %zu floats, capacity %lld", fpx * n, (long long)out_capacity);
+  float* obuf;
+  SS2_TRY(named_buf(ctx, "out_chunks", 2 * WARP_CHUNK * fpx * sizeof(float), &obuf));
+  SS2_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_hr, 0));
+  // resample+blend in chunks, double-buffered so the D2H of chunk c overlaps the warp of c+1
+  int ci = 0;
+  for (int f0 = 0; f0 < n; f0 += WARP_CHUNK, ++ci) {
+    const int nf = n - f0 < WARP_CHUNK ? n - f0 : WARP_CHUNK;
+    const int slot = ci & 1;
+    float* dst = obuf + (size_t)slot * WARP_CHUNK * fpx;
+    if (ci >= 2) SS2_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_d2h[slot], 0));
+    SS2_TRY(ss2_stable_frames(ctx, hr1 + (size_t)f0 * 3 * H * W, hr2 + (size_t)f0 * 3 * H * W, S1 + (size_t)f0 * SS2_NPT * 2,
+                              S2 + (size_t)f0 * SS2_NPT * 2, nf, H, W, h_mm, mode, tps, dst, sc));
+    SS2_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[slot], sc));
+    SS2_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->ev_chunk[slot], 0));
+    SS2_CUDA(ctx, cudaMemcpyAsync(h_out + (size_t)f0 * fpx, dst, (size_t)nf * fpx * sizeof(float), cudaMemcpyDeviceToHost, sx));
+    SS2_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[slot], sx));
+  }
+  SS2_CUDA(ctx, cudaStreamSynchronize(sx));
+  SS2_CUDA(ctx, cudaStreamSynchronize(sc));
+  return SS2_OK;
+}

@@ -1,0 +1,229 @@
+"""Sequence glue of the hot path (the functions the reference keeps inside its driver script,
+Full_model_inference/Codes/test_online_tra.py) on top of libss2.
+
+  get_stable_sqe(...)      same signature/return as test_online_tra.py:96 (AVERAGE fusion)
+  stream_meshes(...)       test_online_tra.py:284-392 for a device-resident stream
+  stitch_stream(...)       device-resident whole stream -> fused frames [n,3,Ho,Wo]
+  stitch_stream_host(...)  the same through HOST buffers in one C call (H2D + D2H inside)
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, grid_res
+from .smooth_network import smooth_windows
+
+grid_h = grid_res.GRID_H
+grid_w = grid_res.GRID_W
+WINDOW = 7
+
+
+def _sync_nets(ctx, spatial_net, temporal_net, smooth_net):
+    spatial_net.sync_weights(ctx)
+    temporal_net.sync_weights(ctx)
+    smooth_net.sync_weights(ctx)
+
+
+def canvas_minmax(mesh1, mesh2, img_h, img_w):
+    """test_online_tra.py:103-117 -> CUDA tensor [4] = (xmin, xmax, ymin, ymax) in hr pixels."""
+    ctx = _lib.context()
+    m1 = _lib.dev_f32(mesh1).reshape(-1, 7, 9, 2)
+    m2 = _lib.dev_f32(mesh2).reshape(-1, 7, 9, 2)
+    out = torch.empty(4, device=m1.device, dtype=torch.float32)
+    ctx.check(ctx.lib.ss2_canvas_minmax(ctx.handle, _lib.ptr(m1), _lib.ptr(m2), m1.shape[0], int(img_h), int(img_w),
+                                        _lib.ptr(out), _lib.cur_stream()))
+    return out
+
+
+def canvas_size(minmax_host):
+    ctx_lib = _lib.load_library()
+    mm = (ctypes.c_float * 4)(*[float(v) for v in minmax_host])
+    h, w = ctypes.c_int(), ctypes.c_int()
+    ctx_lib.ss2_canvas_size(mm, ctypes.byref(h), ctypes.byref(w))
+    return h.value, w.value
+
+
+def stable_frames(hr1, hr2, mesh1, mesh2, minmax_host, mode="NORMAL", tps=None, out=None):
+    """The get_stable_sqe loop for n frames given the (global) canvas: hr [n,3,H,W] CUDA,
+    meshes [n,7,9,2] @480x360 -> fused [n,3,Ho,Wo]."""
+    from .utils import torch_tps_transform as tt
+    ctx = _lib.context()
+    hr1, hr2 = _lib.dev_f32(hr1), _lib.dev_f32(hr2)
+    m1 = _lib.dev_f32(mesh1).reshape(-1, 7, 9, 2)
+    m2 = _lib.dev_f32(mesh2).reshape(-1, 7, 9, 2)
+    n, _, H, W = hr1.shape
+    Ho, Wo = canvas_size(minmax_host)
+    if out is None:
+        out = torch.empty(n, 3, Ho, Wo, device=hr1.device, dtype=torch.float32)
+    mm = (ctypes.c_float * 4)(*[float(v) for v in minmax_host])
+    ctx.check(ctx.lib.ss2_stable_frames(ctx.handle, _lib.ptr(hr1), _lib.ptr(hr2), _lib.ptr(m1), _lib.ptr(m2), n, H, W,
+                                        mm, _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps, _lib.ptr(out),
+                                        _lib.cur_stream()))
+    return out
+
+
+def get_stable_sqe(img1_list, img2_list, smooth_mesh1, smooth_mesh2, warp_mode="NORMAL", fusion_mode="AVERAGE"):
+    """Drop-in for test_online_tra.py:96-154 (AVERAGE fusion): lists of [1,3,H,W] fp32 0..255
+    frames, smooth meshes [1,N,7,9,2] -> (list of [Ho,Wo,3] numpy frames, out_width, out_height)."""
+    if fusion_mode != "AVERAGE":
+        raise NotImplementedError("LINEAR fusion is SURVEY.md 8(f) 'next #1'; this path implements AVERAGE")
+    hr1 = torch.cat([_lib.dev_f32(t) for t in img1_list], 0)
+    hr2 = torch.cat([_lib.dev_f32(t) for t in img2_list], 0)
+    _, _, H, W = hr2.shape
+    m1 = _lib.dev_f32(smooth_mesh1).reshape(-1, 7, 9, 2)
+    m2 = _lib.dev_f32(smooth_mesh2).reshape(-1, 7, 9, 2)
+    mm = canvas_minmax(m1, m2, H, W).cpu().tolist()
+    fused = stable_frames(hr1, hr2, m1, m2, mm, warp_mode)
+    Ho, Wo = fused.shape[2:]
+    host = fused.permute(0, 2, 3, 1).contiguous().cpu().numpy()
+    return ([host[k] for k in range(host.shape[0])], torch.tensor(Wo, dtype=torch.int32),
+            torch.tensor(Ho, dtype=torch.int32))
+
+
+def stream_meshes(spatial_net, temporal_net, smooth_net, lr1, lr2, want_raw=False):
+    """lr1, lr2 [n,3,360,480] CUDA in [-1,1] -> smooth meshes ([n,7,9,2], [n,7,9,2])."""
+    ctx = _lib.context()
+    _sync_nets(ctx, spatial_net, temporal_net, smooth_net)
+    lr1, lr2 = _lib.dev_f32(lr1), _lib.dev_f32(lr2)
+    n = lr1.shape[0]
+    mk = lambda: torch.empty(n, 7, 9, 2, device=lr1.device, dtype=torch.float32)  # noqa: E731
+    s1, s2 = mk(), mk()
+    raw = [mk() for _ in range(4)] if want_raw else [None] * 4
+    ctx.check(ctx.lib.ss2_stream_meshes(ctx.handle, _lib.ptr(lr1), _lib.ptr(lr2), n, _lib.ptr(s1), _lib.ptr(s2),
+                                        *[_lib.ptr(r) for r in raw], _lib.cur_stream()))
+    if want_raw:
+        return s1, s2, dict(smotion1=raw[0], smotion2=raw[1], tmotion1=raw[2], tmotion2=raw[3])
+    return s1, s2
+
+
+def stitch_stream(spatial_net, temporal_net, smooth_net, lr1, lr2, hr1, hr2, mode="NORMAL", tps=None):
+    """Whole hot path, device resident: returns (fused [n,3,Ho,Wo], smooth_mesh1, smooth_mesh2)."""
+    s1, s2 = stream_meshes(spatial_net, temporal_net, smooth_net, lr1, lr2)
+    _, _, H, W = hr1.shape
+    mm = canvas_minmax(s1, s2, H, W).cpu().tolist()  # the one data-dependent host read (16 B)
+    return stable_frames(hr1, hr2, s1, s2, mm, mode, tps), s1, s2
+
+
+def stitch_stream_host(spatial_net, temporal_net, smooth_net, lr1, lr2, hr1, hr2, out, mode="NORMAL", tps=None,
+                       want_meshes=False):
+    """ss2_stitch_stream_host: all inputs/outputs are HOST tensors (pin them for full PCIe
+    speed); `out` is a flat fp32 host buffer large enough for n*3*Ho*Wo.  Returns (Ho, Wo)
+    [, smooth_mesh1, smooth_mesh2 as host tensors]."""
+    from .utils import torch_tps_transform as tt
+    ctx = _lib.context()
+    _sync_nets(ctx, spatial_net, temporal_net, smooth_net)
+    for t in (lr1, lr2, hr1, hr2, out):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("stitch_stream_host takes contiguous fp32 HOST tensors")
+    n, _, H, W = hr1.shape
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    m1 = torch.empty(n, 7, 9, 2) if want_meshes else None
+    m2 = torch.empty(n, 7, 9, 2) if want_meshes else None
+    ctx.check(ctx.lib.ss2_stitch_stream_host(ctx.handle, _lib.ptr(lr1), _lib.ptr(lr2), _lib.ptr(hr1), _lib.ptr(hr2),
+                                             n, H, W, _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps,
+                                             _lib.ptr(out), out.numel(), ctypes.byref(ho), ctypes.byref(wo),
+                                             _lib.ptr(m1), _lib.ptr(m2)))
+    if want_meshes:
+        return ho.value, wo.value, m1, m2
+    return ho.value, wo.value
+
+
+# ------------------------------------------------------------------------------------------
+# temporally sharded stream: one process per GPU, rank r owns frames [r*F, (r+1)*F)
+# (new design - the reference has no multi-GPU path)
+# ------------------------------------------------------------------------------------------
+def shard_plan(rank, world, frames_per_rank):
+    """Index arithmetic of the temporal sharding.  Frame k's smoothed mesh comes from the
+    window k-6..k (test_online_tra.py:359-392), whose tsmotion needs the raw spatial mesh of
+    frame k-7+1.. and the temporal motion of its own frames (test_online_tra.py:324-340):
+      start, stop   this rank's frames
+      ctx0          first frame whose raw (smotion, tmotion) this rank needs: max(0, start-6)
+      prev          frame whose smotion seeds tsmotion[ctx0] (-1: ctx0 is the stream start)
+      nwin          SmoothNet windows this rank evaluates
+      with_head     rank 0 keeps all 7 meshes of window 0
+      input_halo    extra leading input frames TemporalNet needs (frame start-1)"""
+    F = int(frames_per_rank)
+    if F < WINDOW:
+        raise ValueError("a shard needs at least %d frames (got %d)" % (WINDOW, F))
+    start, stop = rank * F, (rank + 1) * F
+    ctx0 = max(0, start - (WINDOW - 1))
+    with_head = ctx0 == 0
+    nwin = (stop - ctx0) - (WINDOW - 1)
+    if not with_head:
+        assert nwin == F
+    return dict(start=start, stop=stop, ctx0=ctx0, prev=ctx0 - 1, nwin=nwin, with_head=with_head,
+                input_halo=1 if rank > 0 else 0, total=world * F)
+
+
+def exchange_raw_meshes(raw, group=None):
+    """All-gather of the per-frame raw motions: raw [4,F,7,9,2] (smotion1, smotion2, tmotion1,
+    tmotion2 of this rank's frames) -> [4, world*F, 7,9,2] in stream order.  ~4 KB per frame:
+    latency-bound on NVLink, so one collective for everything."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(raw) for _ in range(world)]
+    dist.all_gather(parts, raw.contiguous(), group=group)
+    return torch.cat(parts, 1)
+
+
+def allreduce_canvas(minmax, group=None):
+    """Global canvas (test_online_tra.py:106-117 over ALL frames): (xmin,xmax,ymin,ymax) per
+    rank -> global, as ONE min-all-reduce of (xmin,-xmax,ymin,-ymax) (negation is exact)."""
+    import torch.distributed as dist
+    sign = torch.tensor([1.0, -1.0, 1.0, -1.0], device=minmax.device, dtype=minmax.dtype)
+    v = minmax * sign
+    dist.all_reduce(v, op=dist.ReduceOp.MIN, group=group)
+    return v * sign
+
+
+def stitch_stream_sharded(spatial_net, temporal_net, smooth_net, lr1, lr2, hr1, hr2, input_halo, mode="NORMAL",
+                          tps=None, group=None):
+    """This rank's part of a temporally sharded stream.  lr1, lr2 [input_halo+F,3,360,480]
+    (rank > 0 also gets frame start-1 for TemporalNet), hr1, hr2 [F,3,H,W]; all CUDA.
+    Returns (fused [F,3,Ho,Wo], smooth_mesh1 [F,7,9,2], smooth_mesh2) - identical to the rows
+    [start, stop) of the single-process result."""
+    import torch.distributed as dist
+    from .spatial_network import build_SpatialNet
+    ctx = _lib.context()
+    _sync_nets(ctx, spatial_net, temporal_net, smooth_net)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    F = hr1.shape[0]
+    plan = shard_plan(rank, world, F)
+    if input_halo != plan["input_halo"] or lr1.shape[0] != F + input_halo:
+        raise ValueError("rank %d expects %d halo frame(s) in lr1/lr2" % (rank, plan["input_halo"]))
+    lr1, lr2 = _lib.dev_f32(lr1), _lib.dev_f32(lr2)
+    dev = lr1.device
+    st = _lib.cur_stream()
+    raw = torch.empty(4, F, 7, 9, 2, device=dev, dtype=torch.float32)
+    sp = build_SpatialNet(spatial_net, lr1[input_halo:], lr2[input_halo:])
+    raw[0], raw[1] = sp["motion1"], sp["motion2"]
+    for v, lr in enumerate((lr1, lr2)):
+        tm = torch.empty(F + input_halo, 7, 9, 2, device=dev, dtype=torch.float32)
+        ctx.check(ctx.lib.ss2_build_temporal(ctx.handle, _lib.ptr(lr), F + input_halo, _lib.ptr(tm), st))
+        raw[2 + v] = tm[input_halo:]
+    allraw = exchange_raw_meshes(raw, group)  # [4, world*F, 7,9,2]
+    c0, stop = plan["ctx0"], plan["stop"]
+    n = stop - c0
+    smesh, tsm = [], []
+    for v in range(2):
+        sm = allraw[v, c0:stop].contiguous()
+        tmo = allraw[2 + v, c0:stop].contiguous()
+        prev = allraw[v, plan["prev"]].contiguous() if plan["prev"] >= 0 else None
+        mesh = torch.empty(n, 7, 9, 2, device=dev, dtype=torch.float32)
+        ts = torch.empty_like(mesh)
+        ctx.check(ctx.lib.ss2_tsmotion(ctx.handle, _lib.ptr(sm), _lib.ptr(tmo), n, 1 if prev is None else 0,
+                                       _lib.ptr(prev), _lib.ptr(mesh), _lib.ptr(ts), st))
+        smesh.append(mesh)
+        tsm.append(ts)
+    win = smooth_windows(smooth_net, tsm[0], tsm[1], smesh[0], smesh[1], plan["nwin"],
+                         want=("smooth_mesh1", "smooth_mesh2"))
+    S = []
+    for key in ("smooth_mesh1", "smooth_mesh2"):
+        o = torch.empty(F, 7, 9, 2, device=dev, dtype=torch.float32)
+        ctx.check(ctx.lib.ss2_assemble_smooth(ctx.handle, _lib.ptr(win[key]), plan["nwin"],
+                                              1 if plan["with_head"] else 0, _lib.ptr(o), st))
+        S.append(o)
+    _, _, H, W = hr1.shape
+    mm = allreduce_canvas(canvas_minmax(S[0], S[1], H, W), group).cpu().tolist()
+    return stable_frames(hr1, hr2, S[0], S[1], mm, mode, tps), S[0], S[1]

@@ -1,0 +1,317 @@
+"""GPU parity tests: the CUDA path (through the Python shims -> C ABI of libss2.so) against
+(1) the committed golden vectors, which are outputs of the unmodified reference, and
+(2) the CPU oracle on the same seeded inputs.
+
+Tolerances (fp32 path; all stated in the unit of the quantity):
+  - geometry ops, TPS coefficients/points: 1e-5 relative-ish absolute on normalised coords
+  - warped pixels: 1e-3 abs (north_star) on band-limited frames for >= 99.9% of pixels; the
+    remainder are the reference's own discontinuities (hard image edge, floor() flips when the
+    source coordinate moves by ~1e-4 px) - additionally bounded through the coordinate error
+    against the fp64 arbiter, which must not exceed the reference's own fp32 error by more
+    than 2e-3 px.
+  - mesh vertices (networks): 5e-3 px at 480x360 against the CPU reference (exact-fp32 SIMT
+    convolutions differ from MKL/oneDNN only by summation order); see DESIGN.md for TF32.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import stabstitch_oracle as O
+from oracle import weights as Wt
+
+pytestmark = pytest.mark.gpu
+
+T = torch.from_numpy
+
+
+def dev(a):
+    return (T(a) if isinstance(a, np.ndarray) else a).cuda()
+
+
+def maxdiff(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else a
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else b
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max())
+
+
+@pytest.fixture(scope="module")
+def nets():
+    from stabstitch2_b200.spatial_network import SpatialNet
+    from stabstitch2_b200.temporal_network import TemporalNet
+    from stabstitch2_b200.smooth_network import SmoothNet
+    from tests.golden.make_golden import MESH_SCALE_S, MESH_SCALE_T
+    s, t, m = SpatialNet().cuda().eval(), TemporalNet().cuda().eval(), SmoothNet().cuda().eval()
+    s.load_state_dict(Wt.spatial_state_dict(mesh_scale=MESH_SCALE_S), strict=True)
+    t.load_state_dict(Wt.temporal_state_dict(mesh_scale=MESH_SCALE_T), strict=True)
+    m.load_state_dict(Wt.smooth_state_dict(), strict=True)
+    return s, t, m
+
+
+@pytest.fixture(scope="module")
+def stream_inputs():
+    from tests.golden.make_golden import STREAM_N, STREAM_H, STREAM_W
+    hr = [[O.synth_frame(t, v, STREAM_H, STREAM_W) for t in range(STREAM_N)] for v in range(2)]
+    lr = [[O.lowres(x) for x in hr[v]] for v in range(2)]
+    return hr, lr
+
+
+# ---------------------------------------------------------------- ops vs golden (reference outputs)
+def test_dlt_golden(golden_ops):
+    from stabstitch2_b200.utils.torch_DLT import tensor_DLT
+    H = tensor_DLT(dev(golden_ops["dlt_src"]), dev(golden_ops["dlt_dst"]))
+    assert maxdiff(H, golden_ops["dlt_H"]) < 2e-5
+
+
+def test_homo_warp_golden(golden_ops):
+    from stabstitch2_b200.utils.torch_homo_transform import transformer
+    out = transformer(dev(golden_ops["homo_U"]), dev(golden_ops["homo_theta"]), (45, 60))
+    d = np.abs(out.cpu().numpy() - golden_ops["homo_out"])
+    assert (d > 1e-4).mean() < 2e-3, ((d > 1e-4).mean(), d.max())
+
+
+def test_cost_volume_golden(golden_ops):
+    from stabstitch2_b200.spatial_network import SpatialNet
+    a, b = dev(golden_ops["cv_a"]), dev(golden_ops["cv_b"])
+    assert maxdiff(SpatialNet.cost_volume(a, b, 5, norm=False), golden_ops["cv_sr5"]) < 1e-5
+    assert maxdiff(SpatialNet.cost_volume(a, b, 3, norm=False), golden_ops["cv_sr3"]) < 1e-5
+
+
+def test_ccl_golden(golden_ops):
+    from stabstitch2_b200.spatial_network import SpatialNet
+    net = SpatialNet()
+    out = net.CCL(dev(golden_ops["ccl_f1"]), dev(golden_ops["ccl_f2"]))
+    assert maxdiff(out, golden_ops["ccl_out"]) < 1e-4
+
+
+def test_ccl_known_answers():
+    from stabstitch2_b200.spatial_network import SpatialNet
+    g = torch.Generator().manual_seed(5)
+    f = torch.randn(1, 64, 12, 16, generator=g)
+    net = SpatialNet()
+    assert net.CCL(f, f).abs().max().item() < 1e-4
+    fl = net.CCL(f, torch.roll(f, (1, 2), (2, 3)))[0, :, 3:-3, 3:-3].cpu()
+    assert (fl[0] - 2).abs().max() < 1e-3 and (fl[1] - 1).abs().max() < 1e-3
+
+
+def test_tps_point_golden(golden_ops):
+    from stabstitch2_b200.utils.torch_tps_transform_point import transformer
+    g = golden_ops
+    out = transformer(dev(g["tps_pts"]), dev(g["tps_rigid"]), dev(g["tps_src"]))
+    assert maxdiff(out, g["tps_point_out"]) < 2e-6
+    rig = dev(g["tps_rigid"])
+    assert maxdiff(transformer(rig, rig, rig), g["tps_rigid"]) < 2e-6  # identity
+
+
+@pytest.mark.parametrize("mode", ["NORMAL", "FAST"])
+def test_tps_warp_golden(golden_ops, mode):
+    from stabstitch2_b200.utils.torch_tps_transform import transformer
+    g = golden_ops
+    out = transformer(dev(g["tps_img"]), dev(g["tps_src_canvas"]), dev(g["tps_rigid"]), (40, 100), mode=mode)
+    d = np.abs(out.cpu().numpy() - g["tps_warp_" + mode.lower()])
+    assert (d > 1e-3).mean() < 2e-3, ((d > 1e-3).mean(), d.max())
+
+
+def test_tps_warp_tensor_out_size_and_channels(golden_ops):
+    """out_size given as 0-dim CUDA int tensors (test_online_tra.py:140) and C=4 (LINEAR's mask channel)."""
+    from stabstitch2_b200.utils.torch_tps_transform import transformer
+    g = golden_ops
+    img = dev(g["tps_img"])
+    img4 = torch.cat([img, torch.ones_like(img[:, :1])], 1)
+    oh, ow = torch.tensor(40.7).cuda().int(), torch.tensor(100.2).cuda().int()
+    out = transformer(img4, dev(g["tps_src_canvas"]), dev(g["tps_rigid"]), (oh, ow))
+    assert out.shape == (2, 4, 40, 100)
+    d = np.abs(out[:, :3].cpu().numpy() - g["tps_warp_normal"])
+    assert (d > 1e-3).mean() < 2e-3
+    ref_mask = O.tps_warp(torch.ones(2, 1, 48, 64), T(g["tps_src_canvas"]), T(g["tps_rigid"]), (40, 100))
+    dm = (out[:, 3:].cpu() - ref_mask).abs()
+    assert (dm > 1e-3).float().mean() < 2e-3
+
+
+def test_empty_and_errors():
+    from stabstitch2_b200 import _lib
+    from stabstitch2_b200.utils.torch_tps_transform import transformer
+    from stabstitch2_b200.utils.torch_DLT import tensor_DLT
+    assert tensor_DLT(torch.zeros(0, 4, 2), torch.zeros(0, 4, 2)).shape == (0, 3, 3)
+    rig = O.norm_mesh(O.rigid_mesh(1, 360, 480), 360, 480)
+    assert transformer(torch.zeros(1, 3, 8, 8), rig, rig, (0, 5)).shape == (1, 3, 0, 5)
+    with pytest.raises(ValueError):
+        transformer(torch.zeros(1, 3, 8, 8), rig[:, :60], rig, (4, 4))
+    ctx = _lib.context()
+    rc = ctx.lib.ss2_tps_warp(ctx.handle, None, None, None, 1, 3, 8, 8, 4, 4, 0, 0, None, None)
+    assert rc == -1 and b"bad arguments" in ctx.lib.ss2_last_error(ctx.handle)
+
+
+# ---------------------------------------------------------------- networks vs golden
+def test_spatial_forward_golden(nets, stream_inputs, golden_stream):
+    s, _, _ = nets
+    _, lr = stream_inputs
+    a, b = torch.cat(lr[0], 0).cuda(), torch.cat(lr[1], 0).cuda()
+    o1, oref, otgt = s(a, b)
+    g = golden_stream
+    assert maxdiff(o1, g["offset_1"]) < 2e-3          # 4-pt offsets, px @480 (magnitude ~170)
+    assert maxdiff(oref, g["offset_2_ref"]) < 5e-3    # mesh residuals, px (magnitude ~5)
+    assert maxdiff(otgt, g["offset_2_tgt"]) < 5e-3
+
+
+def test_build_spatial_batch_equals_single(nets, stream_inputs, golden_stream):
+    from stabstitch2_b200.spatial_network import build_SpatialNet
+    s, _, _ = nets
+    _, lr = stream_inputs
+    g = golden_stream
+    r = build_SpatialNet(s, torch.cat(lr[0], 0), torch.cat(lr[1], 0))  # CPU tensors in, like the driver
+    assert maxdiff(r["motion1"], g["smotion1"]) < 5e-3
+    assert maxdiff(r["motion2"], g["smotion2"]) < 5e-3
+    r1 = build_SpatialNet(s, lr[0][3], lr[1][3])
+    assert maxdiff(r1["motion1"], r["motion1"][3:4]) < 1e-4
+    assert maxdiff(r1["motion2"], r["motion2"][3:4]) < 1e-4
+
+
+def test_temporal_golden(nets, stream_inputs, golden_stream):
+    from stabstitch2_b200.temporal_network import build_TemporalNet
+    _, t, _ = nets
+    _, lr = stream_inputs
+    for v in range(2):
+        ml = build_TemporalNet(t, lr[v])["motion_list"]
+        assert len(ml) == len(lr[v]) and ml[0].abs().max().item() == 0.0
+        assert maxdiff(torch.cat(ml, 0), golden_stream["tmotion%d" % (v + 1)]) < 2e-3
+
+
+def test_smooth_window_golden(nets, golden_stream):
+    from stabstitch2_b200.smooth_network import build_SmoothNet
+    _, _, m = nets
+    g = golden_stream
+    rig = O.rigid_mesh(1, 360, 480)
+    sm = [[rig + T(g["smotion%d" % v][k:k + 1]) for k in range(7)] for v in (1, 2)]
+    ts = [[T(g["tsmotion%d" % v][k:k + 1]) * (0.0 if k == 0 else 1.0) for k in range(7)] for v in (1, 2)]
+    o = build_SmoothNet(m, ts[0], ts[1], sm[0], sm[1])
+    for key in ("ori_path1", "smooth_path1", "ori_mesh1", "smooth_mesh1",
+                "ori_path2", "smooth_path2", "ori_mesh2", "smooth_mesh2"):
+        assert maxdiff(o[key], g["win0_" + key]) < 2e-3, key
+
+
+def test_stream_golden(nets, stream_inputs, golden_stream):
+    """Whole hot path on the small stream: meshes, canvas size, fused frames."""
+    from stabstitch2_b200 import pipeline
+    s, t, m = nets
+    hr, lr = stream_inputs
+    g = golden_stream
+    fused, s1, s2 = pipeline.stitch_stream(s, t, m, torch.cat(lr[0], 0).cuda(), torch.cat(lr[1], 0).cuda(),
+                                           torch.cat(hr[0], 0).cuda(), torch.cat(hr[1], 0).cuda())
+    assert maxdiff(s1[None], g["smooth_mesh1"]) < 5e-3
+    assert maxdiff(s2[None], g["smooth_mesh2"]) < 5e-3
+    assert tuple(fused.shape[2:]) == tuple(g["canvas_hw"])
+    f0 = fused[0].permute(1, 2, 0).cpu().numpy()
+    d = np.abs(f0 - g["frame0"])
+    # mesh differences of ~1e-3 px move pixel values by gradient*1e-3; edges flip single pixels
+    assert (d > 0.05).mean() < 2e-3, ((d > 0.05).mean(), d.max())
+    assert np.median(d) < 1e-3
+    fl = fused[-1].permute(1, 2, 0).cpu().numpy()[::8]
+    assert (np.abs(fl - g["frame_last_rows8"]) > 0.05).mean() < 2e-3
+
+
+def test_stream_host_call_matches_device_path(nets, stream_inputs):
+    from stabstitch2_b200 import pipeline
+    s, t, m = nets
+    hr, lr = stream_inputs
+    ins = [torch.cat(x, 0).contiguous().pin_memory() for x in (lr[0], lr[1], hr[0], hr[1])]
+    fused, s1, s2 = pipeline.stitch_stream(s, t, m, *[x.cuda() for x in ins])
+    out = torch.empty(fused.numel()).pin_memory()
+    ho, wo, m1, m2 = pipeline.stitch_stream_host(s, t, m, *ins, out, want_meshes=True)
+    assert (ho, wo) == tuple(fused.shape[2:])
+    assert maxdiff(m1, s1) == 0.0 and maxdiff(m2, s2) == 0.0
+    assert maxdiff(out.view_as(fused), fused) == 0.0
+
+
+def test_get_stable_sqe_dropin(golden_stream, stream_inputs):
+    """Reference-shaped call (lists of CPU tensors, [1,N,7,9,2] meshes) with the golden meshes:
+    isolates the resampler+blend from the networks."""
+    from stabstitch2_b200.pipeline import get_stable_sqe
+    hr, _ = stream_inputs
+    g = golden_stream
+    frames, ow, oh = get_stable_sqe(hr[0], hr[1], T(g["smooth_mesh1"]), T(g["smooth_mesh2"]), "NORMAL", "AVERAGE")
+    assert (int(oh), int(ow)) == tuple(g["canvas_hw"]) and len(frames) == len(hr[0])
+    d = np.abs(frames[0] - g["frame0"])
+    assert (d > 1e-3).mean() < 5e-3, ((d > 1e-3).mean(), d.max())
+    assert (d > 0.05).mean() < 5e-4
+
+
+# ---------------------------------------------------------------- full-size checks (720p)
+def _canvas_case(H=720, W=1280):
+    """Synthetic smooth meshes shaped like SURVEY.md 8d's probe: view 2 ~35% to the right."""
+    g = torch.Generator().manual_seed(11)
+    rig = O.rigid_mesh(1, 360, 480)
+    m1 = rig + torch.tensor([-86.0, 0.0]) + 3.0 * torch.randn(1, 7, 9, 2, generator=g)
+    m2 = rig + torch.tensor([86.0, 0.0]) + 3.0 * torch.randn(1, 7, 9, 2, generator=g)
+    return m1, m2
+
+
+def test_fullsize_frame_vs_oracle_and_arbiter():
+    from stabstitch2_b200 import pipeline
+    from stabstitch2_b200.utils.torch_tps_transform import transformer
+    H, W = 720, 1280
+    m1, m2 = _canvas_case(H, W)
+    hr1, hr2 = O.synth_frame(0, 0, H, W), O.synth_frame(0, 1, H, W)
+    M1, M2, wmin, hmin, ow, oh = O.canvas(m1[None], m2[None], H, W)
+    fused_ref, warp_ref = O.stable_frame(hr1, hr2, M1[:, 0], M2[:, 0], wmin, hmin, ow, oh)
+    mm = pipeline.canvas_minmax(m1, m2, H, W).cpu().tolist()
+    assert abs(mm[0] - float(wmin)) < 1e-4 and abs(mm[2] - float(hmin)) < 1e-4
+    fused = pipeline.stable_frames(hr1.cuda(), hr2.cuda(), m1, m2, mm)[0]
+    assert tuple(fused.shape) == tuple(fused_ref.shape)
+    d = (fused.cpu() - fused_ref).abs()
+    assert (d > 1e-3).float().mean() < 1e-2, ((d > 1e-3).float().mean(), d.max())
+    assert (d > 0.05).float().mean() < 5e-4
+    # coordinate-space check against the fp64 arbiter: warp ramp images (value = x resp. y index)
+    Ho, Wo = fused.shape[1:]
+    nrig = O.norm_mesh(O.rigid_mesh(1, H, W), H, W)
+    t1 = torch.stack([M1[0, 0, ..., 0] - wmin, M1[0, 0, ..., 1] - hmin], 2)[None]
+    src = O.norm_mesh(t1, oh, ow)
+    ax, ay = O.tps_source_coords_fp64(src, nrig, Ho, Wo, W, H)
+    ramp = torch.stack([torch.arange(W, dtype=torch.float32)[None, :].expand(H, W),
+                        torch.arange(H, dtype=torch.float32)[:, None].expand(H, W)], 0)[None]
+    got = transformer(ramp.cuda(), src.cuda(), nrig.cuda(), (Ho, Wo)).cpu().numpy()[0]
+    ref = O.tps_warp(ramp, src, nrig, (Ho, Wo)).numpy()[0]
+    inside = (ax[0] > 1) & (ax[0] < W - 2) & (ay[0] > 1) & (ay[0] < H - 2)
+    ex_got = np.abs(got[0] - ax[0])[inside].max()
+    ex_ref = np.abs(ref[0] - ax[0])[inside].max()
+    ey_got = np.abs(got[1] - ay[0])[inside].max()
+    ey_ref = np.abs(ref[1] - ay[0])[inside].max()
+    print("coord err vs fp64 (px): ours x %.2e y %.2e | reference x %.2e y %.2e" % (ex_got, ey_got, ex_ref, ey_ref))
+    assert ex_got < ex_ref + 2e-3 and ey_got < ey_ref + 2e-3
+
+
+def test_fullsize_properties():
+    """Size-independent properties at BASELINE's 720p size."""
+    from stabstitch2_b200.utils.torch_tps_transform import transformer, warp_blend_average
+    H, W = 720, 1280
+    nrig = O.norm_mesh(O.rigid_mesh(1, H, W), H, W).cuda()
+    img = O.synth_frame(3, 0, H, W).cuda()
+    # identity mesh: out == in resampled at (x+1)*W/2 with x on linspace(-1,1,W): compare with the oracle
+    out = transformer(img, nrig, nrig, (H, W))
+    ref = O.tps_warp(img.cpu(), nrig.cpu(), nrig.cpu(), (H, W))
+    d = (out.cpu() - ref).abs()
+    assert (d > 1e-3).float().mean() < 1e-2 and (d > 0.05).float().mean() < 5e-4
+    # linearity in the image
+    a = transformer(img * 0.5, nrig, nrig, (300, 500))
+    b = transformer(img, nrig, nrig, (300, 500))
+    assert (a - 0.5 * b).abs().max().item() < 1e-3
+    # blending a view with itself returns the view: a*(a/(2a+eps)) + a*(a/(2a+eps)) ~= a
+    st = torch.stack([nrig[0], nrig[0]], 0)[None]
+    both = warp_blend_average(img, img, st, st, (300, 500))
+    rel = (both - b).abs() / (b.abs() + 1.0)
+    assert rel.max().item() < 1e-3
+    # fused kernel == generic kernel + torch blend
+    m1, m2 = _canvas_case(H, W)
+    img2 = O.synth_frame(3, 1, H, W).cuda()
+    M1, M2, wmin, hmin, ow, oh = O.canvas(m1[None], m2[None], H, W)
+    srcs = []
+    for M in (M1, M2):
+        t = torch.stack([M[0, 0, ..., 0] - wmin, M[0, 0, ..., 1] - hmin], 2)[None]
+        srcs.append(O.norm_mesh(t, oh, ow))
+    src = torch.cat(srcs, 0).cuda()
+    tgt = torch.cat([nrig, nrig], 0)
+    Ho, Wo = int(oh.int()), int(ow.int())
+    w = transformer(torch.cat([img, img2], 0), src, tgt, (Ho, Wo))
+    fused = warp_blend_average(img, img2, src[None], tgt[None], (Ho, Wo))[0]
+    s = w[0] + w[1] + 1e-6
+    assert (fused - (w[0] * (w[0] / s) + w[1] * (w[1] / s))).abs().max().item() < 1e-4

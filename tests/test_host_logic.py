@@ -1,0 +1,200 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/ss2.h
+declares (no compute calls), the drop-in modules keep the reference's state-dict contract,
+the synthetic workload generators agree with the oracle's copies, and the temporal sharding
+logic (plan + halo all-gather + canvas all-reduce) reproduces the single-process result under
+a world_size-2 gloo group with the oracle doing the per-rank arithmetic."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import stabstitch_oracle as O
+from oracle import weights as Wt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "ss2.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ss2_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from stabstitch2_b200 import _lib
+    lib = _lib.load_library()
+    names = _header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libss2.so does not export " + n
+        assert n in _lib.SIGNATURES, "no ctypes prototype for " + n
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.ss2_version().startswith(b"ss2 ")
+    # host-only helper: canvas truncation like torch .int() (test_online_tra.py:140)
+    from stabstitch2_b200.pipeline import canvas_size
+    assert canvas_size([-10.5, 1733.9, -3.25, 724.0]) == (727, 1744)
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from stabstitch2_b200 import _lib
+    from stabstitch2_b200.utils.torch_DLT import tensor_DLT
+    with pytest.raises(_lib.SS2Error):
+        tensor_DLT(torch.zeros(1, 4, 2), torch.zeros(1, 4, 2))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "stabstitch2_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_state_dict_contract():
+    """strict load of checkpoints with the reference's key names."""
+    from stabstitch2_b200.smooth_network import SmoothNet
+    from stabstitch2_b200.spatial_network import SpatialNet
+    from stabstitch2_b200.temporal_network import TemporalNet
+    for cls, sd in ((SpatialNet, Wt.spatial_state_dict()), (TemporalNet, Wt.temporal_state_dict()),
+                    (SmoothNet, Wt.smooth_state_dict())):
+        net = cls().eval()
+        res = net.load_state_dict(sd, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        own = net.state_dict()
+        assert set(own) == set(sd)
+        for k in sd:
+            assert tuple(own[k].shape) == tuple(sd[k].shape), k
+    n = sum(v.numel() for k, v in SpatialNet().state_dict().items() if v.dtype.is_floating_point
+            and "running" not in k)
+    assert n == 11138756
+
+
+def test_synthetic_generators_match_oracle_copies():
+    from stabstitch2_b200 import synthetic as S
+    for a, b in ((S.spatial_state_dict(mesh_scale=20.0), Wt.spatial_state_dict(mesh_scale=20.0)),
+                 (S.temporal_state_dict(), Wt.temporal_state_dict()), (S.smooth_state_dict(), Wt.smooth_state_dict())):
+        assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    x, y = S.synth_frame(5, 1, 90, 160), O.synth_frame(5, 1, 90, 160)
+    assert torch.equal(x, y) and torch.equal(S.lowres(x), O.lowres(y))
+
+
+def test_shard_plan():
+    from stabstitch2_b200.pipeline import shard_plan
+    with pytest.raises(ValueError):
+        shard_plan(0, 2, 6)
+    for world in (1, 2, 4, 8):
+        for F in (7, 8, 16):
+            seen = []
+            for r in range(world):
+                p = shard_plan(r, world, F)
+                assert p["stop"] - p["start"] == F and p["ctx0"] == max(0, p["start"] - 6)
+                assert p["with_head"] == (r == 0) and p["input_halo"] == (1 if r else 0)
+                out = p["nwin"] + 6 if p["with_head"] else p["nwin"]
+                assert out == F
+                seen += list(range(p["start"], p["stop"]))
+            assert seen == list(range(world * F))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _sharded_worker(rank, world, port, F, raws, q):
+    """Per-rank arithmetic with the ORACLE's ops, distributed logic from the product."""
+    import torch.distributed as dist
+    from stabstitch2_b200 import pipeline
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        plan = pipeline.shard_plan(rank, world, F)
+        raw = raws[:, plan["start"]:plan["stop"]].clone()          # what this rank's nets produced
+        allraw = pipeline.exchange_raw_meshes(raw)
+        c0, stop = plan["ctx0"], plan["stop"]
+        rig = O.rigid_mesh(1, 360, 480)
+        nrig = O.norm_mesh(rig, 360, 480)
+        smesh, ts = [[], []], [[], []]
+        for v in range(2):
+            for k in range(c0, stop):
+                sm = rig + allraw[v, k][None]
+                if k == 0:
+                    t = sm * 0
+                else:
+                    moved = O.tps_point(O.norm_mesh(rig + allraw[2 + v, k][None], 360, 480), nrig,
+                                        O.norm_mesh(rig + allraw[v, k - 1][None], 360, 480))
+                    t = O.recover_mesh(moved, 360, 480) - sm
+                smesh[v].append(sm)
+                ts[v].append(t)
+        sdm = Wt.smooth_state_dict()
+        S = [[], []]
+        for w in range(plan["nwin"]):
+            a1, a2 = list(ts[0][w:w + 7]), list(ts[1][w:w + 7])
+            a1[0], a2[0] = a1[0] * 0, a2[0] * 0
+            o = O.smooth_forward(sdm, a1, a2, smesh[0][w:w + 7], smesh[1][w:w + 7])
+            for v, key in enumerate(("smooth_mesh1", "smooth_mesh2")):
+                if w == 0 and plan["with_head"]:
+                    S[v] += [o[key][:, i] for i in range(7)]
+                else:
+                    S[v].append(o[key][:, 6])
+        S1, S2 = torch.cat(S[0], 0), torch.cat(S[1], 0)
+        assert S1.shape[0] == F
+        m1, m2, wmin, hmin, ow, oh = O.canvas(S1[None], S2[None], 180, 320)
+        mm = torch.stack([wmin, torch.maximum(m1[..., 0].max(), m2[..., 0].max()), hmin,
+                          torch.maximum(m1[..., 1].max(), m2[..., 1].max())])
+        g = pipeline.allreduce_canvas(mm)
+        q.put((rank, S1.numpy(), S2.numpy(), g.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_stream_matches_single_process_gloo():
+    import torch.multiprocessing as mp
+    world, F = 2, 7
+    N = world * F
+    g = torch.Generator().manual_seed(3)
+    # raw network outputs of a 14-frame stream: smotion1/2 (view 2 shifted), tmotion1/2
+    raws = torch.randn(4, N, 7, 9, 2, generator=g) * torch.tensor([3.0, 3.0, 1.0, 1.0])[:, None, None, None, None]
+    raws[0, ..., 0] -= 80.0
+    raws[1, ..., 0] += 80.0
+    # single process: the oracle's own stream functions
+    with torch.no_grad():
+        sm1 = [raws[0, k][None] for k in range(N)]
+        sm2 = [raws[1, k][None] for k in range(N)]
+        tm1 = [raws[2, k][None] for k in range(N)]
+        tm2 = [raws[3, k][None] for k in range(N)]
+        smesh1, ts1 = O.tsmotion_prep(sm1, tm1)
+        smesh2, ts2 = O.tsmotion_prep(sm2, tm2)
+        S1, S2 = O.smooth_stream(Wt.smooth_state_dict(), smesh1, smesh2, ts1, ts2)
+        m1, m2, wmin, hmin, ow, oh = O.canvas(S1, S2, 180, 320)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, F, raws, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r, a, b, mm = q.get(timeout=300)
+        res[r] = (a, b, mm)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got1 = np.concatenate([res[r][0] for r in range(world)], 0)
+    got2 = np.concatenate([res[r][1] for r in range(world)], 0)
+    assert np.abs(got1 - S1[0].numpy()).max() < 1e-4
+    assert np.abs(got2 - S2[0].numpy()).max() < 1e-4
+    for r in range(world):
+        mm = res[r][2]
+        assert abs(mm[0] - float(wmin)) < 1e-3 and abs(mm[2] - float(hmin)) < 1e-3
+        assert abs((mm[1] - mm[0]) - float(ow)) < 1e-3 and abs((mm[3] - mm[2]) - float(oh)) < 1e-3
