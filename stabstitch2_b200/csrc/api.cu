@@ -47,6 +47,26 @@ void ss2_prof_end(ss2_ctx* ctx, int which, cudaStream_t st, double work) {
   p.work += work;
 }
 
+int tps_scratch_alloc(ss2_ctx* ctx, int bn, int Ho, int Wo, int tps, size_t extra_floats, TpsScratch* s, cudaStream_t st) {
+  const size_t nT = (size_t)bn * 2 * SS2_NSYS, nA = (size_t)bn * 8;
+  const size_t nN = tps == SS2_TPS_LATTICE ? tps_lattice_workspace_floats(bn, Ho, Wo) : 0;
+  const size_t pad = 64;  // keep every part 256-byte aligned
+  auto up = [&](size_t v) { return (v + pad - 1) / pad * pad; };
+  SS2_CUDA(ctx, cudaMallocAsync((void**)&s->base, (up(nT) + up(nA) + up(nN) + extra_floats) * sizeof(float), st));
+  s->T = s->base;
+  s->aux = s->T + up(nT);
+  s->nodes = s->aux + up(nA);
+  return SS2_OK;
+}
+
+int tps_solve_for_warp(ss2_ctx* ctx, const float* d_source, const float* d_target, int bn, int H, int W, int Ho, int Wo,
+                       int mode, int tps, const TpsScratch& s, cudaStream_t st) {
+  if (tps != SS2_TPS_LATTICE) return tps_solve_launch(ctx, d_source, d_target, bn, s.T, st);
+  const float hw = mode == SS2_MODE_NORMAL ? 0.5f * W : 0.5f * (W - 1);
+  const float hh = mode == SS2_MODE_NORMAL ? 0.5f * H : 0.5f * (H - 1);
+  return tps_solve_aux_launch(ctx, d_source, d_target, bn, s.T, s.aux, hw, hh, Ho, Wo, st);
+}
+
 extern "C" {
 
 int ss2_profile_enable(ss2_ctx* ctx, int which, int enable) {
@@ -159,11 +179,12 @@ int ss2_tps_warp(ss2_ctx* ctx, const float* d_U, const float* d_source, const fl
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_tps_warp: bad arguments");
   if (bn == 0 || Ho == 0 || Wo == 0) return SS2_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  float* T = nullptr;
-  SS2_CUDA(ctx, cudaMallocAsync((void**)&T, (size_t)bn * 2 * SS2_NSYS * sizeof(float), st));
-  int rc = tps_solve_launch(ctx, d_source, d_target, bn, T, st);
-  if (rc == SS2_OK) rc = tps_warp_launch(ctx, d_U, d_source, T, bn, C, H, W, Ho, Wo, mode, tps, d_out, st);
-  cudaFreeAsync(T, st);
+  if (tps != SS2_TPS_LATTICE || C != 3 || !tps_lattice_supported(Ho, Wo)) tps = SS2_TPS_EXACT;
+  TpsScratch sc;
+  SS2_TRY(tps_scratch_alloc(ctx, bn, Ho, Wo, tps, 0, &sc, st));
+  int rc = tps_solve_for_warp(ctx, d_source, d_target, bn, H, W, Ho, Wo, mode, tps, sc, st);
+  if (rc == SS2_OK) rc = tps_warp_launch(ctx, d_U, d_source, sc.T, bn, C, H, W, Ho, Wo, mode, tps, d_out, st, sc.aux, sc.nodes);
+  cudaFreeAsync(sc.base, st);
   return rc;
 }
 
@@ -176,11 +197,13 @@ int ss2_tps_warp_blend_avg(ss2_ctx* ctx, const float* d_img1, const float* d_img
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_tps_warp_blend_avg: bad arguments");
   if (nframes == 0 || Ho == 0 || Wo == 0) return SS2_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  float* T = nullptr;
-  SS2_CUDA(ctx, cudaMallocAsync((void**)&T, (size_t)nframes * 2 * 2 * SS2_NSYS * sizeof(float), st));
-  int rc = tps_solve_launch(ctx, d_source, d_target, 2 * nframes, T, st);
-  if (rc == SS2_OK) rc = tps_warp_blend_launch(ctx, d_img1, d_img2, d_source, T, nframes, H, W, Ho, Wo, mode, tps, d_out, st);
-  cudaFreeAsync(T, st);
+  if (tps != SS2_TPS_LATTICE || !tps_lattice_supported(Ho, Wo)) tps = SS2_TPS_EXACT;
+  TpsScratch sc;
+  SS2_TRY(tps_scratch_alloc(ctx, 2 * nframes, Ho, Wo, tps, 0, &sc, st));
+  int rc = tps_solve_for_warp(ctx, d_source, d_target, 2 * nframes, H, W, Ho, Wo, mode, tps, sc, st);
+  if (rc == SS2_OK)
+    rc = tps_warp_blend_launch(ctx, d_img1, d_img2, d_source, sc.T, nframes, H, W, Ho, Wo, mode, tps, d_out, st, sc.aux, sc.nodes);
+  cudaFreeAsync(sc.base, st);
   return rc;
 }
 
@@ -251,14 +274,16 @@ int ss2_stable_frames(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, cons
   if (!d_out) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stable_frames: null output");
   cudaStream_t st = (cudaStream_t)stream;
   const float out_w = h_minmax[1] - h_minmax[0], out_h = h_minmax[3] - h_minmax[2];
-  float* buf = nullptr;
+  if (tps != SS2_TPS_LATTICE || !tps_lattice_supported(Ho, Wo)) tps = SS2_TPS_EXACT;
   const size_t m = (size_t)n * 2 * SS2_NPT * 2;
-  SS2_CUDA(ctx, cudaMallocAsync((void**)&buf, (2 * m + (size_t)n * 2 * 2 * SS2_NSYS) * sizeof(float), st));
-  float *source = buf, *target = buf + m, *T = buf + 2 * m;
+  TpsScratch sc;
+  SS2_TRY(tps_scratch_alloc(ctx, 2 * n, Ho, Wo, tps, 2 * m, &sc, st));
+  float *source = sc.nodes + (tps == SS2_TPS_LATTICE ? (tps_lattice_workspace_floats(2 * n, Ho, Wo) + 63) / 64 * 64 : 0);
+  float* target = source + m;
   int rc = stable_meshes_launch(ctx, d_mesh1, d_mesh2, n, H, W, h_minmax[0], h_minmax[2], out_w, out_h, source, target, st);
-  if (rc == SS2_OK) rc = tps_solve_launch(ctx, source, target, 2 * n, T, st);
-  if (rc == SS2_OK) rc = tps_warp_blend_launch(ctx, d_hr1, d_hr2, source, T, n, H, W, Ho, Wo, mode, tps, d_out, st);
-  cudaFreeAsync(buf, st);
+  if (rc == SS2_OK) rc = tps_solve_for_warp(ctx, source, target, 2 * n, H, W, Ho, Wo, mode, tps, sc, st);
+  if (rc == SS2_OK) rc = tps_warp_blend_launch(ctx, d_hr1, d_hr2, source, sc.T, n, H, W, Ho, Wo, mode, tps, d_out, st, sc.aux, sc.nodes);
+  cudaFreeAsync(sc.base, st);
   return rc;
 }
 

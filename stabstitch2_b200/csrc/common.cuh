@@ -106,6 +106,7 @@ struct ss2_ctx {
   cudaEvent_t ev_hr = nullptr, ev_chunk[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   ProfClass prof[SS2_PROF_COUNT];
   int use_tc = 1;  // tcgen05 implicit-GEMM path for eligible layers
+  bool lag_tables_ready = false;
 };
 
 int ss2_fail(ss2_ctx* ctx, int code, const char* fmt, ...);
@@ -150,11 +151,25 @@ int tps_solve_launch(ss2_ctx* ctx, const float* d_source, const float* d_target,
                      cudaStream_t st);
 int tps_point_launch(ss2_ctx* ctx, const float* d_point, const float* d_source, const float* d_T, int bn,
                      float* d_out, cudaStream_t st);
+int tps_solve_aux_launch(ss2_ctx* ctx, const float* d_source, const float* d_target, int bn, float* d_T, float* d_aux,
+                         float half_w, float half_h, int Ho, int Wo, cudaStream_t st);
+size_t tps_lattice_workspace_floats(int bn, int Ho, int Wo);
+bool tps_lattice_supported(int Ho, int Wo);
+// d_aux [bn][8] + d_nodes (tps_lattice_workspace_floats) are needed by tps == SS2_TPS_LATTICE
 int tps_warp_launch(ss2_ctx* ctx, const float* d_U, const float* d_source, const float* d_T, int bn, int C,
-                    int H, int W, int Ho, int Wo, int mode, int tps, float* d_out, cudaStream_t st);
+                    int H, int W, int Ho, int Wo, int mode, int tps, float* d_out, cudaStream_t st,
+                    const float* d_aux, float* d_nodes);
 int tps_warp_blend_launch(ss2_ctx* ctx, const float* d_img1, const float* d_img2, const float* d_source,
                           const float* d_T, int nframes, int H, int W, int Ho, int Wo, int mode, int tps,
-                          float* d_out, cudaStream_t st);
+                          float* d_out, cudaStream_t st, const float* d_aux, float* d_nodes);
+// one stream-ordered allocation holding T [bn][2][66], aux [bn][8] and the lattice nodes
+struct TpsScratch {
+  float* base = nullptr;
+  float *T = nullptr, *aux = nullptr, *nodes = nullptr;
+};
+int tps_scratch_alloc(ss2_ctx* ctx, int bn, int Ho, int Wo, int tps, size_t extra_floats, TpsScratch* s, cudaStream_t st);
+int tps_solve_for_warp(ss2_ctx* ctx, const float* d_source, const float* d_target, int bn, int H, int W, int Ho, int Wo,
+                       int mode, int tps, const TpsScratch& s, cudaStream_t st);
 // geom.cu
 int dlt_launch(ss2_ctx* ctx, const float* d_src, const float* d_dst, int bs, float* d_H, cudaStream_t st);
 int homo_warp_nchw_launch(ss2_ctx* ctx, const float* d_U, const float* d_theta, int bn, int C, int H, int W,

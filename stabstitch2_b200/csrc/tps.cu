@@ -21,7 +21,8 @@
 #define AUG (SS2_NSYS + 2)
 
 __global__ void __launch_bounds__(SOLVE_THREADS)
-tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ target, float* __restrict__ Tout) {
+tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ target, float* __restrict__ Tout,
+                 float* __restrict__ aux, float half_w, float half_h, float kx, float ky) {
   __shared__ double A[SS2_NSYS][AUG];
   __shared__ float sx[SS2_NPT], sy[SS2_NPT];
   __shared__ int piv_row;
@@ -104,12 +105,58 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
     int c = e / SS2_NSYS, j = e % SS2_NSYS;
     Tout[(size_t)b * 2 * SS2_NSYS + c * SS2_NSYS + j] = (float)(A[j][SS2_NSYS + c] / A[j][j]);
   }
+  // Affine predictor for the lattice resampler: least-squares fit target ~ a*sx + b*sy + c over
+  // the 63 control points, expressed in source PIXEL units as a function of the canvas pixel
+  // index (col,row): px = aux[0]*col + aux[1]*row + aux[2], py = aux[3]*col + aux[4]*row + aux[5].
+  // Cubic interpolation reproduces affine functions exactly, so any affine predictor is
+  // mathematically neutral; it only keeps the interpolated residuals small (fp32 rounding).
+  if (aux && tid == 0) {
+    double S[6] = {0, 0, 0, 0, 0, 0}, Bx[3] = {0, 0, 0}, By[3] = {0, 0, 0};
+    for (int i = 0; i < SS2_NPT; ++i) {
+      const double x = sx[i], y = sy[i], u = tgt[2 * i], v = tgt[2 * i + 1];
+      S[0] += x * x; S[1] += x * y; S[2] += x; S[3] += y * y; S[4] += y; S[5] += 1.0;
+      Bx[0] += x * u; Bx[1] += y * u; Bx[2] += u;
+      By[0] += x * v; By[1] += y * v; By[2] += v;
+    }
+    // normal equations [[S0 S1 S2],[S1 S3 S4],[S2 S4 S5]] p = B, Cramer's rule
+    const double m00 = S[3] * S[5] - S[4] * S[4], m01 = S[1] * S[5] - S[4] * S[2], m02 = S[1] * S[4] - S[3] * S[2];
+    const double det = S[0] * m00 - S[1] * m01 + S[2] * m02;
+    double sol[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    if (fabs(det) > 1e-30) {
+      const double inv[3][3] = {
+          {m00 / det, -m01 / det, m02 / det},
+          {-m01 / det, (S[0] * S[5] - S[2] * S[2]) / det, -(S[0] * S[4] - S[1] * S[2]) / det},
+          {m02 / det, -(S[0] * S[4] - S[1] * S[2]) / det, (S[0] * S[3] - S[1] * S[1]) / det}};
+      for (int r = 0; r < 3; ++r) {
+        sol[0][r] = inv[r][0] * Bx[0] + inv[r][1] * Bx[1] + inv[r][2] * Bx[2];
+        sol[1][r] = inv[r][0] * By[0] + inv[r][1] * By[1] + inv[r][2] * By[2];
+      }
+    }
+    float* o = aux + (size_t)b * 8;
+    // s = -1 + k*idx  ->  pix = half * (a*kx*col + b*ky*row + (c + 1 - a - b))
+    o[0] = (float)(half_w * sol[0][0] * kx); o[1] = (float)(half_w * sol[0][1] * ky);
+    o[2] = (float)(half_w * (sol[0][2] + 1.0 - sol[0][0] - sol[0][1]));
+    o[3] = (float)(half_h * sol[1][0] * kx); o[4] = (float)(half_h * sol[1][1] * ky);
+    o[5] = (float)(half_h * (sol[1][2] + 1.0 - sol[1][0] - sol[1][1]));
+    o[6] = 0.f; o[7] = 0.f;
+  }
 }
 
 int tps_solve_launch(ss2_ctx* ctx, const float* d_source, const float* d_target, int bn, float* d_T,
                      cudaStream_t st) {
   if (bn <= 0) return SS2_OK;
-  tps_solve_kernel<<<bn, SOLVE_THREADS, 0, st>>>(d_source, d_target, d_T);
+  tps_solve_kernel<<<bn, SOLVE_THREADS, 0, st>>>(d_source, d_target, d_T, nullptr, 0.f, 0.f, 0.f, 0.f);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+
+// solve + affine predictor (aux [bn][8]) for the lattice resampler: (half_w, half_h) convert the
+// normalised source coordinate to pixels, (Wo, Ho) is the canvas the dense grid spans
+int tps_solve_aux_launch(ss2_ctx* ctx, const float* d_source, const float* d_target, int bn, float* d_T, float* d_aux,
+                         float half_w, float half_h, int Ho, int Wo, cudaStream_t st) {
+  if (bn <= 0) return SS2_OK;
+  const float kx = Wo > 1 ? (float)(2.0 / (Wo - 1)) : 0.f, ky = Ho > 1 ? (float)(2.0 / (Ho - 1)) : 0.f;
+  tps_solve_kernel<<<bn, SOLVE_THREADS, 0, st>>>(d_source, d_target, d_T, d_aux, half_w, half_h, kx, ky);
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }
@@ -167,10 +214,8 @@ __device__ __forceinline__ float lin11(int i, int n, float step) {
 // coordinates, separate multiplies and adds in the reference's order, so that out-of-image
 // samples cancel to the same kind of rounding residue the reference produces.
 template <int C>
-__device__ __forceinline__ void sample_normal(const float* __restrict__ img, int H, int W, float xs, float ys,
+__device__ __forceinline__ void sample_normal(const float* __restrict__ img, int H, int W, float x, float y,
                                               float (&out)[C]) {
-  const float x = __fmul_rn(__fmul_rn(__fadd_rn(xs, 1.0f), (float)W), 0.5f);
-  const float y = __fmul_rn(__fmul_rn(__fadd_rn(ys, 1.0f), (float)H), 0.5f);
   const float fx = floorf(x), fy = floorf(y);
   // float->int conversion saturates like torch's .int() for finite values
   int x0 = (int)fminf(fmaxf(fx, -2.0e9f), 2.0e9f);
@@ -197,10 +242,8 @@ __device__ __forceinline__ void sample_normal(const float* __restrict__ img, int
 
 // F.grid_sample(bilinear, padding_mode='zeros', align_corners=True)
 template <int C>
-__device__ __forceinline__ void sample_fast(const float* __restrict__ img, int H, int W, float xs, float ys,
+__device__ __forceinline__ void sample_fast(const float* __restrict__ img, int H, int W, float x, float y,
                                             float (&out)[C]) {
-  const float x = (xs + 1.0f) * 0.5f * (float)(W - 1);
-  const float y = (ys + 1.0f) * 0.5f * (float)(H - 1);
   const float fx = floorf(x), fy = floorf(y);
   const int x0 = (int)fminf(fmaxf(fx, -2.0e9f), 2.0e9f), y0 = (int)fminf(fmaxf(fy, -2.0e9f), 2.0e9f);
   const int x1 = x0 + 1, y1 = y0 + 1;
@@ -229,8 +272,14 @@ __device__ __forceinline__ float blend_avg(float a, float b) {
   return __fadd_rn(__fmul_rn(a, __fdiv_rn(a, s)), __fmul_rn(b, __fdiv_rn(b, s)));
 }
 
+// ------------------------------------------------------------------------------------------
+// EXACT field: all 63 radial terms per pixel in the reference's arithmetic (fp32, accurate
+// logf, unfused d2), accumulated in control-point order.  This is the validation mode and the
+// generic utils.torch_tps_transform.transformer path; the production path is the lattice
+// resampler below.
 // Tile geometry: a CTA of TX x TY threads covers TX x (TY*RPT) canvas pixels; each thread owns
 // RPT pixels of one column (rows r, r+TY, ...), so dx and dx^2 are shared between them.
+// ------------------------------------------------------------------------------------------
 #define TX 32
 #define TY 4
 #define RPT 2
@@ -243,14 +292,20 @@ struct WarpParams {
   float* out;            // BLEND: [n][C][Ho][Wo]; else [n*V][C][Ho][Wo]
   int H, W, Ho, Wo;
   float stepx, stepy;
+  // lattice mode
+  const float* aux;      // [n][V][8] affine predictor
+  const float2* nodes;   // [n][ny][nx][V] residual source pixel coordinates at the lattice nodes
+  int nx, ny;
+  float R2, p0, p1, p2, p3;  // near radius^2 (normalised units) and the blending cubic P(s)
+  float q0, q1, q2, q3;      // P / ln2
+  float half_w, half_h;      // normalised -> pixel scale of the source image
 };
 
-// Exact field: all 63 radial terms, lg2 on the MUFU pipe with ln2 folded into the weights.
 // V = views evaluated per pixel (2 for the fused blend, 1 for the generic transformer).
 template <int V, int C, int MODE, bool BLEND>
 __global__ void __launch_bounds__(TX* TY)
 tps_warp_exact_kernel(WarpParams P) {
-  __shared__ float4 cp[V][SS2_NPT_PAD];  // (px, py, wx*ln2, wy*ln2)
+  __shared__ float4 cp[V][SS2_NPT_PAD];  // (px, py, wx, wy)
   __shared__ float aff[V][6];
   const int n = blockIdx.z;
   const int tid = threadIdx.y * TX + threadIdx.x;
@@ -260,7 +315,7 @@ tps_warp_exact_kernel(WarpParams P) {
     if (j < SS2_NPT) {
       const float* s = P.source + ((size_t)(n * V + v) * SS2_NPT + j) * 2;
       const float* t = P.T + (size_t)(n * V + v) * 2 * SS2_NSYS;
-      c = make_float4(s[0], s[1], t[3 + j] * LN2F, t[SS2_NSYS + 3 + j] * LN2F);
+      c = make_float4(s[0], s[1], t[3 + j], t[SS2_NSYS + 3 + j]);
     }
     cp[v][j] = c;
   }
@@ -283,19 +338,19 @@ tps_warp_exact_kernel(WarpParams P) {
     float ax[RPT], ay[RPT];
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
-      ax[r] = aff[v][0] + aff[v][1] * xt + aff[v][2] * yt[r];
-      ay[r] = aff[v][3] + aff[v][4] * xt + aff[v][5] * yt[r];
+      ax[r] = fmaf(aff[v][2], yt[r], fmaf(aff[v][1], xt, aff[v][0]));
+      ay[r] = fmaf(aff[v][5], yt[r], fmaf(aff[v][4], xt, aff[v][3]));
     }
-#pragma unroll 7
+#pragma unroll 3
     for (int i = 0; i < SS2_NPT; ++i) {
       const float4 c = cp[v][i];
-      const float dx = xt - c.x;
-      const float dx2 = dx * dx;
+      const float dx = __fsub_rn(xt, c.x);
+      const float dx2 = __fmul_rn(dx, dx);
 #pragma unroll
       for (int r = 0; r < RPT; ++r) {
-        const float dy = yt[r] - c.y;
-        const float d2 = fmaf(dy, dy, dx2);
-        const float rr = d2 * __log2f(d2 + 1e-6f);
+        const float dy = __fsub_rn(yt[r], c.y);
+        const float d2 = __fadd_rn(dx2, __fmul_rn(dy, dy));
+        const float rr = __fmul_rn(d2, logf(__fadd_rn(d2, 1e-6f)));
         ax[r] = fmaf(c.z, rr, ax[r]);
         ay[r] = fmaf(c.w, rr, ay[r]);
       }
@@ -303,8 +358,15 @@ tps_warp_exact_kernel(WarpParams P) {
     const float* img = P.img[BLEND ? v : 0] + (size_t)(BLEND ? n : n * V + v) * C * P.H * P.W;
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
-      if (MODE == SS2_MODE_NORMAL) sample_normal<C>(img, P.H, P.W, ax[r], ay[r], res[r][v]);
-      else sample_fast<C>(img, P.H, P.W, ax[r], ay[r], res[r][v]);
+      if (MODE == SS2_MODE_NORMAL) {
+        const float x = __fmul_rn(__fmul_rn(__fadd_rn(ax[r], 1.0f), (float)P.W), 0.5f);
+        const float y = __fmul_rn(__fmul_rn(__fadd_rn(ay[r], 1.0f), (float)P.H), 0.5f);
+        sample_normal<C>(img, P.H, P.W, x, y, res[r][v]);
+      } else {
+        const float x = (ax[r] + 1.0f) * 0.5f * (float)(P.W - 1);
+        const float y = (ay[r] + 1.0f) * 0.5f * (float)(P.H - 1);
+        sample_fast<C>(img, P.H, P.W, x, y, res[r][v]);
+      }
     }
   }
   const size_t plane = (size_t)P.Ho * P.Wo;
@@ -327,18 +389,485 @@ tps_warp_exact_kernel(WarpParams P) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// LATTICE resampler (production path).
+//
+// The TPS field f(p) = affine(p) + sum_i w_i phi(|p-c_i|^2), phi(s) = s log(s + 1e-6), is split
+//     phi = phi_far + psi,   phi_far(s) = phi(s) for s >= R^2, = P(s) for s < R^2,
+// with P the cubic Taylor polynomial of phi at s = R^2 (phi_far is C^3 with derivatives of the
+// size phi has at distance R), and psi = phi - P compactly supported in the disc s < R^2.
+//   * tps_nodes_kernel evaluates affine + sum_i w_i phi_far exactly (accurate logf, fp64
+//     accumulation) on a lattice with SX x SY pixel spacing and stores it as residual source
+//     PIXEL coordinates w.r.t. the affine predictor of tps_solve_kernel (small magnitudes, so
+//     the fp32 interpolation below rounds at the 1e-6 px level).
+//   * tps_warp_lattice_kernel interpolates the lattice with tensor-product QUINTIC Lagrange
+//     weights (6x6 nodes): the y contraction is done once per (row, node column) of the CTA's
+//     tile into shared memory, the x contraction is 6 FMAs per coordinate per pixel; it then
+//     adds sum w_i psi for the few control points whose disc touches the tile (1 MUFU lg2
+//     each), samples, blends and stores.
+// Interpolation error ~ c h^6 |f_far^(6)|: with (SX,SY,R) of lattice_config() the source
+// coordinate is as close to the fp64 arbiter as the reference's own fp32 evaluation
+// (tests/test_gpu_parity.py::test_fullsize_frame_vs_oracle_and_arbiter).
+// Out-of-image samples are exactly 0 here (the reference's clamped taps cancel to a rounding
+// residue of a few 1e-3 grey levels; DESIGN.md "OOB residue").
+// ------------------------------------------------------------------------------------------
+#define LAT_THREADS 128
+#define LAT_TAPS 6
+#define LAT_LO 2  // lattice index of array slot 0 is -LAT_LO
+
+__device__ __forceinline__ float blend_poly(float s, float R2, float p0, float p1, float p2, float p3) {
+  const float u = s - R2;
+  return fmaf(u, fmaf(u, fmaf(u, p3, p2), p1), p0);
+}
+
+// one thread per (node, view): grid (node blocks, V, frames)
+template <int V>
+__global__ void __launch_bounds__(128)
+tps_nodes_kernel(WarpParams P, int SX, int SY) {
+  __shared__ float2 cxy[SS2_NPT];
+  __shared__ double2 cw[SS2_NPT];
+  __shared__ double aff[6];
+  __shared__ float pred[6];
+  const int n = blockIdx.z, v = blockIdx.y, tid = threadIdx.x;
+  const float* t = P.T + (size_t)(n * V + v) * 2 * SS2_NSYS;
+  if (tid < SS2_NPT) {
+    const float* s = P.source + ((size_t)(n * V + v) * SS2_NPT + tid) * 2;
+    cxy[tid] = make_float2(s[0], s[1]);
+    cw[tid] = make_double2((double)t[3 + tid], (double)t[SS2_NSYS + 3 + tid]);
+  } else if (tid < SS2_NPT + 6) {
+    const int k = tid - SS2_NPT;
+    aff[k] = (double)t[(k / 3) * SS2_NSYS + (k % 3)];
+    pred[k] = P.aux[(size_t)(n * V + v) * 8 + k];
+  }
+  __syncthreads();
+  const int node = blockIdx.x * blockDim.x + tid;
+  if (node >= P.nx * P.ny) return;
+  const int jy = node / P.nx, jx = node % P.nx;
+  const int col = (jx - LAT_LO) * SX, row = (jy - LAT_LO) * SY;
+  const double xd = P.Wo > 1 ? -1.0 + 2.0 * (double)col / (double)(P.Wo - 1) : -1.0;
+  const double yd = P.Ho > 1 ? -1.0 + 2.0 * (double)row / (double)(P.Ho - 1) : -1.0;
+  const float xt = (float)xd, yt = (float)yd;
+  double ax = aff[0] + aff[1] * xd + aff[2] * yd;
+  double ay = aff[3] + aff[4] * xd + aff[5] * yd;
+#pragma unroll 9
+  for (int i = 0; i < SS2_NPT; ++i) {
+    const float2 c = cxy[i];
+    const float dx = xt - c.x, dy = yt - c.y;
+    const float d2 = fmaf(dy, dy, dx * dx);
+    const float f = d2 >= P.R2 ? d2 * logf(d2 + 1e-6f) : blend_poly(d2, P.R2, P.p0, P.p1, P.p2, P.p3);
+    const double2 w = cw[i];
+    ax = fma(w.x, (double)f, ax);
+    ay = fma(w.y, (double)f, ay);
+  }
+  const double px = (ax + 1.0) * (double)P.half_w - ((double)pred[0] * col + (double)pred[1] * row + (double)pred[2]);
+  const double py = (ay + 1.0) * (double)P.half_h - ((double)pred[3] * col + (double)pred[4] * row + (double)pred[5]);
+  const_cast<float2*>(P.nodes)[((size_t)n * P.ny * P.nx + node) * V + v] = make_float2((float)px, (float)py);
+}
+
+// quintic Lagrange weights for nodes at -2..3 and t = k/S, k = 0..S-1
+struct LagrangeTable { float w[16][8]; };
+__constant__ LagrangeTable c_lag[4];  // spacing 6, 8, 12, 16
+__host__ __device__ constexpr int lag_idx(int S) { return S == 6 ? 0 : S == 8 ? 1 : S == 12 ? 2 : 3; }
+
+// base + off*4 as ONE IMAD.WIDE.U32 (the compiler's generic 64-bit indexing costs 4-5 instructions)
+__device__ __forceinline__ const float* f32_at(const float* base, unsigned off) {
+  unsigned long long a;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(off), "l"(reinterpret_cast<unsigned long long>(base)));
+  return reinterpret_cast<const float*>(a);
+}
+__device__ __forceinline__ float lg2_approx(float x) {  // x is a normal positive number here
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// a*(a/s) + b*(b/s), s = a+b+1e-6 (test_online_tra.py:142) as (a*a + b*b) * (1/s); MUFU.RCP is
+// accurate to ~1 ulp, i.e. <= 3e-5 grey levels here
+__device__ __forceinline__ float blend_avg_fast(float a, float b) {
+  const float s = (a + b) + 1e-6f;
+  return fmaf(b, b, a * a) * rcp_approx(s);
+}
+
+// node-column slots a tile of LAT_THREADS pixel columns can touch
+template <int SX> struct LatCols { static constexpr int value = (LAT_THREADS + SX - 1) / SX + LAT_TAPS; };
+
+// IW, IH > 0: source image size known at compile time (all 12 tap addresses of a view become
+// ONE 64-bit pointer + immediate offsets); 0 = runtime size.
+#ifndef LAT_MINB
+#define LAT_MINB 8
+#endif
+#ifndef LAT_PREFETCH
+#define LAT_PREFETCH 2  // source rows ahead pulled towards L1 (0/undefined: off)
+#endif
+#ifndef LAT_NCELL
+#define LAT_NCELL 4
+#endif
+// LAT_NCELL: lattice cell rows per CTA: the tile is LAT_THREADS x (LAT_NCELL*SY) canvas pixels
+
+template <int V, int C, int MODE, bool BLEND, int SX, int SY, int IW, int IH>
+__global__ void __launch_bounds__(LAT_THREADS, LAT_MINB)
+tps_warp_lattice_kernel(WarpParams P) {
+  constexpr int NCOL = LatCols<SX>::value;
+  __shared__ float4 near_list[V * SS2_NPT];  // (cx, cy, wx_px*ln2, wy_px*ln2), view-0 entries first
+  __shared__ int warp_cnt[LAT_THREADS / 32][2];
+  __shared__ float s_pred[V][6];
+  __shared__ __align__(16) float2 ysm[SY][NCOL][V];  // y-contracted residuals of the current cell row
+  const int n = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int col0 = blockIdx.x * LAT_THREADS, row00 = blockIdx.y * (LAT_NCELL * SY);
+  const int jx0 = col0 / SX;  // node slot of the first cell (slot s <-> lattice column s - LAT_LO)
+  const int W = IW > 0 ? IW : P.W, H = IH > 0 ? IH : P.H;
+  // ---- near list: control points whose disc s < R2 touches this tile (deterministic order)
+  {
+    float4 ent = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool hit = false;
+    const int pv = tid / SS2_NPT, pi = tid - pv * SS2_NPT;
+    if (tid < V * SS2_NPT) {
+      const float x_lo = fmaf(P.stepx, (float)col0, -1.0f), x_hi = fmaf(P.stepx, (float)min(col0 + LAT_THREADS - 1, P.Wo - 1), -1.0f);
+      const float y_lo = fmaf(P.stepy, (float)row00, -1.0f), y_hi = fmaf(P.stepy, (float)min(row00 + LAT_NCELL * SY - 1, P.Ho - 1), -1.0f);
+      const float2 c = *reinterpret_cast<const float2*>(P.source + ((size_t)(n * V + pv) * SS2_NPT + pi) * 2);
+      const float* t = P.T + (size_t)(n * V + pv) * 2 * SS2_NSYS;
+      const float ddx = fmaxf(fmaxf(x_lo - c.x, c.x - x_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
+      hit = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
+      if (hit) ent = make_float4(c.x, c.y, t[3 + pi] * (P.half_w * LN2F), t[SS2_NSYS + 3 + pi] * (P.half_h * LN2F));
+    }
+    const unsigned m_all = __ballot_sync(0xffffffffu, hit), m_v0 = __ballot_sync(0xffffffffu, hit && pv == 0);
+    if (lane == 0) { warp_cnt[wid][0] = __popc(m_all); warp_cnt[wid][1] = __popc(m_v0); }
+    if (tid < V * 6) s_pred[tid / 6][tid % 6] = P.aux[(size_t)(n * V + tid / 6) * 8 + tid % 6];
+    __syncthreads();
+    int off = 0;
+#pragma unroll
+    for (int w = 0; w < LAT_THREADS / 32; ++w)
+      if (w < wid) off += warp_cnt[w][0];
+    if (hit) near_list[off + __popc(m_all & ((1u << lane) - 1u))] = ent;
+  }
+  int n0 = 0, n_all = 0;
+#pragma unroll
+  for (int w = 0; w < LAT_THREADS / 32; ++w) { n_all += warp_cnt[w][0]; n0 += warp_cnt[w][1]; }
+  // ---- per-column constants
+  const int col = min(col0 + tid, P.Wo - 1);
+  const bool active = col0 + tid < P.Wo;
+  const int cxi = col / SX, rx = col - cxi * SX, js = cxi - jx0;  // this column's first node slot in ysm
+  float lx[LAT_TAPS];
+#pragma unroll
+  for (int a = 0; a < LAT_TAPS; ++a) lx[a] = c_lag[lag_idx(SX)].w[rx][a];
+  const float colf = (float)col;
+  float pcol[V][2], prow[V][2];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    pcol[v][0] = fmaf(s_pred[v][0], colf, s_pred[v][2]);
+    pcol[v][1] = fmaf(s_pred[v][3], colf, s_pred[v][5]);
+    prow[v][0] = s_pred[v][1];
+    prow[v][1] = s_pred[v][4];
+  }
+  const float xt = fmaf(P.stepx, colf, -1.0f);
+  // x extent of this warp's 32 columns, for the per-warp candidate culling
+  const float wx_lo = fmaf(P.stepx, (float)min(col0 + wid * 32, P.Wo - 1), -1.0f);
+  const float wx_hi = fmaf(P.stepx, (float)min(col0 + wid * 32 + 31, P.Wo - 1), -1.0f);
+  const unsigned W1 = (unsigned)(W - 1), H1 = (unsigned)(H - 1);
+  const unsigned oplane = (unsigned)(P.Ho * P.Wo);
+  const unsigned iplane = (unsigned)(H * W);
+  // per-view frame bases (64-bit once); everything below indexes them with 32-bit offsets
+  const float* imgv[V];
+  const float* outv[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    imgv[v] = P.img[BLEND ? v : 0] + (size_t)(BLEND ? n : n * V + v) * C * iplane;
+    outv[v] = P.out + (size_t)(BLEND ? n : n * V + v) * C * oplane;
+  }
+  const bool cull = n_all <= 32;  // one candidate per lane; longer lists (never seen) are not culled
+
+  for (int cell = 0; cell < LAT_NCELL; ++cell) {
+    const int row0 = row00 + cell * SY;
+    if (row0 >= P.Ho) break;  // CTA-uniform
+    const int cyi = blockIdx.y * LAT_NCELL + cell;
+    __syncthreads();  // previous cell's readers of ysm are done (also orders near_list on the first pass)
+    // ---- y contraction of the tile's node columns: ysm[r][j] = sum_b Ly[r][b] * node[cyi + b][jx0 + j]
+    for (int item = tid; item < SY * NCOL; item += LAT_THREADS) {
+      const int r = item / NCOL, j = item - r * NCOL;
+      if (jx0 + j < P.nx) {
+        const float2* nd = P.nodes + (((size_t)n * P.ny + cyi) * P.nx + (jx0 + j)) * V;
+        float acc[V][2];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v][0] = acc[v][1] = 0.f;
+#pragma unroll
+        for (int b = 0; b < LAT_TAPS; ++b) {
+          const float w = c_lag[lag_idx(SY)].w[r][b];
+          if (V == 2) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(nd + (size_t)b * P.nx * V));
+            acc[0][0] = fmaf(w, q.x, acc[0][0]); acc[0][1] = fmaf(w, q.y, acc[0][1]);
+            acc[V - 1][0] = fmaf(w, q.z, acc[V - 1][0]); acc[V - 1][1] = fmaf(w, q.w, acc[V - 1][1]);
+          } else {
+            const float2 q = __ldg(nd + (size_t)b * P.nx * V);
+            acc[0][0] = fmaf(w, q.x, acc[0][0]); acc[0][1] = fmaf(w, q.y, acc[0][1]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) ysm[r][j][v] = make_float2(acc[v][0], acc[v][1]);
+      }
+    }
+    __syncthreads();
+    // ---- per-warp culling of the near list against this warp's 32 x SY pixel block
+    unsigned cand = 0;
+    if (n_all > 0) {
+      if (cull) {
+        bool keep = false;
+        if (lane < n_all) {
+          const float4 c = near_list[lane];
+          const float y_lo = fmaf(P.stepy, (float)row0, -1.0f), y_hi = fmaf(P.stepy, (float)min(row0 + SY - 1, P.Ho - 1), -1.0f);
+          const float ddx = fmaxf(fmaxf(wx_lo - c.x, c.x - wx_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
+          keep = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
+        }
+        cand = __ballot_sync(0xffffffffu, keep);
+      } else {
+        cand = 0xffffffffu;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SY; ++r) {
+      const int row = row0 + r;
+      if (row >= P.Ho) break;
+      const float rowf = (float)row;
+      float px[V], py[V];
+      {
+        float ax[V], ay[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) ax[v] = ay[v] = 0.f;
+#pragma unroll
+        for (int a = 0; a < LAT_TAPS; ++a) {
+          if (V == 2) {
+            const float4 q = *reinterpret_cast<const float4*>(&ysm[r][js + a][0]);
+            ax[0] = fmaf(lx[a], q.x, ax[0]); ay[0] = fmaf(lx[a], q.y, ay[0]);
+            ax[V - 1] = fmaf(lx[a], q.z, ax[V - 1]); ay[V - 1] = fmaf(lx[a], q.w, ay[V - 1]);
+          } else {
+            const float2 q = ysm[r][js + a][0];
+            ax[0] = fmaf(lx[a], q.x, ax[0]); ay[0] = fmaf(lx[a], q.y, ay[0]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          px[v] = ax[v] + fmaf(prow[v][0], rowf, pcol[v][0]);
+          py[v] = ay[v] + fmaf(prow[v][1], rowf, pcol[v][1]);
+        }
+      }
+      // near-field corrections (branch-free: s is clamped to R2, where psi vanishes)
+      if (cand != 0u) {
+        const float yt = fmaf(P.stepy, rowf, -1.0f);
+        if (cull) {
+          unsigned m = cand;
+#pragma unroll 1
+          while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const float4 c = near_list[k];
+            const float dx = xt - c.x, dy = yt - c.y;
+            const float s = fminf(fmaf(dy, dy, dx * dx), P.R2);
+            // psi/ln2 = s*lg2(s+eps) - P(s)/ln2 (q0..q3 = P/ln2; the weights carry the ln2)
+            const float psi = fmaf(s, lg2_approx(s + 1e-6f), -blend_poly(s, P.R2, P.q0, P.q1, P.q2, P.q3));
+            if (V == 1 || k < n0) { px[0] = fmaf(c.z, psi, px[0]); py[0] = fmaf(c.w, psi, py[0]); }
+            else { px[V - 1] = fmaf(c.z, psi, px[V - 1]); py[V - 1] = fmaf(c.w, psi, py[V - 1]); }
+          }
+        } else {
+#pragma unroll 1
+          for (int k = 0; k < n_all; ++k) {
+            const float4 c = near_list[k];
+            const float dx = xt - c.x, dy = yt - c.y;
+            const float s = fminf(fmaf(dy, dy, dx * dx), P.R2);
+            const float psi = fmaf(s, lg2_approx(s + 1e-6f), -blend_poly(s, P.R2, P.q0, P.q1, P.q2, P.q3));
+            if (V == 1 || k < n0) { px[0] = fmaf(c.z, psi, px[0]); py[0] = fmaf(c.w, psi, py[0]); }
+            else { px[V - 1] = fmaf(c.z, psi, px[V - 1]); py[V - 1] = fmaf(c.w, psi, py[V - 1]); }
+          }
+        }
+      }
+      float res[V][C];
+      if (MODE == SS2_MODE_NORMAL) {
+        // Phase A: tap weights and addresses of every view (branch-free; an out-of-image sample
+        // gets zero weights and reads the frame's first pixel).  Phase B: all loads of all views
+        // back to back (a view no lane of the warp sees is skipped).  Phase C: the FMAs.
+        float wq[V][4];
+        const float* tp[V];
+        bool anyv[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int xi = __float2int_rd(px[v]), yi = __float2int_rd(py[v]);
+          const bool inb = (unsigned)xi < W1 && (unsigned)yi < H1;  // no tap is clamped: plain bilinear == _interpolate
+          const float fx0 = px[v] - (float)xi, fy = py[v] - (float)yi;
+          const float fx = inb ? fx0 : 0.0f, gx = inb ? 1.0f - fx0 : 0.0f, gy = 1.0f - fy;
+          wq[v][0] = gx * gy; wq[v][1] = gx * fy; wq[v][2] = fx * gy; wq[v][3] = fx * fy;
+          tp[v] = f32_at(imgv[v], inb ? (unsigned)(yi * W + xi) : 0u);
+          anyv[v] = __any_sync(0xffffffffu, inb);
+#if LAT_PREFETCH > 0
+          // the next canvas row samples (about) one source row further down: pull that row
+          // towards L1 now so that its demand loads hit
+          if (anyv[v] && inb && (unsigned)(yi + LAT_PREFETCH) < H1) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(f32_at(tp[v], c * iplane + LAT_PREFETCH * W)));
+          }
+#endif
+        }
+        float tap[V][C][4];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          if (anyv[v]) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              if (IW > 0 && IH > 0 && (size_t)(C - 1) * IW * IH * 4 + (size_t)IW * 4 + 4 < (1u << 23)) {
+                const float* p = tp[v] + c * (IW * IH);  // compile-time offsets off ONE pointer
+                tap[v][c][0] = __ldg(p); tap[v][c][2] = __ldg(p + 1);
+                tap[v][c][1] = __ldg(p + IW); tap[v][c][3] = __ldg(p + IW + 1);
+              } else {
+                const float* p0 = c == 0 ? tp[v] : f32_at(tp[v], c * iplane);
+                const float* p1 = f32_at(tp[v], c * iplane + W);
+                tap[v][c][0] = __ldg(p0); tap[v][c][2] = __ldg(p0 + 1);
+                tap[v][c][1] = __ldg(p1); tap[v][c][3] = __ldg(p1 + 1);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            res[v][c] = 0.0f;
+            if (anyv[v])
+              res[v][c] = fmaf(wq[v][3], tap[v][c][3], fmaf(wq[v][2], tap[v][c][2], fmaf(wq[v][1], tap[v][c][1], wq[v][0] * tap[v][c][0])));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) sample_fast<C>(imgv[v], H, W, px[v], py[v], res[v]);
+      }
+      if (active) {
+        const unsigned opix = (unsigned)(row * P.Wo + col);
+        if (BLEND) {
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+            __stcs(const_cast<float*>(f32_at(outv[0], opix + c * oplane)), blend_avg_fast(res[0][c], res[V - 1][c]));
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) __stcs(const_cast<float*>(f32_at(outv[v], opix + c * oplane)), res[v][c]);
+          }
+        }
+      }
+    }
+  }
+}
+
 static inline float linstep(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 
+// lattice configuration: spacing (SX, SY) in canvas pixels and near radius R (normalised)
+struct LatticeConfig { int SX, SY; float R; bool ok; };
+
+// The interpolation error is governed by the lattice step in NORMALISED canvas units,
+// hx = SX*2/(Wo-1), hy = SY*2/(Ho-1): take the coarsest instantiated spacing with h <= 0.0185
+// (12x6 on a 741x1748 canvas: hx 0.0137, hy 0.0162), near radius R = 4.3*h.  Canvases too small
+// for that (h would exceed the bound even at the finest spacing) use the EXACT evaluation.
+static LatticeConfig lattice_config(int Ho, int Wo) {
+  LatticeConfig c;
+  const double hmax = 0.0185, ux = 2.0 / (Wo > 1 ? Wo - 1 : 1), uy = 2.0 / (Ho > 1 ? Ho - 1 : 1);
+  c.SX = 16 * ux <= hmax ? 16 : (12 * ux <= hmax ? 12 : 8);
+  c.SY = 8 * uy <= hmax ? 8 : 6;
+  const char* e = getenv("SS2_TPS_S");
+  if (e && atoi(e) > 100) { c.SX = atoi(e) / 10; c.SY = atoi(e) % 10; }   // e.g. 168, 126, 88
+  const double h = c.SX * ux > c.SY * uy ? c.SX * ux : c.SY * uy;
+  c.ok = h <= hmax * 1.0001 || e;
+  c.R = (float)(4.3 * h);
+  e = getenv("SS2_TPS_R");
+  if (e) c.R = (float)atof(e);
+  return c;
+}
+
+static void lagrange_table(int S, LagrangeTable* t) {
+  const double xs[LAT_TAPS] = {-2, -1, 0, 1, 2, 3};
+  for (int k = 0; k < 16; ++k) {
+    const double u = k < S ? (double)k / S : 0.0;
+    for (int j = 0; j < 8; ++j) {
+      double w = 0.0;
+      if (j < LAT_TAPS) {
+        w = 1.0;
+        for (int m = 0; m < LAT_TAPS; ++m)
+          if (m != j) w *= (u - xs[m]) / (xs[j] - xs[m]);
+      }
+      t->w[k][j] = (float)w;
+    }
+  }
+}
+
+bool tps_lattice_supported(int Ho, int Wo) { return Ho > 0 && Wo > 0 && lattice_config(Ho, Wo).ok; }
+
+// workspace of the lattice path for `bn` (frame, view) systems on a Ho x Wo canvas
+size_t tps_lattice_workspace_floats(int bn, int Ho, int Wo) {
+  const LatticeConfig c = lattice_config(Ho, Wo);
+  const size_t nx = (size_t)(Wo - 1) / c.SX + LAT_TAPS, ny = (size_t)(Ho - 1) / c.SY + LAT_TAPS;
+  return (size_t)bn * nx * ny * 2;
+}
+
+template <int V, int C, bool BLEND>
+static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, float* d_nodes, cudaStream_t st) {
+  const LatticeConfig cfg = lattice_config(P.Ho, P.Wo);
+  P.nx = (P.Wo - 1) / cfg.SX + LAT_TAPS;
+  P.ny = (P.Ho - 1) / cfg.SY + LAT_TAPS;
+  P.nodes = reinterpret_cast<const float2*>(d_nodes);
+  const double R2 = (double)cfg.R * cfg.R, e = 1e-6, L = log(R2 + e);
+  P.R2 = (float)R2;
+  P.p0 = (float)(R2 * L);
+  P.p1 = (float)(L + R2 / (R2 + e));
+  P.p2 = (float)(0.5 * (1.0 / (R2 + e) + e / ((R2 + e) * (R2 + e))));
+  P.p3 = (float)((-1.0 / ((R2 + e) * (R2 + e)) - 2.0 * e / ((R2 + e) * (R2 + e) * (R2 + e))) / 6.0);
+  const double ln2 = 0.69314718055994530942;
+  P.q0 = (float)(R2 * L / ln2);
+  P.q1 = (float)((L + R2 / (R2 + e)) / ln2);
+  P.q2 = (float)(0.5 * (1.0 / (R2 + e) + e / ((R2 + e) * (R2 + e))) / ln2);
+  P.q3 = (float)((-1.0 / ((R2 + e) * (R2 + e)) - 2.0 * e / ((R2 + e) * (R2 + e) * (R2 + e))) / 6.0 / ln2);
+  if (!ctx->lag_tables_ready) {
+    // one-time upload of the interpolation weight tables of this context's device
+    LagrangeTable t[4];
+    const int S[4] = {6, 8, 12, 16};
+    for (int i = 0; i < 4; ++i) lagrange_table(S[i], &t[i]);
+    SS2_CUDA(ctx, cudaMemcpyToSymbol(c_lag, t, sizeof(t)));
+    ctx->lag_tables_ready = true;
+  }
+  const int nnodes = P.nx * P.ny;
+  tps_nodes_kernel<V><<<dim3(cdiv(nnodes, 128), V, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY);
+  SS2_LAUNCH_CHECK(ctx);
+  dim3 grid(cdiv(P.Wo, LAT_THREADS), cdiv(P.Ho, cfg.SY * LAT_NCELL), nframes);
+  // source-size specialisations of the production (fused, NORMAL) kernel: 720p and 1080p
+  const int spec = (BLEND && mode == SS2_MODE_NORMAL) ? ((P.W == 1280 && P.H == 720) ? 1 : (P.W == 1920 && P.H == 1080) ? 2 : 0) : 0;
+#define LAT_CASE(SXV, SYV)                                                                                   \
+  if (cfg.SX == SXV && cfg.SY == SYV) {                                                                      \
+    if (spec == 1) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, BLEND ? 1280 : 0, BLEND ? 720 : 0><<<grid, LAT_THREADS, 0, st>>>(P); \
+    else if (spec == 2) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, BLEND ? 1920 : 0, BLEND ? 1080 : 0><<<grid, LAT_THREADS, 0, st>>>(P); \
+    else if (mode == SS2_MODE_NORMAL) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, 0, 0><<<grid, LAT_THREADS, 0, st>>>(P); \
+    else tps_warp_lattice_kernel<V, C, SS2_MODE_FAST, BLEND, SXV, SYV, 0, 0><<<grid, LAT_THREADS, 0, st>>>(P);  \
+  }
+  LAT_CASE(16, 8) LAT_CASE(16, 6) LAT_CASE(12, 8) LAT_CASE(12, 6) LAT_CASE(8, 8) LAT_CASE(8, 6)
+#undef LAT_CASE
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+
 int tps_warp_launch(ss2_ctx* ctx, const float* d_U, const float* d_source, const float* d_T, int bn, int C,
-                    int H, int W, int Ho, int Wo, int mode, int tps, float* d_out, cudaStream_t st) {
+                    int H, int W, int Ho, int Wo, int mode, int tps, float* d_out, cudaStream_t st,
+                    const float* d_aux, float* d_nodes) {
   if (bn <= 0 || Ho <= 0 || Wo <= 0) return SS2_OK;
   WarpParams P;
   P.img[0] = d_U; P.img[1] = d_U;
   P.source = d_source; P.T = d_T; P.out = d_out;
   P.H = H; P.W = W; P.Ho = Ho; P.Wo = Wo;
   P.stepx = linstep(Wo); P.stepy = linstep(Ho);
+  P.aux = d_aux;
+  P.half_w = mode == SS2_MODE_NORMAL ? 0.5f * W : 0.5f * (W - 1);
+  P.half_h = mode == SS2_MODE_NORMAL ? 0.5f * H : 0.5f * (H - 1);
+  if (tps == SS2_TPS_LATTICE && d_aux && d_nodes && C == 3 && tps_lattice_supported(Ho, Wo))
+    return lattice_launch<1, 3, false>(ctx, P, bn, mode, d_nodes, st);
   dim3 grid(cdiv(Wo, TX), cdiv(Ho, TILE_H), bn), block(TX, TY);
-  (void)tps;
 #define WARP_CASE(CC)                                                                              \
   if (C == CC) {                                                                                   \
     if (mode == SS2_MODE_NORMAL) tps_warp_exact_kernel<1, CC, SS2_MODE_NORMAL, false><<<grid, block, 0, st>>>(P); \
@@ -350,8 +879,6 @@ int tps_warp_launch(ss2_ctx* ctx, const float* d_U, const float* d_source, const
 #undef WARP_CASE
   // other channel counts: one plane at a time
   for (int c = 0; c < C; ++c) {
-    // planes of different batch entries are C*H*W apart, which the kernel's indexing assumes
-    // to be contiguous - so only C<=4 is vectorised; fall back per (b, c).
     for (int b = 0; b < bn; ++b) {
       WarpParams Q = P;
       Q.img[0] = Q.img[1] = d_U + ((size_t)b * C + c) * H * W;
@@ -369,20 +896,29 @@ int tps_warp_launch(ss2_ctx* ctx, const float* d_U, const float* d_source, const
 
 int tps_warp_blend_launch(ss2_ctx* ctx, const float* d_img1, const float* d_img2, const float* d_source,
                           const float* d_T, int nframes, int H, int W, int Ho, int Wo, int mode, int tps,
-                          float* d_out, cudaStream_t st) {
+                          float* d_out, cudaStream_t st, const float* d_aux, float* d_nodes) {
   if (nframes <= 0 || Ho <= 0 || Wo <= 0) return SS2_OK;
   WarpParams P;
   P.img[0] = d_img1; P.img[1] = d_img2;
   P.source = d_source; P.T = d_T; P.out = d_out;
   P.H = H; P.W = W; P.Ho = Ho; P.Wo = Wo;
   P.stepx = linstep(Wo); P.stepy = linstep(Ho);
+  P.aux = d_aux;
+  P.half_w = mode == SS2_MODE_NORMAL ? 0.5f * W : 0.5f * (W - 1);
+  P.half_h = mode == SS2_MODE_NORMAL ? 0.5f * H : 0.5f * (H - 1);
+  // algorithmic bytes: both source frames read once, the fused frame written once
+  const double bytes = (double)nframes * (2.0 * 3 * H * W + 3.0 * Ho * Wo) * 4.0;
+  if (tps == SS2_TPS_LATTICE && d_aux && d_nodes && tps_lattice_supported(Ho, Wo)) {
+    ss2_prof_begin(ctx, SS2_PROF_WARP, st);
+    int rc = lattice_launch<2, 3, true>(ctx, P, nframes, mode, d_nodes, st);
+    ss2_prof_end(ctx, SS2_PROF_WARP, st, bytes);
+    return rc;
+  }
   dim3 grid(cdiv(Wo, TX), cdiv(Ho, TILE_H), nframes), block(TX, TY);
-  (void)tps;
   ss2_prof_begin(ctx, SS2_PROF_WARP, st);
   if (mode == SS2_MODE_NORMAL) tps_warp_exact_kernel<2, 3, SS2_MODE_NORMAL, true><<<grid, block, 0, st>>>(P);
   else tps_warp_exact_kernel<2, 3, SS2_MODE_FAST, true><<<grid, block, 0, st>>>(P);
-  // algorithmic bytes: both source frames read once, the fused frame written once
-  ss2_prof_end(ctx, SS2_PROF_WARP, st, (double)nframes * (2.0 * 3 * H * W + 3.0 * Ho * Wo) * 4.0);
+  ss2_prof_end(ctx, SS2_PROF_WARP, st, bytes);
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }

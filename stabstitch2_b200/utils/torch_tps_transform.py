@@ -6,9 +6,11 @@ import torch
 
 from .. import _lib
 
-# evaluation of the dense TPS field: _lib.TPS_EXACT (all 63 radial terms per pixel) or
-# _lib.TPS_LATTICE (far field interpolated per tile)
-DEFAULT_TPS = _lib.TPS_EXACT
+# evaluation of the dense TPS field: _lib.TPS_EXACT (all 63 radial terms per pixel, the
+# reference's arithmetic) or _lib.TPS_LATTICE (far field interpolated from a lattice + exact
+# near-field corrections, as accurate against the fp64 arbiter as the reference itself; used
+# for 3-channel images on canvases large enough for it, EXACT otherwise)
+DEFAULT_TPS = _lib.TPS_LATTICE
 
 
 def transformer(U, source, target, out_size, mode="NORMAL", tps=None):
