@@ -35,7 +35,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--frames", type=int, default=32, help="frame pairs per step per GPU")
@@ -65,12 +65,16 @@ class ClockSampler:
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
+
+    def mark(self):
+        """samples before this point (warm-up) are not part of the timed region"""
+        self.first = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -91,7 +95,7 @@ class ClockSampler:
             self.proc.kill()
         self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[self.first:] or self.lines[-1:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -236,14 +240,17 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi's start-up (NVML init) briefly contends with kernel launches: start it before the
+    # warm-up so that only its periodic samples fall into the timed region
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         fused = step()
     barrier()
     Ho, Wo = int(fused.shape[2]), int(fused.shape[3])
-
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     ctx.launch_count(reset=True)
     ctx.profile_enable(_lib.PROF_WARP, True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -109,6 +109,18 @@ int ss2_cost_volume_nhwc(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int
 int ss2_ccl_nhwc(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H, int W, int C,
                  float* d_flow, void* stream);
 
+/* ---- convolution primitive --------------------------------------------------------------- */
+/* nn.Conv2d / nn.Conv3d (bias optional, + optional residual add and ReLU) on NHWC / NDHWC fp32
+ * activations - the layer type all three networks are built from (spatial_network.py:147-259,
+ * temporal_network.py:65-104, smooth_network.py:124-131).  d_in [B,D,H,W,Cin] (Cin % 4 == 0),
+ * h_weight HOST [Cout,Cin,(KD,)KH,KW] (reference layout), h_bias HOST [Cout] or NULL,
+ * d_residual [B,Do,Ho,Wo,Cout] or NULL -> d_out [B,Do,Ho,Wo,Cout].  use_tc != 0 runs the tcgen05
+ * tensor-core kernel (needs Cin % 32 == 0 and Cout % 4 == 0), 0 the exact-fp32 SIMT kernel.
+ * Synchronous (packs the filter on every call): a test / reuse entry, not the hot path. */
+int ss2_conv_nhwc(ss2_ctx* ctx, const float* d_in, int B, int D, int H, int W, int Cin, const float* h_weight,
+                  const int64_t* wshape, int wndim, const float* h_bias, int stride, int pad, int pad_d, int relu,
+                  const float* d_residual, int use_tc, float* d_out, void* stream);
+
 /* ---- networks ------------------------------------------------------------------------- */
 /* SpatialNet.forward, spatial_network.py:276: img1,img2 [bs,3,360,480] ->
  * offset_1 [bs,8], offset_2_ref [bs,126], offset_2_tgt [bs,126] */

@@ -35,6 +35,7 @@ SIGNATURES = {
     "ss2_tps_warp_blend_avg": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ss2_cost_volume_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ss2_ccl_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ss2_conv_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, ctypes.POINTER(_i64), _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "ss2_spatial_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "ss2_build_spatial": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "ss2_spatial_tail": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
@@ -142,3 +143,31 @@ def ptr(t):
 
 def cur_stream():
     return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def conv_nhwc(x, weight, bias=None, stride=1, pad=0, pad_d=0, relu=False, residual=None, use_tc=True):
+    """ss2_conv_nhwc: x [B,(D,)H,W,Cin] CUDA fp32 channels-last, weight [Cout,Cin,(KD,)KH,KW] (any device),
+    -> [B,(Do,)Ho,Wo,Cout].  Test / reuse entry for the convolution kernels."""
+    ctx = context()
+    x = dev_f32(x)
+    three_d = weight.dim() == 5
+    if not three_d:
+        x5 = x.unsqueeze(1)
+    else:
+        x5 = x
+    B, D, H, W, Cin = x5.shape
+    wh = weight.detach().to("cpu", torch.float32).contiguous()
+    bh = bias.detach().to("cpu", torch.float32).contiguous() if bias is not None else None
+    Cout = wh.shape[0]
+    KD = wh.shape[2] if three_d else 1
+    KH, KW = wh.shape[-2], wh.shape[-1]
+    Do = (D + 2 * pad_d - KD) + 1
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    out = torch.empty(B, Do, Ho, Wo, Cout, device=x.device, dtype=torch.float32)
+    res = dev_f32(residual) if residual is not None else None
+    shape = (ctypes.c_int64 * wh.dim())(*wh.shape)
+    ctx.check(ctx.lib.ss2_conv_nhwc(ctx.handle, ptr(x5), B, D, H, W, Cin, _vp(wh.data_ptr()), shape, wh.dim(),
+                                    _vp(bh.data_ptr()) if bh is not None else _vp(0), stride, pad, pad_d,
+                                    1 if relu else 0, ptr(res), 1 if use_tc else 0, ptr(out), cur_stream()))
+    return out if three_d else out.squeeze(1)

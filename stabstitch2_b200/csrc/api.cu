@@ -105,6 +105,8 @@ int ss2_create(int device, ss2_ctx** out) {
   c->device = device;
   const char* env = getenv("SS2_USE_TC");
   if (env) c->use_tc = atoi(env);
+  env = getenv("SS2_TC_PASSES");
+  if (env) c->tc_passes = atoi(env) == 1 ? 1 : 3;
   *out = c;
   return SS2_OK;
 }
@@ -212,7 +214,9 @@ int ss2_cost_volume_nhwc(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int
   if (!ctx) return SS2_ERR_INVALID;
   if (B < 0 || H <= 0 || W <= 0 || sr < 0 || (B > 0 && (!d_x1 || !d_x2 || !d_out)))
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_cost_volume_nhwc: bad arguments");
-  return cost_volume_launch(ctx, d_x1, d_x2, B, H, W, C, sr, CP, d_out, (cudaStream_t)stream);
+  ActRef o;
+  o.v = d_out;
+  return cost_volume_launch(ctx, d_x1, d_x2, B, H, W, C, sr, CP, o, (cudaStream_t)stream);
 }
 
 int ss2_ccl_nhwc(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H, int W, int C, float* d_flow,

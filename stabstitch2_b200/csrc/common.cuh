@@ -31,7 +31,17 @@ struct ConvLayer {
   int KD = 1, KH = 1, KW = 1;
   int sd = 1, sh = 1, sw = 1;  // strides
   int pd = 0, ph = 0, pw = 0;  // paddings
-  void* tmap = nullptr;        // device copy of the CUtensorMap of w (tcgen05 path)
+  // tcgen05 path: K-major filter matrices [CoutP][KD*KH*KW*CinP], hi = rna_tf32(w), lo = w - hi
+  float* wk_hi = nullptr;
+  float* wk_lo = nullptr;
+};
+
+// An activation tensor: plain fp32 values and (for the tensor-core layers that consume it) the
+// split hi = rna_tf32(v), lo = v - hi.  hi/lo may be null.
+struct ActRef {
+  float* v = nullptr;
+  float* hi = nullptr;
+  float* lo = nullptr;
 };
 
 struct ResBlock {
@@ -107,6 +117,7 @@ struct ss2_ctx {
   ProfClass prof[SS2_PROF_COUNT];
   int use_tc = 1;  // tcgen05 implicit-GEMM path for eligible layers
   bool lag_tables_ready = false;
+  int tc_passes = 3;  // 3 = split-TF32 (fp32-grade), 1 = plain TF32
 };
 
 int ss2_fail(ss2_ctx* ctx, int code, const char* fmt, ...);
@@ -144,6 +155,34 @@ static inline T* arena_alloc(ss2_ctx* ctx, size_t n) {
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+#ifdef __CUDACC__
+// hi = rna_tf32(v), lo = v - hi (exact); v == hi + lo
+__device__ __forceinline__ void tf32_split(float v, float* hi, float* lo) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  *hi = __uint_as_float(r);
+  *lo = v - *hi;
+}
+__device__ __forceinline__ void store_split4(const ActRef& o, size_t idx, float4 v) {
+  *reinterpret_cast<float4*>(o.v + idx) = v;
+  if (o.hi) {
+    float4 h, l;
+    tf32_split(v.x, &h.x, &l.x); tf32_split(v.y, &h.y, &l.y); tf32_split(v.z, &h.z, &l.z); tf32_split(v.w, &h.w, &l.w);
+    *reinterpret_cast<float4*>(o.hi + idx) = h;
+    if (o.lo) *reinterpret_cast<float4*>(o.lo + idx) = l;
+  }
+}
+__device__ __forceinline__ void store_split1(const ActRef& o, size_t idx, float v) {
+  o.v[idx] = v;
+  if (o.hi) {
+    float h, l;
+    tf32_split(v, &h, &l);
+    o.hi[idx] = h;
+    if (o.lo) o.lo[idx] = l;
+  }
+}
+#endif
 
 // ---- kernels' host launchers (defined in the .cu files) ------------------------------------
 // tps.cu
@@ -191,21 +230,24 @@ int stable_meshes_launch(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh
                          int img_w, float xmin, float ymin, float out_w, float out_h, float* d_source,
                          float* d_target, cudaStream_t st);
 // conv.cu
-int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_in, int B, int D, int H, int W, float* d_out,
+int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D, int H, int W, const ActRef& out,
                 const float* d_residual, int relu, cudaStream_t st, int groups = 1, size_t w_group_stride = 0);
+bool conv_tc_eligible(const ConvLayer& L);
+int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D, int H, int W, const ActRef& out,
+                   const float* d_residual, int relu, cudaStream_t st);
 void conv_out_dims(const ConvLayer& L, int D, int H, int W, int* Do, int* Ho, int* Wo);
 int maxpool_launch(ss2_ctx* ctx, const float* d_in, int B, int H, int W, int C, int k, int s, int p,
-                   float* d_out, cudaStream_t st);
+                   const ActRef& out, cudaStream_t st);
 int nchw_to_nhwc4_launch(ss2_ctx* ctx, const float* d_in, int B, int C, int H, int W, float* d_out,
                          cudaStream_t st);
 // corr.cu
 int cost_volume_launch(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B, int H, int W, int C, int sr,
-                       int CP, float* d_out, cudaStream_t st);
+                       int CP, const ActRef& out, cudaStream_t st);
 int ccl_launch(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H, int W, int C, float* d_flow,
                cudaStream_t st);
 // smooth.cu
 int smooth_embed_launch(ss2_ctx* ctx, const SmoothWeights& sw, const float* ts1, const float* ts2,
-                        const float* sm1, const float* sm2, int nwin, int zero_first, float* d_hidden, float* d_path1,
+                        const float* sm1, const float* sm2, int nwin, int zero_first, const ActRef& hidden, float* d_path1,
                         float* d_path2, cudaStream_t st);
 int smooth_decode_launch(ss2_ctx* ctx, const SmoothWeights& sw, const float* d_hidden, const float* sm1,
                          const float* sm2, const float* path1, const float* path2, int nwin, float* op1,

@@ -26,6 +26,8 @@ struct ConvParams {
   const float* bias;
   const float* residual;
   float* out;
+  float* out_hi;  // optional tf32 split of the output (for a tensor-core consumer)
+  float* out_lo;
   int B, D, H, W, Cin;       // Cin = padded input channels (multiple of 4)
   int Do, Ho, Wo, Cout, CoutP;
   int KD, KH, KW, sd, sh, sw, pd, ph, pw;
@@ -48,6 +50,8 @@ conv_igemm_kernel(ConvParams P) {
   const float* in = P.in + blockIdx.z * P.in_group_stride;
   const float* wgt = P.w + blockIdx.z * P.w_group_stride;
   float* out = P.out + blockIdx.z * P.out_group_stride;
+  const ActRef oref = {out, P.out_hi ? P.out_hi + blockIdx.z * P.out_group_stride : nullptr,
+                       P.out_lo ? P.out_lo + blockIdx.z * P.out_group_stride : nullptr};
   const float* residual = P.residual ? P.residual + blockIdx.z * P.out_group_stride : nullptr;
 
   // A loader: each thread owns rows (tid/4 + 64*i) and the 4-wide k group (tid%4)
@@ -167,7 +171,6 @@ conv_igemm_kernel(ConvParams P) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) v[q] += __ldg(P.bias + n + q);  // bias is CoutP long
       }
-      float* o = out + (size_t)m * P.Cout + n;
       if (n + 3 < P.Cout && (P.Cout & 3) == 0) {
         if (residual) {
           const float4 r = __ldg(reinterpret_cast<const float4*>(residual + (size_t)m * P.Cout + n));
@@ -177,7 +180,7 @@ conv_igemm_kernel(ConvParams P) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) v[q] = fmaxf(v[q], 0.f);
         }
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        store_split4(oref, (size_t)m * P.Cout + n, make_float4(v[0], v[1], v[2], v[3]));
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -185,7 +188,7 @@ conv_igemm_kernel(ConvParams P) {
             float x = v[q];
             if (residual) x += residual[(size_t)m * P.Cout + n + q];
             if (P.relu) x = fmaxf(x, 0.f);
-            o[q] = x;
+            store_split1(oref, (size_t)m * P.Cout + n + q, x);
           }
         }
       }
@@ -193,13 +196,11 @@ conv_igemm_kernel(ConvParams P) {
   }
 }
 
-int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_in, int B, int D, int H, int W, float* d_out,
-                   const float* d_residual, int relu, cudaStream_t st, bool* handled);
-
-int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_in, int B, int D, int H, int W, float* d_out,
+int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D, int H, int W, const ActRef& out,
                 const float* d_residual, int relu, cudaStream_t st, int groups, size_t w_group_stride) {
   ConvParams P;
-  P.in = d_in; P.w = L.w; P.bias = L.bias; P.residual = d_residual; P.out = d_out;
+  P.in = in.v; P.w = L.w; P.bias = L.bias; P.residual = d_residual; P.out = out.v;
+  P.out_hi = out.hi; P.out_lo = out.lo;
   P.B = B; P.D = D; P.H = H; P.W = W; P.Cin = L.CinP;
   conv_out_dims(L, D, H, W, &P.Do, &P.Ho, &P.Wo);
   P.Cout = L.Cout; P.CoutP = L.CoutP;
@@ -213,11 +214,8 @@ int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_in, int B, int 
   P.out_group_stride = (size_t)P.M * L.Cout;
   if (P.M <= 0) return SS2_OK;
   if ((L.CinP & 3) || (L.CoutP & 63)) return ss2_fail(ctx, SS2_ERR_INVALID, "conv: unpadded layer");
-  if (groups == 1 && ctx->use_tc) {
-    bool handled = false;
-    SS2_TRY(conv_tc_launch(ctx, L, d_in, B, D, H, W, d_out, d_residual, relu, st, &handled));
-    if (handled) return SS2_OK;
-  }
+  if (groups == 1 && ctx->use_tc && in.hi && conv_tc_eligible(L))
+    return conv_tc_launch(ctx, L, in, B, D, H, W, out, d_residual, relu, st);
   ss2_prof_begin(ctx, SS2_PROF_CONV, st);
   if (P.M >= 128 * 148) {
     dim3 grid(cdiv(P.M, 128), L.CoutP / 64, groups);
@@ -236,7 +234,7 @@ int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_in, int B, int 
 // max pooling, NHWC, float4 over channels (C % 4 == 0); floor mode, -inf padding
 // ------------------------------------------------------------------------------------------
 __global__ void maxpool_nhwc_kernel(const float4* __restrict__ in, int B, int H, int W, int C4, int k, int s, int p,
-                                    int Ho, int Wo, float4* __restrict__ out) {
+                                    int Ho, int Wo, ActRef out) {
   const size_t total = (size_t)B * Ho * Wo * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t t = i;
@@ -255,18 +253,17 @@ __global__ void maxpool_nhwc_kernel(const float4* __restrict__ in, int B, int H,
         m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
       }
     }
-    out[i] = m;
+    store_split4(out, i * 4, m);
   }
 }
 
 int maxpool_launch(ss2_ctx* ctx, const float* d_in, int B, int H, int W, int C, int k, int s, int p,
-                   float* d_out, cudaStream_t st) {
+                   const ActRef& out, cudaStream_t st) {
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
   const size_t total = (size_t)B * Ho * Wo * (C / 4);
   if (total == 0) return SS2_OK;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-  maxpool_nhwc_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(d_in), B, H, W, C / 4, k, s, p, Ho,
-                                             Wo, reinterpret_cast<float4*>(d_out));
+  maxpool_nhwc_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(d_in), B, H, W, C / 4, k, s, p, Ho, Wo, out);
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }

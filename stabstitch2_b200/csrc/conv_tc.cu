@@ -1,14 +1,392 @@
-// tcgen05 tensor-core implicit-GEMM convolution (placeholder until the UMMA kernel lands).
+// tcgen05 tensor-core implicit-GEMM convolution for sm_100a (NHWC / NDHWC activations).
+//
+//   out[m][n] = act( sum_k A[m][k] * Wt[n][k] + bias[n] + residual[m][n] )
+//   m = (b, do, ho, wo) output position, k = (kd, kh, kw, cin), n = cout
+//
+// Data path
+//   * A (im2col rows) never exists in memory: for one filter tap and one 32-channel slice the
+//     rows of an output tile (TN images x TT x TH x TW positions, <= 128 rows) are ONE 5-D TMA
+//     box of the activation tensor {C, W, H, D, B} (element strides = conv strides, out-of-range
+//     coordinates zero-filled by the TMA unit = the conv padding), landing in shared memory as a
+//     K-major SWIZZLE_128B tile - exactly the layout the UMMA shared-memory descriptor reads.
+//   * B (weights) is a 2-D TMA box {32 k, 64 cout} of the K-major packed filter matrix.
+//   * D accumulates in TMEM (128 lanes x 64 fp32 columns); one elected thread issues
+//     tcgen05.mma.kind::tf32 (M=128, N=64, K=8), tcgen05.commit releases the smem stage.
+//   * fp32-grade results ("3xTF32"): activations and weights are stored as hi = rna_tf32(v) and
+//     lo = v - hi; D += Ahi*Bhi + Alo*Bhi + Ahi*Blo (error ~2^-21 relative instead of TF32's
+//     2^-11).  NPASS=1 runs plain TF32 (what cuDNN does for the reference's GPU convolutions).
+//   * epilogue: 4 warps tcgen05.ld their 32 TMEM lanes, add bias / residual, ReLU, and store the
+//     row as fp32 plus its (hi, lo) split for the next tensor-core layer.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM lane
+// quarter = warp_id % 4), warp 2 also owns the TMEM allocation.
+//
+// Replaces cuDNN under nn.Conv2d / nn.Conv3d of spatial_network.py:147-259, temporal_network.py:
+// 65-104, smooth_network.py:124-131 and torchvision's BasicBlocks (spatial_network.py:123-139).
+#include <cuda.h>
+
 #include "common.cuh"
 
-int conv_tc_prepare(ss2_ctx* ctx, ConvLayer& L) {
-  (void)ctx; (void)L;
+#define TC_BM 128
+#define TC_BN 64
+#define TC_BK 32
+#define TC_THREADS 192
+// pipeline depth: 2 x 48 KB (split-TF32) / 4 x 24 KB (plain TF32) keeps two CTAs per SM resident,
+// so one CTA's epilogue and pipeline fill overlap the other's main loop
+#ifndef TC_STAGES3
+#define TC_STAGES3 2
+#endif
+#ifndef TC_STAGES1
+#define TC_STAGES1 4
+#endif
+#define TC_A_BYTES (TC_BM * TC_BK * 4)  // 16 KB
+#define TC_B_BYTES (TC_BN * TC_BK * 4)  // 8 KB
+
+struct TcParams {
+  const float* bias;      // [CoutP] or null
+  const float* residual;  // plain fp32 [M][Cout] or null
+  float* out_v;           // plain fp32 [M][Cout]
+  float* out_hi;          // split planes for the next tensor-core layer (may be null)
+  float* out_lo;
+  int B, Do, Ho, Wo, Cout;
+  int TN, TT, TH, TW;      // tile extents (images, depth, rows, cols); rows = TN*TT*TH*TW <= 128
+  int nN, nT, nH, nW;      // tile counts per dimension
+  int KD, KH, KW, nchunk;  // filter taps and CinP/32
+  int sd, sh, sw, pd, ph, pw;
+  int CinP;
+  int relu;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+// rows 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused (=1) for swizzled K-major
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address
+  d |= (uint64_t)1 << 16;                       // leading byte offset (ignored)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset
+  d |= (uint64_t)1 << 46;                       // descriptor version
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float rna_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// instruction descriptor: D fp32, A/B tf32, both K-major, N = 64, M = 128
+__host__ __device__ constexpr uint32_t tc_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+template <int NPASS, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams P) {
+  constexpr int NOPER = NPASS == 3 ? 2 : 1;  // operand planes per matrix (hi [, lo])
+  constexpr int STAGE_BYTES = NOPER * (TC_A_BYTES + TC_B_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int tix = blockIdx.x;
+  const int tw = tix % P.nW; tix /= P.nW;
+  const int th = tix % P.nH; tix /= P.nH;
+  const int tt = tix % P.nT; tix /= P.nT;
+  const int tn = tix;
+  const int w0 = tw * P.TW, h0 = th * P.TH, t0 = tt * P.TT, n0 = tn * P.TN;
+  const int cout0 = blockIdx.y * TC_BN;
+  const int rows = P.TN * P.TT * P.TH * P.TW;
+  const int ntaps = P.KD * P.KH * P.KW;
+  const int niter = ntaps * P.nchunk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TC_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)NOPER * ((uint32_t)rows * TC_BK * 4 + TC_B_BYTES);
+      int it = 0;
+      for (int tap = 0; tap < ntaps; ++tap) {
+        const int kw = tap % P.KW, kh = (tap / P.KW) % P.KH, kd = tap / (P.KW * P.KH);
+        const int cw = w0 * P.sw + kw - P.pw, ch = h0 * P.sh + kh - P.ph, cd = t0 * P.sd + kd - P.pd;
+        for (int ck = 0; ck < P.nchunk; ++ck, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+          uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], tx_bytes);
+          tma_load_5d(st, &tmA_hi, &full_bar[s], ck * TC_BK, cw, ch, cd, n0);
+          tma_load_2d(st + NOPER * TC_A_BYTES, &tmB_hi, &full_bar[s], tap * P.CinP + ck * TC_BK, cout0);
+          if (NPASS == 3) {
+            tma_load_5d(st + TC_A_BYTES, &tmA_lo, &full_bar[s], ck * TC_BK, cw, ch, cd, n0);
+            tma_load_2d(st + NOPER * TC_A_BYTES + TC_B_BYTES, &tmB_lo, &full_bar[s], tap * P.CinP + ck * TC_BK, cout0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      const uint32_t idesc = tc_idesc();
+      for (int it = 0; it < niter; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t b_hi = a_hi + NOPER * TC_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint64_t da = umma_desc_sw128(a_hi + k * 32), db = umma_desc_sw128(b_hi + k * 32);
+          umma_tf32(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if (NPASS == 3) {
+            const uint64_t dal = umma_desc_sw128(a_hi + TC_A_BYTES + k * 32), dbl = umma_desc_sw128(b_hi + TC_B_BYTES + k * 32);
+            umma_tf32(tmem_base, dal, db, idesc, 1u);
+            umma_tf32(tmem_base, da, dbl, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above have read it
+      }
+      umma_commit(&accum_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quarter q = warp % 4 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    mbar_wait(&accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // row -> output position
+    int rr = r;
+    const int wl = rr % P.TW; rr /= P.TW;
+    const int hl = rr % P.TH; rr /= P.TH;
+    const int tl = rr % P.TT; rr /= P.TT;
+    const int nl = rr;
+    const int ow = w0 + wl, oh = h0 + hl, ot = t0 + tl, on = n0 + nl;
+    const bool valid = r < rows && ow < P.Wo && oh < P.Ho && ot < P.Do && on < P.B;
+    const size_t m = (((size_t)on * P.Do + ot) * P.Ho + oh) * P.Wo + ow;
+#pragma unroll
+    for (int half = 0; half < TC_BN / 32; ++half) {
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + half * 32, acc);  // warp-collective
+      if (valid) {
+        const int c0 = cout0 + half * 32;
+        const size_t o = m * P.Cout + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (c0 + j < P.Cout) {
+            float v[4] = {__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3])};
+            if (P.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + j));
+              v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+            }
+            if (P.residual) {
+              const float4 rs = __ldg(reinterpret_cast<const float4*>(P.residual + o + j));
+              v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            *reinterpret_cast<float4*>(P.out_v + o + j) = make_float4(v[0], v[1], v[2], v[3]);
+            if (P.out_hi) {
+              float hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { hi[e] = rna_tf32(v[e]); lo[e] = v[e] - hi[e]; }
+              *reinterpret_cast<float4*>(P.out_hi + o + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_BN));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// activation tensor {C, W, H, D, B} (fp32, innermost first) with a box of one output tile
+static int make_act_map(ss2_ctx* ctx, CUtensorMap* map, const float* base, int C, int W, int H, int D, int B, int bw,
+                        int bh, int bd, int bn, int sw, int sh, int sd) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)D * H * W * C * 4};
+  cuuint32_t box[5] = {TC_BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, (cuuint32_t)bn};
+  cuuint32_t est[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sd, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, est,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return ss2_fail(ctx, SS2_ERR_CUDA, "cuTensorMapEncodeTiled(activations C=%d W=%d H=%d D=%d B=%d box %d,%d,%d,%d stride %d,%d,%d) = %d",
+                    C, W, H, D, B, bw, bh, bd, bn, sw, sh, sd, (int)r);
   return SS2_OK;
 }
 
-int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_in, int B, int D, int H, int W, float* d_out,
-                   const float* d_residual, int relu, cudaStream_t st, bool* handled) {
-  (void)ctx; (void)L; (void)d_in; (void)B; (void)D; (void)H; (void)W; (void)d_out; (void)d_residual; (void)relu; (void)st;
-  *handled = false;
+static int make_weight_map(ss2_ctx* ctx, CUtensorMap* map, const float* base, int Ktot, int CoutP) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)CoutP};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
+  cuuint32_t box[2] = {TC_BK, TC_BN};
+  cuuint32_t est[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, est,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return ss2_fail(ctx, SS2_ERR_CUDA, "cuTensorMapEncodeTiled(weights K=%d N=%d) = %d", Ktot, CoutP, (int)r);
+  return SS2_OK;
+}
+
+// K-major hi/lo filter matrices [CoutP][Ktot] are built at pack time (nets.cu: pack_conv)
+bool conv_tc_eligible(const ConvLayer& L) {
+  return L.wk_hi != nullptr && (L.CinP % TC_BK) == 0 && (L.CoutP % TC_BN) == 0 && (L.Cout % 4) == 0;
+}
+
+static void tile_shape(int B, int Do, int Ho, int Wo, int* TN, int* TT, int* TH, int* TW) {
+  int tw = Wo;
+  if (tw > TC_BM) { const int parts = (Wo + TC_BM - 1) / TC_BM; tw = (Wo + parts - 1) / parts; }
+  int th = TC_BM / tw; if (th > Ho) th = Ho; if (th < 1) th = 1;
+  int tt = TC_BM / (tw * th); if (tt > Do) tt = Do; if (tt < 1) tt = 1;
+  int tn = TC_BM / (tw * th * tt); if (tn > B) tn = B; if (tn < 1) tn = 1;
+  *TN = tn; *TT = tt; *TH = th; *TW = tw;
+}
+
+int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D, int H, int W, const ActRef& out,
+                   const float* d_residual, int relu, cudaStream_t st) {
+  TcParams P;
+  conv_out_dims(L, D, H, W, &P.Do, &P.Ho, &P.Wo);
+  P.B = B; P.Cout = L.Cout; P.CinP = L.CinP;
+  P.KD = L.KD; P.KH = L.KH; P.KW = L.KW; P.nchunk = L.CinP / TC_BK;
+  P.sd = L.sd; P.sh = L.sh; P.sw = L.sw; P.pd = L.pd; P.ph = L.ph; P.pw = L.pw;
+  P.relu = relu; P.bias = L.bias; P.residual = d_residual;
+  P.out_v = out.v; P.out_hi = out.hi; P.out_lo = out.lo;
+  tile_shape(B, P.Do, P.Ho, P.Wo, &P.TN, &P.TT, &P.TH, &P.TW);
+  P.nW = cdiv(P.Wo, P.TW); P.nH = cdiv(P.Ho, P.TH); P.nT = cdiv(P.Do, P.TT); P.nN = cdiv(B, P.TN);
+  const int npass = (ctx->tc_passes == 1 || !in.lo || !L.wk_lo) ? 1 : 3;
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  const int bw = (P.TW - 1) * L.sw + 1, bh = (P.TH - 1) * L.sh + 1, bd = (P.TT - 1) * L.sd + 1;
+  if (bw > 256 || bh > 256 || bd > 256) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_tc: TMA box too large");
+  SS2_TRY(make_act_map(ctx, &mA_hi, in.hi, L.CinP, W, H, D, B, bw, bh, bd, P.TN, L.sw, L.sh, L.sd));
+  SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_hi, L.KD * L.KH * L.KW * L.CinP, L.CoutP));
+  if (npass == 3) {
+    SS2_TRY(make_act_map(ctx, &mA_lo, in.lo, L.CinP, W, H, D, B, bw, bh, bd, P.TN, L.sw, L.sh, L.sd));
+    SS2_TRY(make_weight_map(ctx, &mB_lo, L.wk_lo, L.KD * L.KH * L.KW * L.CinP, L.CoutP));
+  } else {
+    mA_lo = mA_hi; mB_lo = mB_hi;
+  }
+  dim3 grid(P.nW * P.nH * P.nT * P.nN, L.CoutP / TC_BN);
+  const double flops = 2.0 * B * P.Do * P.Ho * P.Wo * (double)L.Cout * L.KD * L.KH * L.KW * L.Cin;
+  ss2_prof_begin(ctx, SS2_PROF_CONV, st);
+  if (npass == 3) {
+    constexpr int STAGES = TC_STAGES3;
+    const size_t smem = (size_t)STAGES * 2 * (TC_A_BYTES + TC_B_BYTES) + 1024;
+    static bool attr3 = false;
+    if (!attr3) { SS2_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<3, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr3 = true; }
+    conv_tc_kernel<3, STAGES><<<grid, TC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  } else {
+    constexpr int STAGES = TC_STAGES1;
+    const size_t smem = (size_t)STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024;
+    static bool attr1 = false;
+    if (!attr1) { SS2_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<1, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr1 = true; }
+    conv_tc_kernel<1, STAGES><<<grid, TC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  }
+  ss2_prof_end(ctx, SS2_PROF_CONV, st, flops);
+  SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }

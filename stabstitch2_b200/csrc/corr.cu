@@ -15,7 +15,7 @@
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 cost_volume_kernel(const float4* __restrict__ x1, const float4* __restrict__ x2, int H, int W, int C4, int sr, int CP,
-                   float* __restrict__ out) {
+                   ActRef out) {
   const int b = blockIdx.y;
   const int pix = blockIdx.x * 8 + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
@@ -26,7 +26,7 @@ cost_volume_kernel(const float4* __restrict__ x1, const float4* __restrict__ x2,
   const float4 a = act ? __ldg(x1 + (img + pix) * C4 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float inv_c = 1.0f / (float)(4 * C4);
   const int k = 2 * sr + 1, nd = k * k;
-  float* o = out + (img + pix) * CP;
+  const size_t o = (img + pix) * CP;
   for (int d0 = 0; d0 < CP; d0 += 32) {
     float keep = 0.f;
     for (int dd = 0; dd < 32; ++dd) {
@@ -45,18 +45,18 @@ cost_volume_kernel(const float4* __restrict__ x1, const float4* __restrict__ x2,
       }
       if (lane == dd) keep = s;
     }
-    if (d0 + lane < CP) o[d0 + lane] = keep;
+    if (d0 + lane < CP) store_split1(out, o + d0 + lane, keep);
   }
 }
 
 int cost_volume_launch(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B, int H, int W, int C, int sr,
-                       int CP, float* d_out, cudaStream_t st) {
+                       int CP, const ActRef& out, cudaStream_t st) {
   if (C <= 0 || C > 128 || (C & 3)) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "cost_volume: C must be a multiple of 4, <= 128 (got %d)", C);
   if ((2 * sr + 1) * (2 * sr + 1) > CP || (CP & 31)) return ss2_fail(ctx, SS2_ERR_INVALID, "cost_volume: CP must be a multiple of 32 and >= (2sr+1)^2");
   if (B <= 0) return SS2_OK;
   dim3 grid(cdiv(H * W, 8), B);
   cost_volume_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(d_x1),
-                                          reinterpret_cast<const float4*>(d_x2), H, W, C / 4, sr, CP, d_out);
+                                          reinterpret_cast<const float4*>(d_x2), H, W, C / 4, sr, CP, out);
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }
@@ -145,7 +145,9 @@ int ccl_launch(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H,
   L.w = Wp; L.bias = nullptr;
   L.Cin = L.CinP = C; L.Cout = HW; L.CoutP = KP;
   L.KH = L.KW = 3; L.ph = L.pw = 1;
-  SS2_TRY(conv_launch(ctx, L, n1, 1, 1, H, W, match, nullptr, 0, st, B, (size_t)9 * C * KP));
+  ActRef a_in, a_out;
+  a_in.v = n1; a_out.v = match;
+  SS2_TRY(conv_launch(ctx, L, a_in, 1, 1, H, W, a_out, nullptr, 0, st, B, (size_t)9 * C * KP));
   ccl_softmax_flow_kernel<<<dim3(cdiv(HW, 8), B), 256, 0, st>>>(match, H, W, reinterpret_cast<float4*>(d_flow));
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;

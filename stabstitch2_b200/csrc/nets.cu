@@ -8,6 +8,7 @@
 // State-dict key names: SURVEY.md Appendix B (verified by strict load into the reference).
 #include <math.h>
 #include <stdarg.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -28,7 +29,6 @@ static int upload(ss2_ctx* ctx, const std::vector<float>& h, float** d) {
   return SS2_OK;
 }
 
-int conv_tc_prepare(ss2_ctx* ctx, ConvLayer& L);
 
 // conv weight [Cout,Cin,(KD,)KH,KW] (+ optional BN prefix, + optional bias key) -> ConvLayer.
 // `flatten_hw` > 0 packs a Linear that consumes an NCHW-flattened [C, flatten_hw] map whose
@@ -90,13 +90,33 @@ static int pack_conv(ss2_ctx* ctx, int net, const std::string& wkey, const std::
         wp[krow * L->CoutP + o] = (float)v;
       }
   SS2_TRY(upload(ctx, wp, &L->w));
+  // tensor-core path: K-major [CoutP][Ktot] split into hi = rna_tf32(w), lo = w - hi
+  L->wk_hi = L->wk_lo = nullptr;
+  if (flatten_hw == 0 && (L->CinP % 32) == 0 && (Cout % 4) == 0) {
+    const size_t Ktot = (size_t)taps * L->CinP;
+    std::vector<float> hi((size_t)L->CoutP * Ktot, 0.f), lo((size_t)L->CoutP * Ktot, 0.f);
+    for (size_t k = 0; k < Ktot; ++k)
+      for (int o = 0; o < L->CoutP; ++o) {
+        const float v = wp[k * L->CoutP + o];
+        uint32_t b;
+        memcpy(&b, &v, 4);
+        b = (b + 0x1000u) & 0xFFFFE000u;  // round-to-nearest (ties away) to 10 mantissa bits, like cvt.rna.tf32
+        float h;
+        memcpy(&h, &b, 4);
+        if (!isfinite(h)) h = v;
+        hi[(size_t)o * Ktot + k] = h;
+        lo[(size_t)o * Ktot + k] = v - h;
+      }
+    SS2_TRY(upload(ctx, hi, &L->wk_hi));
+    SS2_TRY(upload(ctx, lo, &L->wk_lo));
+  }
   L->bias = nullptr;
   if (has_bias) {
     std::vector<float> bp(L->CoutP, 0.f);
     for (int o = 0; o < Cout; ++o) bp[o] = (float)shift[o];
     SS2_TRY(upload(ctx, bp, &L->bias));
   }
-  return conv_tc_prepare(ctx, *L);
+  return SS2_OK;
 }
 
 static int pack_block(ss2_ctx* ctx, int net, const std::string& pfx, int stride, ResBlock* b) {
@@ -191,19 +211,31 @@ extern "C" int ss2_finalize_weights(ss2_ctx* ctx, int net_id) {
   T* ptr = arena_alloc<T>(ctx, (size_t)(n));                                                    \
   if (!ptr) return ss2_fail(ctx, SS2_ERR_OOM, "workspace arena exhausted at %s:%d", __FILE__, __LINE__)
 
-static int run_block(ss2_ctx* ctx, const ResBlock& b, const float* x, int NB, int H, int W, float** out, int* Ho,
+// activation with (when the tensor-core path is on) its tf32 hi/lo split planes
+#define ARENA_ACT(ref, n)                                                                       \
+  ActRef ref;                                                                                   \
+  {                                                                                             \
+    const size_t n__ = ((size_t)(n) + 63) / 64 * 64;                                            \
+    ref.v = arena_alloc<float>(ctx, (ctx->use_tc ? 3 : 1) * n__);                               \
+    if (!ref.v) return ss2_fail(ctx, SS2_ERR_OOM, "workspace arena exhausted at %s:%d", __FILE__, __LINE__); \
+    if (ctx->use_tc) { ref.hi = ref.v + n__; ref.lo = ref.v + 2 * n__; }                        \
+  }
+
+static int run_block(ss2_ctx* ctx, const ResBlock& b, const ActRef& x, int NB, int H, int W, ActRef* out, int* Ho,
                      int* Wo, cudaStream_t st) {
   int d, h, w;
   conv_out_dims(b.c1, 1, H, W, &d, &h, &w);
-  ARENA(t1, float, (size_t)NB * h * w * b.c1.Cout);
+  ARENA_ACT(t1, (size_t)NB * h * w * b.c1.Cout);
   SS2_TRY(conv_launch(ctx, b.c1, x, NB, 1, H, W, t1, nullptr, 1, st));
-  const float* idt = x;
+  const float* idt = x.v;
   if (b.has_down) {
-    ARENA(t2, float, (size_t)NB * h * w * b.down.Cout);
-    SS2_TRY(conv_launch(ctx, b.down, x, NB, 1, H, W, t2, nullptr, 0, st));
-    idt = t2;
+    ARENA_ACT(t2, (size_t)NB * h * w * b.down.Cout);
+    ActRef t2v;
+    t2v.v = t2.v;  // only the plain values of the shortcut are consumed (as the residual)
+    SS2_TRY(conv_launch(ctx, b.down, x, NB, 1, H, W, t2v, nullptr, 0, st));
+    idt = t2.v;
   }
-  ARENA(t3, float, (size_t)NB * h * w * b.c2.Cout);
+  ARENA_ACT(t3, (size_t)NB * h * w * b.c2.Cout);
   SS2_TRY(conv_launch(ctx, b.c2, t1, NB, 1, h, w, t3, idt, 1, st));
   *out = t3; *Ho = h; *Wo = w;
   return SS2_OK;
@@ -217,56 +249,60 @@ static int run_backbone(ss2_ctx* ctx, const Backbone& bb, const float* x_nchw, i
   int d, h, w;
   conv_out_dims(bb.stem, 1, H, W, &d, &h, &w);
   ARENA(s, float, (size_t)NB * h * w * 64);
-  SS2_TRY(conv_launch(ctx, bb.stem, x, NB, 1, H, W, s, nullptr, 1, st));
+  ActRef xin, sout;
+  xin.v = x; sout.v = s;
+  SS2_TRY(conv_launch(ctx, bb.stem, xin, NB, 1, H, W, sout, nullptr, 1, st));
   const int hp = (h + 2 - 3) / 2 + 1, wp = (w + 2 - 3) / 2 + 1;
-  ARENA(p, float, (size_t)NB * hp * wp * 64);
+  ARENA_ACT(p, (size_t)NB * hp * wp * 64);
   SS2_TRY(maxpool_launch(ctx, s, NB, h, w, 64, 3, 2, 1, p, st));
-  float* cur = p;
+  ActRef cur = p;
   h = hp; w = wp;
   SS2_TRY(run_block(ctx, bb.l1[0], cur, NB, h, w, &cur, &h, &w, st));
   SS2_TRY(run_block(ctx, bb.l1[1], cur, NB, h, w, &cur, &h, &w, st));
   SS2_TRY(run_block(ctx, bb.l2[0], cur, NB, h, w, &cur, &h, &w, st));
   SS2_TRY(run_block(ctx, bb.l2[1], cur, NB, h, w, &cur, &h, &w, st));
-  *f64 = cur; *h64 = h; *w64 = w;
+  *f64 = cur.v; *h64 = h; *w64 = w;
   if (stage2) {
     SS2_TRY(run_block(ctx, bb.l3[0], cur, NB, h, w, &cur, &h, &w, st));
     SS2_TRY(run_block(ctx, bb.l3[1], cur, NB, h, w, &cur, &h, &w, st));
-    *f32 = cur; *h32 = h; *w32 = w;
+    *f32 = cur.v; *h32 = h; *w32 = w;
   }
   return SS2_OK;
 }
 
 // x [NB,H,W,CinP] -> out [NB, fc[2].Cout]
-static int run_regressor(ss2_ctx* ctx, const Regressor& r, const float* x, int NB, int H, int W, float* out,
+static int run_regressor(ss2_ctx* ctx, const Regressor& r, const ActRef& x, int NB, int H, int W, float* out,
                          cudaStream_t st) {
-  const float* cur = x;
+  ActRef cur = x;
   int h = H, w = W;
   for (size_t i = 0; i < r.convs.size(); ++i) {
     const ConvLayer& L = r.convs[i];
-    ARENA(t, float, (size_t)NB * h * w * L.Cout);
+    ARENA_ACT(t, (size_t)NB * h * w * L.Cout);
     SS2_TRY(conv_launch(ctx, L, cur, NB, 1, h, w, t, nullptr, 1, st));
     cur = t;
     if (r.pool_after[i]) {
       const int hp = h / 2, wp = w / 2;
-      ARENA(q, float, (size_t)NB * hp * wp * L.Cout);
-      SS2_TRY(maxpool_launch(ctx, cur, NB, h, w, L.Cout, 2, 2, 0, q, st));
+      ARENA_ACT(q, (size_t)NB * hp * wp * L.Cout);
+      SS2_TRY(maxpool_launch(ctx, cur.v, NB, h, w, L.Cout, 2, 2, 0, q, st));
       cur = q; h = hp; w = wp;
     }
   }
   const int feat = h * w * r.convs.back().Cout;
   if (feat != r.fc[0].Cin) return ss2_fail(ctx, SS2_ERR_INVALID, "regressor: %d features, Linear expects %d", feat, r.fc[0].Cin);
   ARENA(a, float, (size_t)NB * r.fc[0].Cout);
-  SS2_TRY(conv_launch(ctx, r.fc[0], cur, NB, 1, 1, 1, a, nullptr, 1, st));
   ARENA(b, float, (size_t)NB * r.fc[1].Cout);
-  SS2_TRY(conv_launch(ctx, r.fc[1], a, NB, 1, 1, 1, b, nullptr, 1, st));
-  SS2_TRY(conv_launch(ctx, r.fc[2], b, NB, 1, 1, 1, out, nullptr, 0, st));
+  ActRef xa, xb, xo, xi;
+  xi.v = cur.v; xa.v = a; xb.v = b; xo.v = out;
+  SS2_TRY(conv_launch(ctx, r.fc[0], xi, NB, 1, 1, 1, xa, nullptr, 1, st));
+  SS2_TRY(conv_launch(ctx, r.fc[1], xa, NB, 1, 1, 1, xb, nullptr, 1, st));
+  SS2_TRY(conv_launch(ctx, r.fc[2], xb, NB, 1, 1, 1, xo, nullptr, 0, st));
   return SS2_OK;
 }
 
 #define NET_IMG_H 360
 #define NET_IMG_W 480
-static const size_t kBytesPerImageBackbone = (size_t)48 << 20;   // generous bound, see DESIGN.md
-static const size_t kBytesPerPairHead = (size_t)40 << 20;
+static const size_t kBytesPerImageBackbone = (size_t)3 * 48 << 20;   // generous bound (x3: tf32 hi/lo planes), see DESIGN.md
+static const size_t kBytesPerPairHead = (size_t)3 * 40 << 20;
 
 static int spatial_chunk(ss2_ctx* ctx, const float* img1, const float* img2, int bs, int H, int W, float* o1,
                          float* oref, float* otgt, cudaStream_t st) {
@@ -283,7 +319,9 @@ static int spatial_chunk(ss2_ctx* ctx, const float* img1, const float* img2, int
   // stage 1: global correlation -> 4-point offsets
   ARENA(flow, float, (size_t)bs * h32 * w32 * 4);
   SS2_TRY(ccl_launch(ctx, f32, f32 + (size_t)bs * h32 * w32 * 256, bs, h32, w32, 256, flow, st));
-  SS2_TRY(run_regressor(ctx, S.r1, flow, bs, h32, w32, o1, st));
+  ActRef flow_ref;
+  flow_ref.v = flow;
+  SS2_TRY(run_regressor(ctx, S.r1, flow_ref, bs, h32, w32, o1, st));
   // homography split on the middle plane, warp both 1/8-scale feature maps
   ARENA(theta, float, (size_t)2 * bs * 9);
   SS2_TRY(spatial_split_launch(ctx, o1, bs, H, W, theta, theta + (size_t)bs * 9, st));
@@ -291,11 +329,12 @@ static int spatial_chunk(ss2_ctx* ctx, const float* img1, const float* img2, int
   SS2_TRY(homo_warp_nhwc_launch(ctx, f64, theta, 2 * bs, 128, h64, w64, warped, st));
   // stage 2: two local cost volumes -> two mesh regressors
   const size_t half = (size_t)bs * h64 * w64 * 128;
-  ARENA(cv, float, 2 * half);
-  SS2_TRY(cost_volume_launch(ctx, warped, warped + half, bs, h64, w64, 128, 5, 128, cv, st));
-  SS2_TRY(cost_volume_launch(ctx, warped + half, warped, bs, h64, w64, 128, 5, 128, cv + half, st));
-  SS2_TRY(run_regressor(ctx, S.r2_ref, cv, bs, h64, w64, oref, st));
-  SS2_TRY(run_regressor(ctx, S.r2_tgt, cv + half, bs, h64, w64, otgt, st));
+  ARENA_ACT(cv_ref, half);
+  ARENA_ACT(cv_tgt, half);
+  SS2_TRY(cost_volume_launch(ctx, warped, warped + half, bs, h64, w64, 128, 5, 128, cv_ref, st));
+  SS2_TRY(cost_volume_launch(ctx, warped + half, warped, bs, h64, w64, 128, 5, 128, cv_tgt, st));
+  SS2_TRY(run_regressor(ctx, S.r2_ref, cv_ref, bs, h64, w64, oref, st));
+  SS2_TRY(run_regressor(ctx, S.r2_tgt, cv_tgt, bs, h64, w64, otgt, st));
   return SS2_OK;
 }
 
@@ -368,7 +407,7 @@ extern "C" int ss2_build_temporal(ss2_ctx* ctx, const float* d_frames, int n, fl
     SS2_TRY(run_backbone(ctx, T.bb, d_frames + (size_t)(f0 - 1) * 3 * H * W, nimg, H, W, false, &f64, &h64, &w64,
                          &f32, &h32, &w32, st));
     const int nm = nimg - 1;
-    ARENA(cv, float, (size_t)nm * h64 * w64 * 64);
+    ARENA_ACT(cv, (size_t)nm * h64 * w64 * 64);
     SS2_TRY(cost_volume_launch(ctx, f64, f64 + (size_t)h64 * w64 * 128, nm, h64, w64, 128, 3, 64, cv, st));
     SS2_TRY(run_regressor(ctx, T.r2, cv, nm, h64, w64, d_motions + (size_t)f0 * 126, st));
     if (chunk == 1) break;
@@ -387,13 +426,13 @@ extern "C" int ss2_build_smooth(ss2_ctx* ctx, const float* d_ts1, const float* d
   const SmoothWeights& M = ctx->smooth;
   const size_t per_win = (size_t)SS2_WINDOW * SS2_NPT * 128 * sizeof(float);
   const int chunk = nwin < SMOOTH_CHUNK ? nwin : SMOOTH_CHUNK;
-  SS2_TRY(ss2_ensure_arena(ctx, (size_t)chunk * per_win * 5 + ((size_t)16 << 20)));
+  SS2_TRY(ss2_ensure_arena(ctx, (size_t)chunk * per_win * 8 + ((size_t)16 << 20)));
   for (int w0 = 0; w0 < nwin; w0 += chunk) {
     const int nw = nwin - w0 < chunk ? nwin - w0 : chunk;
     ctx->arena.reset();
     const size_t hid = (size_t)nw * SS2_WINDOW * SS2_NPT * 128;
-    ARENA(h0, float, hid);
-    ARENA(h1, float, hid);
+    ARENA_ACT(h0, hid);
+    ARENA_ACT(h1, hid);
     ARENA(p1, float, (size_t)nw * SS2_WINDOW * SS2_NPT * 2);
     ARENA(p2, float, (size_t)nw * SS2_WINDOW * SS2_NPT * 2);
     const size_t fo = (size_t)w0 * SS2_NPT * 2;  // frame offset of the first window of the chunk
@@ -403,8 +442,69 @@ extern "C" int ss2_build_smooth(ss2_ctx* ctx, const float* d_ts1, const float* d
     SS2_TRY(conv_launch(ctx, M.conv3d[2], h0, nw, SS2_WINDOW, SS2_GRID_H + 1, SS2_GRID_W + 1, h1, nullptr, 1, st));
     const size_t oo = (size_t)w0 * SS2_WINDOW * SS2_NPT * 2;
     auto at = [&](float* p) { return p ? p + oo : nullptr; };
-    SS2_TRY(smooth_decode_launch(ctx, M, h1, d_sm1 + fo, d_sm2 + fo, p1, p2, nw, at(op1), at(sp1), at(om1), at(smm1),
+    SS2_TRY(smooth_decode_launch(ctx, M, h1.v, d_sm1 + fo, d_sm2 + fo, p1, p2, nw, at(op1), at(sp1), at(om1), at(smm1),
                                  at(op2), at(sp2), at(om2), at(smm2), st));
   }
   return SS2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic NHWC / NDHWC convolution primitive (the layer type every network above is built of),
+// exposed for unit tests and reuse.  Synchronous: packs the filter on every call.
+// ------------------------------------------------------------------------------------------
+__global__ void split_tf32_kernel(const float* __restrict__ in, size_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float h, l;
+    tf32_split(in[i], &h, &l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+extern "C" int ss2_conv_nhwc(ss2_ctx* ctx, const float* d_in, int B, int D, int H, int W, int Cin, const float* h_weight,
+                             const int64_t* wshape, int wndim, const float* h_bias, int stride, int pad, int pad_d,
+                             int relu, const float* d_residual, int use_tc, float* d_out, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (!d_in || !h_weight || !wshape || !d_out || (wndim != 4 && wndim != 5) || B <= 0 || D <= 0 || H <= 0 || W <= 0 ||
+      wshape[1] != Cin || (Cin & 3))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_conv_nhwc: bad arguments (Cin must be a multiple of 4 and match the filter)");
+  cudaStream_t st = (cudaStream_t)stream;
+  HostTensor wt, bt;
+  wt.shape.assign(wshape, wshape + wndim);
+  wt.data.assign(h_weight, h_weight + wt.numel());
+  ctx->host_weights[0]["__conv.weight"] = wt;
+  if (h_bias) {
+    bt.shape = {wshape[0]};
+    bt.data.assign(h_bias, h_bias + wshape[0]);
+    ctx->host_weights[0]["__conv.bias"] = bt;
+  }
+  ConvLayer L;
+  const size_t owned0 = ctx->owned.size();
+  int rc = pack_conv(ctx, 0, "__conv.weight", "", h_bias ? "__conv.bias" : "", stride, pad, pad_d, 0, &L);
+  ctx->host_weights[0].erase("__conv.weight");
+  ctx->host_weights[0].erase("__conv.bias");
+  float* split = nullptr;
+  if (rc == SS2_OK) {
+    ActRef in, out;
+    in.v = const_cast<float*>(d_in);
+    out.v = d_out;
+    const size_t n = (size_t)B * D * H * W * Cin;
+    const int saved = ctx->use_tc;
+    ctx->use_tc = use_tc;
+    if (use_tc) {
+      if (!conv_tc_eligible(L)) rc = ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "ss2_conv_nhwc: layer not eligible for the tensor-core path");
+      if (rc == SS2_OK && cudaMalloc((void**)&split, 2 * n * sizeof(float)) != cudaSuccess) rc = ss2_fail(ctx, SS2_ERR_OOM, "ss2_conv_nhwc: split buffer");
+      if (rc == SS2_OK) {
+        split_tf32_kernel<<<592, 256, 0, st>>>(d_in, n, split, split + n);
+        in.hi = split;
+        in.lo = split + n;
+      }
+    }
+    if (rc == SS2_OK) rc = conv_launch(ctx, L, in, B, D, H, W, out, d_residual, relu, st);
+    ctx->use_tc = saved;
+  }
+  cudaStreamSynchronize(st);
+  if (split) cudaFree(split);
+  while (ctx->owned.size() > owned0) { cudaFree(ctx->owned.back()); ctx->owned.pop_back(); }
+  return rc;
 }

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(128)
 smooth_embed_kernel(const float* __restrict__ e1w, const float* __restrict__ e1b, const float* __restrict__ e3w,
                     const float* __restrict__ e3b, const float* __restrict__ ts1, const float* __restrict__ ts2,
                     const float* __restrict__ sm1, const float* __restrict__ sm2, int zero_first,
-                    float* __restrict__ hidden, float* __restrict__ path1, float* __restrict__ path2) {
+                    ActRef hidden, float* __restrict__ path1, float* __restrict__ path2) {
   __shared__ float in[4][SS2_NPT][2];  // mesh1, path1, mesh2, path2 for this (window, t)
   const int w = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
   for (int e = tid; e < 2 * SS2_NPT * 2; e += 128) {
@@ -36,19 +36,19 @@ smooth_embed_kernel(const float* __restrict__ e1w, const float* __restrict__ e1b
   const float* W = (grp & 1) ? e3w : e1w;
   const float* Bv = (grp & 1) ? e3b : e1b;
   const float w0 = W[2 * j], w1 = W[2 * j + 1], bb = Bv[j];
-  float* h = hidden + ((size_t)w * SW_T + t) * SS2_NPT * 128 + tid;
+  const size_t h = ((size_t)w * SW_T + t) * SS2_NPT * 128 + tid;
   for (int p = 0; p < SS2_NPT; ++p) {
     const float v = __fadd_rn(fmaf(in[grp][p][1], w1, in[grp][p][0] * w0), bb);
-    h[(size_t)p * 128] = fmaxf(v, 0.f);
+    store_split1(hidden, h + (size_t)p * 128, fmaxf(v, 0.f));
   }
 }
 
 int smooth_embed_launch(ss2_ctx* ctx, const SmoothWeights& sw, const float* ts1, const float* ts2,
-                        const float* sm1, const float* sm2, int nwin, int zero_first, float* d_hidden, float* d_path1,
+                        const float* sm1, const float* sm2, int nwin, int zero_first, const ActRef& hidden, float* d_path1,
                         float* d_path2, cudaStream_t st) {
   if (nwin <= 0) return SS2_OK;
   smooth_embed_kernel<<<dim3(nwin, SW_T), 128, 0, st>>>(sw.emb1_w, sw.emb1_b, sw.emb3_w, sw.emb3_b, ts1, ts2, sm1,
-                                                       sm2, zero_first, d_hidden, d_path1, d_path2);
+                                                       sm2, zero_first, hidden, d_path1, d_path2);
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }

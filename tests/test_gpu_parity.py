@@ -366,3 +366,44 @@ def test_fullsize_properties():
     fused = warp_blend_average(img, img2, src[None], tgt[None], (Ho, Wo))[0]
     s = w[0] + w[1] + 1e-6
     assert (fused - (w[0] * (w[0] / s) + w[1] * (w[1] / s))).abs().max().item() < 1e-4
+
+
+# ---------------------------------------------------------------- convolution kernels (SIMT fp32 and tcgen05)
+CONV_CASES = [
+    # B, D, H, W, Cin, Cout, k, stride, pad, kd, pad_d
+    (2, 1, 45, 60, 128, 128, 3, 1, 1, 1, 0),    # ResNet layer2 body
+    (3, 1, 90, 120, 64, 128, 3, 2, 1, 1, 0),    # layer2 entry, stride 2
+    (3, 1, 90, 120, 64, 128, 1, 2, 0, 1, 0),    # 1x1 stride-2 shortcut
+    (2, 1, 23, 30, 256, 256, 3, 1, 1, 1, 0),    # layer3 body
+    (5, 1, 5, 7, 128, 256, 3, 1, 1, 1, 0),      # regressor tail: several images per M tile
+    (4, 1, 2, 3, 256, 256, 3, 1, 1, 1, 0),
+    (2, 1, 45, 60, 128, 64, 3, 1, 1, 1, 0),     # cost volume (121 -> 128 padded) into the regressor
+    (3, 7, 7, 9, 128, 128, 3, 1, 1, 5, 2),      # SmoothNet Conv3d (5,3,3)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_conv_kernels_vs_torch(case, use_tc):
+    """plain PyTorch fp32 reference of the same op (CPU, fp64 accumulate) vs our kernels"""
+    from stabstitch2_b200 import _lib
+    B, D, H, W, Cin, Cout, k, stride, pad, kd, pad_d = case
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    three_d = kd > 1
+    x = torch.randn(B, D, H, W, Cin, generator=g)
+    w = torch.randn(*( (Cout, Cin, kd, k, k) if three_d else (Cout, Cin, k, k) ), generator=g) / (Cin * k * k * kd) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    xin = x if three_d else x[:, 0]
+    if three_d:
+        ref = torch.nn.functional.conv3d(x.permute(0, 4, 1, 2, 3).double(), w.double(), b.double(), 1, (pad_d, pad, pad))
+        ref = ref.permute(0, 2, 3, 4, 1)
+    else:
+        ref = torch.nn.functional.conv2d(xin.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride, pad).permute(0, 2, 3, 1)
+    res = torch.randn(*ref.shape, generator=g)
+    ref = torch.relu(ref + res.double()).float()
+    out = _lib.conv_nhwc(xin.cuda(), w, b, stride=stride, pad=pad, pad_d=pad_d, relu=True, residual=res.cuda(), use_tc=use_tc)
+    assert out.shape == ref.shape
+    err = (out.cpu() - ref).abs().max().item()
+    # SIMT path: fp32 FMA chain.  Tensor-core path: split-TF32 operands (2^-21 relative) but the
+    # TMEM accumulator truncates on every one of the K/8 accumulation steps, ~K/8 * 2^-24 * |sum|
+    assert err < (3e-4 if use_tc else 2e-5), err
