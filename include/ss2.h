@@ -196,6 +196,17 @@ int ss2_stitch_stream_host(ss2_ctx* ctx, const float* h_lr1, const float* h_lr2,
                            int64_t out_capacity, int* out_h, int* out_w, float* h_smooth_mesh1,
                            float* h_smooth_mesh2);
 
+/* Pipelined form: _async returns once the resample+blend launches and the D2H copies of this
+ * chunk are ENQUEUED (it still blocks for the networks, because the canvas size is data
+ * dependent); ss2_stitch_stream_host_wait(slot) blocks until h_out is complete.  With the two
+ * slots (0, 1) a caller overlaps the D2H of chunk k with the H2D + networks of chunk k+1.
+ * Host buffers of a slot must stay untouched until its wait returns. */
+int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2, const float* h_hr1,
+                                 const float* h_hr2, int n, int H, int W, int mode, int tps, float* h_out,
+                                 int64_t out_capacity, int* out_h, int* out_w, float* h_smooth_mesh1,
+                                 float* h_smooth_mesh2);
+int ss2_stitch_stream_host_wait(ss2_ctx* ctx, int slot);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,9 @@ SIGNATURES = {
     "ss2_stream_meshes": (_i, [_vp, _vp, _vp, _i] + [_vp] * 6 + [_vp]),
     "ss2_stitch_stream_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64,
                                     ctypes.POINTER(_i), ctypes.POINTER(_i), _vp, _vp]),
+    "ss2_stitch_stream_host_async": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64,
+                                          ctypes.POINTER(_i), ctypes.POINTER(_i), _vp, _vp]),
+    "ss2_stitch_stream_host_wait": (_i, [_vp, _i]),
 }
 
 _lib = None

@@ -75,46 +75,77 @@ extern "C" int ss2_stream_meshes(ss2_ctx* ctx, const float* d_lr1, const float* 
 }
 
 #define WARP_CHUNK 8
+#define HOST_SLOTS 2
 
-extern "C" int ss2_stitch_stream_host(ss2_ctx* ctx, const float* h_lr1, const float* h_lr2, const float* h_hr1,
-                                      const float* h_hr2, int n, int H, int W, int mode, int tps, float* h_out,
-                                      int64_t out_capacity, int* out_h, int* out_w, float* h_smooth_mesh1,
-                                      float* h_smooth_mesh2) {
+// per-slot streams / events of the host-buffer pipeline
+struct HostSlot {
+  cudaStream_t s_copy = nullptr;
+  cudaEvent_t ev_hr = nullptr, ev_chunk[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_done = nullptr;
+  bool busy = false;
+};
+static HostSlot g_slots[8][HOST_SLOTS];  // [device][slot]
+
+static int slot_init(ss2_ctx* ctx, HostSlot& h) {
+  if (h.s_copy) return SS2_OK;
+  SS2_CUDA(ctx, cudaStreamCreateWithFlags(&h.s_copy, cudaStreamNonBlocking));
+  SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_hr, cudaEventDisableTiming));
+  SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_done, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_chunk[i], cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_d2h[i], cudaEventDisableTiming));
+  return SS2_OK;
+}
+
+extern "C" int ss2_stitch_stream_host_wait(ss2_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= HOST_SLOTS || ctx->device < 0 || ctx->device >= 8) return SS2_ERR_INVALID;
+  HostSlot& h = g_slots[ctx->device][slot];
+  if (!h.busy) return SS2_OK;
+  SS2_CUDA(ctx, cudaEventSynchronize(h.ev_done));
+  h.busy = false;
+  return SS2_OK;
+}
+
+extern "C" int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2,
+                                            const float* h_hr1, const float* h_hr2, int n, int H, int W, int mode, int tps,
+                                            float* h_out, int64_t out_capacity, int* out_h, int* out_w,
+                                            float* h_smooth_mesh1, float* h_smooth_mesh2) {
   if (!ctx) return SS2_ERR_INVALID;
+  if (slot < 0 || slot >= HOST_SLOTS || ctx->device < 0 || ctx->device >= 8) return ss2_fail(ctx, SS2_ERR_INVALID, "bad slot");
   if (n < SS2_WINDOW) return ss2_fail(ctx, SS2_ERR_INVALID, "a stream needs at least %d frames (got %d)", SS2_WINDOW, n);
   if (!h_lr1 || !h_lr2 || !h_hr1 || !h_hr2 || !h_out || !out_h || !out_w || H <= 0 || W <= 0)
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stitch_stream_host: bad arguments");
   SS2_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (!ctx->s_compute) {
-    SS2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
-    SS2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
-    SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_hr, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
-  }
-  cudaStream_t sc = ctx->s_compute, sx = ctx->s_copy;
+  HostSlot& hs = g_slots[ctx->device][slot];
+  SS2_TRY(slot_init(ctx, hs));
+  SS2_TRY(ss2_stitch_stream_host_wait(ctx, slot));  // the slot's buffers must be free
+  if (!ctx->s_compute) SS2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+  cudaStream_t sc = ctx->s_compute, sx = hs.s_copy;
   const size_t lrb = (size_t)n * 3 * 360 * 480 * sizeof(float), hrb = (size_t)n * 3 * H * W * sizeof(float);
   const size_t mb = (size_t)n * SS2_NPT * 2 * sizeof(float);
   float *lr1, *lr2, *hr1, *hr2, *small;
-  SS2_TRY(named_buf(ctx, "lr1", lrb, &lr1));
-  SS2_TRY(named_buf(ctx, "lr2", lrb, &lr2));
-  SS2_TRY(named_buf(ctx, "hr1", hrb, &hr1));
-  SS2_TRY(named_buf(ctx, "hr2", hrb, &hr2));
-  SS2_TRY(named_buf(ctx, "small", 2 * mb + 64, &small));
+  char nm[32];
+  auto name = [&](const char* base) { snprintf(nm, sizeof(nm), "%s.%d", base, slot); return nm; };
+  SS2_TRY(named_buf(ctx, name("lr1"), lrb, &lr1));
+  SS2_TRY(named_buf(ctx, name("lr2"), lrb, &lr2));
+  SS2_TRY(named_buf(ctx, name("hr1"), hrb, &hr1));
+  SS2_TRY(named_buf(ctx, name("hr2"), hrb, &hr2));
+  SS2_TRY(named_buf(ctx, name("small"), 2 * mb + 64, &small));
   float *S1 = small, *S2 = small + (size_t)n * SS2_NPT * 2, *mm = S2 + (size_t)n * SS2_NPT * 2;
-  // network inputs first on the compute stream; the (much larger) hr frames on the copy stream
-  SS2_CUDA(ctx, cudaMemcpyAsync(lr1, h_lr1, lrb, cudaMemcpyHostToDevice, sc));
-  SS2_CUDA(ctx, cudaMemcpyAsync(lr2, h_lr2, lrb, cudaMemcpyHostToDevice, sc));
+  // the network inputs go first on the slot's copy stream, then the (much larger) hr frames;
+  // the compute stream only waits for the former before it starts the networks
+  SS2_CUDA(ctx, cudaMemcpyAsync(lr1, h_lr1, lrb, cudaMemcpyHostToDevice, sx));
+  SS2_CUDA(ctx, cudaMemcpyAsync(lr2, h_lr2, lrb, cudaMemcpyHostToDevice, sx));
+  SS2_CUDA(ctx, cudaEventRecord(hs.ev_hr, sx));
+  SS2_CUDA(ctx, cudaStreamWaitEvent(sc, hs.ev_hr, 0));
   SS2_CUDA(ctx, cudaMemcpyAsync(hr1, h_hr1, hrb, cudaMemcpyHostToDevice, sx));
   SS2_CUDA(ctx, cudaMemcpyAsync(hr2, h_hr2, hrb, cudaMemcpyHostToDevice, sx));
-  SS2_CUDA(ctx, cudaEventRecord(ctx->ev_hr, sx));
+  SS2_CUDA(ctx, cudaEventRecord(hs.ev_hr, sx));
   SS2_TRY(ss2_stream_meshes(ctx, lr1, lr2, n, S1, S2, nullptr, nullptr, nullptr, nullptr, sc));
   SS2_TRY(canvas_minmax_launch(ctx, S1, S2, n, H, W, mm, sc));
   float h_mm[4];
   SS2_CUDA(ctx, cudaMemcpyAsync(h_mm, mm, sizeof(h_mm), cudaMemcpyDeviceToHost, sc));
   if (h_smooth_mesh1) SS2_CUDA(ctx, cudaMemcpyAsync(h_smooth_mesh1, S1, mb, cudaMemcpyDeviceToHost, sc));
   if (h_smooth_mesh2) SS2_CUDA(ctx, cudaMemcpyAsync(h_smooth_mesh2, S2, mb, cudaMemcpyDeviceToHost, sc));
-  SS2_CUDA(ctx, cudaStreamSynchronize(sc));  // the canvas size is data dependent
+  SS2_CUDA(ctx, cudaStreamSynchronize(sc));  // the canvas size is data dependent (16-byte read)
   int Ho, Wo;
   ss2_canvas_size(h_mm, &Ho, &Wo);
   *out_h = Ho; *out_w = Wo;
@@ -122,24 +153,30 @@ extern "C" int ss2_stitch_stream_host(ss2_ctx* ctx, const float* h_lr1, const fl
   const size_t fpx = (size_t)3 * Ho * Wo;
   if ((int64_t)(fpx * n) > out_capacity)
     return ss2_fail(ctx, SS2_ERR_INVALID, "output needs %zu floats, capacity %lld", fpx * n, (long long)out_capacity);
+  // The whole chunk is resampled into a device buffer of its own (HBM is plentiful), so the compute
+  // stream is free for the next chunk's networks while the copy stream drains the frames to the host.
   float* obuf;
-  SS2_TRY(named_buf(ctx, "out_chunks", 2 * WARP_CHUNK * fpx * sizeof(float), &obuf));
-  SS2_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_hr, 0));
-  // resample+blend in chunks, double-buffered so the D2H of chunk c overlaps the warp of c+1
-  int ci = 0;
-  for (int f0 = 0; f0 < n; f0 += WARP_CHUNK, ++ci) {
+  SS2_TRY(named_buf(ctx, name("out_frames"), (size_t)n * fpx * sizeof(float), &obuf));
+  SS2_CUDA(ctx, cudaStreamWaitEvent(sc, hs.ev_hr, 0));
+  for (int f0 = 0; f0 < n; f0 += WARP_CHUNK) {
     const int nf = n - f0 < WARP_CHUNK ? n - f0 : WARP_CHUNK;
-    const int slot = ci & 1;
-    float* dst = obuf + (size_t)slot * WARP_CHUNK * fpx;
-    if (ci >= 2) SS2_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_d2h[slot], 0));
+    float* dst = obuf + (size_t)f0 * fpx;
     SS2_TRY(ss2_stable_frames(ctx, hr1 + (size_t)f0 * 3 * H * W, hr2 + (size_t)f0 * 3 * H * W, S1 + (size_t)f0 * SS2_NPT * 2,
                               S2 + (size_t)f0 * SS2_NPT * 2, nf, H, W, h_mm, mode, tps, dst, sc));
-    SS2_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[slot], sc));
-    SS2_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->ev_chunk[slot], 0));
+    SS2_CUDA(ctx, cudaEventRecord(hs.ev_chunk[0], sc));
+    SS2_CUDA(ctx, cudaStreamWaitEvent(sx, hs.ev_chunk[0], 0));
     SS2_CUDA(ctx, cudaMemcpyAsync(h_out + (size_t)f0 * fpx, dst, (size_t)nf * fpx * sizeof(float), cudaMemcpyDeviceToHost, sx));
-    SS2_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[slot], sx));
   }
-  SS2_CUDA(ctx, cudaStreamSynchronize(sx));
-  SS2_CUDA(ctx, cudaStreamSynchronize(sc));
+  SS2_CUDA(ctx, cudaEventRecord(hs.ev_done, sx));
+  hs.busy = true;
   return SS2_OK;
+}
+
+extern "C" int ss2_stitch_stream_host(ss2_ctx* ctx, const float* h_lr1, const float* h_lr2, const float* h_hr1,
+                                      const float* h_hr2, int n, int H, int W, int mode, int tps, float* h_out,
+                                      int64_t out_capacity, int* out_h, int* out_w, float* h_smooth_mesh1,
+                                      float* h_smooth_mesh2) {
+  SS2_TRY(ss2_stitch_stream_host_async(ctx, 0, h_lr1, h_lr2, h_hr1, h_hr2, n, H, W, mode, tps, h_out, out_capacity, out_h,
+                                       out_w, h_smooth_mesh1, h_smooth_mesh2));
+  return ss2_stitch_stream_host_wait(ctx, 0);
 }

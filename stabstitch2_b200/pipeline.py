@@ -105,6 +105,31 @@ def stitch_stream(spatial_net, temporal_net, smooth_net, lr1, lr2, hr1, hr2, mod
     return stable_frames(hr1, hr2, s1, s2, mm, mode, tps), s1, s2
 
 
+def stitch_stream_host_async(spatial_net, temporal_net, smooth_net, slot, lr1, lr2, hr1, hr2, out, mode="NORMAL",
+                             tps=None):
+    """Pipelined form of stitch_stream_host (ss2_stitch_stream_host_async): returns (Ho, Wo) once the
+    chunk's resample+blend and D2H copies are enqueued; `stitch_stream_host_wait(slot)` completes it.
+    Two slots (0, 1) overlap the D2H of one chunk with the H2D + networks of the next."""
+    from .utils import torch_tps_transform as tt
+    ctx = _lib.context()
+    _sync_nets(ctx, spatial_net, temporal_net, smooth_net)
+    for t in (lr1, lr2, hr1, hr2, out):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("stitch_stream_host takes contiguous fp32 HOST tensors")
+    n, _, H, W = hr1.shape
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    ctx.check(ctx.lib.ss2_stitch_stream_host_async(ctx.handle, int(slot), _lib.ptr(lr1), _lib.ptr(lr2), _lib.ptr(hr1),
+                                                   _lib.ptr(hr2), n, H, W, _lib.MODE[mode],
+                                                   tt.DEFAULT_TPS if tps is None else tps, _lib.ptr(out), out.numel(),
+                                                   ctypes.byref(ho), ctypes.byref(wo), None, None))
+    return ho.value, wo.value
+
+
+def stitch_stream_host_wait(slot):
+    ctx = _lib.context()
+    ctx.check(ctx.lib.ss2_stitch_stream_host_wait(ctx.handle, int(slot)))
+
+
 def stitch_stream_host(spatial_net, temporal_net, smooth_net, lr1, lr2, hr1, hr2, out, mode="NORMAL", tps=None,
                        want_meshes=False):
     """ss2_stitch_stream_host: all inputs/outputs are HOST tensors (pin them for full PCIe
