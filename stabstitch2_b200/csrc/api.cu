@@ -225,7 +225,7 @@ int ss2_ccl_nhwc(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int 
   if (B < 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || (B > 0 && (!d_f1 || !d_f2 || !d_flow)))
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_ccl_nhwc: bad arguments (C must be a multiple of 4)");
   const size_t hw = (size_t)H * W, kp = (hw + 63) / 64 * 64;
-  SS2_TRY(ss2_ensure_arena(ctx, (size_t)B * (2 * hw * C + 9 * C * kp + hw * hw) * sizeof(float) + (1 << 20)));
+  SS2_TRY(ss2_ensure_arena(ctx, (size_t)B * (6 * hw * C + 9 * C * kp + hw * kp) * sizeof(float) + (1 << 20)));
   ctx->arena.reset();
   return ccl_launch(ctx, d_f1, d_f2, B, H, W, C, d_flow, (cudaStream_t)stream);
 }

@@ -233,6 +233,9 @@ int stable_meshes_launch(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh
 int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D, int H, int W, const ActRef& out,
                 const float* d_residual, int relu, cudaStream_t st, int groups = 1, size_t w_group_stride = 0);
 bool conv_tc_eligible(const ConvLayer& L);
+int conv_tc_corr_rows(int W);
+int conv_tc_corr_launch(ss2_ctx* ctx, const ActRef& n1, const ActRef& n2, int B, int H, int W, int C, float* d_match,
+                        int ldo, cudaStream_t st);
 int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D, int H, int W, const ActRef& out,
                    const float* d_residual, int relu, cudaStream_t st);
 void conv_out_dims(const ConvLayer& L, int D, int H, int W, int* Do, int* Ho, int* Wo);

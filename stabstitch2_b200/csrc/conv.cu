@@ -196,6 +196,76 @@ conv_igemm_kernel(ConvParams P) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Linear layers on a handful of rows (the regressor heads: M = frames of the chunk <= 32,
+// K up to 1536, N up to 1024).  The work is reading the weight matrix once: a CTA owns 32 output
+// columns, its 8 warps split K, every lane streams one weight column (128 B coalesced per k) and
+// keeps M accumulators; x is staged in shared memory in K chunks and read as broadcast float4.
+// ------------------------------------------------------------------------------------------
+#define FC_MAXM 32
+#define FC_KC 128
+
+template <int M>
+__global__ void __launch_bounds__(256)
+linear_smallm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int Mreal,
+                     int K, int CoutP, int Cout, int relu, float* __restrict__ out) {
+  __shared__ __align__(16) float xs[M][FC_KC];
+  __shared__ float red[8][M][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  float acc[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) acc[m] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += FC_KC) {
+    const int kc = min(FC_KC, K - k0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < M * FC_KC; e += 256) {
+      const int m = e / FC_KC, k = e % FC_KC;
+      xs[m][k] = (k < kc && m < Mreal) ? __ldg(x + (size_t)m * K + k0 + k) : 0.f;
+    }
+    __syncthreads();
+    // warp `warp` takes k = warp*4 + 32*j .. +3 of the chunk
+    for (int kk = warp * 4; kk < kc; kk += 32) {
+      float wv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wv[q] = (kk + q < kc) ? __ldg(w + (size_t)(k0 + kk + q) * CoutP + n) : 0.f;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const float4 xv = *reinterpret_cast<const float4*>(&xs[m][kk]);
+        acc[m] = fmaf(xv.w, wv[3], fmaf(xv.z, wv[2], fmaf(xv.y, wv[1], fmaf(xv.x, wv[0], acc[m]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < M; ++m) red[warp][m][lane] = acc[m];
+  __syncthreads();
+  for (int e = threadIdx.x; e < M * 32; e += 256) {
+    const int m = e / 32, c = e % 32, col = blockIdx.x * 32 + c;
+    if (col < Cout && m < Mreal) {
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v += red[q][m][c];
+      if (bias) v += bias[col];
+      if (relu) v = fmaxf(v, 0.f);
+      out[(size_t)m * Cout + col] = v;
+    }
+  }
+}
+
+static bool linear_smallm_try(ss2_ctx* ctx, const ConvLayer& L, const float* x, int M, float* out, int relu, cudaStream_t st) {
+  const int K = L.CinP;
+  const dim3 grid(L.CoutP / 32);
+#define FC_CASE(MM)                                                                                       \
+  if (M <= MM) {                                                                                          \
+    linear_smallm_kernel<MM><<<grid, 256, 0, st>>>(x, L.w, L.bias, M, K, L.CoutP, L.Cout, relu, out);     \
+    return true;                                                                                          \
+  }
+  FC_CASE(4) FC_CASE(8) FC_CASE(16) FC_CASE(32)
+#undef FC_CASE
+  (void)ctx;
+  return false;
+}
+
 int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D, int H, int W, const ActRef& out,
                 const float* d_residual, int relu, cudaStream_t st, int groups, size_t w_group_stride) {
   ConvParams P;
@@ -216,6 +286,16 @@ int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D
   if ((L.CinP & 3) || (L.CoutP & 63)) return ss2_fail(ctx, SS2_ERR_INVALID, "conv: unpadded layer");
   if (groups == 1 && ctx->use_tc && in.hi && conv_tc_eligible(L))
     return conv_tc_launch(ctx, L, in, B, D, H, W, out, d_residual, relu, st);
+  if (groups == 1 && L.KD * L.KH * L.KW == 1 && D * H * W == 1 && !d_residual && !out.hi && L.sh == 1 && L.ph == 0) {
+    ss2_prof_begin(ctx, SS2_PROF_CONV, st);
+    const bool done = linear_smallm_try(ctx, L, in.v, B, out.v, relu, st);
+    if (done) {
+      ss2_prof_end(ctx, SS2_PROF_CONV, st, 2.0 * B * (double)L.Cout * L.Cin);
+      SS2_LAUNCH_CHECK(ctx);
+      return SS2_OK;
+    }
+    ss2_prof_end(ctx, SS2_PROF_CONV, st, 0.0);
+  }
   ss2_prof_begin(ctx, SS2_PROF_CONV, st);
   if (P.M >= 128 * 148) {
     dim3 grid(cdiv(P.M, 128), L.CoutP / 64, groups);

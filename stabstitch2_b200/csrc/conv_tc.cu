@@ -54,6 +54,11 @@ struct TcParams {
   int sd, sh, sw, pd, ph, pw;
   int CinP;
   int relu;
+  // correlation mode (CCL): the B operand is the im2col of a second activation tensor
+  // (spatial_network.py:369-425: every 3x3 patch of f2 is a filter); N tile = bTH x bTW of its pixels
+  int b_act, bTH, bTW;
+  int ldo;   // output row stride in floats (== Cout for convolutions)
+  int ncol;  // output columns per N tile (64 for convolutions)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -157,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int tt = tix % P.nT; tix /= P.nT;
   const int tn = tix;
   const int w0 = tw * P.TW, h0 = th * P.TH, t0 = tt * P.TT, n0 = tn * P.TN;
-  const int cout0 = blockIdx.y * TC_BN;
+  const int cout0 = blockIdx.y * P.ncol;
   const int rows = P.TN * P.TT * P.TH * P.TW;
   const int ntaps = P.KD * P.KH * P.KW;
   const int niter = ntaps * P.nchunk;
@@ -179,7 +184,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)NOPER * ((uint32_t)rows * TC_BK * 4 + TC_B_BYTES);
+      const uint32_t b_bytes = P.b_act ? (uint32_t)(P.bTH * P.bTW) * TC_BK * 4 : (uint32_t)TC_B_BYTES;
+      const uint32_t tx_bytes = (uint32_t)NOPER * ((uint32_t)rows * TC_BK * 4 + b_bytes);
+      const int bh0 = blockIdx.y * P.bTH;
       int it = 0;
       for (int tap = 0; tap < ntaps; ++tap) {
         const int kw = tap % P.KW, kh = (tap / P.KW) % P.KH, kd = tap / (P.KW * P.KH);
@@ -190,10 +197,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], tx_bytes);
           tma_load_5d(st, &tmA_hi, &full_bar[s], ck * TC_BK, cw, ch, cd, n0);
-          tma_load_2d(st + NOPER * TC_A_BYTES, &tmB_hi, &full_bar[s], tap * P.CinP + ck * TC_BK, cout0);
+          if (P.b_act) tma_load_5d(st + NOPER * TC_A_BYTES, &tmB_hi, &full_bar[s], ck * TC_BK, kw - P.pw, bh0 + kh - P.ph, 0, n0);
+          else tma_load_2d(st + NOPER * TC_A_BYTES, &tmB_hi, &full_bar[s], tap * P.CinP + ck * TC_BK, cout0);
           if (NPASS == 3) {
             tma_load_5d(st + TC_A_BYTES, &tmA_lo, &full_bar[s], ck * TC_BK, cw, ch, cd, n0);
-            tma_load_2d(st + NOPER * TC_A_BYTES + TC_B_BYTES, &tmB_lo, &full_bar[s], tap * P.CinP + ck * TC_BK, cout0);
+            if (P.b_act) tma_load_5d(st + NOPER * TC_A_BYTES + TC_B_BYTES, &tmB_lo, &full_bar[s], ck * TC_BK, kw - P.pw, bh0 + kh - P.ph, 0, n0);
+            else tma_load_2d(st + NOPER * TC_A_BYTES + TC_B_BYTES, &tmB_lo, &full_bar[s], tap * P.CinP + ck * TC_BK, cout0);
           }
         }
       }
@@ -243,10 +252,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + half * 32, acc);  // warp-collective
       if (valid) {
         const int c0 = cout0 + half * 32;
-        const size_t o = m * P.Cout + c0;
+        const size_t o = m * P.ldo + c0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          if (c0 + j < P.Cout) {
+          if (c0 + j < P.Cout && half * 32 + j < P.ncol) {
             float v[4] = {__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3])};
             if (P.bias) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + j));
@@ -355,6 +364,7 @@ int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   P.KD = L.KD; P.KH = L.KH; P.KW = L.KW; P.nchunk = L.CinP / TC_BK;
   P.sd = L.sd; P.sh = L.sh; P.sw = L.sw; P.pd = L.pd; P.ph = L.ph; P.pw = L.pw;
   P.relu = relu; P.bias = L.bias; P.residual = d_residual;
+  P.b_act = 0; P.bTH = P.bTW = 0; P.ldo = L.Cout; P.ncol = TC_BN;
   P.out_v = out.v; P.out_hi = out.hi; P.out_lo = out.lo;
   tile_shape(B, P.Do, P.Ho, P.Wo, &P.TN, &P.TT, &P.TH, &P.TW);
   P.nW = cdiv(P.Wo, P.TW); P.nH = cdiv(P.Ho, P.TH); P.nT = cdiv(P.Do, P.TT); P.nN = cdiv(B, P.TN);
@@ -387,6 +397,62 @@ int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
     conv_tc_kernel<1, STAGES><<<grid, TC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
   }
   ss2_prof_end(ctx, SS2_PROF_CONV, st, flops);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// CCL correlation on the tensor cores: match[b][p][k] = sum_{tap,c} n1pad[b][p+tap][c] * n2pad[b][k+tap][c]
+// (spatial_network.py:369-425).  Both operands are im2col views of activation tensors.
+// match rows have stride ldo >= H*W floats.
+// ------------------------------------------------------------------------------------------
+// rows of the second feature map per N tile: the largest count with rows*W <= 64 and rows*W % 4 == 0
+// (the epilogue stores float4 columns), 0 if there is none
+int conv_tc_corr_rows(int W) {
+  for (int r = TC_BN / W; r >= 1; --r)
+    if ((r * W) % 4 == 0) return r;
+  return 0;
+}
+
+int conv_tc_corr_launch(ss2_ctx* ctx, const ActRef& n1, const ActRef& n2, int B, int H, int W, int C, float* d_match,
+                        int ldo, cudaStream_t st) {
+  if ((C % TC_BK) != 0 || W > 64 || (ldo & 3)) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_tc_corr: unsupported shape");
+  TcParams P;
+  P.B = B; P.Do = 1; P.Ho = H; P.Wo = W; P.Cout = H * W; P.CinP = C;
+  P.KD = 1; P.KH = 3; P.KW = 3; P.nchunk = C / TC_BK;
+  P.sd = P.sh = P.sw = 1; P.pd = 0; P.ph = P.pw = 1;
+  P.relu = 0; P.bias = nullptr; P.residual = nullptr;
+  P.out_v = d_match; P.out_hi = nullptr; P.out_lo = nullptr;
+  tile_shape(1, 1, H, W, &P.TN, &P.TT, &P.TH, &P.TW);  // one sample per tile
+  P.nW = cdiv(W, P.TW); P.nH = cdiv(H, P.TH); P.nT = 1; P.nN = B;
+  P.b_act = 1; P.bTW = W; P.bTH = conv_tc_corr_rows(W);
+  if (P.bTH < 1) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_tc_corr: no aligned N tile for W=%d", W);
+  P.ncol = P.bTH * P.bTW; P.ldo = ldo;
+  if (P.TW != W || P.nW != 1) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_tc_corr: feature map too wide");
+  const int npass = (ctx->tc_passes == 1 || !n1.lo || !n2.lo) ? 1 : 3;
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  SS2_TRY(make_act_map(ctx, &mA_hi, n1.hi, C, W, H, 1, B, P.TW, P.TH, 1, 1, 1, 1, 1));
+  SS2_TRY(make_act_map(ctx, &mB_hi, n2.hi, C, W, H, 1, B, P.bTW, P.bTH, 1, 1, 1, 1, 1));
+  if (npass == 3) {
+    SS2_TRY(make_act_map(ctx, &mA_lo, n1.lo, C, W, H, 1, B, P.TW, P.TH, 1, 1, 1, 1, 1));
+    SS2_TRY(make_act_map(ctx, &mB_lo, n2.lo, C, W, H, 1, B, P.bTW, P.bTH, 1, 1, 1, 1, 1));
+  } else {
+    mA_lo = mA_hi; mB_lo = mB_hi;
+  }
+  dim3 grid(P.nH * B, cdiv(H, P.bTH));
+  ss2_prof_begin(ctx, SS2_PROF_CONV, st);
+  if (npass == 3) {
+    constexpr int STAGES = TC_STAGES3;
+    const size_t smem = (size_t)STAGES * 2 * (TC_A_BYTES + TC_B_BYTES) + 1024;
+    SS2_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<3, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<3, STAGES><<<grid, TC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  } else {
+    constexpr int STAGES = TC_STAGES1;
+    const size_t smem = (size_t)STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024;
+    SS2_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<1, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<1, STAGES><<<grid, TC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  }
+  ss2_prof_end(ctx, SS2_PROF_CONV, st, 2.0 * B * (double)H * W * H * W * 9 * C);
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }

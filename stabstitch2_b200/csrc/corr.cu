@@ -49,11 +49,122 @@ cost_volume_kernel(const float4* __restrict__ x1, const float4* __restrict__ x2,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Blocked cost volume for C = 128 (the production shape): a CTA owns an 8x8 pixel tile, stages
+// x1 (64 px) and the x2 halo ((8+2sr)^2 px) in shared memory 32 channels at a time, and every
+// thread accumulates 2 horizontally adjacent pixels x up to 3 displacement rows x (2sr+1)
+// displacements in registers: one x2 float4 from shared memory feeds both pixels (7 FMAs per
+// LDS.128).  Results go through shared memory so that the NHWC rows (and their tf32 split) are
+// written with coalesced float4 stores.
+// ------------------------------------------------------------------------------------------
+#define CVT 8          // tile edge
+#define CV_CK 32       // channels per stage
+#define CV_LD 36       // padded row length (floats): conflict-free LDS.128 across 8 lanes
+
+template <int SR>
+__global__ void __launch_bounds__(128)
+cost_volume_tiled_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int H, int W, int CP, ActRef out) {
+  constexpr int KD = 2 * SR + 1, HALO = CVT + 2 * SR, NJ = (KD + 3) / 4;
+  extern __shared__ __align__(16) float sm[];
+  float* s1 = sm;                         // [64][CV_LD]
+  float* s2 = sm + CVT * CVT * CV_LD;     // [HALO*HALO][CV_LD]
+  const int b = blockIdx.z, ty0 = blockIdx.y * CVT, tx0 = blockIdx.x * CVT;
+  const int tid = threadIdx.x, pp = tid & 31, g = tid >> 5;
+  const int py = pp >> 2, px = (pp & 3) * 2;  // pixel pair (py, px), (py, px+1) of the tile
+  const size_t img = (size_t)b * H * W;
+  float acc[2][NJ][KD];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+      for (int i = 0; i < KD; ++i) acc[a][jj][i] = 0.f;
+  for (int c0 = 0; c0 < 128; c0 += CV_CK) {
+    __syncthreads();
+    // stage x1 tile and x2 halo (zero outside the image), 8 float4 per pixel
+    for (int e = tid; e < CVT * CVT * (CV_CK / 4); e += 128) {
+      const int p = e / (CV_CK / 4), q = e % (CV_CK / 4);
+      const int y = ty0 + p / CVT, x = tx0 + p % CVT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y < H && x < W) v = __ldg(reinterpret_cast<const float4*>(x1 + (img + (size_t)y * W + x) * 128 + c0) + q);
+      *reinterpret_cast<float4*>(s1 + p * CV_LD + q * 4) = v;
+    }
+    for (int e = tid; e < HALO * HALO * (CV_CK / 4); e += 128) {
+      const int p = e / (CV_CK / 4), q = e % (CV_CK / 4);
+      const int y = ty0 - SR + p / HALO, x = tx0 - SR + p % HALO;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W)
+        v = __ldg(reinterpret_cast<const float4*>(x2 + (img + (size_t)y * W + x) * 128 + c0) + q);
+      *reinterpret_cast<float4*>(s2 + p * CV_LD + q * 4) = v;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int q = 0; q < CV_CK / 4; ++q) {
+      const float4 a0 = *reinterpret_cast<const float4*>(s1 + (py * CVT + px) * CV_LD + q * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(s1 + (py * CVT + px + 1) * CV_LD + q * 4);
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) {
+        const int j = g + 4 * jj;
+        if (j < KD) {  // warp-uniform
+          const float* row = s2 + ((py + j) * HALO + px) * CV_LD + q * 4;
+#pragma unroll
+          for (int i = 0; i <= KD; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(row + i * CV_LD);
+            if (i < KD) acc[0][jj][i] = fmaf(a0.w, v.w, fmaf(a0.z, v.z, fmaf(a0.y, v.y, fmaf(a0.x, v.x, acc[0][jj][i]))));
+            if (i > 0) acc[1][jj][i - 1] = fmaf(a1.w, v.w, fmaf(a1.z, v.z, fmaf(a1.y, v.y, fmaf(a1.x, v.x, acc[1][jj][i - 1]))));
+          }
+        }
+      }
+    }
+  }
+  // results -> shared [64][CP] -> coalesced NHWC rows
+  __syncthreads();
+  float* so = sm;  // 64 * CP floats (CP <= 128) fit in the x2 halo area
+  for (int e = tid; e < CVT * CVT * CP; e += 128) so[e] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = g + 4 * jj;
+      if (j < KD) {
+#pragma unroll
+        for (int i = 0; i < KD; ++i) {
+          float v = acc[a][jj][i] * (1.0f / 128.0f);
+          v = v > 0.f ? v : 0.1f * v;
+          so[(py * CVT + px + a) * CP + j * KD + i] = v;
+        }
+      }
+    }
+  __syncthreads();
+  for (int e = tid; e < CVT * CVT * (CP / 4); e += 128) {
+    const int p = e / (CP / 4), q = e % (CP / 4);
+    const int y = ty0 + p / CVT, x = tx0 + p % CVT;
+    if (y < H && x < W)
+      store_split4(out, (img + (size_t)y * W + x) * CP + q * 4, *reinterpret_cast<const float4*>(so + p * CP + q * 4));
+  }
+}
+
 int cost_volume_launch(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B, int H, int W, int C, int sr,
                        int CP, const ActRef& out, cudaStream_t st) {
   if (C <= 0 || C > 128 || (C & 3)) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "cost_volume: C must be a multiple of 4, <= 128 (got %d)", C);
   if ((2 * sr + 1) * (2 * sr + 1) > CP || (CP & 31)) return ss2_fail(ctx, SS2_ERR_INVALID, "cost_volume: CP must be a multiple of 32 and >= (2sr+1)^2");
   if (B <= 0) return SS2_OK;
+  if (C == 128 && (sr == 5 || sr == 3) && CP <= 128 && (CP & 3) == 0) {
+    const int halo = CVT + 2 * sr;
+    const size_t smem = (size_t)(CVT * CVT + halo * halo) * CV_LD * sizeof(float);
+    dim3 g(cdiv(W, CVT), cdiv(H, CVT), B);
+    static bool attr = false;
+    if (!attr) {
+      SS2_CUDA(ctx, cudaFuncSetAttribute(cost_volume_tiled_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      SS2_CUDA(ctx, cudaFuncSetAttribute(cost_volume_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr = true;
+    }
+    if (sr == 5) cost_volume_tiled_kernel<5><<<g, 128, smem, st>>>(d_x1, d_x2, H, W, CP, out);
+    else cost_volume_tiled_kernel<3><<<g, 128, smem, st>>>(d_x1, d_x2, H, W, CP, out);
+    SS2_LAUNCH_CHECK(ctx);
+    return SS2_OK;
+  }
   dim3 grid(cdiv(H * W, 8), B);
   cost_volume_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(d_x1),
                                           reinterpret_cast<const float4*>(d_x2), H, W, C / 4, sr, CP, out);
@@ -68,7 +179,7 @@ int cost_volume_launch(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B
 //   3. match[b][p][k] = conv3x3(n1[b], Wp[b])           -> the implicit-GEMM conv kernel
 //   4. softmax_k(10*match) expectation of (k%W - w, k//W - h) -> flow (flow_w, flow_h, 0, 0)
 // ------------------------------------------------------------------------------------------
-__global__ void l2norm_nhwc_kernel(const float* __restrict__ in, int npix, int C, float* __restrict__ out) {
+__global__ void l2norm_nhwc_kernel(const float* __restrict__ in, int npix, int C, ActRef out) {
   const int pix = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
   if (pix >= npix) return;
@@ -78,7 +189,7 @@ __global__ void l2norm_nhwc_kernel(const float* __restrict__ in, int npix, int C
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
-  for (int c = lane; c < C; c += 32) out[(size_t)pix * C + c] = p[c] * inv;
+  for (int c = lane; c < C; c += 32) store_split1(out, (size_t)pix * C + c, p[c] * inv);
 }
 
 __global__ void ccl_filters_kernel(const float* __restrict__ n2, int H, int W, int C, int KP,
@@ -97,13 +208,13 @@ __global__ void ccl_filters_kernel(const float* __restrict__ n2, int H, int W, i
   Wp[((size_t)b * 9 * C + row) * KP + k] = v;
 }
 
-__global__ void ccl_softmax_flow_kernel(const float* __restrict__ match, int H, int W, float4* __restrict__ flow) {
+__global__ void ccl_softmax_flow_kernel(const float* __restrict__ match, int H, int W, int ld, float4* __restrict__ flow) {
   const int HW = H * W;
   const int b = blockIdx.y;
   const int pix = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
   if (pix >= HW) return;
-  const float* m = match + ((size_t)b * HW + pix) * HW;
+  const float* m = match + ((size_t)b * HW + pix) * ld;
   float mx = -INFINITY;
   for (int k = lane; k < HW; k += 32) mx = fmaxf(mx, m[k]);
 #pragma unroll
@@ -130,25 +241,36 @@ int ccl_launch(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H,
   if (B <= 0) return SS2_OK;
   const int HW = H * W;
   const int KP = (HW + 63) / 64 * 64;
-  float* n1 = arena_alloc<float>(ctx, (size_t)B * HW * C);
-  float* n2 = arena_alloc<float>(ctx, (size_t)B * HW * C);
-  float* Wp = arena_alloc<float>(ctx, (size_t)B * 9 * C * KP);
-  float* match = arena_alloc<float>(ctx, (size_t)B * HW * HW);
-  if (!n1 || !n2 || !Wp || !match) return ss2_fail(ctx, SS2_ERR_OOM, "ccl: workspace arena exhausted");
+  const bool tc = ctx->use_tc && (C % 32) == 0 && W <= 64 && conv_tc_corr_rows(W) >= 1;
+  const size_t nact = ((size_t)B * HW * C + 63) / 64 * 64;
+  ActRef n1, n2;
+  n1.v = arena_alloc<float>(ctx, (tc ? 3 : 1) * nact);
+  n2.v = arena_alloc<float>(ctx, (tc ? 3 : 1) * nact);
+  float* match = arena_alloc<float>(ctx, (size_t)B * HW * KP);
+  if (!n1.v || !n2.v || !match) return ss2_fail(ctx, SS2_ERR_OOM, "ccl: workspace arena exhausted");
+  if (tc) { n1.hi = n1.v + nact; n1.lo = n1.v + 2 * nact; n2.hi = n2.v + nact; n2.lo = n2.v + 2 * nact; }
   l2norm_nhwc_kernel<<<cdiv(B * HW, 8), 256, 0, st>>>(d_f1, B * HW, C, n1);
   SS2_LAUNCH_CHECK(ctx);
   l2norm_nhwc_kernel<<<cdiv(B * HW, 8), 256, 0, st>>>(d_f2, B * HW, C, n2);
   SS2_LAUNCH_CHECK(ctx);
-  ccl_filters_kernel<<<dim3(cdiv(KP, 128), 9 * C, B), 128, 0, st>>>(n2, H, W, C, KP, Wp);
-  SS2_LAUNCH_CHECK(ctx);
-  ConvLayer L;
-  L.w = Wp; L.bias = nullptr;
-  L.Cin = L.CinP = C; L.Cout = HW; L.CoutP = KP;
-  L.KH = L.KW = 3; L.ph = L.pw = 1;
-  ActRef a_in, a_out;
-  a_in.v = n1; a_out.v = match;
-  SS2_TRY(conv_launch(ctx, L, a_in, 1, 1, H, W, a_out, nullptr, 0, st, B, (size_t)9 * C * KP));
-  ccl_softmax_flow_kernel<<<dim3(cdiv(HW, 8), B), 256, 0, st>>>(match, H, W, reinterpret_cast<float4*>(d_flow));
+  int ld = HW;
+  if (tc) {
+    ld = KP;
+    SS2_TRY(conv_tc_corr_launch(ctx, n1, n2, B, H, W, C, match, ld, st));
+  } else {
+    float* Wp = arena_alloc<float>(ctx, (size_t)B * 9 * C * KP);
+    if (!Wp) return ss2_fail(ctx, SS2_ERR_OOM, "ccl: workspace arena exhausted");
+    ccl_filters_kernel<<<dim3(cdiv(KP, 128), 9 * C, B), 128, 0, st>>>(n2.v, H, W, C, KP, Wp);
+    SS2_LAUNCH_CHECK(ctx);
+    ConvLayer L;
+    L.w = Wp; L.bias = nullptr;
+    L.Cin = L.CinP = C; L.Cout = HW; L.CoutP = KP;
+    L.KH = L.KW = 3; L.ph = L.pw = 1;
+    ActRef a_in, a_out;
+    a_in.v = n1.v; a_out.v = match;
+    SS2_TRY(conv_launch(ctx, L, a_in, 1, 1, H, W, a_out, nullptr, 0, st, B, (size_t)9 * C * KP));
+  }
+  ccl_softmax_flow_kernel<<<dim3(cdiv(HW, 8), B), 256, 0, st>>>(match, H, W, ld, reinterpret_cast<float4*>(d_flow));
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }

@@ -501,6 +501,9 @@ template <int SX> struct LatCols { static constexpr int value = (LAT_THREADS + S
 #ifndef LAT_MINB
 #define LAT_MINB 8
 #endif
+#ifndef LAT_RPI
+#define LAT_RPI 1  // canvas rows whose taps are in flight together (2-3 measured slower: registers)
+#endif
 #ifndef LAT_PREFETCH
 #define LAT_PREFETCH 2  // source rows ahead pulled towards L1 (0/undefined: off)
 #endif
@@ -627,13 +630,16 @@ tps_warp_lattice_kernel(WarpParams P) {
         cand = 0xffffffffu;
       }
     }
+    // LAT_RPI canvas rows per iteration: coordinates of all of them first, then ALL their taps
+    // (2 views x 3 channels x 4 taps per row) in flight together, then the FMAs / blend / stores
 #pragma unroll
-    for (int r = 0; r < SY; ++r) {
-      const int row = row0 + r;
-      if (row >= P.Ho) break;
-      const float rowf = (float)row;
-      float px[V], py[V];
-      {
+    for (int r0 = 0; r0 < SY; r0 += LAT_RPI) {
+      if (row0 + r0 >= P.Ho) break;
+      float px[LAT_RPI][V], py[LAT_RPI][V];
+#pragma unroll
+      for (int i = 0; i < LAT_RPI; ++i) {
+        const int r = r0 + i < SY ? r0 + i : SY - 1;
+        const float rowf = (float)(row0 + r);
         float ax[V], ay[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) ax[v] = ay[v] = 0.f;
@@ -650,109 +656,118 @@ tps_warp_lattice_kernel(WarpParams P) {
         }
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          px[v] = ax[v] + fmaf(prow[v][0], rowf, pcol[v][0]);
-          py[v] = ay[v] + fmaf(prow[v][1], rowf, pcol[v][1]);
+          px[i][v] = ax[v] + fmaf(prow[v][0], rowf, pcol[v][0]);
+          py[i][v] = ay[v] + fmaf(prow[v][1], rowf, pcol[v][1]);
         }
       }
       // near-field corrections (branch-free: s is clamped to R2, where psi vanishes)
       if (cand != 0u) {
-        const float yt = fmaf(P.stepy, rowf, -1.0f);
-        if (cull) {
-          unsigned m = cand;
+        float yt[LAT_RPI];
+#pragma unroll
+        for (int i = 0; i < LAT_RPI; ++i) yt[i] = fmaf(P.stepy, (float)(row0 + min(r0 + i, SY - 1)), -1.0f);
+        unsigned m = cull ? cand : 0u;
+        int kk = 0;
 #pragma unroll 1
-          while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
-            const float4 c = near_list[k];
-            const float dx = xt - c.x, dy = yt - c.y;
-            const float s = fminf(fmaf(dy, dy, dx * dx), P.R2);
+        while (cull ? (m != 0u) : (kk < n_all)) {
+          int k;
+          if (cull) { k = __ffs(m) - 1; m &= m - 1; } else { k = kk++; }
+          const float4 c = near_list[k];
+          const float dx = xt - c.x, dxx = dx * dx;
+          const bool v0 = V == 1 || k < n0;
+#pragma unroll
+          for (int i = 0; i < LAT_RPI; ++i) {
+            const float dy = yt[i] - c.y;
+            const float s = fminf(fmaf(dy, dy, dxx), P.R2);
             // psi/ln2 = s*lg2(s+eps) - P(s)/ln2 (q0..q3 = P/ln2; the weights carry the ln2)
             const float psi = fmaf(s, lg2_approx(s + 1e-6f), -blend_poly(s, P.R2, P.q0, P.q1, P.q2, P.q3));
-            if (V == 1 || k < n0) { px[0] = fmaf(c.z, psi, px[0]); py[0] = fmaf(c.w, psi, py[0]); }
-            else { px[V - 1] = fmaf(c.z, psi, px[V - 1]); py[V - 1] = fmaf(c.w, psi, py[V - 1]); }
-          }
-        } else {
-#pragma unroll 1
-          for (int k = 0; k < n_all; ++k) {
-            const float4 c = near_list[k];
-            const float dx = xt - c.x, dy = yt - c.y;
-            const float s = fminf(fmaf(dy, dy, dx * dx), P.R2);
-            const float psi = fmaf(s, lg2_approx(s + 1e-6f), -blend_poly(s, P.R2, P.q0, P.q1, P.q2, P.q3));
-            if (V == 1 || k < n0) { px[0] = fmaf(c.z, psi, px[0]); py[0] = fmaf(c.w, psi, py[0]); }
-            else { px[V - 1] = fmaf(c.z, psi, px[V - 1]); py[V - 1] = fmaf(c.w, psi, py[V - 1]); }
+            if (v0) { px[i][0] = fmaf(c.z, psi, px[i][0]); py[i][0] = fmaf(c.w, psi, py[i][0]); }
+            else { px[i][V - 1] = fmaf(c.z, psi, px[i][V - 1]); py[i][V - 1] = fmaf(c.w, psi, py[i][V - 1]); }
           }
         }
       }
-      float res[V][C];
+      float res[LAT_RPI][V][C];
       if (MODE == SS2_MODE_NORMAL) {
-        // Phase A: tap weights and addresses of every view (branch-free; an out-of-image sample
-        // gets zero weights and reads the frame's first pixel).  Phase B: all loads of all views
-        // back to back (a view no lane of the warp sees is skipped).  Phase C: the FMAs.
-        float wq[V][4];
-        const float* tp[V];
-        bool anyv[V];
+        // Phase A: tap weights and addresses (branch-free; an out-of-image sample gets zero
+        // weights and reads the frame's first pixel).  Phase B: all loads back to back (a view no
+        // lane of the warp sees is skipped).  Phase C: the FMAs.
+        float wq[LAT_RPI][V][4];
+        const float* tp[LAT_RPI][V];
+        bool anyv[LAT_RPI][V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const int xi = __float2int_rd(px[v]), yi = __float2int_rd(py[v]);
-          const bool inb = (unsigned)xi < W1 && (unsigned)yi < H1;  // no tap is clamped: plain bilinear == _interpolate
-          const float fx0 = px[v] - (float)xi, fy = py[v] - (float)yi;
-          const float fx = inb ? fx0 : 0.0f, gx = inb ? 1.0f - fx0 : 0.0f, gy = 1.0f - fy;
-          wq[v][0] = gx * gy; wq[v][1] = gx * fy; wq[v][2] = fx * gy; wq[v][3] = fx * fy;
-          tp[v] = f32_at(imgv[v], inb ? (unsigned)(yi * W + xi) : 0u);
-          anyv[v] = __any_sync(0xffffffffu, inb);
+        for (int i = 0; i < LAT_RPI; ++i) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const int xi = __float2int_rd(px[i][v]), yi = __float2int_rd(py[i][v]);
+            const bool inb = (unsigned)xi < W1 && (unsigned)yi < H1;  // no tap is clamped: plain bilinear == _interpolate
+            const float fx0 = px[i][v] - (float)xi, fy = py[i][v] - (float)yi;
+            const float fx = inb ? fx0 : 0.0f, gx = inb ? 1.0f - fx0 : 0.0f, gy = 1.0f - fy;
+            wq[i][v][0] = gx * gy; wq[i][v][1] = gx * fy; wq[i][v][2] = fx * gy; wq[i][v][3] = fx * fy;
+            tp[i][v] = f32_at(imgv[v], inb ? (unsigned)(yi * W + xi) : 0u);
+            anyv[i][v] = __any_sync(0xffffffffu, inb);
 #if LAT_PREFETCH > 0
-          // the next canvas row samples (about) one source row further down: pull that row
-          // towards L1 now so that its demand loads hit
-          if (anyv[v] && inb && (unsigned)(yi + LAT_PREFETCH) < H1) {
+            // the next iteration samples (about) LAT_RPI source rows further down: pull them towards L1
+            if (i == LAT_RPI - 1 && anyv[i][v] && inb && (unsigned)(yi + LAT_PREFETCH) < H1) {
 #pragma unroll
-            for (int c = 0; c < C; ++c)
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(f32_at(tp[v], c * iplane + LAT_PREFETCH * W)));
-          }
+              for (int c = 0; c < C; ++c)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(f32_at(tp[i][v], c * iplane + LAT_PREFETCH * W)));
+            }
 #endif
+          }
         }
-        float tap[V][C][4];
+        float tap[LAT_RPI][V][C][4];
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          if (anyv[v]) {
+        for (int i = 0; i < LAT_RPI; ++i) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-              if (IW > 0 && IH > 0 && (size_t)(C - 1) * IW * IH * 4 + (size_t)IW * 4 + 4 < (1u << 23)) {
-                const float* p = tp[v] + c * (IW * IH);  // compile-time offsets off ONE pointer
-                tap[v][c][0] = __ldg(p); tap[v][c][2] = __ldg(p + 1);
-                tap[v][c][1] = __ldg(p + IW); tap[v][c][3] = __ldg(p + IW + 1);
-              } else {
-                const float* p0 = c == 0 ? tp[v] : f32_at(tp[v], c * iplane);
-                const float* p1 = f32_at(tp[v], c * iplane + W);
-                tap[v][c][0] = __ldg(p0); tap[v][c][2] = __ldg(p0 + 1);
-                tap[v][c][1] = __ldg(p1); tap[v][c][3] = __ldg(p1 + 1);
+          for (int v = 0; v < V; ++v) {
+            if (anyv[i][v]) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                if (IW > 0 && IH > 0 && (size_t)(C - 1) * IW * IH * 4 + (size_t)IW * 4 + 4 < (1u << 23)) {
+                  const float* p = tp[i][v] + c * (IW * IH);  // compile-time offsets off ONE pointer
+                  tap[i][v][c][0] = __ldg(p); tap[i][v][c][2] = __ldg(p + 1);
+                  tap[i][v][c][1] = __ldg(p + IW); tap[i][v][c][3] = __ldg(p + IW + 1);
+                } else {
+                  const float* p0 = c == 0 ? tp[i][v] : f32_at(tp[i][v], c * iplane);
+                  const float* p1 = f32_at(tp[i][v], c * iplane + W);
+                  tap[i][v][c][0] = __ldg(p0); tap[i][v][c][2] = __ldg(p0 + 1);
+                  tap[i][v][c][1] = __ldg(p1); tap[i][v][c][3] = __ldg(p1 + 1);
+                }
               }
             }
           }
         }
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
+        for (int i = 0; i < LAT_RPI; ++i)
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            res[v][c] = 0.0f;
-            if (anyv[v])
-              res[v][c] = fmaf(wq[v][3], tap[v][c][3], fmaf(wq[v][2], tap[v][c][2], fmaf(wq[v][1], tap[v][c][1], wq[v][0] * tap[v][c][0])));
-          }
-        }
+          for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              res[i][v][c] = 0.0f;
+              if (anyv[i][v])
+                res[i][v][c] = fmaf(wq[i][v][3], tap[i][v][c][3], fmaf(wq[i][v][2], tap[i][v][c][2],
+                                    fmaf(wq[i][v][1], tap[i][v][c][1], wq[i][v][0] * tap[i][v][c][0])));
+            }
       } else {
 #pragma unroll
-        for (int v = 0; v < V; ++v) sample_fast<C>(imgv[v], H, W, px[v], py[v], res[v]);
+        for (int i = 0; i < LAT_RPI; ++i)
+#pragma unroll
+          for (int v = 0; v < V; ++v) sample_fast<C>(imgv[v], H, W, px[i][v], py[i][v], res[i][v]);
       }
-      if (active) {
-        const unsigned opix = (unsigned)(row * P.Wo + col);
-        if (BLEND) {
 #pragma unroll
-          for (int c = 0; c < C; ++c)
-            __stcs(const_cast<float*>(f32_at(outv[0], opix + c * oplane)), blend_avg_fast(res[0][c], res[V - 1][c]));
-        } else {
+      for (int i = 0; i < LAT_RPI; ++i) {
+        const int row = row0 + r0 + i;
+        if (active && r0 + i < SY && row < P.Ho) {
+          const unsigned opix = (unsigned)(row * P.Wo + col);
+          if (BLEND) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
+            for (int c = 0; c < C; ++c)
+              __stcs(const_cast<float*>(f32_at(outv[0], opix + c * oplane)), blend_avg_fast(res[i][0][c], res[i][V - 1][c]));
+          } else {
 #pragma unroll
-            for (int c = 0; c < C; ++c) __stcs(const_cast<float*>(f32_at(outv[v], opix + c * oplane)), res[v][c]);
+            for (int v = 0; v < V; ++v) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) __stcs(const_cast<float*>(f32_at(outv[v], opix + c * oplane)), res[i][v][c]);
+            }
           }
         }
       }

@@ -407,3 +407,23 @@ def test_conv_kernels_vs_torch(case, use_tc):
     # SIMT path: fp32 FMA chain.  Tensor-core path: split-TF32 operands (2^-21 relative) but the
     # TMEM accumulator truncates on every one of the K/8 accumulation steps, ~K/8 * 2^-24 * |sum|
     assert err < (3e-4 if use_tc else 2e-5), err
+
+
+@pytest.mark.parametrize("sr", [5, 3])
+def test_cost_volume_c128_tiled_vs_oracle(sr):
+    """production shape (C = 128, 45x60 map): the shared-memory tiled kernel against the oracle"""
+    from stabstitch2_b200.spatial_network import SpatialNet
+    g = torch.Generator().manual_seed(40 + sr)
+    a, b = torch.randn(2, 128, 45, 60, generator=g), torch.randn(2, 128, 45, 60, generator=g)
+    got = SpatialNet.cost_volume(a.cuda(), b.cuda(), sr, norm=False)
+    assert maxdiff(got, O.cost_volume(a, b, sr)) < 2e-6
+
+
+def test_ccl_c256_tensor_core_vs_oracle():
+    """production shape (C = 256, 23x30 map): correlation GEMM on the tensor cores"""
+    from stabstitch2_b200.spatial_network import SpatialNet
+    g = torch.Generator().manual_seed(77)
+    f1 = torch.randn(2, 256, 23, 30, generator=g)
+    f2 = torch.roll(f1, (1, -2), (2, 3)) + 0.3 * torch.randn(2, 256, 23, 30, generator=g)
+    got = SpatialNet().CCL(f1.cuda(), f2.cuda())
+    assert maxdiff(got, O.ccl(f1, f2)) < 2e-4
