@@ -59,57 +59,65 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML
+    (nvidia_ml_py).  A polling `nvidia-smi -lms` child was measured to stall kernel launches for
+    100-250 ms once per run on these hosts; NVML calls from a thread do not."""
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines, self.first = index, None, [], 0
+        self.index, self.samples, self.first, self.stop_flag, self.thread, self.h = index, [], 0, False, None, None
 
     def mark(self):
         """samples before this point (warm-up) are not part of the timed region"""
-        self.first = len(self.lines)
+        self.first = len(self.samples)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if visible:
+                try:
+                    idx = int(visible.split(",")[self.index])
+                except (ValueError, IndexError):
+                    idx = self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.h = None
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _poll(self):
+        nv = self.nv
+        masks = ((getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                 (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                 (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                 (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap"))
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, [n for m, n in masks if bits & m]))
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "unavailable"}
+        self.stop_flag = True
         self.thread.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines[self.first:] or self.lines[-1:]:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(self.NAMES, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        use = self.samples[self.first:] or self.samples[-1:]
+        sm = sorted(x[0] for x in use)
+        reasons = sorted({r for x in use for r in x[1]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": "nvml, 50 ms period"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -253,13 +261,16 @@ def run_native(args):
     ctx.launch_count(reset=True)
     ctx.profile_enable(_lib.PROF_WARP, True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         fused = step()
+        marks[i].record()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    per_step = sorted([(marks[i - 1] if i else e0).elapsed_time(marks[i]) for i in range(args.steps)])
     launches = ctx.launch_count()
     warp_ms, warp_n, warp_bytes = ctx.profile_read(_lib.PROF_WARP)
     ctx.profile_enable(_lib.PROF_WARP, False)
@@ -321,7 +332,9 @@ def run_native(args):
                "sample": "48-frame %dx%d stream (42 SmoothNet windows) through all network stages of the CPU oracle "
                          "port; resample+blend timed on 16 frames and scaled x3 (%.1f s of CPU work)" % (H, W, spent)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%dp synthetic pair stream, full Spatial+Temporal+Smooth inference + fused TPS "
                                    "resample/AVERAGE blend" % H, "height": H, "width": W, "canvas": [Ho, Wo],

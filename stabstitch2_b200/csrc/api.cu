@@ -103,6 +103,16 @@ int ss2_create(int device, ss2_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return SS2_ERR_CUDA;
   ss2_ctx* c = new ss2_ctx();
   c->device = device;
+  {
+    // keep the stream-ordered allocator's memory cached across synchronisation points: the small
+    // per-call scratch (TPS coefficients, lattice nodes) would otherwise be returned to the OS at
+    // every host sync and re-mapped on the next call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   const char* env = getenv("SS2_USE_TC");
   if (env) c->use_tc = atoi(env);
   env = getenv("SS2_TC_PASSES");
