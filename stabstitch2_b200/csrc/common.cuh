@@ -229,6 +229,8 @@ int canvas_minmax_launch(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh
 int stable_meshes_launch(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh2, int n, int img_h,
                          int img_w, float xmin, float ymin, float out_w, float out_h, float* d_source,
                          float* d_target, cudaStream_t st);
+// conv_tc.cu: cuTensorMapEncodeTiled (driver entry point), null if unavailable
+void* ss2_tensormap_encode_fn();
 // conv.cu
 int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D, int H, int W, const ActRef& out,
                 const float* d_residual, int relu, cudaStream_t st, int groups = 1, size_t w_group_stride = 0);

@@ -296,7 +296,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn encode_fn() {
+void* ss2_tensormap_encode_fn();
+static EncodeTiledFn encode_fn() { return reinterpret_cast<EncodeTiledFn>(ss2_tensormap_encode_fn()); }
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda symbol dependency); shared with tps.cu
+void* ss2_tensormap_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -307,7 +310,7 @@ static EncodeTiledFn encode_fn() {
         q == cudaDriverEntryPointSuccess)
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
-  return fn;
+  return reinterpret_cast<void*>(fn);
 }
 
 // activation tensor {C, W, H, D, B} (fp32, innermost first) with a box of one output tile

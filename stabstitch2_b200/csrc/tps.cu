@@ -8,6 +8,8 @@
 //   utils/torch_tps_transform.py:158-162  F.grid_sample(align_corners=True) (FAST) -> sample_fast
 //   utils/torch_tps_transform_point.py    -> tps_point_kernel
 //   test_online_tra.py:142                AVERAGE fusion -> blend_avg
+#include <cuda.h>
+
 #include "common.cuh"
 
 #define LN2F 0.69314718055994530942f
@@ -299,6 +301,7 @@ struct WarpParams {
   float R2, p0, p1, p2, p3;  // near radius^2 (normalised units) and the blending cubic P(s)
   float q0, q1, q2, q3;      // P / ln2
   float half_w, half_h;      // normalised -> pixel scale of the source image
+  int dbg;                   // tile kernel debugging (SS2_TILE_DBG): 1 = stage nothing (every sample takes the global-load path)
 };
 
 // V = views evaluated per pixel (2 for the fused blend, 1 for the generic transformer).
@@ -775,6 +778,440 @@ tps_warp_lattice_kernel(WarpParams P) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// TILE resampler: the production kernel of the fused NORMAL resample + AVERAGE blend.
+//
+// Same field evaluation as tps_warp_lattice_kernel (quintic lattice interpolation + exact near
+// field), but the bilinear taps never touch global memory from a thread:
+//   * a CTA owns a TL_W x TL_H tile of the canvas.  From the lattice nodes bracketing the tile it
+//     bounds the tile's source footprint per view and has the TMA unit copy that box of the
+//     three colour planes ([3][TL_BH][TL_BW] floats per view, 8-row boxes issued by the lanes of
+//     warp 0, out-of-image elements zero-filled) into shared memory while the CTA y-contracts
+//     the lattice for its rows;
+//   * the affine predictor and the box origin are folded into the y-contracted node values
+//     (Lagrange weights sum to one and reproduce linear functions), so the x contraction
+//     (6 LDS.128 + 12 packed FFMA2) directly yields box-local source coordinates of both views;
+//   * taps are LDS with compile-time offsets from one per-view index; tap pairs and weight pairs
+//     go through packed fp32 FMAs (fma.rn.f32x2), as does the blend.
+// A sample whose taps are not inside the staged box although it is inside the image (footprint
+// larger than the box: scale > 1.15, strong shear, or a near-field bump beyond the margin)
+// takes the per-warp slow path with global loads, so the result never depends on the bound.
+// Three CTAs (3 x 66 KB) are resident per SM; one's TMA wait overlaps the others' sampling.
+// ------------------------------------------------------------------------------------------
+#define TL_W 64
+#define TL_H 16
+#define TL_THREADS 256
+#define TL_RPT 4  // canvas rows per thread (a warp owns a 32 x 4 block)
+#define TL_BW 96   // staged box: columns
+#define TL_BH 28   //             rows; TMA boxes of TL_BH0, TL_BH1 or TL_BH rows, whichever the footprint needs
+#define TL_BH0 16
+#define TL_BH1 24
+#define TL_PLANE (TL_BW * TL_BH)
+#define TL_MARGIN 3
+#define TL_SMEM_BYTES (2 * 3 * TL_PLANE * 4)
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t tl_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+// four taps of one colour plane at byte address ad + OFF of the staged box, weights (w00, w10) and (w01, w11)
+template <int OFF>
+__device__ __forceinline__ void tile_taps(uint32_t ad, u64 wA, u64 wB, float& out) {
+  float t00, t10, t01, t11;
+  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(t00) : "r"(ad), "n"(OFF));
+  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(t10) : "r"(ad), "n"(OFF + 4));
+  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(t01) : "r"(ad), "n"(OFF + TL_BW * 4));
+  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(t11) : "r"(ad), "n"(OFF + TL_BW * 4 + 4));
+  float lo, hi;
+  upk2(ffma2(pk2(t01, t11), wB, fmul2(pk2(t00, t10), wA)), lo, hi);
+  out = lo + hi;
+}
+
+struct TileGeo {       // per view, written by one lane of warp 0
+  int tx0, ty0;        // image coordinates of the staged box's element (0, 0)
+  int lox, wxn;        // window (in R0-relative sample coordinates) of sample origins whose four taps are staged AND
+  int loy, wyn;        // inside the image: lox <= xi < lox + wxn
+  int shift;           // box element index = yi * TL_BW + xi - shift
+  int rows;            // rows of the TMA box (0: nothing staged for this view)
+};
+
+template <int SX> struct TileCols { static constexpr int value = (TL_W + SX - 1) / SX + LAT_TAPS; };
+
+__device__ LagrangeTable g_lag[4];  // the same tables in global memory: lanes read DIFFERENT rows (constant memory would serialise)
+
+template <int SX, int SY>
+__global__ void __launch_bounds__(TL_THREADS, 3)
+tps_warp_tile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_constant__ CUtensorMap tm0b,
+                     const __grid_constant__ CUtensorMap tm0c, const __grid_constant__ CUtensorMap tm1a,
+                     const __grid_constant__ CUtensorMap tm1b, const __grid_constant__ CUtensorMap tm1c, WarpParams P) {
+  constexpr int V = 2, C = 3;
+  constexpr int NCOL = TileCols<SX>::value;
+  constexpr int NLW = (V * SS2_NPT + 31) / 32;  // warps that test the control points
+  extern __shared__ __align__(128) float tile[];  // [V][3][TL_BH][TL_BW], TMA destination
+  __shared__ float4 near_list[V * SS2_NPT];
+  __shared__ __align__(16) float2 ysm[TL_H][NCOL][V];
+  __shared__ int warp_cnt[NLW][2];
+  __shared__ float s_pred[V][6];
+  __shared__ float s_r0f[V][2];
+  __shared__ int s_r0[V][2];
+  __shared__ TileGeo s_geo[V];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int n = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int col0 = blockIdx.x * TL_W, row0 = blockIdx.y * TL_H;
+  const int jx0 = col0 / SX;
+  const int W = P.W, H = P.H;
+  const unsigned FULL = 0xffffffffu;
+
+  // ---- phase 0: control points whose disc s < R2 touches the tile (warps 0..NLW-1); predictor and the integer
+  // reference origin R0 = floor(predictor at the tile origin) of each view (last warp); barrier
+  float4 ent = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool hit = false;
+  unsigned m_all = 0;
+  if (wid < NLW) {
+    const int pv = tid / SS2_NPT, pi = tid - pv * SS2_NPT;
+    if (tid < V * SS2_NPT) {
+      const float x_lo = fmaf(P.stepx, (float)col0, -1.0f), x_hi = fmaf(P.stepx, (float)min(col0 + TL_W - 1, P.Wo - 1), -1.0f);
+      const float y_lo = fmaf(P.stepy, (float)row0, -1.0f), y_hi = fmaf(P.stepy, (float)min(row0 + TL_H - 1, P.Ho - 1), -1.0f);
+      const float2 c = *reinterpret_cast<const float2*>(P.source + ((size_t)(n * V + pv) * SS2_NPT + pi) * 2);
+      const float ddx = fmaxf(fmaxf(x_lo - c.x, c.x - x_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
+      hit = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
+      if (hit) {
+        const float* t = P.T + (size_t)(n * V + pv) * 2 * SS2_NSYS;
+        ent = make_float4(c.x, c.y, t[3 + pi] * (P.half_w * LN2F), t[SS2_NSYS + 3 + pi] * (P.half_h * LN2F));
+      }
+    }
+    m_all = __ballot_sync(FULL, hit);
+    const unsigned m_v0 = __ballot_sync(FULL, hit && pv == 0);
+    if (lane == 0) { warp_cnt[wid][0] = __popc(m_all); warp_cnt[wid][1] = __popc(m_v0); }
+  } else if (wid == TL_THREADS / 32 - 1) {
+    float pr = 0.f;
+    if (lane < V * 6) {
+      pr = P.aux[(size_t)(n * V + lane / 6) * 8 + lane % 6];
+      s_pred[lane / 6][lane % 6] = pr;
+    }
+    // lanes 6v + {0, 3}: x and y of view v
+    const float p1 = __shfl_down_sync(FULL, pr, 1), p2 = __shfl_down_sync(FULL, pr, 2);
+    if (lane < V * 6 && (lane % 3) == 0) {
+      const double b = (double)pr * col0 + (double)p1 * row0 + (double)p2;
+      const double fb = floor(fmin(fmax(b, -1.0e6), 1.0e6));
+      s_r0[lane / 6][(lane % 6) / 3] = (int)fb;
+      s_r0f[lane / 6][(lane % 6) / 3] = (float)(b - fb);
+    }
+    if (lane == 31) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tl_smem_u32(&s_bar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  int n0 = 0, n_all = 0;
+#pragma unroll
+  for (int w = 0; w < NLW; ++w) { n_all += warp_cnt[w][0]; n0 += warp_cnt[w][1]; }
+  if (hit) {
+    int off = 0;
+#pragma unroll
+    for (int w = 0; w < NLW; ++w)
+      if (w < wid) off += warp_cnt[w][0];
+    near_list[off + __popc(m_all & ((1u << lane) - 1u))] = ent;
+  }
+  int r0x[V], r0y[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) { r0x[v] = s_r0[v][0]; r0y[v] = s_r0[v][1]; }
+  // ---- phase 1: y contraction of the tile's node columns with the predictor folded in, relative to R0:
+  // ysm[r][j][v] = sum_b Ly[b] node[cy+b][jx0+j] + pred(node column, row) - R0
+  for (int item = tid; item < TL_H * NCOL; item += TL_THREADS) {
+    const int r = item / NCOL, j = item - r * NCOL;
+    if (jx0 + j < P.nx) {
+      const int row = min(row0 + r, P.Ho - 1);
+      const int cy = row / SY, ry = row - cy * SY;
+      const float2* nd = P.nodes + (((size_t)n * P.ny + cy) * P.nx + (jx0 + j)) * V;
+      const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SY)].w[ry][0]));
+      const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SY)].w[ry][4]));
+      const float wy[LAT_TAPS] = {wlo.x, wlo.y, wlo.z, wlo.w, whi.x, whi.y};
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int b = 0; b < LAT_TAPS; ++b) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(nd + (size_t)b * P.nx * V));
+        a0 = fmaf(wy[b], q.x, a0); a1 = fmaf(wy[b], q.y, a1); a2 = fmaf(wy[b], q.z, a2); a3 = fmaf(wy[b], q.w, a3);
+      }
+      const float cr = (float)((jx0 + j - LAT_LO) * SX - col0), rr = (float)(row - row0);
+      a0 += fmaf(s_pred[0][0], cr, fmaf(s_pred[0][1], rr, s_r0f[0][0]));
+      a1 += fmaf(s_pred[0][3], cr, fmaf(s_pred[0][4], rr, s_r0f[0][1]));
+      a2 += fmaf(s_pred[1][0], cr, fmaf(s_pred[1][1], rr, s_r0f[1][0]));
+      a3 += fmaf(s_pred[1][3], cr, fmaf(s_pred[1][4], rr, s_r0f[1][1]));
+      *reinterpret_cast<float4*>(&ysm[r][j][0]) = make_float4(a0, a1, a2, a3);
+    }
+  }
+  // ---- per-thread constants: one canvas column, TL_RPT consecutive rows (a warp owns a 32 x TL_RPT block)
+  const int wx = wid & 1, wy = wid >> 1;
+  const int colt = wx * 32 + lane, rt0 = wy * TL_RPT;
+  const int col = min(col0 + colt, P.Wo - 1);
+  const bool active = col0 + colt < P.Wo;
+  const int cxi = col / SX, rx = col - cxi * SX, js = cxi - jx0;
+  float lxw[LAT_TAPS];
+  {
+    const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SX)].w[rx][0]));
+    const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SX)].w[rx][4]));
+    lxw[0] = wlo.x; lxw[1] = wlo.y; lxw[2] = wlo.z; lxw[3] = wlo.w; lxw[4] = whi.x; lxw[5] = whi.y;
+  }
+  const float xt = fmaf(P.stepx, (float)col, -1.0f);
+  __syncthreads();  // ysm complete
+  // ---- phase 2 (warp 0): source footprint of the tile from the field at its corners and edge midpoints (an extremum
+  // of a fold-free, nearly affine map over a rectangle lies at a corner; the margin and the slow path cover the rest),
+  // box geometry, TMA issue
+  if (wid == 0) {
+    const int lastc = min(TL_W - 1, P.Wo - 1 - col0), lastr = min(TL_H - 1, P.Ho - 1 - row0);
+    const int k = lane & 7;  // 3 x 3 sample points without the centre
+    const int kk = k < 4 ? k : k + 1;
+    const int pr = (kk / 3) * lastr / 2, pc = (kk % 3) * lastc / 2;
+    const int pcol = col0 + pc, pcx = pcol / SX, prx = pcol - pcx * SX, pjs = pcx - jx0;
+    float e[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SX)].w[prx][0]));
+      const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SX)].w[prx][4]));
+      const float wq[LAT_TAPS] = {wlo.x, wlo.y, wlo.z, wlo.w, whi.x, whi.y};
+#pragma unroll
+      for (int a = 0; a < LAT_TAPS; ++a) {
+        const float4 q = *reinterpret_cast<const float4*>(&ysm[pr][pjs + a][0]);
+        e[0] = fmaf(wq[a], q.x, e[0]); e[1] = fmaf(wq[a], q.y, e[1]); e[2] = fmaf(wq[a], q.z, e[2]); e[3] = fmaf(wq[a], q.w, e[3]);
+      }
+    }
+    float mn[4], mx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      mn[q] = mx[q] = e[q];
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        mn[q] = fminf(mn[q], __shfl_xor_sync(FULL, mn[q], o));
+        mx[q] = fmaxf(mx[q], __shfl_xor_sync(FULL, mx[q], o));
+      }
+    }
+    if (lane < V) {
+      const int v = lane;
+      const float lim = 1.0e6f;
+      const float fxmin = fmaxf(v == 0 ? mn[0] : mn[2], -lim), fymin = fmaxf(v == 0 ? mn[1] : mn[3], -lim);
+      const float fxmax = fminf(v == 0 ? mx[0] : mx[2], lim), fymax = fminf(v == 0 ? mx[1] : mx[3], lim);
+      TileGeo g;
+      // box origin relative to R0 (the box must start on a 16-byte boundary of the frame row: image x0 = r0x + bx0 is
+      // rounded down to a multiple of 4), then in image coordinates
+      const int bx0 = (((int)floorf(fxmin) - TL_MARGIN + r0x[v]) & ~3) - r0x[v], by0 = (int)floorf(fymin) - TL_MARGIN;
+      const int need_w = (int)floorf(fxmax) + 2 + TL_MARGIN - bx0, need_h = (int)floorf(fymax) + 2 + TL_MARGIN - by0;
+      g.tx0 = r0x[v] + bx0;
+      g.ty0 = r0y[v] + by0;
+      const bool hits = g.tx0 + need_w > 0 && g.tx0 < W && g.ty0 + need_h > 0 && g.ty0 < H;
+      const bool use = hits && need_w <= TL_BW && need_h <= TL_BH && !(P.dbg & 1) && !((P.dbg & 2) && v == 1);
+      g.rows = use ? (need_h <= TL_BH0 ? TL_BH0 : need_h <= TL_BH1 ? TL_BH1 : TL_BH) : 0;
+      const int lox = max(0, -g.tx0), loy = max(0, -g.ty0);
+      g.wxn = use ? max(min(TL_BW - 1, W - 1 - g.tx0) - lox, 0) : 0;
+      g.wyn = use ? max(min(g.rows - 1, H - 1 - g.ty0) - loy, 0) : 0;
+      if (g.wxn == 0 || g.wyn == 0) { g.rows = 0; g.wxn = 0; g.wyn = 0; }
+      // window and index shift in R0-relative sample coordinates
+      g.lox = lox + bx0;
+      g.loy = loy + by0;
+      g.shift = by0 * TL_BW + bx0;
+      s_geo[v] = g;
+    }
+    __syncwarp();
+    // one thread issues the copies (a TMA instruction wants a single active lane): per view and colour plane one box
+    // of TL_BH0, TL_BH1 or TL_BH rows (three tensor maps per view), whichever covers the footprint
+    if (lane == 0) {
+      const int rows0 = s_geo[0].rows, rows1 = s_geo[1].rows;
+      if (rows0 + rows1 > 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tl_smem_u32(&s_bar)),
+                     "r"((uint32_t)((rows0 + rows1) * C * TL_BW * 4)) : "memory");
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int rows = v == 0 ? rows0 : rows1;
+          if (rows > 0) {
+            const CUtensorMap* map = v == 0 ? (rows == TL_BH0 ? &tm0a : rows == TL_BH1 ? &tm0b : &tm0c)
+                                            : (rows == TL_BH0 ? &tm1a : rows == TL_BH1 ? &tm1b : &tm1c);
+            const int tx0 = s_geo[v].tx0, ty0 = s_geo[v].ty0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              asm volatile(
+                  "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                  ::"r"(tl_smem_u32(tile + (v * C + c) * TL_PLANE)), "l"(map), "r"(tl_smem_u32(&s_bar)), "r"(tx0), "r"(ty0),
+                  "r"(n * C + c)
+                  : "memory");
+            }
+          }
+        }
+      }
+    }
+  }
+  u64 lxp[LAT_TAPS];
+#pragma unroll
+  for (int a = 0; a < LAT_TAPS; ++a) lxp[a] = pk2(lxw[a], lxw[a]);
+  // per-warp culling of the near list against this warp's 32 x TL_RPT block
+  unsigned cand = 0;
+  const bool cull = n_all <= 32;
+  if (n_all > 0) {
+    if (cull) {
+      bool keep = false;
+      if (lane < n_all) {
+        const float4 c = near_list[lane];
+        const float wx_lo = fmaf(P.stepx, (float)min(col0 + wx * 32, P.Wo - 1), -1.0f);
+        const float wx_hi = fmaf(P.stepx, (float)min(col0 + wx * 32 + 31, P.Wo - 1), -1.0f);
+        const float y_lo = fmaf(P.stepy, (float)min(row0 + rt0, P.Ho - 1), -1.0f);
+        const float y_hi = fmaf(P.stepy, (float)min(row0 + rt0 + TL_RPT - 1, P.Ho - 1), -1.0f);
+        const float ddx = fmaxf(fmaxf(wx_lo - c.x, c.x - wx_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
+        keep = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
+      }
+      cand = __ballot_sync(FULL, keep);
+    } else {
+      cand = FULL;
+    }
+  }
+  const unsigned oplane = (unsigned)(P.Ho * P.Wo);
+  float* outp = P.out + (size_t)n * C * oplane;
+  const float* imgv[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) imgv[v] = P.img[v] + (size_t)n * C * H * W;
+  __syncthreads();  // s_geo
+  int g_lox[V], g_wxn[V], g_loy[V], g_wyn[V];
+  uint32_t tbase[V];  // shared byte address of the view's staged box, pre-shifted so that R0-relative coordinates index it
+  const uint32_t tbase0 = tl_smem_u32(tile);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    g_lox[v] = s_geo[v].lox; g_wxn[v] = s_geo[v].wxn; g_loy[v] = s_geo[v].loy; g_wyn[v] = s_geo[v].wyn;
+    tbase[v] = tbase0 + (uint32_t)((v * (C * TL_PLANE) - s_geo[v].shift) * 4);
+  }
+  if (s_geo[0].rows + s_geo[1].rows > 0) {
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}\n"
+          : "=r"(ok)
+          : "r"(tl_smem_u32(&s_bar))
+          : "memory");
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < TL_RPT; ++i) {
+    const int r = rt0 + i, row = row0 + r;
+    if (row >= P.Ho) break;  // warp-uniform
+    // ---- x contraction: box-local source coordinates (x, y) of both views
+    u64 acc0, acc1;
+    {
+      const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(&ysm[r][js][0]);
+      acc0 = fmul2(q.x, lxp[0]);
+      acc1 = fmul2(q.y, lxp[0]);
+    }
+#pragma unroll
+    for (int a = 1; a < LAT_TAPS; ++a) {
+      const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(&ysm[r][js + a][0]);
+      acc0 = ffma2(q.x, lxp[a], acc0);
+      acc1 = ffma2(q.y, lxp[a], acc1);
+    }
+    float px[V], py[V];
+    upk2(acc0, px[0], py[0]);
+    upk2(acc1, px[1], py[1]);
+    // ---- near-field corrections (branch-free: s is clamped to R2, where psi vanishes)
+    if (cand != 0u) {
+      const float yt = fmaf(P.stepy, (float)row, -1.0f);
+      unsigned m = cull ? cand : 0u;
+      int kk = 0;
+#pragma unroll 1
+      while (cull ? (m != 0u) : (kk < n_all)) {
+        int k;
+        if (cull) { k = __ffs(m) - 1; m &= m - 1; } else { k = kk++; }
+        const float4 c = near_list[k];
+        const float dx = xt - c.x, dy = yt - c.y;
+        const float s = fminf(fmaf(dy, dy, dx * dx), P.R2);
+        const float psi = fmaf(s, lg2_approx(s + 1e-6f), -blend_poly(s, P.R2, P.q0, P.q1, P.q2, P.q3));
+        if (k < n0) { px[0] = fmaf(c.z, psi, px[0]); py[0] = fmaf(c.w, psi, py[0]); }
+        else { px[1] = fmaf(c.z, psi, px[1]); py[1] = fmaf(c.w, psi, py[1]); }
+      }
+    }
+    // ---- bilinear taps
+    float res[V][C];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int xi = __float2int_rd(px[v]), yi = __float2int_rd(py[v]);
+      const float fx = px[v] - (float)xi, fy = py[v] - (float)yi;
+      const bool ok = (unsigned)(xi - g_lox[v]) < (unsigned)g_wxn[v] && (unsigned)(yi - g_loy[v]) < (unsigned)g_wyn[v];
+      const unsigned okm = __ballot_sync(FULL, ok);
+      if (okm == FULL) {
+        // every lane's four taps are staged and inside the image
+        const float gx = 1.0f - fx, gy = 1.0f - fy;
+        const u64 wA = pk2(gx * gy, fx * gy), wB = pk2(gx * fy, fx * fy);
+        const uint32_t ad = tbase[v] + (uint32_t)(yi * (TL_BW * 4) + xi * 4);
+        tile_taps<0>(ad, wA, wB, res[v][0]);
+        tile_taps<TL_PLANE * 4>(ad, wA, wB, res[v][1]);
+        tile_taps<2 * TL_PLANE * 4>(ad, wA, wB, res[v][2]);
+      } else {
+        // image border, outside the image, or outside the staged box
+        const bool inimg = (unsigned)(xi + r0x[v]) < (unsigned)(W - 1) && (unsigned)(yi + r0y[v]) < (unsigned)(H - 1);
+        const bool slow = __any_sync(FULL, inimg && !ok);
+        const bool use = slow ? inimg : ok;
+        res[v][0] = res[v][1] = res[v][2] = 0.0f;
+        if (__any_sync(FULL, use)) {
+          const float fxs = use ? fx : 0.0f, gxs = use ? 1.0f - fx : 0.0f, fys = use ? fy : 0.0f, gys = 1.0f - fys;
+          const u64 wA = pk2(gxs * gys, fxs * gys), wB = pk2(gxs * fys, fxs * fys);
+          if (!slow) {
+            const uint32_t ad = use ? tbase[v] + (uint32_t)(yi * (TL_BW * 4) + xi * 4) : tbase0;
+            tile_taps<0>(ad, wA, wB, res[v][0]);
+            tile_taps<TL_PLANE * 4>(ad, wA, wB, res[v][1]);
+            tile_taps<2 * TL_PLANE * 4>(ad, wA, wB, res[v][2]);
+            if (!use) res[v][0] = res[v][1] = res[v][2] = 0.0f;  // tbase0 may hold stale bits (0 * NaN)
+          } else {
+            const float* p = imgv[v] + (use ? (size_t)(yi + r0y[v]) * W + (xi + r0x[v]) : (size_t)0);
+            const size_t iplane = (size_t)H * W;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const u64 top = pk2(__ldg(p + c * iplane), __ldg(p + c * iplane + 1));
+              const u64 bot = pk2(__ldg(p + c * iplane + W), __ldg(p + c * iplane + W + 1));
+              float lo, hi;
+              upk2(ffma2(bot, wB, fmul2(top, wA)), lo, hi);
+              res[v][c] = lo + hi;
+            }
+          }
+        }
+      }
+    }
+    // ---- AVERAGE blend (a*a + b*b) / (a + b + 1e-6) and streaming stores
+    if (active) {
+      const unsigned opix = (unsigned)(row * P.Wo + col);
+      const u64 A = pk2(res[0][0], res[0][1]), B = pk2(res[1][0], res[1][1]);
+      float s0, s1, q0, q1;
+      upk2(fadd2(fadd2(A, B), pk2(1e-6f, 1e-6f)), s0, s1);
+      upk2(ffma2(B, B, fmul2(A, A)), q0, q1);
+      __stcs(const_cast<float*>(f32_at(outp, opix)), q0 * rcp_approx(s0));
+      __stcs(const_cast<float*>(f32_at(outp, opix + oplane)), q1 * rcp_approx(s1));
+      __stcs(const_cast<float*>(f32_at(outp, opix + 2 * oplane)), blend_avg_fast(res[0][2], res[1][2]));
+    }
+  }
+}
+
 static inline float linstep(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 
 // lattice configuration: spacing (SX, SY) in canvas pixels and near radius R (normalised)
@@ -824,6 +1261,31 @@ size_t tps_lattice_workspace_floats(int bn, int Ho, int Wo) {
   return (size_t)bn * nx * ny * 2;
 }
 
+// The tile kernel needs TMA-addressable frames (16-byte aligned base and row pitch) and 32-bit output indexing.
+static bool tile_path_ok(const WarpParams& P, int nframes) {
+  const char* e = getenv("SS2_TPS_TILE");
+  if (e && atoi(e) == 0) return false;
+  if ((P.W & 3) || ((uintptr_t)P.img[0] & 15) || ((uintptr_t)P.img[1] & 15)) return false;
+  if (P.W < 2 || P.H < 2 || (double)P.Ho * P.Wo * 3.0 > 2.0e9 || (double)nframes * 3.0 > 2.0e9) return false;
+  return true;
+}
+
+// frames of one view as a 3-D tensor {W, H, nframes*3 planes}; box = TL_BW x box_rows elements of one plane, zero fill
+static bool make_img_map(CUtensorMap* map, const float* base, int W, int H, int planes, int box_rows) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ss2_tensormap_encode_fn());
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+  cuuint32_t box[3] = {TL_BW, (cuuint32_t)box_rows, 1};
+  cuuint32_t est[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, est,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int V, int C, bool BLEND>
 static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, float* d_nodes, cudaStream_t st) {
   const LatticeConfig cfg = lattice_config(P.Ho, P.Wo);
@@ -847,11 +1309,37 @@ static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, flo
     const int S[4] = {6, 8, 12, 16};
     for (int i = 0; i < 4; ++i) lagrange_table(S[i], &t[i]);
     SS2_CUDA(ctx, cudaMemcpyToSymbol(c_lag, t, sizeof(t)));
+    SS2_CUDA(ctx, cudaMemcpyToSymbol(g_lag, t, sizeof(t)));
     ctx->lag_tables_ready = true;
   }
   const int nnodes = P.nx * P.ny;
   tps_nodes_kernel<V><<<dim3(cdiv(nnodes, 128), V, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY);
   SS2_LAUNCH_CHECK(ctx);
+  { const char* e = getenv("SS2_TILE_DBG"); P.dbg = e ? atoi(e) : 0; }
+  if (BLEND && V == 2 && C == 3 && mode == SS2_MODE_NORMAL && tile_path_ok(P, nframes)) {
+    CUtensorMap m[2][3];
+    bool maps = true;
+    for (int v = 0; v < 2; ++v)
+      for (int h = 0; h < 3; ++h)
+        maps = maps && make_img_map(&m[v][h], P.img[v], P.W, P.H, nframes * 3, h == 0 ? TL_BH0 : h == 1 ? TL_BH1 : TL_BH);
+    if (maps) {
+      dim3 tgrid(cdiv(P.Wo, TL_W), cdiv(P.Ho, TL_H), nframes);
+#define TILE_CASE(SXV, SYV)                                                                                     \
+      if (cfg.SX == SXV && cfg.SY == SYV) {                                                                     \
+        static bool attr = false;                                                                               \
+        if (!attr) {                                                                                            \
+          SS2_CUDA(ctx, cudaFuncSetAttribute(tps_warp_tile_kernel<SXV, SYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM_BYTES)); \
+          SS2_CUDA(ctx, cudaFuncSetAttribute(tps_warp_tile_kernel<SXV, SYV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+          attr = true;                                                                                          \
+        }                                                                                                       \
+        tps_warp_tile_kernel<SXV, SYV><<<tgrid, TL_THREADS, TL_SMEM_BYTES, st>>>(m[0][0], m[0][1], m[0][2], m[1][0], m[1][1], m[1][2], P);                    \
+      }
+      TILE_CASE(16, 8) TILE_CASE(16, 6) TILE_CASE(12, 8) TILE_CASE(12, 6) TILE_CASE(8, 8) TILE_CASE(8, 6)
+#undef TILE_CASE
+      SS2_LAUNCH_CHECK(ctx);
+      return SS2_OK;
+    }
+  }
   dim3 grid(cdiv(P.Wo, LAT_THREADS), cdiv(P.Ho, cfg.SY * LAT_NCELL), nframes);
   // source-size specialisations of the production (fused, NORMAL) kernel: 720p and 1080p
   const int spec = (BLEND && mode == SS2_MODE_NORMAL) ? ((P.W == 1280 && P.H == 720) ? 1 : (P.W == 1920 && P.H == 1080) ? 2 : 0) : 0;

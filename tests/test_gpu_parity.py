@@ -307,6 +307,23 @@ def test_fullsize_frame_vs_oracle_and_arbiter(tps):
                   % (v, tps, e_got.max(), e_got.mean(), e_ref.max(), e_ref.mean()))
             assert e_got.max() < 1.5 * e_ref.max() + 2e-4   # the max of rounding noise is itself noisy
             assert e_got.mean() < 1.2 * e_ref.mean() + 2e-5
+    # ---- the same check through the FUSED kernel (the production resampler evaluates the field in tile-local
+    # coordinates): view v carries the coordinate ramp, the other view is black, so fused = a*a/(a+1e-6) ~ a
+    zero = torch.zeros_like(ramp)
+    for v, M in enumerate((M1, M2)):
+        tt = torch.stack([M[0, 0, ..., 0] - wmin, M[0, 0, ..., 1] - hmin], 2)[None]
+        src = O.norm_mesh(tt, oh, ow)
+        ax, ay = O.tps_source_coords_fp64(src, nrig, Ho, Wo, W, H)
+        ref = O.tps_warp(ramp, src, nrig, (Ho, Wo)).numpy()[0]
+        a, b = (ramp, zero) if v == 0 else (zero, ramp)
+        got = pipeline.stable_frames(a.cuda(), b.cuda(), m1, m2, mm, tps=mode)[0].cpu().numpy()
+        inside = (ax[0] > 2) & (ax[0] < W - 2) & (ay[0] > 2) & (ay[0] < H - 2)
+        for got_c, ref_c, arb in ((got[0], ref[0], ax[0]), (got[1], ref[1], ay[0])):
+            e_got, e_ref = np.abs(got_c - arb)[inside], np.abs(ref_c - arb)[inside]
+            print("view %d %s FUSED coord err vs fp64 (px): ours max %.2e mean %.2e | reference max %.2e mean %.2e"
+                  % (v, tps, e_got.max(), e_got.mean(), e_ref.max(), e_ref.mean()))
+            assert e_got.max() < 1.5 * e_ref.max() + 2e-4
+            assert e_got.mean() < 1.2 * e_ref.mean() + 2e-5
     # ---- pixel space on the textured frame: gradient-scaled bound, hard-edge flips as a fraction
     d = (fused.cpu() - fused_ref).abs().numpy()
     bound = max(grad_max(hr1), grad_max(hr2)) * COORD_TOL_PX + 1e-3
@@ -365,7 +382,14 @@ def test_fullsize_properties():
     w = transformer(torch.cat([img, img2], 0), src, tgt, (Ho, Wo))
     fused = warp_blend_average(img, img2, src[None], tgt[None], (Ho, Wo))[0]
     s = w[0] + w[1] + 1e-6
-    assert (fused - (w[0] * (w[0] / s) + w[1] * (w[1] / s))).abs().max().item() < 1e-4
+    # The fused kernel stages source tiles and evaluates the field in tile-local coordinates, the generic
+    # kernel in frame coordinates: two fp32 roundings of the same field (each checked against the fp64
+    # arbiter in test_fullsize_frame_vs_oracle_and_arbiter), so the bound is gradient x coordinate noise;
+    # a sample that flips across the hard image edge is counted as a fraction.
+    d = (fused - (w[0] * (w[0] / s) + w[1] * (w[1] / s))).abs()
+    bound = max(grad_max(img), grad_max(img2)) * COORD_TOL_PX + 1e-3
+    assert (d > bound).float().mean().item() < 2e-4, ((d > bound).float().mean().item(), d.max().item(), bound)
+    assert d.median().item() < 1e-4
 
 
 # ---------------------------------------------------------------- convolution kernels (SIMT fp32 and tcgen05)
