@@ -799,15 +799,28 @@ tps_warp_lattice_kernel(WarpParams P) {
 // Three CTAs (3 x 66 KB) are resident per SM; one's TMA wait overlaps the others' sampling.
 // ------------------------------------------------------------------------------------------
 #define TL_W 64
-#define TL_H 16
+#ifndef TL_RPT
+#define TL_RPT 8   // canvas rows per thread (a warp owns a 32 x TL_RPT block)
+#endif
+#define TL_H (4 * TL_RPT)
 #define TL_THREADS 256
-#define TL_RPT 4  // canvas rows per thread (a warp owns a 32 x 4 block)
-#define TL_BW 96   // staged box: columns
-#define TL_BH 28   //             rows; TMA boxes of TL_BH0, TL_BH1 or TL_BH rows, whichever the footprint needs
+#if TL_RPT == 8
+#define TL_BW 88   // staged box: columns
+#define TL_BH 44   //             rows; TMA boxes of TL_BH0, TL_BH1 or TL_BH rows, whichever the footprint needs
+#define TL_BH0 36
+#define TL_BH1 40
+#define TL_MINB 2
+#define TL_UNROLL 2
+#else
+#define TL_BW 96
+#define TL_BH 28
 #define TL_BH0 16
 #define TL_BH1 24
+#define TL_MINB 3
+#define TL_UNROLL 4
+#endif
 #define TL_PLANE (TL_BW * TL_BH)
-#define TL_MARGIN 3
+#define TL_MARGIN 4
 #define TL_SMEM_BYTES (2 * 3 * TL_PLANE * 4)
 
 typedef unsigned long long u64;
@@ -865,17 +878,17 @@ template <int SX> struct TileCols { static constexpr int value = (TL_W + SX - 1)
 __device__ LagrangeTable g_lag[4];  // the same tables in global memory: lanes read DIFFERENT rows (constant memory would serialise)
 
 template <int SX, int SY>
-__global__ void __launch_bounds__(TL_THREADS, 3)
+__global__ void __launch_bounds__(TL_THREADS, TL_MINB)
 tps_warp_tile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_constant__ CUtensorMap tm0b,
                      const __grid_constant__ CUtensorMap tm0c, const __grid_constant__ CUtensorMap tm1a,
                      const __grid_constant__ CUtensorMap tm1b, const __grid_constant__ CUtensorMap tm1c, WarpParams P) {
   constexpr int V = 2, C = 3;
   constexpr int NCOL = TileCols<SX>::value;
-  constexpr int NLW = (V * SS2_NPT + 31) / 32;  // warps that test the control points
+  constexpr int GEOW = TL_THREADS / 32 - 1;       // the warp that owns predictor, box geometry and TMA issue
   extern __shared__ __align__(128) float tile[];  // [V][3][TL_BH][TL_BW], TMA destination
   __shared__ float4 near_list[V * SS2_NPT];
   __shared__ __align__(16) float2 ysm[TL_H][NCOL][V];
-  __shared__ int warp_cnt[NLW][2];
+  __shared__ int s_cnt[2];
   __shared__ float s_pred[V][6];
   __shared__ float s_r0f[V][2];
   __shared__ int s_r0[V][2];
@@ -887,127 +900,81 @@ tps_warp_tile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_cons
   const int W = P.W, H = P.H;
   const unsigned FULL = 0xffffffffu;
 
-  // ---- phase 0: control points whose disc s < R2 touches the tile (warps 0..NLW-1); predictor and the integer
-  // reference origin R0 = floor(predictor at the tile origin) of each view (last warp); barrier
-  float4 ent = make_float4(0.f, 0.f, 0.f, 0.f);
-  bool hit = false;
-  unsigned m_all = 0;
-  if (wid < NLW) {
-    const int pv = tid / SS2_NPT, pi = tid - pv * SS2_NPT;
-    if (tid < V * SS2_NPT) {
-      const float x_lo = fmaf(P.stepx, (float)col0, -1.0f), x_hi = fmaf(P.stepx, (float)min(col0 + TL_W - 1, P.Wo - 1), -1.0f);
-      const float y_lo = fmaf(P.stepy, (float)row0, -1.0f), y_hi = fmaf(P.stepy, (float)min(row0 + TL_H - 1, P.Ho - 1), -1.0f);
-      const float2 c = *reinterpret_cast<const float2*>(P.source + ((size_t)(n * V + pv) * SS2_NPT + pi) * 2);
-      const float ddx = fmaxf(fmaxf(x_lo - c.x, c.x - x_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
-      hit = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
-      if (hit) {
-        const float* t = P.T + (size_t)(n * V + pv) * 2 * SS2_NSYS;
-        ent = make_float4(c.x, c.y, t[3 + pi] * (P.half_w * LN2F), t[SS2_NSYS + 3 + pi] * (P.half_h * LN2F));
+  // ---- phase 0, warp 0: near list = control points whose disc s < R2 touches the tile (view-0 entries first)
+  if (wid == 0) {
+    const float x_lo = fmaf(P.stepx, (float)col0, -1.0f), x_hi = fmaf(P.stepx, (float)min(col0 + TL_W - 1, P.Wo - 1), -1.0f);
+    const float y_lo = fmaf(P.stepy, (float)row0, -1.0f), y_hi = fmaf(P.stepy, (float)min(row0 + TL_H - 1, P.Ho - 1), -1.0f);
+    int cnt = 0, cnt0 = 0;
+#pragma unroll
+    for (int it = 0; it < (V * SS2_NPT + 31) / 32; ++it) {
+      const int idx = it * 32 + lane;
+      bool hit = false;
+      float2 c = make_float2(0.f, 0.f);
+      if (idx < V * SS2_NPT) {
+        c = *reinterpret_cast<const float2*>(P.source + ((size_t)n * V * SS2_NPT + idx) * 2);
+        const float ddx = fmaxf(fmaxf(x_lo - c.x, c.x - x_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
+        hit = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
       }
+      const unsigned m = __ballot_sync(FULL, hit);
+      if (hit) {
+        const int pv = idx >= SS2_NPT ? 1 : 0, pi = idx - pv * SS2_NPT;
+        const float* t = P.T + (size_t)(n * V + pv) * 2 * SS2_NSYS;
+        near_list[cnt + __popc(m & ((1u << lane) - 1u))] =
+            make_float4(c.x, c.y, t[3 + pi] * (P.half_w * LN2F), t[SS2_NSYS + 3 + pi] * (P.half_h * LN2F));
+      }
+      cnt += __popc(m);
+      // entries of view 0 are idx < 63: whole iteration 0, the first 31 lanes of iteration 1
+      cnt0 += it == 0 ? __popc(m) : (it == 1 ? __popc(m & ((1u << (SS2_NPT - 32)) - 1u)) : 0);
     }
-    m_all = __ballot_sync(FULL, hit);
-    const unsigned m_v0 = __ballot_sync(FULL, hit && pv == 0);
-    if (lane == 0) { warp_cnt[wid][0] = __popc(m_all); warp_cnt[wid][1] = __popc(m_v0); }
-  } else if (wid == TL_THREADS / 32 - 1) {
+    if (lane == 0) { s_cnt[0] = cnt; s_cnt[1] = cnt0; }
+  } else if (wid == GEOW) {
+    // ---- phase 0, last warp: predictor, R0 = floor(predictor at the tile origin), box geometry from an ESTIMATE of
+    // the tile's source footprint (predictor + the residual of the nearest lattice node at the tile's corners and
+    // edge midpoints; residuals vary by a fraction of a pixel between nodes, the margin absorbs it and the per-sample
+    // window test keeps the result independent of it), TMA issue: the copies fly while the CTA does phase 1
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tl_smem_u32(&s_bar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     float pr = 0.f;
     if (lane < V * 6) {
       pr = P.aux[(size_t)(n * V + lane / 6) * 8 + lane % 6];
       s_pred[lane / 6][lane % 6] = pr;
     }
-    // lanes 6v + {0, 3}: x and y of view v
-    const float p1 = __shfl_down_sync(FULL, pr, 1), p2 = __shfl_down_sync(FULL, pr, 2);
-    if (lane < V * 6 && (lane % 3) == 0) {
-      const double b = (double)pr * col0 + (double)p1 * row0 + (double)p2;
-      const double fb = floor(fmin(fmax(b, -1.0e6), 1.0e6));
-      s_r0[lane / 6][(lane % 6) / 3] = (int)fb;
-      s_r0f[lane / 6][(lane % 6) / 3] = (float)(b - fb);
-    }
-    if (lane == 31) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tl_smem_u32(&s_bar)));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-  }
-  __syncthreads();
-  int n0 = 0, n_all = 0;
+    float pd[V][6];
 #pragma unroll
-  for (int w = 0; w < NLW; ++w) { n_all += warp_cnt[w][0]; n0 += warp_cnt[w][1]; }
-  if (hit) {
-    int off = 0;
+    for (int q = 0; q < V * 6; ++q) pd[q / 6][q % 6] = __shfl_sync(FULL, pr, q);
+    int r0[V][2];
+    float base[V][2];  // predictor at the tile origin minus R0
 #pragma unroll
-    for (int w = 0; w < NLW; ++w)
-      if (w < wid) off += warp_cnt[w][0];
-    near_list[off + __popc(m_all & ((1u << lane) - 1u))] = ent;
-  }
-  int r0x[V], r0y[V];
+    for (int v = 0; v < V; ++v)
 #pragma unroll
-  for (int v = 0; v < V; ++v) { r0x[v] = s_r0[v][0]; r0y[v] = s_r0[v][1]; }
-  // ---- phase 1: y contraction of the tile's node columns with the predictor folded in, relative to R0:
-  // ysm[r][j][v] = sum_b Ly[b] node[cy+b][jx0+j] + pred(node column, row) - R0
-  for (int item = tid; item < TL_H * NCOL; item += TL_THREADS) {
-    const int r = item / NCOL, j = item - r * NCOL;
-    if (jx0 + j < P.nx) {
-      const int row = min(row0 + r, P.Ho - 1);
-      const int cy = row / SY, ry = row - cy * SY;
-      const float2* nd = P.nodes + (((size_t)n * P.ny + cy) * P.nx + (jx0 + j)) * V;
-      const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SY)].w[ry][0]));
-      const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SY)].w[ry][4]));
-      const float wy[LAT_TAPS] = {wlo.x, wlo.y, wlo.z, wlo.w, whi.x, whi.y};
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-      for (int b = 0; b < LAT_TAPS; ++b) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(nd + (size_t)b * P.nx * V));
-        a0 = fmaf(wy[b], q.x, a0); a1 = fmaf(wy[b], q.y, a1); a2 = fmaf(wy[b], q.z, a2); a3 = fmaf(wy[b], q.w, a3);
+      for (int d = 0; d < 2; ++d) {
+        const double b = (double)pd[v][3 * d] * col0 + (double)pd[v][3 * d + 1] * row0 + (double)pd[v][3 * d + 2];
+        const double fb = floor(fmin(fmax(b, -1.0e6), 1.0e6));
+        r0[v][d] = (int)fb;
+        base[v][d] = (float)(b - fb);
       }
-      const float cr = (float)((jx0 + j - LAT_LO) * SX - col0), rr = (float)(row - row0);
-      a0 += fmaf(s_pred[0][0], cr, fmaf(s_pred[0][1], rr, s_r0f[0][0]));
-      a1 += fmaf(s_pred[0][3], cr, fmaf(s_pred[0][4], rr, s_r0f[0][1]));
-      a2 += fmaf(s_pred[1][0], cr, fmaf(s_pred[1][1], rr, s_r0f[1][0]));
-      a3 += fmaf(s_pred[1][3], cr, fmaf(s_pred[1][4], rr, s_r0f[1][1]));
-      *reinterpret_cast<float4*>(&ysm[r][j][0]) = make_float4(a0, a1, a2, a3);
-    }
-  }
-  // ---- per-thread constants: one canvas column, TL_RPT consecutive rows (a warp owns a 32 x TL_RPT block)
-  const int wx = wid & 1, wy = wid >> 1;
-  const int colt = wx * 32 + lane, rt0 = wy * TL_RPT;
-  const int col = min(col0 + colt, P.Wo - 1);
-  const bool active = col0 + colt < P.Wo;
-  const int cxi = col / SX, rx = col - cxi * SX, js = cxi - jx0;
-  float lxw[LAT_TAPS];
-  {
-    const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SX)].w[rx][0]));
-    const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SX)].w[rx][4]));
-    lxw[0] = wlo.x; lxw[1] = wlo.y; lxw[2] = wlo.z; lxw[3] = wlo.w; lxw[4] = whi.x; lxw[5] = whi.y;
-  }
-  const float xt = fmaf(P.stepx, (float)col, -1.0f);
-  __syncthreads();  // ysm complete
-  // ---- phase 2 (warp 0): source footprint of the tile from the field at its corners and edge midpoints (an extremum
-  // of a fold-free, nearly affine map over a rectangle lies at a corner; the margin and the slow path cover the rest),
-  // box geometry, TMA issue
-  if (wid == 0) {
+    if (lane < V * 2) { s_r0[lane >> 1][lane & 1] = r0[lane >> 1][lane & 1]; s_r0f[lane >> 1][lane & 1] = base[lane >> 1][lane & 1]; }
     const int lastc = min(TL_W - 1, P.Wo - 1 - col0), lastr = min(TL_H - 1, P.Ho - 1 - row0);
-    const int k = lane & 7;  // 3 x 3 sample points without the centre
-    const int kk = k < 4 ? k : k + 1;
-    const int pr = (kk / 3) * lastr / 2, pc = (kk % 3) * lastc / 2;
-    const int pcol = col0 + pc, pcx = pcol / SX, prx = pcol - pcx * SX, pjs = pcx - jx0;
-    float e[4] = {0.f, 0.f, 0.f, 0.f};
-    {
-      const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SX)].w[prx][0]));
-      const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SX)].w[prx][4]));
-      const float wq[LAT_TAPS] = {wlo.x, wlo.y, wlo.z, wlo.w, whi.x, whi.y};
-#pragma unroll
-      for (int a = 0; a < LAT_TAPS; ++a) {
-        const float4 q = *reinterpret_cast<const float4*>(&ysm[pr][pjs + a][0]);
-        e[0] = fmaf(wq[a], q.x, e[0]); e[1] = fmaf(wq[a], q.y, e[1]); e[2] = fmaf(wq[a], q.z, e[2]); e[3] = fmaf(wq[a], q.w, e[3]);
-      }
-    }
+    const int k = lane & 7, kk = k < 4 ? k : k + 1;  // 3 x 3 sample points without the centre
+    const int pr_ = (kk / 3) * lastr / 2, pc_ = (kk % 3) * lastc / 2;
+    const int ix = min((col0 + pc_ + SX / 2) / SX, P.nx - 1 - LAT_LO), iy = min((row0 + pr_ + SY / 2) / SY, P.ny - 1 - LAT_LO);
+    const float4 q = __ldg(reinterpret_cast<const float4*>(P.nodes + (((size_t)n * P.ny + iy + LAT_LO) * P.nx + ix + LAT_LO) * V));
+    const float fc = (float)pc_, fr = (float)pr_;
+    float e[4];
+    e[0] = q.x + fmaf(pd[0][0], fc, fmaf(pd[0][1], fr, base[0][0]));
+    e[1] = q.y + fmaf(pd[0][3], fc, fmaf(pd[0][4], fr, base[0][1]));
+    e[2] = q.z + fmaf(pd[1][0], fc, fmaf(pd[1][1], fr, base[1][0]));
+    e[3] = q.w + fmaf(pd[1][3], fc, fmaf(pd[1][4], fr, base[1][1]));
     float mn[4], mx[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      mn[q] = mx[q] = e[q];
+    for (int d = 0; d < 4; ++d) {
+      mn[d] = mx[d] = e[d];
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
-        mn[q] = fminf(mn[q], __shfl_xor_sync(FULL, mn[q], o));
-        mx[q] = fmaxf(mx[q], __shfl_xor_sync(FULL, mx[q], o));
+        mn[d] = fminf(mn[d], __shfl_xor_sync(FULL, mn[d], o));
+        mx[d] = fmaxf(mx[d], __shfl_xor_sync(FULL, mx[d], o));
       }
     }
     if (lane < V) {
@@ -1015,13 +982,14 @@ tps_warp_tile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_cons
       const float lim = 1.0e6f;
       const float fxmin = fmaxf(v == 0 ? mn[0] : mn[2], -lim), fymin = fmaxf(v == 0 ? mn[1] : mn[3], -lim);
       const float fxmax = fminf(v == 0 ? mx[0] : mx[2], lim), fymax = fminf(v == 0 ? mx[1] : mx[3], lim);
+      const int rx0 = v == 0 ? r0[0][0] : r0[1][0], ry0 = v == 0 ? r0[0][1] : r0[1][1];
       TileGeo g;
-      // box origin relative to R0 (the box must start on a 16-byte boundary of the frame row: image x0 = r0x + bx0 is
+      // box origin relative to R0 (the box must start on a 16-byte boundary of the frame row: image x0 = rx0 + bx0 is
       // rounded down to a multiple of 4), then in image coordinates
-      const int bx0 = (((int)floorf(fxmin) - TL_MARGIN + r0x[v]) & ~3) - r0x[v], by0 = (int)floorf(fymin) - TL_MARGIN;
+      const int bx0 = (((int)floorf(fxmin) - TL_MARGIN + rx0) & ~3) - rx0, by0 = (int)floorf(fymin) - TL_MARGIN;
       const int need_w = (int)floorf(fxmax) + 2 + TL_MARGIN - bx0, need_h = (int)floorf(fymax) + 2 + TL_MARGIN - by0;
-      g.tx0 = r0x[v] + bx0;
-      g.ty0 = r0y[v] + by0;
+      g.tx0 = rx0 + bx0;
+      g.ty0 = ry0 + by0;
       const bool hits = g.tx0 + need_w > 0 && g.tx0 < W && g.ty0 + need_h > 0 && g.ty0 < H;
       const bool use = hits && need_w <= TL_BW && need_h <= TL_BH && !(P.dbg & 1) && !((P.dbg & 2) && v == 1);
       g.rows = use ? (need_h <= TL_BH0 ? TL_BH0 : need_h <= TL_BH1 ? TL_BH1 : TL_BH) : 0;
@@ -1063,6 +1031,49 @@ tps_warp_tile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_cons
       }
     }
   }
+  // ---- per-thread constants: one canvas column, TL_RPT consecutive rows (a warp owns a 32 x TL_RPT block)
+  const int wx = wid & 1, wy = wid >> 1;
+  const int colt = wx * 32 + lane, rt0 = wy * TL_RPT;
+  const int col = min(col0 + colt, P.Wo - 1);
+  const bool active = col0 + colt < P.Wo;
+  const int cxi = col / SX, rx = col - cxi * SX, js = cxi - jx0;
+  float lxw[LAT_TAPS];
+  {
+    const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SX)].w[rx][0]));
+    const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SX)].w[rx][4]));
+    lxw[0] = wlo.x; lxw[1] = wlo.y; lxw[2] = wlo.z; lxw[3] = wlo.w; lxw[4] = whi.x; lxw[5] = whi.y;
+  }
+  const float xt = fmaf(P.stepx, (float)col, -1.0f);
+  __syncthreads();  // near list, predictor, R0, box geometry
+  const int n_all = s_cnt[0], n0 = s_cnt[1];
+  int r0x[V], r0y[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) { r0x[v] = s_r0[v][0]; r0y[v] = s_r0[v][1]; }
+  // ---- phase 1: y contraction of the tile's node columns with the predictor folded in, relative to R0:
+  // ysm[r][j][v] = sum_b Ly[b] node[cy+b][jx0+j] + pred(node column, row) - R0
+  for (int item = tid; item < TL_H * NCOL; item += TL_THREADS) {
+    const int r = item / NCOL, j = item - r * NCOL;
+    if (jx0 + j < P.nx) {
+      const int row = min(row0 + r, P.Ho - 1);
+      const int cy = row / SY, ry = row - cy * SY;
+      const float2* nd = P.nodes + (((size_t)n * P.ny + cy) * P.nx + (jx0 + j)) * V;
+      const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SY)].w[ry][0]));
+      const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SY)].w[ry][4]));
+      const float wy_[LAT_TAPS] = {wlo.x, wlo.y, wlo.z, wlo.w, whi.x, whi.y};
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int b = 0; b < LAT_TAPS; ++b) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(nd + (size_t)b * P.nx * V));
+        a0 = fmaf(wy_[b], q.x, a0); a1 = fmaf(wy_[b], q.y, a1); a2 = fmaf(wy_[b], q.z, a2); a3 = fmaf(wy_[b], q.w, a3);
+      }
+      const float cr = (float)((jx0 + j - LAT_LO) * SX - col0), rr = (float)(row - row0);
+      a0 += fmaf(s_pred[0][0], cr, fmaf(s_pred[0][1], rr, s_r0f[0][0]));
+      a1 += fmaf(s_pred[0][3], cr, fmaf(s_pred[0][4], rr, s_r0f[0][1]));
+      a2 += fmaf(s_pred[1][0], cr, fmaf(s_pred[1][1], rr, s_r0f[1][0]));
+      a3 += fmaf(s_pred[1][3], cr, fmaf(s_pred[1][4], rr, s_r0f[1][1]));
+      *reinterpret_cast<float4*>(&ysm[r][j][0]) = make_float4(a0, a1, a2, a3);
+    }
+  }
   u64 lxp[LAT_TAPS];
 #pragma unroll
   for (int a = 0; a < LAT_TAPS; ++a) lxp[a] = pk2(lxw[a], lxw[a]);
@@ -1091,7 +1102,6 @@ tps_warp_tile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_cons
   const float* imgv[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) imgv[v] = P.img[v] + (size_t)n * C * H * W;
-  __syncthreads();  // s_geo
   int g_lox[V], g_wxn[V], g_loy[V], g_wyn[V];
   uint32_t tbase[V];  // shared byte address of the view's staged box, pre-shifted so that R0-relative coordinates index it
   const uint32_t tbase0 = tl_smem_u32(tile);
@@ -1100,7 +1110,9 @@ tps_warp_tile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_cons
     g_lox[v] = s_geo[v].lox; g_wxn[v] = s_geo[v].wxn; g_loy[v] = s_geo[v].loy; g_wyn[v] = s_geo[v].wyn;
     tbase[v] = tbase0 + (uint32_t)((v * (C * TL_PLANE) - s_geo[v].shift) * 4);
   }
-  if (s_geo[0].rows + s_geo[1].rows > 0) {
+  const bool staged = s_geo[0].rows + s_geo[1].rows > 0;
+  __syncthreads();  // ysm complete
+  if (staged) {
     uint32_t ok = 0;
     while (!ok) {
       asm volatile(
@@ -1115,7 +1127,8 @@ tps_warp_tile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_cons
     }
   }
 
-#pragma unroll
+  constexpr int kUnroll = TL_UNROLL;
+#pragma unroll kUnroll
   for (int i = 0; i < TL_RPT; ++i) {
     const int r = rt0 + i, row = row0 + r;
     if (row >= P.Ho) break;  // warp-uniform
@@ -1263,8 +1276,11 @@ size_t tps_lattice_workspace_floats(int bn, int Ho, int Wo) {
 
 // The tile kernel needs TMA-addressable frames (16-byte aligned base and row pitch) and 32-bit output indexing.
 static bool tile_path_ok(const WarpParams& P, int nframes) {
+  // Opt-in (SS2_TPS_TILE=1): measured on B200 (round 1, 720p) the staged kernel runs 17-19 us per frame against
+  // 12.8 us of tps_warp_lattice_kernel: its per-tile prologue + TMA wait leave the SM under-occupied (2-3 CTAs), and
+  // tiles whose footprint exceeds the box fall back to global loads.  DESIGN.md section 4.1 has the numbers.
   const char* e = getenv("SS2_TPS_TILE");
-  if (e && atoi(e) == 0) return false;
+  if (!e || atoi(e) == 0) return false;
   if ((P.W & 3) || ((uintptr_t)P.img[0] & 15) || ((uintptr_t)P.img[1] & 15)) return false;
   if (P.W < 2 || P.H < 2 || (double)P.Ho * P.Wo * 3.0 > 2.0e9 || (double)nframes * 3.0 > 2.0e9) return false;
   return true;

@@ -42,7 +42,7 @@ def main():
     N = int(a[2]) if len(a) >= 3 else 8
     hr1 = torch.cat([synthetic.synth_frame(k, 0, H, W) for k in range(N)], 0).cuda()
     hr2 = torch.cat([synthetic.synth_frame(k, 1, H, W) for k in range(N)], 0).cuda()
-    for name, kw in (("bench-like", dict(shift=170.0, amp=4.0)), ("rotated 3deg", dict(shift=120.0, amp=3.0, rot=0.052)),
+    for name, kw in (("smooth", dict(shift=170.0, amp=1.0)), ("bench-like", dict(shift=170.0, amp=4.0)), ("rotated 3deg", dict(shift=120.0, amp=3.0, rot=0.052)),
                      ("strong", dict(shift=60.0, amp=12.0, rot=-0.1))):
         m1 = meshes(N, 1, 0.0, kw["amp"], kw.get("rot", 0.0) * 0.5).cuda()
         m2 = meshes(N, 2, kw["shift"], kw["amp"], kw.get("rot", 0.0)).cuda()

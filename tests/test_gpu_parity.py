@@ -16,6 +16,8 @@ Tolerances (fp32 path; all stated in the unit of the quantity):
   - mesh vertices (networks): 5e-3 px at 480x360 against the CPU reference (exact-fp32 SIMT
     convolutions differ from MKL/oneDNN only by summation order); see DESIGN.md for TF32.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -309,21 +311,33 @@ def test_fullsize_frame_vs_oracle_and_arbiter(tps):
             assert e_got.mean() < 1.2 * e_ref.mean() + 2e-5
     # ---- the same check through the FUSED kernel (the production resampler evaluates the field in tile-local
     # coordinates): view v carries the coordinate ramp, the other view is black, so fused = a*a/(a+1e-6) ~ a
+    # SS2_TPS_TILE=1 selects the opt-in TMA-staged tile kernel (lattice mode only), 0 the default direct-load kernel
     zero = torch.zeros_like(ramp)
-    for v, M in enumerate((M1, M2)):
-        tt = torch.stack([M[0, 0, ..., 0] - wmin, M[0, 0, ..., 1] - hmin], 2)[None]
-        src = O.norm_mesh(tt, oh, ow)
-        ax, ay = O.tps_source_coords_fp64(src, nrig, Ho, Wo, W, H)
-        ref = O.tps_warp(ramp, src, nrig, (Ho, Wo)).numpy()[0]
-        a, b = (ramp, zero) if v == 0 else (zero, ramp)
-        got = pipeline.stable_frames(a.cuda(), b.cuda(), m1, m2, mm, tps=mode)[0].cpu().numpy()
-        inside = (ax[0] > 2) & (ax[0] < W - 2) & (ay[0] > 2) & (ay[0] < H - 2)
-        for got_c, ref_c, arb in ((got[0], ref[0], ax[0]), (got[1], ref[1], ay[0])):
-            e_got, e_ref = np.abs(got_c - arb)[inside], np.abs(ref_c - arb)[inside]
-            print("view %d %s FUSED coord err vs fp64 (px): ours max %.2e mean %.2e | reference max %.2e mean %.2e"
-                  % (v, tps, e_got.max(), e_got.mean(), e_ref.max(), e_ref.mean()))
-            assert e_got.max() < 1.5 * e_ref.max() + 2e-4
-            assert e_got.mean() < 1.2 * e_ref.mean() + 2e-5
+    for tile in (("0", "1") if tps == "lattice" else ("0",)):
+        os.environ["SS2_TPS_TILE"] = tile
+        try:
+            for v, M in enumerate((M1, M2)):
+                tt = torch.stack([M[0, 0, ..., 0] - wmin, M[0, 0, ..., 1] - hmin], 2)[None]
+                src = O.norm_mesh(tt, oh, ow)
+                ax, ay = O.tps_source_coords_fp64(src, nrig, Ho, Wo, W, H)
+                ref = O.tps_warp(ramp, src, nrig, (Ho, Wo)).numpy()[0]
+                a, b = (ramp, zero) if v == 0 else (zero, ramp)
+                got = pipeline.stable_frames(a.cuda(), b.cuda(), m1, m2, mm, tps=mode)[0].cpu().numpy()
+                inside = (ax[0] > 2) & (ax[0] < W - 2) & (ay[0] > 2) & (ay[0] < H - 2)
+                for got_c, ref_c, arb in ((got[0], ref[0], ax[0]), (got[1], ref[1], ay[0])):
+                    e_got, e_ref = np.abs(got_c - arb)[inside], np.abs(ref_c - arb)[inside]
+                    print("view %d %s tile=%s FUSED coord err vs fp64 (px): ours max %.2e mean %.2e | reference max %.2e mean %.2e"
+                          % (v, tps, tile, e_got.max(), e_got.mean(), e_ref.max(), e_ref.mean()))
+                    assert e_got.max() < 1.5 * e_ref.max() + 2e-4
+                    assert e_got.mean() < 1.2 * e_ref.mean() + 2e-5
+            if tile == "1":
+                # the staged kernel against the oracle frame, same bounds as the default kernel below
+                f_t = pipeline.stable_frames(hr1.cuda(), hr2.cuda(), m1, m2, mm, tps=mode)[0]
+                dt = (f_t.cpu() - fused_ref).abs().numpy()
+                bt = max(grad_max(hr1), grad_max(hr2)) * COORD_TOL_PX + 1e-3
+                assert (dt > bt).mean() < 5e-4 and np.median(dt) < 2e-3 and (dt > 0.05).mean() < 5e-4
+        finally:
+            os.environ.pop("SS2_TPS_TILE", None)
     # ---- pixel space on the textured frame: gradient-scaled bound, hard-edge flips as a fraction
     d = (fused.cpu() - fused_ref).abs().numpy()
     bound = max(grad_max(hr1), grad_max(hr2)) * COORD_TOL_PX + 1e-3
