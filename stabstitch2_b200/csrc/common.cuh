@@ -118,6 +118,7 @@ struct ss2_ctx {
   int use_tc = 1;  // tcgen05 implicit-GEMM path for eligible layers
   bool lag_tables_ready = false;
   int tc_passes = 3;  // 3 = split-TF32 (fp32-grade), 1 = plain TF32
+  int use_dc = 1;     // direct 3x3 kernel (conv_dc.cu) for eligible layers; SS2_CONV_DC=0 disables
 };
 
 int ss2_fail(ss2_ctx* ctx, int code, const char* fmt, ...);
@@ -239,6 +240,10 @@ int conv_tc_corr_rows(int W);
 int conv_tc_corr_launch(ss2_ctx* ctx, const ActRef& n1, const ActRef& n2, int B, int H, int W, int C, float* d_match,
                         int ldo, cudaStream_t st);
 int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D, int H, int W, const ActRef& out,
+                   const float* d_residual, int relu, cudaStream_t st);
+// conv_dc.cu: direct 3x3 stride-1 convolution (one staged input tile, nine shifted tap descriptors)
+bool conv_dc_eligible(const ConvLayer& L, int D, int H, int W);
+int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int H, int W, const ActRef& out,
                    const float* d_residual, int relu, cudaStream_t st);
 void conv_out_dims(const ConvLayer& L, int D, int H, int W, int* Do, int* Ho, int* Wo);
 int maxpool_launch(ss2_ctx* ctx, const float* d_in, int B, int H, int W, int C, int k, int s, int p,

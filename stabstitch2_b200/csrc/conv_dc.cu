@@ -1,0 +1,270 @@
+// tcgen05 DIRECT convolution for the stride-1 3x3 layers (sm_100a): the nine filter taps read ONE
+// staged input tile at nine row offsets instead of nine im2col copies.
+//
+// conv_tc.cu's implicit GEMM moves, per 128-row output tile, one TMA box per (tap, 32-channel chunk): the same
+// input pixels cross L2 -> shared memory nine times, and on B200 the ResNet layers ran exactly at the L2 -> SM
+// bandwidth (layer1: 2.5 GB per launch at ~8 TB/s = the measured 315 us).  Here:
+//   * the output tile is TH full image rows and the GEMM row index is m = h * P + w', P = W + 2, i.e. the two
+//     halo columns are carried as junk rows (never stored).  The staged input tile is the (TH + 2) x P pixels
+//     (h0 - 1 .., -1 ..) of one 32-channel chunk, ONE TMA box with zero fill = the padding, landing as P * (TH + 2)
+//     K-major 128-byte rows (SWIZZLE_128B).  For tap (kh, kw) the A operand of output row m is staged row
+//     m + kh * P + kw: a constant offset, so the tap's UMMA descriptor is the tile's descriptor advanced by
+//     (kh * P + kw) * 128 bytes (the swizzle is a function of the absolute shared-memory address for both the
+//     TMA write and the MMA read, so any 128-byte row is a valid start).  A bytes per tile drop 9x (per chunk: one
+//     box instead of nine).
+//   * weights stream through their own ring (one [64 cout][32 k] hi/lo stage per (chunk, tap)).
+//   * persistent CTAs (one per SM) with two TMEM accumulators: the epilogue of tile i overlaps the MMAs of
+//     tile i + 1.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue.
+// Numerics are those of conv_tc.cu (split TF32, fp32 accumulation in TMEM).
+#include "tc_common.cuh"
+
+#define DC_THREADS 192
+#define DC_BN 64
+#define DC_BK 32
+#define DC_B_BYTES (DC_BN * DC_BK * 4)  // 8 KB per plane
+
+struct DcParams {
+  const float* bias;
+  const float* residual;
+  float* out_v;
+  float* out_hi;
+  float* out_lo;
+  int B, H, W, Cout;
+  int P, TH;           // padded pitch W + 2, output rows per tile
+  int tiles_h;         // ceil(H / TH)
+  int n_mtiles, n_ntiles;
+  int nchunk, CinP;
+  int a_rows;          // staged rows per plane (allocation; >= 128 + 2 P + 2, multiple of 8)
+  int NA, NB;          // ring depths
+  int relu;
+  int npass;           // 3 = split TF32, 1 = plain TF32
+};
+
+// K-major SWIZZLE_128B descriptor whose start sits on ANY 128-byte row of the 1024-byte swizzle atom.  Measured on
+// B200 (tests/probe_dc.py): the tensor core applies the 128B swizzle to the absolute shared-memory address, exactly
+// like the TMA unit that wrote the tile, so the descriptor's base-offset field stays 0 (filling it with the row
+// phase of the start address gives wrong results for every tap whose offset is not a multiple of 8 rows).
+__device__ __forceinline__ uint64_t dc_desc_sw128(uint32_t smem_addr) { return umma_desc_sw128(smem_addr); }
+
+__global__ void __launch_bounds__(DC_THREADS, 1)
+conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DcParams P) {
+  extern __shared__ __align__(1024) uint8_t dc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dc_smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t a_full[4], a_empty[4], b_full[8], b_empty[8], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nplanes = P.npass == 3 ? 2 : 1;
+  const uint32_t a_plane = (uint32_t)P.a_rows * 128u;
+  const uint32_t a_stage = a_plane * nplanes;
+  const uint32_t b_stage = (uint32_t)DC_B_BYTES * nplanes;
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + (size_t)P.NA * a_stage;
+  const int total = P.n_mtiles * P.n_ntiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < P.NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(2 * DC_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint32_t a_bytes = (uint32_t)nplanes * (uint32_t)(P.P * (P.TH + 2)) * 128u;
+      int ia = 0, ib = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int mt = t / P.n_ntiles, nt = t - mt * P.n_ntiles;
+        const int n = mt / P.tiles_h, h0 = (mt - n * P.tiles_h) * P.TH;
+        for (int ck = 0; ck < P.nchunk; ++ck) {
+          const int sa = ia % P.NA;
+          if (ia >= P.NA) mbar_wait(&a_empty[sa], ((ia / P.NA) - 1) & 1);
+          uint8_t* ad = a_ring + (size_t)sa * a_stage;
+          mbar_expect_tx(&a_full[sa], a_bytes);
+          tma_load_5d(ad, &tmA_hi, &a_full[sa], ck * DC_BK, -1, h0 - 1, 0, n);
+          if (nplanes == 2) tma_load_5d(ad + a_plane, &tmA_lo, &a_full[sa], ck * DC_BK, -1, h0 - 1, 0, n);
+          ++ia;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int sb = ib % P.NB;
+            if (ib >= P.NB) mbar_wait(&b_empty[sb], ((ib / P.NB) - 1) & 1);
+            uint8_t* bd = b_ring + (size_t)sb * b_stage;
+            mbar_expect_tx(&b_full[sb], b_stage);
+            tma_load_2d(bd, &tmB_hi, &b_full[sb], tap * P.CinP + ck * DC_BK, nt * DC_BN);
+            if (nplanes == 2) tma_load_2d(bd + DC_B_BYTES, &tmB_lo, &b_full[sb], tap * P.CinP + ck * DC_BK, nt * DC_BN);
+            ++ib;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B tf32, both K-major, N = 64, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int ia = 0, ib = 0, it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        if (it >= 2) mbar_wait(&acc_empty[as], ((it >> 1) - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * DC_BN);
+        for (int ck = 0; ck < P.nchunk; ++ck) {
+          const int sa = ia % P.NA;
+          mbar_wait(&a_full[sa], (ia / P.NA) & 1);
+          const uint32_t a_base = smem_u32(a_ring + (size_t)sa * a_stage);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int sb = ib % P.NB;
+            mbar_wait(&b_full[sb], (ib / P.NB) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int kh = tap / 3, kw = tap - kh * 3;
+            const uint32_t a_tap = a_base + (uint32_t)(kh * P.P + kw) * 128u;
+            const uint32_t b_hi = smem_u32(b_ring + (size_t)sb * b_stage);
+#pragma unroll
+            for (int k = 0; k < DC_BK / 8; ++k) {
+              const uint64_t da = dc_desc_sw128(a_tap + k * 32), db = umma_desc_sw128(b_hi + k * 32);
+              umma_tf32(d_tmem, da, db, idesc, (ck > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              if (nplanes == 2) {
+                const uint64_t dal = dc_desc_sw128(a_tap + a_plane + k * 32), dbl = umma_desc_sw128(b_hi + DC_B_BYTES + k * 32);
+                umma_tf32(d_tmem, dal, db, idesc, 1u);
+                umma_tf32(d_tmem, da, dbl, idesc, 1u);
+              }
+            }
+            umma_commit(&b_empty[sb]);
+            ++ib;
+          }
+          umma_commit(&a_empty[sa]);
+          ++ia;
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quarter q = warp % 4 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int hl = r / P.P, wl = r - hl * P.P;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const int mt = t / P.n_ntiles, nt = t - mt * P.n_ntiles;
+      const int n = mt / P.tiles_h, h0 = (mt - n * P.tiles_h) * P.TH;
+      mbar_wait(&acc_full[as], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int oh = h0 + hl;
+      const bool valid = hl < P.TH && wl < P.W && oh < P.H;
+      const size_t m = ((size_t)n * P.H + oh) * P.W + wl;
+      const int cout0 = nt * DC_BN;
+#pragma unroll
+      for (int half = 0; half < DC_BN / 32; ++half) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * DC_BN + half * 32), acc);  // warp-collective
+        if (half == DC_BN / 32 - 1) {
+          // this warp's accumulator quarter is in registers: hand the TMEM stage back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+        }
+        if (valid) {
+          const int c0 = cout0 + half * 32;
+          const size_t o = m * P.Cout + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c0 + j < P.Cout) {
+              float v[4] = {__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3])};
+              if (P.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + j));
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+              }
+              if (P.residual) {
+                const float4 rs = __ldg(reinterpret_cast<const float4*>(P.residual + o + j));
+                v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
+              }
+              if (P.relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+              }
+              *reinterpret_cast<float4*>(P.out_v + o + j) = make_float4(v[0], v[1], v[2], v[3]);
+              if (P.out_hi) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { hi[e] = rna_tf32(v[e]); lo[e] = v[e] - hi[e]; }
+                *reinterpret_cast<float4*>(P.out_hi + o + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * DC_BN));
+  }
+}
+
+// stride-1 3x3 2-D layers with 32-channel chunks, Cout a multiple of 64 and a row that fits one tile
+bool conv_dc_eligible(const ConvLayer& L, int D, int H, int W) {
+  return L.wk_hi != nullptr && L.KD == 1 && L.KH == 3 && L.KW == 3 && L.sh == 1 && L.sw == 1 && L.ph == 1 && L.pw == 1 &&
+         L.pd == 0 && D == 1 && (L.CinP % DC_BK) == 0 && (L.CoutP % DC_BN) == 0 && (L.Cout % DC_BN) == 0 && W + 2 <= 128 &&
+         W >= 4 && H >= 1;
+}
+
+int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int H, int W, const ActRef& out,
+                   const float* d_residual, int relu, cudaStream_t st) {
+  DcParams P;
+  P.bias = L.bias; P.residual = d_residual;
+  P.out_v = out.v; P.out_hi = out.hi; P.out_lo = out.lo;
+  P.B = B; P.H = H; P.W = W; P.Cout = L.Cout;
+  P.P = W + 2;
+  P.TH = 128 / P.P; if (P.TH > H) P.TH = H;
+  P.tiles_h = cdiv(H, P.TH);
+  P.n_mtiles = B * P.tiles_h;
+  P.n_ntiles = L.CoutP / DC_BN;
+  P.nchunk = L.CinP / DC_BK; P.CinP = L.CinP;
+  P.a_rows = (128 + 2 * P.P + 2 + 7) / 8 * 8;
+  P.relu = relu;
+  P.npass = (ctx->tc_passes == 1 || !in.lo || !L.wk_lo) ? 1 : 3;
+  const int nplanes = P.npass == 3 ? 2 : 1;
+  const size_t a_stage = (size_t)P.a_rows * 128 * nplanes, b_stage = (size_t)DC_B_BYTES * nplanes;
+  const size_t budget = 227 * 1024 - 2048;
+  P.NA = P.nchunk >= 2 ? 2 : 1;
+  if ((size_t)P.NA * a_stage + 2 * b_stage + 1024 > budget) P.NA = 1;
+  if ((size_t)P.NA * a_stage + 2 * b_stage + 1024 > budget) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_dc: tile does not fit shared memory");
+  P.NB = (int)((budget - 1024 - (size_t)P.NA * a_stage) / b_stage);
+  if (P.NB > 8) P.NB = 8;
+  const size_t smem = (size_t)P.NA * a_stage + (size_t)P.NB * b_stage + 1024;
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  SS2_TRY(make_act_map(ctx, &mA_hi, in.hi, L.CinP, W, H, 1, B, P.P, P.TH + 2, 1, 1, 1, 1, 1));
+  SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_hi, 9 * L.CinP, L.CoutP));
+  if (P.npass == 3) {
+    SS2_TRY(make_act_map(ctx, &mA_lo, in.lo, L.CinP, W, H, 1, B, P.P, P.TH + 2, 1, 1, 1, 1, 1));
+    SS2_TRY(make_weight_map(ctx, &mB_lo, L.wk_lo, 9 * L.CinP, L.CoutP));
+  } else {
+    mA_lo = mA_hi; mB_lo = mB_hi;
+  }
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    SS2_CUDA(ctx, cudaFuncSetAttribute(conv_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int total = P.n_mtiles * P.n_ntiles;
+  const int grid = total < nsm ? total : nsm;
+  const double flops = 2.0 * B * H * W * (double)L.Cout * 9 * L.Cin;
+  ss2_prof_begin(ctx, SS2_PROF_CONV, st);
+  conv_dc_kernel<<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  ss2_prof_end(ctx, SS2_PROF_CONV, st, flops);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}

@@ -410,6 +410,8 @@ def test_fullsize_properties():
 CONV_CASES = [
     # B, D, H, W, Cin, Cout, k, stride, pad, kd, pad_d
     (2, 1, 45, 60, 128, 128, 3, 1, 1, 1, 0),    # ResNet layer2 body
+    (2, 1, 90, 120, 64, 64, 3, 1, 1, 1, 0),     # ResNet layer1 body (one image row per direct-conv tile)
+    (3, 1, 11, 15, 128, 128, 3, 1, 1, 1, 0),    # regressor stage: ragged last tile (11 rows, 7 per tile)
     (3, 1, 90, 120, 64, 128, 3, 2, 1, 1, 0),    # layer2 entry, stride 2
     (3, 1, 90, 120, 64, 128, 1, 2, 0, 1, 0),    # 1x1 stride-2 shortcut
     (2, 1, 23, 30, 256, 256, 3, 1, 1, 1, 0),    # layer3 body
