@@ -19,9 +19,8 @@
 #include "tc_common.cuh"
 
 #define DC_THREADS 192
-#define DC_BN 64
 #define DC_BK 32
-#define DC_B_BYTES (DC_BN * DC_BK * 4)  // 8 KB per plane
+#define DC_BOX_N 64                      // rows of one weight TMA box
 
 struct DcParams {
   const float* bias;
@@ -46,9 +45,45 @@ struct DcParams {
 // phase of the start address gives wrong results for every tap whose offset is not a multiple of 8 rows).
 __device__ __forceinline__ uint64_t dc_desc_sw128(uint32_t smem_addr) { return umma_desc_sw128(smem_addr); }
 
+// one lane of a fully active warp (ptxas then knows the region has a single active thread and emits the UTCHMMA /
+// UTMALDG instructions without a per-lane waterfall loop)
+__device__ __forceinline__ bool dc_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// tcgen05.mma with descriptors given as their low words (start address field | LBO) plus the constant high word:
+// the issuing thread advances a descriptor with ONE 32-bit add
+__device__ __forceinline__ void dc_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t dc_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+// high word of the K-major SWIZZLE_128B descriptor: SBO = 1024 B, version 1, swizzle mode 2 (see umma_desc_sw128)
+#define DC_DESC_HI ((uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29))
+
+template <int BN>
 __global__ void __launch_bounds__(DC_THREADS, 1)
 conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DcParams P) {
+  constexpr int DC_BN = BN;
+  constexpr int DC_B_BYTES = BN * DC_BK * 4;  // per plane
   extern __shared__ __align__(1024) uint8_t dc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dc_smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t a_full[4], a_empty[4], b_full[8], b_empty[8], acc_full[2], acc_empty[2];
@@ -69,7 +104,7 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(2 * DC_BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(2 * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -79,7 +114,7 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (dc_elect_one()) {
       const uint32_t a_bytes = (uint32_t)nplanes * (uint32_t)(P.P * (P.TH + 2)) * 128u;
       int ia = 0, ib = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -98,8 +133,13 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (ib >= P.NB) mbar_wait(&b_empty[sb], ((ib / P.NB) - 1) & 1);
             uint8_t* bd = b_ring + (size_t)sb * b_stage;
             mbar_expect_tx(&b_full[sb], b_stage);
-            tma_load_2d(bd, &tmB_hi, &b_full[sb], tap * P.CinP + ck * DC_BK, nt * DC_BN);
-            if (nplanes == 2) tma_load_2d(bd + DC_B_BYTES, &tmB_lo, &b_full[sb], tap * P.CinP + ck * DC_BK, nt * DC_BN);
+#pragma unroll
+            for (int j = 0; j < BN / DC_BOX_N; ++j) {
+              tma_load_2d(bd + j * (DC_BOX_N * DC_BK * 4), &tmB_hi, &b_full[sb], tap * P.CinP + ck * DC_BK, nt * DC_BN + j * DC_BOX_N);
+              if (nplanes == 2)
+                tma_load_2d(bd + DC_B_BYTES + j * (DC_BOX_N * DC_BK * 4), &tmB_lo, &b_full[sb], tap * P.CinP + ck * DC_BK,
+                            nt * DC_BN + j * DC_BOX_N);
+            }
             ++ib;
           }
         }
@@ -107,9 +147,10 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A/B tf32, both K-major, N = 64, M = 128
+    if (dc_elect_one()) {
+      // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t a_plane16 = a_plane >> 4;
       int ia = 0, ib = 0, it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int as = it & 1;
@@ -119,26 +160,33 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int ck = 0; ck < P.nchunk; ++ck) {
           const int sa = ia % P.NA;
           mbar_wait(&a_full[sa], (ia / P.NA) & 1);
-          const uint32_t a_base = smem_u32(a_ring + (size_t)sa * a_stage);
+          const uint32_t a_lo0 = dc_desc_lo(smem_u32(a_ring + (size_t)sa * a_stage));
+          uint32_t tap_off = 0;  // (kh * P + kw) * 128 / 16
           for (int tap = 0; tap < 9; ++tap) {
             const int sb = ib % P.NB;
             mbar_wait(&b_full[sb], (ib / P.NB) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int kh = tap / 3, kw = tap - kh * 3;
-            const uint32_t a_tap = a_base + (uint32_t)(kh * P.P + kw) * 128u;
-            const uint32_t b_hi = smem_u32(b_ring + (size_t)sb * b_stage);
+            const uint32_t da = a_lo0 + tap_off;
+            const uint32_t db = dc_desc_lo(smem_u32(b_ring + (size_t)sb * b_stage));
+            if (nplanes == 2) {
+              const uint32_t dal = da + a_plane16, dbl = db + (DC_B_BYTES >> 4);
+              dc_mma(d_tmem, da, db, DC_DESC_HI, idesc, (ck > 0 || tap > 0) ? 1u : 0u);
+              dc_mma(d_tmem, dal, db, DC_DESC_HI, idesc, 1u);
+              dc_mma(d_tmem, da, dbl, DC_DESC_HI, idesc, 1u);
 #pragma unroll
-            for (int k = 0; k < DC_BK / 8; ++k) {
-              const uint64_t da = dc_desc_sw128(a_tap + k * 32), db = umma_desc_sw128(b_hi + k * 32);
-              umma_tf32(d_tmem, da, db, idesc, (ck > 0 || tap > 0 || k > 0) ? 1u : 0u);
-              if (nplanes == 2) {
-                const uint64_t dal = dc_desc_sw128(a_tap + a_plane + k * 32), dbl = umma_desc_sw128(b_hi + DC_B_BYTES + k * 32);
-                umma_tf32(d_tmem, dal, db, idesc, 1u);
-                umma_tf32(d_tmem, da, dbl, idesc, 1u);
+              for (int k = 1; k < DC_BK / 8; ++k) {
+                dc_mma(d_tmem, da + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);
+                dc_mma(d_tmem, dal + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);
+                dc_mma(d_tmem, da + 2 * k, dbl + 2 * k, DC_DESC_HI, idesc, 1u);
               }
+            } else {
+              dc_mma(d_tmem, da, db, DC_DESC_HI, idesc, (ck > 0 || tap > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k = 1; k < DC_BK / 8; ++k) dc_mma(d_tmem, da + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);
             }
             umma_commit(&b_empty[sb]);
             ++ib;
+            tap_off += (tap % 3 == 2) ? (uint32_t)(P.P - 2) * 8u : 8u;
           }
           umma_commit(&a_empty[sa]);
           ++ia;
@@ -208,14 +256,14 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * DC_BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
   }
 }
 
 // stride-1 3x3 2-D layers with 32-channel chunks, Cout a multiple of 64 and a row that fits one tile
 bool conv_dc_eligible(const ConvLayer& L, int D, int H, int W) {
   return L.wk_hi != nullptr && L.KD == 1 && L.KH == 3 && L.KW == 3 && L.sh == 1 && L.sw == 1 && L.ph == 1 && L.pw == 1 &&
-         L.pd == 0 && D == 1 && (L.CinP % DC_BK) == 0 && (L.CoutP % DC_BN) == 0 && (L.Cout % DC_BN) == 0 && W + 2 <= 128 &&
+         L.pd == 0 && D == 1 && (L.CinP % DC_BK) == 0 && (L.CoutP % 64) == 0 && (L.Cout % 64) == 0 && W + 2 <= 128 &&
          W >= 4 && H >= 1;
 }
 
@@ -229,13 +277,16 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   P.TH = 128 / P.P; if (P.TH > H) P.TH = H;
   P.tiles_h = cdiv(H, P.TH);
   P.n_mtiles = B * P.tiles_h;
-  P.n_ntiles = L.CoutP / DC_BN;
+  // N tile: 128 output channels per MMA where the layer has them (half the tcgen05.mma instructions per FLOP and the
+  // staged input tile is read once for 128 channels), else 64
+  const int BN = (L.CoutP % 128) == 0 ? 128 : 64;
+  P.n_ntiles = L.CoutP / BN;
   P.nchunk = L.CinP / DC_BK; P.CinP = L.CinP;
   P.a_rows = (128 + 2 * P.P + 2 + 7) / 8 * 8;
   P.relu = relu;
   P.npass = (ctx->tc_passes == 1 || !in.lo || !L.wk_lo) ? 1 : 3;
   const int nplanes = P.npass == 3 ? 2 : 1;
-  const size_t a_stage = (size_t)P.a_rows * 128 * nplanes, b_stage = (size_t)DC_B_BYTES * nplanes;
+  const size_t a_stage = (size_t)P.a_rows * 128 * nplanes, b_stage = (size_t)BN * DC_BK * 4 * nplanes;
   const size_t budget = 227 * 1024 - 2048;
   P.NA = P.nchunk >= 2 ? 2 : 1;
   if ((size_t)P.NA * a_stage + 2 * b_stage + 1024 > budget) P.NA = 1;
@@ -252,10 +303,11 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   } else {
     mA_lo = mA_hi; mB_lo = mB_hi;
   }
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    SS2_CUDA(ctx, cudaFuncSetAttribute(conv_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  static size_t attr_smem[2] = {0, 0};
+  if (smem > attr_smem[BN == 128]) {
+    if (BN == 128) SS2_CUDA(ctx, cudaFuncSetAttribute(conv_dc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else SS2_CUDA(ctx, cudaFuncSetAttribute(conv_dc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[BN == 128] = smem;
   }
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -263,7 +315,8 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   const int grid = total < nsm ? total : nsm;
   const double flops = 2.0 * B * H * W * (double)L.Cout * 9 * L.Cin;
   ss2_prof_begin(ctx, SS2_PROF_CONV, st);
-  conv_dc_kernel<<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  if (BN == 128) conv_dc_kernel<128><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  else conv_dc_kernel<64><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
   ss2_prof_end(ctx, SS2_PROF_CONV, st, flops);
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
