@@ -37,6 +37,7 @@ struct DcParams {
   int NA, NB;          // ring depths
   int relu;
   int npass;           // 3 = split TF32, 1 = plain TF32
+  int dbg;             // timing experiments (SS2_DC_DBG): 1 = no TMA traffic (MMAs on stale smem), 2 = no MMAs
 };
 
 // K-major SWIZZLE_128B descriptor whose start sits on ANY 128-byte row of the 1024-byte swizzle atom.  Measured on
@@ -78,7 +79,11 @@ __device__ __forceinline__ uint32_t dc_desc_lo(uint32_t smem_addr) { return ((sm
 // high word of the K-major SWIZZLE_128B descriptor: SBO = 1024 B, version 1, swizzle mode 2 (see umma_desc_sw128)
 #define DC_DESC_HI ((uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29))
 
-template <int BN>
+// MT = 128-row GEMM blocks per tile (1 or 2).  Measured on B200 the kernel is bound by the bytes the TMA unit can
+// deliver into one SM (~22 B/clk: 110-130 cycles per MMA for N = 64 and N = 128 alike, tensor pipe ~30% active), not
+// by MMA issue or accumulator dependencies, so a tile of two blocks (2 TH image rows) shares every weight stage between
+// two MMAs and its TH + 2 input rows between 2 TH output rows: ~45% fewer staged bytes per output row.
+template <int BN, int MT>
 __global__ void __launch_bounds__(DC_THREADS, 1)
 conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DcParams P) {
@@ -104,7 +109,7 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(2 * BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(2 * MT * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -114,7 +119,7 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (dc_elect_one()) {
+    if (dc_elect_one() && !(P.dbg & 1)) {
       const uint32_t a_bytes = (uint32_t)nplanes * (uint32_t)(P.P * (P.TH + 2)) * 128u;
       int ia = 0, ib = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -156,33 +161,37 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int as = it & 1;
         if (it >= 2) mbar_wait(&acc_empty[as], ((it >> 1) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * DC_BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * DC_BN);
         for (int ck = 0; ck < P.nchunk; ++ck) {
           const int sa = ia % P.NA;
-          mbar_wait(&a_full[sa], (ia / P.NA) & 1);
+          if (!(P.dbg & 1)) mbar_wait(&a_full[sa], (ia / P.NA) & 1);
           const uint32_t a_lo0 = dc_desc_lo(smem_u32(a_ring + (size_t)sa * a_stage));
           uint32_t tap_off = 0;  // (kh * P + kw) * 128 / 16
           for (int tap = 0; tap < 9; ++tap) {
             const int sb = ib % P.NB;
-            mbar_wait(&b_full[sb], (ib / P.NB) & 1);
+            if (!(P.dbg & 1)) mbar_wait(&b_full[sb], (ib / P.NB) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t da = a_lo0 + tap_off;
             const uint32_t db = dc_desc_lo(smem_u32(b_ring + (size_t)sb * b_stage));
-            if (nplanes == 2) {
+            const uint32_t first = (ck > 0 || tap > 0) ? 1u : 0u;  // accumulate flag of the first MMA into each accumulator
+            constexpr uint32_t BLK = 128 * 128 / 16;                   // descriptor units between the tile's row blocks
+            if (P.dbg & 2) {
+            } else if (nplanes == 2) {
               const uint32_t dal = da + a_plane16, dbl = db + (DC_B_BYTES >> 4);
-              dc_mma(d_tmem, da, db, DC_DESC_HI, idesc, (ck > 0 || tap > 0) ? 1u : 0u);
-              dc_mma(d_tmem, dal, db, DC_DESC_HI, idesc, 1u);
-              dc_mma(d_tmem, da, dbl, DC_DESC_HI, idesc, 1u);
 #pragma unroll
-              for (int k = 1; k < DC_BK / 8; ++k) {
-                dc_mma(d_tmem, da + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);
-                dc_mma(d_tmem, dal + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);
-                dc_mma(d_tmem, da + 2 * k, dbl + 2 * k, DC_DESC_HI, idesc, 1u);
+              for (int k = 0; k < DC_BK / 8; ++k) {
+#pragma unroll
+                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * DC_BN, da + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc, k == 0 ? first : 1u);
+#pragma unroll
+                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * DC_BN, dal + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);
+#pragma unroll
+                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * DC_BN, da + b * BLK + 2 * k, dbl + 2 * k, DC_DESC_HI, idesc, 1u);
               }
             } else {
-              dc_mma(d_tmem, da, db, DC_DESC_HI, idesc, (ck > 0 || tap > 0) ? 1u : 0u);
 #pragma unroll
-              for (int k = 1; k < DC_BK / 8; ++k) dc_mma(d_tmem, da + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);
+              for (int k = 0; k < DC_BK / 8; ++k)
+#pragma unroll
+                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * DC_BN, da + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc, k == 0 ? first : 1u);
             }
             umma_commit(&b_empty[sb]);
             ++ib;
@@ -197,8 +206,6 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else {
     // ===== epilogue warps: TMEM lane quarter q = warp % 4 =====
     const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int hl = r / P.P, wl = r - hl * P.P;
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int as = it & 1;
@@ -206,46 +213,51 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int n = mt / P.tiles_h, h0 = (mt - n * P.tiles_h) * P.TH;
       mbar_wait(&acc_full[as], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int oh = h0 + hl;
-      const bool valid = hl < P.TH && wl < P.W && oh < P.H;
-      const size_t m = ((size_t)n * P.H + oh) * P.W + wl;
       const int cout0 = nt * DC_BN;
 #pragma unroll
-      for (int half = 0; half < DC_BN / 32; ++half) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * DC_BN + half * 32), acc);  // warp-collective
-        if (half == DC_BN / 32 - 1) {
-          // this warp's accumulator quarter is in registers: hand the TMEM stage back to the MMA warp
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
-        }
-        if (valid) {
-          const int c0 = cout0 + half * 32;
-          const size_t o = m * P.Cout + c0;
+      for (int blk = 0; blk < MT; ++blk) {
+        const int r = blk * 128 + q * 32 + lane;
+        const int hl = r / P.P, wl = r - hl * P.P;
+        const int oh = h0 + hl;
+        const bool valid = hl < P.TH && wl < P.W && oh < P.H;
+        const size_t m = ((size_t)n * P.H + oh) * P.W + wl;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (c0 + j < P.Cout) {
-              float v[4] = {__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3])};
-              if (P.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + j));
-                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-              }
-              if (P.residual) {
-                const float4 rs = __ldg(reinterpret_cast<const float4*>(P.residual + o + j));
-                v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
-              }
-              if (P.relu) {
+        for (int half = 0; half < DC_BN / 32; ++half) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * MT + blk) * DC_BN + half * 32), acc);  // warp-collective
+          if (blk == MT - 1 && half == DC_BN / 32 - 1) {
+            // this warp's accumulator quarter is in registers: hand the TMEM stage back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+          }
+          if (valid) {
+            const int c0 = cout0 + half * 32;
+            const size_t o = m * P.Cout + c0;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-              }
-              *reinterpret_cast<float4*>(P.out_v + o + j) = make_float4(v[0], v[1], v[2], v[3]);
-              if (P.out_hi) {
-                float hi[4], lo[4];
+            for (int j = 0; j < 32; j += 4) {
+              if (c0 + j < P.Cout) {
+                float v[4] = {__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3])};
+                if (P.bias) {
+                  const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + j));
+                  v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+                }
+                if (P.residual) {
+                  const float4 rs = __ldg(reinterpret_cast<const float4*>(P.residual + o + j));
+                  v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
+                }
+                if (P.relu) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { hi[e] = rna_tf32(v[e]); lo[e] = v[e] - hi[e]; }
-                *reinterpret_cast<float4*>(P.out_hi + o + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                  for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+                }
+                *reinterpret_cast<float4*>(P.out_v + o + j) = make_float4(v[0], v[1], v[2], v[3]);
+                if (P.out_hi) {
+                  float hi[4], lo[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) { hi[e] = rna_tf32(v[e]); lo[e] = v[e] - hi[e]; }
+                  *reinterpret_cast<float4*>(P.out_hi + o + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                  if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
               }
             }
           }
@@ -256,7 +268,7 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * MT * BN));
   }
 }
 
@@ -274,7 +286,17 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   P.out_v = out.v; P.out_hi = out.hi; P.out_lo = out.lo;
   P.B = B; P.H = H; P.W = W; P.Cout = L.Cout;
   P.P = W + 2;
-  P.TH = 128 / P.P; if (P.TH > H) P.TH = H;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+  // two 128-row blocks per tile when that still leaves every SM several tiles (measured on B200, 32 images: 64->64 at
+  // 90x120 206 us against 245 us with one block; 256->256 at 23x30 has only 192 two-block tiles and loses to the
+  // wave quantisation, 187 us against 152 us)
+  int MT = 2;
+  P.TH = 256 / P.P; if (P.TH > H) P.TH = H;
+  if (P.TH * P.P <= 128 || (long)B * cdiv(H, P.TH) * (L.CoutP / ((L.CoutP % 128) == 0 ? 128 : 64)) < 3L * nsm) {
+    MT = 1;
+    P.TH = 128 / P.P; if (P.TH > H) P.TH = H;
+  }
   P.tiles_h = cdiv(H, P.TH);
   P.n_mtiles = B * P.tiles_h;
   // N tile: 128 output channels per MMA where the layer has them (half the tcgen05.mma instructions per FLOP and the
@@ -282,8 +304,9 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   const int BN = (L.CoutP % 128) == 0 ? 128 : 64;
   P.n_ntiles = L.CoutP / BN;
   P.nchunk = L.CinP / DC_BK; P.CinP = L.CinP;
-  P.a_rows = (128 + 2 * P.P + 2 + 7) / 8 * 8;
+  P.a_rows = (128 * MT + 2 * P.P + 2 + 7) / 8 * 8;
   P.relu = relu;
+  { const char* e = getenv("SS2_DC_DBG"); P.dbg = e ? atoi(e) : 0; }
   P.npass = (ctx->tc_passes == 1 || !in.lo || !L.wk_lo) ? 1 : 3;
   const int nplanes = P.npass == 3 ? 2 : 1;
   const size_t a_stage = (size_t)P.a_rows * 128 * nplanes, b_stage = (size_t)BN * DC_BK * 4 * nplanes;
@@ -303,20 +326,22 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   } else {
     mA_lo = mA_hi; mB_lo = mB_hi;
   }
-  static size_t attr_smem[2] = {0, 0};
-  if (smem > attr_smem[BN == 128]) {
-    if (BN == 128) SS2_CUDA(ctx, cudaFuncSetAttribute(conv_dc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else SS2_CUDA(ctx, cudaFuncSetAttribute(conv_dc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem[BN == 128] = smem;
+  static size_t attr_smem[4] = {0, 0, 0, 0};
+  const int variant = (BN == 128 ? 2 : 0) + (MT == 2 ? 1 : 0);
+  if (smem > attr_smem[variant]) {
+    const void* fn = variant == 0 ? (const void*)conv_dc_kernel<64, 1> : variant == 1 ? (const void*)conv_dc_kernel<64, 2>
+                   : variant == 2 ? (const void*)conv_dc_kernel<128, 1> : (const void*)conv_dc_kernel<128, 2>;
+    SS2_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[variant] = smem;
   }
-  int nsm = 148;
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
   const int total = P.n_mtiles * P.n_ntiles;
   const int grid = total < nsm ? total : nsm;
   const double flops = 2.0 * B * H * W * (double)L.Cout * 9 * L.Cin;
   ss2_prof_begin(ctx, SS2_PROF_CONV, st);
-  if (BN == 128) conv_dc_kernel<128><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
-  else conv_dc_kernel<64><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  if (variant == 0) conv_dc_kernel<64, 1><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  else if (variant == 1) conv_dc_kernel<64, 2><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  else if (variant == 2) conv_dc_kernel<128, 1><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  else conv_dc_kernel<128, 2><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
   ss2_prof_end(ctx, SS2_PROF_CONV, st, flops);
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
