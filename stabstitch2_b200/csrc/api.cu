@@ -117,6 +117,8 @@ int ss2_create(int device, ss2_ctx** out) {
   if (env) c->use_tc = atoi(env);
   env = getenv("SS2_TC_PASSES");
   if (env) c->tc_passes = atoi(env) == 1 ? 1 : 3;
+  env = getenv("SS2_TC_STEM");
+  if (env) c->use_tc_stem = atoi(env);
   env = getenv("SS2_CONV_DC");
   if (env) c->use_dc = atoi(env);
   *out = c;

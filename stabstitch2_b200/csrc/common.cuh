@@ -34,6 +34,9 @@ struct ConvLayer {
   // tcgen05 path: K-major filter matrices [CoutP][KD*KH*KW*CinP], hi = rna_tf32(w), lo = w - hi
   float* wk_hi = nullptr;
   float* wk_lo = nullptr;
+  // 7x7 stride-2 stem with 3 input channels: wk_hi/lo are [CoutP][7 * 32], k = kh * 32 + kw * 4 + c (one filter row =
+  // 8 NHWC4 pixels, the eighth and the fourth channel are zero); consumed by conv_tc_stem_launch
+  bool stem_k32 = false;
 };
 
 // An activation tensor: plain fp32 values and (for the tensor-core layers that consume it) the
@@ -118,6 +121,7 @@ struct ss2_ctx {
   int use_tc = 1;  // tcgen05 implicit-GEMM path for eligible layers
   bool lag_tables_ready = false;
   int tc_passes = 3;  // 3 = split-TF32 (fp32-grade), 1 = plain TF32
+  int use_tc_stem = 1;  // tensor-core 7x7 stem (SS2_TC_STEM=0: exact-fp32 SIMT stem)
   int use_dc = 1;     // direct 3x3 kernel (conv_dc.cu) for eligible layers; SS2_CONV_DC=0 disables
 };
 
@@ -248,6 +252,11 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
 void conv_out_dims(const ConvLayer& L, int D, int H, int W, int* Do, int* Ho, int* Wo);
 int maxpool_launch(ss2_ctx* ctx, const float* d_in, int B, int H, int W, int C, int k, int s, int p,
                    const ActRef& out, cudaStream_t st);
+int nchw_to_nhwc4_pad_split_launch(ss2_ctx* ctx, const float* d_in, int B, int H, int W, int pad, int Hp, int Wp,
+                                   float* d_hi, float* d_lo, cudaStream_t st);
+// conv_tc.cu: 7x7 stride-2 stem on the tensor cores from the padded split planes above; out [B, Ho, Wo, 64] (ReLU)
+int conv_tc_stem_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_hi, const float* d_lo, int B, int H, int W,
+                        int Hp, int Wp, const ActRef& out, int relu, cudaStream_t st);
 int nchw_to_nhwc4_launch(ss2_ctx* ctx, const float* d_in, int B, int C, int H, int W, float* d_out,
                          cudaStream_t st);
 // corr.cu

@@ -365,6 +365,39 @@ __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ in, int B, int C,
   }
 }
 
+// NCHW [B,3,H,W] -> zero-padded NHWC4 split planes [B][H + 2*pad][Wp][4] (hi = rna_tf32(v), lo = v - hi): the A
+// operand of the tensor-core stem (conv_tc_stem_launch): the 7x7 stride-2 padding is materialised so that one output
+// pixel's filter row is 32 contiguous floats
+__global__ void nchw_to_nhwc4_pad_split_kernel(const float* __restrict__ in, int B, int H, int W, int pad, int Hp, int Wp,
+                                               float4* __restrict__ hi, float4* __restrict__ lo) {
+  const size_t total = (size_t)B * Hp * Wp, HW = (size_t)H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xp = (int)(i % Wp), yp = (int)((i / Wp) % Hp);
+    const size_t b = i / ((size_t)Wp * Hp);
+    const int x = xp - pad, y = yp - pad;
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
+    if (x >= 0 && x < W && y >= 0 && y < H) {
+      const float* src = in + b * 3 * HW + (size_t)y * W + x;
+      tf32_split(__ldg(src), &h.x, &l.x);
+      tf32_split(__ldg(src + HW), &h.y, &l.y);
+      tf32_split(__ldg(src + 2 * HW), &h.z, &l.z);
+    }
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+int nchw_to_nhwc4_pad_split_launch(ss2_ctx* ctx, const float* d_in, int B, int H, int W, int pad, int Hp, int Wp,
+                                   float* d_hi, float* d_lo, cudaStream_t st) {
+  const size_t total = (size_t)B * Hp * Wp;
+  if (total == 0) return SS2_OK;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  nchw_to_nhwc4_pad_split_kernel<<<blocks, 256, 0, st>>>(d_in, B, H, W, pad, Hp, Wp, reinterpret_cast<float4*>(d_hi),
+                                                         reinterpret_cast<float4*>(d_lo));
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+
 int nchw_to_nhwc4_launch(ss2_ctx* ctx, const float* d_in, int B, int C, int H, int W, float* d_out,
                          cudaStream_t st) {
   const size_t total = (size_t)B * H * W;

@@ -326,6 +326,61 @@ int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
 }
 
 // ------------------------------------------------------------------------------------------
+// 7x7 stride-2 stem (3 input channels) as an implicit GEMM with K = 7 filter rows x 32: the A row of output pixel
+// (ho, wo) for filter row kh is the 32 contiguous floats of the padded NHWC4 input starting at pixel (2 ho + kh, 2 wo)
+// (7 taps x 4 channels + one pixel that meets zero weights).  The tensor map describes exactly that overlapping view:
+// {32 floats, Wo pixels 32 B apart, Hp rows, 1, B}; the row stride 2 is the box's traversal stride.
+// ------------------------------------------------------------------------------------------
+int conv_tc_stem_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_hi, const float* d_lo, int B, int H, int W,
+                        int Hp, int Wp, const ActRef& out, int relu, cudaStream_t st) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+  TcParams P;
+  conv_out_dims(L, 1, H, W, &P.Do, &P.Ho, &P.Wo);
+  P.B = B; P.Cout = L.Cout; P.CinP = 32;
+  P.KD = 1; P.KH = 7; P.KW = 1; P.nchunk = 1;
+  P.sd = 1; P.sh = 2; P.sw = 1; P.pd = 0; P.ph = 0; P.pw = 0;  // padding and the column stride live in the tensor map
+  P.relu = relu; P.bias = L.bias; P.residual = nullptr;
+  P.b_act = 0; P.bTH = P.bTW = 0; P.ldo = L.Cout; P.ncol = TC_BN;
+  P.out_v = out.v; P.out_hi = out.hi; P.out_lo = out.lo;
+  tile_shape(B, 1, P.Ho, P.Wo, &P.TN, &P.TT, &P.TH, &P.TW);
+  P.nW = cdiv(P.Wo, P.TW); P.nH = cdiv(P.Ho, P.TH); P.nT = 1; P.nN = cdiv(B, P.TN);
+  const int npass = (ctx->tc_passes == 1 || !d_lo || !L.wk_lo) ? 1 : 3;
+  const int bh = (P.TH - 1) * 2 + 1;
+  if (bh > 256 || P.TW > 256) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_tc_stem: TMA box too large");
+  CUtensorMap mA[2], mB[2];
+  for (int pl = 0; pl < (npass == 3 ? 2 : 1); ++pl) {
+    cuuint64_t dims[5] = {32, (cuuint64_t)P.Wo, (cuuint64_t)Hp, 1, (cuuint64_t)B};
+    cuuint64_t strides[4] = {32, (cuuint64_t)Wp * 16, (cuuint64_t)Hp * Wp * 16, (cuuint64_t)Hp * Wp * 16};
+    cuuint32_t box[5] = {32, (cuuint32_t)P.TW, (cuuint32_t)bh, 1, (cuuint32_t)P.TN};
+    cuuint32_t est[5] = {1, 1, 2, 1, 1};
+    CUresult r = fn(&mA[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(pl == 0 ? d_hi : d_lo), dims, strides, box,
+                    est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ss2_fail(ctx, SS2_ERR_CUDA, "cuTensorMapEncodeTiled(stem input) = %d", (int)r);
+    SS2_TRY(make_weight_map(ctx, &mB[pl], pl == 0 ? L.wk_hi : L.wk_lo, 7 * 32, L.CoutP));
+  }
+  if (npass != 3) { mA[1] = mA[0]; mB[1] = mB[0]; }
+  dim3 grid(P.nW * P.nH * P.nT * P.nN, L.CoutP / TC_BN);
+  const double flops = 2.0 * B * P.Ho * P.Wo * (double)L.Cout * 49 * 3;
+  ss2_prof_begin(ctx, SS2_PROF_CONV, st);
+  if (npass == 3) {
+    constexpr int STAGES = TC_STAGES3;
+    const size_t smem = (size_t)STAGES * 2 * (TC_A_BYTES + TC_B_BYTES) + 1024;
+    SS2_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<3, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<3, STAGES><<<grid, TC_THREADS, smem, st>>>(mA[0], mA[1], mB[0], mB[1], P);
+  } else {
+    constexpr int STAGES = TC_STAGES1;
+    const size_t smem = (size_t)STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024;
+    SS2_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<1, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<1, STAGES><<<grid, TC_THREADS, smem, st>>>(mA[0], mA[1], mB[0], mB[1], P);
+  }
+  ss2_prof_end(ctx, SS2_PROF_CONV, st, flops);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // CCL correlation on the tensor cores: match[b][p][k] = sum_{tap,c} n1pad[b][p+tap][c] * n2pad[b][k+tap][c]
 // (spatial_network.py:369-425).  Both operands are im2col views of activation tensors.
 // match rows have stride ldo >= H*W floats.

@@ -110,6 +110,28 @@ static int pack_conv(ss2_ctx* ctx, int net, const std::string& wkey, const std::
     SS2_TRY(upload(ctx, hi, &L->wk_hi));
     SS2_TRY(upload(ctx, lo, &L->wk_lo));
   }
+  L->stem_k32 = false;
+  if (flatten_hw == 0 && KD == 1 && KH == 7 && KW == 7 && Cin == 3 && stride == 2 && pad == 3 && (Cout % 4) == 0) {
+    const size_t Ktot = 7 * 32;
+    std::vector<float> hi((size_t)L->CoutP * Ktot, 0.f), lo((size_t)L->CoutP * Ktot, 0.f);
+    for (int o = 0; o < Cout; ++o)
+      for (int kh = 0; kh < 7; ++kh)
+        for (int kw = 0; kw < 7; ++kw)
+          for (int c = 0; c < 3; ++c) {
+            const float v = wp[((size_t)(kh * 7 + kw) * L->CinP + c) * L->CoutP + o];
+            uint32_t b;
+            memcpy(&b, &v, 4);
+            b = (b + 0x1000u) & 0xFFFFE000u;
+            float h;
+            memcpy(&h, &b, 4);
+            if (!isfinite(h)) h = v;
+            hi[(size_t)o * Ktot + kh * 32 + kw * 4 + c] = h;
+            lo[(size_t)o * Ktot + kh * 32 + kw * 4 + c] = v - h;
+          }
+    SS2_TRY(upload(ctx, hi, &L->wk_hi));
+    SS2_TRY(upload(ctx, lo, &L->wk_lo));
+    L->stem_k32 = true;
+  }
   L->bias = nullptr;
   if (has_bias) {
     std::vector<float> bp(L->CoutP, 0.f);
@@ -244,14 +266,24 @@ static int run_block(ss2_ctx* ctx, const ResBlock& b, const ActRef& x, int NB, i
 // x: NCHW [NB,3,H,W] -> f64 [NB,H/8,W/8,128] (and f32 [NB,.,.,256] when stage2)
 static int run_backbone(ss2_ctx* ctx, const Backbone& bb, const float* x_nchw, int NB, int H, int W, bool stage2,
                         float** f64, int* h64, int* w64, float** f32, int* h32, int* w32, cudaStream_t st) {
-  ARENA(x, float, (size_t)NB * H * W * 4);
-  SS2_TRY(nchw_to_nhwc4_launch(ctx, x_nchw, NB, 3, H, W, x, st));
   int d, h, w;
   conv_out_dims(bb.stem, 1, H, W, &d, &h, &w);
   ARENA(s, float, (size_t)NB * h * w * 64);
   ActRef xin, sout;
-  xin.v = x; sout.v = s;
-  SS2_TRY(conv_launch(ctx, bb.stem, xin, NB, 1, H, W, sout, nullptr, 1, st));
+  sout.v = s;
+  if (ctx->use_tc && ctx->use_tc_stem && bb.stem.stem_k32) {
+    // tensor-core stem: zero-padded NHWC4 split planes, one filter row (8 pixels x 4 channels) per 32-wide K chunk
+    const int Hp = H + 6, Wp = (2 * (w - 1) + 8 + 3) / 4 * 4;
+    ARENA(xh, float, (size_t)NB * Hp * Wp * 4);
+    ARENA(xl, float, (size_t)NB * Hp * Wp * 4);
+    SS2_TRY(nchw_to_nhwc4_pad_split_launch(ctx, x_nchw, NB, H, W, 3, Hp, Wp, xh, xl, st));
+    SS2_TRY(conv_tc_stem_launch(ctx, bb.stem, xh, xl, NB, H, W, Hp, Wp, sout, 1, st));
+  } else {
+    ARENA(x, float, (size_t)NB * H * W * 4);
+    SS2_TRY(nchw_to_nhwc4_launch(ctx, x_nchw, NB, 3, H, W, x, st));
+    xin.v = x;
+    SS2_TRY(conv_launch(ctx, bb.stem, xin, NB, 1, H, W, sout, nullptr, 1, st));
+  }
   const int hp = (h + 2 - 3) / 2 + 1, wp = (w + 2 - 3) / 2 + 1;
   ARENA_ACT(p, (size_t)NB * hp * wp * 64);
   SS2_TRY(maxpool_launch(ctx, s, NB, h, w, 64, 3, 2, 1, p, st));
