@@ -169,6 +169,22 @@ int ss2_stable_frames(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, cons
 /* canvas size helper (host arithmetic identical to the kernels') */
 int ss2_canvas_size(const float* h_minmax, int* out_h, int* out_w);
 
+/* ---- three views (test_online_tra_threeview.py:345-505, AVERAGE fusion) ------------------- */
+/* Middle-plane alignment of two stitched pairs that share their middle view (:345-455).
+ * d_w12m1, d_w12m2: smooth meshes [n,7,9,2] @480x360 of pair (1,2); d_w23m1, d_w23m2: of pair (2,3);
+ * w12m2 and w23m1 are the two instances of the shared view.  Outputs [n,7,9,2] in provisional-canvas
+ * pixels: d_mesh1 (view 1 moved onto the middle plane), d_middle, d_mesh3; d_canvas[4] (device) =
+ * {width_min, height_min, out_width, out_height} of the NEW canvas over the three output meshes. */
+int ss2_three_view_meshes(ss2_ctx* ctx, const float* d_w12m1, const float* d_w12m2, const float* d_w23m1,
+                          const float* d_w23m2, int n, int img_h, int img_w, float* d_mesh1, float* d_middle,
+                          float* d_mesh3, float* d_canvas, void* stream);
+/* The three-image warp + fusion loop (:461-490) for n frames: images [n,3,H,W] fp32 0..255 per view,
+ * the three meshes of ss2_three_view_meshes, h_canvas[4] on the HOST; out [n,3,Ho,Wo] with
+ * Ho = (int)out_height, Wo = (int)out_width; fuse(1,2) then fuse(12,3) in the reference's operation order. */
+int ss2_three_view_frames(ss2_ctx* ctx, const float* d_img1, const float* d_img2, const float* d_img3,
+                          const float* d_mesh1, const float* d_middle, const float* d_mesh3, int n, int H, int W,
+                          const float* h_canvas, int mode, int tps, float* d_out, void* stream);
+
 /* ---- whole stream, device resident ------------------------------------------------------- */
 /* smooth meshes of a stream from per-window SmoothNet outputs (test_online_tra.py:378-392):
  * d_win_smooth [nwin,7,7,9,2].  with_head != 0: first window contributes its 7 meshes, every

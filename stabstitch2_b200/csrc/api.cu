@@ -223,6 +223,75 @@ int ss2_tps_warp_blend_avg(ss2_ctx* ctx, const float* d_img1, const float* d_img
   return rc;
 }
 
+int ss2_three_view_meshes(ss2_ctx* ctx, const float* d_w12m1, const float* d_w12m2, const float* d_w23m1,
+                          const float* d_w23m2, int n, int img_h, int img_w, float* d_mesh1, float* d_middle,
+                          float* d_mesh3, float* d_canvas, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (n <= 0 || img_h <= 0 || img_w <= 0 || !d_w12m1 || !d_w12m2 || !d_w23m1 || !d_w23m2 || !d_mesh1 || !d_middle ||
+      !d_mesh3 || !d_canvas)
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_three_view_meshes: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t m = (size_t)n * SS2_NPT * 2;
+  float* buf = nullptr;
+  // work (5 m) | pt12 src12 pt23 src23 tgt (5 m) | moved12 moved23 (2 m) | canvas1 (64) | T (2 systems sets)
+  SS2_CUDA(ctx, cudaMallocAsync((void**)&buf, (12 * m + 64 + (size_t)2 * n * 2 * SS2_NSYS) * sizeof(float), st));
+  float *work = buf, *pt12 = buf + 5 * m, *src12 = pt12 + m, *pt23 = src12 + m, *src23 = pt23 + m, *tgt = src23 + m;
+  float *moved12 = tgt + m, *moved23 = moved12 + m, *canvas1 = moved23 + m, *T = canvas1 + 64;
+  int rc = three_view_align_launch(ctx, d_w12m1, d_w12m2, d_w23m1, d_w23m2, n, img_h, img_w, work, pt12, src12, pt23,
+                                   src23, tgt, d_middle, canvas1, st);
+  // view 1 through the TPS (shared view of pair (1,2) -> middle), view 3 through (shared view of pair (2,3) -> middle)
+  if (rc == SS2_OK) rc = tps_solve_launch(ctx, src12, tgt, n, T, st);
+  if (rc == SS2_OK) rc = tps_point_launch(ctx, pt12, src12, T, n, moved12, st);
+  if (rc == SS2_OK) rc = tps_solve_launch(ctx, src23, tgt, n, T + (size_t)n * 2 * SS2_NSYS, st);
+  if (rc == SS2_OK) rc = tps_point_launch(ctx, pt23, src23, T + (size_t)n * 2 * SS2_NSYS, n, moved23, st);
+  if (rc == SS2_OK) rc = three_view_canvas_launch(ctx, moved12, moved23, d_middle, canvas1, n, d_mesh1, d_mesh3, d_canvas, st);
+  cudaFreeAsync(buf, st);
+  return rc;
+}
+
+int ss2_three_view_frames(ss2_ctx* ctx, const float* d_img1, const float* d_img2, const float* d_img3,
+                          const float* d_mesh1, const float* d_middle, const float* d_mesh3, int n, int H, int W,
+                          const float* h_canvas, int mode, int tps, float* d_out, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (n < 0 || H <= 0 || W <= 0 || !h_canvas || (mode != SS2_MODE_NORMAL && mode != SS2_MODE_FAST) ||
+      (n > 0 && (!d_img1 || !d_img2 || !d_img3 || !d_mesh1 || !d_middle || !d_mesh3)))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_three_view_frames: bad arguments");
+  const float out_w = h_canvas[2], out_h = h_canvas[3];
+  const int Ho = (int)out_h, Wo = (int)out_w;
+  if (Ho < 0 || Wo < 0) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_three_view_frames: negative canvas");
+  if (n == 0 || Ho == 0 || Wo == 0) return SS2_OK;
+  if (!d_out) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_three_view_frames: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tps != SS2_TPS_LATTICE || !tps_lattice_supported(Ho, Wo)) tps = SS2_TPS_EXACT;
+  const int chunk = n < 4 ? n : 4;  // frames warped per pass: 3 x chunk temporaries of the canvas size
+  const size_t m = (size_t)n * SS2_NPT * 2, plane3 = (size_t)3 * Ho * Wo;
+  TpsScratch sc;
+  SS2_TRY(tps_scratch_alloc(ctx, chunk, Ho, Wo, tps, 6 * m + 3 * (size_t)chunk * plane3 + 64, &sc, st));
+  float* source = sc.nodes + (tps == SS2_TPS_LATTICE ? (tps_lattice_workspace_floats(chunk, Ho, Wo) + 63) / 64 * 64 : 0);
+  float* target = source + 3 * m;
+  float* tmp = target + 3 * m;
+  tmp += (64 - ((size_t)(tmp - sc.base) & 63)) & 63;  // keep the image temporaries 256-byte aligned
+  int rc = three_view_sources_launch(ctx, d_mesh1, d_middle, d_mesh3, n, H, W, h_canvas[0], h_canvas[1], out_w, out_h,
+                                     source, target, st);
+  const float* imgs[3] = {d_img1, d_img2, d_img3};
+  for (int k0 = 0; k0 < n && rc == SS2_OK; k0 += chunk) {
+    const int nk = n - k0 < chunk ? n - k0 : chunk;
+    for (int v = 0; v < 3 && rc == SS2_OK; ++v) {
+      const float* src = source + ((size_t)v * n + k0) * SS2_NPT * 2;
+      const float* tgt = target + ((size_t)v * n + k0) * SS2_NPT * 2;
+      rc = tps_solve_for_warp(ctx, src, tgt, nk, H, W, Ho, Wo, mode, tps, sc, st);
+      if (rc == SS2_OK)
+        rc = tps_warp_launch(ctx, imgs[v] + (size_t)k0 * 3 * H * W, src, sc.T, nk, 3, H, W, Ho, Wo, mode, tps,
+                             tmp + (size_t)v * chunk * plane3, st, sc.aux, sc.nodes);
+    }
+    if (rc == SS2_OK)
+      rc = blend3_avg_launch(ctx, tmp, tmp + (size_t)chunk * plane3, tmp + 2 * (size_t)chunk * plane3, (size_t)nk * plane3,
+                             d_out + (size_t)k0 * plane3, st);
+  }
+  cudaFreeAsync(sc.base, st);
+  return rc;
+}
+
 int ss2_cost_volume_nhwc(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B, int H, int W, int C, int sr, int CP,
                          float* d_out, void* stream) {
   if (!ctx) return SS2_ERR_INVALID;

@@ -234,6 +234,17 @@ int canvas_minmax_launch(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh
 int stable_meshes_launch(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh2, int n, int img_h,
                          int img_w, float xmin, float ymin, float out_w, float out_h, float* d_source,
                          float* d_target, cudaStream_t st);
+// geom.cu: three-view glue (test_online_tra_threeview.py:345-505)
+int three_view_align_launch(ss2_ctx* ctx, const float* w12m1, const float* w12m2, const float* w23m1, const float* w23m2,
+                            int n, int img_h, int img_w, float* work, float* pt12, float* src12, float* pt23, float* src23,
+                            float* tgt, float* mid_c, float* canvas1, cudaStream_t st);
+int three_view_canvas_launch(ss2_ctx* ctx, const float* moved12, const float* moved23, const float* mid_c,
+                             const float* canvas1, int n, float* m1_c, float* m3_c, float* canvas2, cudaStream_t st);
+int three_view_sources_launch(ss2_ctx* ctx, const float* m1_c, const float* mid_c, const float* m3_c, int n, int img_h,
+                              int img_w, float xmin, float ymin, float out_w, float out_h, float* source, float* target,
+                              cudaStream_t st);
+int blend3_avg_launch(ss2_ctx* ctx, const float* w1, const float* w2, const float* w3, size_t count, float* out,
+                      cudaStream_t st);
 // conv_tc.cu: cuTensorMapEncodeTiled (driver entry point), null if unavailable
 void* ss2_tensormap_encode_fn();
 // conv.cu

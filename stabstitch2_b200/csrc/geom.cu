@@ -407,3 +407,180 @@ int stable_meshes_launch(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Three-view glue (test_online_tra_threeview.py:345-455): two stitched pairs (1,2) and (2,3) share their
+// middle view; pair (2,3) is shifted onto pair (1,2) by the per-frame mean vertex offset of the shared view, the
+// middle plane is the average of the two instances of that view, and the outer meshes are moved through the TPS
+// that maps their pair's instance of the shared view onto the middle plane.
+// All three kernels are single-CTA (a stream has a few thousand vertices) and keep the reference's fp32
+// operation order.  Block-wide min/max helper first.
+// ------------------------------------------------------------------------------------------
+__device__ void block_minmax4(float& xmin, float& xmax, float& ymin, float& ymax, float (*red)[32]) {
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+    ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+  }
+  const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+  __syncthreads();
+  if (l == 0) { red[0][w] = xmin; red[1][w] = xmax; red[2][w] = ymin; red[3][w] = ymax; }
+  __syncthreads();
+  const int nw = blockDim.x / 32;
+  xmin = red[0][0]; xmax = red[1][0]; ymin = red[2][0]; ymax = red[3][0];
+  for (int i = 1; i < nw; ++i) {
+    xmin = fminf(xmin, red[0][i]); xmax = fmaxf(xmax, red[1][i]);
+    ymin = fminf(ymin, red[2][i]); ymax = fmaxf(ymax, red[3][i]);
+  }
+}
+
+// work: 5 arrays [n][63][2] (a1, a2, b1, b2, mid in hr pixels); outputs: the five normalised TPS-point operands,
+// mid_c (middle mesh in provisional-canvas pixels), canvas1 = (wmin, hmin, out_w, out_h)
+__global__ void __launch_bounds__(256)
+three_view_align_kernel(const float* __restrict__ w12m1, const float* __restrict__ w12m2,
+                        const float* __restrict__ w23m1, const float* __restrict__ w23m2, int n, float img_h,
+                        float img_w, float* __restrict__ work, float* __restrict__ pt12, float* __restrict__ src12,
+                        float* __restrict__ pt23, float* __restrict__ src23, float* __restrict__ tgt,
+                        float* __restrict__ mid_c, float* __restrict__ canvas1) {
+  __shared__ float red[4][32];
+  const size_t m = (size_t)n * SS2_NPT * 2;
+  float *a1 = work, *a2 = work + m, *b1 = work + 2 * m, *b2 = work + 3 * m, *mid = work + 4 * m;
+  // rescale to the frame resolution (:347-351)
+  for (size_t i = threadIdx.x; i < m; i += blockDim.x) {
+    const bool isx = (i & 1) == 0;
+    const float s = isx ? img_w : img_h, d = isx ? 480.0f : 360.0f;
+    a1[i] = __fdiv_rn(__fmul_rn(w12m1[i], s), d);
+    a2[i] = __fdiv_rn(__fmul_rn(w12m2[i], s), d);
+    b1[i] = __fdiv_rn(__fmul_rn(w23m1[i], s), d);
+    b2[i] = __fdiv_rn(__fmul_rn(w23m2[i], s), d);
+  }
+  __syncthreads();
+  // per-frame mean offset of the shared view (:354-360), shift pair (2,3), middle plane (:363); one warp per frame
+  for (int k = threadIdx.x / 32; k < n; k += blockDim.x / 32) {
+    const int lane = threadIdx.x % 32;
+    float sx = 0.f, sy = 0.f;
+    for (int p = lane; p < SS2_NPT; p += 32) {
+      const size_t o = ((size_t)k * SS2_NPT + p) * 2;
+      sx += a2[o] - b1[o];
+      sy += a2[o + 1] - b1[o + 1];
+    }
+    for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+    const float ox = sx / (float)SS2_NPT, oy = sy / (float)SS2_NPT;
+    for (int p = lane; p < SS2_NPT; p += 32) {
+      const size_t o = ((size_t)k * SS2_NPT + p) * 2;
+      b1[o] += ox; b1[o + 1] += oy;
+      b2[o] += ox; b2[o + 1] += oy;
+      mid[o] = (a2[o] + b1[o]) / 2.0f;
+      mid[o + 1] = (a2[o + 1] + b1[o + 1]) / 2.0f;
+    }
+  }
+  __syncthreads();
+  // provisional canvas over the four meshes (:366-399)
+  float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  for (size_t i = threadIdx.x; i < 4 * (m / 2); i += blockDim.x) {
+    const float x = work[2 * i], y = work[2 * i + 1];
+    xmin = fminf(xmin, x); xmax = fmaxf(xmax, x);
+    ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+  }
+  block_minmax4(xmin, xmax, ymin, ymax, red);
+  const float ow = xmax - xmin, oh = ymax - ymin;
+  if (threadIdx.x == 0) { canvas1[0] = xmin; canvas1[1] = ymin; canvas1[2] = ow; canvas1[3] = oh; }
+  // translate into the canvas and normalise (:406-420)
+  for (size_t i = threadIdx.x; i < m; i += blockDim.x) {
+    const bool isx = (i & 1) == 0;
+    const float mn = isx ? xmin : ymin, ext = isx ? ow : oh;
+    pt12[i] = norm1(a1[i] - mn, ext);
+    src12[i] = norm1(a2[i] - mn, ext);
+    pt23[i] = norm1(b2[i] - mn, ext);
+    src23[i] = norm1(b1[i] - mn, ext);
+    const float mc = mid[i] - mn;
+    mid_c[i] = mc;
+    tgt[i] = norm1(mc, ext);
+  }
+}
+
+// moved12 / moved23: TPS-point outputs (normalised) -> recovered meshes m1_c, m3_c (provisional-canvas pixels,
+// :421-424) and the new canvas over (m1_c, mid_c, m3_c) (:436-455): canvas2 = (wmin, hmin, out_w, out_h)
+__global__ void __launch_bounds__(256)
+three_view_canvas_kernel(const float* __restrict__ moved12, const float* __restrict__ moved23,
+                         const float* __restrict__ mid_c, const float* __restrict__ canvas1, int n,
+                         float* __restrict__ m1_c, float* __restrict__ m3_c, float* __restrict__ canvas2) {
+  __shared__ float red[4][32];
+  const size_t m = (size_t)n * SS2_NPT * 2;
+  const float ow = canvas1[2], oh = canvas1[3];
+  float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  for (size_t i = threadIdx.x; i < m / 2; i += blockDim.x) {
+    // recover_mesh: (n + 1) * extent / 2
+    const float x1 = __fdiv_rn(__fmul_rn(__fadd_rn(moved12[2 * i], 1.0f), ow), 2.0f);
+    const float y1 = __fdiv_rn(__fmul_rn(__fadd_rn(moved12[2 * i + 1], 1.0f), oh), 2.0f);
+    const float x3 = __fdiv_rn(__fmul_rn(__fadd_rn(moved23[2 * i], 1.0f), ow), 2.0f);
+    const float y3 = __fdiv_rn(__fmul_rn(__fadd_rn(moved23[2 * i + 1], 1.0f), oh), 2.0f);
+    m1_c[2 * i] = x1; m1_c[2 * i + 1] = y1;
+    m3_c[2 * i] = x3; m3_c[2 * i + 1] = y3;
+    const float x2 = mid_c[2 * i], y2 = mid_c[2 * i + 1];
+    xmin = fminf(xmin, fminf(x1, fminf(x2, x3))); xmax = fmaxf(xmax, fmaxf(x1, fmaxf(x2, x3)));
+    ymin = fminf(ymin, fminf(y1, fminf(y2, y3))); ymax = fmaxf(ymax, fmaxf(y1, fmaxf(y2, y3)));
+  }
+  block_minmax4(xmin, xmax, ymin, ymax, red);
+  if (threadIdx.x == 0) { canvas2[0] = xmin; canvas2[1] = ymin; canvas2[2] = xmax - xmin; canvas2[3] = ymax - ymin; }
+}
+
+// per view v (grid.y): normalised canvas mesh (source) and normalised rigid mesh (target), [n][63][2] each (:470-486)
+__global__ void three_view_sources_kernel(const float* __restrict__ m1_c, const float* __restrict__ mid_c,
+                                          const float* __restrict__ m3_c, int n, float img_h, float img_w, float xmin,
+                                          float ymin, float out_w, float out_h, float* __restrict__ source,
+                                          float* __restrict__ target) {
+  const int k = blockIdx.x, v = blockIdx.y, tid = threadIdx.x;
+  if (tid >= SS2_NPT) return;
+  const float* p = (v == 0 ? m1_c : v == 1 ? mid_c : m3_c) + ((size_t)k * SS2_NPT + tid) * 2;
+  const size_t o = (((size_t)v * n + k) * SS2_NPT + tid) * 2;
+  source[o] = norm1(__fsub_rn(p[0], xmin), out_w);
+  source[o + 1] = norm1(__fsub_rn(p[1], ymin), out_h);
+  const int gi = tid / (SS2_GRID_W + 1), gj = tid % (SS2_GRID_W + 1);
+  target[o] = norm1(lin0(gj, SS2_GRID_W + 1, img_w), img_w);
+  target[o + 1] = norm1(lin0(gi, SS2_GRID_H + 1, img_h), img_h);
+}
+
+// AVERAGE fusion of three warped views: fuse(1,2) then fuse(12,3) (:489-490), reference operation order
+__global__ void blend3_avg_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3,
+                                  size_t count, float* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    const float a = w1[i], b = w2[i], c = w3[i];
+    const float s = __fadd_rn(__fadd_rn(a, b), 1e-6f);
+    const float f12 = __fadd_rn(__fmul_rn(a, __fdiv_rn(a, s)), __fmul_rn(b, __fdiv_rn(b, s)));
+    const float t = __fadd_rn(__fadd_rn(f12, c), 1e-6f);
+    __stcs(out + i, __fadd_rn(__fmul_rn(f12, __fdiv_rn(f12, t)), __fmul_rn(c, __fdiv_rn(c, t))));
+  }
+}
+
+int three_view_align_launch(ss2_ctx* ctx, const float* w12m1, const float* w12m2, const float* w23m1, const float* w23m2,
+                            int n, int img_h, int img_w, float* work, float* pt12, float* src12, float* pt23, float* src23,
+                            float* tgt, float* mid_c, float* canvas1, cudaStream_t st) {
+  three_view_align_kernel<<<1, 256, 0, st>>>(w12m1, w12m2, w23m1, w23m2, n, (float)img_h, (float)img_w, work, pt12, src12,
+                                             pt23, src23, tgt, mid_c, canvas1);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+int three_view_canvas_launch(ss2_ctx* ctx, const float* moved12, const float* moved23, const float* mid_c,
+                             const float* canvas1, int n, float* m1_c, float* m3_c, float* canvas2, cudaStream_t st) {
+  three_view_canvas_kernel<<<1, 256, 0, st>>>(moved12, moved23, mid_c, canvas1, n, m1_c, m3_c, canvas2);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+int three_view_sources_launch(ss2_ctx* ctx, const float* m1_c, const float* mid_c, const float* m3_c, int n, int img_h,
+                              int img_w, float xmin, float ymin, float out_w, float out_h, float* source, float* target,
+                              cudaStream_t st) {
+  three_view_sources_kernel<<<dim3(n, 3), 64, 0, st>>>(m1_c, mid_c, m3_c, n, (float)img_h, (float)img_w, xmin, ymin, out_w,
+                                                      out_h, source, target);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+int blend3_avg_launch(ss2_ctx* ctx, const float* w1, const float* w2, const float* w3, size_t count, float* out,
+                      cudaStream_t st) {
+  if (count == 0) return SS2_OK;
+  const int blocks = (int)((count + 255) / 256 < 148 * 16 ? (count + 255) / 256 : 148 * 16);
+  blend3_avg_kernel<<<blocks, 256, 0, st>>>(w1, w2, w3, count, out);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}

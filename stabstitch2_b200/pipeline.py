@@ -63,6 +63,52 @@ def stable_frames(hr1, hr2, mesh1, mesh2, minmax_host, mode="NORMAL", tps=None, 
     return out
 
 
+def three_view_meshes(w12m1, w12m2, w23m1, w23m2, img_h, img_w):
+    """Middle-plane alignment of two stitched pairs sharing their middle view
+    (test_online_tra_threeview.py:345-455).  Smooth meshes [n,7,9,2] @480x360 (w12m2 and w23m1 are the two
+    instances of the shared view) -> (mesh1, middle, mesh3 [n,7,9,2] CUDA, canvas [4] CUDA =
+    width_min, height_min, out_width, out_height of the new canvas)."""
+    ctx = _lib.context()
+    ms = [_lib.dev_f32(t).reshape(-1, 7, 9, 2) for t in (w12m1, w12m2, w23m1, w23m2)]
+    n = ms[0].shape[0]
+    outs = [torch.empty(n, 7, 9, 2, device=ms[0].device, dtype=torch.float32) for _ in range(3)]
+    canvas = torch.empty(4, device=ms[0].device, dtype=torch.float32)
+    ctx.check(ctx.lib.ss2_three_view_meshes(ctx.handle, *[_lib.ptr(t) for t in ms], n, int(img_h), int(img_w),
+                                            *[_lib.ptr(t) for t in outs], _lib.ptr(canvas), _lib.cur_stream()))
+    return outs[0], outs[1], outs[2], canvas
+
+
+def three_view_frames(imgs1, imgs2, imgs3, mesh1, middle, mesh3, canvas_host, mode="NORMAL", tps=None):
+    """The three-image warp + AVERAGE fusion loop (test_online_tra_threeview.py:461-490): images [n,3,H,W] CUDA
+    per view, meshes from three_view_meshes, canvas (4 host floats) -> fused [n,3,Ho,Wo]."""
+    from .utils import torch_tps_transform as tt
+    ctx = _lib.context()
+    a, b, c = _lib.dev_f32(imgs1), _lib.dev_f32(imgs2), _lib.dev_f32(imgs3)
+    n, _, H, W = a.shape
+    cv = [float(v) for v in canvas_host]
+    Ho, Wo = int(cv[3]), int(cv[2])
+    out = torch.empty(n, 3, Ho, Wo, device=a.device, dtype=torch.float32)
+    hc = (ctypes.c_float * 4)(*cv)
+    ctx.check(ctx.lib.ss2_three_view_frames(ctx.handle, _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(_lib.dev_f32(mesh1)),
+                                            _lib.ptr(_lib.dev_f32(middle)), _lib.ptr(_lib.dev_f32(mesh3)), n, H, W, hc,
+                                            _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps, _lib.ptr(out),
+                                            _lib.cur_stream()))
+    return out
+
+
+def three_view_stable(img1_list, img2_list, img3_list, w12m1, w12m2, w23m1, w23m2, warp_mode="NORMAL"):
+    """Drop-in for the tail of test_online_tra_threeview.py's test() (:345-505, AVERAGE fusion): image lists of
+    [1,3,H,W] fp32 0..255, smooth meshes [1,N,7,9,2] of the two pairs -> list of N CPU tensors [3,Ho,Wo]."""
+    a = torch.cat([_lib.dev_f32(t) for t in img1_list], 0)
+    b = torch.cat([_lib.dev_f32(t) for t in img2_list], 0)
+    c = torch.cat([_lib.dev_f32(t) for t in img3_list], 0)
+    _, _, H, W = a.shape
+    m1, mid, m3, canvas = three_view_meshes(w12m1, w12m2, w23m1, w23m2, H, W)
+    fused = three_view_frames(a, b, c, m1, mid, m3, canvas.cpu().tolist(), warp_mode)
+    host = fused.cpu()
+    return [host[k] for k in range(host.shape[0])]
+
+
 def get_stable_sqe(img1_list, img2_list, smooth_mesh1, smooth_mesh2, warp_mode="NORMAL", fusion_mode="AVERAGE"):
     """Drop-in for test_online_tra.py:96-154 (AVERAGE fusion): lists of [1,3,H,W] fp32 0..255
     frames, smooth meshes [1,N,7,9,2] -> (list of [Ho,Wo,3] numpy frames, out_width, out_height)."""

@@ -23,3 +23,9 @@ def golden_ops():
 def golden_stream():
     import numpy as np
     return dict(np.load(os.path.join(GOLDEN, "stream_small.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_threeview():
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "threeview.npz")))

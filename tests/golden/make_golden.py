@@ -69,6 +69,52 @@ def ops_case(m):
     return {k: v.detach().numpy() for k, v in out.items()}
 
 
+def threeview_inputs():
+    """Seeded inputs of the three-view case: four smooth meshes @480x360 (pair (1,2) and pair (2,3) of a
+    three-camera rig; the shared middle view appears in both pairs with a different absolute position) and
+    three 3-frame 96x128 image streams."""
+    g = torch.Generator().manual_seed(33)
+    N = 3
+    rig = O.rigid_mesh(1, 360, 480)[:, None].expand(1, N, 7, 9, 2)
+
+    def mesh(dx, dy, amp):
+        return rig + torch.tensor([dx, dy]) + amp * torch.randn(1, N, 7, 9, 2, generator=g)
+    w12m1, w12m2 = mesh(-80.0, 3.0, 2.5), mesh(85.0, -2.0, 2.5)
+    w23m1, w23m2 = mesh(-70.0, 6.0, 2.5), mesh(95.0, 1.0, 2.5)
+    H, W = 96, 128
+    imgs = [[O.synth_frame(t, v, H, W) for t in range(N)] for v in range(3)]
+    return w12m1, w12m2, w23m1, w23m2, imgs
+
+
+def threeview_case(m):
+    """Runs the reference's OWN three-view glue: the body of test() in test_online_tra_threeview.py between
+    '# resize the mesh to the original resolution' and the video writer is executed verbatim (read from
+    /root/reference at generation time, never copied into the repository) on the inputs above."""
+    import argparse
+    import textwrap
+    w12m1, w12m2, w23m1, w23m2, imgs = threeview_inputs()
+    path = os.path.join(ref_harness.REF_DIR, "test_online_tra_threeview.py")
+    lines = open(path).read().split("\n")
+    start = next(i for i, l in enumerate(lines) if "resize the mesh to the original resolution" in l)
+    stop = next(i for i, l in enumerate(lines) if 'print("begin to write into video")' in l)
+    body = textwrap.dedent("\n".join(lines[start:stop]))
+    D = m["test_online_tra"]
+    ns = {"torch": torch, "get_norm_mesh": D.get_norm_mesh, "recover_mesh": D.recover_mesh,
+          "get_rigid_mesh": D.get_rigid_mesh, "torch_tps_transform": m["utils.torch_tps_transform"],
+          "torch_tps_transform_point": m["utils.torch_tps_transform_point"],
+          "args": argparse.Namespace(fusion_mode="AVERAGE", warp_mode="NORMAL"),
+          "img1_list": imgs[0], "img2_list": imgs[1], "img3_list": imgs[2],
+          "warp12_mesh1": w12m1.clone(), "warp12_mesh2": w12m2.clone(),
+          "warp23_mesh1": w23m1.clone(), "warp23_mesh2": w23m2.clone()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(body, path, "exec"), ns)
+    out = {"in_w12m1": w12m1, "in_w12m2": w12m2, "in_w23m1": w23m1, "in_w23m2": w23m2,
+           "mesh1": ns["warp12_mesh1"], "middle": ns["middle_mesh"], "mesh3": ns["warp23_mesh2"],
+           "canvas": torch.stack([ns["width_min"], ns["height_min"], ns["out_width"], ns["out_height"]]),
+           "frames": torch.stack(ns["stable_list"], 0)}
+    return {k: (v.detach().numpy() if torch.is_tensor(v) else v) for k, v in out.items()}
+
+
 def stream_case(m):
     S, T, Sm, D = (m["spatial_network"], m["temporal_network"], m["smooth_network"], m["test_online_tra"])
     tpp = m["utils.torch_tps_transform_point"]
@@ -144,7 +190,12 @@ def stream_case(m):
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
     mods = ref_harness.load()
-    np.savez_compressed(os.path.join(HERE, "ops.npz"), **ops_case(mods))
-    np.savez_compressed(os.path.join(HERE, "stream_small.npz"), **stream_case(mods))
-    for f in ("ops.npz", "stream_small.npz"):
+    only = sys.argv[1:]
+    if not only or "ops" in only:
+        np.savez_compressed(os.path.join(HERE, "ops.npz"), **ops_case(mods))
+    if not only or "stream" in only:
+        np.savez_compressed(os.path.join(HERE, "stream_small.npz"), **stream_case(mods))
+    if not only or "threeview" in only:
+        np.savez_compressed(os.path.join(HERE, "threeview.npz"), **threeview_case(mods))
+    for f in ("ops.npz", "stream_small.npz", "threeview.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -467,3 +467,80 @@ def test_ccl_c256_tensor_core_vs_oracle():
     f2 = torch.roll(f1, (1, -2), (2, 3)) + 0.3 * torch.randn(2, 256, 23, 30, generator=g)
     got = SpatialNet().CCL(f1.cuda(), f2.cuda())
     assert maxdiff(got, O.ccl(f1, f2)) < 2e-4
+
+
+# ---------------------------------------------------------------- three views (test_online_tra_threeview.py:345-505)
+def test_three_view_vs_reference_golden(golden_threeview):
+    """middle-plane meshes, canvas and fused frames against the reference's own three-view glue"""
+    from stabstitch2_b200 import pipeline
+    from tests.golden.make_golden import threeview_inputs
+    g = golden_threeview
+    w12m1, w12m2, w23m1, w23m2, imgs = threeview_inputs()
+    m1, mid, m3, canvas = pipeline.three_view_meshes(w12m1[0], w12m2[0], w23m1[0], w23m2[0], 96, 128)
+    for got, key in ((m1, "mesh1"), (mid, "middle"), (m3, "mesh3")):
+        assert np.abs(got.cpu().numpy() - g[key][0]).max() < 2e-3, key
+    assert np.abs(canvas.cpu().numpy() - g["canvas"]).max() < 2e-3
+    frames = pipeline.three_view_stable(imgs[0], imgs[1], imgs[2], w12m1, w12m2, w23m1, w23m2)
+    assert len(frames) == 3 and tuple(frames[0].shape) == tuple(g["frames"][0].shape)
+    for k in range(3):
+        d = np.abs(frames[k].numpy() - g["frames"][k])
+        # 96x128 frames: the three hard image borders (where a 1e-4 px coordinate difference flips a sample in or
+        # out of a view) are ~6% of this small canvas, so the flip fraction is higher than on full-size frames
+        assert (d > 0.05).mean() < 4e-3, (k, (d > 0.05).mean())
+        assert np.median(d) < 1e-3 and np.percentile(d, 99) < 2e-2
+
+
+def test_three_view_720p_vs_oracle():
+    """full-size three-view frame (lattice field) against the CPU oracle's restatement"""
+    from stabstitch2_b200 import pipeline
+    H, W = 720, 1280
+    g = torch.Generator().manual_seed(5)
+    rig = O.rigid_mesh(1, 360, 480)[:, None]
+
+    def mesh(dx, dy):
+        return rig + torch.tensor([dx, dy]) + 2.5 * torch.randn(1, 1, 7, 9, 2, generator=g)
+    w12m1, w12m2, w23m1, w23m2 = mesh(-80.0, 3.0), mesh(85.0, -2.0), mesh(-70.0, 6.0), mesh(95.0, 1.0)
+    # mid-grey smooth frames: the reference's blend a*(a/(a+b+1e-6)) amplifies the rounding residue of an uncovered
+    # view wherever the covered view is dark, which no re-implementation reproduces
+    imgs = [_smooth_frame(10 + v, H, W) for v in range(3)]
+    with torch.no_grad():
+        rm1, rmid, rm3, wmin, hmin, ow, oh = O.three_view_meshes(w12m1, w12m2, w23m1, w23m2, H, W)
+        ref = O.three_view_frame(imgs[0], imgs[1], imgs[2], rm1[:, 0], rmid[:, 0], rm3[:, 0], wmin, hmin, ow, oh)
+    m1, mid, m3, canvas = pipeline.three_view_meshes(w12m1[0], w12m2[0], w23m1[0], w23m2[0], H, W)
+    assert (m1.cpu() - rm1[0]).abs().max() < 5e-3 and (m3.cpu() - rm3[0]).abs().max() < 5e-3
+    assert (mid.cpu() - rmid[0]).abs().max() < 1e-3
+    cv = canvas.cpu().tolist()
+    assert abs(cv[2] - float(ow)) < 5e-3 and abs(cv[3] - float(oh)) < 5e-3
+    # use the oracle's canvas so that both sides sample the same grid even if the extents differ in the last bit
+    fused = pipeline.three_view_frames(imgs[0].cuda(), imgs[1].cuda(), imgs[2].cuda(), rm1[0].cuda(), rmid[0].cuda(), rm3[0].cuda(),
+                                       [float(wmin), float(hmin), float(ow), float(oh)])[0].cpu()
+    assert tuple(fused.shape) == tuple(ref.shape)
+    # The reference's AVERAGE fusion a*(a/(a+b+1e-6)) is ill-conditioned wherever BOTH of its inputs are rounding
+    # residues of uncovered views: in the part of the canvas that only view 3 covers, stage one fuses two residues
+    # (|r| <~ 3e-2) and returns up to +-20 grey levels at ~1% of the pixels (tests/probe_tv.py), which then leak
+    # into the output; where nothing covers, values reach 5e5.  No re-implementation reproduces those bits, so:
+    #   region A (view 1 or view 2 covers): compare with the reference restatement, residue-sized bounds;
+    #   region B (only view 3 covers): our frame must equal view 3 warped alone (c*c/(c+1e-6));
+    #   elsewhere: ~0 from us.
+    Ho, Wo = ref.shape[1:]
+    nrig = O.norm_mesh(O.rigid_mesh(1, H, W), H, W)
+    cov, srcs, far = [], [], []
+    for M in (rm1, rmid, rm3):
+        tt = torch.stack([M[0, 0, ..., 0] - wmin, M[0, 0, ..., 1] - hmin], 2)[None]
+        srcs.append(O.norm_mesh(tt, oh, ow))
+        ax, ay = O.tps_source_coords_fp64(srcs[-1], nrig, Ho, Wo, W, H)
+        cov.append((ax[0] > 1) & (ax[0] < W - 2) & (ay[0] > 1) & (ay[0] < H - 2))
+        far.append((ax[0] < -1) | (ax[0] > W) | (ay[0] < -1) | (ay[0] > H))  # certainly outside the image
+    region_a = cov[0] | cov[1]
+    region_b = cov[2] & far[0] & far[1]
+    assert region_a.mean() > 0.4 and region_b.mean() > 0.05
+    d = (fused - ref).abs().numpy()
+    da = d[:, region_a]
+    assert (da > 0.1).mean() < 1e-3, ((da > 0.1).mean(), da.max())
+    assert np.median(da) < 2e-3 and np.percentile(da, 99) < 6e-2, (np.median(da), np.percentile(da, 99))
+    with torch.no_grad():
+        c = O.tps_warp(imgs[2], srcs[2], nrig, (Ho, Wo))[0]
+    db = (fused - c * (c / (c + 1e-6))).abs().numpy()[:, region_b]
+    assert (db > 0.1).mean() < 1e-3 and np.percentile(db, 99) < 6e-2, ((db > 0.1).mean(), np.percentile(db, 99))
+    rest = np.abs(fused.numpy()[:, far[0] & far[1] & far[2]])
+    assert rest.max() < 256.0 and np.median(rest) < 1e-3

@@ -99,3 +99,23 @@ def test_stream(golden_stream):
     assert (d > 0.05).mean() < 1e-3, (d > 0.05).mean()
     d = np.abs(out["frames"][-1][::8] - g["frame_last_rows8"])
     assert (d > 0.05).mean() < 1e-3
+
+
+def test_three_view(golden_threeview):
+    """the oracle's three-view glue against the reference's own (test_online_tra_threeview.py:345-505,
+    executed verbatim by tests/golden/make_golden.py::threeview_case)"""
+    from tests.golden.make_golden import threeview_inputs
+    g = golden_threeview
+    w12m1, w12m2, w23m1, w23m2, imgs = threeview_inputs()
+    close(w12m1, g["in_w12m1"], 0.0)
+    with torch.no_grad():
+        m1, mid, m3, wmin, hmin, ow, oh = O.three_view_meshes(w12m1, w12m2, w23m1, w23m2, 96, 128)
+        close(m1, g["mesh1"], 1e-4)
+        close(mid, g["middle"], 1e-4)
+        close(m3, g["mesh3"], 1e-4)
+        assert np.abs(np.array([float(wmin), float(hmin), float(ow), float(oh)]) - g["canvas"]).max() < 1e-4
+        for k in range(3):
+            f = O.three_view_frame(imgs[0][k], imgs[1][k], imgs[2][k], m1[:, k], mid[:, k], m3[:, k], wmin, hmin, ow, oh)
+            d = np.abs(f.numpy() - g["frames"][k])
+            assert (d > 0.05).mean() < 1e-3, (d > 0.05).mean()
+            assert np.median(d) < 1e-4
