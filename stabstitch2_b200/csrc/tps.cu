@@ -1270,6 +1270,396 @@ tps_warp_tile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// PERSISTENT tile resampler (SS2_TPS_TILE=2): the staged kernel above with its per-tile prologue taken off the
+// critical path.  One CTA per SM walks a contiguous range of 64 x 32 canvas tiles (consecutive tiles are vertical
+// neighbours, so their source boxes overlap in L2).  Two PRODUCER warps run one tile ahead of sixteen CONSUMER
+// warps through a two-slot ring (source boxes, y-contracted lattice, near list, box geometry per slot):
+//   producer 0:   predictor, box geometry from the footprint estimate, TMA issue;
+//   producer 1:   near list;
+//   producers 2+: y contraction of the lattice with predictor and reference origin folded in (a quarter each);
+//   consumers:  x contraction, near field, LDS taps, packed blend, streaming stores (4 rows per thread).
+// full[slot] counts the producer warps + the TMA bytes, empty[slot] the sixteen consumer warps.
+// ------------------------------------------------------------------------------------------
+#define PT_W TL_W
+#define PT_H 32
+#define PT_RPT 4
+#define PT_CWARPS 16
+#define PT_YWARPS 4                         // producer warps sharing the y contraction
+#define PT_PWARPS (2 + PT_YWARPS)           // + box geometry / TMA issue, near list
+#define PT_THREADS ((PT_CWARPS + PT_PWARPS) * 32)
+#define PT_SMEM_BYTES (2 * 2 * 3 * TL_PLANE * 4)
+
+__device__ __forceinline__ void pt_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(tl_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void pt_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl_smem_u32(bar)) : "memory");
+}
+
+template <int SX, int SY>
+__global__ void __launch_bounds__(PT_THREADS, 1)
+tps_warp_ptile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_constant__ CUtensorMap tm0b,
+                      const __grid_constant__ CUtensorMap tm0c, const __grid_constant__ CUtensorMap tm1a,
+                      const __grid_constant__ CUtensorMap tm1b, const __grid_constant__ CUtensorMap tm1c, WarpParams P,
+                      int ntx, int nty, int total) {
+  static_assert(TL_RPT == 8 && PT_H == TL_H, "the persistent kernel shares the 64 x 32 tile / 88 x 44 box of the staged kernel");
+  constexpr int V = 2, C = 3;
+  constexpr int NCOL = TileCols<SX>::value;
+  constexpr int SLOT_FLOATS = V * C * TL_PLANE;
+  extern __shared__ __align__(128) float tiles[];  // [2 slots][V][3][TL_BH][TL_BW]
+  __shared__ float4 s_near[2][V * SS2_NPT];
+  __shared__ __align__(16) float2 s_ysm[2][PT_H][NCOL][V];
+  __shared__ int s_cnt[2][2];
+  __shared__ int s_r0[2][V][2];
+  __shared__ TileGeo s_geo[2][V];
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int W = P.W, H = P.H;
+  const unsigned FULL = 0xffffffffu;
+  const int t_begin = (int)((long long)blockIdx.x * total / gridDim.x), t_end = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
+
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&s_full[b])), "n"(PT_PWARPS));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&s_empty[b])), "n"(PT_CWARPS));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (wid >= PT_CWARPS) {
+    // ================= producers =================
+    const int role = wid - PT_CWARPS;  // 0: box geometry + TMA issue, 1: near list, 2..: y contraction
+    for (int t = t_begin, i = 0; t < t_end; ++t, ++i) {
+      const int slot = i & 1;
+      const int by = t % nty, bx = (t / nty) % ntx, n = t / (nty * ntx);
+      const int col0 = bx * PT_W, row0 = by * PT_H;
+      const int jx0 = col0 / SX;
+      if (i >= 2) pt_wait(&s_empty[slot], ((i >> 1) - 1) & 1);
+      // predictor and R0 = floor(predictor at the tile origin): both producers need them
+      float pr = 0.f;
+      if (lane < V * 6) pr = P.aux[(size_t)(n * V + lane / 6) * 8 + lane % 6];
+      float pd[V][6];
+#pragma unroll
+      for (int q = 0; q < V * 6; ++q) pd[q / 6][q % 6] = __shfl_sync(FULL, pr, q);
+      int r0[V][2];
+      float base[V][2];
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const double b = (double)pd[v][3 * d] * col0 + (double)pd[v][3 * d + 1] * row0 + (double)pd[v][3 * d + 2];
+          const double fb = floor(fmin(fmax(b, -1.0e6), 1.0e6));
+          r0[v][d] = (int)fb;
+          base[v][d] = (float)(b - fb);
+        }
+      if (role == 1) {
+        // ---- near list (view-0 entries first)
+        {
+          const float x_lo = fmaf(P.stepx, (float)col0, -1.0f), x_hi = fmaf(P.stepx, (float)min(col0 + PT_W - 1, P.Wo - 1), -1.0f);
+          const float y_lo = fmaf(P.stepy, (float)row0, -1.0f), y_hi = fmaf(P.stepy, (float)min(row0 + PT_H - 1, P.Ho - 1), -1.0f);
+          int cnt = 0, cnt0 = 0;
+          float2 cs[(V * SS2_NPT + 31) / 32];
+#pragma unroll
+          for (int it = 0; it < (V * SS2_NPT + 31) / 32; ++it) {  // all loads in flight together
+            const int idx = it * 32 + lane;
+            cs[it] = idx < V * SS2_NPT ? __ldg(reinterpret_cast<const float2*>(P.source + ((size_t)n * V * SS2_NPT + idx) * 2))
+                                       : make_float2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int it = 0; it < (V * SS2_NPT + 31) / 32; ++it) {
+            const int idx = it * 32 + lane;
+            bool hit = false;
+            const float2 c = cs[it];
+            if (idx < V * SS2_NPT) {
+              const float ddx = fmaxf(fmaxf(x_lo - c.x, c.x - x_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
+              hit = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
+            }
+            const unsigned m = __ballot_sync(FULL, hit);
+            if (hit) {
+              const int pv = idx >= SS2_NPT ? 1 : 0, pi = idx - pv * SS2_NPT;
+              const float* tt = P.T + (size_t)(n * V + pv) * 2 * SS2_NSYS;
+              s_near[slot][cnt + __popc(m & ((1u << lane) - 1u))] =
+                  make_float4(c.x, c.y, tt[3 + pi] * (P.half_w * LN2F), tt[SS2_NSYS + 3 + pi] * (P.half_h * LN2F));
+            }
+            cnt += __popc(m);
+            cnt0 += it == 0 ? __popc(m) : (it == 1 ? __popc(m & ((1u << (SS2_NPT - 32)) - 1u)) : 0);
+          }
+          if (lane == 0) { s_cnt[slot][0] = cnt; s_cnt[slot][1] = cnt0; }
+        }
+        __syncwarp();
+        if (lane == 0) pt_arrive(&s_full[slot]);
+      } else if (role == 0) {
+        if (lane < V * 2) s_r0[slot][lane >> 1][lane & 1] = r0[lane >> 1][lane & 1];
+        // ---- footprint estimate, box geometry (see tps_warp_tile_kernel)
+        const int lastc = min(PT_W - 1, P.Wo - 1 - col0), lastr = min(PT_H - 1, P.Ho - 1 - row0);
+        const int k = lane & 7, kk = k < 4 ? k : k + 1;
+        const int pr_ = (kk / 3) * lastr / 2, pc_ = (kk % 3) * lastc / 2;
+        const int ix = min((col0 + pc_ + SX / 2) / SX, P.nx - 1 - LAT_LO), iy = min((row0 + pr_ + SY / 2) / SY, P.ny - 1 - LAT_LO);
+        const float4 q = __ldg(reinterpret_cast<const float4*>(P.nodes + (((size_t)n * P.ny + iy + LAT_LO) * P.nx + ix + LAT_LO) * V));
+        const float fc = (float)pc_, fr = (float)pr_;
+        float e[4];
+        e[0] = q.x + fmaf(pd[0][0], fc, fmaf(pd[0][1], fr, base[0][0]));
+        e[1] = q.y + fmaf(pd[0][3], fc, fmaf(pd[0][4], fr, base[0][1]));
+        e[2] = q.z + fmaf(pd[1][0], fc, fmaf(pd[1][1], fr, base[1][0]));
+        e[3] = q.w + fmaf(pd[1][3], fc, fmaf(pd[1][4], fr, base[1][1]));
+        float mn[4], mx[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          mn[d] = mx[d] = e[d];
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(FULL, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(FULL, mx[d], o));
+          }
+        }
+        if (lane < V) {
+          const int v = lane;
+          const float lim = 1.0e6f;
+          const float fxmin = fmaxf(v == 0 ? mn[0] : mn[2], -lim), fymin = fmaxf(v == 0 ? mn[1] : mn[3], -lim);
+          const float fxmax = fminf(v == 0 ? mx[0] : mx[2], lim), fymax = fminf(v == 0 ? mx[1] : mx[3], lim);
+          const int rx0 = v == 0 ? r0[0][0] : r0[1][0], ry0 = v == 0 ? r0[0][1] : r0[1][1];
+          TileGeo g;
+          const int bx0 = (((int)floorf(fxmin) - TL_MARGIN + rx0) & ~3) - rx0, by0 = (int)floorf(fymin) - TL_MARGIN;
+          const int need_w = (int)floorf(fxmax) + 2 + TL_MARGIN - bx0, need_h = (int)floorf(fymax) + 2 + TL_MARGIN - by0;
+          g.tx0 = rx0 + bx0;
+          g.ty0 = ry0 + by0;
+          const bool hits = g.tx0 + need_w > 0 && g.tx0 < W && g.ty0 + need_h > 0 && g.ty0 < H;
+          const bool use = hits && need_w <= TL_BW && need_h <= TL_BH && !(P.dbg & 1);
+          g.rows = use ? (need_h <= TL_BH0 ? TL_BH0 : need_h <= TL_BH1 ? TL_BH1 : TL_BH) : 0;
+          const int lox = max(0, -g.tx0), loy = max(0, -g.ty0);
+          g.wxn = use ? max(min(TL_BW - 1, W - 1 - g.tx0) - lox, 0) : 0;
+          g.wyn = use ? max(min(g.rows - 1, H - 1 - g.ty0) - loy, 0) : 0;
+          if (g.wxn == 0 || g.wyn == 0) { g.rows = 0; g.wxn = 0; g.wyn = 0; }
+          g.lox = lox + bx0;
+          g.loy = loy + by0;
+          g.shift = by0 * TL_BW + bx0;
+          s_geo[slot][v] = g;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          const int rows0 = s_geo[slot][0].rows, rows1 = s_geo[slot][1].rows;
+          float* dst0 = tiles + (size_t)slot * SLOT_FLOATS;
+          if (rows0 + rows1 > 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tl_smem_u32(&s_full[slot])),
+                         "r"((uint32_t)((rows0 + rows1) * C * TL_BW * 4)) : "memory");
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const int rows = v == 0 ? rows0 : rows1;
+              if (rows > 0) {
+                const CUtensorMap* map = v == 0 ? (rows == TL_BH0 ? &tm0a : rows == TL_BH1 ? &tm0b : &tm0c)
+                                                : (rows == TL_BH0 ? &tm1a : rows == TL_BH1 ? &tm1b : &tm1c);
+                const int tx0 = s_geo[slot][v].tx0, ty0 = s_geo[slot][v].ty0;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                  asm volatile(
+                      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                      ::"r"(tl_smem_u32(dst0 + (v * C + c) * TL_PLANE)), "l"(map), "r"(tl_smem_u32(&s_full[slot])), "r"(tx0),
+                      "r"(ty0), "r"(n * C + c)
+                      : "memory");
+                }
+              }
+            }
+          } else {
+            pt_arrive(&s_full[slot]);
+          }
+        }
+      } else {
+        // ---- y contraction of the tile's node columns with predictor and R0 folded in
+        for (int item = (role - 2) * 32 + lane; item < PT_H * NCOL; item += 32 * PT_YWARPS) {
+          const int r = item / NCOL, j = item - r * NCOL;
+          if (jx0 + j < P.nx) {
+            const int row = min(row0 + r, P.Ho - 1);
+            const int cy = row / SY, ry = row - cy * SY;
+            const float2* nd = P.nodes + (((size_t)n * P.ny + cy) * P.nx + (jx0 + j)) * V;
+            const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SY)].w[ry][0]));
+            const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SY)].w[ry][4]));
+            const float wy_[LAT_TAPS] = {wlo.x, wlo.y, wlo.z, wlo.w, whi.x, whi.y};
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int b = 0; b < LAT_TAPS; ++b) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(nd + (size_t)b * P.nx * V));
+              a0 = fmaf(wy_[b], q.x, a0); a1 = fmaf(wy_[b], q.y, a1); a2 = fmaf(wy_[b], q.z, a2); a3 = fmaf(wy_[b], q.w, a3);
+            }
+            const float cr = (float)((jx0 + j - LAT_LO) * SX - col0), rr = (float)(row - row0);
+            a0 += fmaf(pd[0][0], cr, fmaf(pd[0][1], rr, base[0][0]));
+            a1 += fmaf(pd[0][3], cr, fmaf(pd[0][4], rr, base[0][1]));
+            a2 += fmaf(pd[1][0], cr, fmaf(pd[1][1], rr, base[1][0]));
+            a3 += fmaf(pd[1][3], cr, fmaf(pd[1][4], rr, base[1][1]));
+            *reinterpret_cast<float4*>(&s_ysm[slot][r][j][0]) = make_float4(a0, a1, a2, a3);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) pt_arrive(&s_full[slot]);
+      }
+    }
+    return;
+  }
+
+  // ================= consumers: warp (wx, wy) owns columns wx*32.., rows wy*4.. of the tile =================
+  const int wx = wid & 1, wy = wid >> 1;
+  const int colt = wx * 32 + lane, rt0 = wy * PT_RPT;
+  const unsigned oplane = (unsigned)(P.Ho * P.Wo);
+  u64 lxp[LAT_TAPS] = {0, 0, 0, 0, 0, 0};
+  int prev_bx = -1;
+  for (int t = t_begin, i = 0; t < t_end; ++t, ++i) {
+    const int slot = i & 1;
+    const int by = t % nty, bx = (t / nty) % ntx, n = t / (nty * ntx);
+    const int col0 = bx * PT_W, row0 = by * PT_H;
+    const int jx0 = col0 / SX;
+    const int col = min(col0 + colt, P.Wo - 1);
+    const bool active = col0 + colt < P.Wo;
+    const int cxi = col / SX, rx = col - cxi * SX, js = cxi - jx0;
+    if (bx != prev_bx) {  // the column's Lagrange weights only change with the strip
+      const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SX)].w[rx][0]));
+      const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SX)].w[rx][4]));
+      lxp[0] = pk2(wlo.x, wlo.x); lxp[1] = pk2(wlo.y, wlo.y); lxp[2] = pk2(wlo.z, wlo.z); lxp[3] = pk2(wlo.w, wlo.w);
+      lxp[4] = pk2(whi.x, whi.x); lxp[5] = pk2(whi.y, whi.y);
+      prev_bx = bx;
+    }
+    const float xt = fmaf(P.stepx, (float)col, -1.0f);
+    float* outp = P.out + (size_t)n * C * oplane;
+    const float* imgv[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) imgv[v] = P.img[v] + (size_t)n * C * H * W;
+    pt_wait(&s_full[slot], (i >> 1) & 1);
+    const int n_all = s_cnt[slot][0], n0 = s_cnt[slot][1];
+    const float4* near_list = s_near[slot];
+    int r0x[V], r0y[V], g_lox[V], g_wxn[V], g_loy[V], g_wyn[V];
+    uint32_t tbase[V];
+    const uint32_t tbase0 = tl_smem_u32(tiles + (size_t)slot * SLOT_FLOATS);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      r0x[v] = s_r0[slot][v][0]; r0y[v] = s_r0[slot][v][1];
+      g_lox[v] = s_geo[slot][v].lox; g_wxn[v] = s_geo[slot][v].wxn; g_loy[v] = s_geo[slot][v].loy; g_wyn[v] = s_geo[slot][v].wyn;
+      tbase[v] = tbase0 + (uint32_t)((v * (C * TL_PLANE) - s_geo[slot][v].shift) * 4);
+    }
+    unsigned cand = 0;
+    const bool cull = n_all <= 32;
+    if (n_all > 0) {
+      if (cull) {
+        bool keep = false;
+        if (lane < n_all) {
+          const float4 c = near_list[lane];
+          const float wx_lo = fmaf(P.stepx, (float)min(col0 + wx * 32, P.Wo - 1), -1.0f);
+          const float wx_hi = fmaf(P.stepx, (float)min(col0 + wx * 32 + 31, P.Wo - 1), -1.0f);
+          const float y_lo = fmaf(P.stepy, (float)min(row0 + rt0, P.Ho - 1), -1.0f);
+          const float y_hi = fmaf(P.stepy, (float)min(row0 + rt0 + PT_RPT - 1, P.Ho - 1), -1.0f);
+          const float ddx = fmaxf(fmaxf(wx_lo - c.x, c.x - wx_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
+          keep = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
+        }
+        cand = __ballot_sync(FULL, keep);
+      } else {
+        cand = FULL;
+      }
+    }
+#pragma unroll 2
+    for (int ii = 0; ii < PT_RPT; ++ii) {
+      const int r = rt0 + ii, row = row0 + r;
+      if (row >= P.Ho) break;  // warp-uniform
+      u64 acc0, acc1;
+      {
+        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(&s_ysm[slot][r][js][0]);
+        acc0 = fmul2(q.x, lxp[0]);
+        acc1 = fmul2(q.y, lxp[0]);
+      }
+#pragma unroll
+      for (int a = 1; a < LAT_TAPS; ++a) {
+        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(&s_ysm[slot][r][js + a][0]);
+        acc0 = ffma2(q.x, lxp[a], acc0);
+        acc1 = ffma2(q.y, lxp[a], acc1);
+      }
+      float px[V], py[V];
+      upk2(acc0, px[0], py[0]);
+      upk2(acc1, px[1], py[1]);
+      if (cand != 0u) {
+        const float yt = fmaf(P.stepy, (float)row, -1.0f);
+        unsigned m = cull ? cand : 0u;
+        int kk = 0;
+#pragma unroll 1
+        while (cull ? (m != 0u) : (kk < n_all)) {
+          int k;
+          if (cull) { k = __ffs(m) - 1; m &= m - 1; } else { k = kk++; }
+          const float4 c = near_list[k];
+          const float dx = xt - c.x, dy = yt - c.y;
+          const float s = fminf(fmaf(dy, dy, dx * dx), P.R2);
+          const float psi = fmaf(s, lg2_approx(s + 1e-6f), -blend_poly(s, P.R2, P.q0, P.q1, P.q2, P.q3));
+          if (k < n0) { px[0] = fmaf(c.z, psi, px[0]); py[0] = fmaf(c.w, psi, py[0]); }
+          else { px[1] = fmaf(c.z, psi, px[1]); py[1] = fmaf(c.w, psi, py[1]); }
+        }
+      }
+      float res[V][C];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int xi = __float2int_rd(px[v]), yi = __float2int_rd(py[v]);
+        const float fx = px[v] - (float)xi, fy = py[v] - (float)yi;
+        const bool ok = (unsigned)(xi - g_lox[v]) < (unsigned)g_wxn[v] && (unsigned)(yi - g_loy[v]) < (unsigned)g_wyn[v];
+        const unsigned okm = __ballot_sync(FULL, ok);
+        if (okm == FULL) {
+          const float gx = 1.0f - fx, gy = 1.0f - fy;
+          const u64 wA = pk2(gx * gy, fx * gy), wB = pk2(gx * fy, fx * fy);
+          const uint32_t ad = tbase[v] + (uint32_t)(yi * (TL_BW * 4) + xi * 4);
+          tile_taps<0>(ad, wA, wB, res[v][0]);
+          tile_taps<TL_PLANE * 4>(ad, wA, wB, res[v][1]);
+          tile_taps<2 * TL_PLANE * 4>(ad, wA, wB, res[v][2]);
+        } else {
+          const bool inimg = (unsigned)(xi + r0x[v]) < (unsigned)(W - 1) && (unsigned)(yi + r0y[v]) < (unsigned)(H - 1);
+          const bool slow = __any_sync(FULL, inimg && !ok);
+          const bool use = slow ? inimg : ok;
+          res[v][0] = res[v][1] = res[v][2] = 0.0f;
+          if (__any_sync(FULL, use)) {
+            const float fxs = use ? fx : 0.0f, gxs = use ? 1.0f - fx : 0.0f, fys = use ? fy : 0.0f, gys = 1.0f - fys;
+            const u64 wA = pk2(gxs * gys, fxs * gys), wB = pk2(gxs * fys, fxs * fys);
+            if (!slow) {
+              const uint32_t ad = use ? tbase[v] + (uint32_t)(yi * (TL_BW * 4) + xi * 4) : tbase0;
+              tile_taps<0>(ad, wA, wB, res[v][0]);
+              tile_taps<TL_PLANE * 4>(ad, wA, wB, res[v][1]);
+              tile_taps<2 * TL_PLANE * 4>(ad, wA, wB, res[v][2]);
+              if (!use) res[v][0] = res[v][1] = res[v][2] = 0.0f;
+            } else {
+              const float* p = imgv[v] + (use ? (size_t)(yi + r0y[v]) * W + (xi + r0x[v]) : (size_t)0);
+              const size_t iplane = (size_t)H * W;
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                const u64 top = pk2(__ldg(p + c * iplane), __ldg(p + c * iplane + 1));
+                const u64 bot = pk2(__ldg(p + c * iplane + W), __ldg(p + c * iplane + W + 1));
+                float lo, hi;
+                upk2(ffma2(bot, wB, fmul2(top, wA)), lo, hi);
+                res[v][c] = lo + hi;
+              }
+            }
+          }
+        }
+      }
+      if (active) {
+        const unsigned opix = (unsigned)(row * P.Wo + col);
+        const u64 A = pk2(res[0][0], res[0][1]), B = pk2(res[1][0], res[1][1]);
+        float s0, s1, q0, q1;
+        upk2(fadd2(fadd2(A, B), pk2(1e-6f, 1e-6f)), s0, s1);
+        upk2(ffma2(B, B, fmul2(A, A)), q0, q1);
+        __stcs(const_cast<float*>(f32_at(outp, opix)), q0 * rcp_approx(s0));
+        __stcs(const_cast<float*>(f32_at(outp, opix + oplane)), q1 * rcp_approx(s1));
+        __stcs(const_cast<float*>(f32_at(outp, opix + 2 * oplane)), blend_avg_fast(res[0][2], res[1][2]));
+      }
+    }
+    // this warp is done with the slot (its taps are in registers / stored): hand it back to the producers
+    __syncwarp();
+    if (lane == 0) pt_arrive(&s_empty[slot]);
+  }
+}
+
 static inline float linstep(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 
 // lattice configuration: spacing (SX, SY) in canvas pixels and near radius R (normalised)
@@ -1384,6 +1774,30 @@ static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, flo
       for (int h = 0; h < 3; ++h)
         maps = maps && make_img_map(&m[v][h], P.img[v], P.W, P.H, nframes * 3, h == 0 ? TL_BH0 : h == 1 ? TL_BH1 : TL_BH);
     if (maps) {
+      const char* te = getenv("SS2_TPS_TILE");
+      if (te && atoi(te) == 2) {
+        // persistent, warp-specialised variant: one CTA per SM walks a contiguous range of tiles
+        const int ntx = cdiv(P.Wo, PT_W), nty = cdiv(P.Ho, PT_H);
+        const long long total = (long long)ntx * nty * nframes;
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+        const int pgrid = (int)(total < nsm ? total : nsm);
+        if (total < 2000000000LL) {
+#define PTILE_CASE(SXV, SYV)                                                                                    \
+          if (cfg.SX == SXV && cfg.SY == SYV) {                                                                 \
+            static bool attr = false;                                                                           \
+            if (!attr) {                                                                                        \
+              SS2_CUDA(ctx, cudaFuncSetAttribute(tps_warp_ptile_kernel<SXV, SYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES)); \
+              attr = true;                                                                                      \
+            }                                                                                                   \
+            tps_warp_ptile_kernel<SXV, SYV><<<pgrid, PT_THREADS, PT_SMEM_BYTES, st>>>(m[0][0], m[0][1], m[0][2], m[1][0], m[1][1], m[1][2], P, ntx, nty, (int)total); \
+          }
+          PTILE_CASE(16, 8) PTILE_CASE(16, 6) PTILE_CASE(12, 8) PTILE_CASE(12, 6) PTILE_CASE(8, 8) PTILE_CASE(8, 6)
+#undef PTILE_CASE
+          SS2_LAUNCH_CHECK(ctx);
+          return SS2_OK;
+        }
+      }
       dim3 tgrid(cdiv(P.Wo, TL_W), cdiv(P.Ho, TL_H), nframes);
 #define TILE_CASE(SXV, SYV)                                                                                     \
       if (cfg.SX == SXV && cfg.SY == SYV) {                                                                     \

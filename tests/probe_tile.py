@@ -48,14 +48,14 @@ def main():
         m2 = meshes(N, 2, kw["shift"], kw["amp"], kw.get("rot", 0.0)).cuda()
         mm = pipeline.canvas_minmax(m1, m2, H, W).cpu().tolist()
         Ho, Wo = pipeline.canvas_size(mm)
-        os.environ["SS2_TPS_TILE"] = "1"
+        os.environ["SS2_TPS_TILE"] = os.environ.get("TILE_MODE", "1")
         f_tile = pipeline.stable_frames(hr1, hr2, m1, m2, mm, tps=_lib.TPS_LATTICE)
         torch.cuda.synchronize()
         t_tile = timeit(lambda: pipeline.stable_frames(hr1, hr2, m1, m2, mm, tps=_lib.TPS_LATTICE, out=f_tile))
         os.environ["SS2_TPS_TILE"] = "0"
         f_lat = pipeline.stable_frames(hr1, hr2, m1, m2, mm, tps=_lib.TPS_LATTICE)
         t_lat = timeit(lambda: pipeline.stable_frames(hr1, hr2, m1, m2, mm, tps=_lib.TPS_LATTICE, out=f_lat))
-        os.environ["SS2_TPS_TILE"] = "1"
+        os.environ["SS2_TPS_TILE"] = os.environ.get("TILE_MODE", "1")
         d = (f_tile - f_lat).abs()
         print("%-13s canvas %dx%d  tile vs lattice: max %.3e  mean %.3e  frac>1e-3 %.2e | ms/frame tile %.4f lattice %.4f"
               % (name, Ho, Wo, float(d.max()), float(d.mean()), float((d > 1e-3).float().mean()), t_tile / N, t_lat / N))

@@ -311,9 +311,10 @@ def test_fullsize_frame_vs_oracle_and_arbiter(tps):
             assert e_got.mean() < 1.2 * e_ref.mean() + 2e-5
     # ---- the same check through the FUSED kernel (the production resampler evaluates the field in tile-local
     # coordinates): view v carries the coordinate ramp, the other view is black, so fused = a*a/(a+1e-6) ~ a
-    # SS2_TPS_TILE=1 selects the opt-in TMA-staged tile kernel (lattice mode only), 0 the default direct-load kernel
+    # SS2_TPS_TILE=1 / 2 select the opt-in TMA-staged tile kernels (per-tile CTAs / persistent warp-specialised;
+    # lattice mode only), 0 the default direct-load kernel
     zero = torch.zeros_like(ramp)
-    for tile in (("0", "1") if tps == "lattice" else ("0",)):
+    for tile in (("0", "1", "2") if tps == "lattice" else ("0",)):
         os.environ["SS2_TPS_TILE"] = tile
         try:
             for v, M in enumerate((M1, M2)):
@@ -330,7 +331,7 @@ def test_fullsize_frame_vs_oracle_and_arbiter(tps):
                           % (v, tps, tile, e_got.max(), e_got.mean(), e_ref.max(), e_ref.mean()))
                     assert e_got.max() < 1.5 * e_ref.max() + 2e-4
                     assert e_got.mean() < 1.2 * e_ref.mean() + 2e-5
-            if tile == "1":
+            if tile != "0":
                 # the staged kernel against the oracle frame, same bounds as the default kernel below
                 f_t = pipeline.stable_frames(hr1.cuda(), hr2.cuda(), m1, m2, mm, tps=mode)[0]
                 dt = (f_t.cpu() - fused_ref).abs().numpy()
