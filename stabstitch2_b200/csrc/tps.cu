@@ -1292,7 +1292,8 @@ tps_warp_tile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_cons
 
 __device__ __forceinline__ void pt_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
-  while (!ok) {
+  for (int spin = 0; !ok; ++spin) {
+    if (spin > 2) __nanosleep(64);  // a spinning warp would take issue slots from the warps it waits for
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -1323,12 +1324,15 @@ tps_warp_ptile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_con
   __shared__ __align__(16) float2 s_ysm[2][PT_H][NCOL][V];
   __shared__ int s_cnt[2][2];
   __shared__ int s_r0[2][V][2];
+  __shared__ int s_tile[2][4];  // frame, bx, by of the slot's tile (decoded once, by the geometry warp)
   __shared__ TileGeo s_geo[2][V];
   __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int W = P.W, H = P.H;
   const unsigned FULL = 0xffffffffu;
-  const int t_begin = (int)((long long)blockIdx.x * total / gridDim.x), t_end = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
+  // tile t = blockIdx.x + i * gridDim.x: at any time the CTAs cover ~gridDim.x consecutive tiles (a few strips of ONE
+  // frame), so overlapping source boxes of neighbouring tiles meet in L2 instead of being re-read from HBM
+  const int t_begin = blockIdx.x, t_end = total, t_step = gridDim.x;
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
@@ -1342,12 +1346,13 @@ tps_warp_ptile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_con
   if (wid >= PT_CWARPS) {
     // ================= producers =================
     const int role = wid - PT_CWARPS;  // 0: box geometry + TMA issue, 1: near list, 2..: y contraction
-    for (int t = t_begin, i = 0; t < t_end; ++t, ++i) {
+    for (int t = t_begin, i = 0; t < t_end; t += t_step, ++i) {
       const int slot = i & 1;
       const int by = t % nty, bx = (t / nty) % ntx, n = t / (nty * ntx);
       const int col0 = bx * PT_W, row0 = by * PT_H;
       const int jx0 = col0 / SX;
       if (i >= 2) pt_wait(&s_empty[slot], ((i >> 1) - 1) & 1);
+      if (role == 0 && lane == 0) { s_tile[slot][0] = n; s_tile[slot][1] = bx; s_tile[slot][2] = by; }
       // predictor and R0 = floor(predictor at the tile origin): both producers need them
       float pr = 0.f;
       if (lane < V * 6) pr = P.aux[(size_t)(n * V + lane / 6) * 8 + lane % 6];
@@ -1514,9 +1519,10 @@ tps_warp_ptile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_con
   const unsigned oplane = (unsigned)(P.Ho * P.Wo);
   u64 lxp[LAT_TAPS] = {0, 0, 0, 0, 0, 0};
   int prev_bx = -1;
-  for (int t = t_begin, i = 0; t < t_end; ++t, ++i) {
+  for (int t = t_begin, i = 0; t < t_end; t += t_step, ++i) {
     const int slot = i & 1;
-    const int by = t % nty, bx = (t / nty) % ntx, n = t / (nty * ntx);
+    pt_wait(&s_full[slot], (i >> 1) & 1);
+    const int n = s_tile[slot][0], bx = s_tile[slot][1], by = s_tile[slot][2];
     const int col0 = bx * PT_W, row0 = by * PT_H;
     const int jx0 = col0 / SX;
     const int col = min(col0 + colt, P.Wo - 1);
@@ -1534,7 +1540,6 @@ tps_warp_ptile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_con
     const float* imgv[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) imgv[v] = P.img[v] + (size_t)n * C * H * W;
-    pt_wait(&s_full[slot], (i >> 1) & 1);
     const int n_all = s_cnt[slot][0], n0 = s_cnt[slot][1];
     const float4* near_list = s_near[slot];
     int r0x[V], r0y[V], g_lox[V], g_wxn[V], g_loy[V], g_wyn[V];
