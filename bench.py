@@ -316,10 +316,20 @@ def run_native(args):
         return
 
     peak, peak_src = measured_peaks()
+    # DRAM traffic of the same launch from the committed `ncu --set full` capture (a profiler figure cannot be taken
+    # during a timed run); only reported when the capture was made on this exact configuration
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "warp_kernel_traffic.json")))
+        if (tj["height"], tj["width"], tj["frames_per_launch"], list(tj["canvas"])) == (H, W, F, [Ho, Wo]):
+            traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+    except Exception:
+        traffic = None
     achieved = (warp_bytes / warp_n) / (warp_ms / warp_n * 1e-3) / 1e9 if warp_n else None
     roofline = {"bound": "hbm", "kernel": "tps_warp_blend (fused TPS resample + AVERAGE blend)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None, "traffic": None,
+                "frac": achieved / peak if achieved else None, "traffic": traffic,
+                "traffic_source": "profiles/warp_kernel_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch)" if traffic else None,
                 "algorithmic_bytes_per_launch": warp_bytes / warp_n if warp_n else None,
                 "avg_launch_ms": warp_ms / warp_n if warp_n else None, "launches_timed": warp_n,
                 "share_of_step": warp_ms / ms if ms else None}
