@@ -208,7 +208,7 @@ conv_igemm_kernel(ConvParams P) {
 template <int M>
 __global__ void __launch_bounds__(256)
 linear_smallm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int Mreal,
-                     int K, int CoutP, int Cout, int relu, float* __restrict__ out) {
+                     int K, int CoutP, int Cout, int relu, float* __restrict__ out, int kper, float* __restrict__ part) {
   __shared__ __align__(16) float xs[M][FC_KC];
   __shared__ float red[8][M][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -216,8 +216,10 @@ linear_smallm_kernel(const float* __restrict__ x, const float* __restrict__ w, c
   float acc[M];
 #pragma unroll
   for (int m = 0; m < M; ++m) acc[m] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += FC_KC) {
-    const int kc = min(FC_KC, K - k0);
+  // split K: blockIdx.y owns k in [kbeg, kend) and writes raw partial sums (bias / ReLU in linear_reduce_kernel)
+  const int kbeg = blockIdx.y * kper, kend = min(K, kbeg + kper);
+  for (int k0 = kbeg; k0 < kend; k0 += FC_KC) {
+    const int kc = min(FC_KC, kend - k0);
     __syncthreads();
     for (int e = threadIdx.x; e < M * FC_KC; e += 256) {
       const int m = e / FC_KC, k = e % FC_KC;
@@ -245,25 +247,61 @@ linear_smallm_kernel(const float* __restrict__ x, const float* __restrict__ w, c
       float v = 0.f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) v += red[q][m][c];
-      if (bias) v += bias[col];
-      if (relu) v = fmaxf(v, 0.f);
-      out[(size_t)m * Cout + col] = v;
+      if (part) {
+        part[((size_t)blockIdx.y * M + m) * CoutP + col] = v;
+      } else {
+        if (bias) v += bias[col];
+        if (relu) v = fmaxf(v, 0.f);
+        out[(size_t)m * Cout + col] = v;
+      }
     }
   }
 }
 
+// sums the K-split partials in split order (deterministic), then bias and ReLU
+__global__ void linear_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, int nsplit, int Mpad,
+                                     int Mreal, int CoutP, int Cout, int relu, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Mreal * Cout) return;
+  const int m = i / Cout, col = i - m * Cout;
+  float v = 0.f;
+  for (int s = 0; s < nsplit; ++s) v += part[((size_t)s * Mpad + m) * CoutP + col];
+  if (bias) v += bias[col];
+  if (relu) v = fmaxf(v, 0.f);
+  out[i] = v;
+}
+
 static bool linear_smallm_try(ss2_ctx* ctx, const ConvLayer& L, const float* x, int M, float* out, int relu, cudaStream_t st) {
   const int K = L.CinP;
-  const dim3 grid(L.CoutP / 32);
-#define FC_CASE(MM)                                                                                       \
-  if (M <= MM) {                                                                                          \
-    linear_smallm_kernel<MM><<<grid, 256, 0, st>>>(x, L.w, L.bias, M, K, L.CoutP, L.Cout, relu, out);     \
-    return true;                                                                                          \
+  if (M > 32) return false;
+  // few output-column CTAs (Cout / 32): split K so that the weight matrix streams through ~one wave of CTAs
+  const int ncol = L.CoutP / 32;
+  int nsplit = 1;
+  if (ncol < 96 && K >= 4 * FC_KC) {
+    nsplit = (148 + ncol - 1) / ncol;
+    const int maxsplit = K / (2 * FC_KC);
+    if (nsplit > maxsplit) nsplit = maxsplit;
+    if (nsplit > 32) nsplit = 32;
+    if (nsplit < 1) nsplit = 1;
   }
+  int kper = ((K + nsplit - 1) / nsplit + FC_KC - 1) / FC_KC * FC_KC;
+  nsplit = (K + kper - 1) / kper;
+  const int Mpad = M <= 4 ? 4 : M <= 8 ? 8 : M <= 16 ? 16 : 32;
+  float* part = nullptr;
+  if (nsplit > 1) {
+    part = arena_alloc<float>(ctx, (size_t)nsplit * Mpad * L.CoutP);
+    if (!part) { nsplit = 1; kper = K; }
+  }
+  const dim3 grid(ncol, nsplit);
+#define FC_CASE(MM)                                                                                                    \
+  if (Mpad == MM) linear_smallm_kernel<MM><<<grid, 256, 0, st>>>(x, L.w, L.bias, M, K, L.CoutP, L.Cout, relu, out, kper, part);
   FC_CASE(4) FC_CASE(8) FC_CASE(16) FC_CASE(32)
 #undef FC_CASE
-  (void)ctx;
-  return false;
+  if (part) {
+    ctx->launches++;
+    linear_reduce_kernel<<<cdiv(M * L.Cout, 256), 256, 0, st>>>(part, L.bias, nsplit, Mpad, M, L.CoutP, L.Cout, relu, out);
+  }
+  return true;
 }
 
 int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D, int H, int W, const ActRef& out,

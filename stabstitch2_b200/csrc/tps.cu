@@ -21,11 +21,12 @@
 // ------------------------------------------------------------------------------------------
 #define SOLVE_THREADS 256
 #define AUG (SS2_NSYS + 2)
+#define AUGP (AUG + 1)  // padded row length of the shared matrix (bank spread of the column walks)
 
 __global__ void __launch_bounds__(SOLVE_THREADS)
 tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ target, float* __restrict__ Tout,
                  float* __restrict__ aux, float half_w, float half_h, float kx, float ky) {
-  __shared__ double A[SS2_NSYS][AUG];
+  __shared__ double A[SS2_NSYS][AUGP];
   __shared__ float sx[SS2_NPT], sy[SS2_NPT];
   __shared__ int piv_row;
   const int b = blockIdx.x;
@@ -92,13 +93,12 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
     }
     __syncthreads();
     const double inv = 1.0 / A[k][k];
-    // eliminate column k from every other row (columns > k only; column k is left stale)
-    const int ncol = AUG - (k + 1);
-    for (int e = tid; e < SS2_NSYS * ncol; e += SOLVE_THREADS) {
-      int r = e / ncol, c = k + 1 + e % ncol;
+    // eliminate column k from every other row (columns > k only; column k is left stale): warps walk the rows, lanes
+    // the columns (conflict-free), no integer divisions, the row factor is computed once per row
+    for (int r = tid >> 5; r < SS2_NSYS; r += SOLVE_THREADS / 32) {
       if (r != k) {
-        double f = A[r][k] * inv;
-        A[r][c] -= f * A[k][c];
+        const double f = A[r][k] * inv;
+        for (int c = k + 1 + (tid & 31); c < AUG; c += 32) A[r][c] -= f * A[k][c];
       }
     }
     __syncthreads();
