@@ -104,7 +104,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (dc_elect_one()) {
       const uint32_t b_bytes = P.b_act ? (uint32_t)(P.bTH * P.bTW) * TC_BK * 4 : (uint32_t)TC_B_BYTES;
       const uint32_t tx_bytes = (uint32_t)NOPER * ((uint32_t)rows * TC_BK * 4 + b_bytes);
       const int bh0 = blockIdx.y * P.bTH;
@@ -129,23 +129,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer (one elected thread; descriptors advanced with 32-bit adds, see tc_common.cuh) =====
+    if (dc_elect_one()) {
       const uint32_t idesc = tc_idesc();
       for (int it = 0; it < niter; ++it) {
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint32_t b_hi = a_hi + NOPER * TC_A_BYTES;
+        const uint32_t a_hi = dc_desc_lo(smem_u32(smem + (size_t)s * STAGE_BYTES));
+        const uint32_t b_hi = a_hi + ((NOPER * TC_A_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint64_t da = umma_desc_sw128(a_hi + k * 32), db = umma_desc_sw128(b_hi + k * 32);
-          umma_tf32(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          dc_mma(tmem_base, a_hi + 2 * k, b_hi + 2 * k, DC_DESC_HI, idesc, (it > 0 || k > 0) ? 1u : 0u);
           if (NPASS == 3) {
-            const uint64_t dal = umma_desc_sw128(a_hi + TC_A_BYTES + k * 32), dbl = umma_desc_sw128(b_hi + TC_B_BYTES + k * 32);
-            umma_tf32(tmem_base, dal, db, idesc, 1u);
-            umma_tf32(tmem_base, da, dbl, idesc, 1u);
+            dc_mma(tmem_base, a_hi + (TC_A_BYTES >> 4) + 2 * k, b_hi + 2 * k, DC_DESC_HI, idesc, 1u);
+            dc_mma(tmem_base, a_hi + 2 * k, b_hi + (TC_B_BYTES >> 4) + 2 * k, DC_DESC_HI, idesc, 1u);
           }
         }
         umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above have read it
