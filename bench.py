@@ -298,6 +298,8 @@ def run_native(args):
         # two chunks in flight: the D2H of chunk k overlaps the H2D + networks of chunk k+1; every
         # chunk's inputs are copied from pinned host memory and its frames land in pinned host memory
         for i in range(args.steps):
+            if i + 1 < args.steps:  # the next chunk's upload runs underneath this chunk's networks
+                pipeline.stitch_stream_host_prefetch((i + 1) & 1, *pins)
             pipeline.stitch_stream_host_async(s, t, m, i & 1, *pins, outs[i & 1], tps=tps)
         pipeline.stitch_stream_host_wait(0)
         pipeline.stitch_stream_host_wait(1)
@@ -311,7 +313,7 @@ def run_native(args):
                "h2d_bytes_per_step": int(sum(p.numel() for p in pins) * 4),
                "d2h_bytes_per_step": int(F * 3 * eh * ew * 4 + 16),
                "note": "per GPU; the whole stream is processed independently per rank in this leg" if world > 1 else
-                       "ss2_stitch_stream_host_async/_wait through pinned host buffers, two chunks in flight"}
+                       "ss2_stitch_stream_host_prefetch/_async/_wait through pinned host buffers: every chunk is copied H2D and its frames D2H inside the timed region, two chunks in flight"}
 
     if rank != 0:
         if world > 1:

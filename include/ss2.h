@@ -222,6 +222,11 @@ int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float* h_lr1, con
                                  int64_t out_capacity, int* out_h, int* out_w, float* h_smooth_mesh1,
                                  float* h_smooth_mesh2);
 int ss2_stitch_stream_host_wait(ss2_ctx* ctx, int slot);
+/* Starts the host -> device copies of the chunk that the NEXT ss2_stitch_stream_host_async on `slot` will process
+ * (same pointers and sizes) and returns at once: issued before the _async of the chunk in flight, the upload runs
+ * underneath that chunk's networks.  The host buffers must stay valid and unchanged until that _async returns. */
+int ss2_stitch_stream_host_prefetch(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2,
+                                    const float* h_hr1, const float* h_hr2, int n, int H, int W);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,7 @@ SIGNATURES = {
     "ss2_stitch_stream_host_async": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64,
                                           ctypes.POINTER(_i), ctypes.POINTER(_i), _vp, _vp]),
     "ss2_stitch_stream_host_wait": (_i, [_vp, _i]),
+    "ss2_stitch_stream_host_prefetch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i]),
 }
 
 _lib = None

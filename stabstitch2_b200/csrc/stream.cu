@@ -79,19 +79,72 @@ extern "C" int ss2_stream_meshes(ss2_ctx* ctx, const float* d_lr1, const float* 
 
 // per-slot streams / events of the host-buffer pipeline
 struct HostSlot {
-  cudaStream_t s_copy = nullptr;
+  cudaStream_t s_copy = nullptr;   // host -> device (inputs)
+  cudaStream_t s_d2h = nullptr;    // device -> host (frames): a stream of its own, so that the NEXT chunk's inputs
+                                   // are not queued behind this chunk's output copy
   cudaEvent_t ev_hr = nullptr, ev_chunk[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_done = nullptr;
-  bool busy = false;
+  cudaEvent_t ev_lr = nullptr;     // network inputs on the device
+  cudaEvent_t ev_warp = nullptr;   // resampling of the slot's chunk done: its device input buffers may be overwritten
+  bool busy = false, warped = false;
+  // inputs already on their way (ss2_stitch_stream_host_prefetch)
+  const float* pre[4] = {nullptr, nullptr, nullptr, nullptr};
+  int pre_n = 0, pre_h = 0, pre_w = 0;
 };
 static HostSlot g_slots[8][HOST_SLOTS];  // [device][slot]
 
 static int slot_init(ss2_ctx* ctx, HostSlot& h) {
   if (h.s_copy) return SS2_OK;
   SS2_CUDA(ctx, cudaStreamCreateWithFlags(&h.s_copy, cudaStreamNonBlocking));
+  SS2_CUDA(ctx, cudaStreamCreateWithFlags(&h.s_d2h, cudaStreamNonBlocking));
   SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_hr, cudaEventDisableTiming));
+  SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_lr, cudaEventDisableTiming));
+  SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_warp, cudaEventDisableTiming));
   SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_done, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_chunk[i], cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_d2h[i], cudaEventDisableTiming));
+  return SS2_OK;
+}
+
+// device input buffers of a slot + the H2D copies (network inputs first, then the much larger hr frames)
+static int slot_upload(ss2_ctx* ctx, HostSlot& hs, int slot, const float* h_lr1, const float* h_lr2, const float* h_hr1,
+                       const float* h_hr2, int n, int H, int W, float** lr1, float** lr2, float** hr1, float** hr2,
+                       bool enqueue) {
+  const size_t lrb = (size_t)n * 3 * 360 * 480 * sizeof(float), hrb = (size_t)n * 3 * H * W * sizeof(float);
+  char nm[32];
+  auto name = [&](const char* base) { snprintf(nm, sizeof(nm), "%s.%d", base, slot); return nm; };
+  SS2_TRY(named_buf(ctx, name("lr1"), lrb, lr1));
+  SS2_TRY(named_buf(ctx, name("lr2"), lrb, lr2));
+  SS2_TRY(named_buf(ctx, name("hr1"), hrb, hr1));
+  SS2_TRY(named_buf(ctx, name("hr2"), hrb, hr2));
+  if (!enqueue) return SS2_OK;
+  cudaStream_t sx = hs.s_copy;
+  if (hs.warped) SS2_CUDA(ctx, cudaStreamWaitEvent(sx, hs.ev_warp, 0));  // the previous chunk of this slot still reads them
+  SS2_CUDA(ctx, cudaMemcpyAsync(*lr1, h_lr1, lrb, cudaMemcpyHostToDevice, sx));
+  SS2_CUDA(ctx, cudaMemcpyAsync(*lr2, h_lr2, lrb, cudaMemcpyHostToDevice, sx));
+  SS2_CUDA(ctx, cudaEventRecord(hs.ev_lr, sx));
+  SS2_CUDA(ctx, cudaMemcpyAsync(*hr1, h_hr1, hrb, cudaMemcpyHostToDevice, sx));
+  SS2_CUDA(ctx, cudaMemcpyAsync(*hr2, h_hr2, hrb, cudaMemcpyHostToDevice, sx));
+  SS2_CUDA(ctx, cudaEventRecord(hs.ev_hr, sx));
+  return SS2_OK;
+}
+
+// Starts the host -> device copies of a slot's NEXT chunk and returns at once; the following
+// ss2_stitch_stream_host_async on that slot with the same pointers and sizes uses them instead of copying again.
+// Call it before the _async of the chunk in flight: the upload then runs underneath that chunk's networks
+// instead of after the host has waited for them (the canvas size is a data-dependent host read).
+extern "C" int ss2_stitch_stream_host_prefetch(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2,
+                                               const float* h_hr1, const float* h_hr2, int n, int H, int W) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (slot < 0 || slot >= HOST_SLOTS || ctx->device < 0 || ctx->device >= 8) return ss2_fail(ctx, SS2_ERR_INVALID, "bad slot");
+  if (!h_lr1 || !h_lr2 || !h_hr1 || !h_hr2 || n < SS2_WINDOW || H <= 0 || W <= 0)
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stitch_stream_host_prefetch: bad arguments");
+  SS2_CUDA(ctx, cudaSetDevice(ctx->device));
+  HostSlot& hs = g_slots[ctx->device][slot];
+  SS2_TRY(slot_init(ctx, hs));
+  float *lr1, *lr2, *hr1, *hr2;
+  SS2_TRY(slot_upload(ctx, hs, slot, h_lr1, h_lr2, h_hr1, h_hr2, n, H, W, &lr1, &lr2, &hr1, &hr2, true));
+  hs.pre[0] = h_lr1; hs.pre[1] = h_lr2; hs.pre[2] = h_hr1; hs.pre[3] = h_hr2;
+  hs.pre_n = n; hs.pre_h = H; hs.pre_w = W;
   return SS2_OK;
 }
 
@@ -118,27 +171,19 @@ extern "C" int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float*
   SS2_TRY(slot_init(ctx, hs));
   SS2_TRY(ss2_stitch_stream_host_wait(ctx, slot));  // the slot's buffers must be free
   if (!ctx->s_compute) SS2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
-  cudaStream_t sc = ctx->s_compute, sx = hs.s_copy;
-  const size_t lrb = (size_t)n * 3 * 360 * 480 * sizeof(float), hrb = (size_t)n * 3 * H * W * sizeof(float);
+  cudaStream_t sc = ctx->s_compute, sx = hs.s_d2h;
   const size_t mb = (size_t)n * SS2_NPT * 2 * sizeof(float);
   float *lr1, *lr2, *hr1, *hr2, *small;
   char nm[32];
   auto name = [&](const char* base) { snprintf(nm, sizeof(nm), "%s.%d", base, slot); return nm; };
-  SS2_TRY(named_buf(ctx, name("lr1"), lrb, &lr1));
-  SS2_TRY(named_buf(ctx, name("lr2"), lrb, &lr2));
-  SS2_TRY(named_buf(ctx, name("hr1"), hrb, &hr1));
-  SS2_TRY(named_buf(ctx, name("hr2"), hrb, &hr2));
+  const bool prefetched = hs.pre[0] == h_lr1 && hs.pre[1] == h_lr2 && hs.pre[2] == h_hr1 && hs.pre[3] == h_hr2 &&
+                          hs.pre_n == n && hs.pre_h == H && hs.pre_w == W;
+  SS2_TRY(slot_upload(ctx, hs, slot, h_lr1, h_lr2, h_hr1, h_hr2, n, H, W, &lr1, &lr2, &hr1, &hr2, !prefetched));
+  hs.pre[0] = hs.pre[1] = hs.pre[2] = hs.pre[3] = nullptr;
   SS2_TRY(named_buf(ctx, name("small"), 2 * mb + 64, &small));
   float *S1 = small, *S2 = small + (size_t)n * SS2_NPT * 2, *mm = S2 + (size_t)n * SS2_NPT * 2;
-  // the network inputs go first on the slot's copy stream, then the (much larger) hr frames;
-  // the compute stream only waits for the former before it starts the networks
-  SS2_CUDA(ctx, cudaMemcpyAsync(lr1, h_lr1, lrb, cudaMemcpyHostToDevice, sx));
-  SS2_CUDA(ctx, cudaMemcpyAsync(lr2, h_lr2, lrb, cudaMemcpyHostToDevice, sx));
-  SS2_CUDA(ctx, cudaEventRecord(hs.ev_hr, sx));
-  SS2_CUDA(ctx, cudaStreamWaitEvent(sc, hs.ev_hr, 0));
-  SS2_CUDA(ctx, cudaMemcpyAsync(hr1, h_hr1, hrb, cudaMemcpyHostToDevice, sx));
-  SS2_CUDA(ctx, cudaMemcpyAsync(hr2, h_hr2, hrb, cudaMemcpyHostToDevice, sx));
-  SS2_CUDA(ctx, cudaEventRecord(hs.ev_hr, sx));
+  // the compute stream only waits for the network inputs before it starts the networks
+  SS2_CUDA(ctx, cudaStreamWaitEvent(sc, hs.ev_lr, 0));
   SS2_TRY(ss2_stream_meshes(ctx, lr1, lr2, n, S1, S2, nullptr, nullptr, nullptr, nullptr, sc));
   SS2_TRY(canvas_minmax_launch(ctx, S1, S2, n, H, W, mm, sc));
   float h_mm[4];
@@ -167,6 +212,8 @@ extern "C" int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float*
     SS2_CUDA(ctx, cudaStreamWaitEvent(sx, hs.ev_chunk[0], 0));
     SS2_CUDA(ctx, cudaMemcpyAsync(h_out + (size_t)f0 * fpx, dst, (size_t)nf * fpx * sizeof(float), cudaMemcpyDeviceToHost, sx));
   }
+  SS2_CUDA(ctx, cudaEventRecord(hs.ev_warp, sc));
+  hs.warped = true;
   SS2_CUDA(ctx, cudaEventRecord(hs.ev_done, sx));
   hs.busy = true;
   return SS2_OK;

@@ -171,6 +171,18 @@ def stitch_stream_host_async(spatial_net, temporal_net, smooth_net, slot, lr1, l
     return ho.value, wo.value
 
 
+def stitch_stream_host_prefetch(slot, lr1, lr2, hr1, hr2):
+    """ss2_stitch_stream_host_prefetch: start the H2D copies of the chunk the next stitch_stream_host_async on `slot`
+    will process (same host tensors); returns immediately."""
+    ctx = _lib.context()
+    for t in (lr1, lr2, hr1, hr2):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("stitch_stream_host takes contiguous fp32 HOST tensors")
+    n, _, H, W = hr1.shape
+    ctx.check(ctx.lib.ss2_stitch_stream_host_prefetch(ctx.handle, int(slot), _lib.ptr(lr1), _lib.ptr(lr2), _lib.ptr(hr1),
+                                                      _lib.ptr(hr2), n, H, W))
+
+
 def stitch_stream_host_wait(slot):
     ctx = _lib.context()
     ctx.check(ctx.lib.ss2_stitch_stream_host_wait(ctx.handle, int(slot)))
