@@ -240,6 +240,55 @@ def test_stream_host_call_matches_device_path(nets, stream_inputs):
     assert maxdiff(out.view_as(fused), fused) == 0.0
 
 
+def test_stream_host_prefetch_pipeline(nets, stream_inputs):
+    """two chunks in flight with the next chunk's upload prefetched: every chunk bit-identical to the blocking call,
+    also when the prefetched buffers differ from the ones finally submitted (the copy is then repeated)"""
+    from stabstitch2_b200 import pipeline
+    s, t, m = nets
+    hr, lr = stream_inputs
+    ins = [torch.cat(x, 0).contiguous().pin_memory() for x in (lr[0], lr[1], hr[0], hr[1])]
+    ins_b = [x.flip(0).contiguous().pin_memory() for x in ins]  # a second, different chunk
+    fused, _, _ = pipeline.stitch_stream(s, t, m, *[x.cuda() for x in ins])
+    fused_b, _, _ = pipeline.stitch_stream(s, t, m, *[x.cuda() for x in ins_b])
+    outs = [torch.empty(max(fused.numel(), fused_b.numel()) + 1024).pin_memory() for _ in range(2)]
+    chunks = [ins, ins_b, ins, ins_b]
+    sizes = []
+    for i, c in enumerate(chunks):
+        if i + 1 < len(chunks):
+            pipeline.stitch_stream_host_prefetch((i + 1) & 1, *chunks[i + 1])
+        if i >= 2:  # results of the chunk that used this slot two steps ago
+            pipeline.stitch_stream_host_wait(i & 1)
+            ref = fused if (i - 2) % 2 == 0 else fused_b
+            assert maxdiff(outs[i & 1][:ref.numel()].view_as(ref), ref) == 0.0
+        sizes.append(pipeline.stitch_stream_host_async(s, t, m, i & 1, *c, outs[i & 1]))
+    for slot, ref in ((0, fused), (1, fused_b)):
+        pipeline.stitch_stream_host_wait(slot)
+        assert maxdiff(outs[slot][:ref.numel()].view_as(ref), ref) == 0.0
+    assert sizes[0] == tuple(fused.shape[2:]) and sizes[1] == tuple(fused_b.shape[2:])
+    # prefetch one chunk, submit another: the stale prefetch must not be used
+    pipeline.stitch_stream_host_prefetch(0, *ins_b)
+    pipeline.stitch_stream_host_async(s, t, m, 0, *ins, outs[0])
+    pipeline.stitch_stream_host_wait(0)
+    assert maxdiff(outs[0][:fused.numel()].view_as(fused), fused) == 0.0
+
+
+def test_three_view_and_prefetch_errors():
+    from stabstitch2_b200 import _lib
+    ctx = _lib.context()
+    rc = ctx.lib.ss2_three_view_meshes(ctx.handle, None, None, None, None, 1, 96, 128, None, None, None, None, None)
+    assert rc == -1 and b"bad arguments" in ctx.lib.ss2_last_error(ctx.handle)
+    import ctypes
+    cv = (ctypes.c_float * 4)(0.0, 0.0, 10.0, 10.0)
+    rc = ctx.lib.ss2_three_view_frames(ctx.handle, None, None, None, None, None, None, 1, 96, 128, cv, 0, 0, None, None)
+    assert rc == -1
+    rc = ctx.lib.ss2_three_view_frames(ctx.handle, None, None, None, None, None, None, 0, 96, 128, cv, 0, 0, None, None)
+    assert rc == 0  # no frames: nothing to do
+    rc = ctx.lib.ss2_stitch_stream_host_prefetch(ctx.handle, 5, None, None, None, None, 8, 96, 128)
+    assert rc == -1
+    rc = ctx.lib.ss2_stitch_stream_host_prefetch(ctx.handle, 0, None, None, None, None, 8, 96, 128)
+    assert rc == -1 and b"bad arguments" in ctx.lib.ss2_last_error(ctx.handle)
+
+
 def test_get_stable_sqe_dropin(golden_stream, stream_inputs):
     """Reference-shaped call (lists of CPU tensors, [1,N,7,9,2] meshes) with the golden meshes:
     isolates the resampler+blend from the networks."""
