@@ -284,10 +284,27 @@ def run_native(args):
     # ---- e2e: HOST buffers through the C-ABI call, H2D + D2H inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        pins = [x.contiguous().pin_memory() for x in (lr1[halo:], lr2[halo:], hr1, hr2)]
-        # In this leg every rank stitches ITS chunk as an independent stream, so its canvas is the chunk's own (a few
-        # pixels off the sharded run's global canvas): size the host buffers with a margin, count the bytes actually moved
-        outs = [torch.empty(F * 3 * (Ho + 64) * (Wo + 64), dtype=torch.float32).pin_memory() for _ in range(2)]
+        # every rank must take the same path through this leg (it contains barriers): agree first on whether the
+        # pinned host buffers could be had everywhere
+        pins = outs = None
+        ok = 1
+        try:
+            pins = [x.contiguous().pin_memory() for x in (lr1[halo:], lr2[halo:], hr1, hr2)]
+            # In this leg every rank stitches ITS chunk as an independent stream, so its canvas is the chunk's own (a
+            # few pixels off the sharded run's global canvas): size the host buffers with a margin, count the bytes
+            # actually moved
+            outs = [torch.empty(F * 3 * (Ho + 64) * (Wo + 64), dtype=torch.float32).pin_memory() for _ in range(2)]
+        except RuntimeError as exc:
+            ok = 0
+            sys.stderr.write("rank %d: pinned host buffers unavailable (%s)\n" % (rank, str(exc).splitlines()[0]))
+        if world > 1:
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if not ok:
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "note": "pinned host buffers could not be allocated on every rank; leg skipped"}
+    if not args.no_e2e and e2e is None:
         eh, ew = Ho, Wo
         for i in range(max(2, min(args.warmup, 3))):
             eh, ew = pipeline.stitch_stream_host_async(s, t, m, i & 1, *pins, outs[i & 1], tps=tps)
