@@ -846,24 +846,27 @@ tps_warp_lattice_kernel(WarpParams P) {
 }
 
 // ------------------------------------------------------------------------------------------
-// TILE resampler: the production kernel of the fused NORMAL resample + AVERAGE blend.
+// TILE resampler (opt-in, SS2_TPS_TILE=1): the fused NORMAL resample + AVERAGE blend with TMA-staged source tiles.
+// Measured slower than tps_warp_lattice_kernel in round 1, kept as the base of the persistent variant.
 //
 // Same field evaluation as tps_warp_lattice_kernel (quintic lattice interpolation + exact near
 // field), but the bilinear taps never touch global memory from a thread:
-//   * a CTA owns a TL_W x TL_H tile of the canvas.  From the lattice nodes bracketing the tile it
-//     bounds the tile's source footprint per view and has the TMA unit copy that box of the
-//     three colour planes ([3][TL_BH][TL_BW] floats per view, 8-row boxes issued by the lanes of
-//     warp 0, out-of-image elements zero-filled) into shared memory while the CTA y-contracts
-//     the lattice for its rows;
-//   * the affine predictor and the box origin are folded into the y-contracted node values
+//   * a CTA owns a TL_W x TL_H tile of the canvas.  The last warp estimates the tile's source footprint per view
+//     (predictor + residual of the nearest lattice node at the tile's corners and edge midpoints) and has the TMA
+//     unit copy that box of the three colour planes ([3][TL_BH][TL_BW] floats per view; one box per plane, of
+//     TL_BH0, TL_BH1 or TL_BH rows; start column rounded to 16 bytes - an unaligned innermost start is an
+//     illegal instruction on sm_100; out-of-image elements zero-filled) into shared memory while the CTA
+//     y-contracts the lattice for its rows;
+//   * the affine predictor and an integer reference origin R0 are folded into the y-contracted node values
 //     (Lagrange weights sum to one and reproduce linear functions), so the x contraction
-//     (6 LDS.128 + 12 packed FFMA2) directly yields box-local source coordinates of both views;
+//     (6 LDS.128 + 12 packed FFMA2) directly yields R0-relative source coordinates of both views; the box origin
+//     relative to R0 is folded into the per-view shared-memory base address;
 //   * taps are LDS with compile-time offsets from one per-view index; tap pairs and weight pairs
 //     go through packed fp32 FMAs (fma.rn.f32x2), as does the blend.
 // A sample whose taps are not inside the staged box although it is inside the image (footprint
-// larger than the box: scale > 1.15, strong shear, or a near-field bump beyond the margin)
-// takes the per-warp slow path with global loads, so the result never depends on the bound.
-// Three CTAs (3 x 66 KB) are resident per SM; one's TMA wait overlaps the others' sampling.
+// larger than the box: scale > ~1.1, strong shear, or a near-field bump beyond the margin)
+// takes the per-warp slow path with global loads, so the result never depends on the estimate.
+// Two CTAs (2 x 100 KB) are resident per SM; one's TMA wait overlaps the other's sampling.
 // ------------------------------------------------------------------------------------------
 #define TL_W 64
 #ifndef TL_RPT
