@@ -119,3 +119,21 @@ def test_three_view(golden_threeview):
             d = np.abs(f.numpy() - g["frames"][k])
             assert (d > 0.05).mean() < 1e-3, (d > 0.05).mean()
             assert np.median(d) < 1e-4
+
+
+def test_host_edges_against_cv2():
+    """the uint8 front end of the reference (cv2.resize INTER_LINEAR on uint8, test_online_tra.py:259) restated in
+    oracle/host_edges.py: bit-exact against cv2 itself for the reference's down-scaling shapes"""
+    cv2 = __import__("pytest").importorskip("cv2")
+    from oracle import host_edges as HE
+    rng = np.random.default_rng(0)
+    for (h, w) in ((720, 1280), (1080, 1920), (361, 483), (480, 640)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(HE.resize_u8_linear(img, 480, 360), cv2.resize(img, (480, 360))), (h, w)
+    img = rng.integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+    hr, lr = HE.load_frame(img)
+    ref_lr = np.transpose(cv2.resize(img, (480, 360)).astype(np.float32), [2, 0, 1]) / 127.5 - 1.0
+    assert hr.shape == (1, 3, 720, 1280) and np.array_equal(hr[0, :, 5, 7], img[5, 7].astype(np.float32))
+    assert np.array_equal(lr[0], ref_lr.astype(np.float32))
+    f = np.array([[[-0.05, 0.0, 0.99]], [[1.5, 254.99, 255.0]]], np.float32)
+    assert np.array_equal(HE.to_video_frame(f), f.astype(np.uint8))
