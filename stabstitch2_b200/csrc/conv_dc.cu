@@ -293,7 +293,8 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   } else {
     mA_lo = mA_hi; mB_lo = mB_hi;
   }
-  static size_t attr_smem[4] = {0, 0, 0, 0};
+  static size_t attr_smem_dev[16][4] = {{0}};  // per device: function attributes live in the device's context
+  size_t* attr_smem = attr_smem_dev[ctx->device & 15];
   const int variant = (BN == 128 ? 2 : 0) + (MT == 2 ? 1 : 0);
   if (smem > attr_smem[variant]) {
     const void* fn = variant == 0 ? (const void*)conv_dc_kernel<64, 1> : variant == 1 ? (const void*)conv_dc_kernel<64, 2>

@@ -308,13 +308,15 @@ int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   if (npass == 3) {
     constexpr int STAGES = TC_STAGES3;
     const size_t smem = (size_t)STAGES * 2 * (TC_A_BYTES + TC_B_BYTES) + 1024;
-    static bool attr3 = false;
+    static bool attr3_dev[16] = {false};  // per device: function attributes live in the device's context
+    bool& attr3 = attr3_dev[ctx->device & 15];
     if (!attr3) { SS2_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<3, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr3 = true; }
     conv_tc_kernel<3, STAGES><<<grid, TC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
   } else {
     constexpr int STAGES = TC_STAGES1;
     const size_t smem = (size_t)STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024;
-    static bool attr1 = false;
+    static bool attr1_dev[16] = {false};
+    bool& attr1 = attr1_dev[ctx->device & 15];
     if (!attr1) { SS2_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<1, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr1 = true; }
     conv_tc_kernel<1, STAGES><<<grid, TC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
   }

@@ -154,7 +154,8 @@ int cost_volume_launch(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B
     const int halo = CVT + 2 * sr;
     const size_t smem = (size_t)(CVT * CVT + halo * halo) * CV_LD * sizeof(float);
     dim3 g(cdiv(W, CVT), cdiv(H, CVT), B);
-    static bool attr = false;
+    static bool attr_dev[16] = {false};  // per device: function attributes live in the device's context
+    bool& attr = attr_dev[ctx->device & 15];
     if (!attr) {
       SS2_CUDA(ctx, cudaFuncSetAttribute(cost_volume_tiled_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       SS2_CUDA(ctx, cudaFuncSetAttribute(cost_volume_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));

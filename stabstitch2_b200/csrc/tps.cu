@@ -1793,7 +1793,8 @@ static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, flo
         if (total < 2000000000LL) {
 #define PTILE_CASE(SXV, SYV)                                                                                    \
           if (cfg.SX == SXV && cfg.SY == SYV) {                                                                 \
-            static bool attr = false;                                                                           \
+            static bool attr_dev[16] = {false};                                                                 \
+            bool& attr = attr_dev[ctx->device & 15];                                                            \
             if (!attr) {                                                                                        \
               SS2_CUDA(ctx, cudaFuncSetAttribute(tps_warp_ptile_kernel<SXV, SYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES)); \
               attr = true;                                                                                      \
@@ -1809,7 +1810,8 @@ static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, flo
       dim3 tgrid(cdiv(P.Wo, TL_W), cdiv(P.Ho, TL_H), nframes);
 #define TILE_CASE(SXV, SYV)                                                                                     \
       if (cfg.SX == SXV && cfg.SY == SYV) {                                                                     \
-        static bool attr = false;                                                                               \
+        static bool attr_dev[16] = {false};                                                                     \
+        bool& attr = attr_dev[ctx->device & 15];                                                                \
         if (!attr) {                                                                                            \
           SS2_CUDA(ctx, cudaFuncSetAttribute(tps_warp_tile_kernel<SXV, SYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM_BYTES)); \
           SS2_CUDA(ctx, cudaFuncSetAttribute(tps_warp_tile_kernel<SXV, SYV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
