@@ -30,6 +30,10 @@ if ROOT not in sys.path:
 METRIC = "stitched frames/sec at 720p pair"
 UNIT = "frames/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+# the one speed the reference publishes for this path (README.md:30,32: 28.3 fps end to end on
+# one RTX 4090; the resolution is not stated, BASELINE.json labels it "720p pairs")
+PUBLISHED_FPS = 28.3
+BASELINE_NOTE = "value / 28.3 fps (reference README.md:30, 1x RTX 4090, resolution not stated; BASELINE.md section 1)"
 
 
 def parse_args():
@@ -189,7 +193,8 @@ def run_reference(args):
               "resample+blend timed on 1 frame and scaled x7" % (H, W))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / PUBLISHED_FPS if H == 720 else None,
+            "baseline_note": BASELINE_NOTE, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%dp synthetic pair stream, full Spatial+Temporal+Smooth+warp inference" % H,
                        "height": H, "width": W},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
@@ -367,7 +372,8 @@ def run_native(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
             "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": value / PUBLISHED_FPS if H == 720 else None, "baseline_note": BASELINE_NOTE,
+            "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%dp synthetic pair stream, full Spatial+Temporal+Smooth inference + fused TPS "
                                    "resample/AVERAGE blend" % H, "height": H, "width": W, "canvas": [Ho, Wo],
                        "frames_per_step_per_gpu": F, "net_input": [360, 480], "window": 7,
