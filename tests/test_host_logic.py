@@ -6,6 +6,7 @@ a world_size-2 gloo group with the oracle doing the per-rank arithmetic."""
 import os
 import re
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -198,3 +199,20 @@ def test_sharded_stream_matches_single_process_gloo():
         mm = res[r][2]
         assert abs(mm[0] - float(wmin)) < 1e-3 and abs(mm[2] - float(hmin)) < 1e-3
         assert abs((mm[1] - mm[0]) - float(ow)) < 1e-3 and abs((mm[3] - mm[2]) - float(oh)) < 1e-3
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys"""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--height", "96", "--width", "128"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    e = line["e2e"]
+    assert e["value"] == line["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    assert line["gpu_launches"] == 0 and "workload" in line["config"]
