@@ -7,7 +7,8 @@ import threading
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libss2.so")
+# SS2_LIB: another build of the same library (kernel parameter sweeps under profiles/); default the in-tree build
+LIB_PATH = os.environ.get("SS2_LIB") or os.path.join(HERE, "libss2.so")
 
 NET_SPATIAL, NET_TEMPORAL, NET_SMOOTH = 0, 1, 2
 MODE = {"NORMAL": 0, "FAST": 1}
@@ -58,7 +59,7 @@ SIGNATURES = {
 }
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()
 _contexts = {}
 
 
@@ -96,6 +97,7 @@ class Context:
         if rc != 0:
             raise SS2Error("ss2_create(device=%d) failed with %d" % (self.device, rc))
         self.handle = h
+        self.synced = {}  # NET_ID -> signature of the module whose weights are loaded (NativeNet.sync_weights)
 
     def check(self, rc):
         if rc != 0:
@@ -128,10 +130,9 @@ def context(device=None):
     if isinstance(device, torch.device):
         device = device.index if device.index is not None else torch.cuda.current_device()
     with _lock:
-        pass
-    if device not in _contexts:
-        _contexts[device] = Context(device)
-    return _contexts[device]
+        if device not in _contexts:
+            _contexts[device] = Context(device)
+        return _contexts[device]
 
 
 def dev_f32(t, device=None):

@@ -60,16 +60,31 @@ class NativeNet(nn.Module):
 
     def __init__(self):
         super().__init__()
-        self._synced_sig = None
+        self._dirty_gen = 0
 
     def _signature(self):
         return tuple((k, t.data_ptr(), t._version) for k, t in self.state_dict(keep_vars=True).items())
 
+    def mark_dirty(self):
+        """Force a re-upload on the next forward.  Needed after in-place edits through `.data`
+        (they do not bump the tensors' version counters, so _signature cannot see them)."""
+        self._dirty_gen += 1
+
+    def load_state_dict(self, *args, **kwargs):
+        self.mark_dirty()
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.mark_dirty()
+        return super()._apply(fn, *args, **kwargs)
+
     def sync_weights(self, ctx):
-        sig = (ctx.device,) + self._signature()
-        if sig != self._synced_sig:
+        # libss2 keeps ONE packed weight set per NET_ID per context: the signature of what is loaded there lives on
+        # the context and names its owner, so a second instance of the same class always triggers a reload
+        sig = (id(self), self._dirty_gen) + self._signature()
+        if ctx.synced.get(self.NET_ID) != sig:
             ctx.load_state_dict(self.NET_ID, self.state_dict())
-            self._synced_sig = sig
+            ctx.synced[self.NET_ID] = sig
 
     def init_reference_style(self):
         # spatial_network.py:261-266: kaiming-normal convs, BN weight 1 / bias 0
@@ -79,3 +94,4 @@ class NativeNet(nn.Module):
             elif isinstance(m, nn.BatchNorm2d):
                 m.weight.data.fill_(1)
                 m.bias.data.zero_()
+        self.mark_dirty()

@@ -30,6 +30,17 @@ int ss2_ensure_arena(ss2_ctx* ctx, size_t bytes) {
   return SS2_OK;
 }
 
+int ss2_workspace_enter(ss2_ctx* ctx, cudaStream_t st) {
+  if (ctx->ws_used && st != ctx->ws_stream) {
+    if (!ctx->ws_ev) SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ws_ev, cudaEventDisableTiming));
+    SS2_CUDA(ctx, cudaEventRecord(ctx->ws_ev, ctx->ws_stream));
+    SS2_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ws_ev, 0));
+  }
+  ctx->ws_stream = st;
+  ctx->ws_used = true;
+  return SS2_OK;
+}
+
 void ss2_prof_begin(ss2_ctx* ctx, int which, cudaStream_t st) {
   ProfClass& p = ctx->prof[which];
   if (!p.enabled) return;
@@ -129,7 +140,11 @@ void ss2_destroy(ss2_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  ss2_host_slots_free(ctx);
+  if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+  if (ctx->ws_ev) cudaEventDestroy(ctx->ws_ev);
   for (void* p : ctx->owned) cudaFree(p);
+  for (auto& v : ctx->owned_net) for (void* p : v) cudaFree(p);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   for (auto& kv : ctx->stream_bufs) cudaFree(kv.second.first);
   for (auto& pc : ctx->prof) for (cudaEvent_t e : pc.pool) cudaEventDestroy(e);
@@ -216,9 +231,13 @@ int ss2_tps_warp_blend_avg(ss2_ctx* ctx, const float* d_img1, const float* d_img
   if (tps != SS2_TPS_LATTICE || !tps_lattice_supported(Ho, Wo)) tps = SS2_TPS_EXACT;
   TpsScratch sc;
   SS2_TRY(tps_scratch_alloc(ctx, 2 * nframes, Ho, Wo, tps, 0, &sc, st));
+  // SS2_PROF_WARP brackets the WHOLE resampling of the chunk: TPS solves + lattice nodes + resample/blend kernel;
+  // work = algorithmic bytes (both source frames read once, the fused frame written once)
+  ss2_prof_begin(ctx, SS2_PROF_WARP, st);
   int rc = tps_solve_for_warp(ctx, d_source, d_target, 2 * nframes, H, W, Ho, Wo, mode, tps, sc, st);
   if (rc == SS2_OK)
     rc = tps_warp_blend_launch(ctx, d_img1, d_img2, d_source, sc.T, nframes, H, W, Ho, Wo, mode, tps, d_out, st, sc.aux, sc.nodes);
+  ss2_prof_end(ctx, SS2_PROF_WARP, st, (double)nframes * (2.0 * 3 * H * W + 3.0 * Ho * Wo) * 4.0);
   cudaFreeAsync(sc.base, st);
   return rc;
 }
@@ -308,6 +327,7 @@ int ss2_ccl_nhwc(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int 
   if (B < 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || (B > 0 && (!d_f1 || !d_f2 || !d_flow)))
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_ccl_nhwc: bad arguments (C must be a multiple of 4)");
   const size_t hw = (size_t)H * W, kp = (hw + 63) / 64 * 64;
+  SS2_TRY(ss2_workspace_enter(ctx, (cudaStream_t)stream));
   SS2_TRY(ss2_ensure_arena(ctx, (size_t)B * (6 * hw * C + 9 * C * kp + hw * kp) * sizeof(float) + (1 << 20)));
   ctx->arena.reset();
   return ccl_launch(ctx, d_f1, d_f2, B, H, W, C, d_flow, (cudaStream_t)stream);
@@ -367,9 +387,13 @@ int ss2_stable_frames(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, cons
   SS2_TRY(tps_scratch_alloc(ctx, 2 * n, Ho, Wo, tps, 2 * m, &sc, st));
   float *source = sc.nodes + (tps == SS2_TPS_LATTICE ? (tps_lattice_workspace_floats(2 * n, Ho, Wo) + 63) / 64 * 64 : 0);
   float* target = source + m;
+  // SS2_PROF_WARP brackets everything K14 needs per chunk: canvas-normalised meshes, the fp64 TPS
+  // solves, the lattice nodes and the fused resample + blend kernel
+  ss2_prof_begin(ctx, SS2_PROF_WARP, st);
   int rc = stable_meshes_launch(ctx, d_mesh1, d_mesh2, n, H, W, h_minmax[0], h_minmax[2], out_w, out_h, source, target, st);
   if (rc == SS2_OK) rc = tps_solve_for_warp(ctx, source, target, 2 * n, H, W, Ho, Wo, mode, tps, sc, st);
   if (rc == SS2_OK) rc = tps_warp_blend_launch(ctx, d_hr1, d_hr2, source, sc.T, n, H, W, Ho, Wo, mode, tps, d_out, st, sc.aux, sc.nodes);
+  ss2_prof_end(ctx, SS2_PROF_WARP, st, (double)n * (2.0 * 3 * H * W + 3.0 * Ho * Wo) * 4.0);
   cudaFreeAsync(sc.base, st);
   return rc;
 }

@@ -110,6 +110,8 @@ struct ss2_ctx {
   int64_t launches = 0;
   std::map<std::string, HostTensor> host_weights[3];
   std::vector<void*> owned;  // device allocations freed at destroy
+  std::vector<void*> owned_net[3];  // packed weights per network: freed when that network is re-finalized
+  int packing_net = -1;             // network whose weights upload() is packing (-1: ctx->owned)
   SpatialWeights spatial;
   TemporalWeights temporal;
   SmoothWeights smooth;
@@ -118,6 +120,12 @@ struct ss2_ctx {
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   cudaEvent_t ev_hr = nullptr, ev_chunk[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   ProfClass prof[SS2_PROF_COUNT];
+  // the arena and the named buffers are shared workspace: when a call arrives on another stream than the previous
+  // one, it first waits (event) for everything the previous stream was given (ss2_workspace_enter)
+  cudaStream_t ws_stream = nullptr;
+  bool ws_used = false;
+  cudaEvent_t ws_ev = nullptr;
+  void* host_slots = nullptr;  // HostSlot[HOST_SLOTS] of the host-buffer pipeline (stream.cu), created on first use
   int use_tc = 1;  // tcgen05 implicit-GEMM path for eligible layers
   bool lag_tables_ready = false;
   int tc_passes = 3;  // 3 = split-TF32 (fp32-grade), 1 = plain TF32
@@ -126,6 +134,8 @@ struct ss2_ctx {
 };
 
 int ss2_fail(ss2_ctx* ctx, int code, const char* fmt, ...);
+int ss2_workspace_enter(ss2_ctx* ctx, cudaStream_t st);
+void ss2_host_slots_free(ss2_ctx* ctx);  // stream.cu: streams / events of the host pipeline
 int ss2_ensure_arena(ss2_ctx* ctx, size_t bytes);
 // profiling brackets: no-ops unless the class is enabled
 void ss2_prof_begin(ss2_ctx* ctx, int which, cudaStream_t st);

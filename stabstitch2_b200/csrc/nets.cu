@@ -23,7 +23,7 @@ static const HostTensor* find(ss2_ctx* ctx, int net, const std::string& key) {
 static int upload(ss2_ctx* ctx, const std::vector<float>& h, float** d) {
   void* p = nullptr;
   SS2_CUDA(ctx, cudaMalloc(&p, h.size() * sizeof(float)));
-  ctx->owned.push_back(p);
+  (ctx->packing_net >= 0 ? ctx->owned_net[ctx->packing_net] : ctx->owned).push_back(p);
   SS2_CUDA(ctx, cudaMemcpy(p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
   *d = (float*)p;
   return SS2_OK;
@@ -186,9 +186,25 @@ static int upload_key(ss2_ctx* ctx, int net, const std::string& key, float** d) 
   return upload(ctx, t->data, d);
 }
 
+static int finalize_weights_impl(ss2_ctx* ctx, int net_id);
+
 extern "C" int ss2_finalize_weights(ss2_ctx* ctx, int net_id) {
   if (!ctx) return SS2_ERR_INVALID;
+  if (net_id < 0 || net_id > 2) return ss2_fail(ctx, SS2_ERR_INVALID, "unknown net id %d", net_id);
   SS2_CUDA(ctx, cudaSetDevice(ctx->device));
+  // a re-finalize replaces the network's packed weights: wait for launches that still read the old set, free it
+  if (!ctx->owned_net[net_id].empty()) {
+    SS2_CUDA(ctx, cudaDeviceSynchronize());
+    for (void* p : ctx->owned_net[net_id]) cudaFree(p);
+    ctx->owned_net[net_id].clear();
+  }
+  ctx->packing_net = net_id;
+  const int rc = finalize_weights_impl(ctx, net_id);
+  ctx->packing_net = -1;
+  return rc;
+}
+
+static int finalize_weights_impl(ss2_ctx* ctx, int net_id) {
   if (net_id == SS2_NET_SPATIAL) {
     SpatialWeights& s = ctx->spatial;
     s.ready = false;
@@ -383,6 +399,7 @@ extern "C" int ss2_spatial_forward(ss2_ctx* ctx, const float* d_img1, const floa
   cudaStream_t st = (cudaStream_t)stream;
   const int H = NET_IMG_H, W = NET_IMG_W;
   const int chunk = bs < SPATIAL_CHUNK ? bs : SPATIAL_CHUNK;
+  SS2_TRY(ss2_workspace_enter(ctx, st));
   SS2_TRY(ss2_ensure_arena(ctx, (size_t)chunk * (2 * kBytesPerImageBackbone + kBytesPerPairHead) + ((size_t)64 << 20)));
   for (int b0 = 0; b0 < bs; b0 += chunk) {
     const int nb = bs - b0 < chunk ? bs - b0 : chunk;
@@ -427,6 +444,7 @@ extern "C" int ss2_build_temporal(ss2_ctx* ctx, const float* d_frames, int n, fl
   const int H = NET_IMG_H, W = NET_IMG_W;
   SS2_CUDA(ctx, cudaMemsetAsync(d_motions, 0, (size_t)126 * sizeof(float), st));
   const int chunk = (n < TEMPORAL_CHUNK ? n : TEMPORAL_CHUNK);
+  SS2_TRY(ss2_workspace_enter(ctx, st));
   SS2_TRY(ss2_ensure_arena(ctx, (size_t)chunk * (kBytesPerImageBackbone + kBytesPerPairHead) + ((size_t)64 << 20)));
   // chunk c covers frames [f0, f1): features of f0-1 are recomputed (1-frame halo) so chunks
   // stay independent; motion k needs features of frames k-1 and k.
@@ -458,6 +476,7 @@ extern "C" int ss2_build_smooth(ss2_ctx* ctx, const float* d_ts1, const float* d
   const SmoothWeights& M = ctx->smooth;
   const size_t per_win = (size_t)SS2_WINDOW * SS2_NPT * 128 * sizeof(float);
   const int chunk = nwin < SMOOTH_CHUNK ? nwin : SMOOTH_CHUNK;
+  SS2_TRY(ss2_workspace_enter(ctx, st));
   SS2_TRY(ss2_ensure_arena(ctx, (size_t)chunk * per_win * 8 + ((size_t)16 << 20)));
   for (int w0 = 0; w0 < nwin; w0 += chunk) {
     const int nw = nwin - w0 < chunk ? nwin - w0 : chunk;

@@ -53,6 +53,7 @@ extern "C" int ss2_stream_meshes(ss2_ctx* ctx, const float* d_lr1, const float* 
   const int nwin = n - (SS2_WINDOW - 1);
   const size_t wm = (size_t)nwin * SS2_WINDOW * SS2_NPT * 2;
   float* buf;
+  SS2_TRY(ss2_workspace_enter(ctx, st));
   SS2_TRY(named_buf(ctx, "stream_meshes", (8 * m + 2 * wm) * sizeof(float), &buf));
   float *sm1 = buf, *sm2 = buf + m, *tm1 = buf + 2 * m, *tm2 = buf + 3 * m;
   float *mesh1 = buf + 4 * m, *mesh2 = buf + 5 * m, *ts1 = buf + 6 * m, *ts2 = buf + 7 * m;
@@ -90,7 +91,27 @@ struct HostSlot {
   const float* pre[4] = {nullptr, nullptr, nullptr, nullptr};
   int pre_n = 0, pre_h = 0, pre_w = 0;
 };
-static HostSlot g_slots[8][HOST_SLOTS];  // [device][slot]
+// the slots belong to the context (distinct contexts are independent, also on one device)
+static HostSlot* ctx_slots(ss2_ctx* ctx) {
+  if (!ctx->host_slots) ctx->host_slots = new HostSlot[HOST_SLOTS];
+  return static_cast<HostSlot*>(ctx->host_slots);
+}
+
+void ss2_host_slots_free(ss2_ctx* ctx) {
+  if (!ctx->host_slots) return;
+  HostSlot* hs = static_cast<HostSlot*>(ctx->host_slots);
+  for (int i = 0; i < HOST_SLOTS; ++i) {
+    HostSlot& h = hs[i];
+    if (!h.s_copy) continue;
+    cudaStreamDestroy(h.s_copy);
+    cudaStreamDestroy(h.s_d2h);
+    cudaEvent_t evs[] = {h.ev_hr, h.ev_lr, h.ev_warp, h.ev_done, h.ev_chunk[0], h.ev_chunk[1], h.ev_d2h[0], h.ev_d2h[1]};
+    for (cudaEvent_t e : evs)
+      if (e) cudaEventDestroy(e);
+  }
+  delete[] hs;
+  ctx->host_slots = nullptr;
+}
 
 static int slot_init(ss2_ctx* ctx, HostSlot& h) {
   if (h.s_copy) return SS2_OK;
@@ -135,11 +156,11 @@ static int slot_upload(ss2_ctx* ctx, HostSlot& hs, int slot, const float* h_lr1,
 extern "C" int ss2_stitch_stream_host_prefetch(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2,
                                                const float* h_hr1, const float* h_hr2, int n, int H, int W) {
   if (!ctx) return SS2_ERR_INVALID;
-  if (slot < 0 || slot >= HOST_SLOTS || ctx->device < 0 || ctx->device >= 8) return ss2_fail(ctx, SS2_ERR_INVALID, "bad slot");
+  if (slot < 0 || slot >= HOST_SLOTS) return ss2_fail(ctx, SS2_ERR_INVALID, "bad slot");
   if (!h_lr1 || !h_lr2 || !h_hr1 || !h_hr2 || n < SS2_WINDOW || H <= 0 || W <= 0)
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stitch_stream_host_prefetch: bad arguments");
   SS2_CUDA(ctx, cudaSetDevice(ctx->device));
-  HostSlot& hs = g_slots[ctx->device][slot];
+  HostSlot& hs = ctx_slots(ctx)[slot];
   SS2_TRY(slot_init(ctx, hs));
   float *lr1, *lr2, *hr1, *hr2;
   SS2_TRY(slot_upload(ctx, hs, slot, h_lr1, h_lr2, h_hr1, h_hr2, n, H, W, &lr1, &lr2, &hr1, &hr2, true));
@@ -149,8 +170,8 @@ extern "C" int ss2_stitch_stream_host_prefetch(ss2_ctx* ctx, int slot, const flo
 }
 
 extern "C" int ss2_stitch_stream_host_wait(ss2_ctx* ctx, int slot) {
-  if (!ctx || slot < 0 || slot >= HOST_SLOTS || ctx->device < 0 || ctx->device >= 8) return SS2_ERR_INVALID;
-  HostSlot& h = g_slots[ctx->device][slot];
+  if (!ctx || slot < 0 || slot >= HOST_SLOTS) return SS2_ERR_INVALID;
+  HostSlot& h = ctx_slots(ctx)[slot];
   if (!h.busy) return SS2_OK;
   SS2_CUDA(ctx, cudaEventSynchronize(h.ev_done));
   h.busy = false;
@@ -162,12 +183,12 @@ extern "C" int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float*
                                             float* h_out, int64_t out_capacity, int* out_h, int* out_w,
                                             float* h_smooth_mesh1, float* h_smooth_mesh2) {
   if (!ctx) return SS2_ERR_INVALID;
-  if (slot < 0 || slot >= HOST_SLOTS || ctx->device < 0 || ctx->device >= 8) return ss2_fail(ctx, SS2_ERR_INVALID, "bad slot");
+  if (slot < 0 || slot >= HOST_SLOTS) return ss2_fail(ctx, SS2_ERR_INVALID, "bad slot");
   if (n < SS2_WINDOW) return ss2_fail(ctx, SS2_ERR_INVALID, "a stream needs at least %d frames (got %d)", SS2_WINDOW, n);
   if (!h_lr1 || !h_lr2 || !h_hr1 || !h_hr2 || !h_out || !out_h || !out_w || H <= 0 || W <= 0)
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stitch_stream_host: bad arguments");
   SS2_CUDA(ctx, cudaSetDevice(ctx->device));
-  HostSlot& hs = g_slots[ctx->device][slot];
+  HostSlot& hs = ctx_slots(ctx)[slot];
   SS2_TRY(slot_init(ctx, hs));
   SS2_TRY(ss2_stitch_stream_host_wait(ctx, slot));  // the slot's buffers must be free
   if (!ctx->s_compute) SS2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));

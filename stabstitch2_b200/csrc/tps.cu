@@ -18,129 +18,188 @@
 // 66x66 fp64 solve, one CTA per system.  The reference inverts W explicitly in fp64 and
 // multiplies by the targets; solving W T = tp by Gauss-Jordan with partial pivoting in fp64
 // gives the same fp32-rounded coefficients (fp64 noise is ~1e-9 of an fp32 ulp here).
+//
+// Latency-oriented (64 systems per 32-frame chunk: the chip is never full, so the time is the
+// length of one system's dependency chain on ONE SM).  The augmented matrix [W | tp] (66 x 68)
+// lives in REGISTERS: 16 warps x 32 lanes, thread (w, l) owns rows w + 16 i (i < 5) and columns
+// l + 32 j (j < 3).  Per pivot step only the pivot row (68 values) and the pivot column's
+// multipliers (66 values) travel through shared memory; rows are never swapped (the pivot row of
+// step k is remembered) and the search for the next pivot is folded into the elimination: the lane
+// that owns column k+1 offers |value| (top 25 bits) and its row to a shared atomicMax.
+// Round 1's kernel kept the matrix in shared memory (3 barriers, a single-warp search, a physical
+// swap and ~4400 warp instructions per step: 97 us for 64 systems).
 // ------------------------------------------------------------------------------------------
-#define SOLVE_THREADS 256
+#define SOLVE_THREADS 512
+#define SOLVE_ROWS 5   // rows per thread: w, w+16, .., w+64
+#define SOLVE_COLS 3   // columns per thread: l, l+32, l+64
 #define AUG (SS2_NSYS + 2)
-#define AUGP (AUG + 1)  // padded row length of the shared matrix (bank spread of the column walks)
+
+__device__ __forceinline__ unsigned solve_key(double v, int row) {
+  // monotone in |v| (sign stripped, exponent + 13 mantissa bits), row in the low 7 bits
+  const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu;
+  return ((hi >> 6) << 7) | (unsigned)row;
+}
 
 __global__ void __launch_bounds__(SOLVE_THREADS)
 tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ target, float* __restrict__ Tout,
                  float* __restrict__ aux, float half_w, float half_h, float kx, float ky) {
-  __shared__ double A[SS2_NSYS][AUGP];
   __shared__ float sx[SS2_NPT], sy[SS2_NPT];
-  __shared__ int piv_row;
+  __shared__ double pivrow[2][AUG + 2];      // the pivot row of the step (double-buffered by step parity)
+  __shared__ double colk[2][SS2_NSYS + 2];   // column k of every row, published one step ahead
+  __shared__ double pinv[SS2_NSYS];          // 1 / pivot of step k
+  __shared__ double rhs[SS2_NSYS][2];
+  __shared__ unsigned pkey[3];               // step k reads [k%3], offers candidates to [(k+1)%3], clears [(k+2)%3]
+  __shared__ int perm[SS2_NSYS];
   const int b = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const float* src = source + (size_t)b * SS2_NPT * 2;
   const float* tgt = target + (size_t)b * SS2_NPT * 2;
   if (tid < SS2_NPT) {
     sx[tid] = src[2 * tid];
     sy[tid] = src[2 * tid + 1];
   }
+  if (tid < 3) pkey[tid] = 0u;
   __syncthreads();
-  // assemble W (fp32 arithmetic for K exactly like the reference, then widened)
-  for (int e = tid; e < SS2_NSYS * AUG; e += SOLVE_THREADS) {
-    int r = e / AUG, c = e % AUG;
-    double v = 0.0;
-    if (r < SS2_NPT) {
-      if (c == 0) v = 1.0;
-      else if (c == 1) v = (double)sx[r];
-      else if (c == 2) v = (double)sy[r];
-      else if (c < SS2_NSYS) {
-        int j = c - 3;
-        float dx = __fsub_rn(sx[r], sx[j]);
-        float dy = __fsub_rn(sy[r], sy[j]);
-        float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-        float k = __fmul_rn(d2, logf(__fadd_rn(d2, 1e-6f)));
-        v = (double)k;
-      } else {
-        v = (double)tgt[2 * r + (c - SS2_NSYS)];
+  // assemble this thread's elements of [W | tp] (fp32 arithmetic for K exactly like the reference, then widened)
+  double a[SOLVE_ROWS][SOLVE_COLS];
+#pragma unroll
+  for (int i = 0; i < SOLVE_ROWS; ++i) {
+    const int r = wid + 16 * i;
+#pragma unroll
+    for (int j = 0; j < SOLVE_COLS; ++j) {
+      const int c = lane + 32 * j;
+      double v = 0.0;
+      if (r < SS2_NSYS && c < AUG) {
+        if (r < SS2_NPT) {
+          if (c == 0) v = 1.0;
+          else if (c == 1) v = (double)sx[r];
+          else if (c == 2) v = (double)sy[r];
+          else if (c < SS2_NSYS) {
+            const int q = c - 3;
+            const float dx = __fsub_rn(sx[r], sx[q]);
+            const float dy = __fsub_rn(sy[r], sy[q]);
+            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            v = (double)__fmul_rn(d2, logf(__fadd_rn(d2, 1e-6f)));
+          } else {
+            v = (double)tgt[2 * r + (c - SS2_NSYS)];
+          }
+        } else if (c >= 3 && c < SS2_NSYS) {
+          const int q = r - SS2_NPT, pt = c - 3;  // 0: ones, 1: x, 2: y
+          v = q == 0 ? 1.0 : (q == 1 ? (double)sx[pt] : (double)sy[pt]);
+        }
       }
-    } else {
-      int q = r - SS2_NPT;  // 0: ones, 1: x, 2: y
-      if (c >= 3 && c < SS2_NSYS) {
-        int j = c - 3;
-        v = q == 0 ? 1.0 : (q == 1 ? (double)sx[j] : (double)sy[j]);
-      }
+      a[i][j] = v;
     }
-    A[r][c] = v;
-  }
-  __syncthreads();
-  for (int k = 0; k < SS2_NSYS; ++k) {
-    // partial pivoting: warp 0 finds argmax |A[r][k]|, r >= k
-    if (tid < 32) {
-      double best = -1.0;
-      int bi = k;
-      for (int r = k + tid; r < SS2_NSYS; r += 32) {
-        double a = fabs(A[r][k]);
-        if (a > best) { best = a; bi = r; }
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_down_sync(0xffffffffu, best, o);
-        int oi = __shfl_down_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (tid == 0) piv_row = bi;
+    if (lane == 0 && r < SS2_NSYS) {  // column 0: candidates of the first pivot, and the first published column
+      colk[0][r] = a[i][0];
+      atomicMax(&pkey[0], solve_key(a[i][0], r));
     }
-    __syncthreads();
-    const int p = piv_row;
-    if (p != k) {
-      for (int c = tid; c < AUG; c += SOLVE_THREADS) {
-        double t = A[k][c];
-        A[k][c] = A[p][c];
-        A[p][c] = t;
-      }
-    }
-    __syncthreads();
-    const double inv = 1.0 / A[k][k];
-    // eliminate column k from every other row (columns > k only; column k is left stale): warps walk the rows, lanes
-    // the columns (conflict-free), no integer divisions, the row factor is computed once per row
-    for (int r = tid >> 5; r < SS2_NSYS; r += SOLVE_THREADS / 32) {
-      if (r != k) {
-        const double f = A[r][k] * inv;
-        for (int c = k + 1 + (tid & 31); c < AUG; c += 32) A[r][c] -= f * A[k][c];
-      }
-    }
-    __syncthreads();
-  }
-  for (int e = tid; e < 2 * SS2_NSYS; e += SOLVE_THREADS) {
-    int c = e / SS2_NSYS, j = e % SS2_NSYS;
-    Tout[(size_t)b * 2 * SS2_NSYS + c * SS2_NSYS + j] = (float)(A[j][SS2_NSYS + c] / A[j][j]);
   }
   // Affine predictor for the lattice resampler: least-squares fit target ~ a*sx + b*sy + c over
   // the 63 control points, expressed in source PIXEL units as a function of the canvas pixel
   // index (col,row): px = aux[0]*col + aux[1]*row + aux[2], py = aux[3]*col + aux[4]*row + aux[5].
-  // Cubic interpolation reproduces affine functions exactly, so any affine predictor is
+  // Interpolation reproduces affine functions exactly, so any affine predictor is
   // mathematically neutral; it only keeps the interpolated residuals small (fp32 rounding).
-  if (aux && tid == 0) {
-    double S[6] = {0, 0, 0, 0, 0, 0}, Bx[3] = {0, 0, 0}, By[3] = {0, 0, 0};
-    for (int i = 0; i < SS2_NPT; ++i) {
-      const double x = sx[i], y = sy[i], u = tgt[2 * i], v = tgt[2 * i + 1];
+  // One warp, partial sums per lane in control-point order, fixed shuffle tree (deterministic).
+  if (aux && wid == SOLVE_THREADS / 32 - 1) {
+    double S[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) S[q] = 0.0;
+    for (int i = lane; i < SS2_NPT; i += 32) {
+      const double x = src[2 * i], y = src[2 * i + 1], u = tgt[2 * i], v = tgt[2 * i + 1];
       S[0] += x * x; S[1] += x * y; S[2] += x; S[3] += y * y; S[4] += y; S[5] += 1.0;
-      Bx[0] += x * u; Bx[1] += y * u; Bx[2] += u;
-      By[0] += x * v; By[1] += y * v; By[2] += v;
+      S[6] += x * u; S[7] += y * u; S[8] += u;
+      S[9] += x * v; S[10] += y * v; S[11] += v;
     }
-    // normal equations [[S0 S1 S2],[S1 S3 S4],[S2 S4 S5]] p = B, Cramer's rule
-    const double m00 = S[3] * S[5] - S[4] * S[4], m01 = S[1] * S[5] - S[4] * S[2], m02 = S[1] * S[4] - S[3] * S[2];
-    const double det = S[0] * m00 - S[1] * m01 + S[2] * m02;
-    double sol[2][3] = {{0, 0, 0}, {0, 0, 0}};
-    if (fabs(det) > 1e-30) {
-      const double inv[3][3] = {
-          {m00 / det, -m01 / det, m02 / det},
-          {-m01 / det, (S[0] * S[5] - S[2] * S[2]) / det, -(S[0] * S[4] - S[1] * S[2]) / det},
-          {m02 / det, -(S[0] * S[4] - S[1] * S[2]) / det, (S[0] * S[3] - S[1] * S[1]) / det}};
-      for (int r = 0; r < 3; ++r) {
-        sol[0][r] = inv[r][0] * Bx[0] + inv[r][1] * Bx[1] + inv[r][2] * Bx[2];
-        sol[1][r] = inv[r][0] * By[0] + inv[r][1] * By[1] + inv[r][2] * By[2];
+#pragma unroll
+    for (int q = 0; q < 12; ++q)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) S[q] += __shfl_xor_sync(0xffffffffu, S[q], o);
+    if (lane == 0) {
+      const double* Bx = S + 6;
+      const double* By = S + 9;
+      // normal equations [[S0 S1 S2],[S1 S3 S4],[S2 S4 S5]] p = B, Cramer's rule
+      const double m00 = S[3] * S[5] - S[4] * S[4], m01 = S[1] * S[5] - S[4] * S[2], m02 = S[1] * S[4] - S[3] * S[2];
+      const double det = S[0] * m00 - S[1] * m01 + S[2] * m02;
+      double sol[2][3] = {{0, 0, 0}, {0, 0, 0}};
+      if (fabs(det) > 1e-30) {
+        const double inv[3][3] = {
+            {m00 / det, -m01 / det, m02 / det},
+            {-m01 / det, (S[0] * S[5] - S[2] * S[2]) / det, -(S[0] * S[4] - S[1] * S[2]) / det},
+            {m02 / det, -(S[0] * S[4] - S[1] * S[2]) / det, (S[0] * S[3] - S[1] * S[1]) / det}};
+        for (int r = 0; r < 3; ++r) {
+          sol[0][r] = inv[r][0] * Bx[0] + inv[r][1] * Bx[1] + inv[r][2] * Bx[2];
+          sol[1][r] = inv[r][0] * By[0] + inv[r][1] * By[1] + inv[r][2] * By[2];
+        }
+      }
+      float* o = aux + (size_t)b * 8;
+      // s = -1 + k*idx  ->  pix = half * (a*kx*col + b*ky*row + (c + 1 - a - b))
+      o[0] = (float)(half_w * sol[0][0] * kx); o[1] = (float)(half_w * sol[0][1] * ky);
+      o[2] = (float)(half_w * (sol[0][2] + 1.0 - sol[0][0] - sol[0][1]));
+      o[3] = (float)(half_h * sol[1][0] * kx); o[4] = (float)(half_h * sol[1][1] * ky);
+      o[5] = (float)(half_h * (sol[1][2] + 1.0 - sol[1][0] - sol[1][1]));
+      o[6] = 0.f; o[7] = 0.f;
+    }
+  }
+  unsigned used = 0u;  // bit i: this thread's row i has been a pivot row
+  __syncthreads();
+  for (int k = 0; k < SS2_NSYS; ++k) {
+    const int pb = k & 1;
+    const int p = (int)(pkey[k % 3] & 127u);
+    // the warp that owns row p publishes it
+    if ((p & 15) == wid) {
+      const int ip = p >> 4;
+#pragma unroll
+      for (int i = 0; i < SOLVE_ROWS; ++i)
+        if (i == ip) {
+#pragma unroll
+          for (int j = 0; j < SOLVE_COLS; ++j)
+            if (lane + 32 * j < AUG) pivrow[pb][lane + 32 * j] = a[i][j];
+        }
+      used |= 1u << ip;
+    }
+    if (tid == 0) {
+      perm[k] = p;
+      pkey[(k + 2) % 3] = 0u;  // last read in step k-1 (before the previous barrier), next written in step k+1
+    }
+    __syncthreads();
+    const double inv = 1.0 / pivrow[pb][k];
+    if (tid == 0) pinv[k] = inv;
+    double pr[SOLVE_COLS];
+#pragma unroll
+    for (int j = 0; j < SOLVE_COLS; ++j) pr[j] = (lane + 32 * j < AUG) ? pivrow[pb][lane + 32 * j] : 0.0;
+    // eliminate column k from every other row; columns <= k are updated too (they are never read again).
+    // The lane that owns column k+1 publishes it for the next step and offers its unused rows as pivots.
+    const int cn = k + 1;
+    const bool own_next = (cn & 31) == lane && cn < SS2_NSYS;
+#pragma unroll
+    for (int i = 0; i < SOLVE_ROWS; ++i) {
+      const int r = wid + 16 * i;
+      if (r < SS2_NSYS) {
+        const double f = (r == p) ? 0.0 : colk[pb][r] * inv;
+#pragma unroll
+        for (int j = 0; j < SOLVE_COLS; ++j) a[i][j] = fma(-f, pr[j], a[i][j]);
+        if (own_next) {
+          const double v = (cn >> 5) == 0 ? a[i][0] : ((cn >> 5) == 1 ? a[i][1] : a[i][2]);
+          colk[pb ^ 1][r] = v;
+          if (!((used >> i) & 1u)) atomicMax(&pkey[cn % 3], solve_key(v, r));
+        }
       }
     }
-    float* o = aux + (size_t)b * 8;
-    // s = -1 + k*idx  ->  pix = half * (a*kx*col + b*ky*row + (c + 1 - a - b))
-    o[0] = (float)(half_w * sol[0][0] * kx); o[1] = (float)(half_w * sol[0][1] * ky);
-    o[2] = (float)(half_w * (sol[0][2] + 1.0 - sol[0][0] - sol[0][1]));
-    o[3] = (float)(half_h * sol[1][0] * kx); o[4] = (float)(half_h * sol[1][1] * ky);
-    o[5] = (float)(half_h * (sol[1][2] + 1.0 - sol[1][0] - sol[1][1]));
-    o[6] = 0.f; o[7] = 0.f;
+    __syncthreads();
+  }
+  // right-hand sides (columns 66, 67 = lane 2, 3 of the third column group) of every row
+  if (lane == 2 || lane == 3) {
+#pragma unroll
+    for (int i = 0; i < SOLVE_ROWS; ++i) {
+      const int r = wid + 16 * i;
+      if (r < SS2_NSYS) rhs[r][lane - 2] = a[i][2];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 2 * SS2_NSYS; e += SOLVE_THREADS) {
+    const int c = e / SS2_NSYS, j = e % SS2_NSYS;
+    Tout[(size_t)b * 2 * SS2_NSYS + c * SS2_NSYS + j] = (float)(rhs[perm[j]][c] * pinv[j]);
   }
 }
 
@@ -445,8 +504,9 @@ __device__ __forceinline__ float log_pos_normal(float x) {
   return fmaf((float)e, 0.693147182f, r);
 }
 
-// one thread per (node, view): grid (node blocks, V, frames)
-template <int V>
+// one thread per (node, view): grid (node blocks, V, frames).  LAYOUT 0: nodes [n][ny][nx][V] float2 (x, y);
+// LAYOUT 1 (V == 2, tps_warp_lat3_kernel): [n][ny][nx] float4 (x_v0, x_v1, y_v0, y_v1)
+template <int V, int LAYOUT>
 __global__ void __launch_bounds__(128)
 tps_nodes_kernel(WarpParams P, int SX, int SY) {
   __shared__ float2 cxy[SS2_NPT];
@@ -489,7 +549,13 @@ tps_nodes_kernel(WarpParams P, int SX, int SY) {
   }
   const double px = (ax + 1.0) * (double)P.half_w - ((double)pred[0] * col + (double)pred[1] * row + (double)pred[2]);
   const double py = (ay + 1.0) * (double)P.half_h - ((double)pred[3] * col + (double)pred[4] * row + (double)pred[5]);
-  const_cast<float2*>(P.nodes)[((size_t)n * P.ny * P.nx + node) * V + v] = make_float2((float)px, (float)py);
+  if (LAYOUT == 1) {
+    float* o = reinterpret_cast<float*>(const_cast<float2*>(P.nodes)) + ((size_t)n * P.ny * P.nx + node) * 4;
+    o[v] = (float)px;
+    o[2 + v] = (float)py;
+  } else {
+    const_cast<float2*>(P.nodes)[((size_t)n * P.ny * P.nx + node) * V + v] = make_float2((float)px, (float)py);
+  }
 }
 
 // quintic Lagrange weights for nodes at -2..3 and t = k/S, k = 0..S-1
@@ -1668,6 +1734,9 @@ tps_warp_ptile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_con
   }
 }
 
+#include "tps_lat3.cuh"
+#include "tps_lat4.cuh"
+
 static inline float linstep(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 
 // lattice configuration: spacing (SX, SY) in canvas pixels and near radius R (normalised)
@@ -1769,10 +1838,52 @@ static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, flo
     for (int i = 0; i < 4; ++i) lagrange_table(S[i], &t[i]);
     SS2_CUDA(ctx, cudaMemcpyToSymbol(c_lag, t, sizeof(t)));
     SS2_CUDA(ctx, cudaMemcpyToSymbol(g_lag, t, sizeof(t)));
+    LagrangePairs tp[4];
+    for (int i = 0; i < 4; ++i)
+      for (int k = 0; k < 16; ++k)
+        for (int j = 0; j < LAT_TAPS; ++j) tp[i].w[k][j] = make_float2(t[i].w[k][j], t[i].w[k][j]);
+    SS2_CUDA(ctx, cudaMemcpyToSymbol(c_lagp, tp, sizeof(tp)));
     ctx->lag_tables_ready = true;
   }
   const int nnodes = P.nx * P.ny;
-  tps_nodes_kernel<V><<<dim3(cdiv(nnodes, 128), V, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY);
+  // production kernels: fused NORMAL resample + blend of two views, 720p / 1080p sources.
+  // SS2_TPS_L3: unset / 4 = tps_warp_lat4_kernel (one view per warp), 3 = tps_warp_lat3_kernel (both views per
+  // thread), 0 = the generic tps_warp_lattice_kernel below
+  {
+    const char* e3 = getenv("SS2_TPS_L3");
+    const char* et = getenv("SS2_TPS_TILE");
+    const int which = e3 ? atoi(e3) : 4;
+    const int sz = (P.W == 1280 && P.H == 720) ? 1 : (P.W == 1920 && P.H == 1080) ? 2 : 0;
+    if (BLEND && V == 2 && C == 3 && mode == SS2_MODE_NORMAL && sz != 0 && which != 0 && !(et && atoi(et) != 0) &&
+        (double)P.Ho * P.Wo * 3.0 < 2.0e9) {
+      if (which == 3) {
+        tps_nodes_kernel<2, 1><<<dim3(cdiv(nnodes, 128), 2, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY);
+        SS2_LAUNCH_CHECK(ctx);
+        dim3 g3(cdiv(P.Wo, L3_THREADS), cdiv(P.Ho, cfg.SY * L3_NCELL), nframes);
+#define L3_CASE(SXV, SYV)                                                                          \
+        if (cfg.SX == SXV && cfg.SY == SYV) {                                                        \
+          if (sz == 1) tps_warp_lat3_kernel<SXV, SYV, 1280, 720><<<g3, L3_THREADS, 0, st>>>(P);      \
+          else tps_warp_lat3_kernel<SXV, SYV, 1920, 1080><<<g3, L3_THREADS, 0, st>>>(P);             \
+        }
+        L3_CASE(16, 8) L3_CASE(16, 6) L3_CASE(12, 8) L3_CASE(12, 6) L3_CASE(8, 8) L3_CASE(8, 6)
+#undef L3_CASE
+      } else {
+        tps_nodes_kernel<2, 0><<<dim3(cdiv(nnodes, 128), 2, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY);
+        SS2_LAUNCH_CHECK(ctx);
+        dim3 g4(cdiv(P.Wo, L4_COLS), cdiv(P.Ho, cfg.SY * L4_NCELL), nframes);
+#define L4_CASE(SXV, SYV)                                                                          \
+        if (cfg.SX == SXV && cfg.SY == SYV) {                                                        \
+          if (sz == 1) tps_warp_lat4_kernel<SXV, SYV, 1280, 720><<<g4, L4_THREADS, 0, st>>>(P);      \
+          else tps_warp_lat4_kernel<SXV, SYV, 1920, 1080><<<g4, L4_THREADS, 0, st>>>(P);             \
+        }
+        L4_CASE(16, 8) L4_CASE(16, 6) L4_CASE(12, 8) L4_CASE(12, 6) L4_CASE(8, 8) L4_CASE(8, 6)
+#undef L4_CASE
+      }
+      SS2_LAUNCH_CHECK(ctx);
+      return SS2_OK;
+    }
+  }
+  tps_nodes_kernel<V, 0><<<dim3(cdiv(nnodes, 128), V, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY);
   SS2_LAUNCH_CHECK(ctx);
   { const char* e = getenv("SS2_TILE_DBG"); P.dbg = e ? atoi(e) : 0; }
   if (BLEND && V == 2 && C == 3 && mode == SS2_MODE_NORMAL && tile_path_ok(P, nframes)) {
@@ -1894,19 +2005,12 @@ int tps_warp_blend_launch(ss2_ctx* ctx, const float* d_img1, const float* d_img2
   P.aux = d_aux;
   P.half_w = mode == SS2_MODE_NORMAL ? 0.5f * W : 0.5f * (W - 1);
   P.half_h = mode == SS2_MODE_NORMAL ? 0.5f * H : 0.5f * (H - 1);
-  // algorithmic bytes: both source frames read once, the fused frame written once
-  const double bytes = (double)nframes * (2.0 * 3 * H * W + 3.0 * Ho * Wo) * 4.0;
-  if (tps == SS2_TPS_LATTICE && d_aux && d_nodes && tps_lattice_supported(Ho, Wo)) {
-    ss2_prof_begin(ctx, SS2_PROF_WARP, st);
-    int rc = lattice_launch<2, 3, true>(ctx, P, nframes, mode, d_nodes, st);
-    ss2_prof_end(ctx, SS2_PROF_WARP, st, bytes);
-    return rc;
-  }
+  // (the SS2_PROF_WARP bracket is set by the callers in api.cu, around canvas meshes + solves + nodes + this)
+  if (tps == SS2_TPS_LATTICE && d_aux && d_nodes && tps_lattice_supported(Ho, Wo))
+    return lattice_launch<2, 3, true>(ctx, P, nframes, mode, d_nodes, st);
   dim3 grid(cdiv(Wo, TX), cdiv(Ho, TILE_H), nframes), block(TX, TY);
-  ss2_prof_begin(ctx, SS2_PROF_WARP, st);
   if (mode == SS2_MODE_NORMAL) tps_warp_exact_kernel<2, 3, SS2_MODE_NORMAL, true><<<grid, block, 0, st>>>(P);
   else tps_warp_exact_kernel<2, 3, SS2_MODE_FAST, true><<<grid, block, 0, st>>>(P);
-  ss2_prof_end(ctx, SS2_PROF_WARP, st, bytes);
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }

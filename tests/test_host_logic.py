@@ -216,3 +216,20 @@ def test_bench_reference_arm_contract():
     e = line["e2e"]
     assert e["value"] == line["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
     assert line["gpu_launches"] == 0 and "workload" in line["config"]
+
+
+def test_canvas_size_truncation_sweep():
+    """ss2_canvas_size: extent = max - min in fp32, then truncation like torch's .int() (test_online_tra.py:119-120,140),
+    swept across integer boundaries (host arithmetic only: no GPU needed)."""
+    from stabstitch2_b200.pipeline import canvas_size
+    rng = np.random.default_rng(3)
+    for _ in range(4000):
+        lo = np.float32(rng.uniform(-600, 600))
+        k = np.float32(rng.integers(1, 4000))
+        eps = np.float32(rng.choice([-1.0, 1.0]) * 10.0 ** rng.uniform(-6, -1))
+        hi = np.float32(np.float32(lo + k) + eps)
+        lo_y = np.float32(rng.uniform(-50, 50))
+        hi_y = np.float32(lo_y + np.float32(rng.uniform(1, 2000)))
+        ref_w = int((torch.tensor(hi) - torch.tensor(lo)).int())
+        ref_h = int((torch.tensor(hi_y) - torch.tensor(lo_y)).int())
+        assert canvas_size([float(lo), float(hi), float(lo_y), float(hi_y)]) == (ref_h, ref_w)
