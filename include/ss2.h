@@ -15,7 +15,9 @@
  *    pointers.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *  - all entry points are asynchronous and stream-ordered unless documented otherwise.
  *  - a context is bound to one device and is NOT thread-safe; distinct contexts are
- *    independent (one per process/GPU in the multi-GPU layout).
+ *    independent (one per process/GPU in the multi-GPU layout).  The network entry points share
+ *    the context's workspace: a call arriving on another stream than the previous one first
+ *    waits (event) for the work the previous stream was given.
  *  - images are fp32 NCHW exactly like the reference tensors; meshes are fp32 [..,7,9,2]
  *    with last dim (x, y) (grid_res.py:3-4 -> 63 control points).
  */
@@ -63,7 +65,8 @@ int64_t ss2_launch_count(ss2_ctx* ctx, int reset);
 /* While enabled, the launches of kernel class `which` are bracketed by CUDA events recorded on
  * the launching stream.  ss2_profile_read synchronises those events and returns the summed
  * duration (ms) and the number of launches since the last ss2_profile_enable. */
-enum { SS2_PROF_WARP = 0,   /* fused TPS resample + blend kernel */
+enum { SS2_PROF_WARP = 0,   /* the whole resampling of a chunk: canvas meshes + TPS solves + lattice nodes + fused
+                               resample/blend kernel (everything SURVEY.md K14 needs) */
        SS2_PROF_CONV = 1,   /* implicit-GEMM convolution / linear kernels */
        SS2_PROF_COUNT = 2 };
 int ss2_profile_enable(ss2_ctx* ctx, int which, int enable);
@@ -227,6 +230,48 @@ int ss2_stitch_stream_host_wait(ss2_ctx* ctx, int slot);
  * underneath that chunk's networks.  The host buffers must stay valid and unchanged until that _async returns. */
 int ss2_stitch_stream_host_prefetch(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2,
                                     const float* h_hr1, const float* h_hr2, int n, int H, int W);
+
+/* ---- LINEAR fusion (test_online_tra.py:34-58,143-150) ------------------- */
+/* linear_blender: ref,tgt [n,3,Ho,Wo] warped images, ref_m,tgt_m [n,1,Ho,Wo] warped masks -> out [n,3,Ho,Wo]
+ * (and/or mask1 [n,1,Ho,Wo], the reference's mask=True result).  img_stride / mask_stride: elements between
+ * consecutive frames of the image / mask arguments (3*Ho*Wo and Ho*Wo for contiguous tensors).  A mask is the set
+ * of pixels with value > 0.5: residue-free semantics (the reference's torch.nonzero also counts the rounding
+ * residues of out-of-image samples; DESIGN.md has the measured difference).  Needs Ho, Wo > 10 (reflect padding). */
+int ss2_linear_blend(ss2_ctx* ctx, const float* d_ref, const float* d_tgt, int64_t img_stride, const float* d_ref_m,
+                     const float* d_tgt_m, int64_t mask_stride, int n, int Ho, int Wo, float* d_out, float* d_mask1,
+                     void* stream);
+/* The get_stable_sqe loop with fusion_mode == 'LINEAR' (same arguments as ss2_stable_frames): a ones channel rides
+ * through the resampler as the mask (:144-147), then linear_blender per frame. */
+int ss2_stable_frames_linear(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, const float* d_mesh1,
+                             const float* d_mesh2, int n, int H, int W, const float* h_minmax, int mode, int tps,
+                             float* d_out, void* stream);
+
+/* three-image warp + LINEAR fusion (test_online_tra_threeview.py:492-503): arguments of ss2_three_view_frames;
+ * fuse(1,2) with linear_blender, mask12 = mask1 + mask2 - mask1*mask2, then fuse(12,3). */
+int ss2_three_view_frames_linear(ss2_ctx* ctx, const float* d_img1, const float* d_img2, const float* d_img3,
+                                 const float* d_mesh1, const float* d_middle, const float* d_mesh3, int n, int H, int W,
+                                 const float* h_canvas, int mode, int tps, float* d_out, void* stream);
+
+/* ---- uint8 host edges (test_online_tra.py:252-264,152,414) ------------- */
+/* What the reference's driver does to a decoded frame before the networks, on the device:
+ * d_u8 [n,H,W,3] uint8 (cv2.imread layout, BGR) -> d_hr [n,3,H,W] fp32 0..255 (astype(float32) + transpose) and
+ * d_lr [n,3,360,480] fp32 = cv2.resize(img,(480,360)) (INTER_LINEAR, OpenCV's 11-bit fixed-point scheme, bit-exact)
+ * /127.5 - 1.  Either output may be NULL. */
+int ss2_load_frames_u8(ss2_ctx* ctx, const uint8_t* d_u8, int n, int H, int W, float* d_hr, float* d_lr, void* stream);
+/* fused frames [n,3,Ho,Wo] fp32 -> [n,Ho,Wo,3] uint8: transpose(1,2,0) + numpy astype(uint8) (truncation toward zero,
+ * wrap modulo 256), what the driver hands to cv2.VideoWriter (:414). */
+int ss2_frames_to_u8(ss2_ctx* ctx, const float* d_frames, int n, int Ho, int Wo, uint8_t* d_out, void* stream);
+/* The e2e calls with the uint8 interface: h_bgr1,h_bgr2 [n,H,W,3] uint8 HOST (pinned advised) -> h_out receives n
+ * frames [Ho,Wo,3] uint8 (capacity in bytes).  Same slots, pipelining rules and wait call
+ * (ss2_stitch_stream_host_wait) as the fp32 entry points; 4.4x fewer bytes over PCIe than the fp32 interface. */
+int ss2_stitch_stream_host_u8(ss2_ctx* ctx, const uint8_t* h_bgr1, const uint8_t* h_bgr2, int n, int H, int W, int mode,
+                              int tps, uint8_t* h_out, int64_t out_capacity, int* out_h, int* out_w,
+                              float* h_smooth_mesh1, float* h_smooth_mesh2);
+int ss2_stitch_stream_host_u8_async(ss2_ctx* ctx, int slot, const uint8_t* h_bgr1, const uint8_t* h_bgr2, int n, int H,
+                                    int W, int mode, int tps, uint8_t* h_out, int64_t out_capacity, int* out_h,
+                                    int* out_w, float* h_smooth_mesh1, float* h_smooth_mesh2);
+int ss2_stitch_stream_host_u8_prefetch(ss2_ctx* ctx, int slot, const uint8_t* h_bgr1, const uint8_t* h_bgr2, int n,
+                                       int H, int W);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,16 @@ SIGNATURES = {
                                           ctypes.POINTER(_i), ctypes.POINTER(_i), _vp, _vp]),
     "ss2_stitch_stream_host_wait": (_i, [_vp, _i]),
     "ss2_stitch_stream_host_prefetch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "ss2_linear_blend": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
+    "ss2_stable_frames_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _fp, _i, _i, _vp, _vp]),
+    "ss2_three_view_frames_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _fp, _i, _i, _vp, _vp]),
+    "ss2_load_frames_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "ss2_frames_to_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ss2_stitch_stream_host_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64,
+                                       ctypes.POINTER(_i), ctypes.POINTER(_i), _vp, _vp]),
+    "ss2_stitch_stream_host_u8_async": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64,
+                                             ctypes.POINTER(_i), ctypes.POINTER(_i), _vp, _vp]),
+    "ss2_stitch_stream_host_u8_prefetch": (_i, [_vp, _i, _vp, _vp, _i, _i, _i]),
 }
 
 _lib = None

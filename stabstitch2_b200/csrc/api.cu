@@ -210,7 +210,7 @@ int ss2_tps_warp(ss2_ctx* ctx, const float* d_U, const float* d_source, const fl
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_tps_warp: bad arguments");
   if (bn == 0 || Ho == 0 || Wo == 0) return SS2_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (tps != SS2_TPS_LATTICE || C != 3 || !tps_lattice_supported(Ho, Wo)) tps = SS2_TPS_EXACT;
+  if (tps != SS2_TPS_LATTICE || (C != 3 && C != 4) || !tps_lattice_supported(Ho, Wo)) tps = SS2_TPS_EXACT;
   TpsScratch sc;
   SS2_TRY(tps_scratch_alloc(ctx, bn, Ho, Wo, tps, 0, &sc, st));
   int rc = tps_solve_for_warp(ctx, d_source, d_target, bn, H, W, Ho, Wo, mode, tps, sc, st);

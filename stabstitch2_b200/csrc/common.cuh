@@ -128,6 +128,7 @@ struct ss2_ctx {
   void* host_slots = nullptr;  // HostSlot[HOST_SLOTS] of the host-buffer pipeline (stream.cu), created on first use
   int use_tc = 1;  // tcgen05 implicit-GEMM path for eligible layers
   bool lag_tables_ready = false;
+  bool gauss_ready = false;  // linear.cu: 21-tap Gaussian in constant memory
   int tc_passes = 3;  // 3 = split-TF32 (fp32-grade), 1 = plain TF32
   int use_tc_stem = 1;  // tensor-core 7x7 stem (SS2_TC_STEM=0: exact-fp32 SIMT stem)
   int use_dc = 1;     // direct 3x3 kernel (conv_dc.cu) for eligible layers; SS2_CONV_DC=0 disables
@@ -285,6 +286,10 @@ int cost_volume_launch(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B
                        int CP, const ActRef& out, cudaStream_t st);
 int ccl_launch(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H, int W, int C, float* d_flow,
                cudaStream_t st);
+// edges.cu: uint8 host edges on the device (cv2-exact resize, fp32 <-> uint8 layout conversions)
+int load_frames_u8_launch(ss2_ctx* ctx, const unsigned char* d_u8, int n, int H, int W, float* d_hr, float* d_lr,
+                          cudaStream_t st);
+int frames_to_u8_launch(ss2_ctx* ctx, const float* d_frames, int n, int Ho, int Wo, unsigned char* d_out, cudaStream_t st);
 // smooth.cu
 int smooth_embed_launch(ss2_ctx* ctx, const SmoothWeights& sw, const float* ts1, const float* ts2,
                         const float* sm1, const float* sm2, int nwin, int zero_first, const ActRef& hidden, float* d_path1,

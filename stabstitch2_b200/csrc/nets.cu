@@ -443,14 +443,17 @@ extern "C" int ss2_build_temporal(ss2_ctx* ctx, const float* d_frames, int n, fl
   const TemporalWeights& T = ctx->temporal;
   const int H = NET_IMG_H, W = NET_IMG_W;
   SS2_CUDA(ctx, cudaMemsetAsync(d_motions, 0, (size_t)126 * sizeof(float), st));
-  const int chunk = (n < TEMPORAL_CHUNK ? n : TEMPORAL_CHUNK);
+  // n-1 motions; a chunk computes up to TEMPORAL_CHUNK motions from one more image (features of the frame before
+  // the chunk are recomputed: 1-frame halo, so chunks stay independent).  Chunks are BALANCED: a temporal shard of
+  // a stream hands over F+1 = 33 frames, which is one chunk of 33 images - not 32 + a second launch train over 2.
+  const int nmot = n - 1;
+  const int nchunks = nmot > 0 ? cdiv(nmot, TEMPORAL_CHUNK) : 0;
+  const int per = nchunks > 0 ? cdiv(nmot, nchunks) : 0;   // motions per chunk (<= TEMPORAL_CHUNK)
   SS2_TRY(ss2_workspace_enter(ctx, st));
-  SS2_TRY(ss2_ensure_arena(ctx, (size_t)chunk * (kBytesPerImageBackbone + kBytesPerPairHead) + ((size_t)64 << 20)));
-  // chunk c covers frames [f0, f1): features of f0-1 are recomputed (1-frame halo) so chunks
-  // stay independent; motion k needs features of frames k-1 and k.
-  for (int f0 = 1; f0 < n; f0 += chunk - 1) {
-    const int f1 = (f0 + chunk - 1 < n) ? f0 + chunk - 1 : n;  // motions f0..f1-1
-    const int nimg = f1 - f0 + 1;                              // frames f0-1 .. f1-1
+  SS2_TRY(ss2_ensure_arena(ctx, (size_t)(per + 1) * (kBytesPerImageBackbone + kBytesPerPairHead) + ((size_t)64 << 20)));
+  for (int f0 = 1; f0 < n; f0 += per) {
+    const int f1 = (f0 + per < n) ? f0 + per : n;   // motions f0..f1-1
+    const int nimg = f1 - f0 + 1;                    // frames f0-1 .. f1-1
     ctx->arena.reset();
     float *f64, *f32 = nullptr;
     int h64, w64, h32, w32;
@@ -460,7 +463,6 @@ extern "C" int ss2_build_temporal(ss2_ctx* ctx, const float* d_frames, int n, fl
     ARENA_ACT(cv, (size_t)nm * h64 * w64 * 64);
     SS2_TRY(cost_volume_launch(ctx, f64, f64 + (size_t)h64 * w64 * 128, nm, h64, w64, 128, 3, 64, cv, st));
     SS2_TRY(run_regressor(ctx, T.r2, cv, nm, h64, w64, d_motions + (size_t)f0 * 126, st));
-    if (chunk == 1) break;
   }
   return SS2_OK;
 }

@@ -88,8 +88,8 @@ struct HostSlot {
   cudaEvent_t ev_warp = nullptr;   // resampling of the slot's chunk done: its device input buffers may be overwritten
   bool busy = false, warped = false;
   // inputs already on their way (ss2_stitch_stream_host_prefetch)
-  const float* pre[4] = {nullptr, nullptr, nullptr, nullptr};
-  int pre_n = 0, pre_h = 0, pre_w = 0;
+  const void* pre[4] = {nullptr, nullptr, nullptr, nullptr};
+  int pre_n = 0, pre_h = 0, pre_w = 0, pre_u8 = 0;
 };
 // the slots belong to the context (distinct contexts are independent, also on one device)
 static HostSlot* ctx_slots(ss2_ctx* ctx) {
@@ -126,26 +126,59 @@ static int slot_init(ss2_ctx* ctx, HostSlot& h) {
   return SS2_OK;
 }
 
-// device input buffers of a slot + the H2D copies (network inputs first, then the much larger hr frames)
-static int slot_upload(ss2_ctx* ctx, HostSlot& hs, int slot, const float* h_lr1, const float* h_lr2, const float* h_hr1,
-                       const float* h_hr2, int n, int H, int W, float** lr1, float** lr2, float** hr1, float** hr2,
-                       bool enqueue) {
+// device input buffers of a slot + the H2D copies.  fp32 interface: network inputs first, then the much larger hr frames.
+// uint8 interface (u8 != 0): only the decoded BGR frames travel (h_a, h_b [n,H,W,3]); hr / lr are made on the device.
+static int slot_upload(ss2_ctx* ctx, HostSlot& hs, int slot, int u8, const void* h_lr1, const void* h_lr2, const void* h_a,
+                       const void* h_b, int n, int H, int W, float** lr1, float** lr2, float** hr1, float** hr2,
+                       unsigned char** ua, unsigned char** ub, bool enqueue) {
   const size_t lrb = (size_t)n * 3 * 360 * 480 * sizeof(float), hrb = (size_t)n * 3 * H * W * sizeof(float);
+  const size_t u8b = (size_t)n * 3 * H * W;
   char nm[32];
   auto name = [&](const char* base) { snprintf(nm, sizeof(nm), "%s.%d", base, slot); return nm; };
   SS2_TRY(named_buf(ctx, name("lr1"), lrb, lr1));
   SS2_TRY(named_buf(ctx, name("lr2"), lrb, lr2));
   SS2_TRY(named_buf(ctx, name("hr1"), hrb, hr1));
   SS2_TRY(named_buf(ctx, name("hr2"), hrb, hr2));
+  *ua = *ub = nullptr;
+  if (u8) {
+    float *pa, *pb;
+    SS2_TRY(named_buf(ctx, name("u8a"), u8b, &pa));
+    SS2_TRY(named_buf(ctx, name("u8b"), u8b, &pb));
+    *ua = (unsigned char*)pa; *ub = (unsigned char*)pb;
+  }
   if (!enqueue) return SS2_OK;
   cudaStream_t sx = hs.s_copy;
   if (hs.warped) SS2_CUDA(ctx, cudaStreamWaitEvent(sx, hs.ev_warp, 0));  // the previous chunk of this slot still reads them
+  if (u8) {
+    SS2_CUDA(ctx, cudaMemcpyAsync(*ua, h_a, u8b, cudaMemcpyHostToDevice, sx));
+    SS2_CUDA(ctx, cudaMemcpyAsync(*ub, h_b, u8b, cudaMemcpyHostToDevice, sx));
+    SS2_CUDA(ctx, cudaEventRecord(hs.ev_lr, sx));
+    SS2_CUDA(ctx, cudaEventRecord(hs.ev_hr, sx));
+    return SS2_OK;
+  }
   SS2_CUDA(ctx, cudaMemcpyAsync(*lr1, h_lr1, lrb, cudaMemcpyHostToDevice, sx));
   SS2_CUDA(ctx, cudaMemcpyAsync(*lr2, h_lr2, lrb, cudaMemcpyHostToDevice, sx));
   SS2_CUDA(ctx, cudaEventRecord(hs.ev_lr, sx));
-  SS2_CUDA(ctx, cudaMemcpyAsync(*hr1, h_hr1, hrb, cudaMemcpyHostToDevice, sx));
-  SS2_CUDA(ctx, cudaMemcpyAsync(*hr2, h_hr2, hrb, cudaMemcpyHostToDevice, sx));
+  SS2_CUDA(ctx, cudaMemcpyAsync(*hr1, h_a, hrb, cudaMemcpyHostToDevice, sx));
+  SS2_CUDA(ctx, cudaMemcpyAsync(*hr2, h_b, hrb, cudaMemcpyHostToDevice, sx));
   SS2_CUDA(ctx, cudaEventRecord(hs.ev_hr, sx));
+  return SS2_OK;
+}
+
+static int prefetch_impl(ss2_ctx* ctx, int slot, int u8, const void* h_lr1, const void* h_lr2, const void* h_a,
+                         const void* h_b, int n, int H, int W) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (slot < 0 || slot >= HOST_SLOTS) return ss2_fail(ctx, SS2_ERR_INVALID, "bad slot");
+  if ((!u8 && (!h_lr1 || !h_lr2)) || !h_a || !h_b || n < SS2_WINDOW || H <= 0 || W <= 0)
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stitch_stream_host_prefetch: bad arguments");
+  SS2_CUDA(ctx, cudaSetDevice(ctx->device));
+  HostSlot& hs = ctx_slots(ctx)[slot];
+  SS2_TRY(slot_init(ctx, hs));
+  float *lr1, *lr2, *hr1, *hr2;
+  unsigned char *ua, *ub;
+  SS2_TRY(slot_upload(ctx, hs, slot, u8, h_lr1, h_lr2, h_a, h_b, n, H, W, &lr1, &lr2, &hr1, &hr2, &ua, &ub, true));
+  hs.pre[0] = h_lr1; hs.pre[1] = h_lr2; hs.pre[2] = h_a; hs.pre[3] = h_b;
+  hs.pre_n = n; hs.pre_h = H; hs.pre_w = W; hs.pre_u8 = u8;
   return SS2_OK;
 }
 
@@ -155,18 +188,12 @@ static int slot_upload(ss2_ctx* ctx, HostSlot& hs, int slot, const float* h_lr1,
 // instead of after the host has waited for them (the canvas size is a data-dependent host read).
 extern "C" int ss2_stitch_stream_host_prefetch(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2,
                                                const float* h_hr1, const float* h_hr2, int n, int H, int W) {
-  if (!ctx) return SS2_ERR_INVALID;
-  if (slot < 0 || slot >= HOST_SLOTS) return ss2_fail(ctx, SS2_ERR_INVALID, "bad slot");
-  if (!h_lr1 || !h_lr2 || !h_hr1 || !h_hr2 || n < SS2_WINDOW || H <= 0 || W <= 0)
-    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stitch_stream_host_prefetch: bad arguments");
-  SS2_CUDA(ctx, cudaSetDevice(ctx->device));
-  HostSlot& hs = ctx_slots(ctx)[slot];
-  SS2_TRY(slot_init(ctx, hs));
-  float *lr1, *lr2, *hr1, *hr2;
-  SS2_TRY(slot_upload(ctx, hs, slot, h_lr1, h_lr2, h_hr1, h_hr2, n, H, W, &lr1, &lr2, &hr1, &hr2, true));
-  hs.pre[0] = h_lr1; hs.pre[1] = h_lr2; hs.pre[2] = h_hr1; hs.pre[3] = h_hr2;
-  hs.pre_n = n; hs.pre_h = H; hs.pre_w = W;
-  return SS2_OK;
+  return prefetch_impl(ctx, slot, 0, h_lr1, h_lr2, h_hr1, h_hr2, n, H, W);
+}
+
+extern "C" int ss2_stitch_stream_host_u8_prefetch(ss2_ctx* ctx, int slot, const uint8_t* h_bgr1, const uint8_t* h_bgr2,
+                                                  int n, int H, int W) {
+  return prefetch_impl(ctx, slot, 1, nullptr, nullptr, h_bgr1, h_bgr2, n, H, W);
 }
 
 extern "C" int ss2_stitch_stream_host_wait(ss2_ctx* ctx, int slot) {
@@ -178,14 +205,14 @@ extern "C" int ss2_stitch_stream_host_wait(ss2_ctx* ctx, int slot) {
   return SS2_OK;
 }
 
-extern "C" int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2,
-                                            const float* h_hr1, const float* h_hr2, int n, int H, int W, int mode, int tps,
-                                            float* h_out, int64_t out_capacity, int* out_h, int* out_w,
-                                            float* h_smooth_mesh1, float* h_smooth_mesh2) {
+// one chunk through the host pipeline; u8 != 0: uint8 frames in ([n,H,W,3] BGR) and out ([n,Ho,Wo,3])
+static int async_impl(ss2_ctx* ctx, int slot, int u8, const void* h_lr1, const void* h_lr2, const void* h_a, const void* h_b,
+                      int n, int H, int W, int mode, int tps, void* h_out, int64_t out_capacity, int* out_h, int* out_w,
+                      float* h_smooth_mesh1, float* h_smooth_mesh2) {
   if (!ctx) return SS2_ERR_INVALID;
   if (slot < 0 || slot >= HOST_SLOTS) return ss2_fail(ctx, SS2_ERR_INVALID, "bad slot");
   if (n < SS2_WINDOW) return ss2_fail(ctx, SS2_ERR_INVALID, "a stream needs at least %d frames (got %d)", SS2_WINDOW, n);
-  if (!h_lr1 || !h_lr2 || !h_hr1 || !h_hr2 || !h_out || !out_h || !out_w || H <= 0 || W <= 0)
+  if ((!u8 && (!h_lr1 || !h_lr2)) || !h_a || !h_b || !h_out || !out_h || !out_w || H <= 1 || W <= 1)
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stitch_stream_host: bad arguments");
   SS2_CUDA(ctx, cudaSetDevice(ctx->device));
   HostSlot& hs = ctx_slots(ctx)[slot];
@@ -195,16 +222,22 @@ extern "C" int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float*
   cudaStream_t sc = ctx->s_compute, sx = hs.s_d2h;
   const size_t mb = (size_t)n * SS2_NPT * 2 * sizeof(float);
   float *lr1, *lr2, *hr1, *hr2, *small;
+  unsigned char *ua, *ub;
   char nm[32];
   auto name = [&](const char* base) { snprintf(nm, sizeof(nm), "%s.%d", base, slot); return nm; };
-  const bool prefetched = hs.pre[0] == h_lr1 && hs.pre[1] == h_lr2 && hs.pre[2] == h_hr1 && hs.pre[3] == h_hr2 &&
-                          hs.pre_n == n && hs.pre_h == H && hs.pre_w == W;
-  SS2_TRY(slot_upload(ctx, hs, slot, h_lr1, h_lr2, h_hr1, h_hr2, n, H, W, &lr1, &lr2, &hr1, &hr2, !prefetched));
+  const bool prefetched = hs.pre[0] == h_lr1 && hs.pre[1] == h_lr2 && hs.pre[2] == h_a && hs.pre[3] == h_b &&
+                          hs.pre_n == n && hs.pre_h == H && hs.pre_w == W && hs.pre_u8 == u8;
+  SS2_TRY(slot_upload(ctx, hs, slot, u8, h_lr1, h_lr2, h_a, h_b, n, H, W, &lr1, &lr2, &hr1, &hr2, &ua, &ub, !prefetched));
   hs.pre[0] = hs.pre[1] = hs.pre[2] = hs.pre[3] = nullptr;
   SS2_TRY(named_buf(ctx, name("small"), 2 * mb + 64, &small));
   float *S1 = small, *S2 = small + (size_t)n * SS2_NPT * 2, *mm = S2 + (size_t)n * SS2_NPT * 2;
   // the compute stream only waits for the network inputs before it starts the networks
   SS2_CUDA(ctx, cudaStreamWaitEvent(sc, hs.ev_lr, 0));
+  if (u8) {
+    // device front end (test_online_tra.py:252-264): fp32 planar hr frames and the cv2-resized network inputs
+    SS2_TRY(load_frames_u8_launch(ctx, ua, n, H, W, hr1, lr1, sc));
+    SS2_TRY(load_frames_u8_launch(ctx, ub, n, H, W, hr2, lr2, sc));
+  }
   SS2_TRY(ss2_stream_meshes(ctx, lr1, lr2, n, S1, S2, nullptr, nullptr, nullptr, nullptr, sc));
   SS2_TRY(canvas_minmax_launch(ctx, S1, S2, n, H, W, mm, sc));
   float h_mm[4];
@@ -218,20 +251,28 @@ extern "C" int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float*
   if (Ho <= 0 || Wo <= 0) return ss2_fail(ctx, SS2_ERR_INVALID, "degenerate canvas %dx%d", Ho, Wo);
   const size_t fpx = (size_t)3 * Ho * Wo;
   if ((int64_t)(fpx * n) > out_capacity)
-    return ss2_fail(ctx, SS2_ERR_INVALID, "output needs %zu floats, capacity %lld", fpx * n, (long long)out_capacity);
+    return ss2_fail(ctx, SS2_ERR_INVALID, "output needs %zu elements, capacity %lld", fpx * n, (long long)out_capacity);
   // The whole chunk is resampled into a device buffer of its own (HBM is plentiful), so the compute
   // stream is free for the next chunk's networks while the copy stream drains the frames to the host.
-  float* obuf;
+  float *obuf, *obuf8f = nullptr;
   SS2_TRY(named_buf(ctx, name("out_frames"), (size_t)n * fpx * sizeof(float), &obuf));
+  if (u8) SS2_TRY(named_buf(ctx, name("out_u8"), (size_t)n * fpx, &obuf8f));
+  unsigned char* obuf8 = (unsigned char*)obuf8f;
   SS2_CUDA(ctx, cudaStreamWaitEvent(sc, hs.ev_hr, 0));
   for (int f0 = 0; f0 < n; f0 += WARP_CHUNK) {
     const int nf = n - f0 < WARP_CHUNK ? n - f0 : WARP_CHUNK;
     float* dst = obuf + (size_t)f0 * fpx;
     SS2_TRY(ss2_stable_frames(ctx, hr1 + (size_t)f0 * 3 * H * W, hr2 + (size_t)f0 * 3 * H * W, S1 + (size_t)f0 * SS2_NPT * 2,
                               S2 + (size_t)f0 * SS2_NPT * 2, nf, H, W, h_mm, mode, tps, dst, sc));
+    if (u8) SS2_TRY(frames_to_u8_launch(ctx, dst, nf, Ho, Wo, obuf8 + (size_t)f0 * fpx, sc));   // :152,414 astype(uint8)
     SS2_CUDA(ctx, cudaEventRecord(hs.ev_chunk[0], sc));
     SS2_CUDA(ctx, cudaStreamWaitEvent(sx, hs.ev_chunk[0], 0));
-    SS2_CUDA(ctx, cudaMemcpyAsync(h_out + (size_t)f0 * fpx, dst, (size_t)nf * fpx * sizeof(float), cudaMemcpyDeviceToHost, sx));
+    if (u8)
+      SS2_CUDA(ctx, cudaMemcpyAsync((unsigned char*)h_out + (size_t)f0 * fpx, obuf8 + (size_t)f0 * fpx, (size_t)nf * fpx,
+                                    cudaMemcpyDeviceToHost, sx));
+    else
+      SS2_CUDA(ctx, cudaMemcpyAsync((float*)h_out + (size_t)f0 * fpx, dst, (size_t)nf * fpx * sizeof(float),
+                                    cudaMemcpyDeviceToHost, sx));
   }
   SS2_CUDA(ctx, cudaEventRecord(hs.ev_warp, sc));
   hs.warped = true;
@@ -240,11 +281,34 @@ extern "C" int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float*
   return SS2_OK;
 }
 
+extern "C" int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2,
+                                            const float* h_hr1, const float* h_hr2, int n, int H, int W, int mode, int tps,
+                                            float* h_out, int64_t out_capacity, int* out_h, int* out_w,
+                                            float* h_smooth_mesh1, float* h_smooth_mesh2) {
+  return async_impl(ctx, slot, 0, h_lr1, h_lr2, h_hr1, h_hr2, n, H, W, mode, tps, h_out, out_capacity, out_h, out_w,
+                    h_smooth_mesh1, h_smooth_mesh2);
+}
+
+extern "C" int ss2_stitch_stream_host_u8_async(ss2_ctx* ctx, int slot, const uint8_t* h_bgr1, const uint8_t* h_bgr2, int n,
+                                               int H, int W, int mode, int tps, uint8_t* h_out, int64_t out_capacity,
+                                               int* out_h, int* out_w, float* h_smooth_mesh1, float* h_smooth_mesh2) {
+  return async_impl(ctx, slot, 1, nullptr, nullptr, h_bgr1, h_bgr2, n, H, W, mode, tps, h_out, out_capacity, out_h, out_w,
+                    h_smooth_mesh1, h_smooth_mesh2);
+}
+
 extern "C" int ss2_stitch_stream_host(ss2_ctx* ctx, const float* h_lr1, const float* h_lr2, const float* h_hr1,
                                       const float* h_hr2, int n, int H, int W, int mode, int tps, float* h_out,
                                       int64_t out_capacity, int* out_h, int* out_w, float* h_smooth_mesh1,
                                       float* h_smooth_mesh2) {
   SS2_TRY(ss2_stitch_stream_host_async(ctx, 0, h_lr1, h_lr2, h_hr1, h_hr2, n, H, W, mode, tps, h_out, out_capacity, out_h,
                                        out_w, h_smooth_mesh1, h_smooth_mesh2));
+  return ss2_stitch_stream_host_wait(ctx, 0);
+}
+
+extern "C" int ss2_stitch_stream_host_u8(ss2_ctx* ctx, const uint8_t* h_bgr1, const uint8_t* h_bgr2, int n, int H, int W,
+                                         int mode, int tps, uint8_t* h_out, int64_t out_capacity, int* out_h, int* out_w,
+                                         float* h_smooth_mesh1, float* h_smooth_mesh2) {
+  SS2_TRY(ss2_stitch_stream_host_u8_async(ctx, 0, h_bgr1, h_bgr2, n, H, W, mode, tps, h_out, out_capacity, out_h, out_w,
+                                          h_smooth_mesh1, h_smooth_mesh2));
   return ss2_stitch_stream_host_wait(ctx, 0);
 }

@@ -21,7 +21,7 @@
 //
 // Latency-oriented (64 systems per 32-frame chunk: the chip is never full, so the time is the
 // length of one system's dependency chain on ONE SM).  The augmented matrix [W | tp] (66 x 68)
-// lives in REGISTERS: 16 warps x 32 lanes, thread (w, l) owns rows w + 16 i (i < 5) and columns
+// lives in REGISTERS: SOLVE_NW warps x 32 lanes, thread (w, l) owns rows w + SOLVE_NW i and columns
 // l + 32 j (j < 3).  Per pivot step only the pivot row (68 values) and the pivot column's
 // multipliers (66 values) travel through shared memory; rows are never swapped (the pivot row of
 // step k is remembered) and the search for the next pivot is folded into the elimination: the lane
@@ -29,8 +29,11 @@
 // Round 1's kernel kept the matrix in shared memory (3 barriers, a single-warp search, a physical
 // swap and ~4400 warp instructions per step: 97 us for 64 systems).
 // ------------------------------------------------------------------------------------------
-#define SOLVE_THREADS 512
-#define SOLVE_ROWS 5   // rows per thread: w, w+16, .., w+64
+#ifndef SOLVE_NW
+#define SOLVE_NW 8     // warps per system (measured: 16 warps 56 us per 64 systems - the per-warp bookkeeping of a step
+#endif                 // outweighs its 15 DFMAs; 8 warps halve the instructions per step)
+#define SOLVE_THREADS (SOLVE_NW * 32)
+#define SOLVE_ROWS ((SS2_NSYS + SOLVE_NW - 1) / SOLVE_NW)   // rows per thread: w, w+NW, ..
 #define SOLVE_COLS 3   // columns per thread: l, l+32, l+64
 #define AUG (SS2_NSYS + 2)
 
@@ -64,7 +67,7 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
   double a[SOLVE_ROWS][SOLVE_COLS];
 #pragma unroll
   for (int i = 0; i < SOLVE_ROWS; ++i) {
-    const int r = wid + 16 * i;
+    const int r = wid + SOLVE_NW * i;
 #pragma unroll
     for (int j = 0; j < SOLVE_COLS; ++j) {
       const int c = lane + 32 * j;
@@ -146,16 +149,24 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
   for (int k = 0; k < SS2_NSYS; ++k) {
     const int pb = k & 1;
     const int p = (int)(pkey[k % 3] & 127u);
-    // the warp that owns row p publishes it
-    if ((p & 15) == wid) {
-      const int ip = p >> 4;
+    // the warp that owns row p publishes it NORMALISED by the pivot (one fp64 division per step, in that warp only)
+    if ((p % SOLVE_NW) == wid) {
+      const int ip = p / SOLVE_NW;
+      double mine[SOLVE_COLS];
 #pragma unroll
-      for (int i = 0; i < SOLVE_ROWS; ++i)
-        if (i == ip) {
+      for (int j = 0; j < SOLVE_COLS; ++j) {
+        mine[j] = a[0][j];
 #pragma unroll
-          for (int j = 0; j < SOLVE_COLS; ++j)
-            if (lane + 32 * j < AUG) pivrow[pb][lane + 32 * j] = a[i][j];
-        }
+        for (int i = 1; i < SOLVE_ROWS; ++i)
+          if (i == ip) mine[j] = a[i][j];
+      }
+      // pivot = column k of row p: lane k % 32, column group k / 32
+      const double cand_piv = (k >> 5) == 0 ? mine[0] : ((k >> 5) == 1 ? mine[1] : mine[2]);
+      const double inv = 1.0 / __shfl_sync(0xffffffffu, cand_piv, k & 31);
+#pragma unroll
+      for (int j = 0; j < SOLVE_COLS; ++j)
+        if (lane + 32 * j < AUG) pivrow[pb][lane + 32 * j] = mine[j] * inv;
+      if (lane == 0) pinv[k] = inv;
       used |= 1u << ip;
     }
     if (tid == 0) {
@@ -163,8 +174,6 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
       pkey[(k + 2) % 3] = 0u;  // last read in step k-1 (before the previous barrier), next written in step k+1
     }
     __syncthreads();
-    const double inv = 1.0 / pivrow[pb][k];
-    if (tid == 0) pinv[k] = inv;
     double pr[SOLVE_COLS];
 #pragma unroll
     for (int j = 0; j < SOLVE_COLS; ++j) pr[j] = (lane + 32 * j < AUG) ? pivrow[pb][lane + 32 * j] : 0.0;
@@ -174,9 +183,9 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
     const bool own_next = (cn & 31) == lane && cn < SS2_NSYS;
 #pragma unroll
     for (int i = 0; i < SOLVE_ROWS; ++i) {
-      const int r = wid + 16 * i;
+      const int r = wid + SOLVE_NW * i;
       if (r < SS2_NSYS) {
-        const double f = (r == p) ? 0.0 : colk[pb][r] * inv;
+        const double f = (r == p) ? 0.0 : colk[pb][r];   // the published pivot row is already divided by the pivot
 #pragma unroll
         for (int j = 0; j < SOLVE_COLS; ++j) a[i][j] = fma(-f, pr[j], a[i][j]);
         if (own_next) {
@@ -192,7 +201,7 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
   if (lane == 2 || lane == 3) {
 #pragma unroll
     for (int i = 0; i < SOLVE_ROWS; ++i) {
-      const int r = wid + 16 * i;
+      const int r = wid + SOLVE_NW * i;
       if (r < SS2_NSYS) rhs[r][lane - 2] = a[i][2];
     }
   }
@@ -360,7 +369,6 @@ struct WarpParams {
   float R2, p0, p1, p2, p3;  // near radius^2 (normalised units) and the blending cubic P(s)
   float q0, q1, q2, q3;      // P / ln2
   float half_w, half_h;      // normalised -> pixel scale of the source image
-  int dbg;                   // tile kernel debugging (SS2_TILE_DBG): 1 = stage nothing (every sample takes the global-load path)
 };
 
 // V = views evaluated per pixel (2 for the fused blend, 1 for the generic transformer).
@@ -504,9 +512,8 @@ __device__ __forceinline__ float log_pos_normal(float x) {
   return fmaf((float)e, 0.693147182f, r);
 }
 
-// one thread per (node, view): grid (node blocks, V, frames).  LAYOUT 0: nodes [n][ny][nx][V] float2 (x, y);
-// LAYOUT 1 (V == 2, tps_warp_lat3_kernel): [n][ny][nx] float4 (x_v0, x_v1, y_v0, y_v1)
-template <int V, int LAYOUT>
+// one thread per (node, view): grid (node blocks, V, frames); nodes [n][ny][nx][V] float2 (x, y)
+template <int V>
 __global__ void __launch_bounds__(128)
 tps_nodes_kernel(WarpParams P, int SX, int SY) {
   __shared__ float2 cxy[SS2_NPT];
@@ -549,13 +556,7 @@ tps_nodes_kernel(WarpParams P, int SX, int SY) {
   }
   const double px = (ax + 1.0) * (double)P.half_w - ((double)pred[0] * col + (double)pred[1] * row + (double)pred[2]);
   const double py = (ay + 1.0) * (double)P.half_h - ((double)pred[3] * col + (double)pred[4] * row + (double)pred[5]);
-  if (LAYOUT == 1) {
-    float* o = reinterpret_cast<float*>(const_cast<float2*>(P.nodes)) + ((size_t)n * P.ny * P.nx + node) * 4;
-    o[v] = (float)px;
-    o[2 + v] = (float)py;
-  } else {
-    const_cast<float2*>(P.nodes)[((size_t)n * P.ny * P.nx + node) * V + v] = make_float2((float)px, (float)py);
-  }
+  const_cast<float2*>(P.nodes)[((size_t)n * P.ny * P.nx + node) * V + v] = make_float2((float)px, (float)py);
 }
 
 // quintic Lagrange weights for nodes at -2..3 and t = k/S, k = 0..S-1
@@ -911,832 +912,6 @@ tps_warp_lattice_kernel(WarpParams P) {
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// TILE resampler (opt-in, SS2_TPS_TILE=1): the fused NORMAL resample + AVERAGE blend with TMA-staged source tiles.
-// Measured slower than tps_warp_lattice_kernel in round 1, kept as the base of the persistent variant.
-//
-// Same field evaluation as tps_warp_lattice_kernel (quintic lattice interpolation + exact near
-// field), but the bilinear taps never touch global memory from a thread:
-//   * a CTA owns a TL_W x TL_H tile of the canvas.  The last warp estimates the tile's source footprint per view
-//     (predictor + residual of the nearest lattice node at the tile's corners and edge midpoints) and has the TMA
-//     unit copy that box of the three colour planes ([3][TL_BH][TL_BW] floats per view; one box per plane, of
-//     TL_BH0, TL_BH1 or TL_BH rows; start column rounded to 16 bytes - an unaligned innermost start is an
-//     illegal instruction on sm_100; out-of-image elements zero-filled) into shared memory while the CTA
-//     y-contracts the lattice for its rows;
-//   * the affine predictor and an integer reference origin R0 are folded into the y-contracted node values
-//     (Lagrange weights sum to one and reproduce linear functions), so the x contraction
-//     (6 LDS.128 + 12 packed FFMA2) directly yields R0-relative source coordinates of both views; the box origin
-//     relative to R0 is folded into the per-view shared-memory base address;
-//   * taps are LDS with compile-time offsets from one per-view index; tap pairs and weight pairs
-//     go through packed fp32 FMAs (fma.rn.f32x2), as does the blend.
-// A sample whose taps are not inside the staged box although it is inside the image (footprint
-// larger than the box: scale > ~1.1, strong shear, or a near-field bump beyond the margin)
-// takes the per-warp slow path with global loads, so the result never depends on the estimate.
-// Two CTAs (2 x 100 KB) are resident per SM; one's TMA wait overlaps the other's sampling.
-// ------------------------------------------------------------------------------------------
-#define TL_W 64
-#ifndef TL_RPT
-#define TL_RPT 8   // canvas rows per thread (a warp owns a 32 x TL_RPT block)
-#endif
-#define TL_H (4 * TL_RPT)
-#define TL_THREADS 256
-#if TL_RPT == 8
-#define TL_BW 88   // staged box: columns
-#define TL_BH 44   //             rows; TMA boxes of TL_BH0, TL_BH1 or TL_BH rows, whichever the footprint needs
-#define TL_BH0 36
-#define TL_BH1 40
-#define TL_MINB 2
-#define TL_UNROLL 2
-#else
-#define TL_BW 96
-#define TL_BH 28
-#define TL_BH0 16
-#define TL_BH1 24
-#define TL_MINB 3
-#define TL_UNROLL 4
-#endif
-#define TL_PLANE (TL_BW * TL_BH)
-#define TL_MARGIN 4
-#define TL_SMEM_BYTES (2 * 3 * TL_PLANE * 4)
-
-__device__ __forceinline__ uint32_t tl_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-  float v;
-  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
-// four taps of one colour plane at byte address ad + OFF of the staged box, weights (w00, w10) and (w01, w11)
-template <int OFF>
-__device__ __forceinline__ void tile_taps(uint32_t ad, u64 wA, u64 wB, float& out) {
-  float t00, t10, t01, t11;
-  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(t00) : "r"(ad), "n"(OFF));
-  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(t10) : "r"(ad), "n"(OFF + 4));
-  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(t01) : "r"(ad), "n"(OFF + TL_BW * 4));
-  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(t11) : "r"(ad), "n"(OFF + TL_BW * 4 + 4));
-  float lo, hi;
-  upk2(ffma2(pk2(t01, t11), wB, fmul2(pk2(t00, t10), wA)), lo, hi);
-  out = lo + hi;
-}
-
-struct TileGeo {       // per view, written by one lane of warp 0
-  int tx0, ty0;        // image coordinates of the staged box's element (0, 0)
-  int lox, wxn;        // window (in R0-relative sample coordinates) of sample origins whose four taps are staged AND
-  int loy, wyn;        // inside the image: lox <= xi < lox + wxn
-  int shift;           // box element index = yi * TL_BW + xi - shift
-  int rows;            // rows of the TMA box (0: nothing staged for this view)
-};
-
-template <int SX> struct TileCols { static constexpr int value = (TL_W + SX - 1) / SX + LAT_TAPS; };
-
-__device__ LagrangeTable g_lag[4];  // the same tables in global memory: lanes read DIFFERENT rows (constant memory would serialise)
-
-template <int SX, int SY>
-__global__ void __launch_bounds__(TL_THREADS, TL_MINB)
-tps_warp_tile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_constant__ CUtensorMap tm0b,
-                     const __grid_constant__ CUtensorMap tm0c, const __grid_constant__ CUtensorMap tm1a,
-                     const __grid_constant__ CUtensorMap tm1b, const __grid_constant__ CUtensorMap tm1c, WarpParams P) {
-  constexpr int V = 2, C = 3;
-  constexpr int NCOL = TileCols<SX>::value;
-  constexpr int GEOW = TL_THREADS / 32 - 1;       // the warp that owns predictor, box geometry and TMA issue
-  extern __shared__ __align__(128) float tile[];  // [V][3][TL_BH][TL_BW], TMA destination
-  __shared__ float4 near_list[V * SS2_NPT];
-  __shared__ __align__(16) float2 ysm[TL_H][NCOL][V];
-  __shared__ int s_cnt[2];
-  __shared__ float s_pred[V][6];
-  __shared__ float s_r0f[V][2];
-  __shared__ int s_r0[V][2];
-  __shared__ TileGeo s_geo[V];
-  __shared__ __align__(8) uint64_t s_bar;
-  const int n = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int col0 = blockIdx.x * TL_W, row0 = blockIdx.y * TL_H;
-  const int jx0 = col0 / SX;
-  const int W = P.W, H = P.H;
-  const unsigned FULL = 0xffffffffu;
-
-  // ---- phase 0, warp 0: near list = control points whose disc s < R2 touches the tile (view-0 entries first)
-  if (wid == 0) {
-    const float x_lo = fmaf(P.stepx, (float)col0, -1.0f), x_hi = fmaf(P.stepx, (float)min(col0 + TL_W - 1, P.Wo - 1), -1.0f);
-    const float y_lo = fmaf(P.stepy, (float)row0, -1.0f), y_hi = fmaf(P.stepy, (float)min(row0 + TL_H - 1, P.Ho - 1), -1.0f);
-    int cnt = 0, cnt0 = 0;
-#pragma unroll
-    for (int it = 0; it < (V * SS2_NPT + 31) / 32; ++it) {
-      const int idx = it * 32 + lane;
-      bool hit = false;
-      float2 c = make_float2(0.f, 0.f);
-      if (idx < V * SS2_NPT) {
-        c = *reinterpret_cast<const float2*>(P.source + ((size_t)n * V * SS2_NPT + idx) * 2);
-        const float ddx = fmaxf(fmaxf(x_lo - c.x, c.x - x_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
-        hit = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
-      }
-      const unsigned m = __ballot_sync(FULL, hit);
-      if (hit) {
-        const int pv = idx >= SS2_NPT ? 1 : 0, pi = idx - pv * SS2_NPT;
-        const float* t = P.T + (size_t)(n * V + pv) * 2 * SS2_NSYS;
-        near_list[cnt + __popc(m & ((1u << lane) - 1u))] =
-            make_float4(c.x, c.y, t[3 + pi] * (P.half_w * LN2F), t[SS2_NSYS + 3 + pi] * (P.half_h * LN2F));
-      }
-      cnt += __popc(m);
-      // entries of view 0 are idx < 63: whole iteration 0, the first 31 lanes of iteration 1
-      cnt0 += it == 0 ? __popc(m) : (it == 1 ? __popc(m & ((1u << (SS2_NPT - 32)) - 1u)) : 0);
-    }
-    if (lane == 0) { s_cnt[0] = cnt; s_cnt[1] = cnt0; }
-  } else if (wid == GEOW) {
-    // ---- phase 0, last warp: predictor, R0 = floor(predictor at the tile origin), box geometry from an ESTIMATE of
-    // the tile's source footprint (predictor + the residual of the nearest lattice node at the tile's corners and
-    // edge midpoints; residuals vary by a fraction of a pixel between nodes, the margin absorbs it and the per-sample
-    // window test keeps the result independent of it), TMA issue: the copies fly while the CTA does phase 1
-    if (lane == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tl_smem_u32(&s_bar)));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    float pr = 0.f;
-    if (lane < V * 6) {
-      pr = P.aux[(size_t)(n * V + lane / 6) * 8 + lane % 6];
-      s_pred[lane / 6][lane % 6] = pr;
-    }
-    float pd[V][6];
-#pragma unroll
-    for (int q = 0; q < V * 6; ++q) pd[q / 6][q % 6] = __shfl_sync(FULL, pr, q);
-    int r0[V][2];
-    float base[V][2];  // predictor at the tile origin minus R0
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-#pragma unroll
-      for (int d = 0; d < 2; ++d) {
-        const double b = (double)pd[v][3 * d] * col0 + (double)pd[v][3 * d + 1] * row0 + (double)pd[v][3 * d + 2];
-        const double fb = floor(fmin(fmax(b, -1.0e6), 1.0e6));
-        r0[v][d] = (int)fb;
-        base[v][d] = (float)(b - fb);
-      }
-    if (lane < V * 2) { s_r0[lane >> 1][lane & 1] = r0[lane >> 1][lane & 1]; s_r0f[lane >> 1][lane & 1] = base[lane >> 1][lane & 1]; }
-    const int lastc = min(TL_W - 1, P.Wo - 1 - col0), lastr = min(TL_H - 1, P.Ho - 1 - row0);
-    const int k = lane & 7, kk = k < 4 ? k : k + 1;  // 3 x 3 sample points without the centre
-    const int pr_ = (kk / 3) * lastr / 2, pc_ = (kk % 3) * lastc / 2;
-    const int ix = min((col0 + pc_ + SX / 2) / SX, P.nx - 1 - LAT_LO), iy = min((row0 + pr_ + SY / 2) / SY, P.ny - 1 - LAT_LO);
-    const float4 q = __ldg(reinterpret_cast<const float4*>(P.nodes + (((size_t)n * P.ny + iy + LAT_LO) * P.nx + ix + LAT_LO) * V));
-    const float fc = (float)pc_, fr = (float)pr_;
-    float e[4];
-    e[0] = q.x + fmaf(pd[0][0], fc, fmaf(pd[0][1], fr, base[0][0]));
-    e[1] = q.y + fmaf(pd[0][3], fc, fmaf(pd[0][4], fr, base[0][1]));
-    e[2] = q.z + fmaf(pd[1][0], fc, fmaf(pd[1][1], fr, base[1][0]));
-    e[3] = q.w + fmaf(pd[1][3], fc, fmaf(pd[1][4], fr, base[1][1]));
-    float mn[4], mx[4];
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      mn[d] = mx[d] = e[d];
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        mn[d] = fminf(mn[d], __shfl_xor_sync(FULL, mn[d], o));
-        mx[d] = fmaxf(mx[d], __shfl_xor_sync(FULL, mx[d], o));
-      }
-    }
-    if (lane < V) {
-      const int v = lane;
-      const float lim = 1.0e6f;
-      const float fxmin = fmaxf(v == 0 ? mn[0] : mn[2], -lim), fymin = fmaxf(v == 0 ? mn[1] : mn[3], -lim);
-      const float fxmax = fminf(v == 0 ? mx[0] : mx[2], lim), fymax = fminf(v == 0 ? mx[1] : mx[3], lim);
-      const int rx0 = v == 0 ? r0[0][0] : r0[1][0], ry0 = v == 0 ? r0[0][1] : r0[1][1];
-      TileGeo g;
-      // box origin relative to R0 (the box must start on a 16-byte boundary of the frame row: image x0 = rx0 + bx0 is
-      // rounded down to a multiple of 4), then in image coordinates
-      const int bx0 = (((int)floorf(fxmin) - TL_MARGIN + rx0) & ~3) - rx0, by0 = (int)floorf(fymin) - TL_MARGIN;
-      const int need_w = (int)floorf(fxmax) + 2 + TL_MARGIN - bx0, need_h = (int)floorf(fymax) + 2 + TL_MARGIN - by0;
-      g.tx0 = rx0 + bx0;
-      g.ty0 = ry0 + by0;
-      const bool hits = g.tx0 + need_w > 0 && g.tx0 < W && g.ty0 + need_h > 0 && g.ty0 < H;
-      const bool use = hits && need_w <= TL_BW && need_h <= TL_BH && !(P.dbg & 1) && !((P.dbg & 2) && v == 1);
-      g.rows = use ? (need_h <= TL_BH0 ? TL_BH0 : need_h <= TL_BH1 ? TL_BH1 : TL_BH) : 0;
-      const int lox = max(0, -g.tx0), loy = max(0, -g.ty0);
-      g.wxn = use ? max(min(TL_BW - 1, W - 1 - g.tx0) - lox, 0) : 0;
-      g.wyn = use ? max(min(g.rows - 1, H - 1 - g.ty0) - loy, 0) : 0;
-      if (g.wxn == 0 || g.wyn == 0) { g.rows = 0; g.wxn = 0; g.wyn = 0; }
-      // window and index shift in R0-relative sample coordinates
-      g.lox = lox + bx0;
-      g.loy = loy + by0;
-      g.shift = by0 * TL_BW + bx0;
-      s_geo[v] = g;
-    }
-    __syncwarp();
-    // one thread issues the copies (a TMA instruction wants a single active lane): per view and colour plane one box
-    // of TL_BH0, TL_BH1 or TL_BH rows (three tensor maps per view), whichever covers the footprint
-    if (lane == 0) {
-      const int rows0 = s_geo[0].rows, rows1 = s_geo[1].rows;
-      if (rows0 + rows1 > 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tl_smem_u32(&s_bar)),
-                     "r"((uint32_t)((rows0 + rows1) * C * TL_BW * 4)) : "memory");
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const int rows = v == 0 ? rows0 : rows1;
-          if (rows > 0) {
-            const CUtensorMap* map = v == 0 ? (rows == TL_BH0 ? &tm0a : rows == TL_BH1 ? &tm0b : &tm0c)
-                                            : (rows == TL_BH0 ? &tm1a : rows == TL_BH1 ? &tm1b : &tm1c);
-            const int tx0 = s_geo[v].tx0, ty0 = s_geo[v].ty0;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-              asm volatile(
-                  "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                  ::"r"(tl_smem_u32(tile + (v * C + c) * TL_PLANE)), "l"(map), "r"(tl_smem_u32(&s_bar)), "r"(tx0), "r"(ty0),
-                  "r"(n * C + c)
-                  : "memory");
-            }
-          }
-        }
-      }
-    }
-  }
-  // ---- per-thread constants: one canvas column, TL_RPT consecutive rows (a warp owns a 32 x TL_RPT block)
-  const int wx = wid & 1, wy = wid >> 1;
-  const int colt = wx * 32 + lane, rt0 = wy * TL_RPT;
-  const int col = min(col0 + colt, P.Wo - 1);
-  const bool active = col0 + colt < P.Wo;
-  const int cxi = col / SX, rx = col - cxi * SX, js = cxi - jx0;
-  float lxw[LAT_TAPS];
-  {
-    const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SX)].w[rx][0]));
-    const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SX)].w[rx][4]));
-    lxw[0] = wlo.x; lxw[1] = wlo.y; lxw[2] = wlo.z; lxw[3] = wlo.w; lxw[4] = whi.x; lxw[5] = whi.y;
-  }
-  const float xt = fmaf(P.stepx, (float)col, -1.0f);
-  __syncthreads();  // near list, predictor, R0, box geometry
-  const int n_all = s_cnt[0], n0 = s_cnt[1];
-  int r0x[V], r0y[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) { r0x[v] = s_r0[v][0]; r0y[v] = s_r0[v][1]; }
-  // ---- phase 1: y contraction of the tile's node columns with the predictor folded in, relative to R0:
-  // ysm[r][j][v] = sum_b Ly[b] node[cy+b][jx0+j] + pred(node column, row) - R0
-  for (int item = tid; item < TL_H * NCOL; item += TL_THREADS) {
-    const int r = item / NCOL, j = item - r * NCOL;
-    if (jx0 + j < P.nx) {
-      const int row = min(row0 + r, P.Ho - 1);
-      const int cy = row / SY, ry = row - cy * SY;
-      const float2* nd = P.nodes + (((size_t)n * P.ny + cy) * P.nx + (jx0 + j)) * V;
-      const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SY)].w[ry][0]));
-      const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SY)].w[ry][4]));
-      const float wy_[LAT_TAPS] = {wlo.x, wlo.y, wlo.z, wlo.w, whi.x, whi.y};
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-      for (int b = 0; b < LAT_TAPS; ++b) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(nd + (size_t)b * P.nx * V));
-        a0 = fmaf(wy_[b], q.x, a0); a1 = fmaf(wy_[b], q.y, a1); a2 = fmaf(wy_[b], q.z, a2); a3 = fmaf(wy_[b], q.w, a3);
-      }
-      const float cr = (float)((jx0 + j - LAT_LO) * SX - col0), rr = (float)(row - row0);
-      a0 += fmaf(s_pred[0][0], cr, fmaf(s_pred[0][1], rr, s_r0f[0][0]));
-      a1 += fmaf(s_pred[0][3], cr, fmaf(s_pred[0][4], rr, s_r0f[0][1]));
-      a2 += fmaf(s_pred[1][0], cr, fmaf(s_pred[1][1], rr, s_r0f[1][0]));
-      a3 += fmaf(s_pred[1][3], cr, fmaf(s_pred[1][4], rr, s_r0f[1][1]));
-      *reinterpret_cast<float4*>(&ysm[r][j][0]) = make_float4(a0, a1, a2, a3);
-    }
-  }
-  u64 lxp[LAT_TAPS];
-#pragma unroll
-  for (int a = 0; a < LAT_TAPS; ++a) lxp[a] = pk2(lxw[a], lxw[a]);
-  // per-warp culling of the near list against this warp's 32 x TL_RPT block
-  unsigned cand = 0;
-  const bool cull = n_all <= 32;
-  if (n_all > 0) {
-    if (cull) {
-      bool keep = false;
-      if (lane < n_all) {
-        const float4 c = near_list[lane];
-        const float wx_lo = fmaf(P.stepx, (float)min(col0 + wx * 32, P.Wo - 1), -1.0f);
-        const float wx_hi = fmaf(P.stepx, (float)min(col0 + wx * 32 + 31, P.Wo - 1), -1.0f);
-        const float y_lo = fmaf(P.stepy, (float)min(row0 + rt0, P.Ho - 1), -1.0f);
-        const float y_hi = fmaf(P.stepy, (float)min(row0 + rt0 + TL_RPT - 1, P.Ho - 1), -1.0f);
-        const float ddx = fmaxf(fmaxf(wx_lo - c.x, c.x - wx_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
-        keep = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
-      }
-      cand = __ballot_sync(FULL, keep);
-    } else {
-      cand = FULL;
-    }
-  }
-  const unsigned oplane = (unsigned)(P.Ho * P.Wo);
-  float* outp = P.out + (size_t)n * C * oplane;
-  const float* imgv[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) imgv[v] = P.img[v] + (size_t)n * C * H * W;
-  int g_lox[V], g_wxn[V], g_loy[V], g_wyn[V];
-  uint32_t tbase[V];  // shared byte address of the view's staged box, pre-shifted so that R0-relative coordinates index it
-  const uint32_t tbase0 = tl_smem_u32(tile);
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    g_lox[v] = s_geo[v].lox; g_wxn[v] = s_geo[v].wxn; g_loy[v] = s_geo[v].loy; g_wyn[v] = s_geo[v].wyn;
-    tbase[v] = tbase0 + (uint32_t)((v * (C * TL_PLANE) - s_geo[v].shift) * 4);
-  }
-  const bool staged = s_geo[0].rows + s_geo[1].rows > 0;
-  __syncthreads();  // ysm complete
-  if (staged) {
-    uint32_t ok = 0;
-    while (!ok) {
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t"
-          "}\n"
-          : "=r"(ok)
-          : "r"(tl_smem_u32(&s_bar))
-          : "memory");
-    }
-  }
-
-  constexpr int kUnroll = TL_UNROLL;
-#pragma unroll kUnroll
-  for (int i = 0; i < TL_RPT; ++i) {
-    const int r = rt0 + i, row = row0 + r;
-    if (row >= P.Ho) break;  // warp-uniform
-    // ---- x contraction: box-local source coordinates (x, y) of both views
-    u64 acc0, acc1;
-    {
-      const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(&ysm[r][js][0]);
-      acc0 = fmul2(q.x, lxp[0]);
-      acc1 = fmul2(q.y, lxp[0]);
-    }
-#pragma unroll
-    for (int a = 1; a < LAT_TAPS; ++a) {
-      const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(&ysm[r][js + a][0]);
-      acc0 = ffma2(q.x, lxp[a], acc0);
-      acc1 = ffma2(q.y, lxp[a], acc1);
-    }
-    float px[V], py[V];
-    upk2(acc0, px[0], py[0]);
-    upk2(acc1, px[1], py[1]);
-    // ---- near-field corrections (branch-free: s is clamped to R2, where psi vanishes)
-    if (cand != 0u) {
-      const float yt = fmaf(P.stepy, (float)row, -1.0f);
-      unsigned m = cull ? cand : 0u;
-      int kk = 0;
-#pragma unroll 1
-      while (cull ? (m != 0u) : (kk < n_all)) {
-        int k;
-        if (cull) { k = __ffs(m) - 1; m &= m - 1; } else { k = kk++; }
-        const float4 c = near_list[k];
-        const float dx = xt - c.x, dy = yt - c.y;
-        const float s = fminf(fmaf(dy, dy, dx * dx), P.R2);
-        const float psi = fmaf(s, lg2_approx(s + 1e-6f), -blend_poly(s, P.R2, P.q0, P.q1, P.q2, P.q3));
-        if (k < n0) { px[0] = fmaf(c.z, psi, px[0]); py[0] = fmaf(c.w, psi, py[0]); }
-        else { px[1] = fmaf(c.z, psi, px[1]); py[1] = fmaf(c.w, psi, py[1]); }
-      }
-    }
-    // ---- bilinear taps
-    float res[V][C];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int xi = __float2int_rd(px[v]), yi = __float2int_rd(py[v]);
-      const float fx = px[v] - (float)xi, fy = py[v] - (float)yi;
-      const bool ok = (unsigned)(xi - g_lox[v]) < (unsigned)g_wxn[v] && (unsigned)(yi - g_loy[v]) < (unsigned)g_wyn[v];
-      const unsigned okm = __ballot_sync(FULL, ok);
-      if (okm == FULL) {
-        // every lane's four taps are staged and inside the image
-        const float gx = 1.0f - fx, gy = 1.0f - fy;
-        const u64 wA = pk2(gx * gy, fx * gy), wB = pk2(gx * fy, fx * fy);
-        const uint32_t ad = tbase[v] + (uint32_t)(yi * (TL_BW * 4) + xi * 4);
-        tile_taps<0>(ad, wA, wB, res[v][0]);
-        tile_taps<TL_PLANE * 4>(ad, wA, wB, res[v][1]);
-        tile_taps<2 * TL_PLANE * 4>(ad, wA, wB, res[v][2]);
-      } else {
-        // image border, outside the image, or outside the staged box
-        const bool inimg = (unsigned)(xi + r0x[v]) < (unsigned)(W - 1) && (unsigned)(yi + r0y[v]) < (unsigned)(H - 1);
-        const bool slow = __any_sync(FULL, inimg && !ok);
-        const bool use = slow ? inimg : ok;
-        res[v][0] = res[v][1] = res[v][2] = 0.0f;
-        if (__any_sync(FULL, use)) {
-          const float fxs = use ? fx : 0.0f, gxs = use ? 1.0f - fx : 0.0f, fys = use ? fy : 0.0f, gys = 1.0f - fys;
-          const u64 wA = pk2(gxs * gys, fxs * gys), wB = pk2(gxs * fys, fxs * fys);
-          if (!slow) {
-            const uint32_t ad = use ? tbase[v] + (uint32_t)(yi * (TL_BW * 4) + xi * 4) : tbase0;
-            tile_taps<0>(ad, wA, wB, res[v][0]);
-            tile_taps<TL_PLANE * 4>(ad, wA, wB, res[v][1]);
-            tile_taps<2 * TL_PLANE * 4>(ad, wA, wB, res[v][2]);
-            if (!use) res[v][0] = res[v][1] = res[v][2] = 0.0f;  // tbase0 may hold stale bits (0 * NaN)
-          } else {
-            const float* p = imgv[v] + (use ? (size_t)(yi + r0y[v]) * W + (xi + r0x[v]) : (size_t)0);
-            const size_t iplane = (size_t)H * W;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-              const u64 top = pk2(__ldg(p + c * iplane), __ldg(p + c * iplane + 1));
-              const u64 bot = pk2(__ldg(p + c * iplane + W), __ldg(p + c * iplane + W + 1));
-              float lo, hi;
-              upk2(ffma2(bot, wB, fmul2(top, wA)), lo, hi);
-              res[v][c] = lo + hi;
-            }
-          }
-        }
-      }
-    }
-    // ---- AVERAGE blend (a*a + b*b) / (a + b + 1e-6) and streaming stores
-    if (active) {
-      const unsigned opix = (unsigned)(row * P.Wo + col);
-      const u64 A = pk2(res[0][0], res[0][1]), B = pk2(res[1][0], res[1][1]);
-      float s0, s1, q0, q1;
-      upk2(fadd2(fadd2(A, B), pk2(1e-6f, 1e-6f)), s0, s1);
-      upk2(ffma2(B, B, fmul2(A, A)), q0, q1);
-      __stcs(const_cast<float*>(f32_at(outp, opix)), q0 * rcp_approx(s0));
-      __stcs(const_cast<float*>(f32_at(outp, opix + oplane)), q1 * rcp_approx(s1));
-      __stcs(const_cast<float*>(f32_at(outp, opix + 2 * oplane)), blend_avg_fast(res[0][2], res[1][2]));
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// PERSISTENT tile resampler (SS2_TPS_TILE=2): the staged kernel above with its per-tile prologue taken off the
-// critical path.  One CTA per SM walks a contiguous range of 64 x 32 canvas tiles (consecutive tiles are vertical
-// neighbours, so their source boxes overlap in L2).  Two PRODUCER warps run one tile ahead of sixteen CONSUMER
-// warps through a two-slot ring (source boxes, y-contracted lattice, near list, box geometry per slot):
-//   producer 0:   predictor, box geometry from the footprint estimate, TMA issue;
-//   producer 1:   near list;
-//   producers 2+: y contraction of the lattice with predictor and reference origin folded in (a quarter each);
-//   consumers:  x contraction, near field, LDS taps, packed blend, streaming stores (4 rows per thread).
-// full[slot] counts the producer warps + the TMA bytes, empty[slot] the sixteen consumer warps.
-// ------------------------------------------------------------------------------------------
-#define PT_W TL_W
-#define PT_H 32
-#define PT_RPT 4
-#define PT_CWARPS 16
-#define PT_YWARPS 4                         // producer warps sharing the y contraction
-#define PT_PWARPS (2 + PT_YWARPS)           // + box geometry / TMA issue, near list
-#define PT_THREADS ((PT_CWARPS + PT_PWARPS) * 32)
-#define PT_SMEM_BYTES (2 * 2 * 3 * TL_PLANE * 4)
-
-__device__ __forceinline__ void pt_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (int spin = 0; !ok; ++spin) {
-    if (spin > 2) __nanosleep(64);  // a spinning warp would take issue slots from the warps it waits for
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(tl_smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void pt_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl_smem_u32(bar)) : "memory");
-}
-
-template <int SX, int SY>
-__global__ void __launch_bounds__(PT_THREADS, 1)
-tps_warp_ptile_kernel(const __grid_constant__ CUtensorMap tm0a, const __grid_constant__ CUtensorMap tm0b,
-                      const __grid_constant__ CUtensorMap tm0c, const __grid_constant__ CUtensorMap tm1a,
-                      const __grid_constant__ CUtensorMap tm1b, const __grid_constant__ CUtensorMap tm1c, WarpParams P,
-                      int ntx, int nty, int total) {
-  static_assert(TL_RPT == 8 && PT_H == TL_H, "the persistent kernel shares the 64 x 32 tile / 88 x 44 box of the staged kernel");
-  constexpr int V = 2, C = 3;
-  constexpr int NCOL = TileCols<SX>::value;
-  constexpr int SLOT_FLOATS = V * C * TL_PLANE;
-  extern __shared__ __align__(128) float tiles[];  // [2 slots][V][3][TL_BH][TL_BW]
-  __shared__ float4 s_near[2][V * SS2_NPT];
-  __shared__ __align__(16) float2 s_ysm[2][PT_H][NCOL][V];
-  __shared__ int s_cnt[2][2];
-  __shared__ int s_r0[2][V][2];
-  __shared__ int s_tile[2][4];  // frame, bx, by of the slot's tile (decoded once, by the geometry warp)
-  __shared__ TileGeo s_geo[2][V];
-  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int W = P.W, H = P.H;
-  const unsigned FULL = 0xffffffffu;
-  // tile t = blockIdx.x + i * gridDim.x: at any time the CTAs cover ~gridDim.x consecutive tiles (a few strips of ONE
-  // frame), so overlapping source boxes of neighbouring tiles meet in L2 instead of being re-read from HBM
-  const int t_begin = blockIdx.x, t_end = total, t_step = gridDim.x;
-
-  if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&s_full[b])), "n"(PT_PWARPS));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tl_smem_u32(&s_empty[b])), "n"(PT_CWARPS));
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (wid >= PT_CWARPS) {
-    // ================= producers =================
-    const int role = wid - PT_CWARPS;  // 0: box geometry + TMA issue, 1: near list, 2..: y contraction
-    for (int t = t_begin, i = 0; t < t_end; t += t_step, ++i) {
-      const int slot = i & 1;
-      const int by = t % nty, bx = (t / nty) % ntx, n = t / (nty * ntx);
-      const int col0 = bx * PT_W, row0 = by * PT_H;
-      const int jx0 = col0 / SX;
-      if (i >= 2) pt_wait(&s_empty[slot], ((i >> 1) - 1) & 1);
-      if (role == 0 && lane == 0) { s_tile[slot][0] = n; s_tile[slot][1] = bx; s_tile[slot][2] = by; }
-      // predictor and R0 = floor(predictor at the tile origin): both producers need them
-      float pr = 0.f;
-      if (lane < V * 6) pr = P.aux[(size_t)(n * V + lane / 6) * 8 + lane % 6];
-      float pd[V][6];
-#pragma unroll
-      for (int q = 0; q < V * 6; ++q) pd[q / 6][q % 6] = __shfl_sync(FULL, pr, q);
-      int r0[V][2];
-      float base[V][2];
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-          const double b = (double)pd[v][3 * d] * col0 + (double)pd[v][3 * d + 1] * row0 + (double)pd[v][3 * d + 2];
-          const double fb = floor(fmin(fmax(b, -1.0e6), 1.0e6));
-          r0[v][d] = (int)fb;
-          base[v][d] = (float)(b - fb);
-        }
-      if (role == 1) {
-        // ---- near list (view-0 entries first)
-        {
-          const float x_lo = fmaf(P.stepx, (float)col0, -1.0f), x_hi = fmaf(P.stepx, (float)min(col0 + PT_W - 1, P.Wo - 1), -1.0f);
-          const float y_lo = fmaf(P.stepy, (float)row0, -1.0f), y_hi = fmaf(P.stepy, (float)min(row0 + PT_H - 1, P.Ho - 1), -1.0f);
-          int cnt = 0, cnt0 = 0;
-          float2 cs[(V * SS2_NPT + 31) / 32];
-#pragma unroll
-          for (int it = 0; it < (V * SS2_NPT + 31) / 32; ++it) {  // all loads in flight together
-            const int idx = it * 32 + lane;
-            cs[it] = idx < V * SS2_NPT ? __ldg(reinterpret_cast<const float2*>(P.source + ((size_t)n * V * SS2_NPT + idx) * 2))
-                                       : make_float2(0.f, 0.f);
-          }
-#pragma unroll
-          for (int it = 0; it < (V * SS2_NPT + 31) / 32; ++it) {
-            const int idx = it * 32 + lane;
-            bool hit = false;
-            const float2 c = cs[it];
-            if (idx < V * SS2_NPT) {
-              const float ddx = fmaxf(fmaxf(x_lo - c.x, c.x - x_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
-              hit = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
-            }
-            const unsigned m = __ballot_sync(FULL, hit);
-            if (hit) {
-              const int pv = idx >= SS2_NPT ? 1 : 0, pi = idx - pv * SS2_NPT;
-              const float* tt = P.T + (size_t)(n * V + pv) * 2 * SS2_NSYS;
-              s_near[slot][cnt + __popc(m & ((1u << lane) - 1u))] =
-                  make_float4(c.x, c.y, tt[3 + pi] * (P.half_w * LN2F), tt[SS2_NSYS + 3 + pi] * (P.half_h * LN2F));
-            }
-            cnt += __popc(m);
-            cnt0 += it == 0 ? __popc(m) : (it == 1 ? __popc(m & ((1u << (SS2_NPT - 32)) - 1u)) : 0);
-          }
-          if (lane == 0) { s_cnt[slot][0] = cnt; s_cnt[slot][1] = cnt0; }
-        }
-        __syncwarp();
-        if (lane == 0) pt_arrive(&s_full[slot]);
-      } else if (role == 0) {
-        if (lane < V * 2) s_r0[slot][lane >> 1][lane & 1] = r0[lane >> 1][lane & 1];
-        // ---- footprint estimate, box geometry (see tps_warp_tile_kernel)
-        const int lastc = min(PT_W - 1, P.Wo - 1 - col0), lastr = min(PT_H - 1, P.Ho - 1 - row0);
-        const int k = lane & 7, kk = k < 4 ? k : k + 1;
-        const int pr_ = (kk / 3) * lastr / 2, pc_ = (kk % 3) * lastc / 2;
-        const int ix = min((col0 + pc_ + SX / 2) / SX, P.nx - 1 - LAT_LO), iy = min((row0 + pr_ + SY / 2) / SY, P.ny - 1 - LAT_LO);
-        const float4 q = __ldg(reinterpret_cast<const float4*>(P.nodes + (((size_t)n * P.ny + iy + LAT_LO) * P.nx + ix + LAT_LO) * V));
-        const float fc = (float)pc_, fr = (float)pr_;
-        float e[4];
-        e[0] = q.x + fmaf(pd[0][0], fc, fmaf(pd[0][1], fr, base[0][0]));
-        e[1] = q.y + fmaf(pd[0][3], fc, fmaf(pd[0][4], fr, base[0][1]));
-        e[2] = q.z + fmaf(pd[1][0], fc, fmaf(pd[1][1], fr, base[1][0]));
-        e[3] = q.w + fmaf(pd[1][3], fc, fmaf(pd[1][4], fr, base[1][1]));
-        float mn[4], mx[4];
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          mn[d] = mx[d] = e[d];
-#pragma unroll
-          for (int o = 4; o > 0; o >>= 1) {
-            mn[d] = fminf(mn[d], __shfl_xor_sync(FULL, mn[d], o));
-            mx[d] = fmaxf(mx[d], __shfl_xor_sync(FULL, mx[d], o));
-          }
-        }
-        if (lane < V) {
-          const int v = lane;
-          const float lim = 1.0e6f;
-          const float fxmin = fmaxf(v == 0 ? mn[0] : mn[2], -lim), fymin = fmaxf(v == 0 ? mn[1] : mn[3], -lim);
-          const float fxmax = fminf(v == 0 ? mx[0] : mx[2], lim), fymax = fminf(v == 0 ? mx[1] : mx[3], lim);
-          const int rx0 = v == 0 ? r0[0][0] : r0[1][0], ry0 = v == 0 ? r0[0][1] : r0[1][1];
-          TileGeo g;
-          const int bx0 = (((int)floorf(fxmin) - TL_MARGIN + rx0) & ~3) - rx0, by0 = (int)floorf(fymin) - TL_MARGIN;
-          const int need_w = (int)floorf(fxmax) + 2 + TL_MARGIN - bx0, need_h = (int)floorf(fymax) + 2 + TL_MARGIN - by0;
-          g.tx0 = rx0 + bx0;
-          g.ty0 = ry0 + by0;
-          const bool hits = g.tx0 + need_w > 0 && g.tx0 < W && g.ty0 + need_h > 0 && g.ty0 < H;
-          const bool use = hits && need_w <= TL_BW && need_h <= TL_BH && !(P.dbg & 1);
-          g.rows = use ? (need_h <= TL_BH0 ? TL_BH0 : need_h <= TL_BH1 ? TL_BH1 : TL_BH) : 0;
-          const int lox = max(0, -g.tx0), loy = max(0, -g.ty0);
-          g.wxn = use ? max(min(TL_BW - 1, W - 1 - g.tx0) - lox, 0) : 0;
-          g.wyn = use ? max(min(g.rows - 1, H - 1 - g.ty0) - loy, 0) : 0;
-          if (g.wxn == 0 || g.wyn == 0) { g.rows = 0; g.wxn = 0; g.wyn = 0; }
-          g.lox = lox + bx0;
-          g.loy = loy + by0;
-          g.shift = by0 * TL_BW + bx0;
-          s_geo[slot][v] = g;
-        }
-        __syncwarp();
-        if (lane == 0) {
-          const int rows0 = s_geo[slot][0].rows, rows1 = s_geo[slot][1].rows;
-          float* dst0 = tiles + (size_t)slot * SLOT_FLOATS;
-          if (rows0 + rows1 > 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tl_smem_u32(&s_full[slot])),
-                         "r"((uint32_t)((rows0 + rows1) * C * TL_BW * 4)) : "memory");
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-              const int rows = v == 0 ? rows0 : rows1;
-              if (rows > 0) {
-                const CUtensorMap* map = v == 0 ? (rows == TL_BH0 ? &tm0a : rows == TL_BH1 ? &tm0b : &tm0c)
-                                                : (rows == TL_BH0 ? &tm1a : rows == TL_BH1 ? &tm1b : &tm1c);
-                const int tx0 = s_geo[slot][v].tx0, ty0 = s_geo[slot][v].ty0;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                  asm volatile(
-                      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                      ::"r"(tl_smem_u32(dst0 + (v * C + c) * TL_PLANE)), "l"(map), "r"(tl_smem_u32(&s_full[slot])), "r"(tx0),
-                      "r"(ty0), "r"(n * C + c)
-                      : "memory");
-                }
-              }
-            }
-          } else {
-            pt_arrive(&s_full[slot]);
-          }
-        }
-      } else {
-        // ---- y contraction of the tile's node columns with predictor and R0 folded in
-        for (int item = (role - 2) * 32 + lane; item < PT_H * NCOL; item += 32 * PT_YWARPS) {
-          const int r = item / NCOL, j = item - r * NCOL;
-          if (jx0 + j < P.nx) {
-            const int row = min(row0 + r, P.Ho - 1);
-            const int cy = row / SY, ry = row - cy * SY;
-            const float2* nd = P.nodes + (((size_t)n * P.ny + cy) * P.nx + (jx0 + j)) * V;
-            const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SY)].w[ry][0]));
-            const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SY)].w[ry][4]));
-            const float wy_[LAT_TAPS] = {wlo.x, wlo.y, wlo.z, wlo.w, whi.x, whi.y};
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int b = 0; b < LAT_TAPS; ++b) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(nd + (size_t)b * P.nx * V));
-              a0 = fmaf(wy_[b], q.x, a0); a1 = fmaf(wy_[b], q.y, a1); a2 = fmaf(wy_[b], q.z, a2); a3 = fmaf(wy_[b], q.w, a3);
-            }
-            const float cr = (float)((jx0 + j - LAT_LO) * SX - col0), rr = (float)(row - row0);
-            a0 += fmaf(pd[0][0], cr, fmaf(pd[0][1], rr, base[0][0]));
-            a1 += fmaf(pd[0][3], cr, fmaf(pd[0][4], rr, base[0][1]));
-            a2 += fmaf(pd[1][0], cr, fmaf(pd[1][1], rr, base[1][0]));
-            a3 += fmaf(pd[1][3], cr, fmaf(pd[1][4], rr, base[1][1]));
-            *reinterpret_cast<float4*>(&s_ysm[slot][r][j][0]) = make_float4(a0, a1, a2, a3);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) pt_arrive(&s_full[slot]);
-      }
-    }
-    return;
-  }
-
-  // ================= consumers: warp (wx, wy) owns columns wx*32.., rows wy*4.. of the tile =================
-  const int wx = wid & 1, wy = wid >> 1;
-  const int colt = wx * 32 + lane, rt0 = wy * PT_RPT;
-  const unsigned oplane = (unsigned)(P.Ho * P.Wo);
-  u64 lxp[LAT_TAPS] = {0, 0, 0, 0, 0, 0};
-  int prev_bx = -1;
-  for (int t = t_begin, i = 0; t < t_end; t += t_step, ++i) {
-    const int slot = i & 1;
-    pt_wait(&s_full[slot], (i >> 1) & 1);
-    const int n = s_tile[slot][0], bx = s_tile[slot][1], by = s_tile[slot][2];
-    const int col0 = bx * PT_W, row0 = by * PT_H;
-    const int jx0 = col0 / SX;
-    const int col = min(col0 + colt, P.Wo - 1);
-    const bool active = col0 + colt < P.Wo;
-    const int cxi = col / SX, rx = col - cxi * SX, js = cxi - jx0;
-    if (bx != prev_bx) {  // the column's Lagrange weights only change with the strip
-      const float4 wlo = __ldg(reinterpret_cast<const float4*>(&g_lag[lag_idx(SX)].w[rx][0]));
-      const float2 whi = __ldg(reinterpret_cast<const float2*>(&g_lag[lag_idx(SX)].w[rx][4]));
-      lxp[0] = pk2(wlo.x, wlo.x); lxp[1] = pk2(wlo.y, wlo.y); lxp[2] = pk2(wlo.z, wlo.z); lxp[3] = pk2(wlo.w, wlo.w);
-      lxp[4] = pk2(whi.x, whi.x); lxp[5] = pk2(whi.y, whi.y);
-      prev_bx = bx;
-    }
-    const float xt = fmaf(P.stepx, (float)col, -1.0f);
-    float* outp = P.out + (size_t)n * C * oplane;
-    const float* imgv[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) imgv[v] = P.img[v] + (size_t)n * C * H * W;
-    const int n_all = s_cnt[slot][0], n0 = s_cnt[slot][1];
-    const float4* near_list = s_near[slot];
-    int r0x[V], r0y[V], g_lox[V], g_wxn[V], g_loy[V], g_wyn[V];
-    uint32_t tbase[V];
-    const uint32_t tbase0 = tl_smem_u32(tiles + (size_t)slot * SLOT_FLOATS);
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      r0x[v] = s_r0[slot][v][0]; r0y[v] = s_r0[slot][v][1];
-      g_lox[v] = s_geo[slot][v].lox; g_wxn[v] = s_geo[slot][v].wxn; g_loy[v] = s_geo[slot][v].loy; g_wyn[v] = s_geo[slot][v].wyn;
-      tbase[v] = tbase0 + (uint32_t)((v * (C * TL_PLANE) - s_geo[slot][v].shift) * 4);
-    }
-    unsigned cand = 0;
-    const bool cull = n_all <= 32;
-    if (n_all > 0) {
-      if (cull) {
-        bool keep = false;
-        if (lane < n_all) {
-          const float4 c = near_list[lane];
-          const float wx_lo = fmaf(P.stepx, (float)min(col0 + wx * 32, P.Wo - 1), -1.0f);
-          const float wx_hi = fmaf(P.stepx, (float)min(col0 + wx * 32 + 31, P.Wo - 1), -1.0f);
-          const float y_lo = fmaf(P.stepy, (float)min(row0 + rt0, P.Ho - 1), -1.0f);
-          const float y_hi = fmaf(P.stepy, (float)min(row0 + rt0 + PT_RPT - 1, P.Ho - 1), -1.0f);
-          const float ddx = fmaxf(fmaxf(wx_lo - c.x, c.x - wx_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
-          keep = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
-        }
-        cand = __ballot_sync(FULL, keep);
-      } else {
-        cand = FULL;
-      }
-    }
-#pragma unroll 2
-    for (int ii = 0; ii < PT_RPT; ++ii) {
-      const int r = rt0 + ii, row = row0 + r;
-      if (row >= P.Ho) break;  // warp-uniform
-      u64 acc0, acc1;
-      {
-        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(&s_ysm[slot][r][js][0]);
-        acc0 = fmul2(q.x, lxp[0]);
-        acc1 = fmul2(q.y, lxp[0]);
-      }
-#pragma unroll
-      for (int a = 1; a < LAT_TAPS; ++a) {
-        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(&s_ysm[slot][r][js + a][0]);
-        acc0 = ffma2(q.x, lxp[a], acc0);
-        acc1 = ffma2(q.y, lxp[a], acc1);
-      }
-      float px[V], py[V];
-      upk2(acc0, px[0], py[0]);
-      upk2(acc1, px[1], py[1]);
-      if (cand != 0u) {
-        const float yt = fmaf(P.stepy, (float)row, -1.0f);
-        unsigned m = cull ? cand : 0u;
-        int kk = 0;
-#pragma unroll 1
-        while (cull ? (m != 0u) : (kk < n_all)) {
-          int k;
-          if (cull) { k = __ffs(m) - 1; m &= m - 1; } else { k = kk++; }
-          const float4 c = near_list[k];
-          const float dx = xt - c.x, dy = yt - c.y;
-          const float s = fminf(fmaf(dy, dy, dx * dx), P.R2);
-          const float psi = fmaf(s, lg2_approx(s + 1e-6f), -blend_poly(s, P.R2, P.q0, P.q1, P.q2, P.q3));
-          if (k < n0) { px[0] = fmaf(c.z, psi, px[0]); py[0] = fmaf(c.w, psi, py[0]); }
-          else { px[1] = fmaf(c.z, psi, px[1]); py[1] = fmaf(c.w, psi, py[1]); }
-        }
-      }
-      float res[V][C];
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const int xi = __float2int_rd(px[v]), yi = __float2int_rd(py[v]);
-        const float fx = px[v] - (float)xi, fy = py[v] - (float)yi;
-        const bool ok = (unsigned)(xi - g_lox[v]) < (unsigned)g_wxn[v] && (unsigned)(yi - g_loy[v]) < (unsigned)g_wyn[v];
-        const unsigned okm = __ballot_sync(FULL, ok);
-        if (okm == FULL) {
-          const float gx = 1.0f - fx, gy = 1.0f - fy;
-          const u64 wA = pk2(gx * gy, fx * gy), wB = pk2(gx * fy, fx * fy);
-          const uint32_t ad = tbase[v] + (uint32_t)(yi * (TL_BW * 4) + xi * 4);
-          tile_taps<0>(ad, wA, wB, res[v][0]);
-          tile_taps<TL_PLANE * 4>(ad, wA, wB, res[v][1]);
-          tile_taps<2 * TL_PLANE * 4>(ad, wA, wB, res[v][2]);
-        } else {
-          const bool inimg = (unsigned)(xi + r0x[v]) < (unsigned)(W - 1) && (unsigned)(yi + r0y[v]) < (unsigned)(H - 1);
-          const bool slow = __any_sync(FULL, inimg && !ok);
-          const bool use = slow ? inimg : ok;
-          res[v][0] = res[v][1] = res[v][2] = 0.0f;
-          if (__any_sync(FULL, use)) {
-            const float fxs = use ? fx : 0.0f, gxs = use ? 1.0f - fx : 0.0f, fys = use ? fy : 0.0f, gys = 1.0f - fys;
-            const u64 wA = pk2(gxs * gys, fxs * gys), wB = pk2(gxs * fys, fxs * fys);
-            if (!slow) {
-              const uint32_t ad = use ? tbase[v] + (uint32_t)(yi * (TL_BW * 4) + xi * 4) : tbase0;
-              tile_taps<0>(ad, wA, wB, res[v][0]);
-              tile_taps<TL_PLANE * 4>(ad, wA, wB, res[v][1]);
-              tile_taps<2 * TL_PLANE * 4>(ad, wA, wB, res[v][2]);
-              if (!use) res[v][0] = res[v][1] = res[v][2] = 0.0f;
-            } else {
-              const float* p = imgv[v] + (use ? (size_t)(yi + r0y[v]) * W + (xi + r0x[v]) : (size_t)0);
-              const size_t iplane = (size_t)H * W;
-#pragma unroll
-              for (int c = 0; c < C; ++c) {
-                const u64 top = pk2(__ldg(p + c * iplane), __ldg(p + c * iplane + 1));
-                const u64 bot = pk2(__ldg(p + c * iplane + W), __ldg(p + c * iplane + W + 1));
-                float lo, hi;
-                upk2(ffma2(bot, wB, fmul2(top, wA)), lo, hi);
-                res[v][c] = lo + hi;
-              }
-            }
-          }
-        }
-      }
-      if (active) {
-        const unsigned opix = (unsigned)(row * P.Wo + col);
-        const u64 A = pk2(res[0][0], res[0][1]), B = pk2(res[1][0], res[1][1]);
-        float s0, s1, q0, q1;
-        upk2(fadd2(fadd2(A, B), pk2(1e-6f, 1e-6f)), s0, s1);
-        upk2(ffma2(B, B, fmul2(A, A)), q0, q1);
-        __stcs(const_cast<float*>(f32_at(outp, opix)), q0 * rcp_approx(s0));
-        __stcs(const_cast<float*>(f32_at(outp, opix + oplane)), q1 * rcp_approx(s1));
-        __stcs(const_cast<float*>(f32_at(outp, opix + 2 * oplane)), blend_avg_fast(res[0][2], res[1][2]));
-      }
-    }
-    // this warp is done with the slot (its taps are in registers / stored): hand it back to the producers
-    __syncwarp();
-    if (lane == 0) pt_arrive(&s_empty[slot]);
-  }
-}
-
-#include "tps_lat3.cuh"
-#include "tps_lat4.cuh"
-
 static inline float linstep(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 
 // lattice configuration: spacing (SX, SY) in canvas pixels and near radius R (normalised)
@@ -1786,34 +961,6 @@ size_t tps_lattice_workspace_floats(int bn, int Ho, int Wo) {
   return (size_t)bn * nx * ny * 2;
 }
 
-// The tile kernel needs TMA-addressable frames (16-byte aligned base and row pitch) and 32-bit output indexing.
-static bool tile_path_ok(const WarpParams& P, int nframes) {
-  // Opt-in (SS2_TPS_TILE=1): measured on B200 (round 1, 720p) the staged kernel runs 17-19 us per frame against
-  // 12.8 us of tps_warp_lattice_kernel: its per-tile prologue + TMA wait leave the SM under-occupied (2-3 CTAs), and
-  // tiles whose footprint exceeds the box fall back to global loads.  DESIGN.md section 4.1 has the numbers.
-  const char* e = getenv("SS2_TPS_TILE");
-  if (!e || atoi(e) == 0) return false;
-  if ((P.W & 3) || ((uintptr_t)P.img[0] & 15) || ((uintptr_t)P.img[1] & 15)) return false;
-  if (P.W < 2 || P.H < 2 || (double)P.Ho * P.Wo * 3.0 > 2.0e9 || (double)nframes * 3.0 > 2.0e9) return false;
-  return true;
-}
-
-// frames of one view as a 3-D tensor {W, H, nframes*3 planes}; box = TL_BW x box_rows elements of one plane, zero fill
-static bool make_img_map(CUtensorMap* map, const float* base, int W, int H, int planes, int box_rows) {
-  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ss2_tensormap_encode_fn());
-  if (!fn) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
-  cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
-  cuuint32_t box[3] = {TL_BW, (cuuint32_t)box_rows, 1};
-  cuuint32_t est[3] = {1, 1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, est,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int V, int C, bool BLEND>
 static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, float* d_nodes, cudaStream_t st) {
   const LatticeConfig cfg = lattice_config(P.Ho, P.Wo);
@@ -1837,105 +984,11 @@ static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, flo
     const int S[4] = {6, 8, 12, 16};
     for (int i = 0; i < 4; ++i) lagrange_table(S[i], &t[i]);
     SS2_CUDA(ctx, cudaMemcpyToSymbol(c_lag, t, sizeof(t)));
-    SS2_CUDA(ctx, cudaMemcpyToSymbol(g_lag, t, sizeof(t)));
-    LagrangePairs tp[4];
-    for (int i = 0; i < 4; ++i)
-      for (int k = 0; k < 16; ++k)
-        for (int j = 0; j < LAT_TAPS; ++j) tp[i].w[k][j] = make_float2(t[i].w[k][j], t[i].w[k][j]);
-    SS2_CUDA(ctx, cudaMemcpyToSymbol(c_lagp, tp, sizeof(tp)));
     ctx->lag_tables_ready = true;
   }
   const int nnodes = P.nx * P.ny;
-  // production kernels: fused NORMAL resample + blend of two views, 720p / 1080p sources.
-  // SS2_TPS_L3: unset / 4 = tps_warp_lat4_kernel (one view per warp), 3 = tps_warp_lat3_kernel (both views per
-  // thread), 0 = the generic tps_warp_lattice_kernel below
-  {
-    const char* e3 = getenv("SS2_TPS_L3");
-    const char* et = getenv("SS2_TPS_TILE");
-    const int which = e3 ? atoi(e3) : 4;
-    const int sz = (P.W == 1280 && P.H == 720) ? 1 : (P.W == 1920 && P.H == 1080) ? 2 : 0;
-    if (BLEND && V == 2 && C == 3 && mode == SS2_MODE_NORMAL && sz != 0 && which != 0 && !(et && atoi(et) != 0) &&
-        (double)P.Ho * P.Wo * 3.0 < 2.0e9) {
-      if (which == 3) {
-        tps_nodes_kernel<2, 1><<<dim3(cdiv(nnodes, 128), 2, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY);
-        SS2_LAUNCH_CHECK(ctx);
-        dim3 g3(cdiv(P.Wo, L3_THREADS), cdiv(P.Ho, cfg.SY * L3_NCELL), nframes);
-#define L3_CASE(SXV, SYV)                                                                          \
-        if (cfg.SX == SXV && cfg.SY == SYV) {                                                        \
-          if (sz == 1) tps_warp_lat3_kernel<SXV, SYV, 1280, 720><<<g3, L3_THREADS, 0, st>>>(P);      \
-          else tps_warp_lat3_kernel<SXV, SYV, 1920, 1080><<<g3, L3_THREADS, 0, st>>>(P);             \
-        }
-        L3_CASE(16, 8) L3_CASE(16, 6) L3_CASE(12, 8) L3_CASE(12, 6) L3_CASE(8, 8) L3_CASE(8, 6)
-#undef L3_CASE
-      } else {
-        tps_nodes_kernel<2, 0><<<dim3(cdiv(nnodes, 128), 2, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY);
-        SS2_LAUNCH_CHECK(ctx);
-        dim3 g4(cdiv(P.Wo, L4_COLS), cdiv(P.Ho, cfg.SY * L4_NCELL), nframes);
-#define L4_CASE(SXV, SYV)                                                                          \
-        if (cfg.SX == SXV && cfg.SY == SYV) {                                                        \
-          if (sz == 1) tps_warp_lat4_kernel<SXV, SYV, 1280, 720><<<g4, L4_THREADS, 0, st>>>(P);      \
-          else tps_warp_lat4_kernel<SXV, SYV, 1920, 1080><<<g4, L4_THREADS, 0, st>>>(P);             \
-        }
-        L4_CASE(16, 8) L4_CASE(16, 6) L4_CASE(12, 8) L4_CASE(12, 6) L4_CASE(8, 8) L4_CASE(8, 6)
-#undef L4_CASE
-      }
-      SS2_LAUNCH_CHECK(ctx);
-      return SS2_OK;
-    }
-  }
-  tps_nodes_kernel<V, 0><<<dim3(cdiv(nnodes, 128), V, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY);
+  tps_nodes_kernel<V><<<dim3(cdiv(nnodes, 128), V, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY);
   SS2_LAUNCH_CHECK(ctx);
-  { const char* e = getenv("SS2_TILE_DBG"); P.dbg = e ? atoi(e) : 0; }
-  if (BLEND && V == 2 && C == 3 && mode == SS2_MODE_NORMAL && tile_path_ok(P, nframes)) {
-    CUtensorMap m[2][3];
-    bool maps = true;
-    for (int v = 0; v < 2; ++v)
-      for (int h = 0; h < 3; ++h)
-        maps = maps && make_img_map(&m[v][h], P.img[v], P.W, P.H, nframes * 3, h == 0 ? TL_BH0 : h == 1 ? TL_BH1 : TL_BH);
-    if (maps) {
-      const char* te = getenv("SS2_TPS_TILE");
-      if (te && atoi(te) == 2) {
-        // persistent, warp-specialised variant: one CTA per SM walks a contiguous range of tiles
-        const int ntx = cdiv(P.Wo, PT_W), nty = cdiv(P.Ho, PT_H);
-        const long long total = (long long)ntx * nty * nframes;
-        int nsm = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-        const int pgrid = (int)(total < nsm ? total : nsm);
-        if (total < 2000000000LL) {
-#define PTILE_CASE(SXV, SYV)                                                                                    \
-          if (cfg.SX == SXV && cfg.SY == SYV) {                                                                 \
-            static bool attr_dev[16] = {false};                                                                 \
-            bool& attr = attr_dev[ctx->device & 15];                                                            \
-            if (!attr) {                                                                                        \
-              SS2_CUDA(ctx, cudaFuncSetAttribute(tps_warp_ptile_kernel<SXV, SYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES)); \
-              attr = true;                                                                                      \
-            }                                                                                                   \
-            tps_warp_ptile_kernel<SXV, SYV><<<pgrid, PT_THREADS, PT_SMEM_BYTES, st>>>(m[0][0], m[0][1], m[0][2], m[1][0], m[1][1], m[1][2], P, ntx, nty, (int)total); \
-          }
-          PTILE_CASE(16, 8) PTILE_CASE(16, 6) PTILE_CASE(12, 8) PTILE_CASE(12, 6) PTILE_CASE(8, 8) PTILE_CASE(8, 6)
-#undef PTILE_CASE
-          SS2_LAUNCH_CHECK(ctx);
-          return SS2_OK;
-        }
-      }
-      dim3 tgrid(cdiv(P.Wo, TL_W), cdiv(P.Ho, TL_H), nframes);
-#define TILE_CASE(SXV, SYV)                                                                                     \
-      if (cfg.SX == SXV && cfg.SY == SYV) {                                                                     \
-        static bool attr_dev[16] = {false};                                                                     \
-        bool& attr = attr_dev[ctx->device & 15];                                                                \
-        if (!attr) {                                                                                            \
-          SS2_CUDA(ctx, cudaFuncSetAttribute(tps_warp_tile_kernel<SXV, SYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM_BYTES)); \
-          SS2_CUDA(ctx, cudaFuncSetAttribute(tps_warp_tile_kernel<SXV, SYV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
-          attr = true;                                                                                          \
-        }                                                                                                       \
-        tps_warp_tile_kernel<SXV, SYV><<<tgrid, TL_THREADS, TL_SMEM_BYTES, st>>>(m[0][0], m[0][1], m[0][2], m[1][0], m[1][1], m[1][2], P);                    \
-      }
-      TILE_CASE(16, 8) TILE_CASE(16, 6) TILE_CASE(12, 8) TILE_CASE(12, 6) TILE_CASE(8, 8) TILE_CASE(8, 6)
-#undef TILE_CASE
-      SS2_LAUNCH_CHECK(ctx);
-      return SS2_OK;
-    }
-  }
   dim3 grid(cdiv(P.Wo, LAT_THREADS), cdiv(P.Ho, cfg.SY * LAT_NCELL), nframes);
   // source-size specialisations of the production (fused, NORMAL) kernel: 720p and 1080p
   const int spec = (BLEND && mode == SS2_MODE_NORMAL) ? ((P.W == 1280 && P.H == 720) ? 1 : (P.W == 1920 && P.H == 1080) ? 2 : 0) : 0;
@@ -1966,6 +1019,8 @@ int tps_warp_launch(ss2_ctx* ctx, const float* d_U, const float* d_source, const
   P.half_h = mode == SS2_MODE_NORMAL ? 0.5f * H : 0.5f * (H - 1);
   if (tps == SS2_TPS_LATTICE && d_aux && d_nodes && C == 3 && tps_lattice_supported(Ho, Wo))
     return lattice_launch<1, 3, false>(ctx, P, bn, mode, d_nodes, st);
+  if (tps == SS2_TPS_LATTICE && d_aux && d_nodes && C == 4 && tps_lattice_supported(Ho, Wo))   // image + LINEAR's mask
+    return lattice_launch<1, 4, false>(ctx, P, bn, mode, d_nodes, st);
   dim3 grid(cdiv(Wo, TX), cdiv(Ho, TILE_H), bn), block(TX, TY);
 #define WARP_CASE(CC)                                                                              \
   if (C == CC) {                                                                                   \

@@ -1,7 +1,7 @@
 """Sequence glue of the hot path (the functions the reference keeps inside its driver script,
 Full_model_inference/Codes/test_online_tra.py) on top of libss2.
 
-  get_stable_sqe(...)      same signature/return as test_online_tra.py:96 (AVERAGE fusion)
+  get_stable_sqe(...)      same signature/return as test_online_tra.py:96 (AVERAGE and LINEAR fusion)
   stream_meshes(...)       test_online_tra.py:284-392 for a device-resident stream
   stitch_stream(...)       device-resident whole stream -> fused frames [n,3,Ho,Wo]
   stitch_stream_host(...)  the same through HOST buffers in one C call (H2D + D2H inside)
@@ -44,10 +44,13 @@ def canvas_size(minmax_host):
     return h.value, w.value
 
 
-def stable_frames(hr1, hr2, mesh1, mesh2, minmax_host, mode="NORMAL", tps=None, out=None):
+def stable_frames(hr1, hr2, mesh1, mesh2, minmax_host, mode="NORMAL", tps=None, out=None, fusion_mode="AVERAGE"):
     """The get_stable_sqe loop for n frames given the (global) canvas: hr [n,3,H,W] CUDA,
-    meshes [n,7,9,2] @480x360 -> fused [n,3,Ho,Wo]."""
+    meshes [n,7,9,2] @480x360 -> fused [n,3,Ho,Wo]; fusion_mode 'AVERAGE' (test_online_tra.py:142) or 'LINEAR'
+    (:143-150)."""
     from .utils import torch_tps_transform as tt
+    if fusion_mode not in ("AVERAGE", "LINEAR"):
+        raise ValueError("fusion_mode must be 'AVERAGE' or 'LINEAR'")
     ctx = _lib.context()
     hr1, hr2 = _lib.dev_f32(hr1), _lib.dev_f32(hr2)
     m1 = _lib.dev_f32(mesh1).reshape(-1, 7, 9, 2)
@@ -57,10 +60,26 @@ def stable_frames(hr1, hr2, mesh1, mesh2, minmax_host, mode="NORMAL", tps=None, 
     if out is None:
         out = torch.empty(n, 3, Ho, Wo, device=hr1.device, dtype=torch.float32)
     mm = (ctypes.c_float * 4)(*[float(v) for v in minmax_host])
-    ctx.check(ctx.lib.ss2_stable_frames(ctx.handle, _lib.ptr(hr1), _lib.ptr(hr2), _lib.ptr(m1), _lib.ptr(m2), n, H, W,
-                                        mm, _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps, _lib.ptr(out),
-                                        _lib.cur_stream()))
+    fn = ctx.lib.ss2_stable_frames if fusion_mode == "AVERAGE" else ctx.lib.ss2_stable_frames_linear
+    ctx.check(fn(ctx.handle, _lib.ptr(hr1), _lib.ptr(hr2), _lib.ptr(m1), _lib.ptr(m2), n, H, W,
+                 mm, _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps, _lib.ptr(out), _lib.cur_stream()))
     return out
+
+
+def linear_blender(ref, tgt, ref_m, tgt_m, mask=False):
+    """Drop-in for the driver's linear_blender (test_online_tra.py:34-58): ref, tgt [n,3,Ho,Wo]; ref_m, tgt_m
+    [n,1,Ho,Wo] -> stitched [n,3,Ho,Wo] (mask=True: mask1 [n,1,Ho,Wo]).  Masks are thresholded at 0.5 (see
+    ss2_linear_blend)."""
+    ctx = _lib.context()
+    ref, tgt, ref_m, tgt_m = (_lib.dev_f32(t) for t in (ref, tgt, ref_m, tgt_m))
+    n, C, Ho, Wo = ref.shape
+    if C != 3 or tgt.shape != ref.shape or ref_m.shape != (n, 1, Ho, Wo) or tgt_m.shape != (n, 1, Ho, Wo):
+        raise ValueError("linear_blender takes [n,3,Ho,Wo] images and [n,1,Ho,Wo] masks")
+    out = None if mask else torch.empty_like(ref)
+    m1 = torch.empty_like(ref_m) if mask else None
+    ctx.check(ctx.lib.ss2_linear_blend(ctx.handle, _lib.ptr(ref), _lib.ptr(tgt), 3 * Ho * Wo, _lib.ptr(ref_m), _lib.ptr(tgt_m),
+                                       Ho * Wo, n, Ho, Wo, _lib.ptr(out), _lib.ptr(m1), _lib.cur_stream()))
+    return m1 if mask else out
 
 
 def three_view_meshes(w12m1, w12m2, w23m1, w23m2, img_h, img_w):
@@ -78,9 +97,10 @@ def three_view_meshes(w12m1, w12m2, w23m1, w23m2, img_h, img_w):
     return outs[0], outs[1], outs[2], canvas
 
 
-def three_view_frames(imgs1, imgs2, imgs3, mesh1, middle, mesh3, canvas_host, mode="NORMAL", tps=None):
-    """The three-image warp + AVERAGE fusion loop (test_online_tra_threeview.py:461-490): images [n,3,H,W] CUDA
-    per view, meshes from three_view_meshes, canvas (4 host floats) -> fused [n,3,Ho,Wo]."""
+def three_view_frames(imgs1, imgs2, imgs3, mesh1, middle, mesh3, canvas_host, mode="NORMAL", tps=None,
+                      fusion_mode="AVERAGE"):
+    """The three-image warp + fusion loop (test_online_tra_threeview.py:461-503, AVERAGE or LINEAR): images
+    [n,3,H,W] CUDA per view, meshes from three_view_meshes, canvas (4 host floats) -> fused [n,3,Ho,Wo]."""
     from .utils import torch_tps_transform as tt
     ctx = _lib.context()
     a, b, c = _lib.dev_f32(imgs1), _lib.dev_f32(imgs2), _lib.dev_f32(imgs3)
@@ -89,38 +109,39 @@ def three_view_frames(imgs1, imgs2, imgs3, mesh1, middle, mesh3, canvas_host, mo
     Ho, Wo = int(cv[3]), int(cv[2])
     out = torch.empty(n, 3, Ho, Wo, device=a.device, dtype=torch.float32)
     hc = (ctypes.c_float * 4)(*cv)
-    ctx.check(ctx.lib.ss2_three_view_frames(ctx.handle, _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(_lib.dev_f32(mesh1)),
-                                            _lib.ptr(_lib.dev_f32(middle)), _lib.ptr(_lib.dev_f32(mesh3)), n, H, W, hc,
-                                            _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps, _lib.ptr(out),
-                                            _lib.cur_stream()))
+    if fusion_mode not in ("AVERAGE", "LINEAR"):
+        raise ValueError("fusion_mode must be 'AVERAGE' or 'LINEAR'")
+    fn = ctx.lib.ss2_three_view_frames if fusion_mode == "AVERAGE" else ctx.lib.ss2_three_view_frames_linear
+    ctx.check(fn(ctx.handle, _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(_lib.dev_f32(mesh1)),
+                 _lib.ptr(_lib.dev_f32(middle)), _lib.ptr(_lib.dev_f32(mesh3)), n, H, W, hc,
+                 _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps, _lib.ptr(out), _lib.cur_stream()))
     return out
 
 
-def three_view_stable(img1_list, img2_list, img3_list, w12m1, w12m2, w23m1, w23m2, warp_mode="NORMAL"):
-    """Drop-in for the tail of test_online_tra_threeview.py's test() (:345-505, AVERAGE fusion): image lists of
+def three_view_stable(img1_list, img2_list, img3_list, w12m1, w12m2, w23m1, w23m2, warp_mode="NORMAL",
+                      fusion_mode="AVERAGE"):
+    """Drop-in for the tail of test_online_tra_threeview.py's test() (:345-505, AVERAGE or LINEAR fusion): image lists of
     [1,3,H,W] fp32 0..255, smooth meshes [1,N,7,9,2] of the two pairs -> list of N CPU tensors [3,Ho,Wo]."""
     a = torch.cat([_lib.dev_f32(t) for t in img1_list], 0)
     b = torch.cat([_lib.dev_f32(t) for t in img2_list], 0)
     c = torch.cat([_lib.dev_f32(t) for t in img3_list], 0)
     _, _, H, W = a.shape
     m1, mid, m3, canvas = three_view_meshes(w12m1, w12m2, w23m1, w23m2, H, W)
-    fused = three_view_frames(a, b, c, m1, mid, m3, canvas.cpu().tolist(), warp_mode)
+    fused = three_view_frames(a, b, c, m1, mid, m3, canvas.cpu().tolist(), warp_mode, fusion_mode=fusion_mode)
     host = fused.cpu()
     return [host[k] for k in range(host.shape[0])]
 
 
 def get_stable_sqe(img1_list, img2_list, smooth_mesh1, smooth_mesh2, warp_mode="NORMAL", fusion_mode="AVERAGE"):
-    """Drop-in for test_online_tra.py:96-154 (AVERAGE fusion): lists of [1,3,H,W] fp32 0..255
+    """Drop-in for test_online_tra.py:96-154 (AVERAGE and LINEAR fusion): lists of [1,3,H,W] fp32 0..255
     frames, smooth meshes [1,N,7,9,2] -> (list of [Ho,Wo,3] numpy frames, out_width, out_height)."""
-    if fusion_mode != "AVERAGE":
-        raise NotImplementedError("LINEAR fusion is SURVEY.md 8(f) 'next #1'; this path implements AVERAGE")
     hr1 = torch.cat([_lib.dev_f32(t) for t in img1_list], 0)
     hr2 = torch.cat([_lib.dev_f32(t) for t in img2_list], 0)
     _, _, H, W = hr2.shape
     m1 = _lib.dev_f32(smooth_mesh1).reshape(-1, 7, 9, 2)
     m2 = _lib.dev_f32(smooth_mesh2).reshape(-1, 7, 9, 2)
     mm = canvas_minmax(m1, m2, H, W).cpu().tolist()
-    fused = stable_frames(hr1, hr2, m1, m2, mm, warp_mode)
+    fused = stable_frames(hr1, hr2, m1, m2, mm, warp_mode, fusion_mode=fusion_mode)
     Ho, Wo = fused.shape[2:]
     host = fused.permute(0, 2, 3, 1).contiguous().cpu().numpy()
     return ([host[k] for k in range(host.shape[0])], torch.tensor(Wo, dtype=torch.int32),
@@ -207,6 +228,85 @@ def stitch_stream_host(spatial_net, temporal_net, smooth_net, lr1, lr2, hr1, hr2
                                              n, H, W, _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps,
                                              _lib.ptr(out), out.numel(), ctypes.byref(ho), ctypes.byref(wo),
                                              _lib.ptr(m1), _lib.ptr(m2)))
+    if want_meshes:
+        return ho.value, wo.value, m1, m2
+    return ho.value, wo.value
+
+
+# ------------------------------------------------------------------------------------------
+# uint8 host edges (test_online_tra.py:252-264 before the networks, :152,414 before the video writer)
+# ------------------------------------------------------------------------------------------
+def load_frames_u8(frames_u8, want_hr=True, want_lr=True):
+    """frames [n,H,W,3] uint8 (cv2.imread layout, BGR; CUDA or host) -> (hr [n,3,H,W] fp32 0..255,
+    lr [n,3,360,480] fp32 in [-1,1] = cv2.resize(INTER_LINEAR)/127.5-1, bit-exact), on the device."""
+    ctx = _lib.context()
+    u = torch.as_tensor(frames_u8)
+    if u.dtype != torch.uint8 or u.dim() != 4 or u.shape[3] != 3:
+        raise ValueError("frames must be uint8 [n,H,W,3]")
+    u = u.cuda().contiguous()
+    n, H, W, _ = u.shape
+    hr = torch.empty(n, 3, H, W, device=u.device, dtype=torch.float32) if want_hr else None
+    lr = torch.empty(n, 3, 360, 480, device=u.device, dtype=torch.float32) if want_lr else None
+    ctx.check(ctx.lib.ss2_load_frames_u8(ctx.handle, _lib.ptr(u), n, H, W, _lib.ptr(hr), _lib.ptr(lr), _lib.cur_stream()))
+    return hr, lr
+
+
+def frames_to_u8(fused):
+    """fused [n,3,Ho,Wo] fp32 CUDA -> [n,Ho,Wo,3] uint8 CUDA (transpose + astype(uint8) of test_online_tra.py:152,414)."""
+    ctx = _lib.context()
+    f = _lib.dev_f32(fused)
+    n, C, Ho, Wo = f.shape
+    if C != 3:
+        raise ValueError("fused frames must be [n,3,Ho,Wo]")
+    out = torch.empty(n, Ho, Wo, 3, device=f.device, dtype=torch.uint8)
+    ctx.check(ctx.lib.ss2_frames_to_u8(ctx.handle, _lib.ptr(f), n, Ho, Wo, _lib.ptr(out), _lib.cur_stream()))
+    return out
+
+
+def _check_u8_host(*ts):
+    for t in ts:
+        if t.is_cuda or t.dtype != torch.uint8 or not t.is_contiguous():
+            raise ValueError("the uint8 host interface takes contiguous uint8 HOST tensors")
+
+
+def stitch_stream_host_u8_async(spatial_net, temporal_net, smooth_net, slot, bgr1, bgr2, out, mode="NORMAL", tps=None):
+    """ss2_stitch_stream_host_u8_async: bgr1, bgr2 [n,H,W,3] uint8 host frames (as cv2.imread returns them), `out` a
+    flat uint8 host buffer for n*Ho*Wo*3 bytes; returns (Ho, Wo) once the chunk's work and D2H copies are enqueued."""
+    from .utils import torch_tps_transform as tt
+    ctx = _lib.context()
+    _sync_nets(ctx, spatial_net, temporal_net, smooth_net)
+    _check_u8_host(bgr1, bgr2, out)
+    n, H, W, _ = bgr1.shape
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    ctx.check(ctx.lib.ss2_stitch_stream_host_u8_async(ctx.handle, int(slot), _lib.ptr(bgr1), _lib.ptr(bgr2), n, H, W,
+                                                      _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps,
+                                                      _lib.ptr(out), out.numel(), ctypes.byref(ho), ctypes.byref(wo),
+                                                      None, None))
+    return ho.value, wo.value
+
+
+def stitch_stream_host_u8_prefetch(slot, bgr1, bgr2):
+    ctx = _lib.context()
+    _check_u8_host(bgr1, bgr2)
+    n, H, W, _ = bgr1.shape
+    ctx.check(ctx.lib.ss2_stitch_stream_host_u8_prefetch(ctx.handle, int(slot), _lib.ptr(bgr1), _lib.ptr(bgr2), n, H, W))
+
+
+def stitch_stream_host_u8(spatial_net, temporal_net, smooth_net, bgr1, bgr2, out, mode="NORMAL", tps=None,
+                          want_meshes=False):
+    """Blocking form: uint8 frames in, uint8 stitched frames out ([n,Ho,Wo,3] inside `out`); returns (Ho, Wo)
+    [, smooth_mesh1, smooth_mesh2]."""
+    from .utils import torch_tps_transform as tt
+    ctx = _lib.context()
+    _sync_nets(ctx, spatial_net, temporal_net, smooth_net)
+    _check_u8_host(bgr1, bgr2, out)
+    n, H, W, _ = bgr1.shape
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    m1 = torch.empty(n, 7, 9, 2) if want_meshes else None
+    m2 = torch.empty(n, 7, 9, 2) if want_meshes else None
+    ctx.check(ctx.lib.ss2_stitch_stream_host_u8(ctx.handle, _lib.ptr(bgr1), _lib.ptr(bgr2), n, H, W, _lib.MODE[mode],
+                                                tt.DEFAULT_TPS if tps is None else tps, _lib.ptr(out), out.numel(),
+                                                ctypes.byref(ho), ctypes.byref(wo), _lib.ptr(m1), _lib.ptr(m2)))
     if want_meshes:
         return ho.value, wo.value, m1, m2
     return ho.value, wo.value

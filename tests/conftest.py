@@ -29,3 +29,9 @@ def golden_stream():
 def golden_threeview():
     import numpy as np
     return dict(np.load(os.path.join(GOLDEN, "threeview.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_linear():
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "linear.npz")))

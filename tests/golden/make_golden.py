@@ -108,7 +108,14 @@ def threeview_case(m):
           "warp23_mesh1": w23m1.clone(), "warp23_mesh2": w23m2.clone()}
     with contextlib.redirect_stdout(io.StringIO()):
         exec(compile(body, path, "exec"), ns)
-    out = {"in_w12m1": w12m1, "in_w12m2": w12m2, "in_w23m1": w23m1, "in_w23m2": w23m2,
+    # the same source slice once more with --fusion_mode LINEAR (:492-503)
+    ns_lin = dict(ns)
+    ns_lin.update({"args": argparse.Namespace(fusion_mode="LINEAR", warp_mode="NORMAL"), "linear_blender": D.linear_blender,
+                   "warp12_mesh1": w12m1.clone(), "warp12_mesh2": w12m2.clone(),
+                   "warp23_mesh1": w23m1.clone(), "warp23_mesh2": w23m2.clone()})
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(body, path, "exec"), ns_lin)
+    out = {"frames_linear": torch.stack(ns_lin["stable_list"], 0), "in_w12m1": w12m1, "in_w12m2": w12m2, "in_w23m1": w23m1, "in_w23m2": w23m2,
            "mesh1": ns["warp12_mesh1"], "middle": ns["middle_mesh"], "mesh3": ns["warp23_mesh2"],
            "canvas": torch.stack([ns["width_min"], ns["height_min"], ns["out_width"], ns["out_height"]]),
            "frames": torch.stack(ns["stable_list"], 0)}
@@ -187,6 +194,52 @@ def stream_case(m):
     return {k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
 
 
+def linear_inputs():
+    """Seeded inputs of the clean-mask LINEAR case: two overlapping views on a 72x150 canvas with exact 0/1 masks
+    (sheared quadrilaterals, so the overlap is not axis aligned) and smooth 3-channel images."""
+    g = torch.Generator().manual_seed(77)
+    Ho, Wo = 72, 150
+    yy, xx = torch.meshgrid(torch.arange(Ho, dtype=torch.float32), torch.arange(Wo, dtype=torch.float32), indexing="ij")
+    m1 = ((xx + 0.15 * yy < 95) & (xx - 0.1 * yy > 4) & (yy > 2) & (yy < 66)).float()[None, None]
+    m2 = ((xx - 0.12 * yy > 52) & (xx + 0.05 * yy < 146) & (yy > 6) & (yy < 70)).float()[None, None]
+    img = lambda: 127.5 * (1 + torch.tanh(torch.nn.functional.interpolate(torch.randn(1, 3, 5, 9, generator=g), size=(Ho, Wo), mode="bicubic")))  # noqa: E731
+    return img() * m1, img() * m2, m1, m2
+
+
+def linear_case(m):
+    """LINEAR fusion (test_online_tra.py:34-58,143-150): (i) the reference's linear_blender on exact 0/1 masks, (ii) its
+    get_stable_sqe(..., 'LINEAR') on the small stream's reference meshes; plus the centroids it uses (over
+    torch.nonzero of the warped masks, i.e. including the out-of-image rounding residues) next to the centroids of
+    the masks thresholded at 0.5 - the data behind DESIGN.md's note on that mode."""
+    D = m["test_online_tra"]
+    out = {}
+    ref, tgt, m1, m2 = linear_inputs()
+    out["clean_out"] = D.linear_blender(ref, tgt, m1, m2)
+    out["clean_mask1"] = D.linear_blender(ref, tgt, m1, m2, mask=True)
+    gs = dict(np.load(os.path.join(HERE, "stream_small.npz")))
+    N, H, W = STREAM_N, STREAM_H, STREAM_W
+    hr = [[O.synth_frame(t, v, H, W) for t in range(N)] for v in range(2)]
+    S1, S2 = torch.from_numpy(gs["smooth_mesh1"]), torch.from_numpy(gs["smooth_mesh2"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        frames, ow, oh = D.get_stable_sqe(hr[0][:2], hr[1][:2], S1[:, :2], S2[:, :2], warp_mode="NORMAL", fusion_mode="LINEAR")
+    out["stream_canvas_hw"] = np.array([int(oh), int(ow)])
+    out["stream_frame0"] = frames[0]
+    # the warped masks of frame 0 as the reference sees them, and the two kinds of centroid
+    M1, M2, wmin, hmin, oww, ohh = O.canvas(S1[:, :2], S2[:, :2], H, W)
+    nrig = O.norm_mesh(O.rigid_mesh(1, H, W), H, W)
+    tps = m["utils.torch_tps_transform"]
+    cents = []
+    for Mv in (M1, M2):
+        tt = torch.stack([Mv[0, 0, ..., 0] - wmin, Mv[0, 0, ..., 1] - hmin], 2)[None]
+        msk = tps.transformer(torch.ones(1, 1, H, W), O.norm_mesh(tt, ohh, oww), nrig, (int(ohh.int()), int(oww.int())))[0, 0]
+        r, c = torch.nonzero(msk, as_tuple=True)
+        rc, cc = torch.nonzero(msk > 0.5, as_tuple=True)
+        cents.append([float(r.float().mean()), float(c.float().mean()), float(rc.float().mean()), float(cc.float().mean()),
+                      float(len(r)), float(len(rc))])
+    out["stream_centroids"] = np.array(cents)   # per view: (row, col) over nonzero, (row, col) over mask > 0.5, counts
+    return {k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
     mods = ref_harness.load()
@@ -197,5 +250,7 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(HERE, "stream_small.npz"), **stream_case(mods))
     if not only or "threeview" in only:
         np.savez_compressed(os.path.join(HERE, "threeview.npz"), **threeview_case(mods))
-    for f in ("ops.npz", "stream_small.npz", "threeview.npz"):
+    if not only or "linear" in only:
+        np.savez_compressed(os.path.join(HERE, "linear.npz"), **linear_case(mods))
+    for f in ("ops.npz", "stream_small.npz", "threeview.npz", "linear.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)))

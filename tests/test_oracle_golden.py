@@ -1,5 +1,7 @@
 """Pin the CPU oracle (oracle/stabstitch_oracle.py) to the committed golden vectors, which
 are outputs of the unmodified reference (tests/golden/make_golden.py)."""
+import os
+
 import numpy as np
 import torch
 
@@ -7,6 +9,7 @@ from oracle import stabstitch_oracle as O
 from oracle import weights as Wt
 
 T = torch.from_numpy
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def close(a, b, tol):
@@ -137,3 +140,33 @@ def test_host_edges_against_cv2():
     assert np.array_equal(lr[0], ref_lr.astype(np.float32))
     f = np.array([[[-0.05, 0.0, 0.99]], [[1.5, 254.99, 255.0]]], np.float32)
     assert np.array_equal(HE.to_video_frame(f), f.astype(np.uint8))
+
+
+def test_linear_fusion_against_reference(golden_stream, golden_threeview):
+    """LINEAR fusion: the oracle's verbatim restatement (clean=False) of linear_blender / the LINEAR branches of
+    get_stable_sqe (test_online_tra.py:34-58,143-150) and of the three-view driver (test_online_tra_threeview.py:492-503)
+    against the reference's own outputs: bit-exact on this torch build.  And the measured distance of the residue-free
+    mask semantics (clean=True, what the CUDA path implements) to the reference."""
+    from tests.golden.make_golden import linear_inputs, threeview_inputs, STREAM_H, STREAM_W
+    gl = dict(np.load(os.path.join(GOLDEN, "linear.npz")))
+    ref, tgt, m1, m2 = linear_inputs()
+    assert np.array_equal(O.linear_blender(ref, tgt, m1, m2).numpy(), gl["clean_out"])
+    assert np.array_equal(O.linear_blender(ref, tgt, m1, m2, mask=True).numpy(), gl["clean_mask1"])
+    assert np.array_equal(O.linear_blender(ref, tgt, m1, m2, clean=True).numpy(), gl["clean_out"])   # 0/1 masks: same
+    hr = [[O.synth_frame(t, v, STREAM_H, STREAM_W) for t in range(2)] for v in range(2)]
+    S1, S2 = T(golden_stream["smooth_mesh1"])[:, :2], T(golden_stream["smooth_mesh2"])[:, :2]
+    M1, M2, wmin, hmin, ow, oh = O.canvas(S1, S2, STREAM_H, STREAM_W)
+    f = O.stable_frame_linear(hr[0][0], hr[1][0], M1[:, 0], M2[:, 0], wmin, hmin, ow, oh)
+    assert np.abs(f.numpy().transpose(1, 2, 0) - gl["stream_frame0"]).max() < 1e-4
+    fc = O.stable_frame_linear(hr[0][0], hr[1][0], M1[:, 0], M2[:, 0], wmin, hmin, ow, oh, clean=True)
+    d = np.abs(fc.numpy().transpose(1, 2, 0) - gl["stream_frame0"])
+    c = gl["stream_centroids"]
+    print("residue-free masks vs reference LINEAR frame: max %.3f p99 %.3f; centre columns %.1f/%.1f (nonzero) vs %.1f/%.1f "
+          "(mask > 0.5); %d / %d 'mask' pixels of view 1 are residues" % (d.max(), np.percentile(d, 99), c[0, 1], c[1, 1],
+                                                                         c[0, 3], c[1, 3], c[0, 4] - c[0, 5], c[0, 4]))
+    assert d.max() < 1.0 and np.percentile(d, 99) < 0.5
+    w12m1, w12m2, w23m1, w23m2, imgs = threeview_inputs()
+    with torch.no_grad():
+        a, mid, b, wmin, hmin, ow, oh = O.three_view_meshes(w12m1, w12m2, w23m1, w23m2, 96, 128)
+        f3 = O.three_view_frame_linear(imgs[0][0], imgs[1][0], imgs[2][0], a[:, 0], mid[:, 0], b[:, 0], wmin, hmin, ow, oh)
+    assert np.abs(f3.numpy() - golden_threeview["frames_linear"][0]).max() < 1e-4
