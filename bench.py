@@ -65,6 +65,8 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--tps", default="default", choices=["default", "exact", "lattice"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--views", type=int, default=2, choices=[2, 3, 4],
+                    help="views per stitched frame: 2 = the pair pipeline (metric), 3 / 4 = the multi-view chain (config 5)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
     return ap.parse_args()
@@ -459,9 +461,10 @@ def run_native(args):
         cpu = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": "48-frame %dx%d stream (42 SmoothNet windows) through all network stages of the CPU oracle "
                          "port; resample+blend timed on 16 frames and scaled x3 (%.1f s of CPU work)" % (H, W, spent)}
-    gpu_eager = None
+    gpu_eager = dropin = None
     if world == 1 and not args.no_gpu_eager:
         gpu_eager = gpu_eager_sample(H, W)
+        dropin = dropin_replay_sample(H, W)
     line = {"metric": metric_name(H), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
@@ -472,10 +475,38 @@ def run_native(args):
             "tps_field": "exact" if tps == _lib.TPS_EXACT else "lattice",
             "clocks": clocks, "e2e": e2e, "e2e_fp32_interface": e2e_fp32, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_tensor": roofline_tensor, "cpu_baseline": cpu,
-            "gpu_eager_baseline": gpu_eager, "shard_parity": shard_parity}
+            "gpu_eager_baseline": gpu_eager, "dropin_replay": dropin, "shard_parity": shard_parity}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def dropin_replay_sample(H, W, n=16):
+    """The UNCHANGED driver's call sequence (tests/dropin_replay.py: batch-1 build_SpatialNet per pair, per-frame
+    transformer + torch blend + .cpu() like test_online_tra.py:284-399) through the flat drop-in names: the frames/s
+    a maintainer gets with zero edits, next to `value`, which batches a chunk per call."""
+    import torch
+    from stabstitch2_b200 import synthetic
+    from tests import dropin_replay as R
+    try:
+        names = R.import_flat()
+        s, t, m = names["SpatialNet"]().cuda().eval(), names["TemporalNet"]().cuda().eval(), names["SmoothNet"]().cuda().eval()
+        s.load_state_dict(synthetic.spatial_state_dict(mesh_scale=20.0), strict=True)
+        t.load_state_dict(synthetic.temporal_state_dict(mesh_scale=10.0), strict=True)
+        m.load_state_dict(synthetic.smooth_state_dict(), strict=True)
+        hr = [[synthetic.synth_frame(k, v, H, W) for k in range(n)] for v in range(2)]
+        lr = [[synthetic.lowres(x) for x in hr[v]] for v in range(2)]
+        R.replay(names, s, t, m, lr[0][:7], lr[1][:7], hr[0][:7], hr[1][:7])   # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        frames, _, _ = R.replay(names, s, t, m, lr[0], lr[1], hr[0], hr[1])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    except Exception as exc:
+        return {"value": None, "error": "%s: %s" % (type(exc).__name__, str(exc).splitlines()[0][:200])}
+    return {"value": n / dt, "unit": UNIT, "frames": n, "canvas": [int(frames[0].shape[0]), int(frames[0].shape[1])],
+            "note": "per-frame Python loops of the reference driver, batch-1 calls, H2D of every frame and D2H of every fused "
+                    "frame inside the timed region (wall clock)"}
 
 
 def gpu_eager_sample(H, W, n=16, warp_frames=4):
@@ -529,10 +560,159 @@ def gpu_eager_sample(H, W, n=16, warp_frames=4):
                     "scaled x%d" % (warp_frames, n // warp_frames)}
 
 
+def run_nview(args):
+    """--views 3|4 (BASELINE.json config 5: the multi-video stitch of Full_model_inference on N GPUs): per step every rank
+    runs the N-1 pair pipelines (SpatialNet, TemporalNet x2, tsmotion, SmoothNet) over its temporal shard of F frames,
+    the middle-plane chain, and ONE fused N-image resample + AVERAGE blend.  Collectives per step: one mesh-halo
+    all-gather per pair + two canvas all-reduces."""
+    import torch
+    import torch.distributed as dist
+    from stabstitch2_b200 import _lib, pipeline, synthetic
+    from stabstitch2_b200.smooth_network import SmoothNet
+    from stabstitch2_b200.spatial_network import SpatialNet
+    from stabstitch2_b200.temporal_network import TemporalNet
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    H, W, F, V = args.height, args.width, args.frames, args.views
+    ctx = _lib.context()
+    s, t, m = SpatialNet().cuda().eval(), TemporalNet().cuda().eval(), SmoothNet().cuda().eval()
+    s.load_state_dict(synthetic.spatial_state_dict(mesh_scale=20.0), strict=True)
+    t.load_state_dict(synthetic.temporal_state_dict(mesh_scale=10.0), strict=True)
+    m.load_state_dict(synthetic.smooth_state_dict(), strict=True)
+    f0, halo = rank * F, (1 if rank > 0 else 0)
+    hr_all = [torch.cat([synthetic.synth_frame(k, v, H, W, chain=True) for k in range(f0 - halo, f0 + F)], 0) for v in range(V)]
+    d_lr = [synthetic.lowres(x).cuda() for x in hr_all]
+    hr = [x[halo:].contiguous() for x in hr_all]
+    d_hr = [x.cuda() for x in hr]
+
+    def step():
+        return pipeline.stitch_nview_stream(s, t, m, d_lr, d_hr, halo)[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        fused = step()
+    barrier()
+    Ho, Wo = int(fused.shape[2]), int(fused.shape[3])
+    if rank == 0:
+        sampler.mark()
+    ctx.launch_count(reset=True)
+    ctx.profile_enable(_lib.PROF_WARP, True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        fused = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count()
+    warp_ms, warp_n, warp_bytes = ctx.profile_read(_lib.PROF_WARP)
+    ctx.profile_enable(_lib.PROF_WARP, False)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tmax = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = world * F * args.steps / (ms / 1000.0)
+    # shard parity: rank 0 stitches the whole stream alone (outside the timed region)
+    shard_parity = None
+    if world > 1:
+        parts = [torch.empty_like(fused) for _ in range(world)]
+        dist.all_gather(parts, fused.contiguous())
+        lrs = [[torch.empty_like(d_lr[v][halo:]) for _ in range(world)] for v in range(V)]
+        hrs = [[torch.empty_like(d_hr[v]) for _ in range(world)] for v in range(V)]
+        for v in range(V):
+            dist.all_gather(lrs[v], d_lr[v][halo:].contiguous())
+            dist.all_gather(hrs[v], d_hr[v])
+        if rank == 0:
+            # single-process call on the concatenated stream (no process group involved)
+            pairs = [pipeline.stream_meshes(s, t, m, torch.cat(lrs[v], 0), torch.cat(lrs[v + 1], 0)) for v in range(V - 1)]
+            hcat = [torch.cat(hrs[v], 0) for v in range(V)]
+            sh, mi, mm1 = pipeline.nview_align(pairs, H, W)
+            meshes, mm2 = pipeline.nview_remap(sh, mi, mm1.cpu().tolist())
+            ref = pipeline.nview_frames(hcat, meshes, mm2.cpu().tolist())
+            got = torch.cat(parts, 0)
+            same = tuple(got.shape) == tuple(ref.shape)
+            mx = float((got - ref).abs().max().item()) if same else None
+            shard_parity = {"max_abs": mx, "bit_identical": bool(same and mx == 0.0), "frames_compared": int(ref.shape[0]),
+                            "canvas": [int(ref.shape[2]), int(ref.shape[3])]}
+            del ref, got
+        del parts, lrs, hrs
+        torch.cuda.empty_cache()
+    # e2e: pinned host frames of all views in, fused frames out, through the public Python API
+    e2e = None
+    if not args.no_e2e:
+        try:
+            pin_lr = [x.cpu().pin_memory() for x in d_lr]
+            pin_hr = [x.pin_memory() for x in hr]
+            host_out = torch.empty(F, 3, Ho, Wo).pin_memory()   # the canvas of the (fixed) synthetic stream is known from warm-up
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                a = [x.cuda(non_blocking=True) for x in pin_lr]
+                b = [x.cuda(non_blocking=True) for x in pin_hr]
+                out = pipeline.stitch_nview_stream(s, t, m, a, b, halo)[0]
+                host_out.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                tmax = torch.tensor([dt], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                dt = float(tmax.item())
+            e2e = {"value": world * F * args.steps / dt, "unit": UNIT,
+                   "h2d_bytes_per_step": int(sum(x.numel() for x in pin_lr + pin_hr) * 4),
+                   "d2h_bytes_per_step": int(F * 3 * Ho * Wo * 4),
+                   "note": "fp32 tensors from pinned host memory through pipeline.stitch_nview_stream, fused frames back to "
+                           "pinned host memory, copies inside the timed region (no chunk pipelining in this mode)"}
+        except RuntimeError as exc:
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "note": "leg failed: " + str(exc).splitlines()[0][:160]}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    achieved = (warp_bytes / warp_n) / (warp_ms / warp_n * 1e-3) / 1e9 if warp_n else None
+    cfg = make_config(H, W, F, world)
+    cfg["workload"] = "%d-view %dp synthetic multi-video stream: %d stitched pairs (Spatial+Temporal+Smooth) + middle-plane chain + " \
+                      "fused %d-image TPS resample/AVERAGE blend" % (V, H, V - 1, V)
+    cfg["views"] = V
+    cfg["l2"] = "inputs larger than L2: %.0f MB of frames per step per GPU" % (F * V * 3 * H * W * 4 / 1e6)
+    line = {"metric": "stitched frames/sec at %dp, %d views" % (H, V), "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "canvas": [Ho, Wo],
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "N-view resampler bracket: tps_solve + tps_nodes + tps_warp_lattice<V=%d> per 8-frame "
+                                                    "chunk" % V, "achieved": achieved, "peak": peak, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
+                         "algorithmic_bytes_per_launch": warp_bytes / warp_n if warp_n else None,
+                         "avg_launch_ms": warp_ms / warp_n if warp_n else None, "launches_timed": warp_n,
+                         "share_of_step": warp_ms / ms if ms else None},
+            "cpu_baseline": None, "shard_parity": shard_parity}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.views > 2:
+        run_nview(args)
     else:
         run_native(args)
 

@@ -188,6 +188,27 @@ int ss2_three_view_frames(ss2_ctx* ctx, const float* d_img1, const float* d_img2
                           const float* d_mesh1, const float* d_middle, const float* d_mesh3, int n, int H, int W,
                           const float* h_canvas, int mode, int tps, float* d_out, void* stream);
 
+/* ---- N views (BASELINE.json config 5; generalises the three-view glue, identical to it for N = 3) ----------- */
+/* Chain of stitched pairs (1,2), (2,3), .., (N-1,N): h_pair_meshes is a HOST array of 2*(N-1) DEVICE pointers
+ * (meshA, meshB of pair 1, meshA, meshB of pair 2, ..), each [n,7,9,2] @480x360; meshB of pair p and meshA of pair
+ * p+1 are two instances of one physical view.  Step 1 (align): pairs chained by the per-frame mean offset of their
+ * shared views (:354-360), middle plane of every shared view (:363).  Outputs: d_shifted [2(N-1)][n,7,9,2] and
+ * d_mids [N-2][n,7,9,2] in hr pixels, d_minmax1[4] = (xmin,xmax,ymin,ymax) of the shifted meshes = the provisional
+ * canvas (:366-399).  A temporally sharded stream all-reduces d_minmax1 (min on 0,2; max on 1,3) before step 2. */
+int ss2_nview_align(ss2_ctx* ctx, const float* const* h_pair_meshes, int nviews, int n, int img_h, int img_w,
+                    float* d_shifted, float* d_mids, float* d_minmax1, void* stream);
+/* Step 2 (remap): the two outer views follow their pair's instance of the neighbouring shared view through the TPS
+ * onto its middle plane (:411-427).  h_minmax1: the (global) provisional canvas on the HOST.  d_meshes [N][n,7,9,2]:
+ * the final meshes in provisional-canvas pixels; d_minmax2[4] = (xmin,xmax,ymin,ymax) over them = the new canvas
+ * (:433-455), to be all-reduced like d_minmax1. */
+int ss2_nview_remap(ss2_ctx* ctx, int nviews, int n, const float* d_shifted, const float* d_mids, const float* h_minmax1,
+                    float* d_meshes, float* d_minmax2, void* stream);
+/* Step 3: the N-image warp + sequential AVERAGE fusion fuse(..fuse(fuse(1,2),3)..,N) (:461-490) for n frames in ONE
+ * fused pass over the canvas (2 <= N <= 4): h_imgs HOST array of N DEVICE pointers [n,3,H,W]; out [n,3,Ho,Wo] with
+ * Ho = (int)(ymax-ymin), Wo = (int)(xmax-xmin) of h_minmax2. */
+int ss2_nview_frames(ss2_ctx* ctx, const float* const* h_imgs, const float* d_meshes, int nviews, int n, int H, int W,
+                     const float* h_minmax2, int mode, int tps, float* d_out, void* stream);
+
 /* ---- whole stream, device resident ------------------------------------------------------- */
 /* smooth meshes of a stream from per-window SmoothNet outputs (test_online_tra.py:378-392):
  * d_win_smooth [nwin,7,7,9,2].  with_head != 0: first window contributes its 7 meshes, every

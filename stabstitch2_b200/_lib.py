@@ -59,6 +59,9 @@ SIGNATURES = {
     "ss2_linear_blend": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "ss2_stable_frames_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _fp, _i, _i, _vp, _vp]),
     "ss2_three_view_frames_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _fp, _i, _i, _vp, _vp]),
+    "ss2_nview_align": (_i, [_vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ss2_nview_remap": (_i, [_vp, _i, _i, _vp, _vp, _fp, _vp, _vp, _vp]),
+    "ss2_nview_frames": (_i, [_vp, ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _fp, _i, _i, _vp, _vp]),
     "ss2_load_frames_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "ss2_frames_to_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "ss2_stitch_stream_host_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64,

@@ -311,6 +311,79 @@ int ss2_three_view_frames(ss2_ctx* ctx, const float* d_img1, const float* d_img2
   return rc;
 }
 
+// ---- N views (config 5): chain of pairs (1,2), (2,3), .., (N-1,N) ------------------------------------------------
+int ss2_nview_align(ss2_ctx* ctx, const float* const* h_pair_meshes, int nviews, int n, int img_h, int img_w,
+                    float* d_shifted, float* d_mids, float* d_minmax1, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (nviews < 3 || nviews > 8 || n <= 0 || img_h <= 0 || img_w <= 0 || !h_pair_meshes || !d_shifted || !d_mids || !d_minmax1)
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_nview_align: bad arguments (3 <= views <= 8)");
+  for (int q = 0; q < 2 * (nviews - 1); ++q)
+    if (!h_pair_meshes[q]) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_nview_align: null mesh pointer %d", q);
+  return nview_align_launch(ctx, h_pair_meshes, nviews, n, img_h, img_w, d_shifted, d_mids, d_minmax1, (cudaStream_t)stream);
+}
+
+int ss2_nview_remap(ss2_ctx* ctx, int nviews, int n, const float* d_shifted, const float* d_mids, const float* h_minmax1,
+                    float* d_meshes, float* d_minmax2, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (nviews < 3 || nviews > 8 || n <= 0 || !d_shifted || !d_mids || !h_minmax1 || !d_meshes || !d_minmax2)
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_nview_remap: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float xmin = h_minmax1[0], ymin = h_minmax1[2], ow = h_minmax1[1] - h_minmax1[0], oh = h_minmax1[3] - h_minmax1[2];
+  const size_t m = (size_t)n * SS2_NPT * 2;
+  float* buf = nullptr;
+  // pt0 src0 tgt0 pt1 src1 tgt1 (6 m) | moved0 moved1 (2 m) | T (2 sets)
+  SS2_CUDA(ctx, cudaMallocAsync((void**)&buf, (8 * m + (size_t)2 * n * 2 * SS2_NSYS) * sizeof(float), st));
+  float *pt0 = buf, *src0 = buf + m, *tgt0 = buf + 2 * m, *pt1 = buf + 3 * m, *src1 = buf + 4 * m, *tgt1 = buf + 5 * m;
+  float *moved0 = buf + 6 * m, *moved1 = buf + 7 * m, *T = buf + 8 * m;
+  int rc = nview_operands_launch(ctx, d_shifted, d_mids, nviews, n, xmin, ymin, ow, oh, pt0, src0, tgt0, pt1, src1, tgt1, d_meshes, st);
+  if (rc == SS2_OK) rc = tps_solve_launch(ctx, src0, tgt0, n, T, st);
+  if (rc == SS2_OK) rc = tps_point_launch(ctx, pt0, src0, T, n, moved0, st);
+  if (rc == SS2_OK) rc = tps_solve_launch(ctx, src1, tgt1, n, T + (size_t)n * 2 * SS2_NSYS, st);
+  if (rc == SS2_OK) rc = tps_point_launch(ctx, pt1, src1, T + (size_t)n * 2 * SS2_NSYS, n, moved1, st);
+  if (rc == SS2_OK) rc = nview_finish_launch(ctx, moved0, moved1, nviews, n, ow, oh, d_meshes, d_minmax2, st);
+  cudaFreeAsync(buf, st);
+  return rc;
+}
+
+int ss2_nview_frames(ss2_ctx* ctx, const float* const* h_imgs, const float* d_meshes, int nviews, int n, int H, int W,
+                     const float* h_minmax2, int mode, int tps, float* d_out, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (nviews < 2 || nviews > 4 || n < 0 || H <= 0 || W <= 0 || !h_imgs || !h_minmax2 ||
+      (mode != SS2_MODE_NORMAL && mode != SS2_MODE_FAST) || (n > 0 && !d_meshes))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_nview_frames: bad arguments (2 <= views <= 4 in one fused pass)");
+  for (int v = 0; v < nviews; ++v)
+    if (n > 0 && !h_imgs[v]) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_nview_frames: null image pointer %d", v);
+  const float xmin = h_minmax2[0], ymin = h_minmax2[2], out_w = h_minmax2[1] - h_minmax2[0], out_h = h_minmax2[3] - h_minmax2[2];
+  const int Ho = (int)out_h, Wo = (int)out_w;
+  if (Ho < 0 || Wo < 0) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_nview_frames: negative canvas");
+  if (n == 0 || Ho == 0 || Wo == 0) return SS2_OK;
+  if (!d_out) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_nview_frames: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tps != SS2_TPS_LATTICE || !tps_lattice_supported(Ho, Wo)) tps = SS2_TPS_EXACT;
+  const int chunk = n < 8 ? n : 8;
+  const size_t m = (size_t)n * nviews * SS2_NPT * 2, iplane3 = (size_t)3 * H * W, oplane3 = (size_t)3 * Ho * Wo;
+  TpsScratch sc;
+  SS2_TRY(tps_scratch_alloc(ctx, nviews * chunk, Ho, Wo, tps, 2 * m + 64, &sc, st));
+  float* source = sc.nodes + (tps == SS2_TPS_LATTICE ? (tps_lattice_workspace_floats(nviews * chunk, Ho, Wo) + 63) / 64 * 64 : 0);
+  float* target = source + m;
+  int rc = nview_sources_launch(ctx, d_meshes, nviews, n, H, W, xmin, ymin, out_w, out_h, source, target, st);
+  for (int k0 = 0; k0 < n && rc == SS2_OK; k0 += chunk) {
+    const int nk = n - k0 < chunk ? n - k0 : chunk;
+    const float* src = source + (size_t)k0 * nviews * SS2_NPT * 2;
+    const float* tgt = target + (size_t)k0 * nviews * SS2_NPT * 2;
+    const float* imgs[4];
+    for (int v = 0; v < nviews; ++v) imgs[v] = h_imgs[v] + (size_t)k0 * iplane3;
+    ss2_prof_begin(ctx, SS2_PROF_WARP, st);
+    rc = tps_solve_for_warp(ctx, src, tgt, nviews * nk, H, W, Ho, Wo, mode, tps, sc, st);
+    if (rc == SS2_OK)
+      rc = tps_warp_blend_n_launch(ctx, imgs, nviews, src, sc.T, nk, H, W, Ho, Wo, mode, tps, d_out + (size_t)k0 * oplane3, st,
+                                   sc.aux, sc.nodes);
+    ss2_prof_end(ctx, SS2_PROF_WARP, st, (double)nk * ((double)nviews * 3 * H * W + 3.0 * Ho * Wo) * 4.0);
+  }
+  cudaFreeAsync(sc.base, st);
+  return rc;
+}
+
 int ss2_cost_volume_nhwc(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B, int H, int W, int C, int sr, int CP,
                          float* d_out, void* stream) {
   if (!ctx) return SS2_ERR_INVALID;

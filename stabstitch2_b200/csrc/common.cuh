@@ -256,6 +256,20 @@ int three_view_sources_launch(ss2_ctx* ctx, const float* m1_c, const float* mid_
                               cudaStream_t st);
 int blend3_avg_launch(ss2_ctx* ctx, const float* w1, const float* w2, const float* w3, size_t count, float* out,
                       cudaStream_t st);
+// geom.cu: N-view middle-plane chain (config 5)
+int nview_align_launch(ss2_ctx* ctx, const float* const* d_pairs, int nviews, int n, int img_h, int img_w, float* shifted,
+                       float* mids, float* minmax, cudaStream_t st);
+int nview_operands_launch(ss2_ctx* ctx, const float* shifted, const float* mids, int nviews, int n, float xmin, float ymin,
+                          float ow, float oh, float* pt0, float* src0, float* tgt0, float* pt1, float* src1, float* tgt1,
+                          float* meshes_out, cudaStream_t st);
+int nview_finish_launch(ss2_ctx* ctx, const float* moved0, const float* moved1, int nviews, int n, float ow, float oh,
+                        float* meshes_out, float* minmax, cudaStream_t st);
+int nview_sources_launch(ss2_ctx* ctx, const float* meshes, int nviews, int n, int img_h, int img_w, float xmin, float ymin,
+                         float out_w, float out_h, float* source, float* target, cudaStream_t st);
+// tps.cu: fused N-view (2..4) resample + sequential AVERAGE blend; imgs[v] [nframes,3,H,W], source [nframes][V][63][2]
+int tps_warp_blend_n_launch(ss2_ctx* ctx, const float* const* d_imgs, int nviews, const float* d_source, const float* d_T,
+                            int nframes, int H, int W, int Ho, int Wo, int mode, int tps, float* d_out, cudaStream_t st,
+                            const float* d_aux, float* d_nodes);
 // conv_tc.cu: cuTensorMapEncodeTiled (driver entry point), null if unavailable
 void* ss2_tensormap_encode_fn();
 // conv.cu

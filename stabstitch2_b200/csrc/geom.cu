@@ -584,3 +584,160 @@ int blend3_avg_launch(ss2_ctx* ctx, const float* w1, const float* w2, const floa
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// N-view middle-plane chain (BASELINE.json config 5; generalises the three-view glue above and reduces to it for
+// N = 3, tests/test_gpu_parity.py::test_nview_equals_three_view).  Pairs (1,2), (2,3), .., (N-1,N): meshB of pair p and
+// meshA of pair p+1 are two instances of one physical view.
+//   align:  rescale to hr; every pair p >= 2 shifted by the per-frame mean vertex offset that brings its meshA onto
+//           the (already shifted) meshB of pair p-1; middle plane of every shared view; min/max of all shifted meshes
+//   remap:  translate / normalise by the (global) provisional canvas; the two OUTER views follow their pair's instance
+//           of the neighbouring shared view through the TPS onto its middle plane; min/max of the N final meshes
+// The two min/max results leave the kernels so that a temporally sharded stream can all-reduce them (the TPS
+// normalisation depends on the provisional canvas of ALL frames).  Single CTA each, reference fp32 operation order.
+// ------------------------------------------------------------------------------------------
+#define NVIEW_MAX 8
+struct NviewPtrs { const float* p[2 * (NVIEW_MAX - 1)]; };
+
+__global__ void __launch_bounds__(256)
+nview_align_kernel(NviewPtrs in, int nviews, int n, float img_h, float img_w, float* __restrict__ shifted,
+                   float* __restrict__ mids, float* __restrict__ minmax) {
+  __shared__ float red[4][32];
+  const size_t m = (size_t)n * SS2_NPT * 2;
+  const int npair = nviews - 1;
+  for (int q = 0; q < 2 * npair; ++q)
+    for (size_t i = threadIdx.x; i < m; i += blockDim.x) {
+      const bool isx = (i & 1) == 0;
+      shifted[q * m + i] = __fdiv_rn(__fmul_rn(in.p[q][i], isx ? img_w : img_h), isx ? 480.0f : 360.0f);
+    }
+  __syncthreads();
+  // chain: pair p follows pair p-1 (sequential in p, one warp per frame)
+  for (int p = 1; p < npair; ++p) {
+    const float* prevB = shifted + (size_t)(2 * (p - 1) + 1) * m;
+    float* A = shifted + (size_t)(2 * p) * m;
+    float* B = A + m;
+    float* mid = mids + (size_t)(p - 1) * m;
+    for (int k = threadIdx.x / 32; k < n; k += blockDim.x / 32) {
+      const int lane = threadIdx.x % 32;
+      float sx = 0.f, sy = 0.f;
+      for (int v = lane; v < SS2_NPT; v += 32) {
+        const size_t o = ((size_t)k * SS2_NPT + v) * 2;
+        sx += prevB[o] - A[o];
+        sy += prevB[o + 1] - A[o + 1];
+      }
+      for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+      const float ox = sx / (float)SS2_NPT, oy = sy / (float)SS2_NPT;
+      for (int v = lane; v < SS2_NPT; v += 32) {
+        const size_t o = ((size_t)k * SS2_NPT + v) * 2;
+        A[o] += ox; A[o + 1] += oy;
+        B[o] += ox; B[o + 1] += oy;
+        mid[o] = (prevB[o] + A[o]) / 2.0f;
+        mid[o + 1] = (prevB[o + 1] + A[o + 1]) / 2.0f;
+      }
+    }
+    __syncthreads();
+  }
+  float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  for (size_t i = threadIdx.x; i < (size_t)npair * m; i += blockDim.x) {   // i over (x, y) pairs of all 2*npair meshes
+    const float x = shifted[2 * i], y = shifted[2 * i + 1];
+    xmin = fminf(xmin, x); xmax = fmaxf(xmax, x);
+    ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+  }
+  block_minmax4(xmin, xmax, ymin, ymax, red);
+  if (threadIdx.x == 0) { minmax[0] = xmin; minmax[1] = xmax; minmax[2] = ymin; minmax[3] = ymax; }
+}
+
+// TPS-point operands of the two outer views (normalised by the provisional canvas) and the shared views' final meshes
+// (provisional-canvas pixels) written straight into meshes_out[1..N-2]
+__global__ void __launch_bounds__(256)
+nview_operands_kernel(const float* __restrict__ shifted, const float* __restrict__ mids, int nviews, int n, float xmin,
+                      float ymin, float ow, float oh, float* __restrict__ pt0, float* __restrict__ src0,
+                      float* __restrict__ tgt0, float* __restrict__ pt1, float* __restrict__ src1, float* __restrict__ tgt1,
+                      float* __restrict__ meshes_out) {
+  const size_t m = (size_t)n * SS2_NPT * 2;
+  const int npair = nviews - 1;
+  const float *A0 = shifted, *B0 = shifted + m, *AL = shifted + (size_t)(2 * (npair - 1)) * m, *BL = AL + m;
+  const float *mid0 = mids, *midL = mids + (size_t)(npair - 2) * m;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x) {
+    const bool isx = (i & 1) == 0;
+    const float mn = isx ? xmin : ymin, ext = isx ? ow : oh;
+    pt0[i] = norm1(A0[i] - mn, ext);
+    src0[i] = norm1(B0[i] - mn, ext);
+    tgt0[i] = norm1(mid0[i] - mn, ext);
+    pt1[i] = norm1(BL[i] - mn, ext);
+    src1[i] = norm1(AL[i] - mn, ext);
+    tgt1[i] = norm1(midL[i] - mn, ext);
+    for (int k = 0; k < npair - 1; ++k) meshes_out[(size_t)(k + 1) * m + i] = mids[(size_t)k * m + i] - mn;
+  }
+}
+
+// recover the outer views' moved meshes into meshes_out[0], [N-1]; min/max over all N final meshes
+__global__ void __launch_bounds__(256)
+nview_finish_kernel(const float* __restrict__ moved0, const float* __restrict__ moved1, int nviews, int n, float ow, float oh,
+                    float* __restrict__ meshes_out, float* __restrict__ minmax) {
+  __shared__ float red[4][32];
+  const size_t m = (size_t)n * SS2_NPT * 2;
+  float* first = meshes_out;
+  float* last = meshes_out + (size_t)(nviews - 1) * m;
+  for (size_t i = threadIdx.x; i < m; i += blockDim.x) {
+    const float ext = (i & 1) == 0 ? ow : oh;
+    first[i] = __fdiv_rn(__fmul_rn(__fadd_rn(moved0[i], 1.0f), ext), 2.0f);   // recover_mesh: (n + 1) * extent / 2
+    last[i] = __fdiv_rn(__fmul_rn(__fadd_rn(moved1[i], 1.0f), ext), 2.0f);
+  }
+  __syncthreads();
+  float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  for (size_t i = threadIdx.x; i < (size_t)nviews * (m / 2); i += blockDim.x) {
+    const float x = meshes_out[2 * i], y = meshes_out[2 * i + 1];
+    xmin = fminf(xmin, x); xmax = fmaxf(xmax, x);
+    ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+  }
+  block_minmax4(xmin, xmax, ymin, ymax, red);
+  if (threadIdx.x == 0) { minmax[0] = xmin; minmax[1] = xmax; minmax[2] = ymin; minmax[3] = ymax; }
+}
+
+// per view v (grid.y): normalised canvas mesh (source) and normalised rigid mesh (target), laid out [n][V][63][2] as the
+// fused N-view resampler wants them
+__global__ void nview_sources_kernel(const float* __restrict__ meshes, int nviews, int n, float img_h, float img_w, float xmin,
+                                     float ymin, float out_w, float out_h, float* __restrict__ source,
+                                     float* __restrict__ target) {
+  const int k = blockIdx.x, v = blockIdx.y, tid = threadIdx.x;
+  if (tid >= SS2_NPT) return;
+  const float* p = meshes + (((size_t)v * n + k) * SS2_NPT + tid) * 2;
+  const size_t o = (((size_t)k * nviews + v) * SS2_NPT + tid) * 2;
+  source[o] = norm1(__fsub_rn(p[0], xmin), out_w);
+  source[o + 1] = norm1(__fsub_rn(p[1], ymin), out_h);
+  const int gi = tid / (SS2_GRID_W + 1), gj = tid % (SS2_GRID_W + 1);
+  target[o] = norm1(lin0(gj, SS2_GRID_W + 1, img_w), img_w);
+  target[o + 1] = norm1(lin0(gi, SS2_GRID_H + 1, img_h), img_h);
+}
+
+int nview_align_launch(ss2_ctx* ctx, const float* const* d_pairs, int nviews, int n, int img_h, int img_w, float* shifted,
+                       float* mids, float* minmax, cudaStream_t st) {
+  NviewPtrs P;
+  for (int q = 0; q < 2 * (nviews - 1); ++q) P.p[q] = d_pairs[q];
+  nview_align_kernel<<<1, 256, 0, st>>>(P, nviews, n, (float)img_h, (float)img_w, shifted, mids, minmax);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+int nview_operands_launch(ss2_ctx* ctx, const float* shifted, const float* mids, int nviews, int n, float xmin, float ymin,
+                          float ow, float oh, float* pt0, float* src0, float* tgt0, float* pt1, float* src1, float* tgt1,
+                          float* meshes_out, cudaStream_t st) {
+  const size_t m = (size_t)n * SS2_NPT * 2;
+  nview_operands_kernel<<<(int)((m + 255) / 256 < 64 ? (m + 255) / 256 : 64), 256, 0, st>>>(shifted, mids, nviews, n, xmin, ymin, ow, oh,
+                                                                                        pt0, src0, tgt0, pt1, src1, tgt1, meshes_out);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+int nview_finish_launch(ss2_ctx* ctx, const float* moved0, const float* moved1, int nviews, int n, float ow, float oh,
+                        float* meshes_out, float* minmax, cudaStream_t st) {
+  nview_finish_kernel<<<1, 256, 0, st>>>(moved0, moved1, nviews, n, ow, oh, meshes_out, minmax);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+int nview_sources_launch(ss2_ctx* ctx, const float* meshes, int nviews, int n, int img_h, int img_w, float xmin, float ymin,
+                         float out_w, float out_h, float* source, float* target, cudaStream_t st) {
+  nview_sources_kernel<<<dim3(n, nviews), 64, 0, st>>>(meshes, nviews, n, (float)img_h, (float)img_w, xmin, ymin, out_w, out_h,
+                                                       source, target);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}

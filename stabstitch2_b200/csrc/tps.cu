@@ -30,8 +30,8 @@
 // swap and ~4400 warp instructions per step: 97 us for 64 systems).
 // ------------------------------------------------------------------------------------------
 #ifndef SOLVE_NW
-#define SOLVE_NW 8     // warps per system (measured: 16 warps 56 us per 64 systems - the per-warp bookkeeping of a step
-#endif                 // outweighs its 15 DFMAs; 8 warps halve the instructions per step)
+#define SOLVE_NW 16    // warps per system (measured per 64 systems: 8 warps 90 us, 16 warps 56 us)
+#endif
 #define SOLVE_THREADS (SOLVE_NW * 32)
 #define SOLVE_ROWS ((SS2_NSYS + SOLVE_NW - 1) / SOLVE_NW)   // rows per thread: w, w+NW, ..
 #define SOLVE_COLS 3   // columns per thread: l, l+32, l+64
@@ -162,7 +162,7 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
       }
       // pivot = column k of row p: lane k % 32, column group k / 32
       const double cand_piv = (k >> 5) == 0 ? mine[0] : ((k >> 5) == 1 ? mine[1] : mine[2]);
-      const double inv = 1.0 / __shfl_sync(0xffffffffu, cand_piv, k & 31);
+      const double inv = __drcp_rn(__shfl_sync(0xffffffffu, cand_piv, k & 31));
 #pragma unroll
       for (int j = 0; j < SOLVE_COLS; ++j)
         if (lane + 32 * j < AUG) pivrow[pb][lane + 32 * j] = mine[j] * inv;
@@ -177,24 +177,25 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
     double pr[SOLVE_COLS];
 #pragma unroll
     for (int j = 0; j < SOLVE_COLS; ++j) pr[j] = (lane + 32 * j < AUG) ? pivrow[pb][lane + 32 * j] : 0.0;
-    // eliminate column k from every other row; columns <= k are updated too (they are never read again).
-    // The lane that owns column k+1 publishes it for the next step and offers its unused rows as pivots.
+    // eliminate column k from every other row; columns <= k are updated too (they are never read again), and the
+    // padding rows (>= 66) ride along with a zero multiplier: no per-row branches.  The lane that owns column k+1
+    // publishes it for the next step and offers its best unused row as the next pivot (one atomic per warp).
     const int cn = k + 1;
     const bool own_next = (cn & 31) == lane && cn < SS2_NSYS;
+    unsigned best = 0u;
 #pragma unroll
     for (int i = 0; i < SOLVE_ROWS; ++i) {
       const int r = wid + SOLVE_NW * i;
-      if (r < SS2_NSYS) {
-        const double f = (r == p) ? 0.0 : colk[pb][r];   // the published pivot row is already divided by the pivot
+      const bool real = r < SS2_NSYS;
+      const double f = (r == p || !real) ? 0.0 : colk[pb][real ? r : 0];   // the published pivot row is already divided by the pivot
 #pragma unroll
-        for (int j = 0; j < SOLVE_COLS; ++j) a[i][j] = fma(-f, pr[j], a[i][j]);
-        if (own_next) {
-          const double v = (cn >> 5) == 0 ? a[i][0] : ((cn >> 5) == 1 ? a[i][1] : a[i][2]);
-          colk[pb ^ 1][r] = v;
-          if (!((used >> i) & 1u)) atomicMax(&pkey[cn % 3], solve_key(v, r));
-        }
-      }
+      for (int j = 0; j < SOLVE_COLS; ++j) a[i][j] = fma(-f, pr[j], a[i][j]);
+      const double v = (cn >> 5) == 0 ? a[i][0] : ((cn >> 5) == 1 ? a[i][1] : a[i][2]);
+      if (own_next && real) colk[pb ^ 1][r] = v;
+      const unsigned key = (real && !((used >> i) & 1u)) ? solve_key(v, r) : 0u;
+      best = key > best ? key : best;
     }
+    if (own_next && best != 0u) atomicMax(&pkey[cn % 3], best);
     __syncthreads();
   }
   // right-hand sides (columns 66, 67 = lane 2, 3 of the third column group) of every row
@@ -356,7 +357,7 @@ __device__ __forceinline__ float blend_avg(float a, float b) {
 #define TILE_H (TY * RPT)
 
 struct WarpParams {
-  const float* img[2];   // per view: base of [n][C][H][W]
+  const float* img[4];   // per view (up to 4): base of [n][C][H][W]
   const float* source;   // [n][V][63][2]
   const float* T;        // [n][V][2][66]
   float* out;            // BLEND: [n][C][Ho][Wo]; else [n*V][C][Ho][Wo]
@@ -447,7 +448,13 @@ tps_warp_exact_kernel(WarpParams P) {
     if (BLEND) {
       float* o = P.out + (size_t)n * C * plane + (size_t)row * P.Wo + col;
 #pragma unroll
-      for (int c = 0; c < C; ++c) __stcs(o + c * plane, blend_avg(res[r][0][c], res[r][V - 1][c]));
+      for (int c = 0; c < C; ++c) {
+        // fuse(..fuse(fuse(1,2),3)..,V) (test_online_tra_threeview.py:489-490 for V = 3); V = 1: the view itself
+        float f = res[r][0][c];
+#pragma unroll
+        for (int v = 1; v < V; ++v) f = blend_avg(f, res[r][v][c]);
+        __stcs(o + c * plane, f);
+      }
     } else {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
@@ -630,12 +637,15 @@ template <int SX> struct LatCols { static constexpr int value = (LAT_THREADS + S
 #endif
 // LAT_NCELL: lattice cell rows per CTA: the tile is LAT_THREADS x (LAT_NCELL*SY) canvas pixels
 
+// V = views evaluated per pixel: 1 (generic transformer), 2 (the production pair kernel), 3 / 4 (N-view fusion, config 5:
+// one pass over the canvas reads every source once instead of warping each view to a temporary)
 template <int V, int C, int MODE, bool BLEND, int SX, int SY, int IW, int IH>
-__global__ void __launch_bounds__(LAT_THREADS, LAT_MINB)
+__global__ void __launch_bounds__(LAT_THREADS, V <= 2 ? LAT_MINB : (V == 3 ? 5 : 4))
 tps_warp_lattice_kernel(WarpParams P) {
   constexpr int NCOL = LatCols<SX>::value;
-  __shared__ float4 near_list[V * SS2_NPT];  // (cx, cy, wx_px*ln2, wy_px*ln2), view-0 entries first
+  __shared__ float4 near_list[V * SS2_NPT];  // (cx, cy, wx_px*ln2, wy_px*ln2), sorted by view
   __shared__ int warp_cnt[LAT_THREADS / 32][2];
+  __shared__ int view_end[V];                // V > 2: near_list entries of view v end at view_end[v]
   __shared__ float s_pred[V][6];
   __shared__ __align__(16) float2 ysm[SY][NCOL][V];  // y-contracted residuals of the current cell row
   const int n = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -643,7 +653,8 @@ tps_warp_lattice_kernel(WarpParams P) {
   const int jx0 = col0 / SX;  // node slot of the first cell (slot s <-> lattice column s - LAT_LO)
   const int W = IW > 0 ? IW : P.W, H = IH > 0 ? IH : P.H;
   // ---- near list: control points whose disc s < R2 touches this tile (deterministic order)
-  {
+  int n0 = 0, n_all = 0;
+  if (V <= 2) {
     float4 ent = make_float4(0.f, 0.f, 0.f, 0.f);
     bool hit = false;
     const int pv = tid / SS2_NPT, pi = tid - pv * SS2_NPT;
@@ -665,10 +676,33 @@ tps_warp_lattice_kernel(WarpParams P) {
     for (int w = 0; w < LAT_THREADS / 32; ++w)
       if (w < wid) off += warp_cnt[w][0];
     if (hit) near_list[off + __popc(m_all & ((1u << lane) - 1u))] = ent;
-  }
-  int n0 = 0, n_all = 0;
 #pragma unroll
-  for (int w = 0; w < LAT_THREADS / 32; ++w) { n_all += warp_cnt[w][0]; n0 += warp_cnt[w][1]; }
+    for (int w = 0; w < LAT_THREADS / 32; ++w) { n_all += warp_cnt[w][0]; n0 += warp_cnt[w][1]; }
+  } else {
+    // one view after the other (63 points: warps 0 and 1), entries appended view by view
+    if (tid < V * 6) s_pred[tid / 6][tid % 6] = P.aux[(size_t)(n * V + tid / 6) * 8 + tid % 6];
+    for (int pv = 0; pv < V; ++pv) {
+      float4 ent = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool hit = false;
+      if (tid < SS2_NPT) {
+        const float x_lo = fmaf(P.stepx, (float)col0, -1.0f), x_hi = fmaf(P.stepx, (float)min(col0 + LAT_THREADS - 1, P.Wo - 1), -1.0f);
+        const float y_lo = fmaf(P.stepy, (float)row00, -1.0f), y_hi = fmaf(P.stepy, (float)min(row00 + LAT_NCELL * SY - 1, P.Ho - 1), -1.0f);
+        const float2 c = *reinterpret_cast<const float2*>(P.source + ((size_t)(n * V + pv) * SS2_NPT + tid) * 2);
+        const float* t = P.T + (size_t)(n * V + pv) * 2 * SS2_NSYS;
+        const float ddx = fmaxf(fmaxf(x_lo - c.x, c.x - x_hi), 0.f), ddy = fmaxf(fmaxf(y_lo - c.y, c.y - y_hi), 0.f);
+        hit = fmaf(ddx, ddx, ddy * ddy) < P.R2 * 1.0001f + 1e-12f;
+        if (hit) ent = make_float4(c.x, c.y, t[3 + tid] * (P.half_w * LN2F), t[SS2_NSYS + 3 + tid] * (P.half_h * LN2F));
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0 && wid < 2) warp_cnt[wid][0] = __popc(m);
+      __syncthreads();
+      const int c0 = warp_cnt[0][0], c1 = warp_cnt[1][0];
+      if (hit) near_list[n_all + (wid == 1 ? c0 : 0) + __popc(m & ((1u << lane) - 1u))] = ent;
+      n_all += c0 + c1;
+      if (tid == 0) view_end[pv] = n_all;
+      __syncthreads();
+    }
+  }
   // ---- per-column constants
   const int col = min(col0 + tid, P.Wo - 1);
   const bool active = col0 + tid < P.Wo;
@@ -723,8 +757,11 @@ tps_warp_lattice_kernel(WarpParams P) {
             acc[0][0] = fmaf(w, q.x, acc[0][0]); acc[0][1] = fmaf(w, q.y, acc[0][1]);
             acc[V - 1][0] = fmaf(w, q.z, acc[V - 1][0]); acc[V - 1][1] = fmaf(w, q.w, acc[V - 1][1]);
           } else {
-            const float2 q = __ldg(nd + (size_t)b * P.nx * V);
-            acc[0][0] = fmaf(w, q.x, acc[0][0]); acc[0][1] = fmaf(w, q.y, acc[0][1]);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float2 q = __ldg(nd + (size_t)b * P.nx * V + v);
+              acc[v][0] = fmaf(w, q.x, acc[v][0]); acc[v][1] = fmaf(w, q.y, acc[v][1]);
+            }
           }
         }
 #pragma unroll
@@ -772,11 +809,15 @@ tps_warp_lattice_kernel(WarpParams P) {
           upk2(acc0, ax[0], ay[0]);
           upk2(acc1, ax[V - 1], ay[V - 1]);
         } else {
-          ax[0] = ay[0] = 0.f;
+#pragma unroll
+          for (int v = 0; v < V; ++v) ax[v] = ay[v] = 0.f;
 #pragma unroll
           for (int a = 0; a < LAT_TAPS; ++a) {
-            const float2 q = ysm[r][js + a][0];
-            ax[0] = fmaf(lx[a], q.x, ax[0]); ay[0] = fmaf(lx[a], q.y, ay[0]);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float2 q = ysm[r][js + a][v];
+              ax[v] = fmaf(lx[a], q.x, ax[v]); ay[v] = fmaf(lx[a], q.y, ay[v]);
+            }
           }
         }
 #pragma unroll
@@ -799,14 +840,25 @@ tps_warp_lattice_kernel(WarpParams P) {
           const float4 c = near_list[k];
           const float dx = xt - c.x, dxx = dx * dx;
           const bool v0 = V == 1 || k < n0;
+          int vk = 0;   // V > 2: the view this control point belongs to
+          if (V > 2) {
+#pragma unroll
+            for (int v = 0; v < V - 1; ++v) vk += k >= view_end[v] ? 1 : 0;
+          }
 #pragma unroll
           for (int i = 0; i < LAT_RPI; ++i) {
             const float dy = yt[i] - c.y;
             const float s = fminf(fmaf(dy, dy, dxx), P.R2);
             // psi/ln2 = s*lg2(s+eps) - P(s)/ln2 (q0..q3 = P/ln2; the weights carry the ln2)
             const float psi = fmaf(s, lg2_approx(s + 1e-6f), -blend_poly(s, P.R2, P.q0, P.q1, P.q2, P.q3));
-            if (v0) { px[i][0] = fmaf(c.z, psi, px[i][0]); py[i][0] = fmaf(c.w, psi, py[i][0]); }
-            else { px[i][V - 1] = fmaf(c.z, psi, px[i][V - 1]); py[i][V - 1] = fmaf(c.w, psi, py[i][V - 1]); }
+            if (V <= 2) {
+              if (v0) { px[i][0] = fmaf(c.z, psi, px[i][0]); py[i][0] = fmaf(c.w, psi, py[i][0]); }
+              else { px[i][V - 1] = fmaf(c.z, psi, px[i][V - 1]); py[i][V - 1] = fmaf(c.w, psi, py[i][V - 1]); }
+            } else {
+#pragma unroll
+              for (int v = 0; v < V; ++v)
+                if (vk == v) { px[i][v] = fmaf(c.z, psi, px[i][v]); py[i][v] = fmaf(c.w, psi, py[i][v]); }
+            }
           }
         }
       }
@@ -887,7 +939,16 @@ tps_warp_lattice_kernel(WarpParams P) {
         const int row = row0 + r0 + i;
         if (active && r0 + i < SY && row < P.Ho) {
           const unsigned opix = (unsigned)(row * P.Wo + col);
-          if (BLEND && C == 3) {
+          if (BLEND && V > 2) {
+            // fuse(..fuse(fuse(1,2),3)..,V): the reference's sequential AVERAGE fusion (test_online_tra_threeview.py:489-490)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              float f = blend_avg_fast(res[i][0][c], res[i][1][c]);
+#pragma unroll
+              for (int v = 2; v < V; ++v) f = blend_avg_fast(f, res[i][v][c]);
+              __stcs(const_cast<float*>(f32_at(outv[0], opix + c * oplane)), f);
+            }
+          } else if (BLEND && C == 3) {
             const u64 A = pk2(res[i][0][0], res[i][0][1]), B = pk2(res[i][V - 1][0], res[i][V - 1][1]);
             float s0, s1, q0, q1;
             upk2(fadd2(fadd2(A, B), pk2(1e-6f, 1e-6f)), s0, s1);
@@ -991,11 +1052,11 @@ static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, flo
   SS2_LAUNCH_CHECK(ctx);
   dim3 grid(cdiv(P.Wo, LAT_THREADS), cdiv(P.Ho, cfg.SY * LAT_NCELL), nframes);
   // source-size specialisations of the production (fused, NORMAL) kernel: 720p and 1080p
-  const int spec = (BLEND && mode == SS2_MODE_NORMAL) ? ((P.W == 1280 && P.H == 720) ? 1 : (P.W == 1920 && P.H == 1080) ? 2 : 0) : 0;
+  const int spec = (BLEND && V == 2 && mode == SS2_MODE_NORMAL) ? ((P.W == 1280 && P.H == 720) ? 1 : (P.W == 1920 && P.H == 1080) ? 2 : 0) : 0;
 #define LAT_CASE(SXV, SYV)                                                                                   \
   if (cfg.SX == SXV && cfg.SY == SYV) {                                                                      \
-    if (spec == 1) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, BLEND ? 1280 : 0, BLEND ? 720 : 0><<<grid, LAT_THREADS, 0, st>>>(P); \
-    else if (spec == 2) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, BLEND ? 1920 : 0, BLEND ? 1080 : 0><<<grid, LAT_THREADS, 0, st>>>(P); \
+    if (spec == 1) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, (BLEND && V == 2) ? 1280 : 0, (BLEND && V == 2) ? 720 : 0><<<grid, LAT_THREADS, 0, st>>>(P); \
+    else if (spec == 2) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, (BLEND && V == 2) ? 1920 : 0, (BLEND && V == 2) ? 1080 : 0><<<grid, LAT_THREADS, 0, st>>>(P); \
     else if (mode == SS2_MODE_NORMAL) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, 0, 0><<<grid, LAT_THREADS, 0, st>>>(P); \
     else tps_warp_lattice_kernel<V, C, SS2_MODE_FAST, BLEND, SXV, SYV, 0, 0><<<grid, LAT_THREADS, 0, st>>>(P);  \
   }
@@ -1010,7 +1071,7 @@ int tps_warp_launch(ss2_ctx* ctx, const float* d_U, const float* d_source, const
                     const float* d_aux, float* d_nodes) {
   if (bn <= 0 || Ho <= 0 || Wo <= 0) return SS2_OK;
   WarpParams P;
-  P.img[0] = d_U; P.img[1] = d_U;
+  P.img[0] = d_U; P.img[1] = d_U; P.img[2] = d_U; P.img[3] = d_U;
   P.source = d_source; P.T = d_T; P.out = d_out;
   P.H = H; P.W = W; P.Ho = Ho; P.Wo = Wo;
   P.stepx = linstep(Wo); P.stepy = linstep(Ho);
@@ -1053,7 +1114,7 @@ int tps_warp_blend_launch(ss2_ctx* ctx, const float* d_img1, const float* d_img2
                           float* d_out, cudaStream_t st, const float* d_aux, float* d_nodes) {
   if (nframes <= 0 || Ho <= 0 || Wo <= 0) return SS2_OK;
   WarpParams P;
-  P.img[0] = d_img1; P.img[1] = d_img2;
+  P.img[0] = d_img1; P.img[1] = d_img2; P.img[2] = d_img2; P.img[3] = d_img2;
   P.source = d_source; P.T = d_T; P.out = d_out;
   P.H = H; P.W = W; P.Ho = Ho; P.Wo = Wo;
   P.stepx = linstep(Wo); P.stepy = linstep(Ho);
@@ -1066,6 +1127,36 @@ int tps_warp_blend_launch(ss2_ctx* ctx, const float* d_img1, const float* d_img2
   dim3 grid(cdiv(Wo, TX), cdiv(Ho, TILE_H), nframes), block(TX, TY);
   if (mode == SS2_MODE_NORMAL) tps_warp_exact_kernel<2, 3, SS2_MODE_NORMAL, true><<<grid, block, 0, st>>>(P);
   else tps_warp_exact_kernel<2, 3, SS2_MODE_FAST, true><<<grid, block, 0, st>>>(P);
+  SS2_LAUNCH_CHECK(ctx);
+  return SS2_OK;
+}
+
+int tps_warp_blend_n_launch(ss2_ctx* ctx, const float* const* d_imgs, int nviews, const float* d_source, const float* d_T,
+                            int nframes, int H, int W, int Ho, int Wo, int mode, int tps, float* d_out, cudaStream_t st,
+                            const float* d_aux, float* d_nodes) {
+  if (nframes <= 0 || Ho <= 0 || Wo <= 0) return SS2_OK;
+  if (nviews == 2)
+    return tps_warp_blend_launch(ctx, d_imgs[0], d_imgs[1], d_source, d_T, nframes, H, W, Ho, Wo, mode, tps, d_out, st, d_aux, d_nodes);
+  if (nviews != 3 && nviews != 4) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "fused N-view resampler: 2 <= N <= 4 (got %d)", nviews);
+  WarpParams P;
+  for (int v = 0; v < 4; ++v) P.img[v] = d_imgs[v < nviews ? v : 0];
+  P.source = d_source; P.T = d_T; P.out = d_out;
+  P.H = H; P.W = W; P.Ho = Ho; P.Wo = Wo;
+  P.stepx = linstep(Wo); P.stepy = linstep(Ho);
+  P.aux = d_aux;
+  P.half_w = mode == SS2_MODE_NORMAL ? 0.5f * W : 0.5f * (W - 1);
+  P.half_h = mode == SS2_MODE_NORMAL ? 0.5f * H : 0.5f * (H - 1);
+  if (tps == SS2_TPS_LATTICE && d_aux && d_nodes && tps_lattice_supported(Ho, Wo))
+    return nviews == 3 ? lattice_launch<3, 3, true>(ctx, P, nframes, mode, d_nodes, st)
+                       : lattice_launch<4, 3, true>(ctx, P, nframes, mode, d_nodes, st);
+  dim3 grid(cdiv(Wo, TX), cdiv(Ho, TILE_H), nframes), block(TX, TY);
+  if (nviews == 3) {
+    if (mode == SS2_MODE_NORMAL) tps_warp_exact_kernel<3, 3, SS2_MODE_NORMAL, true><<<grid, block, 0, st>>>(P);
+    else tps_warp_exact_kernel<3, 3, SS2_MODE_FAST, true><<<grid, block, 0, st>>>(P);
+  } else {
+    if (mode == SS2_MODE_NORMAL) tps_warp_exact_kernel<4, 3, SS2_MODE_NORMAL, true><<<grid, block, 0, st>>>(P);
+    else tps_warp_exact_kernel<4, 3, SS2_MODE_FAST, true><<<grid, block, 0, st>>>(P);
+  }
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;
 }

@@ -132,6 +132,74 @@ def three_view_stable(img1_list, img2_list, img3_list, w12m1, w12m2, w23m1, w23m
     return [host[k] for k in range(host.shape[0])]
 
 
+# ------------------------------------------------------------------------------------------
+# N views (BASELINE.json config 5): chain of pairs (1,2), (2,3), .., (N-1,N); identical to the three-view glue for N = 3
+# ------------------------------------------------------------------------------------------
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def nview_align(pair_meshes, img_h, img_w):
+    """pair_meshes: list of N-1 (meshA, meshB) smooth meshes [n,7,9,2] @480x360 -> (shifted [2(N-1),n,7,9,2],
+    mids [N-2,n,7,9,2], minmax1 [4] CUDA = provisional canvas (xmin,xmax,ymin,ymax))."""
+    ctx = _lib.context()
+    flat = [_lib.dev_f32(t).reshape(-1, 7, 9, 2) for pr in pair_meshes for t in pr]
+    nviews, n = len(pair_meshes) + 1, flat[0].shape[0]
+    dev = flat[0].device
+    shifted = torch.empty(2 * (nviews - 1), n, 7, 9, 2, device=dev, dtype=torch.float32)
+    mids = torch.empty(max(nviews - 2, 1), n, 7, 9, 2, device=dev, dtype=torch.float32)
+    mm = torch.empty(4, device=dev, dtype=torch.float32)
+    ctx.check(ctx.lib.ss2_nview_align(ctx.handle, _ptr_array(flat), nviews, n, int(img_h), int(img_w), _lib.ptr(shifted),
+                                      _lib.ptr(mids), _lib.ptr(mm), _lib.cur_stream()))
+    return shifted, mids, mm
+
+
+def nview_remap(shifted, mids, minmax1_host):
+    """-> (meshes [N,n,7,9,2] in provisional-canvas pixels, minmax2 [4] CUDA = new canvas)."""
+    ctx = _lib.context()
+    nviews, n = shifted.shape[0] // 2 + 1, shifted.shape[1]
+    meshes = torch.empty(nviews, n, 7, 9, 2, device=shifted.device, dtype=torch.float32)
+    mm2 = torch.empty(4, device=shifted.device, dtype=torch.float32)
+    h = (ctypes.c_float * 4)(*[float(v) for v in minmax1_host])
+    ctx.check(ctx.lib.ss2_nview_remap(ctx.handle, nviews, n, _lib.ptr(shifted), _lib.ptr(mids), h, _lib.ptr(meshes),
+                                      _lib.ptr(mm2), _lib.cur_stream()))
+    return meshes, mm2
+
+
+def nview_frames(imgs, meshes, minmax2_host, mode="NORMAL", tps=None, out=None):
+    """imgs: list of N CUDA tensors [n,3,H,W]; meshes [N,n,7,9,2] -> fused [n,3,Ho,Wo] (one fused pass, 2 <= N <= 4)."""
+    from .utils import torch_tps_transform as tt
+    ctx = _lib.context()
+    imgs = [_lib.dev_f32(t) for t in imgs]
+    n, _, H, W = imgs[0].shape
+    Ho, Wo = canvas_size(minmax2_host)
+    if out is None:
+        out = torch.empty(n, 3, Ho, Wo, device=imgs[0].device, dtype=torch.float32)
+    h = (ctypes.c_float * 4)(*[float(v) for v in minmax2_host])
+    ctx.check(ctx.lib.ss2_nview_frames(ctx.handle, _ptr_array(imgs), _lib.ptr(_lib.dev_f32(meshes)), len(imgs), n, H, W, h,
+                                       _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps, _lib.ptr(out),
+                                       _lib.cur_stream()))
+    return out
+
+
+def nview_stable(img_lists, pair_meshes, warp_mode="NORMAL", group=None):
+    """N image streams (lists of CUDA/CPU tensors [n,3,H,W] or stacked tensors) + the smooth meshes of the N-1 stitched
+    pairs -> fused [n,3,Ho,Wo].  With a torch.distributed `group` (or a default group initialised) of more than one
+    rank, the frames are this rank's temporal shard and the two canvases are all-reduced (allreduce_canvas)."""
+    import torch.distributed as dist
+    imgs = [torch.cat(list(t), 0) if isinstance(t, (list, tuple)) else t for t in img_lists]
+    imgs = [_lib.dev_f32(t) for t in imgs]
+    _, _, H, W = imgs[0].shape
+    sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    shifted, mids, mm1 = nview_align(pair_meshes, H, W)
+    if sharded:
+        mm1 = allreduce_canvas(mm1, group)
+    meshes, mm2 = nview_remap(shifted, mids, mm1.cpu().tolist())
+    if sharded:
+        mm2 = allreduce_canvas(mm2, group)
+    return nview_frames(imgs, meshes, mm2.cpu().tolist(), warp_mode), meshes, mm2
+
+
 def get_stable_sqe(img1_list, img2_list, smooth_mesh1, smooth_mesh2, warp_mode="NORMAL", fusion_mode="AVERAGE"):
     """Drop-in for test_online_tra.py:96-154 (AVERAGE and LINEAR fusion): lists of [1,3,H,W] fp32 0..255
     frames, smooth meshes [1,N,7,9,2] -> (list of [Ho,Wo,3] numpy frames, out_width, out_height)."""
@@ -360,18 +428,17 @@ def allreduce_canvas(minmax, group=None):
     return v * sign
 
 
-def stitch_stream_sharded(spatial_net, temporal_net, smooth_net, lr1, lr2, hr1, hr2, input_halo, mode="NORMAL",
-                          tps=None, group=None):
-    """This rank's part of a temporally sharded stream.  lr1, lr2 [input_halo+F,3,360,480]
-    (rank > 0 also gets frame start-1 for TemporalNet), hr1, hr2 [F,3,H,W]; all CUDA.
-    Returns (fused [F,3,Ho,Wo], smooth_mesh1 [F,7,9,2], smooth_mesh2) - identical to the rows
-    [start, stop) of the single-process result."""
+def stream_meshes_sharded(spatial_net, temporal_net, smooth_net, lr1, lr2, input_halo, frames, group=None):
+    """Smooth meshes of this rank's `frames` frames of a temporally sharded stream.  lr1, lr2
+    [input_halo+frames,3,360,480] (rank > 0 also gets frame start-1 for TemporalNet).  One all-gather of the raw
+    per-frame motions (4 KB per frame) rebuilds the 6-frame SmoothNet context locally.  Returns (S1, S2 [frames,7,9,2])
+    - identical to rows [start, stop) of the single-process result."""
     import torch.distributed as dist
     from .spatial_network import build_SpatialNet
     ctx = _lib.context()
     _sync_nets(ctx, spatial_net, temporal_net, smooth_net)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    F = hr1.shape[0]
+    F = int(frames)
     plan = shard_plan(rank, world, F)
     if input_halo != plan["input_halo"] or lr1.shape[0] != F + input_halo:
         raise ValueError("rank %d expects %d halo frame(s) in lr1/lr2" % (rank, plan["input_halo"]))
@@ -407,6 +474,34 @@ def stitch_stream_sharded(spatial_net, temporal_net, smooth_net, lr1, lr2, hr1, 
         ctx.check(ctx.lib.ss2_assemble_smooth(ctx.handle, _lib.ptr(win[key]), plan["nwin"],
                                               1 if plan["with_head"] else 0, _lib.ptr(o), st))
         S.append(o)
+    return S[0], S[1]
+
+
+def stitch_stream_sharded(spatial_net, temporal_net, smooth_net, lr1, lr2, hr1, hr2, input_halo, mode="NORMAL",
+                          tps=None, group=None):
+    """This rank's part of a temporally sharded stream.  lr1, lr2 [input_halo+F,3,360,480]
+    (rank > 0 also gets frame start-1 for TemporalNet), hr1, hr2 [F,3,H,W]; all CUDA.
+    Returns (fused [F,3,Ho,Wo], smooth_mesh1 [F,7,9,2], smooth_mesh2) - identical to the rows
+    [start, stop) of the single-process result."""
+    S1, S2 = stream_meshes_sharded(spatial_net, temporal_net, smooth_net, lr1, lr2, input_halo, hr1.shape[0], group)
     _, _, H, W = hr1.shape
-    mm = allreduce_canvas(canvas_minmax(S[0], S[1], H, W), group).cpu().tolist()
-    return stable_frames(hr1, hr2, S[0], S[1], mm, mode, tps), S[0], S[1]
+    mm = allreduce_canvas(canvas_minmax(S1, S2, H, W), group).cpu().tolist()
+    return stable_frames(hr1, hr2, S1, S2, mm, mode, tps), S1, S2
+
+
+def stitch_nview_stream(spatial_net, temporal_net, smooth_net, lrs, hrs, input_halo=0, mode="NORMAL", group=None):
+    """BASELINE.json config 5: N views (2 <= N <= 4), N-1 stitched pairs (v, v+1), middle-plane chain, one fused N-image
+    resample + AVERAGE blend.  lrs / hrs: lists of N CUDA tensors [input_halo+F,3,360,480] / [F,3,H,W].  Single process,
+    or one temporal shard per rank when torch.distributed is initialised with more than one rank (mesh halo all-gather
+    per pair, the two canvases all-reduced).  Returns (fused [F,3,Ho,Wo], meshes [N,F,7,9,2])."""
+    import torch.distributed as dist
+    sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    F = hrs[0].shape[0]
+    pairs = []
+    for v in range(len(lrs) - 1):
+        if sharded:
+            pairs.append(stream_meshes_sharded(spatial_net, temporal_net, smooth_net, lrs[v], lrs[v + 1], input_halo, F, group))
+        else:
+            pairs.append(stream_meshes(spatial_net, temporal_net, smooth_net, lrs[v], lrs[v + 1]))
+    fused, meshes, _ = nview_stable(hrs, pairs, warp_mode=mode, group=group)
+    return fused, meshes

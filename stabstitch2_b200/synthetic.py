@@ -114,10 +114,11 @@ def smooth_state_dict(seed=2):
 import torch.nn.functional as F  # noqa: E402
 
 
-def synth_frame(t, v, H, W, coherent=True):
+def synth_frame(t, v, H, W, coherent=True, chain=False):
     """Band-limited noise frame, fp32 0..255, [1,3,H,W].  With coherent=True all frames of
     a view share the same texture shifted by a seeded integer random walk (so TemporalNet
-    sees motion); the two views share the texture with a ~35% horizontal offset."""
+    sees motion); the two views share the texture with a ~35% horizontal offset.  chain=True
+    (multi-view streams, v <= 3): view v looks v x 35 % further right, so consecutive views overlap like a pair."""
     g = torch.Generator().manual_seed(1000)
     zh, zw = H // 16 + 8, (W // 16) * 2 + 8
     z = torch.randn(1, 3, zh, zw, generator=g)
@@ -128,7 +129,7 @@ def synth_frame(t, v, H, W, coherent=True):
     gw = torch.Generator().manual_seed(77)
     walk = torch.randint(-2, 3, (4096, 2), generator=gw).cumsum(0)
     dy = 32 + int(walk[t % 4096, 0]) % 32
-    dx = 32 + int(walk[t % 4096, 1]) % 32 + (int(0.35 * W) if v == 1 else 0)
+    dx = 32 + int(walk[t % 4096, 1]) % 32 + (int(0.35 * W) * v if chain else (int(0.35 * W) if v == 1 else 0))
     crop = big[:, :, dy:dy + H, dx:dx + W]
     return ((torch.tanh(crop) + 1.0) * 127.5).contiguous()
 

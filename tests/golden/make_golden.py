@@ -240,6 +240,28 @@ def linear_case(m):
     return {k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
 
 
+def metric_case(m):
+    """Metric path (test_metric_ssd.py): the reference's own inter_grid_loss / intra_grid_loss / l_num_loss on seeded
+    meshes, and its get_stable_sqe (per-view C = 6 warp at 360x480) on two frames of the small stream."""
+    D = m["test_metric_ssd"]
+    g = torch.Generator().manual_seed(21)
+    rig = O.rigid_mesh(1, 360, 480)[:, None]
+    mesh = rig + torch.tensor([30.0, -4.0]) + 6.0 * torch.randn(1, 12, 7, 9, 2, generator=g)
+    mesh[:, 3, 2, 5, 0] += 160.0      # one stretched cell, so that the intra-grid term is not zero
+    path = torch.cumsum(1.5 * torch.randn(1, 12, 7, 9, 2, generator=g), 1)
+    out = {"mesh": mesh, "path": path,
+           "inter": torch.stack([D.inter_grid_loss(mesh[:, k:k + 1]) for k in range(12)]),
+           "intra": torch.stack([D.intra_grid_loss(mesh[:, k:k + 1]) for k in range(12)]),
+           "l2_lag3": D.l_num_loss(path[:, :-6], path[:, 3:-3], 2)}
+    lr = [[O.lowres(O.synth_frame(t, v, STREAM_H, STREAM_W)) for t in range(2)] for v in range(2)]
+    gs = dict(np.load(os.path.join(HERE, "stream_small.npz")))
+    S1, S2 = torch.from_numpy(gs["smooth_mesh1"])[:, :2], torch.from_numpy(gs["smooth_mesh2"])[:, :2]
+    with contextlib.redirect_stdout(io.StringIO()):
+        l1, l2 = D.get_stable_sqe(lr[0], lr[1], S1, S2)
+    out["warp1_frame0"], out["warp2_frame1_rows4"] = l1[0], l2[1][::4]
+    return {k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
     mods = ref_harness.load()
@@ -252,5 +274,7 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(HERE, "threeview.npz"), **threeview_case(mods))
     if not only or "linear" in only:
         np.savez_compressed(os.path.join(HERE, "linear.npz"), **linear_case(mods))
-    for f in ("ops.npz", "stream_small.npz", "threeview.npz", "linear.npz"):
+    if not only or "metric" in only:
+        np.savez_compressed(os.path.join(HERE, "metric.npz"), **metric_case(mods))
+    for f in ("ops.npz", "stream_small.npz", "threeview.npz", "linear.npz", "metric.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -54,7 +54,7 @@ def load():
         torch.nn.Module.cuda = lambda self, *a, **kw: self
 
     # shim 3
-    for name in ("imageio", "skimage", "matplotlib", "matplotlib.pyplot"):
+    for name in ("imageio", "skimage", "skimage.measure", "matplotlib", "matplotlib.pyplot"):
         if name not in sys.modules:
             try:
                 importlib.import_module(name)
@@ -71,7 +71,7 @@ def load():
     saved_mods = {k: sys.modules.get(k) for k in
                   ("grid_res", "utils", "utils.torch_DLT", "utils.torch_homo_transform",
                    "utils.torch_tps_transform", "utils.torch_tps_transform_point",
-                   "spatial_network", "temporal_network", "smooth_network", "test_online_tra")}
+                   "spatial_network", "temporal_network", "smooth_network", "test_online_tra", "test_metric_ssd")}
     for k in saved_mods:
         sys.modules.pop(k, None)
     sys.path.insert(0, REF_DIR)
@@ -83,6 +83,7 @@ def load():
             mods[name] = importlib.import_module(name)
         # the driver script: import its functions without running __main__
         mods["test_online_tra"] = importlib.import_module("test_online_tra")
+        mods["test_metric_ssd"] = importlib.import_module("test_metric_ssd")
     finally:
         sys.path[:] = saved_path
         for k, v in saved_mods.items():

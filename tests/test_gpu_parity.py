@@ -528,6 +528,34 @@ def test_canvas_minmax_bit_exact_and_truncation_window(golden_stream):
     assert width <= 2 * 2 * noise + 1e-4
 
 
+# ---------------------------------------------------------------- the unchanged driver's call sequence
+def test_dropin_replay_matches_batched_path(stream_inputs, golden_stream):
+    """tests/dropin_replay.py: the reference driver's per-frame loops (batch-1 calls, per-frame transformer, torch
+    blend; test_online_tra.py:284-399) through the flat drop-in names, against the batched whole-stream call and the
+    reference's own golden outputs."""
+    from stabstitch2_b200 import pipeline
+    from tests import dropin_replay as R
+    from tests.golden.make_golden import MESH_SCALE_S, MESH_SCALE_T
+    n = R.import_flat()
+    s, t, m = n["SpatialNet"]().cuda().eval(), n["TemporalNet"]().cuda().eval(), n["SmoothNet"]().cuda().eval()
+    s.load_state_dict(Wt.spatial_state_dict(mesh_scale=MESH_SCALE_S), strict=True)
+    t.load_state_dict(Wt.temporal_state_dict(mesh_scale=MESH_SCALE_T), strict=True)
+    m.load_state_dict(Wt.smooth_state_dict(), strict=True)
+    hr, lr = stream_inputs
+    frames, S1, S2 = R.replay(n, s, t, m, lr[0], lr[1], hr[0], hr[1])
+    g = golden_stream
+    assert maxdiff(S1, g["smooth_mesh1"]) < 2e-3 and maxdiff(S2, g["smooth_mesh2"]) < 2e-3
+    assert tuple(frames[0].shape[:2]) == tuple(g["canvas_hw"]) and len(frames) == len(hr[0])
+    d = np.abs(frames[0] - g["frame0"])
+    assert (d > 0.05).mean() < 2e-3 and np.median(d) < 1e-3
+    fused, b1, b2 = pipeline.stitch_stream(s, t, m, torch.cat(lr[0], 0).cuda(), torch.cat(lr[1], 0).cuda(),
+                                           torch.cat(hr[0], 0).cuda(), torch.cat(hr[1], 0).cuda())
+    # batch-1 calls and the batched stream run the same per-image kernels
+    assert maxdiff(S1[0], b1) < 1e-4 and maxdiff(S2[0], b2) < 1e-4
+    db = np.abs(frames[3] - fused[3].permute(1, 2, 0).cpu().numpy())
+    assert (db > 0.05).mean() < 1e-3 and np.median(db) < 1e-3
+
+
 # ---------------------------------------------------------------- LINEAR fusion (SURVEY.md 8f rank 1)
 def test_linear_blender_clean_masks_vs_reference(golden_linear):
     """the driver's linear_blender (test_online_tra.py:34-58) on exact 0/1 masks, where the reference's nonzero-based
@@ -809,3 +837,78 @@ def test_three_view_720p_vs_oracle():
     assert (db > 0.1).mean() < 1e-3 and np.percentile(db, 99) < 6e-2, ((db > 0.1).mean(), np.percentile(db, 99))
     rest = np.abs(fused.numpy()[:, far[0] & far[1] & far[2]])
     assert rest.max() < 256.0 and np.median(rest) < 1e-3
+
+
+# ---------------------------------------------------------------- N views (BASELINE.json config 5)
+def test_nview_equals_three_view(golden_threeview):
+    """the N-view chain is the three-view glue for N = 3: meshes and canvas bit-identical to ss2_three_view_meshes,
+    frames (fused 3-view pass) against the three-warps + blend path and the reference's golden frames"""
+    from stabstitch2_b200 import pipeline
+    from tests.golden.make_golden import threeview_inputs
+    g = golden_threeview
+    w12m1, w12m2, w23m1, w23m2, imgs = threeview_inputs()
+    m1, mid, m3, canvas = pipeline.three_view_meshes(w12m1[0], w12m2[0], w23m1[0], w23m2[0], 96, 128)
+    shifted, mids, mm1 = pipeline.nview_align([(w12m1[0], w12m2[0]), (w23m1[0], w23m2[0])], 96, 128)
+    meshes, mm2 = pipeline.nview_remap(shifted, mids, mm1.cpu().tolist())
+    for got, ref in zip(meshes, (m1, mid, m3)):
+        assert maxdiff(got, ref) == 0.0
+    c, q = canvas.cpu().tolist(), mm2.cpu().tolist()
+    assert (q[0], q[2]) == (c[0], c[1]) and np.float32(q[1]) - np.float32(q[0]) == np.float32(c[2]) \
+        and np.float32(q[3]) - np.float32(q[2]) == np.float32(c[3])
+    stacks = [torch.cat(imgs[v], 0).cuda() for v in range(3)]
+    fused = pipeline.nview_frames(stacks, meshes, q)
+    ref3 = pipeline.three_view_frames(stacks[0], stacks[1], stacks[2], m1, mid, m3, c)
+    assert tuple(fused.shape) == tuple(ref3.shape)
+    assert maxdiff(fused, ref3) < 1e-4          # one fused pass vs three warps + blend: the same per-view arithmetic
+    for k in range(3):
+        d = np.abs(fused[k].cpu().numpy() - g["frames"][k])
+        assert (d > 0.05).mean() < 4e-3 and np.median(d) < 1e-3
+
+
+def test_nview_4_720p_vs_oracle():
+    """four views at 720p (three chained pairs): meshes and canvas against the oracle's N-view restatement, the fused
+    4-view lattice pass against the oracle's frame where the result is well conditioned"""
+    from stabstitch2_b200 import pipeline
+    H, W = 720, 1280
+    g = torch.Generator().manual_seed(8)
+    rig = O.rigid_mesh(1, 360, 480)[:, None]
+
+    def mesh(dx, dy):
+        return rig + torch.tensor([dx, dy]) + 2.5 * torch.randn(1, 1, 7, 9, 2, generator=g)
+    pairs = [(mesh(-80.0, 3.0), mesh(85.0, -2.0)), (mesh(-70.0, 6.0), mesh(95.0, 1.0)), (mesh(-75.0, -4.0), mesh(90.0, 2.0))]
+    imgs = [_smooth_frame(20 + v, H, W) for v in range(4)]
+    with torch.no_grad():
+        rmeshes, wmin, hmin, ow, oh = O.nview_meshes(pairs, H, W)
+    shifted, mids, mm1 = pipeline.nview_align([(a[0], b[0]) for a, b in pairs], H, W)
+    meshes, mm2 = pipeline.nview_remap(shifted, mids, mm1.cpu().tolist())
+    for v in range(4):
+        assert (meshes[v].cpu() - rmeshes[v][0]).abs().max() < 5e-3, v
+    q = mm2.cpu().tolist()
+    assert abs(q[0] - float(wmin)) < 5e-3 and abs(q[1] - q[0] - float(ow)) < 5e-3 and abs(q[3] - q[2] - float(oh)) < 5e-3
+    # the oracle's canvas and meshes for the frame comparison, so both sides sample the same grid
+    ref_mm = [float(wmin), float(wmin + ow), float(hmin), float(hmin + oh)]
+    fused = pipeline.nview_frames([t.cuda() for t in imgs], torch.stack([m[0] for m in rmeshes], 0).cuda(), ref_mm)[0].cpu()
+    Ho, Wo = fused.shape[1:]
+    assert (Ho, Wo) == (int(oh.int()), int(ow.int())) or abs(Ho - int(oh.int())) <= 1
+    nrig = O.norm_mesh(O.rigid_mesh(1, H, W), H, W)
+    warps, cover, far = [], [], []
+    with torch.no_grad():
+        for v in range(4):
+            M = rmeshes[v]
+            tt = torch.stack([M[0, 0, ..., 0] - wmin, M[0, 0, ..., 1] - hmin], 2)[None]
+            src = O.norm_mesh(tt, oh, ow)
+            ax, ay = O.tps_source_coords_fp64(src, nrig, Ho, Wo, W, H)
+            cover.append((ax[0] > 1) & (ax[0] < W - 2) & (ay[0] > 1) & (ay[0] < H - 2))
+            far.append((ax[0] < -1) | (ax[0] > W) | (ay[0] < -1) | (ay[0] > H))
+            w = O.tps_warp(imgs[v], src, nrig, (Ho, Wo))[0]
+            warps.append(w * torch.from_numpy(cover[-1]).float())      # exactly 0 outside, like the lattice resampler
+        ref = warps[0]
+        for v in range(1, 4):
+            ref = O.average_blend(ref, warps[v])
+    settled = np.ones((Ho, Wo), bool)
+    for v in range(4):
+        settled &= cover[v] | far[v]          # every view either clearly inside or clearly outside its image
+    d = (fused - ref).abs().numpy()[:, settled]
+    print("4-view 720p: canvas %dx%d, settled fraction %.2f, max |diff| %.2e, median %.2e" % (Ho, Wo, settled.mean(), d.max(), np.median(d)))
+    assert settled.mean() > 0.9
+    assert (d > 5e-3).mean() < 1e-4 and np.median(d) < 1e-3

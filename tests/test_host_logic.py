@@ -233,3 +233,53 @@ def test_canvas_size_truncation_sweep():
         ref_w = int((torch.tensor(hi) - torch.tensor(lo)).int())
         ref_h = int((torch.tensor(hi_y) - torch.tensor(lo_y)).int())
         assert canvas_size([float(lo), float(hi), float(lo_y), float(hi_y)]) == (ref_h, ref_w)
+
+
+def test_dropin_flat_names_resolve_to_this_package():
+    """with stabstitch2_b200/dropin first on sys.path the driver's import block
+    (test_online_tra.py:7-9,14-15,21-23) resolves to this package, with every name the drivers use."""
+    from tests import dropin_replay as R
+    n = R.import_flat()
+    for k in ("build_SpatialNet", "SpatialNet", "build_TemporalNet", "TemporalNet", "build_SmoothNet", "SmoothNet"):
+        assert n[k].__module__.startswith("stabstitch2_b200."), (k, n[k].__module__)
+    assert n["torch_tps_transform"].transformer.__module__ == "stabstitch2_b200.utils.torch_tps_transform"
+    assert n["torch_tps_transform_point"].transformer.__module__ == "stabstitch2_b200.utils.torch_tps_transform_point"
+    assert (n["grid_res"].GRID_H, n["grid_res"].GRID_W) == (6, 8)
+    # the flat modules did not leak into sys.modules (a later import of the reference must not pick them up)
+    assert "spatial_network" not in sys.modules or not getattr(sys.modules["spatial_network"], "__file__", "").startswith(R.DROPIN)
+
+
+def test_reference_driver_imports_against_the_dropin():
+    """The UNCHANGED reference driver module imports (and finds every name it needs) with the drop-in shims in place
+    of its own model / utils modules.  Build container only (/root/reference is not on the GPU box)."""
+    ref = "/root/reference/Full_model_inference/Codes"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    import subprocess
+    code = r'''
+import sys, types
+for name in ("imageio", "skimage", "skimage.measure", "matplotlib", "matplotlib.pyplot"):
+    try:
+        __import__(name)
+    except Exception:
+        m = types.ModuleType(name)
+        if name == "matplotlib.pyplot":
+            m.rcParams = {}
+        sys.modules[name] = m
+sys.path.insert(0, "%s")                      # the driver's directory (for nothing but the driver itself)
+sys.path.insert(0, "%s")                      # the repository root
+sys.path.insert(0, "%s")                      # the flat-name shims FIRST
+import test_online_tra as D
+import inspect
+assert D.SpatialNet.__module__ == "stabstitch2_b200.spatial_network", D.SpatialNet.__module__
+assert D.build_TemporalNet.__module__ == "stabstitch2_b200.temporal_network"
+assert D.build_SmoothNet.__module__ == "stabstitch2_b200.smooth_network"
+assert D.torch_tps_transform.transformer.__module__ == "stabstitch2_b200.utils.torch_tps_transform"
+assert D.torch_tps_transform_point.transformer.__module__ == "stabstitch2_b200.utils.torch_tps_transform_point"
+assert "fusion_mode" in inspect.signature(D.get_stable_sqe).parameters
+net = D.SpatialNet()
+assert any(k.startswith("regressNet2_part1_ref") for k in net.state_dict())
+print("ok")
+''' % (ref, ROOT, os.path.join(ROOT, "stabstitch2_b200", "dropin"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]

@@ -170,3 +170,63 @@ def test_linear_fusion_against_reference(golden_stream, golden_threeview):
         a, mid, b, wmin, hmin, ow, oh = O.three_view_meshes(w12m1, w12m2, w23m1, w23m2, 96, 128)
         f3 = O.three_view_frame_linear(imgs[0][0], imgs[1][0], imgs[2][0], a[:, 0], mid[:, 0], b[:, 0], wmin, hmin, ow, oh)
     assert np.abs(f3.numpy() - golden_threeview["frames_linear"][0]).max() < 1e-4
+
+
+def test_nview_reduces_to_three_view():
+    """the N-view middle-plane chain (config 5) is the reference's three-view glue for N = 3: bit-identical meshes,
+    canvas and frames; and N = 4 is self-consistent (a chain of three pairs whose shared views already coincide
+    leaves them in place)."""
+    from tests.golden.make_golden import threeview_inputs
+    w12m1, w12m2, w23m1, w23m2, imgs = threeview_inputs()
+    with torch.no_grad():
+        m1, mid, m3, wmin, hmin, ow, oh = O.three_view_meshes(w12m1, w12m2, w23m1, w23m2, 96, 128)
+        out, wmin2, hmin2, ow2, oh2 = O.nview_meshes([(w12m1, w12m2), (w23m1, w23m2)], 96, 128)
+        for a, b in zip(out, (m1, mid, m3)):
+            assert torch.equal(a, b)
+        assert float(wmin) == float(wmin2) and float(hmin) == float(hmin2) and float(ow) == float(ow2) and float(oh) == float(oh2)
+        f3 = O.three_view_frame(imgs[0][0], imgs[1][0], imgs[2][0], m1[:, 0], mid[:, 0], m3[:, 0], wmin, hmin, ow, oh)
+        fn = O.nview_frame([imgs[v][0] for v in range(3)], [m[:, 0] for m in out], wmin2, hmin2, ow2, oh2)
+        assert torch.equal(f3, fn)
+        # N = 4: pair (3,4) built so that its instance of view 3 equals pair (2,3)'s up to a constant shift
+        g = torch.Generator().manual_seed(5)
+        w34m1 = w23m2 + torch.tensor([7.0, -3.0])
+        w34m2 = w23m2 + torch.tensor([150.0, 2.0]) + 2.0 * torch.randn(w23m2.shape, generator=g)
+        out4, a, b, c, d = O.nview_meshes([(w12m1, w12m2), (w23m1, w23m2), (w34m1, w34m2)], 96, 128)
+        assert len(out4) == 4 and all(t.shape == w12m1.shape for t in out4)
+        # shared view 3: both instances coincide after the chain shift, so its middle plane is pair (2,3)'s (shifted) mesh
+        out3, *_ = O.nview_meshes([(w12m1, w12m2), (w23m1, w23m2)], 96, 128)
+        # (the provisional canvases differ, compare shapes via differences that are translation invariant)
+        d4 = out4[2] - out4[1]
+        d3 = None
+        hr = lambda m: torch.stack([m[..., 0] * 128 / 480, m[..., 1] * 96 / 360], 4)  # noqa: E731
+        off = (hr(w12m2) - hr(w23m1)).reshape(1, 3, -1, 2).mean(2)[:, :, None, None, :]
+        d3 = (hr(w23m2) + off) - (hr(w12m2) + hr(w23m1) + off) / 2.0
+        assert (d4 - d3).abs().max() < 2e-4
+
+
+def test_metric_path_against_reference(golden_stream):
+    """metric path (test_metric_ssd.py): the oracle's restatement of the grid losses, the squared-lag loss and the
+    per-view C = 6 warp against the reference's own functions; PSNR / SSIM (skimage, absent) against plain numpy."""
+    from oracle import metric_oracle as MO
+    from tests.golden.make_golden import STREAM_H, STREAM_W
+    g = dict(np.load(os.path.join(GOLDEN, "metric.npz")))
+    mesh, path = T(g["mesh"]), T(g["path"])
+    for k in range(mesh.shape[1]):
+        assert abs(float(MO.inter_grid_loss(mesh[:, k:k + 1])) - g["inter"][k]) < 1e-7
+        assert abs(float(MO.intra_grid_loss(mesh[:, k:k + 1])) - g["intra"][k]) < 1e-6
+    assert g["intra"].max() > 0.1
+    assert abs(float(MO.l_num_loss(path[:, :-6], path[:, 3:-3], 2)) - float(g["l2_lag3"])) < 1e-6
+    assert MO.distortion_score(mesh) == float(np.max(g["inter"] + g["intra"]))
+    lr = [[O.lowres(O.synth_frame(t, v, STREAM_H, STREAM_W)) for t in range(2)] for v in range(2)]
+    S1, S2 = T(golden_stream["smooth_mesh1"])[:, :2], T(golden_stream["smooth_mesh2"])[:, :2]
+    w1 = MO.metric_warp(lr[0][0], S1[:, 0]).numpy().transpose(1, 2, 0)
+    w2 = MO.metric_warp(lr[1][1], S2[:, 1]).numpy().transpose(1, 2, 0)
+    assert np.abs(w1 - g["warp1_frame0"]).max() < 1e-4
+    assert np.abs(w2[::4] - g["warp2_frame1_rows4"]).max() < 1e-4
+    # PSNR / SSIM sanity (skimage itself is not available: parity unpinned, see the module header)
+    rng = np.random.default_rng(0)
+    a = np.concatenate([rng.uniform(0, 255, (40, 50, 3)), np.ones((40, 50, 3))], 2).astype(np.float32)
+    b = a.copy()
+    b[..., :3] += rng.normal(0, 5, (40, 50, 3)).astype(np.float32)
+    assert abs(MO.psnr_overlap(a, b) - 10 * np.log10(255 ** 2 / np.mean((a[..., :3].astype(np.float64) - b[..., :3]) ** 2))) < 1e-9
+    assert 0.5 < MO.ssim_overlap(a, b) < 1.0 and abs(MO.ssim_overlap(a, a) - 1.0) < 1e-12
