@@ -356,12 +356,12 @@ def run_native(args):
         try:
             if u8:
                 pins = [x.clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory() for x in (hr1, hr2)]
-                outs = [torch.empty(F * 3 * (Ho + 64) * (Wo + 64), dtype=torch.uint8).pin_memory() for _ in range(2)]
+                outs = [torch.empty(F * 3 * (Ho + 64) * (Wo + 64), dtype=torch.uint8).pin_memory() for _ in range(3)]
             else:
                 pins = [x.contiguous().pin_memory() for x in (lr1[halo:], lr2[halo:], hr1, hr2)]
                 # every rank stitches ITS chunk as an independent stream here, so its canvas is the chunk's own (a few
                 # pixels off the sharded run's global canvas): size the host buffers with a margin
-                outs = [torch.empty(F * 3 * (Ho + 64) * (Wo + 64), dtype=torch.float32).pin_memory() for _ in range(2)]
+                outs = [torch.empty(F * 3 * (Ho + 64) * (Wo + 64), dtype=torch.float32).pin_memory() for _ in range(3)]
         except RuntimeError as exc:
             ok = 0
             sys.stderr.write("rank %d: pinned host buffers unavailable (%s)\n" % (rank, str(exc).splitlines()[0]))
@@ -374,23 +374,24 @@ def run_native(args):
                     "note": "pinned host buffers could not be allocated on every rank; leg skipped"}
         run = (lambda slot: pipeline.stitch_stream_host_u8_async(s, t, m, slot, *pins, outs[slot], tps=tps)) if u8 else \
               (lambda slot: pipeline.stitch_stream_host_async(s, t, m, slot, *pins, outs[slot], tps=tps))
-        pre = (lambda slot: pipeline.stitch_stream_host_u8_prefetch(slot, *pins)) if u8 else \
-              (lambda slot: pipeline.stitch_stream_host_prefetch(slot, *pins))
         eh, ew = Ho, Wo
-        for i in range(max(2, min(args.warmup, 3))):
-            eh, ew = run(i & 1)
-        pipeline.stitch_stream_host_wait(0)
-        pipeline.stitch_stream_host_wait(1)
+        for i in range(max(3, min(args.warmup, 6))):
+            eh, ew = run(i % 3)
+        for k in range(3):
+            pipeline.stitch_stream_host_wait(k)
         barrier()
         t0 = time.perf_counter()
-        # two chunks in flight: the D2H of chunk k overlaps the H2D + networks of chunk k+1; every chunk's inputs are
-        # copied from pinned host memory and its frames land in pinned host memory
+        # three slots rotating, two-phase calls: chunk i+1 is SUBMITTED (uploads + networks enqueued) before chunk i is
+        # FINISHED (host waits for its data-dependent canvas, then enqueues resample + blend + downloads), so the GPU
+        # never idles behind the canvas read or behind the downloads of chunk i-1; every chunk's inputs are copied from
+        # pinned host memory and its frames land in pinned host memory inside the timed region
+        pipeline.stitch_stream_host_submit(s, t, m, 0, *pins)
         for i in range(args.steps):
-            if i + 1 < args.steps:  # the next chunk's upload runs underneath this chunk's networks
-                pre((i + 1) & 1)
-            run(i & 1)
-        pipeline.stitch_stream_host_wait(0)
-        pipeline.stitch_stream_host_wait(1)
+            if i + 1 < args.steps:
+                pipeline.stitch_stream_host_submit(s, t, m, (i + 1) % 3, *pins)
+            eh, ew = pipeline.stitch_stream_host_finish(i % 3, outs[i % 3], tps=tps)
+        for k in range(3):
+            pipeline.stitch_stream_host_wait(k)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -405,8 +406,8 @@ def run_native(args):
                 "h2d_bytes_per_step": int(sum(p.numel() for p in pins) * esz),
                 "d2h_bytes_per_step": int(F * 3 * eh * ew * esz + 16), "interface": iface,
                 "note": ("per GPU: every rank stitches its own chunk as an independent stream in this leg; " if world > 1 else "") +
-                        "prefetch/_async/_wait through pinned host buffers: every chunk is copied H2D and its frames D2H "
-                        "inside the timed region, two chunks in flight"}
+                        "_submit/_finish/_wait through pinned host buffers: every chunk is copied H2D and its frames D2H "
+                        "inside the timed region, three slots rotating"}
 
     e2e = e2e_fp32 = None
     if not args.no_e2e:

@@ -112,6 +112,16 @@ int ss2_cost_volume_nhwc(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int
 int ss2_ccl_nhwc(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H, int W, int C,
                  float* d_flow, void* stream);
 
+/* ---- network stem (test / reuse entry) ------------------------------------------------------ */
+/* `feature_extractor_stage1[0..3]` of SpatialNet / TemporalNet (spatial_network.py:123-131,
+ * temporal_network.py:65-73) with the BatchNorm already folded by the caller: Conv2d(3,64,7,stride 2,pad 3) + bias +
+ * ReLU + MaxPool2d(3, stride 2, pad 1).  d_x_nchw [B,3,H,W] -> d_out [B,Hp,Wp,64] (NHWC), Hp = ((H-1)/2)/2 + 1 etc.
+ * h_weight HOST [64,3,7,7], h_bias HOST [64] or NULL.  variant 2 = the production kernel (direct tcgen05 convolution
+ * with the pool fused, needs W = 480 and H % 4 == 0), 1 = implicit-GEMM tensor-core stem + pooling kernel,
+ * 0 = exact-fp32 SIMT stem + pooling kernel.  Synchronous (packs the filter on every call). */
+int ss2_stem_pool(ss2_ctx* ctx, const float* d_x_nchw, int B, int H, int W, const float* h_weight, const float* h_bias,
+                  int variant, float* d_out, void* stream);
+
 /* ---- convolution primitive --------------------------------------------------------------- */
 /* nn.Conv2d / nn.Conv3d (bias optional, + optional residual add and ReLU) on NHWC / NDHWC fp32
  * activations - the layer type all three networks are built from (spatial_network.py:147-259,
@@ -238,8 +248,8 @@ int ss2_stitch_stream_host(ss2_ctx* ctx, const float* h_lr1, const float* h_lr2,
 
 /* Pipelined form: _async returns once the resample+blend launches and the D2H copies of this
  * chunk are ENQUEUED (it still blocks for the networks, because the canvas size is data
- * dependent); ss2_stitch_stream_host_wait(slot) blocks until h_out is complete.  With the two
- * slots (0, 1) a caller overlaps the D2H of chunk k with the H2D + networks of chunk k+1.
+ * dependent); ss2_stitch_stream_host_wait(slot) blocks until h_out is complete.  Alternating two of
+ * the slots (0, 1, 2) a caller overlaps the D2H of chunk k with the H2D + networks of chunk k+1.
  * Host buffers of a slot must stay untouched until its wait returns. */
 int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2, const float* h_hr1,
                                  const float* h_hr2, int n, int H, int W, int mode, int tps, float* h_out,
@@ -273,6 +283,20 @@ int ss2_three_view_frames_linear(ss2_ctx* ctx, const float* d_img1, const float*
                                  const float* d_mesh1, const float* d_middle, const float* d_mesh3, int n, int H, int W,
                                  const float* h_canvas, int mode, int tps, float* d_out, void* stream);
 
+/* ---- metric path (test_metric_ssd.py) ---------------------------------------- */
+/* Whole-stream original / smoothed path of one view from the per-window SmoothNet outputs (:417-436):
+ * d_win_ori_path, d_win_smooth_path [nwin,7,7,9,2] (ss2_build_smooth) -> [nwin+6,7,9,2] each. */
+int ss2_assemble_paths(ss2_ctx* ctx, const float* d_win_ori_path, const float* d_win_smooth_path, int nwin,
+                       float* d_ori_path, float* d_smooth_path, void* stream);
+/* d_out[0] = stability score of d_path [n,7,9,2] (:455-466; n >= 7), d_out[1] = distortion score of d_mesh [n,7,9,2]
+ * (max over frames of inter_grid_loss + intra_grid_loss, :37-88,470-479).  Either input may be NULL. */
+int ss2_metric_scores(ss2_ctx* ctx, const float* d_path, const float* d_mesh, int n, float* d_out, void* stream);
+/* PSNR / SSIM of two warped views inside their overlap (:513-518): d_warp1, d_warp2 [n,6,H,W] (image planes 0..2,
+ * warped ones planes 3..5, the C = 6 output of ss2_tps_warp) -> d_psnr[n], d_ssim[n]; skimage 0.15 compare_psnr /
+ * compare_ssim(multichannel=True) semantics (fp64 accumulation). */
+int ss2_metric_psnr_ssim(ss2_ctx* ctx, const float* d_warp1, const float* d_warp2, int n, int H, int W, float* d_psnr,
+                         float* d_ssim, void* stream);
+
 /* ---- uint8 host edges (test_online_tra.py:252-264,152,414) ------------- */
 /* What the reference's driver does to a decoded frame before the networks, on the device:
  * d_u8 [n,H,W,3] uint8 (cv2.imread layout, BGR) -> d_hr [n,3,H,W] fp32 0..255 (astype(float32) + transpose) and
@@ -293,6 +317,20 @@ int ss2_stitch_stream_host_u8_async(ss2_ctx* ctx, int slot, const uint8_t* h_bgr
                                     int* out_w, float* h_smooth_mesh1, float* h_smooth_mesh2);
 int ss2_stitch_stream_host_u8_prefetch(ss2_ctx* ctx, int slot, const uint8_t* h_bgr1, const uint8_t* h_bgr2, int n,
                                        int H, int W);
+
+/* Two-phase form of the _async calls, for full overlap: _submit only ENQUEUES a chunk's uploads (unless
+ * prefetched), front end and networks and returns at once; _finish waits for that chunk's canvas, enqueues its
+ * resample + blend and frame downloads and returns the output shape (arguments as in the _async call of the same
+ * interface; h_out uint8 after a _u8_submit, float otherwise).  Submitting chunk k+1 before finishing chunk k keeps
+ * the GPU busy while the host waits for chunk k's data-dependent canvas.  A _submit blocks until the slot's previous
+ * downloads are complete, so rotate all THREE slots in this form (with two, the submit of chunk k+1 would wait for
+ * the downloads of chunk k-1 and the networks of chunk k+1 would start late). */
+int ss2_stitch_stream_host_submit(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2, const float* h_hr1,
+                                  const float* h_hr2, int n, int H, int W);
+int ss2_stitch_stream_host_u8_submit(ss2_ctx* ctx, int slot, const uint8_t* h_bgr1, const uint8_t* h_bgr2, int n, int H,
+                                     int W);
+int ss2_stitch_stream_host_finish(ss2_ctx* ctx, int slot, int mode, int tps, void* h_out, int64_t out_capacity,
+                                  int* out_h, int* out_w, float* h_smooth_mesh1, float* h_smooth_mesh2);
 
 #ifdef __cplusplus
 }

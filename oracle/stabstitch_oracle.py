@@ -9,8 +9,9 @@ it, and only as the checker / the timed CPU baseline - the product path
 Parity pinning: the reference (nie-lang/StabStitch2 @ 646dad0) ships NO tests, golden
 vectors or fixtures for this path, so the oracle is pinned against
 OUTPUTS OF THE REFERENCE ITSELF, imported unmodified in the build container
-(tests/golden/ref_harness.py) - see tests/test_oracle_vs_reference.py (live, container only)
-and the committed fixtures in tests/golden/*.npz generated by tests/golden/make_golden.py.
+(tests/golden/ref_harness.py): tests/golden/make_golden.py runs the reference on seeded inputs
+(container only, /root/reference does not travel) and commits its outputs as
+tests/golden/*.npz; tests/test_oracle_golden.py checks every oracle function against them.
 
 All file:line citations are relative to /root/reference/Full_model_inference/Codes/.
 Weights travel as a plain `state_dict` (name -> tensor) with the reference's key names.

@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE (see stabstitch_oracle.py header).  The trained weights are 
 reference repo (Google-Drive links only, Full_model_inference/README.md:2-4) and there is no
 network, so both the oracle and the CUDA path load the SAME seeded dicts made here.  Key
 lists follow SURVEY.md Appendix B and are verified against the live reference modules'
-`load_state_dict(strict=True)` in tests/test_oracle_vs_reference.py.
+`load_state_dict(strict=True)` in tests/golden/make_golden.py:132-134 (run in the build container).
 """
 import math
 

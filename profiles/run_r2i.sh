@@ -1,0 +1,13 @@
+#!/bin/bash
+# round-2 GPU session I: two-phase host pipeline, double-buffered cost volume; launch list of the bench step
+mkdir -p gpurun_out
+( time timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15 ) > gpurun_out/r2i_pytest.log 2>&1
+timeout 600 python bench.py > gpurun_out/r2i_bench.json 2> gpurun_out/r2i_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2i_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-gpu-eager > gpurun_out/r2i_ncu_bench.log 2>&1
+python profiles/launch_summary.py gpurun_out/r2i_launches.csv > gpurun_out/r2i_launches_summary.txt 2>&1
+tail -4 gpurun_out/r2i_pytest.log; python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r2i_bench.json').read().strip().splitlines() if l.startswith('{')][-1])
+print({k:d[k] for k in ['value','ms_per_step']}, 'e2e', d['e2e']['value'], d['e2e_fp32_interface']['value'], 'frac', d['roofline']['frac'], 'tensor', d['roofline_tensor']['achieved'], d['roofline_tensor']['kernel_ms_per_step'])
+PY
+head -20 gpurun_out/r2i_launches_summary.txt

@@ -37,6 +37,7 @@ SIGNATURES = {
     "ss2_cost_volume_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ss2_ccl_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ss2_conv_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, ctypes.POINTER(_i64), _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "ss2_stem_pool": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "ss2_spatial_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "ss2_build_spatial": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "ss2_spatial_tail": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
@@ -62,6 +63,9 @@ SIGNATURES = {
     "ss2_nview_align": (_i, [_vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ss2_nview_remap": (_i, [_vp, _i, _i, _vp, _vp, _fp, _vp, _vp, _vp]),
     "ss2_nview_frames": (_i, [_vp, ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _fp, _i, _i, _vp, _vp]),
+    "ss2_assemble_paths": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ss2_metric_scores": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "ss2_metric_psnr_ssim": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "ss2_load_frames_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "ss2_frames_to_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "ss2_stitch_stream_host_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64,
@@ -69,6 +73,9 @@ SIGNATURES = {
     "ss2_stitch_stream_host_u8_async": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64,
                                              ctypes.POINTER(_i), ctypes.POINTER(_i), _vp, _vp]),
     "ss2_stitch_stream_host_u8_prefetch": (_i, [_vp, _i, _vp, _vp, _i, _i, _i]),
+    "ss2_stitch_stream_host_submit": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "ss2_stitch_stream_host_u8_submit": (_i, [_vp, _i, _vp, _vp, _i, _i, _i]),
+    "ss2_stitch_stream_host_finish": (_i, [_vp, _i, _i, _i, _vp, _i64, ctypes.POINTER(_i), ctypes.POINTER(_i), _vp, _vp]),
 }
 
 _lib = None
@@ -163,6 +170,22 @@ def ptr(t):
 
 def cur_stream():
     return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def stem_pool(x, weight, bias=None, variant=2):
+    """ss2_stem_pool: x [B,3,H,W] CUDA fp32 (NCHW), weight [64,3,7,7], bias [64] -> [B,Hp,Wp,64] (NHWC): conv 7x7 stride 2
+    pad 3 + bias + ReLU + max-pool 3x3 stride 2 pad 1.  variant 2 = fused direct kernel, 1 = implicit GEMM + pool kernel,
+    0 = SIMT fp32.  Test / reuse entry for the stem kernels."""
+    ctx = context()
+    x = dev_f32(x)
+    B, _, H, W = x.shape
+    hc, wc = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(B, (hc - 1) // 2 + 1, (wc - 1) // 2 + 1, 64, device=x.device, dtype=torch.float32)
+    wh = weight.detach().to("cpu", torch.float32).contiguous()
+    bh = bias.detach().to("cpu", torch.float32).contiguous() if bias is not None else None
+    ctx.check(ctx.lib.ss2_stem_pool(ctx.handle, ptr(x), B, H, W, _vp(wh.data_ptr()),
+                                    _vp(bh.data_ptr()) if bh is not None else _vp(0), int(variant), ptr(out), cur_stream()))
+    return out
 
 
 def conv_nhwc(x, weight, bias=None, stride=1, pad=0, pad_d=0, relu=False, residual=None, use_tc=True):

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libss2.so")
-SOURCES = ["api.cu", "tps.cu", "geom.cu", "conv.cu", "conv_tc.cu", "conv_dc.cu", "corr.cu", "smooth.cu", "nets.cu", "stream.cu", "edges.cu", "linear.cu"]
+SOURCES = ["api.cu", "tps.cu", "geom.cu", "conv.cu", "conv_tc.cu", "conv_dc.cu", "conv_stem.cu", "corr.cu", "smooth.cu", "nets.cu", "stream.cu", "edges.cu", "linear.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

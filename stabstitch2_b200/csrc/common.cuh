@@ -37,6 +37,10 @@ struct ConvLayer {
   // 7x7 stride-2 stem with 3 input channels: wk_hi/lo are [CoutP][7 * 32], k = kh * 32 + kw * 4 + c (one filter row =
   // 8 NHWC4 pixels, the eighth and the fourth channel are zero); consumed by conv_tc_stem_launch
   bool stem_k32 = false;
+  // the same stem for the direct kernel (conv_stem.cu): [64][7 * 32], k = kh * 32 + (kw & 1) * 16 + (kw >> 1) * 4 + c
+  // (even filter columns, then odd filter columns + one zero pixel)
+  float* ws_hi = nullptr;
+  float* ws_lo = nullptr;
 };
 
 // An activation tensor: plain fp32 values and (for the tensor-core layers that consume it) the
@@ -130,7 +134,8 @@ struct ss2_ctx {
   bool lag_tables_ready = false;
   bool gauss_ready = false;  // linear.cu: 21-tap Gaussian in constant memory
   int tc_passes = 3;  // 3 = split-TF32 (fp32-grade), 1 = plain TF32
-  int use_tc_stem = 1;  // tensor-core 7x7 stem (SS2_TC_STEM=0: exact-fp32 SIMT stem)
+  int use_tc_stem = 2;  // SS2_TC_STEM: 2 = direct tensor-core stem with the max-pool fused (conv_stem.cu), 1 = implicit-GEMM
+                        // tensor-core stem + pool kernel, 0 = exact-fp32 SIMT stem + pool kernel
   int use_dc = 1;     // direct 3x3 kernel (conv_dc.cu) for eligible layers; SS2_CONV_DC=0 disables
 };
 
@@ -293,6 +298,11 @@ int nchw_to_nhwc4_pad_split_launch(ss2_ctx* ctx, const float* d_in, int B, int H
 // conv_tc.cu: 7x7 stride-2 stem on the tensor cores from the padded split planes above; out [B, Ho, Wo, 64] (ReLU)
 int conv_tc_stem_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_hi, const float* d_lo, int B, int H, int W,
                         int Hp, int Wp, const ActRef& out, int relu, cudaStream_t st);
+// conv_stem.cu: direct 7x7 stride-2 stem + ReLU + 3x3 stride-2 max-pool in one kernel; x NCHW [B,3,H,W] -> out [B,H/4,W/4,64]
+bool conv_stem_direct_eligible(const ConvLayer& L, int H, int W);
+size_t conv_stem_direct_workspace_floats(int B, int H);
+int conv_stem_pool_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_x_nchw, int B, int H, int W, float* d_work,
+                          const ActRef& out, cudaStream_t st);
 int nchw_to_nhwc4_launch(ss2_ctx* ctx, const float* d_in, int B, int C, int H, int W, float* d_out,
                          cudaStream_t st);
 // corr.cu

@@ -54,20 +54,28 @@ cost_volume_kernel(const float4* __restrict__ x1, const float4* __restrict__ x2,
 // x1 (64 px) and the x2 halo ((8+2sr)^2 px) in shared memory 32 channels at a time, and every
 // thread accumulates 2 horizontally adjacent pixels x up to 3 displacement rows x (2sr+1)
 // displacements in registers: one x2 float4 from shared memory feeds both pixels (7 FMAs per
-// LDS.128).  Results go through shared memory so that the NHWC rows (and their tf32 split) are
-// written with coalesced float4 stores.
+// LDS.128).  The channel chunks are double buffered with cp.async (zero fill outside the image =
+// the reference's F.pad): round 1's version staged each chunk with plain loads between two
+// barriers and spent its time waiting for them (219 us per launch for 18 us of FMA work).
+// Results go through shared memory so that the NHWC rows (and their tf32 split) are written with
+// coalesced float4 stores.
 // ------------------------------------------------------------------------------------------
 #define CVT 8          // tile edge
 #define CV_CK 32       // channels per stage
 #define CV_LD 36       // padded row length (floats): conflict-free LDS.128 across 8 lanes
 
+__device__ __forceinline__ void cv_cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+
 template <int SR>
 __global__ void __launch_bounds__(128)
 cost_volume_tiled_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int H, int W, int CP, ActRef out) {
   constexpr int KD = 2 * SR + 1, HALO = CVT + 2 * SR, NJ = (KD + 3) / 4;
+  constexpr int STAGE = (CVT * CVT + HALO * HALO) * CV_LD;   // floats per buffer
   extern __shared__ __align__(16) float sm[];
-  float* s1 = sm;                         // [64][CV_LD]
-  float* s2 = sm + CVT * CVT * CV_LD;     // [HALO*HALO][CV_LD]
   const int b = blockIdx.z, ty0 = blockIdx.y * CVT, tx0 = blockIdx.x * CVT;
   const int tid = threadIdx.x, pp = tid & 31, g = tid >> 5;
   const int py = pp >> 2, px = (pp & 3) * 2;  // pixel pair (py, px), (py, px+1) of the tile
@@ -79,25 +87,35 @@ cost_volume_tiled_kernel(const float* __restrict__ x1, const float* __restrict__
     for (int jj = 0; jj < NJ; ++jj)
 #pragma unroll
       for (int i = 0; i < KD; ++i) acc[a][jj][i] = 0.f;
-  for (int c0 = 0; c0 < 128; c0 += CV_CK) {
-    __syncthreads();
-    // stage x1 tile and x2 halo (zero outside the image), 8 float4 per pixel
+  // stage x1 tile and x2 halo of channel chunk c0 into buffer `buf` (zero outside the image), 8 float4 per pixel
+  auto stage = [&](int buf, int c0) {
+    float* s1 = sm + buf * STAGE;
+    float* s2 = s1 + CVT * CVT * CV_LD;
     for (int e = tid; e < CVT * CVT * (CV_CK / 4); e += 128) {
       const int p = e / (CV_CK / 4), q = e % (CV_CK / 4);
       const int y = ty0 + p / CVT, x = tx0 + p % CVT;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (y < H && x < W) v = __ldg(reinterpret_cast<const float4*>(x1 + (img + (size_t)y * W + x) * 128 + c0) + q);
-      *reinterpret_cast<float4*>(s1 + p * CV_LD + q * 4) = v;
+      const bool ok = y < H && x < W;
+      cv_cp_async16(s1 + p * CV_LD + q * 4, ok ? x1 + (img + (size_t)y * W + x) * 128 + c0 + q * 4 : x1, ok);
     }
     for (int e = tid; e < HALO * HALO * (CV_CK / 4); e += 128) {
       const int p = e / (CV_CK / 4), q = e % (CV_CK / 4);
       const int y = ty0 - SR + p / HALO, x = tx0 - SR + p % HALO;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W)
-        v = __ldg(reinterpret_cast<const float4*>(x2 + (img + (size_t)y * W + x) * 128 + c0) + q);
-      *reinterpret_cast<float4*>(s2 + p * CV_LD + q * 4) = v;
+      const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+      cv_cp_async16(s2 + p * CV_LD + q * 4, ok ? x2 + (img + (size_t)y * W + x) * 128 + c0 + q * 4 : x2, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0, 0);
+  for (int ck = 0; ck < 128 / CV_CK; ++ck) {
+    if (ck + 1 < 128 / CV_CK) {
+      stage((ck + 1) & 1, (ck + 1) * CV_CK);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const float* s1 = sm + (ck & 1) * STAGE;
+    const float* s2 = s1 + CVT * CVT * CV_LD;
 #pragma unroll 2
     for (int q = 0; q < CV_CK / 4; ++q) {
       const float4 a0 = *reinterpret_cast<const float4*>(s1 + (py * CVT + px) * CV_LD + q * 4);
@@ -116,6 +134,7 @@ cost_volume_tiled_kernel(const float* __restrict__ x1, const float* __restrict__
         }
       }
     }
+    __syncthreads();   // all reads of this buffer are done before the chunk after next is staged into it
   }
   // results -> shared [64][CP] -> coalesced NHWC rows
   __syncthreads();
@@ -152,13 +171,13 @@ int cost_volume_launch(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B
   if (B <= 0) return SS2_OK;
   if (C == 128 && (sr == 5 || sr == 3) && CP <= 128 && (CP & 3) == 0) {
     const int halo = CVT + 2 * sr;
-    const size_t smem = (size_t)(CVT * CVT + halo * halo) * CV_LD * sizeof(float);
+    const size_t smem = (size_t)2 * (CVT * CVT + halo * halo) * CV_LD * sizeof(float);   // two channel-chunk buffers
     dim3 g(cdiv(W, CVT), cdiv(H, CVT), B);
     static bool attr_dev[16] = {false};  // per device: function attributes live in the device's context
     bool& attr = attr_dev[ctx->device & 15];
     if (!attr) {
-      SS2_CUDA(ctx, cudaFuncSetAttribute(cost_volume_tiled_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      SS2_CUDA(ctx, cudaFuncSetAttribute(cost_volume_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      SS2_CUDA(ctx, cudaFuncSetAttribute(cost_volume_tiled_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+      SS2_CUDA(ctx, cudaFuncSetAttribute(cost_volume_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
       attr = true;
     }
     if (sr == 5) cost_volume_tiled_kernel<5><<<g, 128, smem, st>>>(d_x1, d_x2, H, W, CP, out);

@@ -131,6 +131,20 @@ static int pack_conv(ss2_ctx* ctx, int net, const std::string& wkey, const std::
     SS2_TRY(upload(ctx, hi, &L->wk_hi));
     SS2_TRY(upload(ctx, lo, &L->wk_lo));
     L->stem_k32 = true;
+    if (L->CoutP == 64) {   // direct kernel: even filter columns first, then the odd ones (conv_stem.cu)
+      std::vector<float> shi(hi.size(), 0.f), slo(lo.size(), 0.f);
+      for (int o = 0; o < Cout; ++o)
+        for (int kh = 0; kh < 7; ++kh)
+          for (int kw = 0; kw < 7; ++kw)
+            for (int c = 0; c < 3; ++c) {
+              const size_t from = (size_t)o * Ktot + kh * 32 + kw * 4 + c;
+              const size_t to = (size_t)o * Ktot + kh * 32 + (kw & 1) * 16 + (kw >> 1) * 4 + c;
+              shi[to] = hi[from];
+              slo[to] = lo[from];
+            }
+      SS2_TRY(upload(ctx, shi, &L->ws_hi));
+      SS2_TRY(upload(ctx, slo, &L->ws_lo));
+    }
   }
   L->bias = nullptr;
   if (has_bias) {
@@ -279,9 +293,10 @@ static int run_block(ss2_ctx* ctx, const ResBlock& b, const ActRef& x, int NB, i
   return SS2_OK;
 }
 
-// x: NCHW [NB,3,H,W] -> f64 [NB,H/8,W/8,128] (and f32 [NB,.,.,256] when stage2)
-static int run_backbone(ss2_ctx* ctx, const Backbone& bb, const float* x_nchw, int NB, int H, int W, bool stage2,
-                        float** f64, int* h64, int* w64, float** f32, int* h32, int* w32, cudaStream_t st) {
+// stem as two kernels (implicit-GEMM tensor-core or SIMT 7x7 conv, then the pooling kernel): shapes the direct kernel
+// does not take, and SS2_TC_STEM < 2
+static int run_stem_pool(ss2_ctx* ctx, const Backbone& bb, const float* x_nchw, int NB, int H, int W, ActRef* out, int* Ho,
+                         int* Wo, cudaStream_t st) {
   int d, h, w;
   conv_out_dims(bb.stem, 1, H, W, &d, &h, &w);
   ARENA(s, float, (size_t)NB * h * w * 64);
@@ -303,8 +318,26 @@ static int run_backbone(ss2_ctx* ctx, const Backbone& bb, const float* x_nchw, i
   const int hp = (h + 2 - 3) / 2 + 1, wp = (w + 2 - 3) / 2 + 1;
   ARENA_ACT(p, (size_t)NB * hp * wp * 64);
   SS2_TRY(maxpool_launch(ctx, s, NB, h, w, 64, 3, 2, 1, p, st));
-  ActRef cur = p;
-  h = hp; w = wp;
+  *out = p; *Ho = hp; *Wo = wp;
+  return SS2_OK;
+}
+
+// x: NCHW [NB,3,H,W] -> f64 [NB,H/8,W/8,128] (and f32 [NB,.,.,256] when stage2)
+static int run_backbone(ss2_ctx* ctx, const Backbone& bb, const float* x_nchw, int NB, int H, int W, bool stage2,
+                        float** f64, int* h64, int* w64, float** f32, int* h32, int* w32, cudaStream_t st) {
+  int d, h, w;
+  conv_out_dims(bb.stem, 1, H, W, &d, &h, &w);
+  ActRef cur;
+  if (ctx->use_tc && ctx->use_tc_stem >= 2 && conv_stem_direct_eligible(bb.stem, H, W)) {
+    // direct tensor-core stem with the max-pool in its epilogue: the conv map is never written
+    ARENA(xw, float, conv_stem_direct_workspace_floats(NB, H));
+    ARENA_ACT(p, (size_t)NB * (H / 4) * (W / 4) * 64);
+    SS2_TRY(conv_stem_pool_launch(ctx, bb.stem, x_nchw, NB, H, W, xw, p, st));
+    cur = p;
+    h = H / 4; w = W / 4;
+  } else {
+    SS2_TRY(run_stem_pool(ctx, bb, x_nchw, NB, H, W, &cur, &h, &w, st));
+  }
   SS2_TRY(run_block(ctx, bb.l1[0], cur, NB, h, w, &cur, &h, &w, st));
   SS2_TRY(run_block(ctx, bb.l1[1], cur, NB, h, w, &cur, &h, &w, st));
   SS2_TRY(run_block(ctx, bb.l2[0], cur, NB, h, w, &cur, &h, &w, st));
@@ -558,6 +591,60 @@ extern "C" int ss2_conv_nhwc(ss2_ctx* ctx, const float* d_in, int B, int D, int 
   }
   cudaStreamSynchronize(st);
   if (split) cudaFree(split);
+  while (ctx->owned.size() > owned0) { cudaFree(ctx->owned.back()); ctx->owned.pop_back(); }
+  return rc;
+}
+
+// Test / reuse entry for the network stem (conv 7x7 s2 p3 + bias + ReLU + max-pool 3x3 s2 p1), see include/ss2.h
+extern "C" int ss2_stem_pool(ss2_ctx* ctx, const float* d_x_nchw, int B, int H, int W, const float* h_weight,
+                             const float* h_bias, int variant, float* d_out, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (!d_x_nchw || !h_weight || !d_out || B <= 0 || H < 8 || W < 8 || variant < 0 || variant > 2)
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stem_pool: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  SS2_TRY(ss2_workspace_enter(ctx, st));
+  HostTensor wt, bt;
+  wt.shape = {64, 3, 7, 7};
+  wt.data.assign(h_weight, h_weight + wt.numel());
+  ctx->host_weights[0]["__stem.weight"] = wt;
+  if (h_bias) {
+    bt.shape = {64};
+    bt.data.assign(h_bias, h_bias + 64);
+    ctx->host_weights[0]["__stem.bias"] = bt;
+  }
+  Backbone bb;
+  const size_t owned0 = ctx->owned.size();
+  int rc = pack_conv(ctx, 0, "__stem.weight", "", h_bias ? "__stem.bias" : "", 2, 3, 0, 0, &bb.stem);
+  ctx->host_weights[0].erase("__stem.weight");
+  ctx->host_weights[0].erase("__stem.bias");
+  const int saved_tc = ctx->use_tc, saved_stem = ctx->use_tc_stem;
+  ctx->use_tc = variant > 0;
+  ctx->use_tc_stem = variant;
+  auto run = [&]() -> int {
+    const int ho = ((H + 6 - 7) / 2 + 1 + 2 - 3) / 2 + 1, wo = ((W + 6 - 7) / 2 + 1 + 2 - 3) / 2 + 1;
+    SS2_TRY(ss2_ensure_arena(ctx, (size_t)B * ((size_t)(H + 6) * (W + 16) * 8 + (size_t)(H / 2 + 3) * 8 * 1024 +
+                                              (size_t)(H / 2 + 1) * (W / 2 + 1) * 64 + (size_t)3 * ho * wo * 64 + 4096) * sizeof(float) +
+                                      ((size_t)4 << 20)));
+    ctx->arena.reset();
+    ActRef o;
+    int h, w;
+    if (variant == 2) {
+      if (!conv_stem_direct_eligible(bb.stem, H, W))
+        return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "ss2_stem_pool: the direct kernel takes W = 480, H % 4 == 0");
+      ARENA(xw, float, conv_stem_direct_workspace_floats(B, H));
+      ARENA_ACT(p, (size_t)B * (H / 4) * (W / 4) * 64);
+      SS2_TRY(conv_stem_pool_launch(ctx, bb.stem, d_x_nchw, B, H, W, xw, p, st));
+      o = p; h = H / 4; w = W / 4;
+    } else {
+      SS2_TRY(run_stem_pool(ctx, bb, d_x_nchw, B, H, W, &o, &h, &w, st));
+    }
+    SS2_CUDA(ctx, cudaMemcpyAsync(d_out, o.v, (size_t)B * h * w * 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return SS2_OK;
+  };
+  if (rc == SS2_OK) rc = run();
+  ctx->use_tc = saved_tc;
+  ctx->use_tc_stem = saved_stem;
+  cudaStreamSynchronize(st);
   while (ctx->owned.size() > owned0) { cudaFree(ctx->owned.back()); ctx->owned.pop_back(); }
   return rc;
 }

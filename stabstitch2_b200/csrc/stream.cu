@@ -76,7 +76,7 @@ extern "C" int ss2_stream_meshes(ss2_ctx* ctx, const float* d_lr1, const float* 
 }
 
 #define WARP_CHUNK 8
-#define HOST_SLOTS 2
+#define HOST_SLOTS 3
 
 // per-slot streams / events of the host-buffer pipeline
 struct HostSlot {
@@ -90,6 +90,12 @@ struct HostSlot {
   // inputs already on their way (ss2_stitch_stream_host_prefetch)
   const void* pre[4] = {nullptr, nullptr, nullptr, nullptr};
   int pre_n = 0, pre_h = 0, pre_w = 0, pre_u8 = 0;
+  // a submitted, not yet finished chunk (ss2_stitch_stream_host*_submit / _finish)
+  bool submitted = false;
+  int sub_n = 0, sub_h = 0, sub_w = 0, sub_u8 = 0;
+  float *sub_hr1 = nullptr, *sub_hr2 = nullptr, *sub_s1 = nullptr, *sub_s2 = nullptr;
+  cudaEvent_t ev_canvas = nullptr;
+  float* h_mm = nullptr;   // pinned: canvas min/max of the submitted chunk
 };
 // the slots belong to the context (distinct contexts are independent, also on one device)
 static HostSlot* ctx_slots(ss2_ctx* ctx) {
@@ -105,7 +111,8 @@ void ss2_host_slots_free(ss2_ctx* ctx) {
     if (!h.s_copy) continue;
     cudaStreamDestroy(h.s_copy);
     cudaStreamDestroy(h.s_d2h);
-    cudaEvent_t evs[] = {h.ev_hr, h.ev_lr, h.ev_warp, h.ev_done, h.ev_chunk[0], h.ev_chunk[1], h.ev_d2h[0], h.ev_d2h[1]};
+    if (h.h_mm) cudaFreeHost(h.h_mm);
+    cudaEvent_t evs[] = {h.ev_hr, h.ev_lr, h.ev_warp, h.ev_done, h.ev_canvas, h.ev_chunk[0], h.ev_chunk[1], h.ev_d2h[0], h.ev_d2h[1]};
     for (cudaEvent_t e : evs)
       if (e) cudaEventDestroy(e);
   }
@@ -121,6 +128,8 @@ static int slot_init(ss2_ctx* ctx, HostSlot& h) {
   SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_lr, cudaEventDisableTiming));
   SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_warp, cudaEventDisableTiming));
   SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_done, cudaEventDisableTiming));
+  SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_canvas, cudaEventDisableTiming));
+  SS2_CUDA(ctx, cudaMallocHost((void**)&h.h_mm, 4 * sizeof(float)));
   for (int i = 0; i < 2; ++i) SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_chunk[i], cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) SS2_CUDA(ctx, cudaEventCreateWithFlags(&h.ev_d2h[i], cudaEventDisableTiming));
   return SS2_OK;
@@ -205,21 +214,27 @@ extern "C" int ss2_stitch_stream_host_wait(ss2_ctx* ctx, int slot) {
   return SS2_OK;
 }
 
-// one chunk through the host pipeline; u8 != 0: uint8 frames in ([n,H,W,3] BGR) and out ([n,Ho,Wo,3])
-static int async_impl(ss2_ctx* ctx, int slot, int u8, const void* h_lr1, const void* h_lr2, const void* h_a, const void* h_b,
-                      int n, int H, int W, int mode, int tps, void* h_out, int64_t out_capacity, int* out_h, int* out_w,
-                      float* h_smooth_mesh1, float* h_smooth_mesh2) {
+// One chunk through the host pipeline in two halves; u8 != 0: uint8 frames in ([n,H,W,3] BGR) and out ([n,Ho,Wo,3]).
+//   submit: H2D of the inputs (unless prefetched), device front end, the three networks, canvas min/max and its
+//           16-byte D2H - everything is only ENQUEUED, the call does not block;
+//   finish: waits for the canvas (the output shape is data dependent), enqueues resample + blend (+ astype(uint8))
+//           and the D2H of the frames.
+// A caller that submits chunk k+1 BEFORE it finishes chunk k keeps the GPU busy while the host waits for chunk k's
+// canvas (stream order on the compute stream: nets(k), nets(k+1), warp(k), nets(k+2), ..).
+static int submit_impl(ss2_ctx* ctx, int slot, int u8, const void* h_lr1, const void* h_lr2, const void* h_a, const void* h_b,
+                       int n, int H, int W) {
   if (!ctx) return SS2_ERR_INVALID;
   if (slot < 0 || slot >= HOST_SLOTS) return ss2_fail(ctx, SS2_ERR_INVALID, "bad slot");
   if (n < SS2_WINDOW) return ss2_fail(ctx, SS2_ERR_INVALID, "a stream needs at least %d frames (got %d)", SS2_WINDOW, n);
-  if ((!u8 && (!h_lr1 || !h_lr2)) || !h_a || !h_b || !h_out || !out_h || !out_w || H <= 1 || W <= 1)
+  if ((!u8 && (!h_lr1 || !h_lr2)) || !h_a || !h_b || H <= 1 || W <= 1)
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stitch_stream_host: bad arguments");
   SS2_CUDA(ctx, cudaSetDevice(ctx->device));
   HostSlot& hs = ctx_slots(ctx)[slot];
   SS2_TRY(slot_init(ctx, hs));
+  if (hs.submitted) return ss2_fail(ctx, SS2_ERR_INVALID, "slot %d: a submitted chunk has not been finished", slot);
   SS2_TRY(ss2_stitch_stream_host_wait(ctx, slot));  // the slot's buffers must be free
   if (!ctx->s_compute) SS2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
-  cudaStream_t sc = ctx->s_compute, sx = hs.s_d2h;
+  cudaStream_t sc = ctx->s_compute;
   const size_t mb = (size_t)n * SS2_NPT * 2 * sizeof(float);
   float *lr1, *lr2, *hr1, *hr2, *small;
   unsigned char *ua, *ub;
@@ -240,11 +255,31 @@ static int async_impl(ss2_ctx* ctx, int slot, int u8, const void* h_lr1, const v
   }
   SS2_TRY(ss2_stream_meshes(ctx, lr1, lr2, n, S1, S2, nullptr, nullptr, nullptr, nullptr, sc));
   SS2_TRY(canvas_minmax_launch(ctx, S1, S2, n, H, W, mm, sc));
-  float h_mm[4];
-  SS2_CUDA(ctx, cudaMemcpyAsync(h_mm, mm, sizeof(h_mm), cudaMemcpyDeviceToHost, sc));
-  if (h_smooth_mesh1) SS2_CUDA(ctx, cudaMemcpyAsync(h_smooth_mesh1, S1, mb, cudaMemcpyDeviceToHost, sc));
-  if (h_smooth_mesh2) SS2_CUDA(ctx, cudaMemcpyAsync(h_smooth_mesh2, S2, mb, cudaMemcpyDeviceToHost, sc));
-  SS2_CUDA(ctx, cudaStreamSynchronize(sc));  // the canvas size is data dependent (16-byte read)
+  SS2_CUDA(ctx, cudaMemcpyAsync(hs.h_mm, mm, 4 * sizeof(float), cudaMemcpyDeviceToHost, sc));
+  SS2_CUDA(ctx, cudaEventRecord(hs.ev_canvas, sc));
+  hs.submitted = true;
+  hs.sub_n = n; hs.sub_h = H; hs.sub_w = W; hs.sub_u8 = u8;
+  hs.sub_hr1 = hr1; hs.sub_hr2 = hr2; hs.sub_s1 = S1; hs.sub_s2 = S2;
+  return SS2_OK;
+}
+
+static int finish_impl(ss2_ctx* ctx, int slot, int mode, int tps, void* h_out, int64_t out_capacity, int* out_h, int* out_w,
+                       float* h_smooth_mesh1, float* h_smooth_mesh2) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (slot < 0 || slot >= HOST_SLOTS) return ss2_fail(ctx, SS2_ERR_INVALID, "bad slot");
+  if (!h_out || !out_h || !out_w) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stitch_stream_host: bad arguments");
+  HostSlot& hs = ctx_slots(ctx)[slot];
+  if (!hs.submitted) return ss2_fail(ctx, SS2_ERR_INVALID, "slot %d: nothing submitted", slot);
+  SS2_CUDA(ctx, cudaSetDevice(ctx->device));
+  hs.submitted = false;
+  const int n = hs.sub_n, H = hs.sub_h, W = hs.sub_w, u8 = hs.sub_u8;
+  float *hr1 = hs.sub_hr1, *hr2 = hs.sub_hr2, *S1 = hs.sub_s1, *S2 = hs.sub_s2;
+  cudaStream_t sc = ctx->s_compute, sx = hs.s_d2h;
+  const size_t mb = (size_t)n * SS2_NPT * 2 * sizeof(float);
+  char nm[32];
+  auto name = [&](const char* base) { snprintf(nm, sizeof(nm), "%s.%d", base, slot); return nm; };
+  SS2_CUDA(ctx, cudaEventSynchronize(hs.ev_canvas));  // the canvas size is data dependent (16-byte read)
+  const float* h_mm = hs.h_mm;
   int Ho, Wo;
   ss2_canvas_size(h_mm, &Ho, &Wo);
   *out_h = Ho; *out_w = Wo;
@@ -252,6 +287,11 @@ static int async_impl(ss2_ctx* ctx, int slot, int u8, const void* h_lr1, const v
   const size_t fpx = (size_t)3 * Ho * Wo;
   if ((int64_t)(fpx * n) > out_capacity)
     return ss2_fail(ctx, SS2_ERR_INVALID, "output needs %zu elements, capacity %lld", fpx * n, (long long)out_capacity);
+  if (h_smooth_mesh1 || h_smooth_mesh2) {   // the meshes are complete once the canvas event has fired
+    SS2_CUDA(ctx, cudaStreamWaitEvent(sx, hs.ev_canvas, 0));
+    if (h_smooth_mesh1) SS2_CUDA(ctx, cudaMemcpyAsync(h_smooth_mesh1, S1, mb, cudaMemcpyDeviceToHost, sx));
+    if (h_smooth_mesh2) SS2_CUDA(ctx, cudaMemcpyAsync(h_smooth_mesh2, S2, mb, cudaMemcpyDeviceToHost, sx));
+  }
   // The whole chunk is resampled into a device buffer of its own (HBM is plentiful), so the compute
   // stream is free for the next chunk's networks while the copy stream drains the frames to the host.
   float *obuf, *obuf8f = nullptr;
@@ -279,6 +319,28 @@ static int async_impl(ss2_ctx* ctx, int slot, int u8, const void* h_lr1, const v
   SS2_CUDA(ctx, cudaEventRecord(hs.ev_done, sx));
   hs.busy = true;
   return SS2_OK;
+}
+
+static int async_impl(ss2_ctx* ctx, int slot, int u8, const void* h_lr1, const void* h_lr2, const void* h_a, const void* h_b,
+                      int n, int H, int W, int mode, int tps, void* h_out, int64_t out_capacity, int* out_h, int* out_w,
+                      float* h_smooth_mesh1, float* h_smooth_mesh2) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (!h_out || !out_h || !out_w) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stitch_stream_host: bad arguments");
+  SS2_TRY(submit_impl(ctx, slot, u8, h_lr1, h_lr2, h_a, h_b, n, H, W));
+  return finish_impl(ctx, slot, mode, tps, h_out, out_capacity, out_h, out_w, h_smooth_mesh1, h_smooth_mesh2);
+}
+
+extern "C" int ss2_stitch_stream_host_submit(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2,
+                                             const float* h_hr1, const float* h_hr2, int n, int H, int W) {
+  return submit_impl(ctx, slot, 0, h_lr1, h_lr2, h_hr1, h_hr2, n, H, W);
+}
+extern "C" int ss2_stitch_stream_host_u8_submit(ss2_ctx* ctx, int slot, const uint8_t* h_bgr1, const uint8_t* h_bgr2, int n,
+                                                int H, int W) {
+  return submit_impl(ctx, slot, 1, nullptr, nullptr, h_bgr1, h_bgr2, n, H, W);
+}
+extern "C" int ss2_stitch_stream_host_finish(ss2_ctx* ctx, int slot, int mode, int tps, void* h_out, int64_t out_capacity,
+                                             int* out_h, int* out_w, float* h_smooth_mesh1, float* h_smooth_mesh2) {
+  return finish_impl(ctx, slot, mode, tps, h_out, out_capacity, out_h, out_w, h_smooth_mesh1, h_smooth_mesh2);
 }
 
 extern "C" int ss2_stitch_stream_host_async(ss2_ctx* ctx, int slot, const float* h_lr1, const float* h_lr2,

@@ -1090,7 +1090,7 @@ int tps_warp_launch(ss2_ctx* ctx, const float* d_U, const float* d_source, const
     SS2_LAUNCH_CHECK(ctx);                                                                         \
     return SS2_OK;                                                                                 \
   }
-  WARP_CASE(1) WARP_CASE(2) WARP_CASE(3) WARP_CASE(4)
+  WARP_CASE(1) WARP_CASE(2) WARP_CASE(3) WARP_CASE(4) WARP_CASE(6)   // 6: image + three mask planes of the metric path
 #undef WARP_CASE
   // other channel counts: one plane at a time
   for (int c = 0; c < C; ++c) {

@@ -353,6 +353,38 @@ def stitch_stream_host_u8_async(spatial_net, temporal_net, smooth_net, slot, bgr
     return ho.value, wo.value
 
 
+def stitch_stream_host_submit(spatial_net, temporal_net, smooth_net, slot, *ins):
+    """First half of the pipelined host call: enqueue a chunk's uploads, front end and networks; returns at once.
+    ins = (bgr1, bgr2) uint8 [n,H,W,3] or (lr1, lr2, hr1, hr2) fp32 host tensors."""
+    ctx = _lib.context()
+    _sync_nets(ctx, spatial_net, temporal_net, smooth_net)
+    if len(ins) == 2:
+        _check_u8_host(*ins)
+        n, H, W, _ = ins[0].shape
+        ctx.check(ctx.lib.ss2_stitch_stream_host_u8_submit(ctx.handle, int(slot), _lib.ptr(ins[0]), _lib.ptr(ins[1]), n, H, W))
+    else:
+        lr1, lr2, hr1, hr2 = ins
+        for t in ins:
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("stitch_stream_host takes contiguous fp32 HOST tensors")
+        n, _, H, W = hr1.shape
+        ctx.check(ctx.lib.ss2_stitch_stream_host_submit(ctx.handle, int(slot), _lib.ptr(lr1), _lib.ptr(lr2), _lib.ptr(hr1),
+                                                        _lib.ptr(hr2), n, H, W))
+
+
+def stitch_stream_host_finish(slot, out, mode="NORMAL", tps=None):
+    """Second half: wait for the submitted chunk's canvas, enqueue resample + blend and the frame downloads into `out`
+    (uint8 after a uint8 submit, fp32 otherwise); returns (Ho, Wo).  stitch_stream_host_wait(slot) completes it."""
+    from .utils import torch_tps_transform as tt
+    ctx = _lib.context()
+    if out.is_cuda or not out.is_contiguous():
+        raise ValueError("`out` must be a contiguous HOST tensor")
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    ctx.check(ctx.lib.ss2_stitch_stream_host_finish(ctx.handle, int(slot), _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps,
+                                                    _lib.ptr(out), out.numel(), ctypes.byref(ho), ctypes.byref(wo), None, None))
+    return ho.value, wo.value
+
+
 def stitch_stream_host_u8_prefetch(slot, bgr1, bgr2):
     ctx = _lib.context()
     _check_u8_host(bgr1, bgr2)

@@ -697,6 +697,28 @@ def test_stream_host_u8_matches_fp32_interface(nets):
     for slot in (0, 1):
         pipeline.stitch_stream_host_wait(slot)
         assert np.array_equal(outs[slot].numpy().reshape(n, ho, wo, 3), ref_u8)
+    # two-phase calls: chunk i+1 submitted before chunk i is finished (what bench.py's e2e leg does)
+    for o in outs:
+        o.zero_()
+    pipeline.stitch_stream_host_submit(s, t, m, 0, p1, p2)
+    for i in range(4):
+        if i + 1 < 4:
+            pipeline.stitch_stream_host_submit(s, t, m, (i + 1) & 1, p1, p2)
+        assert pipeline.stitch_stream_host_finish(i & 1, outs[i & 1]) == (ho, wo)
+        if i >= 1:   # the other slot's chunk (i-1) must be complete before its buffer is checked / reused
+            pipeline.stitch_stream_host_wait((i - 1) & 1)
+            assert np.array_equal(outs[(i - 1) & 1].numpy().reshape(n, ho, wo, 3), ref_u8)
+    pipeline.stitch_stream_host_wait(1)
+    assert np.array_equal(outs[1].numpy().reshape(n, ho, wo, 3), ref_u8)
+    # misuse: finishing a slot with nothing submitted, submitting twice
+    from stabstitch2_b200 import _lib
+    with pytest.raises(_lib.SS2Error):
+        pipeline.stitch_stream_host_finish(0, outs[0])
+    pipeline.stitch_stream_host_submit(s, t, m, 0, p1, p2)
+    with pytest.raises(_lib.SS2Error):
+        pipeline.stitch_stream_host_submit(s, t, m, 0, p1, p2)
+    pipeline.stitch_stream_host_finish(0, outs[0])
+    pipeline.stitch_stream_host_wait(0)
 
 
 # ---------------------------------------------------------------- convolution kernels (SIMT fp32 and tcgen05)
@@ -740,6 +762,30 @@ def test_conv_kernels_vs_torch(case, use_tc):
     # SIMT path: fp32 FMA chain.  Tensor-core path: split-TF32 operands (2^-21 relative) but the
     # TMEM accumulator truncates on every one of the K/8 accumulation steps, ~K/8 * 2^-24 * |sum|
     assert err < (3e-4 if use_tc else 2e-5), err
+
+
+@pytest.mark.parametrize("B,H", [(1, 8), (2, 44), (3, 360), (33, 360)])
+def test_stem_pool_direct_vs_torch(B, H):
+    """the fused direct stem kernel (conv 7x7 s2 + bias + ReLU + max-pool 3x3 s2 in one tcgen05 kernel) against a plain
+    PyTorch reference of the same ops (CPU, fp64 accumulate) and against the two-kernel paths; B = 33 is the
+    TemporalNet halo chunk (band scheduling with a ragged unit count), H = 8 a single band"""
+    from stabstitch2_b200 import _lib
+    g = torch.Generator().manual_seed(77 + B + H)
+    x = torch.rand(B, 3, H, 480, generator=g) * 2 - 1
+    w = torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5
+    b = torch.randn(64, generator=g) * 0.2
+    out = _lib.stem_pool(x.cuda(), w, b, variant=2).cpu()
+    if B <= 3:
+        ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), 2, 3)
+        ref = torch.nn.functional.max_pool2d(torch.relu(ref), 3, 2, 1).permute(0, 2, 3, 1).float()
+        assert out.shape == ref.shape
+        err = (out - ref).abs().max().item()
+        assert err < 1e-4, err           # split TF32: 2^-21 relative per product, K = 147
+        simt = _lib.stem_pool(x.cuda(), w, b, variant=0).cpu()
+        assert (simt - ref).abs().max().item() < 2e-5
+    two = _lib.stem_pool(x.cuda(), w, b, variant=1).cpu()   # same split-TF32 products, other summation order
+    assert out.shape == two.shape
+    assert (out - two).abs().max().item() < 1e-4
 
 
 @pytest.mark.parametrize("sr", [5, 3])
@@ -810,7 +856,7 @@ def test_three_view_720p_vs_oracle():
     assert tuple(fused.shape) == tuple(ref.shape)
     # The reference's AVERAGE fusion a*(a/(a+b+1e-6)) is ill-conditioned wherever BOTH of its inputs are rounding
     # residues of uncovered views: in the part of the canvas that only view 3 covers, stage one fuses two residues
-    # (|r| <~ 3e-2) and returns up to +-20 grey levels at ~1% of the pixels (tests/probe_tv.py), which then leak
+    # (|r| <~ 3e-2) and returns up to +-20 grey levels at ~1% of the pixels (measured once with a throwaway probe), which then leak
     # into the output; where nothing covers, values reach 5e5.  No re-implementation reproduces those bits, so:
     #   region A (view 1 or view 2 covers): compare with the reference restatement, residue-sized bounds;
     #   region B (only view 3 covers): our frame must equal view 3 warped alone (c*c/(c+1e-6));
@@ -912,3 +958,47 @@ def test_nview_4_720p_vs_oracle():
     print("4-view 720p: canvas %dx%d, settled fraction %.2f, max |diff| %.2e, median %.2e" % (Ho, Wo, settled.mean(), d.max(), np.median(d)))
     assert settled.mean() > 0.9
     assert (d > 5e-3).mean() < 1e-4 and np.median(d) < 1e-3
+
+
+# ---------------------------------------------------------------- metric path
+def test_metric_scores_vs_reference_golden():
+    """stability / distortion scores (test_metric_ssd.py:455-479) against the reference's own grid losses and the oracle"""
+    from oracle import metric_oracle as MO
+    from stabstitch2_b200 import metrics
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metric.npz")))
+    mesh, path = T(g["mesh"]), T(g["path"])
+    d = float(metrics.distortion_score(mesh[0]))
+    assert abs(d - float(np.max(g["inter"] + g["intra"]))) < 2e-6 * max(1.0, d)
+    s = float(metrics.stability_score(path[0]))
+    assert abs(s - float(MO.stability_score(path))) < 1e-5 * max(1.0, abs(s))
+    # per-window paths -> whole-stream paths (:417-436)
+    gen = torch.Generator().manual_seed(2)
+    wo = torch.cumsum(torch.randn(5, 7, 7, 9, 2, generator=gen), 1)
+    ws = wo + 0.3 * torch.randn(5, 7, 7, 9, 2, generator=gen)
+    ori, smo = metrics.stream_paths(wo, ws)
+    ro, rs = MO.accumulate_paths(wo, ws)
+    assert maxdiff(ori[None], ro) == 0.0 and maxdiff(smo[None], rs) == 0.0
+
+
+def test_metric_warp_psnr_ssim(golden_stream, stream_inputs):
+    """the metric script's per-view warp with mask planes (C = 6, :151-181) against the reference's own output, and
+    PSNR / SSIM in the overlap against the oracle's restatement of skimage 0.15 (fp64)"""
+    from oracle import metric_oracle as MO
+    from stabstitch2_b200 import metrics
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metric.npz")))
+    _, lr = stream_inputs
+    S1, S2 = T(golden_stream["smooth_mesh1"])[:, :2], T(golden_stream["smooth_mesh2"])[:, :2]
+    l1, l2 = metrics.get_stable_sqe(lr[0][:2], lr[1][:2], S1, S2)
+    assert l1[0].shape == (360, 480, 6)
+    d = np.abs(l1[0] - g["warp1_frame0"])
+    bound = grad_max((lr[0][0] + 1) * 127.5) * COORD_TOL_PX + 1e-3
+    assert (d > bound).mean() < 2e-3 and np.median(d) < 1e-3, ((d > bound).mean(), d.max())
+    d2 = np.abs(l2[1][::4] - g["warp2_frame1_rows4"])
+    assert (d2 > bound).mean() < 2e-3
+    w1 = torch.from_numpy(np.stack(l1, 0)).permute(0, 3, 1, 2).contiguous()
+    w2 = torch.from_numpy(np.stack(l2, 0)).permute(0, 3, 1, 2).contiguous()
+    ps, ss = metrics.psnr_ssim(w1, w2)
+    for k in range(2):
+        rp, rs = MO.psnr_overlap(l1[k], l2[k]), MO.ssim_overlap(l1[k], l2[k])
+        print("frame %d: psnr %.4f (oracle %.4f), ssim %.6f (oracle %.6f)" % (k, float(ps[k]), rp, float(ss[k]), rs))
+        assert abs(float(ps[k]) - rp) < 1e-3 and abs(float(ss[k]) - rs) < 1e-5
