@@ -29,8 +29,8 @@ struct DcParams {
   float* out_hi;
   float* out_lo;
   int B, H, W, Cout;
-  int P, TH;           // padded pitch W + 2, output rows per tile
-  int tiles_h;         // ceil(H / TH)
+  int P, TH, TW;       // padded pitch TW + 2, output rows / columns per tile
+  int tiles_h, tiles_w;  // ceil(H / TH), ceil(W / TW)
   int n_mtiles, n_ntiles;
   int nchunk, CinP;
   int a_rows;          // staged rows per plane (allocation; >= 128 + 2 P + 2, multiple of 8)
@@ -56,6 +56,11 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DcParams P) {
   constexpr int DC_BN = BN;
   constexpr int DC_B_BYTES = BN * DC_BK * 4;  // per plane
+  // Split TF32 as TWO MMAs per k-step instead of three: the weight planes of a stage are adjacent in shared memory,
+  // so A_hi x [B_hi | B_lo] is ONE MMA with N = 2 BN into accumulator columns [D1 | D2], and A_lo x B_hi a second one
+  // with N = BN into D1; the epilogue adds D1 + D2.  A tcgen05 TF32 MMA of 128 x N x 8 takes ~43 + N / 2 cycles on
+  // B200 (operand reads), so 2 BN + BN columns in two instructions cost 182 cycles against 225 for three (BN = 64).
+  constexpr int DC_TMEM_COLS = 2 * MT * 2 * BN > 512 ? 512 : 2 * MT * 2 * BN;
   extern __shared__ __align__(1024) uint8_t dc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dc_smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t a_full[4], a_empty[4], b_full[8], b_empty[8], acc_full[2], acc_empty[2];
@@ -76,7 +81,7 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(2 * MT * BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(DC_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -91,14 +96,15 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       int ia = 0, ib = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const int mt = t / P.n_ntiles, nt = t - mt * P.n_ntiles;
-        const int n = mt / P.tiles_h, h0 = (mt - n * P.tiles_h) * P.TH;
+        const int tw = mt % P.tiles_w, nh = mt / P.tiles_w;
+        const int n = nh / P.tiles_h, h0 = (nh - n * P.tiles_h) * P.TH, w0 = tw * P.TW;
         for (int ck = 0; ck < P.nchunk; ++ck) {
           const int sa = ia % P.NA;
           if (ia >= P.NA) mbar_wait(&a_empty[sa], ((ia / P.NA) - 1) & 1);
           uint8_t* ad = a_ring + (size_t)sa * a_stage;
           mbar_expect_tx(&a_full[sa], a_bytes);
-          tma_load_5d(ad, &tmA_hi, &a_full[sa], ck * DC_BK, -1, h0 - 1, 0, n);
-          if (nplanes == 2) tma_load_5d(ad + a_plane, &tmA_lo, &a_full[sa], ck * DC_BK, -1, h0 - 1, 0, n);
+          tma_load_5d(ad, &tmA_hi, &a_full[sa], ck * DC_BK, w0 - 1, h0 - 1, 0, n);
+          if (nplanes == 2) tma_load_5d(ad + a_plane, &tmA_lo, &a_full[sa], ck * DC_BK, w0 - 1, h0 - 1, 0, n);
           ++ia;
           for (int tap = 0; tap < 9; ++tap) {
             const int sb = ib % P.NB;
@@ -122,13 +128,15 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (dc_elect_one()) {
       // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * DC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t a_plane16 = a_plane >> 4;
+      const uint32_t accw = (uint32_t)(nplanes == 2 ? 2 * DC_BN : DC_BN);   // accumulator columns per 128-row block
       int ia = 0, ib = 0, it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int as = it & 1;
         if (it >= 2) mbar_wait(&acc_empty[as], ((it >> 1) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * DC_BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * MT * accw;
         for (int ck = 0; ck < P.nchunk; ++ck) {
           const int sa = ia % P.NA;
           if (!(P.dbg & 1)) mbar_wait(&a_full[sa], (ia / P.NA) & 1);
@@ -144,21 +152,19 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             constexpr uint32_t BLK = 128 * 128 / 16;                   // descriptor units between the tile's row blocks
             if (P.dbg & 2) {
             } else if (nplanes == 2) {
-              const uint32_t dal = da + a_plane16, dbl = db + (DC_B_BYTES >> 4);
+              const uint32_t dal = da + a_plane16;
 #pragma unroll
               for (int k = 0; k < DC_BK / 8; ++k) {
 #pragma unroll
-                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * DC_BN, da + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc, k == 0 ? first : 1u);
+                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * accw, da + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc2, k == 0 ? first : 1u);
 #pragma unroll
-                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * DC_BN, dal + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);
-#pragma unroll
-                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * DC_BN, da + b * BLK + 2 * k, dbl + 2 * k, DC_DESC_HI, idesc, 1u);
+                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * accw, dal + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);
               }
             } else {
 #pragma unroll
               for (int k = 0; k < DC_BK / 8; ++k)
 #pragma unroll
-                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * DC_BN, da + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc, k == 0 ? first : 1u);
+                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * accw, da + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc, k == 0 ? first : 1u);
             }
             umma_commit(&b_empty[sb]);
             ++ib;
@@ -177,7 +183,8 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int as = it & 1;
       const int mt = t / P.n_ntiles, nt = t - mt * P.n_ntiles;
-      const int n = mt / P.tiles_h, h0 = (mt - n * P.tiles_h) * P.TH;
+      const int tw = mt % P.tiles_w, nh = mt / P.tiles_w;
+      const int n = nh / P.tiles_h, h0 = (nh - n * P.tiles_h) * P.TH, w0 = tw * P.TW;
       mbar_wait(&acc_full[as], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int cout0 = nt * DC_BN;
@@ -185,13 +192,21 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int blk = 0; blk < MT; ++blk) {
         const int r = blk * 128 + q * 32 + lane;
         const int hl = r / P.P, wl = r - hl * P.P;
-        const int oh = h0 + hl;
-        const bool valid = hl < P.TH && wl < P.W && oh < P.H;
-        const size_t m = ((size_t)n * P.H + oh) * P.W + wl;
+        const int oh = h0 + hl, ow = w0 + wl;
+        const bool valid = hl < P.TH && wl < P.TW && ow < P.W && oh < P.H;
+        const size_t m = ((size_t)n * P.H + oh) * P.W + ow;
 #pragma unroll
         for (int half = 0; half < DC_BN / 32; ++half) {
           uint32_t acc[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * MT + blk) * DC_BN + half * 32), acc);  // warp-collective
+          const uint32_t accw = (uint32_t)(nplanes == 2 ? 2 * DC_BN : DC_BN);
+          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT + blk) * accw + (uint32_t)(half * 32);
+          tmem_ld32(tcol, acc);  // warp-collective
+          if (nplanes == 2) {    // D1 + D2 (see the MMA issuer)
+            uint32_t acc2[32];
+            tmem_ld32(tcol + DC_BN, acc2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
+          }
           if (blk == MT - 1 && half == DC_BN / 32 - 1) {
             // this warp's accumulator quarter is in registers: hand the TMEM stage back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -235,7 +250,7 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * MT * BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(DC_TMEM_COLS));
   }
 }
 
@@ -252,37 +267,74 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   P.bias = L.bias; P.residual = d_residual;
   P.out_v = out.v; P.out_hi = out.hi; P.out_lo = out.lo;
   P.B = B; P.H = H; P.W = W; P.Cout = L.Cout;
-  P.P = W + 2;
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-  // two 128-row blocks per tile when that still leaves every SM several tiles (measured on B200, 32 images: 64->64 at
-  // 90x120 206 us against 245 us with one block; 256->256 at 23x30 has only 192 two-block tiles and loses to the
-  // wave quantisation, 187 us against 152 us)
-  int MT = 2;
-  P.TH = 256 / P.P; if (P.TH > H) P.TH = H;
-  if (P.TH * P.P <= 128 || (long)B * cdiv(H, P.TH) * (L.CoutP / ((L.CoutP % 128) == 0 ? 128 : 64)) < 3L * nsm) {
-    MT = 1;
-    P.TH = 128 / P.P; if (P.TH > H) P.TH = H;
-  }
-  P.tiles_h = cdiv(H, P.TH);
-  P.n_mtiles = B * P.tiles_h;
   // N tile: 128 output channels per MMA where the layer has them (half the tcgen05.mma instructions per FLOP and the
   // staged input tile is read once for 128 channels), else 64
-  const int BN = (L.CoutP % 128) == 0 ? 128 : 64;
-  P.n_ntiles = L.CoutP / BN;
+  int BN = (L.CoutP % 128) == 0 ? 128 : 64;
   P.nchunk = L.CinP / DC_BK; P.CinP = L.CinP;
-  P.a_rows = (128 * MT + 2 * P.P + 2 + 7) / 8 * 8;
   P.relu = relu;
   { const char* e = getenv("SS2_DC_DBG"); P.dbg = e ? atoi(e) : 0; }
   P.npass = (ctx->tc_passes == 1 || !in.lo || !L.wk_lo) ? 1 : 3;
   const int nplanes = P.npass == 3 ? 2 : 1;
-  const size_t a_stage = (size_t)P.a_rows * 128 * nplanes, b_stage = (size_t)BN * DC_BK * 4 * nplanes;
   const size_t budget = 227 * 1024 - 2048;
-  P.NA = P.nchunk >= 2 ? 2 : 1;
-  if ((size_t)P.NA * a_stage + 2 * b_stage + 1024 > budget) P.NA = 1;
-  if ((size_t)P.NA * a_stage + 2 * b_stage + 1024 > budget) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_dc: tile does not fit shared memory");
-  P.NB = (int)((budget - 1024 - (size_t)P.NA * a_stage) / b_stage);
-  if (P.NB > 8) P.NB = 8;
+  size_t b_stage = 0;
+  size_t a_stage = 0;
+  int MT = 2;
+  // tile = TH rows x TW columns of the image (pitch TW + 2) in MT 128-row GEMM blocks
+  auto plan = [&](int tiles_w, int mt_blocks) -> bool {
+    P.tiles_w = tiles_w;
+    P.TW = cdiv(W, tiles_w);
+    P.P = P.TW + 2;
+    if (P.P > 128) return false;
+    P.TH = 128 * mt_blocks / P.P; if (P.TH > H) P.TH = H;
+    P.a_rows = (128 * mt_blocks + 2 * P.P + 2 + 7) / 8 * 8;
+    a_stage = (size_t)P.a_rows * 128 * nplanes;
+    P.NA = P.nchunk >= 2 ? 2 : 1;
+    if ((size_t)P.NA * a_stage + 2 * b_stage + 1024 > budget) P.NA = 1;
+    if ((size_t)P.NA * a_stage + 2 * b_stage + 1024 > budget) return false;
+    P.NB = (int)((budget - 1024 - (size_t)P.NA * a_stage) / b_stage);
+    if (P.NB > 8) P.NB = 8;
+    P.tiles_h = cdiv(H, P.TH);
+    P.n_mtiles = B * P.tiles_h * P.tiles_w;
+    return true;
+  };
+  // small maps (the regressor stacks: a few dozen tiles for 148 SMs): 64-channel N tiles double the CTAs, and a
+  // 128x64x8 MMA takes ~0.7x the time of a 128x128x8 one
+  int small_thr = nsm / 2;
+  { const char* e = getenv("SS2_DC_SMALL"); if (e) small_thr = atoi(e); }
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    P.n_ntiles = L.CoutP / BN;
+    b_stage = (size_t)BN * DC_BK * 4 * nplanes;
+    MT = 2;
+    // two 128-row blocks per tile when that still leaves every SM several tiles (measured on B200, 32 images: 64->64 at
+    // 90x120 206 us against 245 us with one block; 256->256 at 23x30 has only 192 two-block tiles and loses to the
+    // wave quantisation, 187 us against 152 us)
+    // (split TF32 with N = 128: one block's [D1 | D2] accumulator pair is 256 TMEM columns, two stages fill the 512)
+    bool ok = !(nplanes == 2 && BN == 128) && plan(1, 2);
+    if (!ok || P.TH * P.P <= 128 || (long)P.n_mtiles * P.n_ntiles < 3L * nsm) { MT = 1; ok = plan(1, 1); }
+    if (!ok) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_dc: tile does not fit shared memory");
+    // A full-width two-block tile of a wide map leaves room for ONE input stage only (90x120x64: 129 KB per stage), so
+    // the input load of chunk k + 1 cannot overlap the MMAs of chunk k.  Splitting the row into column tiles shrinks the
+    // stage (and the halo rows re-read per tile: (TH + 2) / TH drops from 2 to 1.33 with three column tiles) until two
+    // input stages and three weight stages fit.
+    {
+      const char* e = getenv("SS2_DC_TW");
+      const int force = e ? atoi(e) : 0;
+      if (force > 0 && W >= 100) {
+        DcParams keep = P; const size_t keep_a = a_stage;
+        if (!(plan(force, MT) && P.TH >= 1)) { P = keep; a_stage = keep_a; }
+      } else if (MT == 2 && P.NA == 1 && P.nchunk >= 2) {
+        DcParams keep = P; const size_t keep_a = a_stage;
+        bool found = false;
+        for (int tw = 2; tw <= 4 && !found; ++tw)
+          found = plan(tw, 2) && P.NA == 2 && P.NB >= 3 && P.TH >= 2;
+        if (!found) { P = keep; a_stage = keep_a; }
+      }
+    }
+    if (BN == 128 && (long)P.n_mtiles * P.n_ntiles <= small_thr) { BN = 64; continue; }
+    break;
+  }
   const size_t smem = (size_t)P.NA * a_stage + (size_t)P.NB * b_stage + 1024;
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   SS2_TRY(make_act_map(ctx, &mA_hi, in.hi, L.CinP, W, H, 1, B, P.P, P.TH + 2, 1, 1, 1, 1, 1));

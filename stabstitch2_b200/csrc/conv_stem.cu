@@ -16,7 +16,8 @@
 //   * a tile is one conv row of one image half (M = 128 pixels, N = 64 channels); a persistent CTA walks down a band of
 //     conv rows, so each input row pair is staged once per band (ring of row pairs, one 16.5 KB TMA box each);
 //   * the whole filter (7 rows x [64][32], hi/lo: 112 KB) stays resident in shared memory;
-//   * four TMEM accumulator stages: MMAs of later rows overlap the epilogue;
+//   * split TF32 in two MMAs per k-step (A_hi x [B_hi | B_lo] with N = 128 into [D1 | D2], A_lo x B_hi with N = 64 into
+//     D1; the epilogue adds D1 + D2) and four TMEM accumulator stages: MMAs of later rows overlap the epilogue;
 //   * epilogue: thread = one pixel column with 64 channels; the vertical 3-max lives in registers across the rows of
 //     the band, the horizontal 3-max takes the neighbours with warp shuffles (+ a 64-float hand-over between warps),
 //     then bias + ReLU (monotone, so they commute with the max), the TF32 split, and the pooled pixel is stored with
@@ -112,7 +113,7 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __shared__ __align__(16) float s_bias[64];
   __shared__ __align__(16) float xchg[2][4][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* b_smem = smem;                       // [plane][kh][64][32] SWIZZLE_128B
+  uint8_t* b_smem = smem;                       // [kh][plane][64][32] SWIZZLE_128B: hi | lo of a filter row are ONE N = 128 operand
   uint8_t* a_ring = smem + 2 * ST_BPLANE;       // ST_NA row-pair slots
   const int nplanes = P.npass == 3 ? 2 : 1;
 
@@ -124,7 +125,7 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   if (threadIdx.x < 64) s_bias[threadIdx.x] = P.bias ? P.bias[threadIdx.x] : 0.f;
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(ST_NACC * 64));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(ST_NACC * 128));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -137,8 +138,8 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (dc_elect_one()) {
       mbar_expect_tx(&b_full, (uint32_t)(nplanes * ST_BPLANE));
       for (int kh = 0; kh < 7; ++kh) {
-        tma_load_2d(b_smem + kh * ST_BCHUNK, &tmB_hi, &b_full, kh * 32, 0);
-        if (nplanes == 2) tma_load_2d(b_smem + ST_BPLANE + kh * ST_BCHUNK, &tmB_lo, &b_full, kh * 32, 0);
+        tma_load_2d(b_smem + 2 * kh * ST_BCHUNK, &tmB_hi, &b_full, kh * 32, 0);
+        if (nplanes == 2) tma_load_2d(b_smem + (2 * kh + 1) * ST_BCHUNK, &tmB_lo, &b_full, kh * 32, 0);
       }
       int ia = 0;
       for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
@@ -157,6 +158,9 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (dc_elect_one()) {
       // instruction descriptor: D fp32, A/B tf32, both K-major, N = 64, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // split TF32 in two MMAs per k-step: A_hi x [B_hi | B_lo] (N = 128) into [D1 | D2], A_lo x B_hi (N = 64) into D1
+      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t accw = nplanes == 2 ? 128u : 64u;
       const uint32_t b_lo0 = dc_desc_lo(smem_u32(b_smem));
       const uint32_t a_base = smem_u32(a_ring);
       mbar_wait(&b_full, 0);
@@ -170,23 +174,24 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const int g0 = ia0 + (oy - s.oy0);                 // ring index of row pair oy
           for (; waited <= g0 + 3; ++waited) mbar_wait(&a_full[waited % ST_NA], (waited / ST_NA) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 64);
+          const uint32_t d_tmem = tmem_base + (uint32_t)as * accw;
 #pragma unroll
           for (int kh = 0; kh < 7; ++kh) {
             const int sl = (g0 + (kh >> 1)) % ST_NA;
             // sub-row (row parity kh & 1) of the pair, hi plane; low word carries LBO = 16 B
             const uint32_t a_row = (((a_base + (uint32_t)sl * ST_SLOT + (uint32_t)((kh & 1) * 2) * ST_SEG) & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t b_row = b_lo0 + (uint32_t)(kh * ST_BCHUNK >> 4);
+            const uint32_t b_row = b_lo0 + (uint32_t)(2 * kh * ST_BCHUNK >> 4);
 #pragma unroll
             for (int cp = 0; cp < 2; ++cp)
 #pragma unroll
               for (int jp = 0; jp < 2; ++jp) {
                 const uint32_t da = a_row + (uint32_t)((cp * ST_SEG + jp * 32) >> 4);
                 const uint32_t db = b_row + (uint32_t)((cp * 2 + jp) * 2);
-                st_mma(d_tmem, da, db, idesc, (kh | cp | jp) ? 1u : 0u);
                 if (nplanes == 2) {
+                  st_mma(d_tmem, da, db, idesc2, (kh | cp | jp) ? 1u : 0u);
                   st_mma(d_tmem, da + (uint32_t)(4 * ST_SEG >> 4), db, idesc, 1u);
-                  st_mma(d_tmem, da, db + (uint32_t)(ST_BPLANE >> 4), idesc, 1u);
+                } else {
+                  st_mma(d_tmem, da, db, idesc, (kh | cp | jp) ? 1u : 0u);
                 }
               }
           }
@@ -215,9 +220,18 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mbar_wait(&acc_full[as], (it / ST_NACC) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t c0[32], c1[32];
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 64);
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * (nplanes == 2 ? 128u : 64u);
         tmem_ld32(ta, c0);
         tmem_ld32(ta + 32, c1);
+        if (nplanes == 2) {   // D1 + D2
+          uint32_t e0[32];
+          tmem_ld32(ta + 64, e0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) c0[j] = __float_as_uint(__uint_as_float(c0[j]) + __uint_as_float(e0[j]));
+          tmem_ld32(ta + 96, e0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) c1[j] = __float_as_uint(__uint_as_float(c1[j]) + __uint_as_float(e0[j]));
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
@@ -286,7 +300,7 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(ST_NACC * 64));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(ST_NACC * 128));
   }
 }
 

@@ -13,8 +13,9 @@ Tolerances (fp32 path; all stated in the unit of the quantity):
         where 1e-3 is resolvable, and through gradient-scaled bounds on textured frames;
       * pixels on the reference's hard image edge (taps clamp there) flip between
         a value and 0 when the coordinate moves by 1e-4 px: bounded as a fraction (< 5e-4).
-  - mesh vertices (networks): 5e-3 px at 480x360 against the CPU reference (exact-fp32 SIMT
-    convolutions differ from MKL/oneDNN only by summation order); see DESIGN.md for TF32.
+  - mesh vertices (networks): MESH_TOL_PX at 480x360 against the reference's CPU fp32 outputs (split-TF32 tensor-core
+    convolutions: 2^-21 relative per product + TMEM accumulation order); the measured values are printed by the tests
+    and recorded in DESIGN.md section 2.
 """
 import os
 
@@ -48,6 +49,8 @@ def grad_max(img):
 
 
 COORD_TOL_PX = 1.5e-3  # two fp32 evaluations of the TPS field (see header)
+MESH_TOL_PX = 2e-3     # network outputs (mesh vertices, px at 480x360) against the fp32 CPU reference; measured values are printed
+STREAM_FRAC = 2e-3     # fraction of pixels of a small-stream frame off by > 0.05 grey levels (hard-edge flips)
 
 
 @pytest.fixture(scope="module")
@@ -166,9 +169,11 @@ def test_spatial_forward_golden(nets, stream_inputs, golden_stream):
     a, b = torch.cat(lr[0], 0).cuda(), torch.cat(lr[1], 0).cuda()
     o1, oref, otgt = s(a, b)
     g = golden_stream
-    assert maxdiff(o1, g["offset_1"]) < 2e-3          # 4-pt offsets, px @480 (magnitude ~170)
-    assert maxdiff(oref, g["offset_2_ref"]) < 5e-3    # mesh residuals, px (magnitude ~5)
-    assert maxdiff(otgt, g["offset_2_tgt"]) < 5e-3
+    e = (maxdiff(o1, g["offset_1"]), maxdiff(oref, g["offset_2_ref"]), maxdiff(otgt, g["offset_2_tgt"]))
+    print("SpatialNet.forward vs reference: offset_1 %.2e, offset_2_ref %.2e, offset_2_tgt %.2e px" % e)
+    assert e[0] < MESH_TOL_PX         # 4-pt offsets, px @480 (magnitude ~170)
+    assert e[1] < MESH_TOL_PX         # mesh residuals, px (magnitude ~5)
+    assert e[2] < MESH_TOL_PX
 
 
 def test_build_spatial_batch_equals_single(nets, stream_inputs, golden_stream):
@@ -177,8 +182,9 @@ def test_build_spatial_batch_equals_single(nets, stream_inputs, golden_stream):
     _, lr = stream_inputs
     g = golden_stream
     r = build_SpatialNet(s, torch.cat(lr[0], 0), torch.cat(lr[1], 0))  # CPU tensors in, like the driver
-    assert maxdiff(r["motion1"], g["smotion1"]) < 5e-3
-    assert maxdiff(r["motion2"], g["smotion2"]) < 5e-3
+    e = (maxdiff(r["motion1"], g["smotion1"]), maxdiff(r["motion2"], g["smotion2"]))
+    print("build_SpatialNet vs reference: motion1 %.2e, motion2 %.2e px" % e)
+    assert max(e) < MESH_TOL_PX
     r1 = build_SpatialNet(s, lr[0][3], lr[1][3])
     assert maxdiff(r1["motion1"], r["motion1"][3:4]) < 1e-4
     assert maxdiff(r1["motion2"], r["motion2"][3:4]) < 1e-4
@@ -191,7 +197,9 @@ def test_temporal_golden(nets, stream_inputs, golden_stream):
     for v in range(2):
         ml = build_TemporalNet(t, lr[v])["motion_list"]
         assert len(ml) == len(lr[v]) and ml[0].abs().max().item() == 0.0
-        assert maxdiff(torch.cat(ml, 0), golden_stream["tmotion%d" % (v + 1)]) < 2e-3
+        e = maxdiff(torch.cat(ml, 0), golden_stream["tmotion%d" % (v + 1)])
+        print("build_TemporalNet view %d vs reference: %.2e px" % (v + 1, e))
+        assert e < MESH_TOL_PX
 
 
 def test_smooth_window_golden(nets, golden_stream):
@@ -204,7 +212,9 @@ def test_smooth_window_golden(nets, golden_stream):
     o = build_SmoothNet(m, ts[0], ts[1], sm[0], sm[1])
     for key in ("ori_path1", "smooth_path1", "ori_mesh1", "smooth_mesh1",
                 "ori_path2", "smooth_path2", "ori_mesh2", "smooth_mesh2"):
-        assert maxdiff(o[key], g["win0_" + key]) < 2e-3, key
+        e = maxdiff(o[key], g["win0_" + key])
+        print("build_SmoothNet %s vs reference: %.2e px" % (key, e))
+        assert e < MESH_TOL_PX, key
 
 
 def test_stream_golden(nets, stream_inputs, golden_stream):
@@ -215,16 +225,19 @@ def test_stream_golden(nets, stream_inputs, golden_stream):
     g = golden_stream
     fused, s1, s2 = pipeline.stitch_stream(s, t, m, torch.cat(lr[0], 0).cuda(), torch.cat(lr[1], 0).cuda(),
                                            torch.cat(hr[0], 0).cuda(), torch.cat(hr[1], 0).cuda())
-    assert maxdiff(s1[None], g["smooth_mesh1"]) < 5e-3
-    assert maxdiff(s2[None], g["smooth_mesh2"]) < 5e-3
+    e = (maxdiff(s1[None], g["smooth_mesh1"]), maxdiff(s2[None], g["smooth_mesh2"]))
+    print("whole stream vs reference: smooth_mesh1 %.2e, smooth_mesh2 %.2e px" % e)
+    assert max(e) < MESH_TOL_PX
     assert tuple(fused.shape[2:]) == tuple(g["canvas_hw"])
     f0 = fused[0].permute(1, 2, 0).cpu().numpy()
     d = np.abs(f0 - g["frame0"])
     # mesh differences of ~1e-3 px move pixel values by gradient*1e-3; edges flip single pixels
-    assert (d > 0.05).mean() < 2e-3, ((d > 0.05).mean(), d.max())
-    assert np.median(d) < 1e-3
     fl = fused[-1].permute(1, 2, 0).cpu().numpy()[::8]
-    assert (np.abs(fl - g["frame_last_rows8"]) > 0.05).mean() < 2e-3
+    fr = ((d > 0.05).mean(), (np.abs(fl - g["frame_last_rows8"]) > 0.05).mean())
+    print("whole stream vs reference: frame 0 frac(|d| > 0.05) %.2e median %.2e, last frame frac %.2e" % (fr[0], np.median(d), fr[1]))
+    assert fr[0] < STREAM_FRAC, (fr[0], d.max())
+    assert np.median(d) < 1e-3
+    assert fr[1] < STREAM_FRAC
 
 
 def test_stream_host_call_matches_device_path(nets, stream_inputs):
