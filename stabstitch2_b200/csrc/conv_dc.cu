@@ -37,7 +37,7 @@ struct DcParams {
   int NA, NB;          // ring depths
   int relu;
   int npass;           // 3 = split TF32, 1 = plain TF32
-  int dbg;             // timing experiments (SS2_DC_DBG): 1 = no TMA traffic (MMAs on stale smem), 2 = no MMAs
+  int dbg;             // timing experiments (SS2_DC_DBG): 1 = no TMA traffic (MMAs on stale smem), 2 = no MMAs, 4 = no stores
 };
 
 // K-major SWIZZLE_128B descriptor whose start sits on ANY 128-byte row of the 1024-byte swizzle atom.  Measured on
@@ -45,6 +45,39 @@ struct DcParams {
 // like the TMA unit that wrote the tile, so the descriptor's base-offset field stays 0 (filling it with the row
 // phase of the start address gives wrong results for every tap whose offset is not a multiple of 8 rows).
 __device__ __forceinline__ uint64_t dc_desc_sw128(uint32_t smem_addr) { return umma_desc_sw128(smem_addr); }
+
+// tile index -> image, first row / column, N tile
+__device__ __forceinline__ void dc_tile(const DcParams& P, int t, int* n, int* h0, int* w0, int* nt) {
+  const int mt = t / P.n_ntiles;
+  *nt = t - mt * P.n_ntiles;
+  const int tw = mt % P.tiles_w, nh = mt / P.tiles_w;
+  *n = nh / P.tiles_h;
+  *h0 = (nh - *n * P.tiles_h) * P.TH;
+  *w0 = tw * P.TW;
+}
+// epilogue mapping (see the kernel): lane l stores 16 bytes (l & 3) of rows (l >> 2) + 8 i of its warp's 32 rows
+__device__ __forceinline__ bool dc_row(const DcParams& P, int n, int h0, int w0, int r, size_t* off) {
+  const int hl = r / P.P, wl = r - hl * P.P;
+  const int oh = h0 + hl, ow = w0 + wl;
+  *off = (((size_t)n * P.H + oh) * P.W + ow) * P.Cout;
+  return hl < P.TH && wl < P.TW && ow < P.W && oh < P.H;
+}
+// residual values of one epilogue step (128-row block `blk`, 32-column half `half`) of tile t, in the store mapping
+template <int BN>
+__device__ __forceinline__ void dc_residual_issue(const DcParams& P, int t, int blk, int half, int q, int lane, float4 (&rs)[8]) {
+  int n, h0, w0, nt;
+  dc_tile(P, t, &n, &h0, &w0, &nt);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    size_t off;
+    const bool ok = dc_row(P, n, h0, w0, blk * 128 + q * 32 + (lane >> 2) + 8 * i, &off);
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      const int c = nt * BN + half * 32 + sub * 16 + (lane & 3) * 4;
+      rs[sub * 4 + i] = (ok && c < P.Cout) ? __ldg(reinterpret_cast<const float4*>(P.residual + off + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
 
 // MT = 128-row GEMM blocks per tile (1 or 2).  Measured on B200 the kernel is bound by the bytes the TMA unit can
 // deliver into one SM (~22 B/clk: 110-130 cycles per MMA for N = 64 and N = 128 alike, tensor pipe ~30% active), not
@@ -65,6 +98,7 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dc_smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t a_full[4], a_empty[4], b_full[8], b_empty[8], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float4 ep_stage[4][32 * 4];   // per epilogue warp: 32 rows x 16 columns, 16-byte slots XOR-swizzled
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nplanes = P.npass == 3 ? 2 : 1;
   const uint32_t a_plane = (uint32_t)P.a_rows * 128u;
@@ -178,71 +212,93 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else {
     // ===== epilogue warps: TMEM lane quarter q = warp % 4 =====
+    // Stores go out in a COALESCED mapping: the accumulator arrives one row per thread (tcgen05.ld 32x32b), and a
+    // thread-per-row float4 store touches 32 different 128-byte lines per instruction - 32 wavefronts of the L1 /
+    // shared-memory datapath that the MMA operand reads also run on (measured: + 33 us for the two split planes on a
+    // 162 us kernel).  16 columns at a time are transposed through a swizzled 2 KB buffer; then lane l owns 16 bytes
+    // (l & 3) of rows (l >> 2) + 8 i: 8 lines per instruction.  The residual of a step (one 128-row block x 32 columns)
+    // is loaded one step AHEAD - for the first step of a tile before the wait for its accumulator - because a load
+    // issued where it is used exposes a DRAM round trip per step (32 per tile: + 40-57 us per launch).
     const int q = warp & 3;
+    constexpr int NH = DC_BN / 32, NSTEP = MT * NH;
+    float4* stg = ep_stage[q];
+    float4 rs[8];
+    if (P.residual && (int)blockIdx.x < total) dc_residual_issue<BN>(P, blockIdx.x, 0, 0, q, lane, rs);
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int as = it & 1;
-      const int mt = t / P.n_ntiles, nt = t - mt * P.n_ntiles;
-      const int tw = mt % P.tiles_w, nh = mt / P.tiles_w;
-      const int n = nh / P.tiles_h, h0 = (nh - n * P.tiles_h) * P.TH, w0 = tw * P.TW;
+      int n, h0, w0, nt;
+      dc_tile(P, t, &n, &h0, &w0, &nt);
       mbar_wait(&acc_full[as], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int cout0 = nt * DC_BN;
 #pragma unroll
-      for (int blk = 0; blk < MT; ++blk) {
-        const int r = blk * 128 + q * 32 + lane;
-        const int hl = r / P.P, wl = r - hl * P.P;
-        const int oh = h0 + hl, ow = w0 + wl;
-        const bool valid = hl < P.TH && wl < P.TW && ow < P.W && oh < P.H;
-        const size_t m = ((size_t)n * P.H + oh) * P.W + ow;
+      for (int step = 0; step < NSTEP; ++step) {
+        const int blk = step / NH, half = step % NH;
+        float4 rc[8];
 #pragma unroll
-        for (int half = 0; half < DC_BN / 32; ++half) {
-          uint32_t acc[32];
-          const uint32_t accw = (uint32_t)(nplanes == 2 ? 2 * DC_BN : DC_BN);
-          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT + blk) * accw + (uint32_t)(half * 32);
-          tmem_ld32(tcol, acc);  // warp-collective
-          if (nplanes == 2) {    // D1 + D2 (see the MMA issuer)
-            uint32_t acc2[32];
-            tmem_ld32(tcol + DC_BN, acc2);
+        for (int e = 0; e < 8; ++e) rc[e] = rs[e];
+        if (P.residual) {   // next step's residual: this tile's next step, or the first step of this CTA's next tile
+          if (step + 1 < NSTEP) dc_residual_issue<BN>(P, t, (step + 1) / NH, (step + 1) % NH, q, lane, rs);
+          else if (t + (int)gridDim.x < total) dc_residual_issue<BN>(P, t + gridDim.x, 0, 0, q, lane, rs);
+        }
+        size_t mo[4];
+        bool vv[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
-          }
-          if (blk == MT - 1 && half == DC_BN / 32 - 1) {
-            // this warp's accumulator quarter is in registers: hand the TMEM stage back to the MMA warp
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
-          }
-          if (valid) {
-            const int c0 = cout0 + half * 32;
-            const size_t o = m * P.Cout + c0;
+        for (int i = 0; i < 4; ++i) vv[i] = dc_row(P, n, h0, w0, blk * 128 + q * 32 + (lane >> 2) + 8 * i, &mo[i]) && !(P.dbg & 4);
+        uint32_t acc[32];
+        const uint32_t accw = (uint32_t)(nplanes == 2 ? 2 * DC_BN : DC_BN);
+        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT + blk) * accw + (uint32_t)(half * 32);
+        tmem_ld32(tcol, acc);  // warp-collective
+        if (nplanes == 2) {    // D1 + D2 (see the MMA issuer)
+          uint32_t acc2[32];
+          tmem_ld32(tcol + DC_BN, acc2);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (c0 + j < P.Cout) {
-                float v[4] = {__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3])};
-                if (P.bias) {
-                  const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + j));
-                  v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
-                }
-                if (P.residual) {
-                  const float4 rs = __ldg(reinterpret_cast<const float4*>(P.residual + o + j));
-                  v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
-                }
-                if (P.relu) {
+          for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
+        }
+        if (step == NSTEP - 1) {
+          // this warp's accumulator quarter is in registers: hand the TMEM stage back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+        }
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-                }
-                *reinterpret_cast<float4*>(P.out_v + o + j) = make_float4(v[0], v[1], v[2], v[3]);
-                if (P.out_hi) {
-                  float hi[4], lo[4];
+        for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) { hi[e] = rna_tf32(v[e]); lo[e] = v[e] - hi[e]; }
-                  *reinterpret_cast<float4*>(P.out_hi + o + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                  if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                }
+          for (int jj = 0; jj < 4; ++jj)
+            stg[lane * 4 + (jj ^ ((lane >> 1) & 3))] =
+                make_float4(__uint_as_float(acc[sub * 16 + jj * 4]), __uint_as_float(acc[sub * 16 + jj * 4 + 1]),
+                            __uint_as_float(acc[sub * 16 + jj * 4 + 2]), __uint_as_float(acc[sub * 16 + jj * 4 + 3]));
+          __syncwarp();
+          const int c = cout0 + half * 32 + sub * 16 + (lane & 3) * 4;
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (P.bias && c < P.Cout) bb = __ldg(reinterpret_cast<const float4*>(P.bias + c));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = (lane >> 2) + 8 * i;
+            const float4 a = stg[row * 4 + ((lane & 3) ^ ((row >> 1) & 3))];
+            if (vv[i] && c < P.Cout) {
+              const size_t o = mo[i] + c;
+              float v[4] = {a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w};
+              if (P.residual) {
+                const float4 r4 = rc[sub * 4 + i];
+                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+              }
+              if (P.relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+              }
+              if (P.out_v) *reinterpret_cast<float4*>(P.out_v + o) = make_float4(v[0], v[1], v[2], v[3]);
+              if (P.out_hi) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { hi[e] = rna_tf32(v[e]); lo[e] = v[e] - hi[e]; }
+                *reinterpret_cast<float4*>(P.out_hi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
               }
             }
           }
+          __syncwarp();
         }
       }
     }
@@ -277,7 +333,7 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   { const char* e = getenv("SS2_DC_DBG"); P.dbg = e ? atoi(e) : 0; }
   P.npass = (ctx->tc_passes == 1 || !in.lo || !L.wk_lo) ? 1 : 3;
   const int nplanes = P.npass == 3 ? 2 : 1;
-  const size_t budget = 227 * 1024 - 2048;
+  const size_t budget = 227 * 1024 - 2048 - 8192;   // static shared memory: barriers + the epilogue's 8 KB staging buffers
   size_t b_stage = 0;
   size_t a_stage = 0;
   int MT = 2;
@@ -288,6 +344,7 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
     P.P = P.TW + 2;
     if (P.P > 128) return false;
     P.TH = 128 * mt_blocks / P.P; if (P.TH > H) P.TH = H;
+    if (P.TH < 1) return false;
     P.a_rows = (128 * mt_blocks + 2 * P.P + 2 + 7) / 8 * 8;
     a_stage = (size_t)P.a_rows * 128 * nplanes;
     P.NA = P.nchunk >= 2 ? 2 : 1;
@@ -303,35 +360,36 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   // 128x64x8 MMA takes ~0.7x the time of a 128x128x8 one
   int small_thr = nsm / 2;
   { const char* e = getenv("SS2_DC_SMALL"); if (e) small_thr = atoi(e); }
+  int force_tw = 0, force_mt = 0;
+  { const char* e = getenv("SS2_DC_PLAN"); if (e) sscanf(e, "%d,%d", &force_tw, &force_mt); }
   for (int attempt = 0; attempt < 2; ++attempt) {
     P.n_ntiles = L.CoutP / BN;
     b_stage = (size_t)BN * DC_BK * 4 * nplanes;
-    MT = 2;
-    // two 128-row blocks per tile when that still leaves every SM several tiles (measured on B200, 32 images: 64->64 at
-    // 90x120 206 us against 245 us with one block; 256->256 at 23x30 has only 192 two-block tiles and loses to the
-    // wave quantisation, 187 us against 152 us)
-    // (split TF32 with N = 128: one block's [D1 | D2] accumulator pair is 256 TMEM columns, two stages fill the 512)
-    bool ok = !(nplanes == 2 && BN == 128) && plan(1, 2);
-    if (!ok || P.TH * P.P <= 128 || (long)P.n_mtiles * P.n_ntiles < 3L * nsm) { MT = 1; ok = plan(1, 1); }
-    if (!ok) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_dc: tile does not fit shared memory");
-    // A full-width two-block tile of a wide map leaves room for ONE input stage only (90x120x64: 129 KB per stage), so
-    // the input load of chunk k + 1 cannot overlap the MMAs of chunk k.  Splitting the row into column tiles shrinks the
-    // stage (and the halo rows re-read per tile: (TH + 2) / TH drops from 2 to 1.33 with three column tiles) until two
-    // input stages and three weight stages fit.
-    {
-      const char* e = getenv("SS2_DC_TW");
-      const int force = e ? atoi(e) : 0;
-      if (force > 0 && W >= 100) {
-        DcParams keep = P; const size_t keep_a = a_stage;
-        if (!(plan(force, MT) && P.TH >= 1)) { P = keep; a_stage = keep_a; }
-      } else if (MT == 2 && P.NA == 1 && P.nchunk >= 2) {
-        DcParams keep = P; const size_t keep_a = a_stage;
-        bool found = false;
-        for (int tw = 2; tw <= 4 && !found; ++tw)
-          found = plan(tw, 2) && P.NA == 2 && P.NB >= 3 && P.TH >= 2;
-        if (!found) { P = keep; a_stage = keep_a; }
+    // Candidates: 1-4 column tiles x one or two 128-row blocks per tile.  Model of a launch (cycles per CTA, fitted to the
+    // measurements in profiles/r02_conv_dc_plan_sweep.jsonl): rounds x [MMA pairs x cost per pair (junk rows of a tile
+    // are paid like real ones) + staged bytes / rate], with penalties for a single input stage (loads and MMAs
+    // alternate) and for fewer than three weight stages.
+    double best = -1.0;
+    int best_tw = 0, best_mt = 0;
+    for (int mtb = 2; mtb >= 1; --mtb) {
+      if (mtb == 2 && nplanes == 2 && BN == 128) continue;   // [D1 | D2] of two blocks x two stages exceed the 512 TMEM columns
+      for (int tw = 1; tw <= 4; ++tw) {
+        if (force_tw > 0 && (tw != force_tw || mtb != force_mt)) continue;
+        if (!plan(tw, mtb)) continue;
+        if (tw > 1 && P.TW < 8) continue;
+        const double pair = nplanes == 2 ? (BN == 64 ? 201.0 : 300.0) : (BN == 64 ? 75.0 : 110.0);
+        const double mma = (double)P.nchunk * 9 * 4 * mtb * pair;
+        const double bytes = (double)P.nchunk * ((double)(P.TH + 2) * P.P * 128 * nplanes + 9.0 * b_stage);
+        const long ntl = (long)P.n_mtiles * P.n_ntiles;
+        double c = (double)((ntl + nsm - 1) / nsm) * (mma + bytes / 40.0);
+        if (P.NA < 2 && P.nchunk >= 2) c *= 1.15;
+        if (P.NB < 3) c *= 1.03;
+        if (best < 0 || c < best) { best = c; best_tw = tw; best_mt = mtb; }
       }
     }
+    if (best < 0) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_dc: tile does not fit shared memory");
+    MT = best_mt;
+    plan(best_tw, best_mt);
     if (BN == 128 && (long)P.n_mtiles * P.n_ntiles <= small_thr) { BN = 64; continue; }
     break;
   }

@@ -188,7 +188,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
             }
-            *reinterpret_cast<float4*>(P.out_v + o + j) = make_float4(v[0], v[1], v[2], v[3]);
+            if (P.out_v) *reinterpret_cast<float4*>(P.out_v + o + j) = make_float4(v[0], v[1], v[2], v[3]);
             if (P.out_hi) {
               float hi[4], lo[4];
 #pragma unroll

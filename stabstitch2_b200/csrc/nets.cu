@@ -273,11 +273,26 @@ static int finalize_weights_impl(ss2_ctx* ctx, int net_id) {
     if (ctx->use_tc) { ref.hi = ref.v + n__; ref.lo = ref.v + 2 * n__; }                        \
   }
 
+// does conv_launch take a tensor-core kernel for this layer (they read only the hi/lo planes of their input)?
+static bool runs_on_tc(ss2_ctx* ctx, const ConvLayer& L, bool in_has_split, int H, int W) {
+  return ctx->use_tc && in_has_split && ((ctx->use_dc && conv_dc_eligible(L, 1, H, W)) || conv_tc_eligible(L));
+}
+
 static int run_block(ss2_ctx* ctx, const ResBlock& b, const ActRef& x, int NB, int H, int W, ActRef* out, int* Ho,
                      int* Wo, cudaStream_t st) {
   int d, h, w;
   conv_out_dims(b.c1, 1, H, W, &d, &h, &w);
-  ARENA_ACT(t1, (size_t)NB * h * w * b.c1.Cout);
+  // conv1's output feeds conv2 only.  When both run on the tensor cores the plain values are never read (v = hi + lo
+  // exactly), so only the split planes are written: a third less store traffic for these layers.
+  ActRef t1;
+  if (runs_on_tc(ctx, b.c1, x.hi != nullptr, H, W) && runs_on_tc(ctx, b.c2, true, h, w)) {
+    const size_t n1 = ((size_t)NB * h * w * b.c1.Cout + 63) / 64 * 64;
+    ARENA(t1p, float, 2 * n1);
+    t1.hi = t1p; t1.lo = t1p + n1;
+  } else {
+    ARENA_ACT(t1f, (size_t)NB * h * w * b.c1.Cout);
+    t1 = t1f;
+  }
   SS2_TRY(conv_launch(ctx, b.c1, x, NB, 1, H, W, t1, nullptr, 1, st));
   const float* idt = x.v;
   if (b.has_down) {
@@ -586,8 +601,18 @@ extern "C" int ss2_conv_nhwc(ss2_ctx* ctx, const float* d_in, int B, int D, int 
         in.lo = split + n;
       }
     }
+    // SS2_CONV_TEST_SPLIT=1 (profiles/conv_bench.py): also write the hi/lo planes like a layer inside the networks does
+    float* osplit = nullptr;
+    if (rc == SS2_OK && use_tc && getenv("SS2_CONV_TEST_SPLIT") && atoi(getenv("SS2_CONV_TEST_SPLIT"))) {
+      int od, oh, ow;
+      conv_out_dims(L, D, H, W, &od, &oh, &ow);
+      const size_t on = (size_t)B * od * oh * ow * L.Cout;
+      if (cudaMalloc((void**)&osplit, 2 * on * sizeof(float)) == cudaSuccess) { out.hi = osplit; out.lo = osplit + on; }
+    }
     if (rc == SS2_OK) rc = conv_launch(ctx, L, in, B, D, H, W, out, d_residual, relu, st);
     ctx->use_tc = saved;
+    cudaStreamSynchronize(st);
+    if (osplit) cudaFree(osplit);
   }
   cudaStreamSynchronize(st);
   if (split) cudaFree(split);
