@@ -112,6 +112,7 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[64];
   __shared__ __align__(16) float xchg[2][4][64];
+  __shared__ float4 pstage[4][16 * 4];      // per epilogue warp: 16 pooled pixels x 16 channels, swizzled
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* b_smem = smem;                       // [kh][plane][64][32] SWIZZLE_128B: hi | lo of a filter row are ONE N = 128 operand
   uint8_t* a_ring = smem + 2 * ST_BPLANE;       // ST_NA row-pair slots
@@ -213,8 +214,6 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int ox0 = s.half ? P.PW - 1 : 0;
       const int x = ox0 + L;
       const bool centre = !(x & 1);
-      const int pc = x >> 1;
-      const bool store = centre && (s.half ? (pc >= P.PW / 2 && pc < P.PW) : (pc < P.PW / 2));
       for (int oy = s.oy0; oy <= s.oy1; ++oy, ++it) {
         const int as = it % ST_NACC;
         mbar_wait(&acc_full[as], (it / ST_NACC) & 1);
@@ -260,36 +259,61 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             *reinterpret_cast<float4*>(xb + q * 64 + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const size_t o = (((size_t)s.n * P.PH + pr) * P.PW + pc) * 64;
         const bool take_l = !s.half && lane == 0, take_r = s.half && lane == 31;
         const float* nb = xb + (take_l ? (q > 0 ? q - 1 : 0) : (q < 3 ? q + 1 : 3)) * 64;
         const bool edge_l = take_l && q == 0;          // x = -1: outside the image
+        // store mapping: the 16 pooled pixels of this warp x 16 channels go through a swizzled 1 KB buffer, then lane l
+        // owns 16 bytes (l & 3) of pooled pixels (l >> 2) + 8 i: 8 lines per store instruction instead of 16 half-used ones
+        size_t so[2];
+        bool sv[2];
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
-          float m[4];
-          float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (take_l || take_r) e = *reinterpret_cast<const float4*>(nb + j);
-          const float ev[4] = {e.x, e.y, e.z, e.w};
+        for (int i = 0; i < 2; ++i) {
+          const int pcc = (ox0 + q * 32 + 2 * ((lane >> 2) + 8 * i) + s.half) >> 1;
+          sv[i] = s.half ? (pcc >= P.PW / 2 && pcc < P.PW) : (pcc < P.PW / 2);
+          so[i] = (((size_t)s.n * P.PH + pr) * P.PW + pcc) * 64;
+        }
+        float4* pst = pstage[q];
+        const int pp = lane >> 1;                      // pooled pixel of a centre lane within the warp
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float l = __shfl_up_sync(0xffffffffu, acc[j + k], 1);
-            float r = __shfl_down_sync(0xffffffffu, acc[j + k], 1);
-            if (take_l) l = edge_l ? acc[j + k] : ev[k];
-            if (take_r) r = ev[k];
-            m[k] = fmaxf(fmaxf(l, r), acc[j + k]);
+        for (int j = 0; j < 64; j += 16) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float m[4];
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (take_l || take_r) e = *reinterpret_cast<const float4*>(nb + j + jj * 4);
+            const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float a = acc[j + jj * 4 + k];
+              float l = __shfl_up_sync(0xffffffffu, a, 1);
+              float r = __shfl_down_sync(0xffffffffu, a, 1);
+              if (take_l) l = edge_l ? a : ev[k];
+              if (take_r) r = ev[k];
+              m[k] = fmaxf(fmaxf(l, r), a);
+            }
+            if (centre) pst[pp * 4 + (jj ^ ((pp >> 1) & 3))] = make_float4(m[0], m[1], m[2], m[3]);
           }
-          if (store) {
-            const float4 bb = *reinterpret_cast<const float4*>(s_bias + j);
-            float v[4] = {fmaxf(m[0] + bb.x, 0.f), fmaxf(m[1] + bb.y, 0.f), fmaxf(m[2] + bb.z, 0.f), fmaxf(m[3] + bb.w, 0.f)};
-            *reinterpret_cast<float4*>(P.out_v + o + j) = make_float4(v[0], v[1], v[2], v[3]);
-            if (P.out_hi) {
-              float hi[4], lo[4];
+          __syncwarp();
+          const int c = j + (lane & 3) * 4;
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) { hi[k] = rna_tf32(v[k]); lo[k] = v[k] - hi[k]; }
-              *reinterpret_cast<float4*>(P.out_hi + o + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-              if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          for (int i = 0; i < 2; ++i) {
+            const int row = (lane >> 2) + 8 * i;
+            const float4 a = pst[row * 4 + ((lane & 3) ^ ((row >> 1) & 3))];
+            if (sv[i]) {
+              const size_t o = so[i] + c;
+              float v[4] = {fmaxf(a.x + bb.x, 0.f), fmaxf(a.y + bb.y, 0.f), fmaxf(a.z + bb.z, 0.f), fmaxf(a.w + bb.w, 0.f)};
+              *reinterpret_cast<float4*>(P.out_v + o) = make_float4(v[0], v[1], v[2], v[3]);
+              if (P.out_hi) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { hi[k] = rna_tf32(v[k]); lo[k] = v[k] - hi[k]; }
+                *reinterpret_cast<float4*>(P.out_hi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+              }
             }
           }
+          __syncwarp();
         }
         // the carried row for the next pooled row is this odd conv row itself
 #pragma unroll

@@ -70,6 +70,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams P) {
   constexpr int NOPER = NPASS == 3 ? 2 : 1;  // operand planes per matrix (hi [, lo])
   constexpr int STAGE_BYTES = NOPER * (TC_A_BYTES + TC_B_BYTES);
+  // split TF32 in TWO MMAs per k-step (see conv_dc.cu): B_hi | B_lo of a stage are adjacent, so A_hi x [B_hi | B_lo] is
+  // one N = 128 MMA into accumulator columns [D1 | D2] and A_lo x B_hi an N = 64 one into D1; the epilogue adds D1 + D2
+  constexpr int TC_ACC_COLS = NPASS == 3 ? 2 * TC_BN : TC_BN;
+  __shared__ float4 ep_stage[4][32 * 4];   // per epilogue warp: 32 rows x 16 columns, 16-byte slots XOR-swizzled
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
@@ -94,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TC_BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TC_ACC_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -132,6 +136,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===== MMA issuer (one elected thread; descriptors advanced with 32-bit adds, see tc_common.cuh) =====
     if (dc_elect_one()) {
       const uint32_t idesc = tc_idesc();
+      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int it = 0; it < niter; ++it) {
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
@@ -140,10 +145,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const uint32_t b_hi = a_hi + ((NOPER * TC_A_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
-          dc_mma(tmem_base, a_hi + 2 * k, b_hi + 2 * k, DC_DESC_HI, idesc, (it > 0 || k > 0) ? 1u : 0u);
           if (NPASS == 3) {
+            dc_mma(tmem_base, a_hi + 2 * k, b_hi + 2 * k, DC_DESC_HI, idesc2, (it > 0 || k > 0) ? 1u : 0u);
             dc_mma(tmem_base, a_hi + (TC_A_BYTES >> 4) + 2 * k, b_hi + 2 * k, DC_DESC_HI, idesc, 1u);
-            dc_mma(tmem_base, a_hi + 2 * k, b_hi + (TC_B_BYTES >> 4) + 2 * k, DC_DESC_HI, idesc, 1u);
+          } else {
+            dc_mma(tmem_base, a_hi + 2 * k, b_hi + 2 * k, DC_DESC_HI, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above have read it
@@ -152,59 +158,101 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else {
     // ===== epilogue warps: TMEM lane quarter q = warp % 4 =====
+    // Coalesced store mapping as in conv_dc.cu: 16 accumulator columns at a time are transposed through a swizzled 2 KB
+    // buffer, then lane l owns 16 bytes (l & 3) of rows (l >> 2) + 8 i.  These warps idle during the main loop, so the
+    // residual of the first 32 columns is loaded before the wait for the accumulator, the second half during the first.
     const int q = warp & 3;
-    const int r = q * 32 + lane;
+    float4* stg = ep_stage[q];
+    size_t mo[4];
+    bool vv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = q * 32 + (lane >> 2) + 8 * i;
+      int rr = r;
+      const int wl = rr % P.TW; rr /= P.TW;
+      const int hl = rr % P.TH; rr /= P.TH;
+      const int tl = rr % P.TT; rr /= P.TT;
+      const int nl = rr;
+      const int ow = w0 + wl, oh = h0 + hl, ot = t0 + tl, on = n0 + nl;
+      vv[i] = r < rows && ow < P.Wo && oh < P.Ho && ot < P.Do && on < P.B;
+      mo[i] = ((((size_t)on * P.Do + ot) * P.Ho + oh) * P.Wo + ow) * P.ldo;
+    }
+    auto col_ok = [&](int half, int sub) {
+      const int cl = half * 32 + sub * 16 + (lane & 3) * 4;
+      return cout0 + cl < P.Cout && cl < P.ncol;
+    };
+    auto residual_issue = [&](int half, float4 (&rs)[8]) {
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          rs[sub * 4 + i] = (vv[i] && col_ok(half, sub))
+                                ? __ldg(reinterpret_cast<const float4*>(P.residual + mo[i] + cout0 + half * 32 + sub * 16 + (lane & 3) * 4))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 rs[8];
+    if (P.residual) residual_issue(0, rs);
     mbar_wait(&accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // row -> output position
-    int rr = r;
-    const int wl = rr % P.TW; rr /= P.TW;
-    const int hl = rr % P.TH; rr /= P.TH;
-    const int tl = rr % P.TT; rr /= P.TT;
-    const int nl = rr;
-    const int ow = w0 + wl, oh = h0 + hl, ot = t0 + tl, on = n0 + nl;
-    const bool valid = r < rows && ow < P.Wo && oh < P.Ho && ot < P.Do && on < P.B;
-    const size_t m = (((size_t)on * P.Do + ot) * P.Ho + oh) * P.Wo + ow;
 #pragma unroll
     for (int half = 0; half < TC_BN / 32; ++half) {
+      float4 rc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) rc[e] = rs[e];
+      if (P.residual && half + 1 < TC_BN / 32) residual_issue(half + 1, rs);
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + half * 32, acc);  // warp-collective
-      if (valid) {
-        const int c0 = cout0 + half * 32;
-        const size_t o = m * P.ldo + c0;
+      if (NPASS == 3) {   // D1 + D2
+        uint32_t acc2[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TC_BN + half * 32, acc2);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (c0 + j < P.Cout && half * 32 + j < P.ncol) {
-            float v[4] = {__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3])};
-            if (P.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + j));
-              v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-            }
+        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
+      }
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          stg[lane * 4 + (jj ^ ((lane >> 1) & 3))] =
+              make_float4(__uint_as_float(acc[sub * 16 + jj * 4]), __uint_as_float(acc[sub * 16 + jj * 4 + 1]),
+                          __uint_as_float(acc[sub * 16 + jj * 4 + 2]), __uint_as_float(acc[sub * 16 + jj * 4 + 3]));
+        __syncwarp();
+        const bool cok = col_ok(half, sub);
+        const int c = cout0 + half * 32 + sub * 16 + (lane & 3) * 4;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.bias && cok) bb = __ldg(reinterpret_cast<const float4*>(P.bias + c));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = (lane >> 2) + 8 * i;
+          const float4 a = stg[row * 4 + ((lane & 3) ^ ((row >> 1) & 3))];
+          if (vv[i] && cok) {
+            const size_t o = mo[i] + c;
+            float v[4] = {a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w};
             if (P.residual) {
-              const float4 rs = __ldg(reinterpret_cast<const float4*>(P.residual + o + j));
-              v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
+              const float4 r4 = rc[sub * 4 + i];
+              v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
             }
             if (P.relu) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
             }
-            if (P.out_v) *reinterpret_cast<float4*>(P.out_v + o + j) = make_float4(v[0], v[1], v[2], v[3]);
+            if (P.out_v) *reinterpret_cast<float4*>(P.out_v + o) = make_float4(v[0], v[1], v[2], v[3]);
             if (P.out_hi) {
               float hi[4], lo[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) { hi[e] = rna_tf32(v[e]); lo[e] = v[e] - hi[e]; }
-              *reinterpret_cast<float4*>(P.out_hi + o + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-              if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+              *reinterpret_cast<float4*>(P.out_hi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
           }
         }
+        __syncwarp();
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_ACC_COLS));
   }
 }
 
