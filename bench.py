@@ -424,8 +424,14 @@ def run_native(args):
     # cannot be taken during a timed run); only reported when the capture was made on this exact configuration
     traffic = traffic_src = None
     try:
+        import hashlib
         tj = json.load(open(os.path.join(ROOT, "profiles", "warp_kernel_traffic.json")))
-        if (tj["height"], tj["width"], tj["frames_per_launch"], list(tj["canvas"])) == (H, W, F, [Ho, Wo]):
+        sha = hashlib.sha1(open(os.path.join(ROOT, "stabstitch2_b200", "csrc", "tps.cu"), "rb").read()).hexdigest()
+        if (tj["height"], tj["width"], tj["frames_per_launch"], list(tj["canvas"])) != (H, W, F, [Ho, Wo]):
+            traffic_src = "no ncu capture for this configuration"
+        elif tj.get("tps_cu_sha1") != sha:
+            traffic_src = "profiles/warp_kernel_traffic.json was captured from another version of csrc/tps.cu: dropped (re-run profiles/make_traffic_json.py)"
+        else:
             traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
             traffic_src = "profiles/warp_kernel_traffic.json: %s" % tj.get("source", "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch")
     except Exception:

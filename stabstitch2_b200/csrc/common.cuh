@@ -37,8 +37,8 @@ struct ConvLayer {
   // 7x7 stride-2 stem with 3 input channels: wk_hi/lo are [CoutP][7 * 32], k = kh * 32 + kw * 4 + c (one filter row =
   // 8 NHWC4 pixels, the eighth and the fourth channel are zero); consumed by conv_tc_stem_launch
   bool stem_k32 = false;
-  // the same stem for the direct kernel (conv_stem.cu): [64][7 * 32], k = kh * 32 + (kw & 1) * 16 + (kw >> 1) * 4 + c
-  // (even filter columns, then odd filter columns + one zero pixel)
+  // the same stem for the direct kernel (conv_stem.cu): [64][7 * 32] = 25 k-steps of two pixels (+ 3 zero steps), order
+  // in nets.cu pack_conv
   float* ws_hi = nullptr;
   float* ws_lo = nullptr;
 };

@@ -11,8 +11,9 @@
 // pixel = 16 bytes per output pixel, which is exactly the row pitch of the un-swizzled K-major UMMA layout (core
 // matrix = 8 rows x 16 B): with SBO = 128 B and LBO = 16 B the descriptor reads row m, k at 16 (m + k / 4) + 4 (k % 4)
 // bytes, i.e. pixels m + j, m + j + 1 of one staged sub-row - an overlapping ("Toeplitz") A operand straight from the
-// staged image row, no im2col copy anywhere.  One filter row is 4 MMAs of K = 8 (two pixels of one column parity):
-// even columns kw = 0,2,4,6, odd columns kw = 1,3,5 and a zero weight.
+// staged image row, no im2col copy anywhere.  The 49 filter taps are 25 k-steps of K = 8 (two pixels): per filter row
+// even columns (0,2), (4,6) and odd columns (1,3); the left-over column 5 pairs up across two filter rows (LBO = the
+// distance of their sub-rows in the staged row pair).
 //   * a tile is one conv row of one image half (M = 128 pixels, N = 64 channels); a persistent CTA walks down a band of
 //     conv rows, so each input row pair is staged once per band (ring of row pairs, one 16.5 KB TMA box each);
 //   * the whole filter (7 rows x [64][32], hi/lo: 112 KB) stays resident in shared memory;
@@ -176,25 +177,26 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (; waited <= g0 + 3; ++waited) mbar_wait(&a_full[waited % ST_NA], (waited / ST_NA) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d_tmem = tmem_base + (uint32_t)as * accw;
+          // 25 k-steps of K = 8 (two pixels).  Steps 3 kh + {0, 1, 2}: pixels (0, 1), (2, 3) of the even-column sub-row and
+          // (0, 1) of the odd-column sub-row of filter row kh, the two pixels 16 bytes apart (LBO).  The seven left-over
+          // odd-column pixels (filter column 5) pair up ACROSS filter rows: rows 2t and 2t + 1 sit in the same row-pair
+          // slot, two sub-rows apart, so LBO = 2 sub-rows makes them one k-step (the last one pairs with a zero weight).
 #pragma unroll
-          for (int kh = 0; kh < 7; ++kh) {
+          for (int step = 0; step < 25; ++step) {
+            int kh, seg, px;
+            uint32_t lbo = 1u;                                   // 16 B
+            if (step < 21) { kh = step / 3; seg = (kh & 1) * 2 + (step % 3 == 2 ? 1 : 0); px = (step % 3 == 1) ? 2 : 0; }
+            else if (step < 24) { kh = 2 * (step - 21); seg = 1; px = 2; lbo = (uint32_t)(2 * ST_SEG >> 4); }
+            else { kh = 6; seg = 1; px = 2; }
             const int sl = (g0 + (kh >> 1)) % ST_NA;
-            // sub-row (row parity kh & 1) of the pair, hi plane; low word carries LBO = 16 B
-            const uint32_t a_row = (((a_base + (uint32_t)sl * ST_SLOT + (uint32_t)((kh & 1) * 2) * ST_SEG) & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t b_row = b_lo0 + (uint32_t)(2 * kh * ST_BCHUNK >> 4);
-#pragma unroll
-            for (int cp = 0; cp < 2; ++cp)
-#pragma unroll
-              for (int jp = 0; jp < 2; ++jp) {
-                const uint32_t da = a_row + (uint32_t)((cp * ST_SEG + jp * 32) >> 4);
-                const uint32_t db = b_row + (uint32_t)((cp * 2 + jp) * 2);
-                if (nplanes == 2) {
-                  st_mma(d_tmem, da, db, idesc2, (kh | cp | jp) ? 1u : 0u);
-                  st_mma(d_tmem, da + (uint32_t)(4 * ST_SEG >> 4), db, idesc, 1u);
-                } else {
-                  st_mma(d_tmem, da, db, idesc, (kh | cp | jp) ? 1u : 0u);
-                }
-              }
+            const uint32_t da = (((a_base + (uint32_t)sl * ST_SLOT + (uint32_t)seg * ST_SEG + (uint32_t)px * 16u) & 0x3FFFFu) >> 4) | (lbo << 16);
+            const uint32_t db = b_lo0 + (uint32_t)(2 * (step >> 2) * ST_BCHUNK >> 4) + (uint32_t)((step & 3) * 2);
+            if (nplanes == 2) {
+              st_mma(d_tmem, da, db, idesc2, step ? 1u : 0u);
+              st_mma(d_tmem, da + (uint32_t)(4 * ST_SEG >> 4), db, idesc, 1u);
+            } else {
+              st_mma(d_tmem, da, db, idesc, step ? 1u : 0u);
+            }
           }
           umma_commit(&a_empty[g0 % ST_NA]);     // row pair oy is not read by later rows
           umma_commit(&acc_full[as]);

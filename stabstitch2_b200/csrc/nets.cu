@@ -131,17 +131,28 @@ static int pack_conv(ss2_ctx* ctx, int net, const std::string& wkey, const std::
     SS2_TRY(upload(ctx, hi, &L->wk_hi));
     SS2_TRY(upload(ctx, lo, &L->wk_lo));
     L->stem_k32 = true;
-    if (L->CoutP == 64) {   // direct kernel: even filter columns first, then the odd ones (conv_stem.cu)
+    if (L->CoutP == 64) {
+      // direct kernel (conv_stem.cu): 25 k-steps of 8 = two NHWC4 pixels each.  Steps 3 kh + {0, 1, 2}: filter columns
+      // (0, 2), (4, 6), (1, 3) of filter row kh; steps 21 + t: column 5 of rows 2t and 2t + 1; step 24: column 5 of row 6
+      // and a zero pixel.
       std::vector<float> shi(hi.size(), 0.f), slo(lo.size(), 0.f);
-      for (int o = 0; o < Cout; ++o)
-        for (int kh = 0; kh < 7; ++kh)
-          for (int kw = 0; kw < 7; ++kw)
-            for (int c = 0; c < 3; ++c) {
-              const size_t from = (size_t)o * Ktot + kh * 32 + kw * 4 + c;
-              const size_t to = (size_t)o * Ktot + kh * 32 + (kw & 1) * 16 + (kw >> 1) * 4 + c;
-              shi[to] = hi[from];
-              slo[to] = lo[from];
-            }
+      auto put = [&](int o, int step, int half, int kh, int kw) {
+        for (int c = 0; c < 3; ++c) {
+          const size_t from = (size_t)o * Ktot + kh * 32 + kw * 4 + c;
+          const size_t to = (size_t)o * Ktot + step * 8 + half * 4 + c;
+          shi[to] = hi[from];
+          slo[to] = lo[from];
+        }
+      };
+      for (int o = 0; o < Cout; ++o) {
+        for (int kh = 0; kh < 7; ++kh) {
+          put(o, 3 * kh + 0, 0, kh, 0); put(o, 3 * kh + 0, 1, kh, 2);
+          put(o, 3 * kh + 1, 0, kh, 4); put(o, 3 * kh + 1, 1, kh, 6);
+          put(o, 3 * kh + 2, 0, kh, 1); put(o, 3 * kh + 2, 1, kh, 3);
+        }
+        for (int t = 0; t < 3; ++t) { put(o, 21 + t, 0, 2 * t, 5); put(o, 21 + t, 1, 2 * t + 1, 5); }
+        put(o, 24, 0, 6, 5);
+      }
       SS2_TRY(upload(ctx, shi, &L->ws_hi));
       SS2_TRY(upload(ctx, slo, &L->ws_lo));
     }
