@@ -50,19 +50,21 @@ cost_volume_kernel(const float4* __restrict__ x1, const float4* __restrict__ x2,
 }
 
 // ------------------------------------------------------------------------------------------
-// Blocked cost volume for C = 128 (the production shape): a CTA owns an 8x8 pixel tile, stages
-// x1 (64 px) and the x2 halo ((8+2sr)^2 px) in shared memory 32 channels at a time, and every
-// thread accumulates 2 horizontally adjacent pixels x up to 3 displacement rows x (2sr+1)
-// displacements in registers: one x2 float4 from shared memory feeds both pixels (7 FMAs per
-// LDS.128).  The channel chunks are double buffered with cp.async (zero fill outside the image =
-// the reference's F.pad): round 1's version staged each chunk with plain loads between two
-// barriers and spent its time waiting for them (219 us per launch for 18 us of FMA work).
-// Results go through shared memory so that the NHWC rows (and their tf32 split) are written with
-// coalesced float4 stores.
+// Blocked cost volume for C = 128 (the production shape).  A CTA owns an 8x8 pixel tile and stages x1 (64 px) and the
+// x2 halo ((8+2sr)^2 px) in shared memory 32 channels at a time, double buffered with cp.async (zero fill outside
+// the image = the reference's F.pad).  A thread owns ONE ROW of 8 pixels x ONE displacement row j x all (2sr+1)
+// horizontal displacements (88 accumulators for sr = 5) for half of the channels: per 4 channels it loads the 8 x1
+// vectors of its pixel row and the 8+2sr x2 vectors of halo row py + j once and issues 8 x (2sr+1) x 4 FMAs from
+// them - 13.5 FMAs per LDS.128, so the kernel is bound by the FMA pipe and no longer by shared-memory bandwidth.
+// (The previous organisation - a pixel PAIR per thread - fed 7 FMAs per LDS.128 with 4 wavefronts each and ran at
+// 160 us per launch for 18 us of FMA work.)  Lanes of a warp differ in (py, j), i.e. read different rows: the row
+// pitches are padded to 4 banks modulo 32 so that 8 consecutive rows hit 8 different bank groups.
+// The two channel halves meet in shared memory, which also turns the result into coalesced NHWC rows (+ tf32 split).
 // ------------------------------------------------------------------------------------------
 #define CVT 8          // tile edge
 #define CV_CK 32       // channels per stage
-#define CV_LD 36       // padded row length (floats): conflict-free LDS.128 across 8 lanes
+#define CV_LD 32       // floats per staged pixel (all lanes of a load read the same pixel column: no per-pixel padding)
+#define CV_X1_PITCH (CVT * CV_LD + 4)   // floats per x1 tile row: 260 = 4 (mod 32)
 
 __device__ __forceinline__ void cv_cp_async16(float* smem_dst, const float* gsrc, bool valid) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -70,38 +72,48 @@ __device__ __forceinline__ void cv_cp_async16(float* smem_dst, const float* gsrc
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
 }
 
+template <int SR> struct CvShape {
+  static constexpr int KD = 2 * SR + 1, HALO = CVT + 2 * SR;
+  // floats per x2 halo row, padded to 4 (mod 32)
+  static constexpr int X2_PITCH = HALO * CV_LD + ((4 - (HALO * CV_LD) % 32) + 32) % 32;
+  static constexpr int STAGE = CVT * CV_X1_PITCH + HALO * X2_PITCH;   // floats per buffer
+  static constexpr int HALF_THREADS = ((CVT * KD + 31) / 32) * 32;   // each channel half starts on a warp boundary
+  static constexpr int THREADS = 2 * HALF_THREADS;
+  static constexpr int SO_PITCH = CVT * 128 + 4;                     // floats per tile row of the result buffer (4 mod 32)
+};
+
 template <int SR>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(CvShape<SR>::THREADS)
 cost_volume_tiled_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int H, int W, int CP, ActRef out) {
-  constexpr int KD = 2 * SR + 1, HALO = CVT + 2 * SR, NJ = (KD + 3) / 4;
-  constexpr int STAGE = (CVT * CVT + HALO * HALO) * CV_LD;   // floats per buffer
+  using S = CvShape<SR>;
+  constexpr int KD = S::KD, HALO = S::HALO, NT = S::THREADS;
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.z, ty0 = blockIdx.y * CVT, tx0 = blockIdx.x * CVT;
-  const int tid = threadIdx.x, pp = tid & 31, g = tid >> 5;
-  const int py = pp >> 2, px = (pp & 3) * 2;  // pixel pair (py, px), (py, px+1) of the tile
+  const int tid = threadIdx.x;
+  const int idx = tid % S::HALF_THREADS, half = tid / S::HALF_THREADS;
+  const int py = idx % CVT, j = idx / CVT;
+  const bool active = idx < CVT * KD;   // the last lanes of each half's last warp idle
   const size_t img = (size_t)b * H * W;
-  float acc[2][NJ][KD];
+  float acc[CVT][KD];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int p = 0; p < CVT; ++p)
 #pragma unroll
-    for (int jj = 0; jj < NJ; ++jj)
-#pragma unroll
-      for (int i = 0; i < KD; ++i) acc[a][jj][i] = 0.f;
+    for (int i = 0; i < KD; ++i) acc[p][i] = 0.f;
   // stage x1 tile and x2 halo of channel chunk c0 into buffer `buf` (zero outside the image), 8 float4 per pixel
   auto stage = [&](int buf, int c0) {
-    float* s1 = sm + buf * STAGE;
-    float* s2 = s1 + CVT * CVT * CV_LD;
-    for (int e = tid; e < CVT * CVT * (CV_CK / 4); e += 128) {
+    float* s1 = sm + buf * S::STAGE;
+    float* s2 = s1 + CVT * CV_X1_PITCH;
+    for (int e = tid; e < CVT * CVT * (CV_CK / 4); e += NT) {
       const int p = e / (CV_CK / 4), q = e % (CV_CK / 4);
       const int y = ty0 + p / CVT, x = tx0 + p % CVT;
       const bool ok = y < H && x < W;
-      cv_cp_async16(s1 + p * CV_LD + q * 4, ok ? x1 + (img + (size_t)y * W + x) * 128 + c0 + q * 4 : x1, ok);
+      cv_cp_async16(s1 + (p / CVT) * CV_X1_PITCH + (p % CVT) * CV_LD + q * 4, ok ? x1 + (img + (size_t)y * W + x) * 128 + c0 + q * 4 : x1, ok);
     }
-    for (int e = tid; e < HALO * HALO * (CV_CK / 4); e += 128) {
+    for (int e = tid; e < HALO * HALO * (CV_CK / 4); e += NT) {
       const int p = e / (CV_CK / 4), q = e % (CV_CK / 4);
       const int y = ty0 - SR + p / HALO, x = tx0 - SR + p % HALO;
       const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
-      cv_cp_async16(s2 + p * CV_LD + q * 4, ok ? x2 + (img + (size_t)y * W + x) * 128 + c0 + q * 4 : x2, ok);
+      cv_cp_async16(s2 + (p / HALO) * S::X2_PITCH + (p % HALO) * CV_LD + q * 4, ok ? x2 + (img + (size_t)y * W + x) * 128 + c0 + q * 4 : x2, ok);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -114,53 +126,53 @@ cost_volume_tiled_kernel(const float* __restrict__ x1, const float* __restrict__
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    const float* s1 = sm + (ck & 1) * STAGE;
-    const float* s2 = s1 + CVT * CVT * CV_LD;
-#pragma unroll 2
-    for (int q = 0; q < CV_CK / 4; ++q) {
-      const float4 a0 = *reinterpret_cast<const float4*>(s1 + (py * CVT + px) * CV_LD + q * 4);
-      const float4 a1 = *reinterpret_cast<const float4*>(s1 + (py * CVT + px + 1) * CV_LD + q * 4);
+    if (active) {
+      const float* s1 = sm + (ck & 1) * S::STAGE + py * CV_X1_PITCH;
+      const float* s2 = sm + (ck & 1) * S::STAGE + CVT * CV_X1_PITCH + (py + j) * S::X2_PITCH;
+      for (int qq = 0; qq < CV_CK / 8; ++qq) {
+        const int q = 2 * qq + half;
+        float4 a[CVT];
 #pragma unroll
-      for (int jj = 0; jj < NJ; ++jj) {
-        const int j = g + 4 * jj;
-        if (j < KD) {  // warp-uniform
-          const float* row = s2 + ((py + j) * HALO + px) * CV_LD + q * 4;
+        for (int p = 0; p < CVT; ++p) a[p] = *reinterpret_cast<const float4*>(s1 + p * CV_LD + q * 4);
 #pragma unroll
-          for (int i = 0; i <= KD; ++i) {
-            const float4 v = *reinterpret_cast<const float4*>(row + i * CV_LD);
-            if (i < KD) acc[0][jj][i] = fmaf(a0.w, v.w, fmaf(a0.z, v.z, fmaf(a0.y, v.y, fmaf(a0.x, v.x, acc[0][jj][i]))));
-            if (i > 0) acc[1][jj][i - 1] = fmaf(a1.w, v.w, fmaf(a1.z, v.z, fmaf(a1.y, v.y, fmaf(a1.x, v.x, acc[1][jj][i - 1]))));
+        for (int c = 0; c < HALO; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(s2 + c * CV_LD + q * 4);
+#pragma unroll
+          for (int p = 0; p < CVT; ++p) {
+            if (c - p >= 0 && c - p < KD)   // compile time
+              acc[p][c - p] = fmaf(a[p].w, v.w, fmaf(a[p].z, v.z, fmaf(a[p].y, v.y, fmaf(a[p].x, v.x, acc[p][c - p]))));
           }
         }
       }
     }
     __syncthreads();   // all reads of this buffer are done before the chunk after next is staged into it
   }
-  // results -> shared [64][CP] -> coalesced NHWC rows
-  __syncthreads();
-  float* so = sm;  // 64 * CP floats (CP <= 128) fit in the x2 halo area
-  for (int e = tid; e < CVT * CVT * CP; e += 128) so[e] = 0.f;
-  __syncthreads();
+  // the two channel halves go to two shared-memory buffers [8 rows][8 px][CP] (row pitch 4 mod 32: the lanes of a warp
+  // differ in py and j) and are added on the way out as coalesced NHWC rows
+  float* so = sm + half * (CVT * S::SO_PITCH);
+  if (active) {
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+    for (int p = 0; p < CVT; ++p)
 #pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      const int j = g + 4 * jj;
-      if (j < KD) {
-#pragma unroll
-        for (int i = 0; i < KD; ++i) {
-          float v = acc[a][jj][i] * (1.0f / 128.0f);
-          v = v > 0.f ? v : 0.1f * v;
-          so[(py * CVT + px + a) * CP + j * KD + i] = v;
-        }
-      }
-    }
+      for (int i = 0; i < KD; ++i) so[py * S::SO_PITCH + p * CP + j * KD + i] = acc[p][i];
+  }
   __syncthreads();
-  for (int e = tid; e < CVT * CVT * (CP / 4); e += 128) {
+  for (int e = tid; e < CVT * CVT * (CP / 4); e += NT) {
     const int p = e / (CP / 4), q = e % (CP / 4);
     const int y = ty0 + p / CVT, x = tx0 + p % CVT;
-    if (y < H && x < W)
-      store_split4(out, (img + (size_t)y * W + x) * CP + q * 4, *reinterpret_cast<const float4*>(so + p * CP + q * 4));
+    if (y < H && x < W) {
+      const float* s0 = sm + (p / CVT) * S::SO_PITCH + (p % CVT) * CP + q * 4;
+      const float4 u0 = *reinterpret_cast<const float4*>(s0);
+      const float4 u1 = *reinterpret_cast<const float4*>(s0 + CVT * S::SO_PITCH);
+      float v[4] = {u0.x + u1.x, u0.y + u1.y, u0.z + u1.z, u0.w + u1.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k] *= (1.0f / 128.0f);
+        v[k] = v[k] > 0.f ? v[k] : 0.1f * v[k];
+        if (q * 4 + k >= KD * KD) v[k] = 0.f;   // padded channels of the next convolution
+      }
+      store_split4(out, (img + (size_t)y * W + x) * CP + q * 4, make_float4(v[0], v[1], v[2], v[3]));
+    }
   }
 }
 
@@ -170,8 +182,7 @@ int cost_volume_launch(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B
   if ((2 * sr + 1) * (2 * sr + 1) > CP || (CP & 31)) return ss2_fail(ctx, SS2_ERR_INVALID, "cost_volume: CP must be a multiple of 32 and >= (2sr+1)^2");
   if (B <= 0) return SS2_OK;
   if (C == 128 && (sr == 5 || sr == 3) && CP <= 128 && (CP & 3) == 0) {
-    const int halo = CVT + 2 * sr;
-    const size_t smem = (size_t)2 * (CVT * CVT + halo * halo) * CV_LD * sizeof(float);   // two channel-chunk buffers
+    const size_t smem = (size_t)2 * (sr == 5 ? CvShape<5>::STAGE : CvShape<3>::STAGE) * sizeof(float);   // two channel-chunk buffers
     dim3 g(cdiv(W, CVT), cdiv(H, CVT), B);
     static bool attr_dev[16] = {false};  // per device: function attributes live in the device's context
     bool& attr = attr_dev[ctx->device & 15];
@@ -180,8 +191,8 @@ int cost_volume_launch(ss2_ctx* ctx, const float* d_x1, const float* d_x2, int B
       SS2_CUDA(ctx, cudaFuncSetAttribute(cost_volume_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
       attr = true;
     }
-    if (sr == 5) cost_volume_tiled_kernel<5><<<g, 128, smem, st>>>(d_x1, d_x2, H, W, CP, out);
-    else cost_volume_tiled_kernel<3><<<g, 128, smem, st>>>(d_x1, d_x2, H, W, CP, out);
+    if (sr == 5) cost_volume_tiled_kernel<5><<<g, CvShape<5>::THREADS, smem, st>>>(d_x1, d_x2, H, W, CP, out);
+    else cost_volume_tiled_kernel<3><<<g, CvShape<3>::THREADS, smem, st>>>(d_x1, d_x2, H, W, CP, out);
     SS2_LAUNCH_CHECK(ctx);
     return SS2_OK;
   }

@@ -777,6 +777,38 @@ def test_conv_kernels_vs_torch(case, use_tc):
     assert err < (3e-4 if use_tc else 2e-5), err
 
 
+@pytest.mark.parametrize("shape", [(3, 13, 37, 64, 64), (2, 29, 126, 64, 128), (5, 9, 50, 128, 64)])
+def test_conv_dc_every_tile_plan(shape, monkeypatch):
+    """the direct 3x3 kernel under every tile plan the planner can pick (1-4 column tiles x 1-2 row blocks, forced with
+    SS2_DC_PLAN) on ragged shapes (W not a multiple of the column tile, rows not a multiple of the tile), with residual
+    and the split output planes written like inside the networks: every plan against the PyTorch fp64 reference"""
+    from stabstitch2_b200 import _lib
+    B, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(B * 100 + W)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn(B, H, W, Cout, generator=g)
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), 1, 1).permute(0, 2, 3, 1)
+    ref = torch.relu(ref + res.double()).float()
+    monkeypatch.setenv("SS2_CONV_TEST_SPLIT", "1")
+    ran = 0
+    for plan in ["", "1,1", "1,2", "2,1", "2,2", "3,1", "3,2", "4,1", "4,2"]:
+        if plan:
+            monkeypatch.setenv("SS2_DC_PLAN", plan)
+        else:
+            monkeypatch.delenv("SS2_DC_PLAN", raising=False)
+        try:
+            out = _lib.conv_nhwc(x.cuda(), w, b, stride=1, pad=1, relu=True, residual=res.cuda(), use_tc=True).cpu()
+        except Exception as exc:       # a plan that does not fit shared memory / TMEM for this layer is refused, not mis-run
+            assert plan and "conv_dc" in str(exc), (plan, exc)
+            continue
+        ran += 1
+        err = (out - ref).abs().max().item()
+        assert err < 3e-4, (plan, err)
+    assert ran >= 5
+
+
 @pytest.mark.parametrize("B,H", [(1, 8), (2, 44), (3, 360), (33, 360)])
 def test_stem_pool_direct_vs_torch(B, H):
     """the fused direct stem kernel (conv 7x7 s2 + bias + ReLU + max-pool 3x3 s2 in one tcgen05 kernel) against a plain
