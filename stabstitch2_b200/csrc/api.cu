@@ -130,6 +130,8 @@ int ss2_create(int device, ss2_ctx** out) {
   if (env) c->tc_passes = atoi(env) == 1 ? 1 : 3;
   env = getenv("SS2_TC_STEM");
   if (env) c->use_tc_stem = atoi(env);
+  env = getenv("SS2_SIDE_STREAM");
+  if (env) c->use_side = atoi(env);
   env = getenv("SS2_CONV_DC");
   if (env) c->use_dc = atoi(env);
   *out = c;
@@ -143,6 +145,9 @@ void ss2_destroy(ss2_ctx* ctx) {
   ss2_host_slots_free(ctx);
   if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
   if (ctx->ws_ev) cudaEventDestroy(ctx->ws_ev);
+  if (ctx->s_side) cudaStreamDestroy(ctx->s_side);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (void* p : ctx->owned) cudaFree(p);
   for (auto& v : ctx->owned_net) for (void* p : v) cudaFree(p);
   if (ctx->arena.base) cudaFree(ctx->arena.base);

@@ -129,6 +129,10 @@ struct ss2_ctx {
   cudaStream_t ws_stream = nullptr;
   bool ws_used = false;
   cudaEvent_t ws_ev = nullptr;
+  // side stream of independent network branches (SpatialNet's two mesh regressors): fork / join events (nets.cu)
+  cudaStream_t s_side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int use_side = 1;     // SS2_SIDE_STREAM=0: everything on the caller's stream
   void* host_slots = nullptr;  // HostSlot[HOST_SLOTS] of the host-buffer pipeline (stream.cu), created on first use
   int use_tc = 1;  // tcgen05 implicit-GEMM path for eligible layers
   bool lag_tables_ready = false;

@@ -440,6 +440,24 @@ static int spatial_chunk(ss2_ctx* ctx, const float* img1, const float* img2, int
   ARENA_ACT(cv_tgt, half);
   SS2_TRY(cost_volume_launch(ctx, warped, warped + half, bs, h64, w64, 128, 5, 128, cv_ref, st));
   SS2_TRY(cost_volume_launch(ctx, warped + half, warped, bs, h64, w64, 128, 5, 128, cv_tgt, st));
+  // The two mesh regressors are independent stacks of ~20 small launches each (a few dozen CTAs for 148 SMs, bound by
+  // the length of one CTA's K loop): the target branch runs on a side stream next to the reference branch.  Their
+  // workspace comes from the same arena (distinct regions); the caller's stream waits for the side stream before
+  // anything else is enqueued, so the next arena reset is ordered after both.
+  if (ctx->use_side && !ctx->prof[SS2_PROF_CONV].enabled) {
+    if (!ctx->s_side) {
+      SS2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_side, cudaStreamNonBlocking));
+      SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    SS2_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    SS2_CUDA(ctx, cudaStreamWaitEvent(ctx->s_side, ctx->ev_fork, 0));
+    int rc = run_regressor(ctx, S.r2_ref, cv_ref, bs, h64, w64, oref, st);
+    if (rc == SS2_OK) rc = run_regressor(ctx, S.r2_tgt, cv_tgt, bs, h64, w64, otgt, ctx->s_side);
+    SS2_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->s_side));   // also after a failure: never leave the side stream detached
+    SS2_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    return rc;
+  }
   SS2_TRY(run_regressor(ctx, S.r2_ref, cv_ref, bs, h64, w64, oref, st));
   SS2_TRY(run_regressor(ctx, S.r2_tgt, cv_tgt, bs, h64, w64, otgt, st));
   return SS2_OK;
