@@ -149,6 +149,10 @@ int ss2_spatial_tail(ss2_ctx* ctx, const float* d_offset1, const float* d_offset
 /* build_TemporalNet, temporal_network.py:23: frames [n,3,360,480] (consecutive frames of one
  * view) -> motions [n,7,9,2]; motions[0] = 0, motions[k] = motion of frame k w.r.t. k-1 */
 int ss2_build_temporal(ss2_ctx* ctx, const float* d_frames, int n, float* d_motions, void* stream);
+/* Both views of a stream in one batch per chunk (the whole-stream calls use this): same results, bit for bit, as two
+ * ss2_build_temporal calls; frames_a/b [n,3,360,480] -> motions_a/b [n,7,9,2]. */
+int ss2_build_temporal_pair(ss2_ctx* ctx, const float* d_frames_a, const float* d_frames_b, int n, float* d_motions_a,
+                            float* d_motions_b, void* stream);
 /* tsmotion preparation, test_online_tra.py:309-347, one view: smotion,tmotion [n,7,9,2] ->
  * smesh, tsmotion [n,7,9,2].  `first_is_stream_start` != 0 makes tsmotion[0] = 0 (k == 0
  * branch); otherwise smotion_prev [7,9,2] (frame before the chunk) must be given. */

@@ -273,7 +273,14 @@ __global__ void linear_reduce_kernel(const float* __restrict__ part, const float
 
 static bool linear_smallm_try(ss2_ctx* ctx, const ConvLayer& L, const float* x, int M, float* out, int relu, cudaStream_t st) {
   const int K = L.CinP;
-  if (M > 32) return false;
+  if (M > 128) return false;
+  if (M > 32) {
+    // row blocks of 32 through the same kernel: a row's arithmetic (and so its bits) does not depend on how many rows
+    // the call has (the two-view TemporalNet batch against the per-view calls of a temporal shard)
+    for (int m0 = 0; m0 < M; m0 += 32)
+      if (!linear_smallm_try(ctx, L, x + (size_t)m0 * K, M - m0 < 32 ? M - m0 : 32, out + (size_t)m0 * L.Cout, relu, st)) return false;
+    return true;
+  }
   // few output-column CTAs (Cout / 32): split K so that the weight matrix streams through ~one wave of CTAs
   const int ncol = L.CoutP / 32;
   int nsplit = 1;

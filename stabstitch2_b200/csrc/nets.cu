@@ -463,8 +463,12 @@ static int spatial_chunk(ss2_ctx* ctx, const float* img1, const float* img2, int
   return SS2_OK;
 }
 
-#define SPATIAL_CHUNK 16
-#define TEMPORAL_CHUNK 32
+// frames per launch train (SS2_SPATIAL_CHUNK / SS2_TEMPORAL_CHUNK override them for sweeps)
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e && atoi(e) > 0 ? atoi(e) : dflt; }
+// (measured, 32-pair step: 8 pairs per chunk 12.86 ms, 16 -> 11.30 ms, 32 -> 10.66 ms: the regressor stacks behind the
+// backbone are a few dozen CTAs per launch, so their cost is per chunk, not per frame)
+#define SPATIAL_CHUNK env_int("SS2_SPATIAL_CHUNK", 32)
+#define TEMPORAL_CHUNK env_int("SS2_TEMPORAL_CHUNK", 32)
 #define SMOOTH_CHUNK 256
 
 extern "C" int ss2_spatial_forward(ss2_ctx* ctx, const float* d_img1, const float* d_img2, int bs,
@@ -540,6 +544,54 @@ extern "C" int ss2_build_temporal(ss2_ctx* ctx, const float* d_frames, int n, fl
     ARENA_ACT(cv, (size_t)nm * h64 * w64 * 64);
     SS2_TRY(cost_volume_launch(ctx, f64, f64 + (size_t)h64 * w64 * 128, nm, h64, w64, 128, 3, 64, cv, st));
     SS2_TRY(run_regressor(ctx, T.r2, cv, nm, h64, w64, d_motions + (size_t)f0 * 126, st));
+  }
+  return SS2_OK;
+}
+
+// Both views of a stream through TemporalNet as ONE batch per chunk ([view a frames | view b frames] through the shared
+// backbone, one regressor pass over both views' cost volumes): the regressor stack is a train of ~20 launches of a
+// few dozen CTAs each, so its cost is per launch train, not per frame.  Results are bit-identical to two
+// ss2_build_temporal calls (every kernel's per-image / per-row arithmetic is independent of the batch).
+extern "C" int ss2_build_temporal_pair(ss2_ctx* ctx, const float* d_frames_a, const float* d_frames_b, int n,
+                                       float* d_motions_a, float* d_motions_b, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (!ctx->temporal.ready) return ss2_fail(ctx, SS2_ERR_NO_WEIGHTS, "TemporalNet weights not finalized");
+  if (n < 0 || (n > 0 && (!d_frames_a || !d_frames_b || !d_motions_a || !d_motions_b)))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_build_temporal_pair: bad arguments");
+  if (n == 0) return SS2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const TemporalWeights& T = ctx->temporal;
+  const int H = NET_IMG_H, W = NET_IMG_W;
+  SS2_CUDA(ctx, cudaMemsetAsync(d_motions_a, 0, (size_t)126 * sizeof(float), st));
+  SS2_CUDA(ctx, cudaMemsetAsync(d_motions_b, 0, (size_t)126 * sizeof(float), st));
+  const int nmot = n - 1;
+  const int nchunks = nmot > 0 ? cdiv(nmot, TEMPORAL_CHUNK) : 0;
+  const int per = nchunks > 0 ? cdiv(nmot, nchunks) : 0;   // motions per view per chunk (balanced, see ss2_build_temporal)
+  SS2_TRY(ss2_workspace_enter(ctx, st));
+  SS2_TRY(ss2_ensure_arena(ctx, (size_t)2 * (per + 1) * (kBytesPerImageBackbone + kBytesPerPairHead) + ((size_t)64 << 20)));
+  const size_t ipx = (size_t)3 * H * W;
+  for (int f0 = 1; f0 < n; f0 += per) {
+    const int f1 = (f0 + per < n) ? f0 + per : n;   // motions f0..f1-1
+    const int nimg = f1 - f0 + 1, nm = nimg - 1;     // frames f0-1 .. f1-1 of each view
+    ctx->arena.reset();
+    ARENA(both, float, (size_t)2 * nimg * ipx);
+    SS2_CUDA(ctx, cudaMemcpyAsync(both, d_frames_a + (size_t)(f0 - 1) * ipx, (size_t)nimg * ipx * 4, cudaMemcpyDeviceToDevice, st));
+    SS2_CUDA(ctx, cudaMemcpyAsync(both + (size_t)nimg * ipx, d_frames_b + (size_t)(f0 - 1) * ipx, (size_t)nimg * ipx * 4,
+                                  cudaMemcpyDeviceToDevice, st));
+    float *f64, *f32 = nullptr;
+    int h64, w64, h32, w32;
+    SS2_TRY(run_backbone(ctx, T.bb, both, 2 * nimg, H, W, false, &f64, &h64, &w64, &f32, &h32, &w32, st));
+    const size_t fpx = (size_t)h64 * w64 * 128, cpx = (size_t)h64 * w64 * 64;
+    ARENA_ACT(cv, (size_t)2 * nm * cpx);
+    ActRef cvb = cv;   // second view's half of the cost-volume batch
+    cvb.v += (size_t)nm * cpx;
+    if (cvb.hi) { cvb.hi += (size_t)nm * cpx; cvb.lo += (size_t)nm * cpx; }
+    SS2_TRY(cost_volume_launch(ctx, f64, f64 + fpx, nm, h64, w64, 128, 3, 64, cv, st));
+    SS2_TRY(cost_volume_launch(ctx, f64 + (size_t)nimg * fpx, f64 + (size_t)(nimg + 1) * fpx, nm, h64, w64, 128, 3, 64, cvb, st));
+    ARENA(mot, float, (size_t)2 * nm * 126);
+    SS2_TRY(run_regressor(ctx, T.r2, cv, 2 * nm, h64, w64, mot, st));
+    SS2_CUDA(ctx, cudaMemcpyAsync(d_motions_a + (size_t)f0 * 126, mot, (size_t)nm * 126 * 4, cudaMemcpyDeviceToDevice, st));
+    SS2_CUDA(ctx, cudaMemcpyAsync(d_motions_b + (size_t)f0 * 126, mot + (size_t)nm * 126, (size_t)nm * 126 * 4, cudaMemcpyDeviceToDevice, st));
   }
   return SS2_OK;
 }

@@ -480,10 +480,10 @@ def stream_meshes_sharded(spatial_net, temporal_net, smooth_net, lr1, lr2, input
     raw = torch.empty(4, F, 7, 9, 2, device=dev, dtype=torch.float32)
     sp = build_SpatialNet(spatial_net, lr1[input_halo:], lr2[input_halo:])
     raw[0], raw[1] = sp["motion1"], sp["motion2"]
-    for v, lr in enumerate((lr1, lr2)):
-        tm = torch.empty(F + input_halo, 7, 9, 2, device=dev, dtype=torch.float32)
-        ctx.check(ctx.lib.ss2_build_temporal(ctx.handle, _lib.ptr(lr), F + input_halo, _lib.ptr(tm), st))
-        raw[2 + v] = tm[input_halo:]
+    tms = [torch.empty(F + input_halo, 7, 9, 2, device=dev, dtype=torch.float32) for _ in range(2)]
+    ctx.check(ctx.lib.ss2_build_temporal_pair(ctx.handle, _lib.ptr(lr1), _lib.ptr(lr2), F + input_halo, _lib.ptr(tms[0]),
+                                              _lib.ptr(tms[1]), st))
+    raw[2], raw[3] = tms[0][input_halo:], tms[1][input_halo:]
     allraw = exchange_raw_meshes(raw, group)  # [4, world*F, 7,9,2]
     c0, stop = plan["ctx0"], plan["stop"]
     n = stop - c0

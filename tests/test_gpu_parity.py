@@ -202,6 +202,23 @@ def test_temporal_golden(nets, stream_inputs, golden_stream):
         assert e < MESH_TOL_PX
 
 
+def test_temporal_pair_bit_identical_to_per_view(nets, stream_inputs):
+    """ss2_build_temporal_pair (both views as one batch: what the whole-stream calls use) == two ss2_build_temporal
+    calls, bit for bit - the property the sharded stream relies on (batch composition never changes a frame's bits)"""
+    from stabstitch2_b200 import _lib
+    from stabstitch2_b200.temporal_network import build_TemporalNet
+    _, t, _ = nets
+    _, lr = stream_inputs
+    per_view = [torch.cat(build_TemporalNet(t, lr[v])["motion_list"], 0) for v in range(2)]
+    ctx = _lib.context()
+    a, b = torch.cat(lr[0], 0).cuda(), torch.cat(lr[1], 0).cuda()
+    n = a.shape[0]
+    ma, mb = torch.empty(n, 7, 9, 2, device="cuda"), torch.empty(n, 7, 9, 2, device="cuda")
+    ctx.check(ctx.lib.ss2_build_temporal_pair(ctx.handle, _lib.ptr(a), _lib.ptr(b), n, _lib.ptr(ma), _lib.ptr(mb), _lib.cur_stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(ma.cpu(), per_view[0].cpu()) and torch.equal(mb.cpu(), per_view[1].cpu())
+
+
 def test_smooth_window_golden(nets, golden_stream):
     from stabstitch2_b200.smooth_network import build_SmoothNet
     _, _, m = nets
