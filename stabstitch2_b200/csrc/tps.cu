@@ -20,21 +20,34 @@
 // gives the same fp32-rounded coefficients (fp64 noise is ~1e-9 of an fp32 ulp here).
 //
 // Latency-oriented (64 systems per 32-frame chunk: the chip is never full, so the time is the
-// length of one system's dependency chain on ONE SM).  The augmented matrix [W | tp] (66 x 68)
-// lives in REGISTERS: SOLVE_NW warps x 32 lanes, thread (w, l) owns rows w + SOLVE_NW i and columns
-// l + 32 j (j < 3).  Per pivot step only the pivot row (68 values) and the pivot column's
-// multipliers (66 values) travel through shared memory; rows are never swapped (the pivot row of
-// step k is remembered) and the search for the next pivot is folded into the elimination: the lane
-// that owns column k+1 offers |value| (top 25 bits) and its row to a shared atomicMax.
-// Round 1's kernel kept the matrix in shared memory (3 barriers, a single-warp search, a physical
-// swap and ~4400 warp instructions per step: 97 us for 64 systems).
+// length of one system's dependency chain on ONE SM: 66 pivot steps).  The augmented matrix
+// [W | tp] (66 x 68) lives in REGISTERS, rows across LANES and columns across WARPS: thread (w, l)
+// owns rows l + 32 i (i < 3) and columns w + NW j (NW = 8 warps: j < 9).  With that layout
+//   * the pivot row's elements a warp needs are its OWN columns of row p: one shuffle from lane
+//     p % 32, nothing travels between warps;
+//   * column k+1 (the multipliers of the next step and the candidates of its pivot search) sits
+//     in ONE warp, all 66 rows: that warp alone eliminates that column first, searches (redux.sync
+//     max over a monotone key, the reciprocal of every lane's own best candidate computed while the
+//     reduction is in flight), publishes pivot index, reciprocal and the column through shared
+//     memory and raises a step counter; only then it updates its other columns;
+//   * there is NO barrier in the loop: the other warps spin on the step counter (a ring of 32
+//     published columns; a warp publishes every 16th column, so no warp is ever more than 16 steps
+//     behind the writer and a ring slot is never overwritten while it can still be read).
+// The chain per step is therefore: counter visible -> 3 shared loads -> shuffle -> 3 DFMA -> keys ->
+// redux || reciprocal -> stores -> counter.  Rows are never swapped (the pivot row of step k is
+// remembered); columns <= k are dead and their slots are skipped.
+// History (64 systems): matrix in shared memory 97 us; registers with rows across warps, an
+// atomicMax search in every warp and two barriers per step 53 us; rows across lanes with one barrier
+// per step 35 us; this form: see DESIGN.md.
+// A 17th warp computes the affine predictor of the lattice resampler and leaves.
 // ------------------------------------------------------------------------------------------
 #ifndef SOLVE_NW
-#define SOLVE_NW 16    // warps per system (measured per 64 systems: 8 warps 90 us, 16 warps 56 us)
+#define SOLVE_NW 8                       // solver warps per system = column stride
 #endif
-#define SOLVE_THREADS (SOLVE_NW * 32)
-#define SOLVE_ROWS ((SS2_NSYS + SOLVE_NW - 1) / SOLVE_NW)   // rows per thread: w, w+NW, ..
-#define SOLVE_COLS 3   // columns per thread: l, l+32, l+64
+#define SOLVE_THREADS (SOLVE_NW * 32 + 32)
+#define SOLVE_RS 3                       // row slots per thread: lane, lane + 32, lane + 64
+#define SOLVE_CS ((SS2_NSYS + 2 + SOLVE_NW - 1) / SOLVE_NW)   // column slots per thread: warp + SOLVE_NW j
+#define SOLVE_RING 32                    // >= 2 SOLVE_NW
 #define AUG (SS2_NSYS + 2)
 
 __device__ __forceinline__ unsigned solve_key(double v, int row) {
@@ -43,68 +56,75 @@ __device__ __forceinline__ unsigned solve_key(double v, int row) {
   return ((hi >> 6) << 7) | (unsigned)row;
 }
 
+__device__ __forceinline__ void solve_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SOLVE_NW * 32) : "memory"); }
+
+// 1 / x to fp64 rounding noise: MUFU.RCP64H (2^-23) + two Newton steps, a chain of one MUFU and four DFMAs
+// (the IEEE-exact __drcp_rn adds fix-up code to a chain that sits on the critical path of every pivot step)
+__device__ __forceinline__ double solve_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+struct SolveShared {
+  double colk[SOLVE_RING][AUG];   // published columns (the multipliers of step k = column k of every row), ring by k % 32
+  double pinv[SS2_NSYS];          // 1 / pivot of step k
+  double rhs[SS2_NSYS][2];
+  int perm[SS2_NSYS];             // pivot row of step k
+  int ready;                      // columns 0..ready are published
+  float sx[SS2_NPT_PAD], sy[SS2_NPT_PAD];
+};
+
+// Executed by the warp that owns column cn (values v[i] of rows lane + 32 i, already eliminated up to
+// step cn - 1): pick the pivot of step cn among the rows not used yet and publish the column (= the multipliers of
+// step cn, with a zero in the pivot row, which is not eliminated), the pivot row and the reciprocal pivot.
+__device__ __forceinline__ void solve_search(const double v0, const double v1, const double v2, unsigned used, int lane, int cn,
+                                             SolveShared& sh) {
+  const unsigned k0 = (used & 1u) ? 0u : solve_key(v0, lane);
+  const unsigned k1 = (used & 2u) ? 0u : solve_key(v1, lane + 32);
+  const unsigned k2 = (lane + 64 < SS2_NSYS && !(used & 4u)) ? solve_key(v2, lane + 64) : 0u;
+  const unsigned mine = max(k0, max(k1, k2));
+  const unsigned best = __reduce_max_sync(0xffffffffu, mine);
+  // every lane inverts its own best candidate while the reduction is in flight; the winner publishes
+  const double inv = solve_rcp(mine == k0 ? v0 : (mine == k1 ? v1 : v2));
+  double* col = sh.colk[cn & (SOLVE_RING - 1)];
+  col[lane] = (k0 == best && best != 0u) ? 0.0 : v0;
+  col[lane + 32] = (k1 == best && best != 0u) ? 0.0 : v1;
+  if (lane + 64 < SS2_NSYS) col[lane + 64] = (k2 == best && best != 0u) ? 0.0 : v2;
+  if (mine == best && (best != 0u || lane == 0)) {
+    sh.perm[cn] = (int)(best & 127u);
+    sh.pinv[cn] = inv;
+  }
+  __syncwarp();
+  __threadfence_block();
+  if (lane == 0) *(volatile int*)&sh.ready = cn;
+}
+
 __global__ void __launch_bounds__(SOLVE_THREADS)
 tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ target, float* __restrict__ Tout,
                  float* __restrict__ aux, float half_w, float half_h, float kx, float ky) {
-  __shared__ float sx[SS2_NPT], sy[SS2_NPT];
-  __shared__ double pivrow[2][AUG + 2];      // the pivot row of the step (double-buffered by step parity)
-  __shared__ double colk[2][SS2_NSYS + 2];   // column k of every row, published one step ahead
-  __shared__ double pinv[SS2_NSYS];          // 1 / pivot of step k
-  __shared__ double rhs[SS2_NSYS][2];
-  __shared__ unsigned pkey[3];               // step k reads [k%3], offers candidates to [(k+1)%3], clears [(k+2)%3]
-  __shared__ int perm[SS2_NSYS];
+  __shared__ SolveShared sh;
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const float* src = source + (size_t)b * SS2_NPT * 2;
   const float* tgt = target + (size_t)b * SS2_NPT * 2;
   if (tid < SS2_NPT) {
-    sx[tid] = src[2 * tid];
-    sy[tid] = src[2 * tid + 1];
+    sh.sx[tid] = src[2 * tid];
+    sh.sy[tid] = src[2 * tid + 1];
   }
-  if (tid < 3) pkey[tid] = 0u;
+  if (tid == 0) sh.ready = -1;
   __syncthreads();
-  // assemble this thread's elements of [W | tp] (fp32 arithmetic for K exactly like the reference, then widened)
-  double a[SOLVE_ROWS][SOLVE_COLS];
-#pragma unroll
-  for (int i = 0; i < SOLVE_ROWS; ++i) {
-    const int r = wid + SOLVE_NW * i;
-#pragma unroll
-    for (int j = 0; j < SOLVE_COLS; ++j) {
-      const int c = lane + 32 * j;
-      double v = 0.0;
-      if (r < SS2_NSYS && c < AUG) {
-        if (r < SS2_NPT) {
-          if (c == 0) v = 1.0;
-          else if (c == 1) v = (double)sx[r];
-          else if (c == 2) v = (double)sy[r];
-          else if (c < SS2_NSYS) {
-            const int q = c - 3;
-            const float dx = __fsub_rn(sx[r], sx[q]);
-            const float dy = __fsub_rn(sy[r], sy[q]);
-            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-            v = (double)__fmul_rn(d2, logf(__fadd_rn(d2, 1e-6f)));
-          } else {
-            v = (double)tgt[2 * r + (c - SS2_NSYS)];
-          }
-        } else if (c >= 3 && c < SS2_NSYS) {
-          const int q = r - SS2_NPT, pt = c - 3;  // 0: ones, 1: x, 2: y
-          v = q == 0 ? 1.0 : (q == 1 ? (double)sx[pt] : (double)sy[pt]);
-        }
-      }
-      a[i][j] = v;
-    }
-    if (lane == 0 && r < SS2_NSYS) {  // column 0: candidates of the first pivot, and the first published column
-      colk[0][r] = a[i][0];
-      atomicMax(&pkey[0], solve_key(a[i][0], r));
-    }
-  }
-  // Affine predictor for the lattice resampler: least-squares fit target ~ a*sx + b*sy + c over
-  // the 63 control points, expressed in source PIXEL units as a function of the canvas pixel
-  // index (col,row): px = aux[0]*col + aux[1]*row + aux[2], py = aux[3]*col + aux[4]*row + aux[5].
-  // Interpolation reproduces affine functions exactly, so any affine predictor is
-  // mathematically neutral; it only keeps the interpolated residuals small (fp32 rounding).
-  // One warp, partial sums per lane in control-point order, fixed shuffle tree (deterministic).
-  if (aux && wid == SOLVE_THREADS / 32 - 1) {
+  if (wid == SOLVE_NW) {
+    // Affine predictor for the lattice resampler: least-squares fit target ~ a*sx + b*sy + c over
+    // the 63 control points, expressed in source PIXEL units as a function of the canvas pixel
+    // index (col,row): px = aux[0]*col + aux[1]*row + aux[2], py = aux[3]*col + aux[4]*row + aux[5].
+    // Interpolation reproduces affine functions exactly, so any affine predictor is
+    // mathematically neutral; it only keeps the interpolated residuals small (fp32 rounding).
+    // Partial sums per lane in control-point order, fixed shuffle tree (deterministic).
+    if (!aux) return;
     double S[12];
 #pragma unroll
     for (int q = 0; q < 12; ++q) S[q] = 0.0;
@@ -143,73 +163,88 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
       o[5] = (float)(half_h * (sol[1][2] + 1.0 - sol[1][0] - sol[1][1]));
       o[6] = 0.f; o[7] = 0.f;
     }
+    return;
   }
-  unsigned used = 0u;  // bit i: this thread's row i has been a pivot row
-  __syncthreads();
-  for (int k = 0; k < SS2_NSYS; ++k) {
-    const int pb = k & 1;
-    const int p = (int)(pkey[k % 3] & 127u);
-    // the warp that owns row p publishes it NORMALISED by the pivot (one fp64 division per step, in that warp only)
-    if ((p % SOLVE_NW) == wid) {
-      const int ip = p / SOLVE_NW;
-      double mine[SOLVE_COLS];
+  // assemble this thread's elements of [W | tp] (fp32 arithmetic for K exactly like the reference, then widened)
+  double a[SOLVE_RS][SOLVE_CS];
 #pragma unroll
-      for (int j = 0; j < SOLVE_COLS; ++j) {
-        mine[j] = a[0][j];
+  for (int i = 0; i < SOLVE_RS; ++i) {
+    const int r = lane + 32 * i;
 #pragma unroll
-        for (int i = 1; i < SOLVE_ROWS; ++i)
-          if (i == ip) mine[j] = a[i][j];
+    for (int j = 0; j < SOLVE_CS; ++j) {
+      const int c = wid + SOLVE_NW * j;
+      double v = 0.0;
+      if (r < SS2_NSYS && c < AUG) {
+        if (r < SS2_NPT) {
+          if (c == 0) v = 1.0;
+          else if (c == 1) v = (double)sh.sx[r];
+          else if (c == 2) v = (double)sh.sy[r];
+          else if (c < SS2_NSYS) {
+            const int q = c - 3;
+            const float dx = __fsub_rn(sh.sx[r], sh.sx[q]);
+            const float dy = __fsub_rn(sh.sy[r], sh.sy[q]);
+            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            v = (double)__fmul_rn(d2, logf(__fadd_rn(d2, 1e-6f)));
+          } else {
+            v = (double)tgt[2 * r + (c - SS2_NSYS)];
+          }
+        } else if (c >= 3 && c < SS2_NSYS) {
+          const int q = r - SS2_NPT, pt = c - 3;  // 0: ones, 1: x, 2: y
+          v = q == 0 ? 1.0 : (q == 1 ? (double)sh.sx[pt] : (double)sh.sy[pt]);
+        }
       }
-      // pivot = column k of row p: lane k % 32, column group k / 32
-      const double cand_piv = (k >> 5) == 0 ? mine[0] : ((k >> 5) == 1 ? mine[1] : mine[2]);
-      const double inv = __drcp_rn(__shfl_sync(0xffffffffu, cand_piv, k & 31));
-#pragma unroll
-      for (int j = 0; j < SOLVE_COLS; ++j)
-        if (lane + 32 * j < AUG) pivrow[pb][lane + 32 * j] = mine[j] * inv;
-      if (lane == 0) pinv[k] = inv;
-      used |= 1u << ip;
-    }
-    if (tid == 0) {
-      perm[k] = p;
-      pkey[(k + 2) % 3] = 0u;  // last read in step k-1 (before the previous barrier), next written in step k+1
-    }
-    __syncthreads();
-    double pr[SOLVE_COLS];
-#pragma unroll
-    for (int j = 0; j < SOLVE_COLS; ++j) pr[j] = (lane + 32 * j < AUG) ? pivrow[pb][lane + 32 * j] : 0.0;
-    // eliminate column k from every other row; columns <= k are updated too (they are never read again), and the
-    // padding rows (>= 66) ride along with a zero multiplier: no per-row branches.  The lane that owns column k+1
-    // publishes it for the next step and offers its best unused row as the next pivot (one atomic per warp).
-    const int cn = k + 1;
-    const bool own_next = (cn & 31) == lane && cn < SS2_NSYS;
-    unsigned best = 0u;
-#pragma unroll
-    for (int i = 0; i < SOLVE_ROWS; ++i) {
-      const int r = wid + SOLVE_NW * i;
-      const bool real = r < SS2_NSYS;
-      const double f = (r == p || !real) ? 0.0 : colk[pb][real ? r : 0];   // the published pivot row is already divided by the pivot
-#pragma unroll
-      for (int j = 0; j < SOLVE_COLS; ++j) a[i][j] = fma(-f, pr[j], a[i][j]);
-      const double v = (cn >> 5) == 0 ? a[i][0] : ((cn >> 5) == 1 ? a[i][1] : a[i][2]);
-      if (own_next && real) colk[pb ^ 1][r] = v;
-      const unsigned key = (real && !((used >> i) & 1u)) ? solve_key(v, r) : 0u;
-      best = key > best ? key : best;
-    }
-    if (own_next && best != 0u) atomicMax(&pkey[cn % 3], best);
-    __syncthreads();
-  }
-  // right-hand sides (columns 66, 67 = lane 2, 3 of the third column group) of every row
-  if (lane == 2 || lane == 3) {
-#pragma unroll
-    for (int i = 0; i < SOLVE_ROWS; ++i) {
-      const int r = wid + SOLVE_NW * i;
-      if (r < SS2_NSYS) rhs[r][lane - 2] = a[i][2];
+      a[i][j] = v;
     }
   }
-  __syncthreads();
-  for (int e = tid; e < 2 * SS2_NSYS; e += SOLVE_THREADS) {
+  unsigned used = 0u;  // bit i: this lane's row lane + 32 i has been a pivot row (the same in every warp)
+  if (wid == 0) solve_search(a[0][0], a[1][0], a[2][0], used, lane, 0, sh);
+  // Step k eliminates column k; the warp that owns column cn = k + 1 (warp cn % NW, slot cn / NW) searches next.
+  // Phase jn = cn / NW is unrolled: within it the slots below jn are dead (columns <= k are never read again), the slots
+  // above are live, slot jn is live in the warps >= cn % NW: one dynamic predicate per step and no work on dead columns.
+  // pr = the pivot row's element of this column (row p = lane pl, row slot PS: the slot is resolved ONCE per step by
+  // the three-way branch below, the per-warp instruction stream being what bounds a step)
+#define SOLVE_ELIM(J, PS)                                                                     \
+    {                                                                                         \
+      const double pr = __shfl_sync(0xffffffffu, a[PS][J], pl);                               \
+      a[0][J] = fma(-g0, pr, a[0][J]); a[1][J] = fma(-g1, pr, a[1][J]); a[2][J] = fma(-g2, pr, a[2][J]); \
+    }
+#define SOLVE_STEP(PS)                                                                        \
+    {                                                                                         \
+      if (wid >= kk) SOLVE_ELIM(jn, PS)                                                       \
+      if (wid == kk && cn < SS2_NSYS) solve_search(a[0][jn], a[1][jn], a[2][jn], used, lane, cn, sh); \
+      _Pragma("unroll") for (int j = jn + 1; j < SOLVE_CS; ++j) SOLVE_ELIM(j, PS)             \
+    }
+#pragma unroll
+  for (int jn = 0; jn < SOLVE_CS; ++jn) {
+    const int kk1 = SS2_NSYS + 1 - jn * SOLVE_NW < SOLVE_NW ? SS2_NSYS + 1 - jn * SOLVE_NW : SOLVE_NW;   // cn <= 66
+#pragma unroll 1
+    for (int kk = (jn == 0 ? 1 : 0); kk < kk1; ++kk) {
+      const int cn = jn * SOLVE_NW + kk, k = cn - 1;
+      while (*(volatile int*)&sh.ready < k) {}
+      __threadfence_block();
+      const int p = *(volatile int*)&sh.perm[k];
+      const double inv = *(volatile double*)&sh.pinv[k];
+      const volatile double* col = sh.colk[k & (SOLVE_RING - 1)];
+      // multipliers of this lane's rows, already zero in the pivot row; padding rows ride along with zero
+      const double g0 = col[lane] * inv, g1 = col[lane + 32] * inv, g2 = lane + 64 < SS2_NSYS ? col[lane + 64] * inv : 0.0;
+      const int ps = p >> 5, pl = p & 31;
+      used |= (lane == pl ? 1u : 0u) << ps;   // the pivot row is not a candidate any more
+      if (ps == 0) SOLVE_STEP(0) else if (ps == 1) SOLVE_STEP(1) else SOLVE_STEP(2)
+    }
+  }
+#undef SOLVE_STEP
+#undef SOLVE_ELIM
+  // right-hand sides: columns 66, 67 (warps 66 % NW and 67 % NW, slot 66 / NW: the same slot, NW is a power of two >= 4)
+  if (wid == (SS2_NSYS & (SOLVE_NW - 1)) || wid == ((SS2_NSYS + 1) & (SOLVE_NW - 1))) {
+    const int c = wid - (SS2_NSYS & (SOLVE_NW - 1));
+#pragma unroll
+    for (int i = 0; i < SOLVE_RS; ++i)
+      if (lane + 32 * i < SS2_NSYS) sh.rhs[lane + 32 * i][c] = a[i][SS2_NSYS / SOLVE_NW];
+  }
+  solve_bar();
+  for (int e = tid; e < 2 * SS2_NSYS; e += SOLVE_NW * 32) {
     const int c = e / SS2_NSYS, j = e % SS2_NSYS;
-    Tout[(size_t)b * 2 * SS2_NSYS + c * SS2_NSYS + j] = (float)(rhs[perm[j]][c] * pinv[j]);
+    Tout[(size_t)b * 2 * SS2_NSYS + c * SS2_NSYS + j] = (float)(sh.rhs[sh.perm[j]][c] * sh.pinv[j]);
   }
 }
 
@@ -519,22 +554,78 @@ __device__ __forceinline__ float log_pos_normal(float x) {
   return fmaf((float)e, 0.693147182f, r);
 }
 
-// one thread per (node, view): grid (node blocks, V, frames); nodes [n][ny][nx][V] float2 (x, y)
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two lanes of work per issued instruction
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// log_pos_normal of both halves of a packed pair: the same operations in the same order on each half (bit-identical
+// to the scalar function), the polynomial through packed FMAs
+__device__ __forceinline__ u64 log_pos_normal2(u64 x) {
+  float x0, x1;
+  upk2(x, x0, x1);
+  const int i0 = __float_as_int(x0) - 0x3f2aaaab, i1 = __float_as_int(x1) - 0x3f2aaaab;
+  const int e0 = i0 >> 23, e1 = i1 >> 23;
+  const u64 f = fadd2(pk2(__int_as_float(__float_as_int(x0) - (e0 << 23)), __int_as_float(__float_as_int(x1) - (e1 << 23))), pk2(-1.0f, -1.0f));
+#define P2(c) pk2(c, c)
+  u64 q = P2(-0.13346314430236816f);
+  q = ffma2(q, f, P2(0.1415630429983139f));
+  q = ffma2(q, f, P2(-0.1207403615117073f));
+  q = ffma2(q, f, P2(0.13967302441596985f));
+  q = ffma2(q, f, P2(-0.16688990592956543f));
+  q = ffma2(q, f, P2(0.20013076066970825f));
+  q = ffma2(q, f, P2(-0.24999591708183289f));
+  q = ffma2(q, f, P2(0.3333316147327423f));
+  const u64 f2 = fmul2(f, f);
+  u64 r = ffma2(q, fmul2(f2, f), fmul2(P2(-0.5f), f2));
+  r = fadd2(r, f);
+  return ffma2(pk2((float)e0, (float)e1), P2(0.693147182f), r);
+#undef P2
+}
+
+// one thread per (node, view): grid (node blocks, V, frames); nodes [n][ny][nx][V] float2 (x, y).
+// Two control points per iteration through packed fp32 (same operations per point, in control-point order, as the
+// scalar form: results are bit-identical to it); the 64th point is padding with zero weights.
 template <int V>
 __global__ void __launch_bounds__(128)
-tps_nodes_kernel(WarpParams P, int SX, int SY) {
-  __shared__ float2 cxy[SS2_NPT];
-  __shared__ double2 cw[SS2_NPT];
+tps_nodes_kernel(WarpParams P, int SX, int SY, double kxd, double kyd) {
+  __shared__ __align__(16) float4 cneg[SS2_NPT_PAD / 2];   // (-cx[2i], -cx[2i+1], -cy[2i], -cy[2i+1])
+  __shared__ __align__(16) double2 cw[SS2_NPT_PAD];        // (wx, wy)
   __shared__ double aff[6];
   __shared__ float pred[6];
   const int n = blockIdx.z, v = blockIdx.y, tid = threadIdx.x;
   const float* t = P.T + (size_t)(n * V + v) * 2 * SS2_NSYS;
-  if (tid < SS2_NPT) {
-    const float* s = P.source + ((size_t)(n * V + v) * SS2_NPT + tid) * 2;
-    cxy[tid] = make_float2(s[0], s[1]);
-    cw[tid] = make_double2((double)t[3 + tid], (double)t[SS2_NSYS + 3 + tid]);
-  } else if (tid < SS2_NPT + 6) {
-    const int k = tid - SS2_NPT;
+  if (tid < SS2_NPT_PAD) {
+    float* cn = reinterpret_cast<float*>(cneg) + (tid >> 1) * 4 + (tid & 1);
+    if (tid < SS2_NPT) {
+      const float* s = P.source + ((size_t)(n * V + v) * SS2_NPT + tid) * 2;
+      cn[0] = -s[0]; cn[2] = -s[1];
+      cw[tid] = make_double2((double)t[3 + tid], (double)t[SS2_NSYS + 3 + tid]);
+    } else {
+      cn[0] = -3.0f; cn[2] = -3.0f;   // outside the normalised canvas: d2 > 0, weight 0
+      cw[tid] = make_double2(0.0, 0.0);
+    }
+  } else if (tid < SS2_NPT_PAD + 6) {
+    const int k = tid - SS2_NPT_PAD;
     aff[k] = (double)t[(k / 3) * SS2_NSYS + (k % 3)];
     pred[k] = P.aux[(size_t)(n * V + v) * 8 + k];
   }
@@ -543,23 +634,30 @@ tps_nodes_kernel(WarpParams P, int SX, int SY) {
   if (node >= P.nx * P.ny) return;
   const int jy = node / P.nx, jx = node % P.nx;
   const int col = (jx - LAT_LO) * SX, row = (jy - LAT_LO) * SY;
-  const double xd = P.Wo > 1 ? -1.0 + 2.0 * (double)col / (double)(P.Wo - 1) : -1.0;
-  const double yd = P.Ho > 1 ? -1.0 + 2.0 * (double)row / (double)(P.Ho - 1) : -1.0;
+  // normalised canvas coordinate of the node; (kxd, kyd) = 2 / (Wo - 1), 2 / (Ho - 1) from the host (no fp64 division here)
+  const double xd = fma(kxd, (double)col, -1.0), yd = fma(kyd, (double)row, -1.0);
   const float xt = (float)xd, yt = (float)yd;
   double ax = aff[0] + aff[1] * xd + aff[2] * yd;
   double ay = aff[3] + aff[4] * xd + aff[5] * yd;
-#pragma unroll 9
-  for (int i = 0; i < SS2_NPT; ++i) {
-    const float2 c = cxy[i];
-    const float dx = xt - c.x, dy = yt - c.y;
-    const float d2 = fmaf(dy, dy, dx * dx);
+  const u64 xt2 = pk2(xt, xt), yt2 = pk2(yt, yt), eps2 = pk2(1e-6f, 1e-6f);
+  const u64 nR2 = pk2(-P.R2, -P.R2), p0 = pk2(P.p0, P.p0), p1 = pk2(P.p1, P.p1), p2 = pk2(P.p2, P.p2), p3 = pk2(P.p3, P.p3);
+#pragma unroll 4
+  for (int i = 0; i < SS2_NPT_PAD / 2; ++i) {
+    const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(&cneg[i]);
+    const u64 dx = fadd2(xt2, c.x), dy = fadd2(yt2, c.y);
+    const u64 d2 = ffma2(dy, dy, fmul2(dx, dx));
     // branch-free: both the far term d2 * log(d2 + 1e-6) and the blending cubic, then a select
-    const float fl = d2 * log_pos_normal(d2 + 1e-6f);
-    const float fp = blend_poly(d2, P.R2, P.p0, P.p1, P.p2, P.p3);
-    const float f = d2 >= P.R2 ? fl : fp;
-    const double2 w = cw[i];
-    ax = fma(w.x, (double)f, ax);
-    ay = fma(w.y, (double)f, ay);
+    const u64 fl = fmul2(d2, log_pos_normal2(fadd2(d2, eps2)));
+    const u64 u = fadd2(d2, nR2);
+    const u64 fp = ffma2(u, ffma2(u, ffma2(u, p3, p2), p1), p0);
+    float d20, d21, fl0, fl1, fp0, fp1;
+    upk2(d2, d20, d21); upk2(fl, fl0, fl1); upk2(fp, fp0, fp1);
+    const float f0 = d20 >= P.R2 ? fl0 : fp0, f1 = d21 >= P.R2 ? fl1 : fp1;
+    const double2 w0 = cw[2 * i], w1 = cw[2 * i + 1];
+    ax = fma(w0.x, (double)f0, ax);
+    ay = fma(w0.y, (double)f0, ay);
+    ax = fma(w1.x, (double)f1, ax);
+    ay = fma(w1.y, (double)f1, ay);
   }
   const double px = (ax + 1.0) * (double)P.half_w - ((double)pred[0] * col + (double)pred[1] * row + (double)pred[2]);
   const double py = (ay + 1.0) * (double)P.half_h - ((double)pred[3] * col + (double)pred[4] * row + (double)pred[5]);
@@ -595,29 +693,6 @@ __device__ __forceinline__ float blend_avg_fast(float a, float b) {
   return fmaf(b, b, a * a) * rcp_approx(s);
 }
 
-// packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two lanes of work per issued instruction
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk2(float lo, float hi) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
-  u64 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
-  u64 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
-  u64 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 // node-column slots a tile of LAT_THREADS pixel columns can touch
 template <int SX> struct LatCols { static constexpr int value = (LAT_THREADS + SX - 1) / SX + LAT_TAPS; };
 
@@ -628,6 +703,9 @@ template <int SX> struct LatCols { static constexpr int value = (LAT_THREADS + S
 #endif
 #ifndef LAT_RPI
 #define LAT_RPI 1  // canvas rows whose taps are in flight together (2-3 measured slower: registers)
+#endif
+#ifndef LAT_TPI
+#define LAT_TPI LAT_RPI  // canvas rows whose taps are in flight together (divides LAT_RPI)
 #endif
 #ifndef LAT_PREFETCH
 #define LAT_PREFETCH 2  // source rows ahead pulled towards L1 (0/undefined: off)
@@ -862,109 +940,113 @@ tps_warp_lattice_kernel(WarpParams P) {
           }
         }
       }
-      float res[LAT_RPI][V][C];
-      if (MODE == SS2_MODE_NORMAL) {
-        // Phase A: tap weights and addresses (branch-free; an out-of-image sample gets zero
-        // weights and reads the frame's first pixel).  Phase B: all loads back to back (a view no
-        // lane of the warp sees is skipped).  Phase C: the FMAs.
-        float wq[LAT_RPI][V][4];
-        const float* tp[LAT_RPI][V];
-        bool anyv[LAT_RPI][V];
+      // taps, blend and stores of LAT_TPI rows at a time (the coordinates above are computed for LAT_RPI rows at once)
 #pragma unroll
-        for (int i = 0; i < LAT_RPI; ++i) {
+      for (int ib = 0; ib < LAT_RPI; ib += LAT_TPI) {
+        float res[LAT_RPI][V][C];
+        if (MODE == SS2_MODE_NORMAL) {
+          // Phase A: tap weights and addresses (branch-free; an out-of-image sample gets zero
+          // weights and reads the frame's first pixel).  Phase B: all loads back to back (a view no
+          // lane of the warp sees is skipped).  Phase C: the FMAs.
+          float wq[LAT_RPI][V][4];
+          const float* tp[LAT_RPI][V];
+          bool anyv[LAT_RPI][V];
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
-            const int xi = __float2int_rd(px[i][v]), yi = __float2int_rd(py[i][v]);
-            const bool inb = (unsigned)xi < W1 && (unsigned)yi < H1;  // no tap is clamped: plain bilinear == _interpolate
-            const float fx0 = px[i][v] - (float)xi, fy = py[i][v] - (float)yi;
-            const float fx = inb ? fx0 : 0.0f, gx = inb ? 1.0f - fx0 : 0.0f, gy = 1.0f - fy;
-            wq[i][v][0] = gx * gy; wq[i][v][1] = gx * fy; wq[i][v][2] = fx * gy; wq[i][v][3] = fx * fy;
-            tp[i][v] = f32_at(imgv[v], inb ? (unsigned)(yi * W + xi) : 0u);
-            anyv[i][v] = __any_sync(0xffffffffu, inb);
+          for (int i = ib; i < ib + LAT_TPI; ++i) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const int xi = __float2int_rd(px[i][v]), yi = __float2int_rd(py[i][v]);
+              const bool inb = (unsigned)xi < W1 && (unsigned)yi < H1;  // no tap is clamped: plain bilinear == _interpolate
+              const float fx0 = px[i][v] - (float)xi, fy = py[i][v] - (float)yi;
+              const float fx = inb ? fx0 : 0.0f, gx = inb ? 1.0f - fx0 : 0.0f, gy = 1.0f - fy;
+              wq[i][v][0] = gx * gy; wq[i][v][1] = gx * fy; wq[i][v][2] = fx * gy; wq[i][v][3] = fx * fy;
+              tp[i][v] = f32_at(imgv[v], inb ? (unsigned)(yi * W + xi) : 0u);
+              anyv[i][v] = __any_sync(0xffffffffu, inb);
 #if LAT_PREFETCH > 0
-            // the next iteration samples (about) LAT_RPI source rows further down: pull them towards L1
-            if (i == LAT_RPI - 1 && anyv[i][v] && inb && (unsigned)(yi + LAT_PREFETCH) < H1) {
+              // the next iteration samples (about) LAT_TPI source rows further down: pull them towards L1
+              if (i == ib + LAT_TPI - 1 && anyv[i][v] && inb && (unsigned)(yi + LAT_PREFETCH) < H1) {
 #pragma unroll
-              for (int c = 0; c < C; ++c)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(f32_at(tp[i][v], c * iplane + LAT_PREFETCH * W)));
-            }
+                for (int c = 0; c < C; ++c)
+                  asm volatile("prefetch.global.L1 [%0];" ::"l"(f32_at(tp[i][v], c * iplane + LAT_PREFETCH * W)));
+              }
 #endif
+            }
           }
-        }
-        float tap[LAT_RPI][V][C][4];
+          float tap[LAT_RPI][V][C][4];
 #pragma unroll
-        for (int i = 0; i < LAT_RPI; ++i) {
+          for (int i = ib; i < ib + LAT_TPI; ++i) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
-            if (anyv[i][v]) {
+            for (int v = 0; v < V; ++v) {
+              if (anyv[i][v]) {
 #pragma unroll
-              for (int c = 0; c < C; ++c) {
-                if (IW > 0 && IH > 0 && (size_t)(C - 1) * IW * IH * 4 + (size_t)IW * 4 + 4 < (1u << 23)) {
-                  const float* p = tp[i][v] + c * (IW * IH);  // compile-time offsets off ONE pointer
-                  tap[i][v][c][0] = __ldg(p); tap[i][v][c][2] = __ldg(p + 1);
-                  tap[i][v][c][1] = __ldg(p + IW); tap[i][v][c][3] = __ldg(p + IW + 1);
-                } else {
-                  const float* p0 = c == 0 ? tp[i][v] : f32_at(tp[i][v], c * iplane);
-                  const float* p1 = f32_at(tp[i][v], c * iplane + W);
-                  tap[i][v][c][0] = __ldg(p0); tap[i][v][c][2] = __ldg(p0 + 1);
-                  tap[i][v][c][1] = __ldg(p1); tap[i][v][c][3] = __ldg(p1 + 1);
+                for (int c = 0; c < C; ++c) {
+                  if (IW > 0 && IH > 0 && (size_t)(C - 1) * IW * IH * 4 + (size_t)IW * 4 + 4 < (1u << 23)) {
+                    const float* p = tp[i][v] + c * (IW * IH);  // compile-time offsets off ONE pointer
+                    tap[i][v][c][0] = __ldg(p); tap[i][v][c][2] = __ldg(p + 1);
+                    tap[i][v][c][1] = __ldg(p + IW); tap[i][v][c][3] = __ldg(p + IW + 1);
+                  } else {
+                    const float* p0 = c == 0 ? tp[i][v] : f32_at(tp[i][v], c * iplane);
+                    const float* p1 = f32_at(tp[i][v], c * iplane + W);
+                    tap[i][v][c][0] = __ldg(p0); tap[i][v][c][2] = __ldg(p0 + 1);
+                    tap[i][v][c][1] = __ldg(p1); tap[i][v][c][3] = __ldg(p1 + 1);
+                  }
                 }
               }
             }
           }
+#pragma unroll
+          for (int i = ib; i < ib + LAT_TPI; ++i)
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                res[i][v][c] = 0.0f;
+                if (anyv[i][v]) {
+                  // (x0, x1) pairs of the upper and the lower source row through packed FMAs
+                  float lo, hi;
+                  upk2(ffma2(pk2(tap[i][v][c][1], tap[i][v][c][3]), pk2(wq[i][v][1], wq[i][v][3]),
+                             fmul2(pk2(tap[i][v][c][0], tap[i][v][c][2]), pk2(wq[i][v][0], wq[i][v][2]))), lo, hi);
+                  res[i][v][c] = lo + hi;
+                }
+              }
+        } else {
+#pragma unroll
+          for (int i = ib; i < ib + LAT_TPI; ++i)
+#pragma unroll
+            for (int v = 0; v < V; ++v) sample_fast<C>(imgv[v], H, W, px[i][v], py[i][v], res[i][v]);
         }
 #pragma unroll
-        for (int i = 0; i < LAT_RPI; ++i)
+        for (int i = ib; i < ib + LAT_TPI; ++i) {
+          const int row = row0 + r0 + i;
+          if (active && r0 + i < SY && row < P.Ho) {
+            const unsigned opix = (unsigned)(row * P.Wo + col);
+            if (BLEND && V > 2) {
+              // fuse(..fuse(fuse(1,2),3)..,V): the reference's sequential AVERAGE fusion (test_online_tra_threeview.py:489-490)
 #pragma unroll
-          for (int v = 0; v < V; ++v)
+              for (int c = 0; c < C; ++c) {
+                float f = blend_avg_fast(res[i][0][c], res[i][1][c]);
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-              res[i][v][c] = 0.0f;
-              if (anyv[i][v]) {
-                // (x0, x1) pairs of the upper and the lower source row through packed FMAs
-                float lo, hi;
-                upk2(ffma2(pk2(tap[i][v][c][1], tap[i][v][c][3]), pk2(wq[i][v][1], wq[i][v][3]),
-                           fmul2(pk2(tap[i][v][c][0], tap[i][v][c][2]), pk2(wq[i][v][0], wq[i][v][2]))), lo, hi);
-                res[i][v][c] = lo + hi;
+                for (int v = 2; v < V; ++v) f = blend_avg_fast(f, res[i][v][c]);
+                __stcs(const_cast<float*>(f32_at(outv[0], opix + c * oplane)), f);
               }
-            }
-      } else {
+            } else if (BLEND && C == 3) {
+              const u64 A = pk2(res[i][0][0], res[i][0][1]), B = pk2(res[i][V - 1][0], res[i][V - 1][1]);
+              float s0, s1, q0, q1;
+              upk2(fadd2(fadd2(A, B), pk2(1e-6f, 1e-6f)), s0, s1);
+              upk2(ffma2(B, B, fmul2(A, A)), q0, q1);
+              __stcs(const_cast<float*>(f32_at(outv[0], opix)), q0 * rcp_approx(s0));
+              __stcs(const_cast<float*>(f32_at(outv[0], opix + oplane)), q1 * rcp_approx(s1));
+              __stcs(const_cast<float*>(f32_at(outv[0], opix + 2 * oplane)), blend_avg_fast(res[i][0][2], res[i][V - 1][2]));
+            } else if (BLEND) {
 #pragma unroll
-        for (int i = 0; i < LAT_RPI; ++i)
+              for (int c = 0; c < C; ++c)
+                __stcs(const_cast<float*>(f32_at(outv[0], opix + c * oplane)), blend_avg_fast(res[i][0][c], res[i][V - 1][c]));
+            } else {
 #pragma unroll
-          for (int v = 0; v < V; ++v) sample_fast<C>(imgv[v], H, W, px[i][v], py[i][v], res[i][v]);
-      }
+              for (int v = 0; v < V; ++v) {
 #pragma unroll
-      for (int i = 0; i < LAT_RPI; ++i) {
-        const int row = row0 + r0 + i;
-        if (active && r0 + i < SY && row < P.Ho) {
-          const unsigned opix = (unsigned)(row * P.Wo + col);
-          if (BLEND && V > 2) {
-            // fuse(..fuse(fuse(1,2),3)..,V): the reference's sequential AVERAGE fusion (test_online_tra_threeview.py:489-490)
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-              float f = blend_avg_fast(res[i][0][c], res[i][1][c]);
-#pragma unroll
-              for (int v = 2; v < V; ++v) f = blend_avg_fast(f, res[i][v][c]);
-              __stcs(const_cast<float*>(f32_at(outv[0], opix + c * oplane)), f);
-            }
-          } else if (BLEND && C == 3) {
-            const u64 A = pk2(res[i][0][0], res[i][0][1]), B = pk2(res[i][V - 1][0], res[i][V - 1][1]);
-            float s0, s1, q0, q1;
-            upk2(fadd2(fadd2(A, B), pk2(1e-6f, 1e-6f)), s0, s1);
-            upk2(ffma2(B, B, fmul2(A, A)), q0, q1);
-            __stcs(const_cast<float*>(f32_at(outv[0], opix)), q0 * rcp_approx(s0));
-            __stcs(const_cast<float*>(f32_at(outv[0], opix + oplane)), q1 * rcp_approx(s1));
-            __stcs(const_cast<float*>(f32_at(outv[0], opix + 2 * oplane)), blend_avg_fast(res[i][0][2], res[i][V - 1][2]));
-          } else if (BLEND) {
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-              __stcs(const_cast<float*>(f32_at(outv[0], opix + c * oplane)), blend_avg_fast(res[i][0][c], res[i][V - 1][c]));
-          } else {
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-#pragma unroll
-              for (int c = 0; c < C; ++c) __stcs(const_cast<float*>(f32_at(outv[v], opix + c * oplane)), res[i][v][c]);
+                for (int c = 0; c < C; ++c) __stcs(const_cast<float*>(f32_at(outv[v], opix + c * oplane)), res[i][v][c]);
+              }
             }
           }
         }
@@ -1022,23 +1104,28 @@ size_t tps_lattice_workspace_floats(int bn, int Ho, int Wo) {
   return (size_t)bn * nx * ny * 2;
 }
 
+// blending cubic of phi(s) = s log(s + eps) at s = R2 (third-order Taylor polynomial), coefficients divided by `div`
+static void blend_cubic(double R2, double div, float* p) {
+  const double e = 1e-6, L = log(R2 + e);
+  p[0] = (float)(R2 * L / div);
+  p[1] = (float)((L + R2 / (R2 + e)) / div);
+  p[2] = (float)(0.5 * (1.0 / (R2 + e) + e / ((R2 + e) * (R2 + e))) / div);
+  p[3] = (float)((-1.0 / ((R2 + e) * (R2 + e)) - 2.0 * e / ((R2 + e) * (R2 + e) * (R2 + e))) / 6.0 / div);
+}
+
 template <int V, int C, bool BLEND>
 static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, float* d_nodes, cudaStream_t st) {
   const LatticeConfig cfg = lattice_config(P.Ho, P.Wo);
   P.nx = (P.Wo - 1) / cfg.SX + LAT_TAPS;
   P.ny = (P.Ho - 1) / cfg.SY + LAT_TAPS;
   P.nodes = reinterpret_cast<const float2*>(d_nodes);
-  const double R2 = (double)cfg.R * cfg.R, e = 1e-6, L = log(R2 + e);
+  const double R2 = (double)cfg.R * cfg.R;
   P.R2 = (float)R2;
-  P.p0 = (float)(R2 * L);
-  P.p1 = (float)(L + R2 / (R2 + e));
-  P.p2 = (float)(0.5 * (1.0 / (R2 + e) + e / ((R2 + e) * (R2 + e))));
-  P.p3 = (float)((-1.0 / ((R2 + e) * (R2 + e)) - 2.0 * e / ((R2 + e) * (R2 + e) * (R2 + e))) / 6.0);
-  const double ln2 = 0.69314718055994530942;
-  P.q0 = (float)(R2 * L / ln2);
-  P.q1 = (float)((L + R2 / (R2 + e)) / ln2);
-  P.q2 = (float)(0.5 * (1.0 / (R2 + e) + e / ((R2 + e) * (R2 + e))) / ln2);
-  P.q3 = (float)((-1.0 / ((R2 + e) * (R2 + e)) - 2.0 * e / ((R2 + e) * (R2 + e) * (R2 + e))) / 6.0 / ln2);
+  float pc[4];
+  blend_cubic(R2, 1.0, pc);
+  P.p0 = pc[0]; P.p1 = pc[1]; P.p2 = pc[2]; P.p3 = pc[3];
+  blend_cubic(R2, 0.69314718055994530942, pc);
+  P.q0 = pc[0]; P.q1 = pc[1]; P.q2 = pc[2]; P.q3 = pc[3];
   if (!ctx->lag_tables_ready) {
     // one-time upload of the interpolation weight tables of this context's device
     LagrangeTable t[4];
@@ -1047,8 +1134,8 @@ static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, flo
     SS2_CUDA(ctx, cudaMemcpyToSymbol(c_lag, t, sizeof(t)));
     ctx->lag_tables_ready = true;
   }
-  const int nnodes = P.nx * P.ny;
-  tps_nodes_kernel<V><<<dim3(cdiv(nnodes, 128), V, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY);
+  const double kxd = P.Wo > 1 ? 2.0 / (double)(P.Wo - 1) : 0.0, kyd = P.Ho > 1 ? 2.0 / (double)(P.Ho - 1) : 0.0;
+  tps_nodes_kernel<V><<<dim3(cdiv(P.nx * P.ny, 128), V, nframes), 128, 0, st>>>(P, cfg.SX, cfg.SY, kxd, kyd);
   SS2_LAUNCH_CHECK(ctx);
   dim3 grid(cdiv(P.Wo, LAT_THREADS), cdiv(P.Ho, cfg.SY * LAT_NCELL), nframes);
   // source-size specialisations of the production (fused, NORMAL) kernel: 720p and 1080p
