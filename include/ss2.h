@@ -183,6 +183,13 @@ int ss2_canvas_minmax(ss2_ctx* ctx, const float* d_mesh1, const float* d_mesh2, 
 int ss2_stable_frames(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, const float* d_mesh1,
                       const float* d_mesh2, int n, int H, int W, const float* h_minmax, int mode,
                       int tps, float* d_out, void* stream);
+/* The same with the driver's uint8 back end (frame.astype(uint8), test_online_tra.py:152,414) fused into the store of
+ * the resampler: out [n,Ho,Wo,3] uint8 (HWC like the reference's numpy frames), bit-identical to ss2_stable_frames +
+ * ss2_frames_to_u8; the fp32 canvas is never written.  Lattice resampler only: SS2_ERR_UNSUPPORTED for tps ==
+ * SS2_TPS_EXACT and for canvases too small for the lattice (use the two calls there). */
+int ss2_stable_frames_u8(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, const float* d_mesh1,
+                         const float* d_mesh2, int n, int H, int W, const float* h_minmax, int mode,
+                         int tps, uint8_t* d_out, void* stream);
 /* canvas size helper (host arithmetic identical to the kernels') */
 int ss2_canvas_size(const float* h_minmax, int* out_h, int* out_w);
 

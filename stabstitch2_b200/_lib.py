@@ -47,6 +47,7 @@ SIGNATURES = {
     "ss2_build_smooth": (_i, [_vp] + [_vp] * 4 + [_i, _i] + [_vp] * 8 + [_vp]),
     "ss2_canvas_minmax": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "ss2_stable_frames": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _fp, _i, _i, _vp, _vp]),
+    "ss2_stable_frames_u8": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _fp, _i, _i, _vp, _vp]),
     "ss2_three_view_meshes": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "ss2_three_view_frames": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _fp, _i, _i, _vp, _vp]),
     "ss2_canvas_size": (_i, [_fp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),

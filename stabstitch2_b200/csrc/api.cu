@@ -447,8 +447,9 @@ int ss2_canvas_size(const float* h_minmax, int* out_h, int* out_w) {
   return SS2_OK;
 }
 
-int ss2_stable_frames(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, const float* d_mesh1, const float* d_mesh2,
-                      int n, int H, int W, const float* h_minmax, int mode, int tps, float* d_out, void* stream) {
+static int stable_frames_impl(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, const float* d_mesh1, const float* d_mesh2,
+                              int n, int H, int W, const float* h_minmax, int mode, int tps, float* d_out, unsigned char* d_out8,
+                              void* stream) {
   if (!ctx) return SS2_ERR_INVALID;
   if (n < 0 || H <= 0 || W <= 0 || !h_minmax || (n > 0 && (!d_hr1 || !d_hr2 || !d_mesh1 || !d_mesh2)))
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stable_frames: bad arguments");
@@ -456,10 +457,13 @@ int ss2_stable_frames(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, cons
   ss2_canvas_size(h_minmax, &Ho, &Wo);
   if (Ho < 0 || Wo < 0) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stable_frames: negative canvas");
   if (n == 0 || Ho == 0 || Wo == 0) return SS2_OK;
-  if (!d_out) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stable_frames: null output");
+  if (!d_out && !d_out8) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stable_frames: null output");
   cudaStream_t st = (cudaStream_t)stream;
   const float out_w = h_minmax[1] - h_minmax[0], out_h = h_minmax[3] - h_minmax[2];
   if (tps != SS2_TPS_LATTICE || !tps_lattice_supported(Ho, Wo)) tps = SS2_TPS_EXACT;
+  if (d_out8 && tps != SS2_TPS_LATTICE)
+    return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "ss2_stable_frames_u8: the uint8 store is fused into the lattice resampler only "
+                    "(canvas %dx%d / tps mode): use ss2_stable_frames + ss2_frames_to_u8", Ho, Wo);
   const size_t m = (size_t)n * 2 * SS2_NPT * 2;
   TpsScratch sc;
   SS2_TRY(tps_scratch_alloc(ctx, 2 * n, Ho, Wo, tps, 2 * m, &sc, st));
@@ -470,10 +474,22 @@ int ss2_stable_frames(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, cons
   ss2_prof_begin(ctx, SS2_PROF_WARP, st);
   int rc = stable_meshes_launch(ctx, d_mesh1, d_mesh2, n, H, W, h_minmax[0], h_minmax[2], out_w, out_h, source, target, st);
   if (rc == SS2_OK) rc = tps_solve_for_warp(ctx, source, target, 2 * n, H, W, Ho, Wo, mode, tps, sc, st);
-  if (rc == SS2_OK) rc = tps_warp_blend_launch(ctx, d_hr1, d_hr2, source, sc.T, n, H, W, Ho, Wo, mode, tps, d_out, st, sc.aux, sc.nodes);
-  ss2_prof_end(ctx, SS2_PROF_WARP, st, (double)n * (2.0 * 3 * H * W + 3.0 * Ho * Wo) * 4.0);
+  if (rc == SS2_OK) rc = tps_warp_blend_launch(ctx, d_hr1, d_hr2, source, sc.T, n, H, W, Ho, Wo, mode, tps, d_out, st, sc.aux, sc.nodes, d_out8);
+  // algorithmic bytes of the bracket: both sources once + the fused frame once (fp32 canvas, or uint8 when the back end is fused)
+  ss2_prof_end(ctx, SS2_PROF_WARP, st, (double)n * (2.0 * 3 * H * W * 4.0 + 3.0 * Ho * Wo * (d_out8 ? 1.0 : 4.0)));
   cudaFreeAsync(sc.base, st);
   return rc;
+}
+
+int ss2_stable_frames(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, const float* d_mesh1, const float* d_mesh2,
+                      int n, int H, int W, const float* h_minmax, int mode, int tps, float* d_out, void* stream) {
+  return stable_frames_impl(ctx, d_hr1, d_hr2, d_mesh1, d_mesh2, n, H, W, h_minmax, mode, tps, d_out, nullptr, stream);
+}
+
+int ss2_stable_frames_u8(ss2_ctx* ctx, const float* d_hr1, const float* d_hr2, const float* d_mesh1, const float* d_mesh2,
+                         int n, int H, int W, const float* h_minmax, int mode, int tps, uint8_t* d_out, void* stream) {
+  if (ctx && n > 0 && !d_out) return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_stable_frames_u8: null output");
+  return stable_frames_impl(ctx, d_hr1, d_hr2, d_mesh1, d_mesh2, n, H, W, h_minmax, mode, tps, nullptr, d_out, stream);
 }
 
 }  // extern "C"

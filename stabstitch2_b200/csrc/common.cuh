@@ -225,7 +225,7 @@ int tps_warp_launch(ss2_ctx* ctx, const float* d_U, const float* d_source, const
                     const float* d_aux, float* d_nodes);
 int tps_warp_blend_launch(ss2_ctx* ctx, const float* d_img1, const float* d_img2, const float* d_source,
                           const float* d_T, int nframes, int H, int W, int Ho, int Wo, int mode, int tps,
-                          float* d_out, cudaStream_t st, const float* d_aux, float* d_nodes);
+                          float* d_out, cudaStream_t st, const float* d_aux, float* d_nodes, unsigned char* d_out8 = nullptr);
 // one stream-ordered allocation holding T [bn][2][66], aux [bn][8] and the lattice nodes
 struct TpsScratch {
   float* base = nullptr;

@@ -293,17 +293,25 @@ static int finish_impl(ss2_ctx* ctx, int slot, int mode, int tps, void* h_out, i
   }
   // The whole chunk is resampled into a device buffer of its own (HBM is plentiful), so the compute
   // stream is free for the next chunk's networks while the copy stream drains the frames to the host.
-  float *obuf, *obuf8f = nullptr;
-  SS2_TRY(named_buf(ctx, name("out_frames"), (size_t)n * fpx * sizeof(float), &obuf));
+  // uint8 interface: the resampler stores uint8 HWC itself (ss2_stable_frames_u8) where the lattice resampler runs; the
+  // fp32 canvas + conversion pass is the fallback for EXACT mode and small canvases.
+  const bool fused_u8 = u8 && tps == SS2_TPS_LATTICE && tps_lattice_supported(Ho, Wo);
+  float *obuf = nullptr, *obuf8f = nullptr;
+  if (!fused_u8) SS2_TRY(named_buf(ctx, name("out_frames"), (size_t)n * fpx * sizeof(float), &obuf));
   if (u8) SS2_TRY(named_buf(ctx, name("out_u8"), (size_t)n * fpx, &obuf8f));
   unsigned char* obuf8 = (unsigned char*)obuf8f;
   SS2_CUDA(ctx, cudaStreamWaitEvent(sc, hs.ev_hr, 0));
   for (int f0 = 0; f0 < n; f0 += WARP_CHUNK) {
     const int nf = n - f0 < WARP_CHUNK ? n - f0 : WARP_CHUNK;
-    float* dst = obuf + (size_t)f0 * fpx;
-    SS2_TRY(ss2_stable_frames(ctx, hr1 + (size_t)f0 * 3 * H * W, hr2 + (size_t)f0 * 3 * H * W, S1 + (size_t)f0 * SS2_NPT * 2,
-                              S2 + (size_t)f0 * SS2_NPT * 2, nf, H, W, h_mm, mode, tps, dst, sc));
-    if (u8) SS2_TRY(frames_to_u8_launch(ctx, dst, nf, Ho, Wo, obuf8 + (size_t)f0 * fpx, sc));   // :152,414 astype(uint8)
+    float* dst = fused_u8 ? nullptr : obuf + (size_t)f0 * fpx;
+    if (fused_u8) {
+      SS2_TRY(ss2_stable_frames_u8(ctx, hr1 + (size_t)f0 * 3 * H * W, hr2 + (size_t)f0 * 3 * H * W, S1 + (size_t)f0 * SS2_NPT * 2,
+                                   S2 + (size_t)f0 * SS2_NPT * 2, nf, H, W, h_mm, mode, tps, obuf8 + (size_t)f0 * fpx, sc));
+    } else {
+      SS2_TRY(ss2_stable_frames(ctx, hr1 + (size_t)f0 * 3 * H * W, hr2 + (size_t)f0 * 3 * H * W, S1 + (size_t)f0 * SS2_NPT * 2,
+                                S2 + (size_t)f0 * SS2_NPT * 2, nf, H, W, h_mm, mode, tps, dst, sc));
+      if (u8) SS2_TRY(frames_to_u8_launch(ctx, dst, nf, Ho, Wo, obuf8 + (size_t)f0 * fpx, sc));   // :152,414 astype(uint8)
+    }
     SS2_CUDA(ctx, cudaEventRecord(hs.ev_chunk[0], sc));
     SS2_CUDA(ctx, cudaStreamWaitEvent(sx, hs.ev_chunk[0], 0));
     if (u8)

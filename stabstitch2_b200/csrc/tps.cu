@@ -396,6 +396,7 @@ struct WarpParams {
   const float* source;   // [n][V][63][2]
   const float* T;        // [n][V][2][66]
   float* out;            // BLEND: [n][C][Ho][Wo]; else [n*V][C][Ho][Wo]
+  unsigned char* out8;   // fused pair kernel with the uint8 back end folded in: [n][Ho][Wo][3] (else unused)
   int H, W, Ho, Wo;
   float stepx, stepy;
   // lattice mode
@@ -717,7 +718,9 @@ template <int SX> struct LatCols { static constexpr int value = (LAT_THREADS + S
 
 // V = views evaluated per pixel: 1 (generic transformer), 2 (the production pair kernel), 3 / 4 (N-view fusion, config 5:
 // one pass over the canvas reads every source once instead of warping each view to a temporary)
-template <int V, int C, int MODE, bool BLEND, int SX, int SY, int IW, int IH>
+// U8: the driver's uint8 back end (frame.astype(uint8), test_online_tra.py:152,414) folded into the store of the fused pair
+// kernel: the fp32 canvas (the largest buffer of the path) is neither written nor read back by a conversion pass.
+template <int V, int C, int MODE, bool BLEND, int SX, int SY, int IW, int IH, bool U8 = false>
 __global__ void __launch_bounds__(LAT_THREADS, V <= 2 ? LAT_MINB : (V == 3 ? 5 : 4))
 tps_warp_lattice_kernel(WarpParams P) {
   constexpr int NCOL = LatCols<SX>::value;
@@ -1034,9 +1037,18 @@ tps_warp_lattice_kernel(WarpParams P) {
               float s0, s1, q0, q1;
               upk2(fadd2(fadd2(A, B), pk2(1e-6f, 1e-6f)), s0, s1);
               upk2(ffma2(B, B, fmul2(A, A)), q0, q1);
-              __stcs(const_cast<float*>(f32_at(outv[0], opix)), q0 * rcp_approx(s0));
-              __stcs(const_cast<float*>(f32_at(outv[0], opix + oplane)), q1 * rcp_approx(s1));
-              __stcs(const_cast<float*>(f32_at(outv[0], opix + 2 * oplane)), blend_avg_fast(res[i][0][2], res[i][V - 1][2]));
+              const float f0 = q0 * rcp_approx(s0), f1 = q1 * rcp_approx(s1), f2 = blend_avg_fast(res[i][0][2], res[i][V - 1][2]);
+              if (U8) {
+                // 0 <= f < 256 here (non-negative taps and weights), where numpy's astype(uint8) is plain truncation
+                unsigned char* o8 = P.out8 + ((size_t)n * oplane + opix) * 3;
+                __stcs(o8, (unsigned char)__float2int_rz(f0));
+                __stcs(o8 + 1, (unsigned char)__float2int_rz(f1));
+                __stcs(o8 + 2, (unsigned char)__float2int_rz(f2));
+              } else {
+                __stcs(const_cast<float*>(f32_at(outv[0], opix)), f0);
+                __stcs(const_cast<float*>(f32_at(outv[0], opix + oplane)), f1);
+                __stcs(const_cast<float*>(f32_at(outv[0], opix + 2 * oplane)), f2);
+              }
             } else if (BLEND) {
 #pragma unroll
               for (int c = 0; c < C; ++c)
@@ -1113,7 +1125,7 @@ static void blend_cubic(double R2, double div, float* p) {
   p[3] = (float)((-1.0 / ((R2 + e) * (R2 + e)) - 2.0 * e / ((R2 + e) * (R2 + e) * (R2 + e))) / 6.0 / div);
 }
 
-template <int V, int C, bool BLEND>
+template <int V, int C, bool BLEND, bool U8 = false>
 static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, float* d_nodes, cudaStream_t st) {
   const LatticeConfig cfg = lattice_config(P.Ho, P.Wo);
   P.nx = (P.Wo - 1) / cfg.SX + LAT_TAPS;
@@ -1142,10 +1154,10 @@ static int lattice_launch(ss2_ctx* ctx, WarpParams P, int nframes, int mode, flo
   const int spec = (BLEND && V == 2 && mode == SS2_MODE_NORMAL) ? ((P.W == 1280 && P.H == 720) ? 1 : (P.W == 1920 && P.H == 1080) ? 2 : 0) : 0;
 #define LAT_CASE(SXV, SYV)                                                                                   \
   if (cfg.SX == SXV && cfg.SY == SYV) {                                                                      \
-    if (spec == 1) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, (BLEND && V == 2) ? 1280 : 0, (BLEND && V == 2) ? 720 : 0><<<grid, LAT_THREADS, 0, st>>>(P); \
-    else if (spec == 2) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, (BLEND && V == 2) ? 1920 : 0, (BLEND && V == 2) ? 1080 : 0><<<grid, LAT_THREADS, 0, st>>>(P); \
-    else if (mode == SS2_MODE_NORMAL) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, 0, 0><<<grid, LAT_THREADS, 0, st>>>(P); \
-    else tps_warp_lattice_kernel<V, C, SS2_MODE_FAST, BLEND, SXV, SYV, 0, 0><<<grid, LAT_THREADS, 0, st>>>(P);  \
+    if (spec == 1) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, (BLEND && V == 2) ? 1280 : 0, (BLEND && V == 2) ? 720 : 0, U8><<<grid, LAT_THREADS, 0, st>>>(P); \
+    else if (spec == 2) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, (BLEND && V == 2) ? 1920 : 0, (BLEND && V == 2) ? 1080 : 0, U8><<<grid, LAT_THREADS, 0, st>>>(P); \
+    else if (mode == SS2_MODE_NORMAL) tps_warp_lattice_kernel<V, C, SS2_MODE_NORMAL, BLEND, SXV, SYV, 0, 0, U8><<<grid, LAT_THREADS, 0, st>>>(P); \
+    else tps_warp_lattice_kernel<V, C, SS2_MODE_FAST, BLEND, SXV, SYV, 0, 0, U8><<<grid, LAT_THREADS, 0, st>>>(P);  \
   }
   LAT_CASE(16, 8) LAT_CASE(16, 6) LAT_CASE(12, 8) LAT_CASE(12, 6) LAT_CASE(8, 8) LAT_CASE(8, 6)
 #undef LAT_CASE
@@ -1159,7 +1171,7 @@ int tps_warp_launch(ss2_ctx* ctx, const float* d_U, const float* d_source, const
   if (bn <= 0 || Ho <= 0 || Wo <= 0) return SS2_OK;
   WarpParams P;
   P.img[0] = d_U; P.img[1] = d_U; P.img[2] = d_U; P.img[3] = d_U;
-  P.source = d_source; P.T = d_T; P.out = d_out;
+  P.source = d_source; P.T = d_T; P.out = d_out; P.out8 = nullptr;
   P.H = H; P.W = W; P.Ho = Ho; P.Wo = Wo;
   P.stepx = linstep(Wo); P.stepy = linstep(Ho);
   P.aux = d_aux;
@@ -1198,19 +1210,22 @@ int tps_warp_launch(ss2_ctx* ctx, const float* d_U, const float* d_source, const
 
 int tps_warp_blend_launch(ss2_ctx* ctx, const float* d_img1, const float* d_img2, const float* d_source,
                           const float* d_T, int nframes, int H, int W, int Ho, int Wo, int mode, int tps,
-                          float* d_out, cudaStream_t st, const float* d_aux, float* d_nodes) {
+                          float* d_out, cudaStream_t st, const float* d_aux, float* d_nodes, unsigned char* d_out8) {
   if (nframes <= 0 || Ho <= 0 || Wo <= 0) return SS2_OK;
   WarpParams P;
   P.img[0] = d_img1; P.img[1] = d_img2; P.img[2] = d_img2; P.img[3] = d_img2;
-  P.source = d_source; P.T = d_T; P.out = d_out;
+  P.source = d_source; P.T = d_T; P.out = d_out; P.out8 = nullptr;
   P.H = H; P.W = W; P.Ho = Ho; P.Wo = Wo;
   P.stepx = linstep(Wo); P.stepy = linstep(Ho);
   P.aux = d_aux;
   P.half_w = mode == SS2_MODE_NORMAL ? 0.5f * W : 0.5f * (W - 1);
   P.half_h = mode == SS2_MODE_NORMAL ? 0.5f * H : 0.5f * (H - 1);
   // (the SS2_PROF_WARP bracket is set by the callers in api.cu, around canvas meshes + solves + nodes + this)
+  P.out8 = d_out8;
   if (tps == SS2_TPS_LATTICE && d_aux && d_nodes && tps_lattice_supported(Ho, Wo))
-    return lattice_launch<2, 3, true>(ctx, P, nframes, mode, d_nodes, st);
+    return d_out8 ? lattice_launch<2, 3, true, true>(ctx, P, nframes, mode, d_nodes, st)
+                  : lattice_launch<2, 3, true>(ctx, P, nframes, mode, d_nodes, st);
+  if (d_out8) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "uint8 output is fused into the lattice resampler only");
   dim3 grid(cdiv(Wo, TX), cdiv(Ho, TILE_H), nframes), block(TX, TY);
   if (mode == SS2_MODE_NORMAL) tps_warp_exact_kernel<2, 3, SS2_MODE_NORMAL, true><<<grid, block, 0, st>>>(P);
   else tps_warp_exact_kernel<2, 3, SS2_MODE_FAST, true><<<grid, block, 0, st>>>(P);
@@ -1223,11 +1238,11 @@ int tps_warp_blend_n_launch(ss2_ctx* ctx, const float* const* d_imgs, int nviews
                             const float* d_aux, float* d_nodes) {
   if (nframes <= 0 || Ho <= 0 || Wo <= 0) return SS2_OK;
   if (nviews == 2)
-    return tps_warp_blend_launch(ctx, d_imgs[0], d_imgs[1], d_source, d_T, nframes, H, W, Ho, Wo, mode, tps, d_out, st, d_aux, d_nodes);
+    return tps_warp_blend_launch(ctx, d_imgs[0], d_imgs[1], d_source, d_T, nframes, H, W, Ho, Wo, mode, tps, d_out, st, d_aux, d_nodes, nullptr);
   if (nviews != 3 && nviews != 4) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "fused N-view resampler: 2 <= N <= 4 (got %d)", nviews);
   WarpParams P;
   for (int v = 0; v < 4; ++v) P.img[v] = d_imgs[v < nviews ? v : 0];
-  P.source = d_source; P.T = d_T; P.out = d_out;
+  P.source = d_source; P.T = d_T; P.out = d_out; P.out8 = nullptr;
   P.H = H; P.W = W; P.Ho = Ho; P.Wo = Wo;
   P.stepx = linstep(Wo); P.stepy = linstep(Ho);
   P.aux = d_aux;

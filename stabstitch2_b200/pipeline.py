@@ -66,6 +66,26 @@ def stable_frames(hr1, hr2, mesh1, mesh2, minmax_host, mode="NORMAL", tps=None, 
     return out
 
 
+def stable_frames_u8(hr1, hr2, mesh1, mesh2, minmax_host, mode="NORMAL", tps=None, out=None):
+    """stable_frames (AVERAGE) with the driver's `.astype(uint8)` back end (test_online_tra.py:152,414) fused into the
+    resampler's store: fused frames [n,Ho,Wo,3] uint8, bit-identical to stable_frames + frames_to_u8.  Lattice resampler
+    only (raises SS2Error for canvases too small for it)."""
+    from .utils import torch_tps_transform as tt
+    ctx = _lib.context()
+    hr1, hr2 = _lib.dev_f32(hr1), _lib.dev_f32(hr2)
+    m1 = _lib.dev_f32(mesh1).reshape(-1, 7, 9, 2)
+    m2 = _lib.dev_f32(mesh2).reshape(-1, 7, 9, 2)
+    n, _, H, W = hr1.shape
+    Ho, Wo = canvas_size(minmax_host)
+    if out is None:
+        out = torch.empty(n, Ho, Wo, 3, device=hr1.device, dtype=torch.uint8)
+    mm = (ctypes.c_float * 4)(*[float(v) for v in minmax_host])
+    ctx.check(ctx.lib.ss2_stable_frames_u8(ctx.handle, _lib.ptr(hr1), _lib.ptr(hr2), _lib.ptr(m1), _lib.ptr(m2), n, H, W,
+                                           mm, _lib.MODE[mode], tt.DEFAULT_TPS if tps is None else tps, _lib.ptr(out),
+                                           _lib.cur_stream()))
+    return out
+
+
 def linear_blender(ref, tgt, ref_m, tgt_m, mask=False):
     """Drop-in for the driver's linear_blender (test_online_tra.py:34-58): ref, tgt [n,3,Ho,Wo]; ref_m, tgt_m
     [n,1,Ho,Wo] -> stitched [n,3,Ho,Wo] (mask=True: mask1 [n,1,Ho,Wo]).  Masks are thresholded at 0.5 (see

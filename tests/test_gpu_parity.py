@@ -476,6 +476,48 @@ def test_fullsize_properties():
     assert d.median().item() < 1e-4
 
 
+@pytest.mark.parametrize("mode", ["NORMAL", "FAST"])
+def test_stable_frames_u8_fused_store_bit_identical(mode):
+    """ss2_stable_frames_u8 (the uint8 back end fused into the lattice resampler's store, what the uint8 host pipeline
+    runs at 720p) == ss2_stable_frames + ss2_frames_to_u8, byte for byte; the unsupported cases fail loudly."""
+    from stabstitch2_b200 import _lib, pipeline
+    H, W = 720, 1280
+    m1, m2 = _canvas_case(H, W)
+    m1, m2 = torch.cat([m1, m1 + 0.7], 0), torch.cat([m2, m2 - 0.4], 0)
+    hr1 = torch.cat([O.synth_frame(0, 0, H, W), O.synth_frame(1, 0, H, W)], 0).cuda()
+    hr2 = torch.cat([O.synth_frame(0, 1, H, W), O.synth_frame(1, 1, H, W)], 0).cuda()
+    mm = pipeline.canvas_minmax(m1, m2, H, W).cpu().tolist()
+    fused = pipeline.stable_frames(hr1, hr2, m1, m2, mm, mode=mode, tps=_lib.TPS_LATTICE)
+    ref = pipeline.frames_to_u8(fused)
+    got = pipeline.stable_frames_u8(hr1, hr2, m1, m2, mm, mode=mode, tps=_lib.TPS_LATTICE)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == tuple(ref.shape)
+    assert torch.equal(got, ref)
+    assert float(got.float().mean()) > 20.0   # not a blank canvas
+    with pytest.raises(_lib.SS2Error):
+        pipeline.stable_frames_u8(hr1, hr2, m1, m2, mm, mode=mode, tps=_lib.TPS_EXACT)
+    small = [0.0, 100.0, 0.0, 60.0]   # a 60 x 100 canvas: too coarse for the lattice
+    with pytest.raises(_lib.SS2Error):
+        pipeline.stable_frames_u8(hr1, hr2, m1, m2, small, mode=mode, tps=_lib.TPS_LATTICE)
+
+
+def test_stream_host_u8_720p_fused_store(nets):
+    """The uint8 host pipeline at 720p (lattice resampler, so the fused uint8 store runs) == device-side edges + fp32
+    stream + conversion pass, byte for byte."""
+    from stabstitch2_b200 import pipeline
+    s, t, m = nets
+    n, H, W = 7, 720, 1280
+    u1, u2 = _synth_u8(2, n, H, W), _synth_u8(3, n, H, W)
+    hr1, lr1 = pipeline.load_frames_u8(u1)
+    hr2, lr2 = pipeline.load_frames_u8(u2)
+    fused, s1, s2 = pipeline.stitch_stream(s, t, m, lr1, lr2, hr1, hr2)
+    ref = pipeline.frames_to_u8(fused).cpu()
+    out = torch.empty(fused.numel(), dtype=torch.uint8).pin_memory()
+    ho, wo, m1, m2 = pipeline.stitch_stream_host_u8(s, t, m, u1.pin_memory(), u2.pin_memory(), out, want_meshes=True)
+    assert (ho, wo) == tuple(fused.shape[2:])
+    assert maxdiff(m1, s1) == 0.0 and maxdiff(m2, s2) == 0.0
+    assert torch.equal(out.reshape(n, ho, wo, 3), ref)
+
+
 def test_fullsize_fast_mode_lattice():
     """mode='FAST' (F.grid_sample, align_corners=True; utils/torch_tps_transform.py:158-162) with the LATTICE field
     at 720p: fused frame against the oracle, and the source coordinates of the generic single-view FAST kernel
