@@ -20,26 +20,31 @@
 // gives the same fp32-rounded coefficients (fp64 noise is ~1e-9 of an fp32 ulp here).
 //
 // Latency-oriented (64 systems per 32-frame chunk: the chip is never full, so the time is the
-// length of one system's dependency chain on ONE SM: 66 pivot steps).  The augmented matrix
-// [W | tp] (66 x 68) lives in REGISTERS, rows across LANES and columns across WARPS: thread (w, l)
-// owns rows l + 32 i (i < 3) and columns w + NW j (NW = 8 warps: j < 9).  With that layout
+// length of one system's dependency chain on ONE SM: 66 pivot steps).  Measured: a step costs what
+// the busiest warp's INSTRUCTION STREAM costs (~7 cycles per dependent instruction; DFMA issues at
+// 59 lanes per clock per SM on B200, the fp64 pipe is not the limit), so the layout minimises the
+// instructions of the warp on the critical path.  The augmented matrix [W | tp] (66 x 68) lives in
+// REGISTERS, rows across LANES and columns across WARPS: thread (w, l) owns rows l + 32 i (i < 3)
+// and columns w + NW j (NW = 8 warps: j < 9).  With that layout
 //   * the pivot row's elements a warp needs are its OWN columns of row p: one shuffle from lane
-//     p % 32, nothing travels between warps;
+//     p % 32, nothing travels between warps; the row slot of p is resolved by ONE three-way branch
+//     per step;
 //   * column k+1 (the multipliers of the next step and the candidates of its pivot search) sits
 //     in ONE warp, all 66 rows: that warp alone eliminates that column first, searches (redux.sync
 //     max over a monotone key, the reciprocal of every lane's own best candidate computed while the
-//     reduction is in flight), publishes pivot index, reciprocal and the column through shared
-//     memory and raises a step counter; only then it updates its other columns;
-//   * there is NO barrier in the loop: the other warps spin on the step counter (a ring of 32
-//     published columns; a warp publishes every 16th column, so no warp is ever more than 16 steps
-//     behind the writer and a ring slot is never overwritten while it can still be read).
-// The chain per step is therefore: counter visible -> 3 shared loads -> shuffle -> 3 DFMA -> keys ->
-// redux || reciprocal -> stores -> counter.  Rows are never swapped (the pivot row of step k is
-// remembered); columns <= k are dead and their slots are skipped.
+//     reduction is in flight) and publishes pivot row, reciprocal and the column through shared
+//     memory; no atomics, no work in the other warps;
+//   * ONE named barrier per step, placed right after the search: a warp updates its remaining
+//     columns AFTER the barrier, i.e. the searcher's bulk work overlaps the next step, in which another
+//     warp searches;
+//   * columns <= k are dead (never read again): the phase loop below skips their slots.
+// Rows are never swapped (the pivot row of step k is remembered).  Deterministic (the previous
+// kernel's shared atomicMax search could pick different pivots from run to run).
 // History (64 systems): matrix in shared memory 97 us; registers with rows across warps, an
-// atomicMax search in every warp and two barriers per step 53 us; rows across lanes with one barrier
-// per step 35 us; this form: see DESIGN.md.
-// A 17th warp computes the affine predictor of the lattice resampler and leaves.
+// atomicMax search in every warp and two barriers per step 53 us; this layout 24 us (a variant
+// without any barrier - warps spinning on a step counter in shared memory - measured the same and
+// is flagged by racecheck, so the barrier stays).
+// A further warp computes the affine predictor of the lattice resampler and leaves.
 // ------------------------------------------------------------------------------------------
 #ifndef SOLVE_NW
 #define SOLVE_NW 8                       // solver warps per system = column stride
@@ -74,7 +79,6 @@ struct SolveShared {
   double pinv[SS2_NSYS];          // 1 / pivot of step k
   double rhs[SS2_NSYS][2];
   int perm[SS2_NSYS];             // pivot row of step k
-  int ready;                      // columns 0..ready are published
   float sx[SS2_NPT_PAD], sy[SS2_NPT_PAD];
 };
 
@@ -91,16 +95,14 @@ __device__ __forceinline__ void solve_search(const double v0, const double v1, c
   // every lane inverts its own best candidate while the reduction is in flight; the winner publishes
   const double inv = solve_rcp(mine == k0 ? v0 : (mine == k1 ? v1 : v2));
   double* col = sh.colk[cn & (SOLVE_RING - 1)];
-  col[lane] = (k0 == best && best != 0u) ? 0.0 : v0;
-  col[lane + 32] = (k1 == best && best != 0u) ? 0.0 : v1;
-  if (lane + 64 < SS2_NSYS) col[lane + 64] = (k2 == best && best != 0u) ? 0.0 : v2;
+  col[lane] = v0;
+  col[lane + 32] = v1;
+  if (lane + 64 < SS2_NSYS) col[lane + 64] = v2;
   if (mine == best && (best != 0u || lane == 0)) {
+    if (best != 0u) col[best & 127u] = 0.0;   // the pivot row is not eliminated (after this lane's own store above: same warp, in order)
     sh.perm[cn] = (int)(best & 127u);
     sh.pinv[cn] = inv;
   }
-  __syncwarp();
-  __threadfence_block();
-  if (lane == 0) *(volatile int*)&sh.ready = cn;
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS)
@@ -115,7 +117,6 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
     sh.sx[tid] = src[2 * tid];
     sh.sy[tid] = src[2 * tid + 1];
   }
-  if (tid == 0) sh.ready = -1;
   __syncthreads();
   if (wid == SOLVE_NW) {
     // Affine predictor for the lattice resampler: least-squares fit target ~ a*sx + b*sy + c over
@@ -198,6 +199,7 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
   }
   unsigned used = 0u;  // bit i: this lane's row lane + 32 i has been a pivot row (the same in every warp)
   if (wid == 0) solve_search(a[0][0], a[1][0], a[2][0], used, lane, 0, sh);
+  solve_bar();
   // Step k eliminates column k; the warp that owns column cn = k + 1 (warp cn % NW, slot cn / NW) searches next.
   // Phase jn = cn / NW is unrolled: within it the slots below jn are dead (columns <= k are never read again), the slots
   // above are live, slot jn is live in the warps >= cn % NW: one dynamic predicate per step and no work on dead columns.
@@ -212,6 +214,7 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
     {                                                                                         \
       if (wid >= kk) SOLVE_ELIM(jn, PS)                                                       \
       if (wid == kk && cn < SS2_NSYS) solve_search(a[0][jn], a[1][jn], a[2][jn], used, lane, cn, sh); \
+      solve_bar();                                                                            \
       _Pragma("unroll") for (int j = jn + 1; j < SOLVE_CS; ++j) SOLVE_ELIM(j, PS)             \
     }
 #pragma unroll
@@ -220,16 +223,14 @@ tps_solve_kernel(const float* __restrict__ source, const float* __restrict__ tar
 #pragma unroll 1
     for (int kk = (jn == 0 ? 1 : 0); kk < kk1; ++kk) {
       const int cn = jn * SOLVE_NW + kk, k = cn - 1;
-      while (*(volatile int*)&sh.ready < k) {}
-      __threadfence_block();
-      const int p = *(volatile int*)&sh.perm[k];
-      const double inv = *(volatile double*)&sh.pinv[k];
-      const volatile double* col = sh.colk[k & (SOLVE_RING - 1)];
+      const int p = sh.perm[k];
+      const double inv = sh.pinv[k];
+      const double* col = sh.colk[k & (SOLVE_RING - 1)];
       // multipliers of this lane's rows, already zero in the pivot row; padding rows ride along with zero
       const double g0 = col[lane] * inv, g1 = col[lane + 32] * inv, g2 = lane + 64 < SS2_NSYS ? col[lane + 64] * inv : 0.0;
       const int ps = p >> 5, pl = p & 31;
       used |= (lane == pl ? 1u : 0u) << ps;   // the pivot row is not a candidate any more
-      if (ps == 0) SOLVE_STEP(0) else if (ps == 1) SOLVE_STEP(1) else SOLVE_STEP(2)
+      if (ps == 0) SOLVE_STEP(0) else if (ps == 1) SOLVE_STEP(1) else SOLVE_STEP(2)   // one barrier inside, CTA-uniform branch
     }
   }
 #undef SOLVE_STEP
