@@ -153,6 +153,13 @@ int ss2_build_temporal(ss2_ctx* ctx, const float* d_frames, int n, float* d_moti
  * ss2_build_temporal calls; frames_a/b [n,3,360,480] -> motions_a/b [n,7,9,2]. */
 int ss2_build_temporal_pair(ss2_ctx* ctx, const float* d_frames_a, const float* d_frames_b, int n, float* d_motions_a,
                             float* d_motions_b, void* stream);
+/* build_SpatialNet over n frame pairs AND build_TemporalNet over both views in one call (the two networks are independent:
+ * TemporalNet runs on a stream of its own next to SpatialNet, fork / join inside the library; bit-identical to the two
+ * separate calls).  d_lr1, d_lr2 [halo+n,3,360,480]: the first `halo` frames (0, or 1 = the frame before a temporal shard)
+ * feed TemporalNet only.  d_sm1, d_sm2 [n,7,9,2] = SpatialNet's motion1 / motion2; d_tm1, d_tm2 [halo+n,7,9,2] = TemporalNet's
+ * motion lists of the two views (row 0 zero).  SS2_NET_OVERLAP=0 runs one network after the other. */
+int ss2_build_spatial_temporal(ss2_ctx* ctx, const float* d_lr1, const float* d_lr2, int n, int halo, float* d_sm1,
+                               float* d_sm2, float* d_tm1, float* d_tm2, void* stream);
 /* tsmotion preparation, test_online_tra.py:309-347, one view: smotion,tmotion [n,7,9,2] ->
  * smesh, tsmotion [n,7,9,2].  `first_is_stream_start` != 0 makes tsmotion[0] = 0 (k == 0
  * branch); otherwise smotion_prev [7,9,2] (frame before the chunk) must be given. */

@@ -43,6 +43,7 @@ SIGNATURES = {
     "ss2_spatial_tail": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "ss2_build_temporal": (_i, [_vp, _vp, _i, _vp, _vp]),
     "ss2_build_temporal_pair": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ss2_build_spatial_temporal": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "ss2_tsmotion": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "ss2_build_smooth": (_i, [_vp] + [_vp] * 4 + [_i, _i] + [_vp] * 8 + [_vp]),
     "ss2_canvas_minmax": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -31,6 +31,7 @@ int ss2_ensure_arena(ss2_ctx* ctx, size_t bytes) {
 }
 
 int ss2_workspace_enter(ss2_ctx* ctx, cudaStream_t st) {
+  if (ctx->ws_nested) return SS2_OK;   // forked by an outer entry point, which entered on the caller's stream and joins it
   if (ctx->ws_used && st != ctx->ws_stream) {
     if (!ctx->ws_ev) SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ws_ev, cudaEventDisableTiming));
     SS2_CUDA(ctx, cudaEventRecord(ctx->ws_ev, ctx->ws_stream));
@@ -132,6 +133,8 @@ int ss2_create(int device, ss2_ctx** out) {
   if (env) c->use_tc_stem = atoi(env);
   env = getenv("SS2_SIDE_STREAM");
   if (env) c->use_side = atoi(env);
+  env = getenv("SS2_NET_OVERLAP");
+  if (env) c->use_net_overlap = atoi(env);
   env = getenv("SS2_CONV_DC");
   if (env) c->use_dc = atoi(env);
   *out = c;
@@ -151,6 +154,10 @@ void ss2_destroy(ss2_ctx* ctx) {
   for (void* p : ctx->owned) cudaFree(p);
   for (auto& v : ctx->owned_net) for (void* p : v) cudaFree(p);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
+  if (ctx->arena_alt.base) cudaFree(ctx->arena_alt.base);
+  if (ctx->s_net) cudaStreamDestroy(ctx->s_net);
+  if (ctx->ev_nfork) cudaEventDestroy(ctx->ev_nfork);
+  if (ctx->ev_njoin) cudaEventDestroy(ctx->ev_njoin);
   for (auto& kv : ctx->stream_bufs) cudaFree(kv.second.first);
   for (auto& pc : ctx->prof) for (cudaEvent_t e : pc.pool) cudaEventDestroy(e);
   delete ctx;

@@ -133,6 +133,13 @@ struct ss2_ctx {
   cudaStream_t s_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int use_side = 1;     // SS2_SIDE_STREAM=0: everything on the caller's stream
+  // SpatialNet and TemporalNet of a chunk are independent until the tsmotion step: TemporalNet runs on a stream of its
+  // own with a workspace arena of its own next to SpatialNet (ss2_stream_meshes, ss2_build_spatial_temporal)
+  Arena arena_alt;
+  cudaStream_t s_net = nullptr;
+  cudaEvent_t ev_nfork = nullptr, ev_njoin = nullptr;
+  int use_net_overlap = 1;   // SS2_NET_OVERLAP=0: one network after the other on the caller's stream
+  bool ws_nested = false;    // inside such a fork: the inner entry points must not re-serialise the streams
   void* host_slots = nullptr;  // HostSlot[HOST_SLOTS] of the host-buffer pipeline (stream.cu), created on first use
   int use_tc = 1;  // tcgen05 implicit-GEMM path for eligible layers
   bool lag_tables_ready = false;

@@ -10,6 +10,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <utility>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -594,6 +596,43 @@ extern "C" int ss2_build_temporal_pair(ss2_ctx* ctx, const float* d_frames_a, co
     SS2_CUDA(ctx, cudaMemcpyAsync(d_motions_b + (size_t)f0 * 126, mot + (size_t)nm * 126, (size_t)nm * 126 * 4, cudaMemcpyDeviceToDevice, st));
   }
   return SS2_OK;
+}
+
+// SpatialNet over n frame pairs and TemporalNet over both views (halo + n frames each; the first `halo` frames of
+// d_lr1 / d_lr2 only feed TemporalNet: the frame before a temporal shard) as ONE call: the two networks are independent,
+// and behind each backbone sits a train of ~20-40 launches of a few dozen CTAs, so TemporalNet runs on a stream of its own
+// (workspace arena of its own) next to SpatialNet and the trains overlap.  Same kernels on the same data as the two
+// separate calls: bit-identical outputs.  d_tm1 / d_tm2 [halo+n,7,9,2] (row 0 zero), d_sm1 / d_sm2 [n,7,9,2].
+extern "C" int ss2_build_spatial_temporal(ss2_ctx* ctx, const float* d_lr1, const float* d_lr2, int n, int halo, float* d_sm1,
+                                          float* d_sm2, float* d_tm1, float* d_tm2, void* stream) {
+  if (!ctx) return SS2_ERR_INVALID;
+  if (n < 0 || halo < 0 || (n > 0 && (!d_lr1 || !d_lr2 || !d_sm1 || !d_sm2 || !d_tm1 || !d_tm2)))
+    return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_build_spatial_temporal: bad arguments");
+  if (n == 0) return SS2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ipx = (size_t)3 * NET_IMG_H * NET_IMG_W;
+  const float *sp1 = d_lr1 + (size_t)halo * ipx, *sp2 = d_lr2 + (size_t)halo * ipx;
+  if (!ctx->use_net_overlap || ctx->prof[SS2_PROF_CONV].enabled || ctx->ws_nested) {
+    SS2_TRY(ss2_build_spatial(ctx, sp1, sp2, n, d_sm1, d_sm2, stream));
+    return ss2_build_temporal_pair(ctx, d_lr1, d_lr2, halo + n, d_tm1, d_tm2, stream);
+  }
+  SS2_TRY(ss2_workspace_enter(ctx, st));
+  if (!ctx->s_net) {
+    SS2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_net, cudaStreamNonBlocking));
+    SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_nfork, cudaEventDisableTiming));
+    SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_njoin, cudaEventDisableTiming));
+  }
+  SS2_CUDA(ctx, cudaEventRecord(ctx->ev_nfork, st));
+  SS2_CUDA(ctx, cudaStreamWaitEvent(ctx->s_net, ctx->ev_nfork, 0));
+  ctx->ws_nested = true;
+  int rc = ss2_build_spatial(ctx, sp1, sp2, n, d_sm1, d_sm2, stream);
+  std::swap(ctx->arena, ctx->arena_alt);
+  const int rc_t = ss2_build_temporal_pair(ctx, d_lr1, d_lr2, halo + n, d_tm1, d_tm2, ctx->s_net);
+  std::swap(ctx->arena, ctx->arena_alt);
+  ctx->ws_nested = false;
+  SS2_CUDA(ctx, cudaEventRecord(ctx->ev_njoin, ctx->s_net));   // also after a failure: never leave the side stream detached
+  SS2_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_njoin, 0));
+  return rc != SS2_OK ? rc : rc_t;
 }
 
 extern "C" int ss2_build_smooth(ss2_ctx* ctx, const float* d_ts1, const float* d_ts2, const float* d_sm1,

@@ -58,8 +58,7 @@ extern "C" int ss2_stream_meshes(ss2_ctx* ctx, const float* d_lr1, const float* 
   float *sm1 = buf, *sm2 = buf + m, *tm1 = buf + 2 * m, *tm2 = buf + 3 * m;
   float *mesh1 = buf + 4 * m, *mesh2 = buf + 5 * m, *ts1 = buf + 6 * m, *ts2 = buf + 7 * m;
   float *w1 = buf + 8 * m, *w2 = w1 + wm;
-  SS2_TRY(ss2_build_spatial(ctx, d_lr1, d_lr2, n, sm1, sm2, stream));
-  SS2_TRY(ss2_build_temporal_pair(ctx, d_lr1, d_lr2, n, tm1, tm2, stream));
+  SS2_TRY(ss2_build_spatial_temporal(ctx, d_lr1, d_lr2, n, 0, sm1, sm2, tm1, tm2, stream));
   SS2_TRY(ss2_tsmotion(ctx, sm1, tm1, n, 1, nullptr, mesh1, ts1, stream));
   SS2_TRY(ss2_tsmotion(ctx, sm2, tm2, n, 1, nullptr, mesh2, ts2, stream));
   SS2_TRY(ss2_build_smooth(ctx, ts1, ts2, mesh1, mesh2, nwin, 1, nullptr, nullptr, nullptr, w1, nullptr, nullptr, nullptr,

@@ -480,13 +480,29 @@ def allreduce_canvas(minmax, group=None):
     return v * sign
 
 
+def build_spatial_temporal(spatial_net, temporal_net, lr1, lr2, halo=0):
+    """build_SpatialNet over the last n frame pairs and build_TemporalNet over both views of lr1, lr2 [halo+n,3,360,480] in one
+    library call (TemporalNet on a stream of its own next to SpatialNet; bit-identical to the separate calls).
+    Returns (motion1, motion2 [n,7,9,2], tmotion1, tmotion2 [halo+n,7,9,2])."""
+    ctx = _lib.context()
+    spatial_net.sync_weights(ctx)
+    temporal_net.sync_weights(ctx)
+    lr1, lr2 = _lib.dev_f32(lr1), _lib.dev_f32(lr2)
+    n = lr1.shape[0] - int(halo)
+    dev = lr1.device
+    sm = [torch.empty(n, 7, 9, 2, device=dev, dtype=torch.float32) for _ in range(2)]
+    tm = [torch.empty(n + int(halo), 7, 9, 2, device=dev, dtype=torch.float32) for _ in range(2)]
+    ctx.check(ctx.lib.ss2_build_spatial_temporal(ctx.handle, _lib.ptr(lr1), _lib.ptr(lr2), n, int(halo), _lib.ptr(sm[0]),
+                                                 _lib.ptr(sm[1]), _lib.ptr(tm[0]), _lib.ptr(tm[1]), _lib.cur_stream()))
+    return sm[0], sm[1], tm[0], tm[1]
+
+
 def stream_meshes_sharded(spatial_net, temporal_net, smooth_net, lr1, lr2, input_halo, frames, group=None):
     """Smooth meshes of this rank's `frames` frames of a temporally sharded stream.  lr1, lr2
     [input_halo+frames,3,360,480] (rank > 0 also gets frame start-1 for TemporalNet).  One all-gather of the raw
     per-frame motions (4 KB per frame) rebuilds the 6-frame SmoothNet context locally.  Returns (S1, S2 [frames,7,9,2])
     - identical to rows [start, stop) of the single-process result."""
     import torch.distributed as dist
-    from .spatial_network import build_SpatialNet
     ctx = _lib.context()
     _sync_nets(ctx, spatial_net, temporal_net, smooth_net)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -498,11 +514,10 @@ def stream_meshes_sharded(spatial_net, temporal_net, smooth_net, lr1, lr2, input
     dev = lr1.device
     st = _lib.cur_stream()
     raw = torch.empty(4, F, 7, 9, 2, device=dev, dtype=torch.float32)
-    sp = build_SpatialNet(spatial_net, lr1[input_halo:], lr2[input_halo:])
-    raw[0], raw[1] = sp["motion1"], sp["motion2"]
     tms = [torch.empty(F + input_halo, 7, 9, 2, device=dev, dtype=torch.float32) for _ in range(2)]
-    ctx.check(ctx.lib.ss2_build_temporal_pair(ctx.handle, _lib.ptr(lr1), _lib.ptr(lr2), F + input_halo, _lib.ptr(tms[0]),
-                                              _lib.ptr(tms[1]), st))
+    # both networks in one call: TemporalNet (halo frame included) runs next to SpatialNet on a stream of its own
+    ctx.check(ctx.lib.ss2_build_spatial_temporal(ctx.handle, _lib.ptr(lr1), _lib.ptr(lr2), F, input_halo, _lib.ptr(raw[0]),
+                                                 _lib.ptr(raw[1]), _lib.ptr(tms[0]), _lib.ptr(tms[1]), st))
     raw[2], raw[3] = tms[0][input_halo:], tms[1][input_halo:]
     allraw = exchange_raw_meshes(raw, group)  # [4, world*F, 7,9,2]
     c0, stop = plan["ctx0"], plan["stop"]

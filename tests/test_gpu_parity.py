@@ -500,6 +500,28 @@ def test_stable_frames_u8_fused_store_bit_identical(mode):
         pipeline.stable_frames_u8(hr1, hr2, m1, m2, small, mode=mode, tps=_lib.TPS_LATTICE)
 
 
+@pytest.mark.parametrize("halo", [0, 1])
+def test_spatial_temporal_one_call_bit_identical(nets, halo):
+    """ss2_build_spatial_temporal (TemporalNet on a stream and workspace arena of its own next to SpatialNet) == the two
+    separate calls, bit for bit; repeated to catch a race between the two streams."""
+    from stabstitch2_b200 import _lib, pipeline
+    from stabstitch2_b200.spatial_network import build_SpatialNet
+    s, t, m = nets
+    n = 9
+    lr1 = torch.cat([O.lowres(O.synth_frame(k, 0, 360, 480)) for k in range(n + halo)], 0).cuda()
+    lr2 = torch.cat([O.lowres(O.synth_frame(k, 1, 360, 480)) for k in range(n + halo)], 0).cuda()
+    sp = build_SpatialNet(s, lr1[halo:], lr2[halo:])
+    ctx = _lib.context()
+    tm = [torch.empty(n + halo, 7, 9, 2, device="cuda") for _ in range(2)]
+    ctx.check(ctx.lib.ss2_build_temporal_pair(ctx.handle, _lib.ptr(lr1), _lib.ptr(lr2), n + halo, _lib.ptr(tm[0]), _lib.ptr(tm[1]),
+                                              _lib.cur_stream()))
+    for _ in range(3):
+        sm1, sm2, tm1, tm2 = pipeline.build_spatial_temporal(s, t, lr1, lr2, halo)
+        assert torch.equal(sm1, sp["motion1"].reshape(n, 7, 9, 2)) and torch.equal(sm2, sp["motion2"].reshape(n, 7, 9, 2))
+        assert torch.equal(tm1, tm[0]) and torch.equal(tm2, tm[1])
+    assert float(sm1.abs().max()) > 0 and float(tm1[1:].abs().max()) > 0
+
+
 def test_stream_host_u8_720p_fused_store(nets):
     """The uint8 host pipeline at 720p (lattice resampler, so the fused uint8 store runs) == device-side edges + fp32
     stream + conversion pass, byte for byte."""
