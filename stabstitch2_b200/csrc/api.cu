@@ -32,6 +32,11 @@ int ss2_ensure_arena(ss2_ctx* ctx, size_t bytes) {
 
 int ss2_workspace_enter(ss2_ctx* ctx, cudaStream_t st) {
   if (ctx->ws_nested) return SS2_OK;   // forked by an outer entry point, which entered on the caller's stream and joins it
+  if (ctx->h_range_flag && *(volatile int*)ctx->h_range_flag) {
+    *ctx->h_range_flag = 0;
+    return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "an activation of an earlier call exceeded the fp16 range (|v| > 65504) of the fp16 "
+                    "split planes: its results are invalid; run with SS2_F16=0 (TF32 split planes)");
+  }
   if (ctx->ws_used && st != ctx->ws_stream) {
     if (!ctx->ws_ev) SS2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ws_ev, cudaEventDisableTiming));
     SS2_CUDA(ctx, cudaEventRecord(ctx->ws_ev, ctx->ws_stream));
@@ -135,6 +140,16 @@ int ss2_create(int device, ss2_ctx** out) {
   if (env) c->use_side = atoi(env);
   env = getenv("SS2_NET_OVERLAP");
   if (env) c->use_net_overlap = atoi(env);
+  env = getenv("SS2_F16");
+  if (env) c->use_f16 = atoi(env);
+  if (cudaHostAlloc((void**)&c->h_range_flag, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&c->d_range_flag, c->h_range_flag, 0) != cudaSuccess) {
+    cudaGetLastError();
+    c->h_range_flag = c->d_range_flag = nullptr;
+    c->use_f16 = 0;   // no way to report a range overflow: stay on the TF32 planes
+  } else {
+    *c->h_range_flag = 0;
+  }
   env = getenv("SS2_CONV_DC");
   if (env) c->use_dc = atoi(env);
   *out = c;
@@ -155,6 +170,7 @@ void ss2_destroy(ss2_ctx* ctx) {
   for (auto& v : ctx->owned_net) for (void* p : v) cudaFree(p);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->arena_alt.base) cudaFree(ctx->arena_alt.base);
+  if (ctx->h_range_flag) cudaFreeHost(ctx->h_range_flag);
   if (ctx->s_net) cudaStreamDestroy(ctx->s_net);
   if (ctx->ev_nfork) cudaEventDestroy(ctx->ev_nfork);
   if (ctx->ev_njoin) cudaEventDestroy(ctx->ev_njoin);

@@ -1,5 +1,6 @@
 // Shared declarations for libss2.so (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -34,6 +35,10 @@ struct ConvLayer {
   // tcgen05 path: K-major filter matrices [CoutP][KD*KH*KW*CinP], hi = rna_tf32(w), lo = w - hi
   float* wk_hi = nullptr;
   float* wk_lo = nullptr;
+  // stride-1 3x3 layers with CinP % 64 == 0: the same matrices as fp16 planes for the kind::f16 direct kernel (conv_dc.cu):
+  // h16 = fp16(w), l16 = fp16((w - h16) * 2048)
+  __half* wk_h16 = nullptr;
+  __half* wk_l16 = nullptr;
   // 7x7 stride-2 stem with 3 input channels: wk_hi/lo are [CoutP][7 * 32], k = kh * 32 + kw * 4 + c (one filter row =
   // 8 NHWC4 pixels, the eighth and the fourth channel are zero); consumed by conv_tc_stem_launch
   bool stem_k32 = false;
@@ -45,10 +50,14 @@ struct ConvLayer {
 
 // An activation tensor: plain fp32 values and (for the tensor-core layers that consume it) the
 // split hi = rna_tf32(v), lo = v - hi.  hi/lo may be null.
+// h16 / l16: the split as fp16 planes for a consumer that runs kind::f16 MMAs (conv_dc.cu): h16 = fp16(v),
+// l16 = fp16((v - h16) * 2048); 11 + 11 significand bits like the TF32 pair.
 struct ActRef {
   float* v = nullptr;
   float* hi = nullptr;
   float* lo = nullptr;
+  __half* h16 = nullptr;
+  __half* l16 = nullptr;
 };
 
 struct ResBlock {
@@ -147,6 +156,12 @@ struct ss2_ctx {
   int tc_passes = 3;  // 3 = split-TF32 (fp32-grade), 1 = plain TF32
   int use_tc_stem = 2;  // SS2_TC_STEM: 2 = direct tensor-core stem with the max-pool fused (conv_stem.cu), 1 = implicit-GEMM
                         // tensor-core stem + pool kernel, 0 = exact-fp32 SIMT stem + pool kernel
+  // SS2_F16=0: TF32 split planes everywhere.  Default: the stride-1 3x3 layers of the ResNet bodies read fp16 split planes
+  // and run kind::f16 MMAs (conv_dc.cu); their producers' epilogues write those planes.  fp16 holds |v| <= 65504: an
+  // epilogue that meets a larger value raises *range_flag (mapped pinned host memory); the next entry point fails loudly.
+  int use_f16 = 1;
+  int* h_range_flag = nullptr;   // host view
+  int* d_range_flag = nullptr;   // device view of the same word
   int use_dc = 1;     // direct 3x3 kernel (conv_dc.cu) for eligible layers; SS2_CONV_DC=0 disables
 };
 
@@ -195,6 +210,25 @@ __device__ __forceinline__ void tf32_split(float v, float* hi, float* lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   *hi = __uint_as_float(r);
   *lo = v - *hi;
+}
+// fp16 split of the kind::f16 path: h = fp16(v) (|v| clamped to the fp16 range), l = fp16((v - h) * 2^11): v = h + l / 2048
+// to 2^-22 relative (to 2^-36 absolute below fp16's normal range, where the scaled l recovers what the subnormal h loses)
+#define SS2_F16_LO_SCALE 2048.0f
+__device__ __forceinline__ void f16_split(float v, __half* h, __half* l) {
+  const __half hh = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+  *h = hh;
+  *l = __float2half_rn(fminf(fmaxf((v - __half2float(hh)) * SS2_F16_LO_SCALE, -65504.0f), 65504.0f));
+}
+// four consecutive channels of the two fp16 planes (8 bytes each)
+__device__ __forceinline__ void store_f16_planes4(__half* h16, __half* l16, size_t o, const float (&v)[4], int* range_flag) {
+  if (fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))) > 65504.0f) *range_flag = 1;   // (NaN compares false)
+  __half h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) f16_split(v[e], &h[e], &l[e]);
+  *reinterpret_cast<uint2*>(h16 + o) = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                                                  (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+  *reinterpret_cast<uint2*>(l16 + o) = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+                                                  (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
 }
 __device__ __forceinline__ void store_split4(const ActRef& o, size_t idx, float4 v) {
   *reinterpret_cast<float4*>(o.v + idx) = v;

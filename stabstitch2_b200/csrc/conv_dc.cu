@@ -28,6 +28,9 @@ struct DcParams {
   float* out_v;
   float* out_hi;
   float* out_lo;
+  __half* out_h16;     // fp16 split planes for a kind::f16 consumer (may be null)
+  __half* out_l16;
+  int* range_flag;     // raised when a value does not fit fp16 (common.cuh)
   int B, H, W, Cout;
   int P, TH, TW;       // padded pitch TW + 2, output rows / columns per tile
   int tiles_h, tiles_w;  // ceil(H / TH), ceil(W / TW)
@@ -83,12 +86,18 @@ __device__ __forceinline__ void dc_residual_issue(const DcParams& P, int t, int 
 // deliver into one SM (~22 B/clk: 110-130 cycles per MMA for N = 64 and N = 128 alike, tensor pipe ~30% active), not
 // by MMA issue or accumulator dependencies, so a tile of two blocks (2 TH image rows) shares every weight stage between
 // two MMAs and its TH + 2 input rows between 2 TH output rows: ~45% fewer staged bytes per output row.
-template <int BN, int MT>
+// F16: the operands are fp16 split planes (h16 = fp16(v), l16 = fp16((v - h16) * 2048), common.cuh) and the MMAs are
+// kind::f16: K = 16 per instruction at twice the TF32 rate, so a 128-byte K-major row is 64 channels and a layer has half
+// the chunks, stages and MMA instructions.  The same three exact products: A_h x [B_h | B_l] lands as [D1 | D2] with D2
+// carrying the factor 2048 of B_l, A_l x B_h (factor 2048 of A_l) accumulates into D2 as well, the epilogue takes
+// D1 + D2 / 2048.  Everything else (tile, rings, barriers, byte counts) is unchanged.
+template <int BN, int MT, bool F16 = false>
 __global__ void __launch_bounds__(DC_THREADS, 1)
 conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DcParams P) {
   constexpr int DC_BN = BN;
   constexpr int DC_B_BYTES = BN * DC_BK * 4;  // per plane
+  constexpr int BKC = F16 ? 2 * DC_BK : DC_BK;   // channels per chunk (one 128-byte row)
   // Split TF32 as TWO MMAs per k-step instead of three: the weight planes of a stage are adjacent in shared memory,
   // so A_hi x [B_hi | B_lo] is ONE MMA with N = 2 BN into accumulator columns [D1 | D2], and A_lo x B_hi a second one
   // with N = BN into D1; the epilogue adds D1 + D2.  A tcgen05 TF32 MMA of 128 x N x 8 takes ~43 + N / 2 cycles on
@@ -137,8 +146,8 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (ia >= P.NA) mbar_wait(&a_empty[sa], ((ia / P.NA) - 1) & 1);
           uint8_t* ad = a_ring + (size_t)sa * a_stage;
           mbar_expect_tx(&a_full[sa], a_bytes);
-          tma_load_5d(ad, &tmA_hi, &a_full[sa], ck * DC_BK, w0 - 1, h0 - 1, 0, n);
-          if (nplanes == 2) tma_load_5d(ad + a_plane, &tmA_lo, &a_full[sa], ck * DC_BK, w0 - 1, h0 - 1, 0, n);
+          tma_load_5d(ad, &tmA_hi, &a_full[sa], ck * BKC, w0 - 1, h0 - 1, 0, n);
+          if (nplanes == 2) tma_load_5d(ad + a_plane, &tmA_lo, &a_full[sa], ck * BKC, w0 - 1, h0 - 1, 0, n);
           ++ia;
           for (int tap = 0; tap < 9; ++tap) {
             const int sb = ib % P.NB;
@@ -147,9 +156,9 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_expect_tx(&b_full[sb], b_stage);
 #pragma unroll
             for (int j = 0; j < BN / DC_BOX_N; ++j) {
-              tma_load_2d(bd + j * (DC_BOX_N * DC_BK * 4), &tmB_hi, &b_full[sb], tap * P.CinP + ck * DC_BK, nt * DC_BN + j * DC_BOX_N);
+              tma_load_2d(bd + j * (DC_BOX_N * DC_BK * 4), &tmB_hi, &b_full[sb], tap * P.CinP + ck * BKC, nt * DC_BN + j * DC_BOX_N);
               if (nplanes == 2)
-                tma_load_2d(bd + DC_B_BYTES + j * (DC_BOX_N * DC_BK * 4), &tmB_lo, &b_full[sb], tap * P.CinP + ck * DC_BK,
+                tma_load_2d(bd + DC_B_BYTES + j * (DC_BOX_N * DC_BK * 4), &tmB_lo, &b_full[sb], tap * P.CinP + ck * BKC,
                             nt * DC_BN + j * DC_BOX_N);
             }
             ++ib;
@@ -161,8 +170,10 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===== MMA issuer (one thread) =====
     if (dc_elect_one()) {
       // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * DC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // (kind::f16: A/B format 0 = fp16)
+      constexpr uint32_t FMT = F16 ? 0u : ((2u << 7) | (2u << 10));
+      const uint32_t idesc = (1u << 4) | FMT | ((uint32_t)(DC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | FMT | ((uint32_t)(2 * DC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t a_plane16 = a_plane >> 4;
       const uint32_t accw = (uint32_t)(nplanes == 2 ? 2 * DC_BN : DC_BN);   // accumulator columns per 128-row block
       int ia = 0, ib = 0, it = 0;
@@ -190,9 +201,15 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
               for (int k = 0; k < DC_BK / 8; ++k) {
 #pragma unroll
-                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * accw, da + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc2, k == 0 ? first : 1u);
+                for (int b = 0; b < MT; ++b) {
+                  if (F16) dc_mma_f16(d_tmem + b * accw, da + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc2, k == 0 ? first : 1u);
+                  else dc_mma(d_tmem + b * accw, da + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc2, k == 0 ? first : 1u);
+                }
 #pragma unroll
-                for (int b = 0; b < MT; ++b) dc_mma(d_tmem + b * accw, dal + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);
+                for (int b = 0; b < MT; ++b) {
+                  if (F16) dc_mma_f16(d_tmem + b * accw + DC_BN, dal + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);   // scaled: into D2
+                  else dc_mma(d_tmem + b * accw, dal + b * BLK + 2 * k, db + 2 * k, DC_DESC_HI, idesc, 1u);
+                }
               }
             } else {
 #pragma unroll
@@ -254,7 +271,9 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           uint32_t acc2[32];
           tmem_ld32(tcol + DC_BN, acc2);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
+          for (int j = 0; j < 32; ++j)
+            acc[j] = __float_as_uint(F16 ? fmaf(__uint_as_float(acc2[j]), 1.0f / SS2_F16_LO_SCALE, __uint_as_float(acc[j]))
+                                         : __uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
         }
         if (step == NSTEP - 1) {
           // this warp's accumulator quarter is in registers: hand the TMEM stage back to the MMA warp
@@ -296,6 +315,7 @@ conv_dc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 *reinterpret_cast<float4*>(P.out_hi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
               }
+              if (P.out_h16) store_f16_planes4(P.out_h16, P.out_l16, o, v, P.range_flag);
             }
           }
           __syncwarp();
@@ -322,16 +342,20 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   DcParams P;
   P.bias = L.bias; P.residual = d_residual;
   P.out_v = out.v; P.out_hi = out.hi; P.out_lo = out.lo;
+  P.out_h16 = out.h16; P.out_l16 = out.h16 ? out.l16 : nullptr; P.range_flag = ctx->d_range_flag;
+  const bool f16 = in.h16 != nullptr && in.hi == nullptr;   // fp16 split planes in: kind::f16 MMAs
+  if (f16 && (!in.l16 || !L.wk_h16 || !L.wk_l16 || (L.CinP % 64) != 0 || ctx->tc_passes == 1))
+    return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_dc: fp16 planes given to a layer without fp16 filter planes");
   P.B = B; P.H = H; P.W = W; P.Cout = L.Cout;
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
   // N tile: 128 output channels per MMA where the layer has them (half the tcgen05.mma instructions per FLOP and the
   // staged input tile is read once for 128 channels), else 64
   int BN = (L.CoutP % 128) == 0 ? 128 : 64;
-  P.nchunk = L.CinP / DC_BK; P.CinP = L.CinP;
+  P.nchunk = L.CinP / (f16 ? 2 * DC_BK : DC_BK); P.CinP = L.CinP;
   P.relu = relu;
   { const char* e = getenv("SS2_DC_DBG"); P.dbg = e ? atoi(e) : 0; }
-  P.npass = (ctx->tc_passes == 1 || !in.lo || !L.wk_lo) ? 1 : 3;
+  P.npass = f16 ? 3 : (ctx->tc_passes == 1 || !in.lo || !L.wk_lo) ? 1 : 3;
   const int nplanes = P.npass == 3 ? 2 : 1;
   const size_t budget = 227 * 1024 - 2048 - 8192;   // static shared memory: barriers + the epilogue's 8 KB staging buffers
   size_t b_stage = 0;
@@ -395,6 +419,12 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   }
   const size_t smem = (size_t)P.NA * a_stage + (size_t)P.NB * b_stage + 1024;
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  if (f16) {
+    SS2_TRY(make_act_map(ctx, &mA_hi, in.h16, L.CinP, W, H, 1, B, P.P, P.TH + 2, 1, 1, 1, 1, 1, true));
+    SS2_TRY(make_act_map(ctx, &mA_lo, in.l16, L.CinP, W, H, 1, B, P.P, P.TH + 2, 1, 1, 1, 1, 1, true));
+    SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_h16, 9 * L.CinP, L.CoutP, true));
+    SS2_TRY(make_weight_map(ctx, &mB_lo, L.wk_l16, 9 * L.CinP, L.CoutP, true));
+  } else {
   SS2_TRY(make_act_map(ctx, &mA_hi, in.hi, L.CinP, W, H, 1, B, P.P, P.TH + 2, 1, 1, 1, 1, 1));
   SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_hi, 9 * L.CinP, L.CoutP));
   if (P.npass == 3) {
@@ -403,12 +433,15 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   } else {
     mA_lo = mA_hi; mB_lo = mB_hi;
   }
-  static size_t attr_smem_dev[16][4] = {{0}};  // per device: function attributes live in the device's context
+  }
+  static size_t attr_smem_dev[16][8] = {{0}};  // per device: function attributes live in the device's context
   size_t* attr_smem = attr_smem_dev[ctx->device & 15];
-  const int variant = (BN == 128 ? 2 : 0) + (MT == 2 ? 1 : 0);
+  const int variant = (BN == 128 ? 2 : 0) + (MT == 2 ? 1 : 0) + (f16 ? 4 : 0);
   if (smem > attr_smem[variant]) {
     const void* fn = variant == 0 ? (const void*)conv_dc_kernel<64, 1> : variant == 1 ? (const void*)conv_dc_kernel<64, 2>
-                   : variant == 2 ? (const void*)conv_dc_kernel<128, 1> : (const void*)conv_dc_kernel<128, 2>;
+                   : variant == 2 ? (const void*)conv_dc_kernel<128, 1> : variant == 3 ? (const void*)conv_dc_kernel<128, 2>
+                   : variant == 4 ? (const void*)conv_dc_kernel<64, 1, true> : variant == 5 ? (const void*)conv_dc_kernel<64, 2, true>
+                   : (const void*)conv_dc_kernel<128, 1, true>;
     SS2_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem[variant] = smem;
   }
@@ -419,7 +452,10 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   if (variant == 0) conv_dc_kernel<64, 1><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
   else if (variant == 1) conv_dc_kernel<64, 2><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
   else if (variant == 2) conv_dc_kernel<128, 1><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
-  else conv_dc_kernel<128, 2><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  else if (variant == 3) conv_dc_kernel<128, 2><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  else if (variant == 4) conv_dc_kernel<64, 1, true><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  else if (variant == 5) conv_dc_kernel<64, 2, true><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  else conv_dc_kernel<128, 1, true><<<grid, DC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
   ss2_prof_end(ctx, SS2_PROF_CONV, st, flops);
   SS2_LAUNCH_CHECK(ctx);
   return SS2_OK;

@@ -40,6 +40,9 @@ struct StemParams {
   float* out_v;
   float* out_hi;
   float* out_lo;
+  __half* out_h16;   // fp16 split planes for a kind::f16 consumer (conv_dc.cu; may be null)
+  __half* out_l16;
+  int* range_flag;     // raised when a value does not fit fp16 (common.cuh)
   int B, Hc, PH, PW;    // images, conv rows, pooled rows / cols
   int NQ;               // row pairs per image = Hc + 3
   int bp, nbands;       // pooled rows per band, bands per image half
@@ -313,6 +316,7 @@ conv_stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 *reinterpret_cast<float4*>(P.out_hi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
               }
+              if (P.out_h16) store_f16_planes4(P.out_h16, P.out_l16, o, v, P.range_flag);
             }
           }
           __syncwarp();
@@ -346,6 +350,7 @@ int conv_stem_pool_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_x_nch
   StemParams P;
   P.bias = L.bias;
   P.out_v = out.v; P.out_hi = out.hi; P.out_lo = out.lo;
+  P.out_h16 = out.h16; P.out_l16 = out.h16 ? out.l16 : nullptr; P.range_flag = ctx->d_range_flag;
   P.B = B; P.Hc = H / 2; P.PH = H / 4; P.PW = W / 4;
   P.NQ = P.Hc + 3;
   P.npass = ctx->tc_passes == 1 ? 1 : 3;

@@ -45,6 +45,9 @@ struct TcParams {
   float* out_v;           // plain fp32 [M][Cout]
   float* out_hi;          // split planes for the next tensor-core layer (may be null)
   float* out_lo;
+  __half* out_h16;        // fp16 split planes for a kind::f16 consumer (conv_dc.cu; may be null)
+  __half* out_l16;
+  int* range_flag;     // raised when a value does not fit fp16 (common.cuh)
   int B, Do, Ho, Wo, Cout;
   int TN, TT, TH, TW;      // tile extents (images, depth, rows, cols); rows = TN*TT*TH*TW <= 128
   int nN, nT, nH, nW;      // tile counts per dimension
@@ -243,6 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               *reinterpret_cast<float4*>(P.out_hi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
               if (P.out_lo) *reinterpret_cast<float4*>(P.out_lo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
+            if (P.out_h16) store_f16_planes4(P.out_h16, P.out_l16, o, v, P.range_flag);
           }
         }
         __syncwarp();
@@ -281,15 +285,16 @@ void* ss2_tensormap_encode_fn() {
 }
 
 // activation tensor {C, W, H, D, B} (fp32, innermost first) with a box of one output tile
-int make_act_map(ss2_ctx* ctx, CUtensorMap* map, const float* base, int C, int W, int H, int D, int B, int bw,
-                        int bh, int bd, int bn, int sw, int sh, int sd) {
+int make_act_map(ss2_ctx* ctx, CUtensorMap* map, const void* base, int C, int W, int H, int D, int B, int bw,
+                        int bh, int bd, int bn, int sw, int sh, int sd, bool f16) {
+  const cuuint64_t es = f16 ? 2 : 4;   // a 128-byte inner box either way: 32 fp32 or 64 fp16 channels
   EncodeTiledFn fn = encode_fn();
   if (!fn) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
-  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)D * H * W * C * 4};
-  cuuint32_t box[5] = {TC_BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, (cuuint32_t)bn};
+  cuuint64_t strides[4] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es, (cuuint64_t)D * H * W * C * es};
+  cuuint32_t box[5] = {(cuuint32_t)(f16 ? 2 * TC_BK : TC_BK), (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, (cuuint32_t)bn};
   cuuint32_t est[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sd, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, est,
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, strides, box, est,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -298,14 +303,14 @@ int make_act_map(ss2_ctx* ctx, CUtensorMap* map, const float* base, int C, int W
   return SS2_OK;
 }
 
-int make_weight_map(ss2_ctx* ctx, CUtensorMap* map, const float* base, int Ktot, int CoutP) {
+int make_weight_map(ss2_ctx* ctx, CUtensorMap* map, const void* base, int Ktot, int CoutP, bool f16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)CoutP};
-  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
-  cuuint32_t box[2] = {TC_BK, TC_BN};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * (f16 ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(f16 ? 2 * TC_BK : TC_BK), TC_BN};
   cuuint32_t est[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, est,
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, est,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return ss2_fail(ctx, SS2_ERR_CUDA, "cuTensorMapEncodeTiled(weights K=%d N=%d) = %d", Ktot, CoutP, (int)r);
@@ -336,6 +341,7 @@ int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   P.relu = relu; P.bias = L.bias; P.residual = d_residual;
   P.b_act = 0; P.bTH = P.bTW = 0; P.ldo = L.Cout; P.ncol = TC_BN;
   P.out_v = out.v; P.out_hi = out.hi; P.out_lo = out.lo;
+  P.out_h16 = out.h16; P.out_l16 = out.h16 ? out.l16 : nullptr; P.range_flag = ctx->d_range_flag;
   tile_shape(B, P.Do, P.Ho, P.Wo, &P.TN, &P.TT, &P.TH, &P.TW);
   P.nW = cdiv(P.Wo, P.TW); P.nH = cdiv(P.Ho, P.TH); P.nT = cdiv(P.Do, P.TT); P.nN = cdiv(B, P.TN);
   const int npass = (ctx->tc_passes == 1 || !in.lo || !L.wk_lo) ? 1 : 3;
@@ -391,6 +397,7 @@ int conv_tc_stem_launch(ss2_ctx* ctx, const ConvLayer& L, const float* d_hi, con
   P.relu = relu; P.bias = L.bias; P.residual = nullptr;
   P.b_act = 0; P.bTH = P.bTW = 0; P.ldo = L.Cout; P.ncol = TC_BN;
   P.out_v = out.v; P.out_hi = out.hi; P.out_lo = out.lo;
+  P.out_h16 = out.h16; P.out_l16 = out.h16 ? out.l16 : nullptr; P.range_flag = ctx->d_range_flag;
   tile_shape(B, 1, P.Ho, P.Wo, &P.TN, &P.TT, &P.TH, &P.TW);
   P.nW = cdiv(P.Wo, P.TW); P.nH = cdiv(P.Ho, P.TH); P.nT = 1; P.nN = cdiv(B, P.TN);
   const int npass = (ctx->tc_passes == 1 || !d_lo || !L.wk_lo) ? 1 : 3;
@@ -450,6 +457,7 @@ int conv_tc_corr_launch(ss2_ctx* ctx, const ActRef& n1, const ActRef& n2, int B,
   P.sd = P.sh = P.sw = 1; P.pd = 0; P.ph = P.pw = 1;
   P.relu = 0; P.bias = nullptr; P.residual = nullptr;
   P.out_v = d_match; P.out_hi = nullptr; P.out_lo = nullptr;
+  P.out_h16 = P.out_l16 = nullptr; P.range_flag = nullptr;
   tile_shape(1, 1, H, W, &P.TN, &P.TT, &P.TH, &P.TW);  // one sample per tile
   P.nW = cdiv(W, P.TW); P.nH = cdiv(H, P.TH); P.nT = 1; P.nN = B;
   P.b_act = 1; P.bTW = W; P.bTH = conv_tc_corr_rows(W);

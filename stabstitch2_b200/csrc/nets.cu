@@ -111,6 +111,30 @@ static int pack_conv(ss2_ctx* ctx, int net, const std::string& wkey, const std::
       }
     SS2_TRY(upload(ctx, hi, &L->wk_hi));
     SS2_TRY(upload(ctx, lo, &L->wk_lo));
+    // stride-1 3x3 layers (conv_dc.cu) whose input can arrive as fp16 split planes: the same matrix as h16 = fp16(w),
+    // l16 = fp16((w - h16) * 2048), two fp16 values per uploaded float
+    L->wk_h16 = L->wk_l16 = nullptr;
+    float wmax = 0.f;
+    for (float v : wp) wmax = fmaxf(wmax, fabsf(v));
+    if (KD == 1 && KH == 3 && KW == 3 && stride == 1 && pad == 1 && (L->CinP % 64) == 0 && (Cout % 64) == 0 && wmax <= 65504.0f) {
+      const size_t nel = (size_t)L->CoutP * Ktot;   // even: CinP % 64 == 0
+      std::vector<float> ph(nel / 2), pl(nel / 2);
+      __half* h16 = reinterpret_cast<__half*>(ph.data());
+      __half* l16 = reinterpret_cast<__half*>(pl.data());
+      for (size_t k = 0; k < Ktot; ++k)
+        for (int o = 0; o < L->CoutP; ++o) {
+          const float v = wp[k * L->CoutP + o];
+          const float vc = v > 65504.0f ? 65504.0f : (v < -65504.0f ? -65504.0f : v);
+          const __half hh = __float2half_rn(vc);
+          h16[(size_t)o * Ktot + k] = hh;
+          l16[(size_t)o * Ktot + k] = __float2half_rn((v - __half2float(hh)) * 2048.0f);
+        }
+      float *dh = nullptr, *dl = nullptr;
+      SS2_TRY(upload(ctx, ph, &dh));
+      SS2_TRY(upload(ctx, pl, &dl));
+      L->wk_h16 = reinterpret_cast<__half*>(dh);
+      L->wk_l16 = reinterpret_cast<__half*>(dl);
+    }
   }
   L->stem_k32 = false;
   if (flatten_hw == 0 && KD == 1 && KH == 7 && KW == 7 && Cin == 3 && stride == 2 && pad == 3 && (Cout % 4) == 0) {
@@ -291,14 +315,41 @@ static bool runs_on_tc(ss2_ctx* ctx, const ConvLayer& L, bool in_has_split, int 
   return ctx->use_tc && in_has_split && ((ctx->use_dc && conv_dc_eligible(L, 1, H, W)) || conv_tc_eligible(L));
 }
 
+// does the direct 3x3 kernel take this layer with fp16 split planes as its input (kind::f16 MMAs, conv_dc.cu)?
+static bool dc16_ok(ss2_ctx* ctx, const ConvLayer& L, int H, int W) {
+  return ctx->use_f16 && ctx->use_tc && ctx->use_dc && ctx->tc_passes != 1 && L.wk_h16 != nullptr && conv_dc_eligible(L, 1, H, W);
+}
+// a block whose input may arrive as plain values + fp16 split planes: conv1 is such a layer and nothing else reads planes
+static bool block_takes_f16(ss2_ctx* ctx, const ResBlock& b, int H, int W) { return !b.has_down && dc16_ok(ctx, b.c1, H, W); }
+
+// activation with plain values + fp16 split planes (8 bytes per value instead of 12)
+#define ARENA_ACT16(ref, n)                                                                     \
+  ActRef ref;                                                                                   \
+  {                                                                                             \
+    const size_t n__ = ((size_t)(n) + 63) / 64 * 64;                                            \
+    ref.v = arena_alloc<float>(ctx, 2 * n__);                                                   \
+    if (!ref.v) return ss2_fail(ctx, SS2_ERR_OOM, "workspace arena exhausted at %s:%d", __FILE__, __LINE__); \
+    ref.h16 = reinterpret_cast<__half*>(ref.v + n__); ref.l16 = ref.h16 + n__;                  \
+  }
+
+// `next`: the block that consumes this block's output (null: the output's planes are TF32, for any consumer)
 static int run_block(ss2_ctx* ctx, const ResBlock& b, const ActRef& x, int NB, int H, int W, ActRef* out, int* Ho,
-                     int* Wo, cudaStream_t st) {
+                     int* Wo, cudaStream_t st, const ResBlock* next = nullptr) {
   int d, h, w;
   conv_out_dims(b.c1, 1, H, W, &d, &h, &w);
+  const bool c1_f16 = x.hi == nullptr && x.h16 != nullptr;   // (the caller asked the producer for fp16 planes: block_takes_f16)
+  if (c1_f16 && !block_takes_f16(ctx, b, H, W)) return ss2_fail(ctx, SS2_ERR_INVALID, "run_block: fp16 planes for a block that cannot read them");
+  const bool c1_tc = c1_f16 || runs_on_tc(ctx, b.c1, x.hi != nullptr, H, W);
   // conv1's output feeds conv2 only.  When both run on the tensor cores the plain values are never read (v = hi + lo
-  // exactly), so only the split planes are written: a third less store traffic for these layers.
+  // exactly), so only the split planes are written: a third less store traffic for these layers.  When conv2 is a direct
+  // 3x3 layer the planes are fp16 (4 bytes per value instead of 8) and conv2 runs kind::f16 MMAs: half the chunks, stages
+  // and MMA instructions of the TF32 pair.
   ActRef t1;
-  if (runs_on_tc(ctx, b.c1, x.hi != nullptr, H, W) && runs_on_tc(ctx, b.c2, true, h, w)) {
+  if (c1_tc && dc16_ok(ctx, b.c2, h, w)) {
+    const size_t n1 = ((size_t)NB * h * w * b.c1.Cout + 63) / 64 * 64;
+    ARENA(t1h, __half, 2 * n1);
+    t1.h16 = t1h; t1.l16 = t1h + n1;
+  } else if (c1_tc && runs_on_tc(ctx, b.c2, true, h, w)) {
     const size_t n1 = ((size_t)NB * h * w * b.c1.Cout + 63) / 64 * 64;
     ARENA(t1p, float, 2 * n1);
     t1.hi = t1p; t1.lo = t1p + n1;
@@ -315,7 +366,14 @@ static int run_block(ss2_ctx* ctx, const ResBlock& b, const ActRef& x, int NB, i
     SS2_TRY(conv_launch(ctx, b.down, x, NB, 1, H, W, t2v, nullptr, 0, st));
     idt = t2.v;
   }
-  ARENA_ACT(t3, (size_t)NB * h * w * b.c2.Cout);
+  ActRef t3;
+  if (next && block_takes_f16(ctx, *next, h, w) && (t1.h16 || t1.hi)) {
+    ARENA_ACT16(t3h, (size_t)NB * h * w * b.c2.Cout);
+    t3 = t3h;
+  } else {
+    ARENA_ACT(t3f, (size_t)NB * h * w * b.c2.Cout);
+    t3 = t3f;
+  }
   SS2_TRY(conv_launch(ctx, b.c2, t1, NB, 1, h, w, t3, idt, 1, st));
   *out = t3; *Ho = h; *Wo = w;
   return SS2_OK;
@@ -359,20 +417,26 @@ static int run_backbone(ss2_ctx* ctx, const Backbone& bb, const float* x_nchw, i
   if (ctx->use_tc && ctx->use_tc_stem >= 2 && conv_stem_direct_eligible(bb.stem, H, W)) {
     // direct tensor-core stem with the max-pool in its epilogue: the conv map is never written
     ARENA(xw, float, conv_stem_direct_workspace_floats(NB, H));
-    ARENA_ACT(p, (size_t)NB * (H / 4) * (W / 4) * 64);
-    SS2_TRY(conv_stem_pool_launch(ctx, bb.stem, x_nchw, NB, H, W, xw, p, st));
-    cur = p;
     h = H / 4; w = W / 4;
+    if (block_takes_f16(ctx, bb.l1[0], h, w)) {
+      ARENA_ACT16(p, (size_t)NB * h * w * 64);
+      SS2_TRY(conv_stem_pool_launch(ctx, bb.stem, x_nchw, NB, H, W, xw, p, st));
+      cur = p;
+    } else {
+      ARENA_ACT(p, (size_t)NB * h * w * 64);
+      SS2_TRY(conv_stem_pool_launch(ctx, bb.stem, x_nchw, NB, H, W, xw, p, st));
+      cur = p;
+    }
   } else {
     SS2_TRY(run_stem_pool(ctx, bb, x_nchw, NB, H, W, &cur, &h, &w, st));
   }
-  SS2_TRY(run_block(ctx, bb.l1[0], cur, NB, h, w, &cur, &h, &w, st));
-  SS2_TRY(run_block(ctx, bb.l1[1], cur, NB, h, w, &cur, &h, &w, st));
-  SS2_TRY(run_block(ctx, bb.l2[0], cur, NB, h, w, &cur, &h, &w, st));
+  SS2_TRY(run_block(ctx, bb.l1[0], cur, NB, h, w, &cur, &h, &w, st, &bb.l1[1]));
+  SS2_TRY(run_block(ctx, bb.l1[1], cur, NB, h, w, &cur, &h, &w, st, &bb.l2[0]));
+  SS2_TRY(run_block(ctx, bb.l2[0], cur, NB, h, w, &cur, &h, &w, st, &bb.l2[1]));
   SS2_TRY(run_block(ctx, bb.l2[1], cur, NB, h, w, &cur, &h, &w, st));
   *f64 = cur.v; *h64 = h; *w64 = w;
   if (stage2) {
-    SS2_TRY(run_block(ctx, bb.l3[0], cur, NB, h, w, &cur, &h, &w, st));
+    SS2_TRY(run_block(ctx, bb.l3[0], cur, NB, h, w, &cur, &h, &w, st, &bb.l3[1]));
     SS2_TRY(run_block(ctx, bb.l3[1], cur, NB, h, w, &cur, &h, &w, st));
     *f32 = cur.v; *h32 = h; *w32 = w;
   }
@@ -673,6 +737,13 @@ extern "C" int ss2_build_smooth(ss2_ctx* ctx, const float* d_ts1, const float* d
 // generic NHWC / NDHWC convolution primitive (the layer type every network above is built of),
 // exposed for unit tests and reuse.  Synchronous: packs the filter on every call.
 // ------------------------------------------------------------------------------------------
+__global__ void split_f16_kernel(const float* __restrict__ in, size_t n, __half* __restrict__ h, __half* __restrict__ l) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) f16_split(in[i], &h[i], &l[i]);
+}
+__global__ void merge_f16_kernel(const __half* __restrict__ h, const __half* __restrict__ l, size_t n, float* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __half2float(h[i]) + __half2float(l[i]) * (1.0f / SS2_F16_LO_SCALE);
+}
 __global__ void split_tf32_kernel(const float* __restrict__ in, size_t n, float* __restrict__ hi, float* __restrict__ lo) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float h, l;
@@ -690,6 +761,7 @@ extern "C" int ss2_conv_nhwc(ss2_ctx* ctx, const float* d_in, int B, int D, int 
       wshape[1] != Cin || (Cin & 3))
     return ss2_fail(ctx, SS2_ERR_INVALID, "ss2_conv_nhwc: bad arguments (Cin must be a multiple of 4 and match the filter)");
   cudaStream_t st = (cudaStream_t)stream;
+  SS2_TRY(ss2_workspace_enter(ctx, st));
   HostTensor wt, bt;
   wt.shape.assign(wshape, wshape + wndim);
   wt.data.assign(h_weight, h_weight + wt.numel());
@@ -721,6 +793,26 @@ extern "C" int ss2_conv_nhwc(ss2_ctx* ctx, const float* d_in, int B, int D, int 
         in.lo = split + n;
       }
     }
+    // SS2_CONV_TEST_F16 (tests): 1 = the input arrives as fp16 split planes only (kind::f16 kernel), 2 = the output leaves as
+    // fp16 split planes only and is merged back into d_out, 3 = both
+    const int t16 = use_tc && getenv("SS2_CONV_TEST_F16") ? atoi(getenv("SS2_CONV_TEST_F16")) : 0;
+    __half *in16 = nullptr, *out16 = nullptr;
+    size_t on16 = 0;
+    if (rc == SS2_OK && (t16 & 1)) {
+      if (cudaMalloc((void**)&in16, 2 * n * sizeof(__half)) != cudaSuccess) rc = ss2_fail(ctx, SS2_ERR_OOM, "ss2_conv_nhwc: fp16 split buffer");
+      else {
+        split_f16_kernel<<<592, 256, 0, st>>>(d_in, n, in16, in16 + n);
+        in.v = nullptr; in.hi = in.lo = nullptr;
+        in.h16 = in16; in.l16 = in16 + n;
+      }
+    }
+    if (rc == SS2_OK && (t16 & 2)) {
+      int od, oh, ow;
+      conv_out_dims(L, D, H, W, &od, &oh, &ow);
+      on16 = (size_t)B * od * oh * ow * L.Cout;
+      if (cudaMalloc((void**)&out16, 2 * on16 * sizeof(__half)) != cudaSuccess) rc = ss2_fail(ctx, SS2_ERR_OOM, "ss2_conv_nhwc: fp16 output buffer");
+      else { out.v = nullptr; out.h16 = out16; out.l16 = out16 + on16; }
+    }
     // SS2_CONV_TEST_SPLIT=1 (profiles/conv_bench.py): also write the hi/lo planes like a layer inside the networks does
     float* osplit = nullptr;
     if (rc == SS2_OK && use_tc && getenv("SS2_CONV_TEST_SPLIT") && atoi(getenv("SS2_CONV_TEST_SPLIT"))) {
@@ -730,9 +822,12 @@ extern "C" int ss2_conv_nhwc(ss2_ctx* ctx, const float* d_in, int B, int D, int 
       if (cudaMalloc((void**)&osplit, 2 * on * sizeof(float)) == cudaSuccess) { out.hi = osplit; out.lo = osplit + on; }
     }
     if (rc == SS2_OK) rc = conv_launch(ctx, L, in, B, D, H, W, out, d_residual, relu, st);
+    if (rc == SS2_OK && out16) merge_f16_kernel<<<592, 256, 0, st>>>(out16, out16 + on16, on16, d_out);
     ctx->use_tc = saved;
     cudaStreamSynchronize(st);
     if (osplit) cudaFree(osplit);
+    if (in16) cudaFree(in16);
+    if (out16) cudaFree(out16);
   }
   cudaStreamSynchronize(st);
   if (split) cudaFree(split);

@@ -111,6 +111,21 @@ __device__ __forceinline__ void dc_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t 
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with fp16 operands (K = 16 per instruction: the same 32 bytes of a K-major row)
+__device__ __forceinline__ void dc_mma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t dc_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 // high word of the K-major SWIZZLE_128B descriptor: SBO = 1024 B, version 1, swizzle mode 2 (see umma_desc_sw128)
 #define DC_DESC_HI ((uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29))
@@ -118,6 +133,6 @@ __device__ __forceinline__ uint32_t dc_desc_lo(uint32_t smem_addr) { return ((sm
 
 // host: tensor maps (conv_tc.cu).  Activations {C, W, H, D, B} with a box {32, bw, bh, bd, bn} and element strides
 // (traversal strides) {1, sw, sh, sd, 1}; K-major filter matrix [CoutP][Ktot] with a box {32, 64}.  SWIZZLE_128B.
-int make_act_map(ss2_ctx* ctx, CUtensorMap* map, const float* base, int C, int W, int H, int D, int B, int bw, int bh,
-                 int bd, int bn, int sw, int sh, int sd);
-int make_weight_map(ss2_ctx* ctx, CUtensorMap* map, const float* base, int Ktot, int CoutP);
+int make_act_map(ss2_ctx* ctx, CUtensorMap* map, const void* base, int C, int W, int H, int D, int B, int bw, int bh,
+                 int bd, int bn, int sw, int sh, int sd, bool f16 = false);
+int make_weight_map(ss2_ctx* ctx, CUtensorMap* map, const void* base, int Ktot, int CoutP, bool f16 = false);

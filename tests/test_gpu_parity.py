@@ -890,6 +890,50 @@ def test_conv_dc_every_tile_plan(shape, monkeypatch):
     assert ran >= 5
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("shape", [(2, 11, 37, 64, 64), (1, 23, 30, 256, 256), (3, 9, 60, 128, 128), (2, 90, 120, 64, 64)])
+def test_conv_dc_f16_planes(shape, mode, monkeypatch):
+    """the fp16-plane path of the direct 3x3 kernel (h16 = fp16(v), l16 = fp16((v - h16) * 2048); kind::f16 MMAs with the
+    correction products in a 2048-scaled accumulator) against the PyTorch fp64 reference, at the accuracy asked of the
+    split-TF32 path: mode 1 = fp16 planes in, 2 = fp16 planes out (merged back), 3 = both; with residual, bias, ReLU.
+    Inputs span six orders of magnitude so that values below fp16's normal range are covered by the scaled low plane."""
+    from stabstitch2_b200 import _lib
+    B, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(B * 1000 + W + mode)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    x = x * torch.pow(10.0, torch.randint(-5, 2, (B, H, W, 1), generator=g).float())   # per-pixel scales 1e-5 .. 10
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn(B, H, W, Cout, generator=g)
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), 1, 1).permute(0, 2, 3, 1)
+    ref = torch.relu(ref + res.double()).float()
+    monkeypatch.delenv("SS2_DC_PLAN", raising=False)
+    base = _lib.conv_nhwc(x.cuda(), w, b, stride=1, pad=1, relu=True, residual=res.cuda(), use_tc=True).cpu()
+    monkeypatch.setenv("SS2_CONV_TEST_F16", str(mode))
+    out = _lib.conv_nhwc(x.cuda(), w, b, stride=1, pad=1, relu=True, residual=res.cuda(), use_tc=True).cpu()
+    scale = ref.abs().max().item()
+    err, err_base = (out - ref).abs().max().item(), (base - ref).abs().max().item()
+    assert err < 1e-4 * max(scale, 1.0), (err, err_base, scale)
+    assert err < 4 * err_base + 1e-6 * max(scale, 1.0), (err, err_base)    # no worse than the split-TF32 kernel's own error
+
+
+def test_f16_planes_range_overflow_fails_loudly(monkeypatch):
+    """an activation beyond fp16's range (|v| > 65504) written to the fp16 split planes raises the context's range flag: the
+    next entry point reports it (once) instead of handing out clamped values silently"""
+    from stabstitch2_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 8, 16, 64, generator=g)
+    w = torch.randn(64, 64, 3, 3, generator=g) / 24.0
+    ok = _lib.conv_nhwc(x.cuda(), w, None, stride=1, pad=1, use_tc=True).cpu()
+    monkeypatch.setenv("SS2_CONV_TEST_F16", "2")
+    _lib.conv_nhwc((x * 1e6).cuda(), w, None, stride=1, pad=1, use_tc=True)     # outputs ~1e6: do not fit
+    monkeypatch.delenv("SS2_CONV_TEST_F16")
+    with pytest.raises(_lib.SS2Error, match="fp16 range"):
+        _lib.conv_nhwc(x.cuda(), w, None, stride=1, pad=1, use_tc=True)
+    again = _lib.conv_nhwc(x.cuda(), w, None, stride=1, pad=1, use_tc=True).cpu()   # reported once, the context works on
+    assert torch.equal(ok, again)
+
+
 @pytest.mark.parametrize("B,H", [(1, 8), (2, 44), (3, 360), (33, 360)])
 def test_stem_pool_direct_vs_torch(B, H):
     """the fused direct stem kernel (conv 7x7 s2 + bias + ReLU + max-pool 3x3 s2 in one tcgen05 kernel) against a plain
