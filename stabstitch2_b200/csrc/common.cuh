@@ -58,6 +58,7 @@ struct ActRef {
   float* lo = nullptr;
   __half* h16 = nullptr;
   __half* l16 = nullptr;
+  int* flag = nullptr;   // fp16 range flag of the context (set with h16 / l16), raised by store_split* on overflow
 };
 
 struct ResBlock {
@@ -159,7 +160,7 @@ struct ss2_ctx {
   // SS2_F16=0: TF32 split planes everywhere.  Default: the stride-1 3x3 layers of the ResNet bodies read fp16 split planes
   // and run kind::f16 MMAs (conv_dc.cu); their producers' epilogues write those planes.  fp16 holds |v| <= 65504: an
   // epilogue that meets a larger value raises *range_flag (mapped pinned host memory); the next entry point fails loudly.
-  int use_f16 = 1;
+  int use_f16 = 3;   // bit 0: the direct 3x3 kernel, bit 1: the implicit-GEMM kernel (stride-2 entries, shortcuts, Conv3d, CCL)
   int* h_range_flag = nullptr;   // host view
   int* d_range_flag = nullptr;   // device view of the same word
   int use_dc = 1;     // direct 3x3 kernel (conv_dc.cu) for eligible layers; SS2_CONV_DC=0 disables
@@ -238,6 +239,10 @@ __device__ __forceinline__ void store_split4(const ActRef& o, size_t idx, float4
     *reinterpret_cast<float4*>(o.hi + idx) = h;
     if (o.lo) *reinterpret_cast<float4*>(o.lo + idx) = l;
   }
+  if (o.h16) {
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    store_f16_planes4(o.h16, o.l16, idx, vv, o.flag);
+  }
 }
 __device__ __forceinline__ void store_split1(const ActRef& o, size_t idx, float v) {
   o.v[idx] = v;
@@ -246,6 +251,10 @@ __device__ __forceinline__ void store_split1(const ActRef& o, size_t idx, float 
     tf32_split(v, &h, &l);
     o.hi[idx] = h;
     if (o.lo) o.lo[idx] = l;
+  }
+  if (o.h16) {
+    if (fabsf(v) > 65504.0f) *o.flag = 1;
+    f16_split(v, &o.h16[idx], &o.l16[idx]);
   }
 }
 #endif

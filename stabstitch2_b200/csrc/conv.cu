@@ -331,9 +331,9 @@ int conv_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, int D
   if ((L.CinP & 3) || (L.CoutP & 63)) return ss2_fail(ctx, SS2_ERR_INVALID, "conv: unpadded layer");
   if (groups == 1 && ctx->use_tc && ctx->use_dc && (in.hi || in.h16) && conv_dc_eligible(L, D, H, W))
     return conv_dc_launch(ctx, L, in, B, H, W, out, d_residual, relu, st);
-  if (!in.v && !in.hi) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv: fp16 split planes are read by the direct 3x3 kernel only");
-  if (groups == 1 && ctx->use_tc && in.hi && conv_tc_eligible(L))
+  if (groups == 1 && ctx->use_tc && (in.hi || in.h16) && conv_tc_eligible(L))
     return conv_tc_launch(ctx, L, in, B, D, H, W, out, d_residual, relu, st);
+  if (!in.v) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv: split planes without plain values are read by the tcgen05 kernels only");
   if (groups == 1 && L.KD * L.KH * L.KW == 1 && D * H * W == 1 && !d_residual && !out.hi && L.sh == 1 && L.ph == 0) {
     ss2_prof_begin(ctx, SS2_PROF_CONV, st);
     const bool done = linear_smallm_try(ctx, L, in.v, B, out.v, relu, st);

@@ -67,12 +67,15 @@ __host__ __device__ constexpr uint32_t tc_idesc() {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-template <int NPASS, int STAGES>
+// F16 (with NPASS == 3): the operands are fp16 split planes and the MMAs kind::f16, exactly as in conv_dc.cu: a 128-byte
+// row is 64 channels, K = 16 per instruction, A_l x B_h accumulates into the 2048-scaled D2, the epilogue takes D1 + D2 / 2048.
+template <int NPASS, int STAGES, bool F16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams P) {
   constexpr int NOPER = NPASS == 3 ? 2 : 1;  // operand planes per matrix (hi [, lo])
   constexpr int STAGE_BYTES = NOPER * (TC_A_BYTES + TC_B_BYTES);
+  constexpr int BKC = F16 ? 2 * TC_BK : TC_BK;   // channels per chunk (one 128-byte row)
   // split TF32 in TWO MMAs per k-step (see conv_dc.cu): B_hi | B_lo of a stage are adjacent, so A_hi x [B_hi | B_lo] is
   // one N = 128 MMA into accumulator columns [D1 | D2] and A_lo x B_hi an N = 64 one into D1; the epilogue adds D1 + D2
   constexpr int TC_ACC_COLS = NPASS == 3 ? 2 * TC_BN : TC_BN;
@@ -124,13 +127,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], tx_bytes);
-          tma_load_5d(st, &tmA_hi, &full_bar[s], ck * TC_BK, cw, ch, cd, n0);
-          if (P.b_act) tma_load_5d(st + NOPER * TC_A_BYTES, &tmB_hi, &full_bar[s], ck * TC_BK, kw - P.pw, bh0 + kh - P.ph, 0, n0);
-          else tma_load_2d(st + NOPER * TC_A_BYTES, &tmB_hi, &full_bar[s], tap * P.CinP + ck * TC_BK, cout0);
+          tma_load_5d(st, &tmA_hi, &full_bar[s], ck * BKC, cw, ch, cd, n0);
+          if (P.b_act) tma_load_5d(st + NOPER * TC_A_BYTES, &tmB_hi, &full_bar[s], ck * BKC, kw - P.pw, bh0 + kh - P.ph, 0, n0);
+          else tma_load_2d(st + NOPER * TC_A_BYTES, &tmB_hi, &full_bar[s], tap * P.CinP + ck * BKC, cout0);
           if (NPASS == 3) {
-            tma_load_5d(st + TC_A_BYTES, &tmA_lo, &full_bar[s], ck * TC_BK, cw, ch, cd, n0);
-            if (P.b_act) tma_load_5d(st + NOPER * TC_A_BYTES + TC_B_BYTES, &tmB_lo, &full_bar[s], ck * TC_BK, kw - P.pw, bh0 + kh - P.ph, 0, n0);
-            else tma_load_2d(st + NOPER * TC_A_BYTES + TC_B_BYTES, &tmB_lo, &full_bar[s], tap * P.CinP + ck * TC_BK, cout0);
+            tma_load_5d(st + TC_A_BYTES, &tmA_lo, &full_bar[s], ck * BKC, cw, ch, cd, n0);
+            if (P.b_act) tma_load_5d(st + NOPER * TC_A_BYTES + TC_B_BYTES, &tmB_lo, &full_bar[s], ck * BKC, kw - P.pw, bh0 + kh - P.ph, 0, n0);
+            else tma_load_2d(st + NOPER * TC_A_BYTES + TC_B_BYTES, &tmB_lo, &full_bar[s], tap * P.CinP + ck * BKC, cout0);
           }
         }
       }
@@ -138,8 +141,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer (one elected thread; descriptors advanced with 32-bit adds, see tc_common.cuh) =====
     if (dc_elect_one()) {
-      const uint32_t idesc = tc_idesc();
-      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      constexpr uint32_t FMT = F16 ? 0u : ((2u << 7) | (2u << 10));   // kind::f16: A/B format 0 = fp16
+      const uint32_t idesc = (1u << 4) | FMT | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | FMT | ((uint32_t)(2 * TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int it = 0; it < niter; ++it) {
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
@@ -148,7 +152,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const uint32_t b_hi = a_hi + ((NOPER * TC_A_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
-          if (NPASS == 3) {
+          if (NPASS == 3 && F16) {
+            dc_mma_f16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, DC_DESC_HI, idesc2, (it > 0 || k > 0) ? 1u : 0u);
+            dc_mma_f16(tmem_base + TC_BN, a_hi + (TC_A_BYTES >> 4) + 2 * k, b_hi + 2 * k, DC_DESC_HI, idesc, 1u);   // scaled: into D2
+          } else if (NPASS == 3) {
             dc_mma(tmem_base, a_hi + 2 * k, b_hi + 2 * k, DC_DESC_HI, idesc2, (it > 0 || k > 0) ? 1u : 0u);
             dc_mma(tmem_base, a_hi + (TC_A_BYTES >> 4) + 2 * k, b_hi + 2 * k, DC_DESC_HI, idesc, 1u);
           } else {
@@ -209,7 +216,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         uint32_t acc2[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TC_BN + half * 32, acc2);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
+        for (int j = 0; j < 32; ++j)
+          acc[j] = __float_as_uint(F16 ? fmaf(__uint_as_float(acc2[j]), 1.0f / SS2_F16_LO_SCALE, __uint_as_float(acc[j]))
+                                       : __uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
       }
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
@@ -336,7 +345,10 @@ int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   TcParams P;
   conv_out_dims(L, D, H, W, &P.Do, &P.Ho, &P.Wo);
   P.B = B; P.Cout = L.Cout; P.CinP = L.CinP;
-  P.KD = L.KD; P.KH = L.KH; P.KW = L.KW; P.nchunk = L.CinP / TC_BK;
+  const bool f16 = in.h16 != nullptr && in.hi == nullptr;   // fp16 split planes in: kind::f16 MMAs
+  if (f16 && (!in.l16 || !L.wk_h16 || !L.wk_l16 || (L.CinP % 64) != 0 || ctx->tc_passes == 1))
+    return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_tc: fp16 planes given to a layer without fp16 filter planes");
+  P.KD = L.KD; P.KH = L.KH; P.KW = L.KW; P.nchunk = L.CinP / (f16 ? 2 * TC_BK : TC_BK);
   P.sd = L.sd; P.sh = L.sh; P.sw = L.sw; P.pd = L.pd; P.ph = L.ph; P.pw = L.pw;
   P.relu = relu; P.bias = L.bias; P.residual = d_residual;
   P.b_act = 0; P.bTH = P.bTW = 0; P.ldo = L.Cout; P.ncol = TC_BN;
@@ -344,10 +356,16 @@ int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   P.out_h16 = out.h16; P.out_l16 = out.h16 ? out.l16 : nullptr; P.range_flag = ctx->d_range_flag;
   tile_shape(B, P.Do, P.Ho, P.Wo, &P.TN, &P.TT, &P.TH, &P.TW);
   P.nW = cdiv(P.Wo, P.TW); P.nH = cdiv(P.Ho, P.TH); P.nT = cdiv(P.Do, P.TT); P.nN = cdiv(B, P.TN);
-  const int npass = (ctx->tc_passes == 1 || !in.lo || !L.wk_lo) ? 1 : 3;
+  const int npass = f16 ? 3 : (ctx->tc_passes == 1 || !in.lo || !L.wk_lo) ? 1 : 3;
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   const int bw = (P.TW - 1) * L.sw + 1, bh = (P.TH - 1) * L.sh + 1, bd = (P.TT - 1) * L.sd + 1;
   if (bw > 256 || bh > 256 || bd > 256) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_tc: TMA box too large");
+  if (f16) {
+    SS2_TRY(make_act_map(ctx, &mA_hi, in.h16, L.CinP, W, H, D, B, bw, bh, bd, P.TN, L.sw, L.sh, L.sd, true));
+    SS2_TRY(make_act_map(ctx, &mA_lo, in.l16, L.CinP, W, H, D, B, bw, bh, bd, P.TN, L.sw, L.sh, L.sd, true));
+    SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_h16, L.KD * L.KH * L.KW * L.CinP, L.CoutP, true));
+    SS2_TRY(make_weight_map(ctx, &mB_lo, L.wk_l16, L.KD * L.KH * L.KW * L.CinP, L.CoutP, true));
+  } else {
   SS2_TRY(make_act_map(ctx, &mA_hi, in.hi, L.CinP, W, H, D, B, bw, bh, bd, P.TN, L.sw, L.sh, L.sd));
   SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_hi, L.KD * L.KH * L.KW * L.CinP, L.CoutP));
   if (npass == 3) {
@@ -356,10 +374,18 @@ int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
   } else {
     mA_lo = mA_hi; mB_lo = mB_hi;
   }
+  }
   dim3 grid(P.nW * P.nH * P.nT * P.nN, L.CoutP / TC_BN);
   const double flops = 2.0 * B * P.Do * P.Ho * P.Wo * (double)L.Cout * L.KD * L.KH * L.KW * L.Cin;
   ss2_prof_begin(ctx, SS2_PROF_CONV, st);
-  if (npass == 3) {
+  if (f16) {
+    constexpr int STAGES = TC_STAGES3;
+    const size_t smem = (size_t)STAGES * 2 * (TC_A_BYTES + TC_B_BYTES) + 1024;
+    static bool attr16_dev[16] = {false};
+    bool& attr16 = attr16_dev[ctx->device & 15];
+    if (!attr16) { SS2_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<3, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr16 = true; }
+    conv_tc_kernel<3, STAGES, true><<<grid, TC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  } else if (npass == 3) {
     constexpr int STAGES = TC_STAGES3;
     const size_t smem = (size_t)STAGES * 2 * (TC_A_BYTES + TC_B_BYTES) + 1024;
     static bool attr3_dev[16] = {false};  // per device: function attributes live in the device's context
@@ -451,9 +477,12 @@ int conv_tc_corr_rows(int W) {
 int conv_tc_corr_launch(ss2_ctx* ctx, const ActRef& n1, const ActRef& n2, int B, int H, int W, int C, float* d_match,
                         int ldo, cudaStream_t st) {
   if ((C % TC_BK) != 0 || W > 64 || (ldo & 3)) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_tc_corr: unsupported shape");
+  const bool f16 = n1.h16 != nullptr && n1.hi == nullptr;   // both maps as fp16 split planes
+  if (f16 && (!n1.l16 || !n2.h16 || !n2.l16 || (C % 64) != 0 || ctx->tc_passes == 1))
+    return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_tc_corr: incomplete fp16 planes");
   TcParams P;
   P.B = B; P.Do = 1; P.Ho = H; P.Wo = W; P.Cout = H * W; P.CinP = C;
-  P.KD = 1; P.KH = 3; P.KW = 3; P.nchunk = C / TC_BK;
+  P.KD = 1; P.KH = 3; P.KW = 3; P.nchunk = C / (f16 ? 2 * TC_BK : TC_BK);
   P.sd = P.sh = P.sw = 1; P.pd = 0; P.ph = P.pw = 1;
   P.relu = 0; P.bias = nullptr; P.residual = nullptr;
   P.out_v = d_match; P.out_hi = nullptr; P.out_lo = nullptr;
@@ -464,8 +493,14 @@ int conv_tc_corr_launch(ss2_ctx* ctx, const ActRef& n1, const ActRef& n2, int B,
   if (P.bTH < 1) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_tc_corr: no aligned N tile for W=%d", W);
   P.ncol = P.bTH * P.bTW; P.ldo = ldo;
   if (P.TW != W || P.nW != 1) return ss2_fail(ctx, SS2_ERR_UNSUPPORTED, "conv_tc_corr: feature map too wide");
-  const int npass = (ctx->tc_passes == 1 || !n1.lo || !n2.lo) ? 1 : 3;
+  const int npass = f16 ? 3 : (ctx->tc_passes == 1 || !n1.lo || !n2.lo) ? 1 : 3;
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  if (f16) {
+    SS2_TRY(make_act_map(ctx, &mA_hi, n1.h16, C, W, H, 1, B, P.TW, P.TH, 1, 1, 1, 1, 1, true));
+    SS2_TRY(make_act_map(ctx, &mB_hi, n2.h16, C, W, H, 1, B, P.bTW, P.bTH, 1, 1, 1, 1, 1, true));
+    SS2_TRY(make_act_map(ctx, &mA_lo, n1.l16, C, W, H, 1, B, P.TW, P.TH, 1, 1, 1, 1, 1, true));
+    SS2_TRY(make_act_map(ctx, &mB_lo, n2.l16, C, W, H, 1, B, P.bTW, P.bTH, 1, 1, 1, 1, 1, true));
+  } else {
   SS2_TRY(make_act_map(ctx, &mA_hi, n1.hi, C, W, H, 1, B, P.TW, P.TH, 1, 1, 1, 1, 1));
   SS2_TRY(make_act_map(ctx, &mB_hi, n2.hi, C, W, H, 1, B, P.bTW, P.bTH, 1, 1, 1, 1, 1));
   if (npass == 3) {
@@ -474,9 +509,15 @@ int conv_tc_corr_launch(ss2_ctx* ctx, const ActRef& n1, const ActRef& n2, int B,
   } else {
     mA_lo = mA_hi; mB_lo = mB_hi;
   }
+  }
   dim3 grid(P.nH * B, cdiv(H, P.bTH));
   ss2_prof_begin(ctx, SS2_PROF_CONV, st);
-  if (npass == 3) {
+  if (f16) {
+    constexpr int STAGES = TC_STAGES3;
+    const size_t smem = (size_t)STAGES * 2 * (TC_A_BYTES + TC_B_BYTES) + 1024;
+    SS2_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<3, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<3, STAGES, true><<<grid, TC_THREADS, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, P);
+  } else if (npass == 3) {
     constexpr int STAGES = TC_STAGES3;
     const size_t smem = (size_t)STAGES * 2 * (TC_A_BYTES + TC_B_BYTES) + 1024;
     SS2_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<3, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -274,12 +274,16 @@ int ccl_launch(ss2_ctx* ctx, const float* d_f1, const float* d_f2, int B, int H,
   const int KP = (HW + 63) / 64 * 64;
   const bool tc = ctx->use_tc && (C % 32) == 0 && W <= 64 && conv_tc_corr_rows(W) >= 1;
   const size_t nact = ((size_t)B * HW * C + 63) / 64 * 64;
+  const bool f16 = tc && (ctx->use_f16 & 2) && ctx->tc_passes != 1 && (C % 64) == 0;   // fp16 split planes, kind::f16 correlation
   ActRef n1, n2;
-  n1.v = arena_alloc<float>(ctx, (tc ? 3 : 1) * nact);
-  n2.v = arena_alloc<float>(ctx, (tc ? 3 : 1) * nact);
+  n1.v = arena_alloc<float>(ctx, (f16 ? 2 : tc ? 3 : 1) * nact);
+  n2.v = arena_alloc<float>(ctx, (f16 ? 2 : tc ? 3 : 1) * nact);
   float* match = arena_alloc<float>(ctx, (size_t)B * HW * KP);
   if (!n1.v || !n2.v || !match) return ss2_fail(ctx, SS2_ERR_OOM, "ccl: workspace arena exhausted");
-  if (tc) { n1.hi = n1.v + nact; n1.lo = n1.v + 2 * nact; n2.hi = n2.v + nact; n2.lo = n2.v + 2 * nact; }
+  if (f16) {
+    n1.h16 = reinterpret_cast<__half*>(n1.v + nact); n1.l16 = n1.h16 + nact; n1.flag = ctx->d_range_flag;
+    n2.h16 = reinterpret_cast<__half*>(n2.v + nact); n2.l16 = n2.h16 + nact; n2.flag = ctx->d_range_flag;
+  } else if (tc) { n1.hi = n1.v + nact; n1.lo = n1.v + 2 * nact; n2.hi = n2.v + nact; n2.lo = n2.v + 2 * nact; }
   l2norm_nhwc_kernel<<<cdiv(B * HW, 8), 256, 0, st>>>(d_f1, B * HW, C, n1);
   SS2_LAUNCH_CHECK(ctx);
   l2norm_nhwc_kernel<<<cdiv(B * HW, 8), 256, 0, st>>>(d_f2, B * HW, C, n2);

@@ -111,12 +111,12 @@ static int pack_conv(ss2_ctx* ctx, int net, const std::string& wkey, const std::
       }
     SS2_TRY(upload(ctx, hi, &L->wk_hi));
     SS2_TRY(upload(ctx, lo, &L->wk_lo));
-    // stride-1 3x3 layers (conv_dc.cu) whose input can arrive as fp16 split planes: the same matrix as h16 = fp16(w),
+    // layers whose input can arrive as fp16 split planes (conv_dc.cu, conv_tc.cu): the same matrix as h16 = fp16(w),
     // l16 = fp16((w - h16) * 2048), two fp16 values per uploaded float
     L->wk_h16 = L->wk_l16 = nullptr;
     float wmax = 0.f;
     for (float v : wp) wmax = fmaxf(wmax, fabsf(v));
-    if (KD == 1 && KH == 3 && KW == 3 && stride == 1 && pad == 1 && (L->CinP % 64) == 0 && (Cout % 64) == 0 && wmax <= 65504.0f) {
+    if ((L->CinP % 64) == 0 && (Cout % 64) == 0 && wmax <= 65504.0f) {
       const size_t nel = (size_t)L->CoutP * Ktot;   // even: CinP % 64 == 0
       std::vector<float> ph(nel / 2), pl(nel / 2);
       __half* h16 = reinterpret_cast<__half*>(ph.data());
@@ -317,10 +317,21 @@ static bool runs_on_tc(ss2_ctx* ctx, const ConvLayer& L, bool in_has_split, int 
 
 // does the direct 3x3 kernel take this layer with fp16 split planes as its input (kind::f16 MMAs, conv_dc.cu)?
 static bool dc16_ok(ss2_ctx* ctx, const ConvLayer& L, int H, int W) {
-  return ctx->use_f16 && ctx->use_tc && ctx->use_dc && ctx->tc_passes != 1 && L.wk_h16 != nullptr && conv_dc_eligible(L, 1, H, W);
+  return (ctx->use_f16 & 1) && ctx->use_tc && ctx->use_dc && ctx->tc_passes != 1 && L.wk_h16 != nullptr && conv_dc_eligible(L, 1, H, W);
 }
-// a block whose input may arrive as plain values + fp16 split planes: conv1 is such a layer and nothing else reads planes
-static bool block_takes_f16(ss2_ctx* ctx, const ResBlock& b, int H, int W) { return !b.has_down && dc16_ok(ctx, b.c1, H, W); }
+// ... or the implicit-GEMM kernel (conv_tc.cu: stride-2 entries, 1x1 shortcuts, Conv3d, maps too small for the direct kernel)?
+static bool tc16_ok(ss2_ctx* ctx, const ConvLayer& L) {
+  return (ctx->use_f16 & 2) && ctx->use_tc && ctx->tc_passes != 1 && L.wk_h16 != nullptr && conv_tc_eligible(L);
+}
+// the kernel conv_launch picks for this layer reads fp16 planes
+static bool layer16_ok(ss2_ctx* ctx, const ConvLayer& L, int H, int W) {
+  if (ctx->use_tc && ctx->use_dc && conv_dc_eligible(L, 1, H, W)) return dc16_ok(ctx, L, H, W);
+  return tc16_ok(ctx, L);
+}
+// a block whose input may arrive as plain values + fp16 split planes: every layer that reads the input's planes takes them
+static bool block_takes_f16(ss2_ctx* ctx, const ResBlock& b, int H, int W) {
+  return layer16_ok(ctx, b.c1, H, W) && (!b.has_down || layer16_ok(ctx, b.down, H, W));
+}
 
 // activation with plain values + fp16 split planes (8 bytes per value instead of 12)
 #define ARENA_ACT16(ref, n)                                                                     \
@@ -330,6 +341,18 @@ static bool block_takes_f16(ss2_ctx* ctx, const ResBlock& b, int H, int W) { ret
     ref.v = arena_alloc<float>(ctx, 2 * n__);                                                   \
     if (!ref.v) return ss2_fail(ctx, SS2_ERR_OOM, "workspace arena exhausted at %s:%d", __FILE__, __LINE__); \
     ref.h16 = reinterpret_cast<__half*>(ref.v + n__); ref.l16 = ref.h16 + n__;                  \
+    ref.flag = ctx->d_range_flag;                                                               \
+  }
+// the one or the other
+#define ARENA_ACT_SEL(ref, n, f16)                                                              \
+  ActRef ref;                                                                                   \
+  {                                                                                             \
+    const size_t n__ = ((size_t)(n) + 63) / 64 * 64;                                            \
+    const bool f__ = (f16);                                                                     \
+    ref.v = arena_alloc<float>(ctx, (f__ ? 2 : (ctx->use_tc ? 3 : 1)) * n__);                   \
+    if (!ref.v) return ss2_fail(ctx, SS2_ERR_OOM, "workspace arena exhausted at %s:%d", __FILE__, __LINE__); \
+    if (f__) { ref.h16 = reinterpret_cast<__half*>(ref.v + n__); ref.l16 = ref.h16 + n__; ref.flag = ctx->d_range_flag; } \
+    else if (ctx->use_tc) { ref.hi = ref.v + n__; ref.lo = ref.v + 2 * n__; }                   \
   }
 
 // `next`: the block that consumes this block's output (null: the output's planes are TF32, for any consumer)
@@ -345,7 +368,7 @@ static int run_block(ss2_ctx* ctx, const ResBlock& b, const ActRef& x, int NB, i
   // 3x3 layer the planes are fp16 (4 bytes per value instead of 8) and conv2 runs kind::f16 MMAs: half the chunks, stages
   // and MMA instructions of the TF32 pair.
   ActRef t1;
-  if (c1_tc && dc16_ok(ctx, b.c2, h, w)) {
+  if (c1_tc && layer16_ok(ctx, b.c2, h, w)) {
     const size_t n1 = ((size_t)NB * h * w * b.c1.Cout + 63) / 64 * 64;
     ARENA(t1h, __half, 2 * n1);
     t1.h16 = t1h; t1.l16 = t1h + n1;
@@ -450,14 +473,32 @@ static int run_regressor(ss2_ctx* ctx, const Regressor& r, const ActRef& x, int 
   int h = H, w = W;
   for (size_t i = 0; i < r.convs.size(); ++i) {
     const ConvLayer& L = r.convs[i];
-    ARENA_ACT(t, (size_t)NB * h * w * L.Cout);
+    const bool last = i + 1 == r.convs.size();
+    const int hn = r.pool_after[i] ? h / 2 : h, wn = r.pool_after[i] ? w / 2 : w;   // the next layer's input size
+    const bool next16 = !last && layer16_ok(ctx, r.convs[i + 1], hn, wn);           // it reads fp16 split planes
+    // this layer runs a tcgen05 kernel (their epilogues write whichever planes are asked for, plain values optional)
+    const bool tc = runs_on_tc(ctx, L, cur.hi != nullptr, h, w) || (cur.h16 != nullptr && layer16_ok(ctx, L, h, w));
+    const size_t nel = (size_t)NB * h * w * L.Cout;
+    ActRef t;
+    if (tc && (r.pool_after[i] || last)) {
+      // read by the pooling kernel / the Linear head through its plain values only: no split planes are written
+      ARENA(tv, float, nel);
+      t.v = tv;
+    } else if (tc && next16) {
+      // read by the next direct 3x3 layer through its fp16 planes only
+      const size_t n1 = (nel + 63) / 64 * 64;
+      ARENA(th, __half, 2 * n1);
+      t.h16 = th; t.l16 = th + n1; t.flag = ctx->d_range_flag;
+    } else {
+      ARENA_ACT(tf, nel);
+      t = tf;
+    }
     SS2_TRY(conv_launch(ctx, L, cur, NB, 1, h, w, t, nullptr, 1, st));
     cur = t;
     if (r.pool_after[i]) {
-      const int hp = h / 2, wp = w / 2;
-      ARENA_ACT(q, (size_t)NB * hp * wp * L.Cout);
+      ARENA_ACT_SEL(q, (size_t)NB * hn * wn * L.Cout, next16);
       SS2_TRY(maxpool_launch(ctx, cur.v, NB, h, w, L.Cout, 2, 2, 0, q, st));
-      cur = q; h = hp; w = wp;
+      cur = q; h = hn; w = wn;
     }
   }
   const int feat = h * w * r.convs.back().Cout;
@@ -502,8 +543,8 @@ static int spatial_chunk(ss2_ctx* ctx, const float* img1, const float* img2, int
   SS2_TRY(homo_warp_nhwc_launch(ctx, f64, theta, 2 * bs, 128, h64, w64, warped, st));
   // stage 2: two local cost volumes -> two mesh regressors
   const size_t half = (size_t)bs * h64 * w64 * 128;
-  ARENA_ACT(cv_ref, half);
-  ARENA_ACT(cv_tgt, half);
+  ARENA_ACT_SEL(cv_ref, half, layer16_ok(ctx, S.r2_ref.convs[0], h64, w64));   // fp16 planes when the regressor's first layer reads them
+  ARENA_ACT_SEL(cv_tgt, half, layer16_ok(ctx, S.r2_tgt.convs[0], h64, w64));
   SS2_TRY(cost_volume_launch(ctx, warped, warped + half, bs, h64, w64, 128, 5, 128, cv_ref, st));
   SS2_TRY(cost_volume_launch(ctx, warped + half, warped, bs, h64, w64, 128, 5, 128, cv_tgt, st));
   // The two mesh regressors are independent stacks of ~20 small launches each (a few dozen CTAs for 148 SMs, bound by
@@ -607,7 +648,7 @@ extern "C" int ss2_build_temporal(ss2_ctx* ctx, const float* d_frames, int n, fl
     SS2_TRY(run_backbone(ctx, T.bb, d_frames + (size_t)(f0 - 1) * 3 * H * W, nimg, H, W, false, &f64, &h64, &w64,
                          &f32, &h32, &w32, st));
     const int nm = nimg - 1;
-    ARENA_ACT(cv, (size_t)nm * h64 * w64 * 64);
+    ARENA_ACT_SEL(cv, (size_t)nm * h64 * w64 * 64, layer16_ok(ctx, T.r2.convs[0], h64, w64));
     SS2_TRY(cost_volume_launch(ctx, f64, f64 + (size_t)h64 * w64 * 128, nm, h64, w64, 128, 3, 64, cv, st));
     SS2_TRY(run_regressor(ctx, T.r2, cv, nm, h64, w64, d_motions + (size_t)f0 * 126, st));
   }
@@ -648,10 +689,11 @@ extern "C" int ss2_build_temporal_pair(ss2_ctx* ctx, const float* d_frames_a, co
     int h64, w64, h32, w32;
     SS2_TRY(run_backbone(ctx, T.bb, both, 2 * nimg, H, W, false, &f64, &h64, &w64, &f32, &h32, &w32, st));
     const size_t fpx = (size_t)h64 * w64 * 128, cpx = (size_t)h64 * w64 * 64;
-    ARENA_ACT(cv, (size_t)2 * nm * cpx);
+    ARENA_ACT_SEL(cv, (size_t)2 * nm * cpx, layer16_ok(ctx, T.r2.convs[0], h64, w64));
     ActRef cvb = cv;   // second view's half of the cost-volume batch
     cvb.v += (size_t)nm * cpx;
     if (cvb.hi) { cvb.hi += (size_t)nm * cpx; cvb.lo += (size_t)nm * cpx; }
+    if (cvb.h16) { cvb.h16 += (size_t)nm * cpx; cvb.l16 += (size_t)nm * cpx; }
     SS2_TRY(cost_volume_launch(ctx, f64, f64 + fpx, nm, h64, w64, 128, 3, 64, cv, st));
     SS2_TRY(cost_volume_launch(ctx, f64 + (size_t)nimg * fpx, f64 + (size_t)(nimg + 1) * fpx, nm, h64, w64, 128, 3, 64, cvb, st));
     ARENA(mot, float, (size_t)2 * nm * 126);
@@ -716,8 +758,9 @@ extern "C" int ss2_build_smooth(ss2_ctx* ctx, const float* d_ts1, const float* d
     const int nw = nwin - w0 < chunk ? nwin - w0 : chunk;
     ctx->arena.reset();
     const size_t hid = (size_t)nw * SS2_WINDOW * SS2_NPT * 128;
-    ARENA_ACT(h0, hid);
-    ARENA_ACT(h1, hid);
+    const bool s16 = tc16_ok(ctx, M.conv3d[0]) && tc16_ok(ctx, M.conv3d[1]) && tc16_ok(ctx, M.conv3d[2]);   // Conv3d on fp16 planes
+    ARENA_ACT_SEL(h0, hid, s16);
+    ARENA_ACT_SEL(h1, hid, s16);
     ARENA(p1, float, (size_t)nw * SS2_WINDOW * SS2_NPT * 2);
     ARENA(p2, float, (size_t)nw * SS2_WINDOW * SS2_NPT * 2);
     const size_t fo = (size_t)w0 * SS2_NPT * 2;  // frame offset of the first window of the chunk

@@ -858,6 +858,34 @@ def test_conv_kernels_vs_torch(case, use_tc):
     assert err < (3e-4 if use_tc else 2e-5), err
 
 
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("mode", [1, 3])
+def test_conv_kernels_f16_planes_vs_torch(case, mode, monkeypatch):
+    """every production layer shape with fp16 split planes in (mode 1) and in + out (mode 3): the direct 3x3 kernel and the
+    implicit-GEMM kernel (stride-2 entries, 1x1 shortcuts, Conv3d, small maps) run kind::f16 MMAs; same bound as the
+    split-TF32 path in test_conv_kernels_vs_torch"""
+    from stabstitch2_b200 import _lib
+    B, D, H, W, Cin, Cout, k, stride, pad, kd, pad_d = case
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    three_d = kd > 1
+    x = torch.randn(B, D, H, W, Cin, generator=g)
+    w = torch.randn(*((Cout, Cin, kd, k, k) if three_d else (Cout, Cin, k, k)), generator=g) / (Cin * k * k * kd) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    xin = x if three_d else x[:, 0]
+    if three_d:
+        ref = torch.nn.functional.conv3d(x.permute(0, 4, 1, 2, 3).double(), w.double(), b.double(), 1, (pad_d, pad, pad))
+        ref = ref.permute(0, 2, 3, 4, 1)
+    else:
+        ref = torch.nn.functional.conv2d(xin.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride, pad).permute(0, 2, 3, 1)
+    res = torch.randn(*ref.shape, generator=g)
+    ref = torch.relu(ref + res.double()).float()
+    monkeypatch.setenv("SS2_CONV_TEST_F16", str(mode))
+    out = _lib.conv_nhwc(xin.cuda(), w, b, stride=stride, pad=pad, pad_d=pad_d, relu=True, residual=res.cuda(), use_tc=True)
+    assert out.shape == ref.shape
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 3e-4, err
+
+
 @pytest.mark.parametrize("shape", [(3, 13, 37, 64, 64), (2, 29, 126, 64, 128), (5, 9, 50, 128, 64)])
 def test_conv_dc_every_tile_plan(shape, monkeypatch):
     """the direct 3x3 kernel under every tile plan the planner can pick (1-4 column tiles x 1-2 row blocks, forced with
