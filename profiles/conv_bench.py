@@ -17,7 +17,14 @@ LAYERS = [("layer1 64->64 90x120", 32, 90, 120, 64, 64), ("layer2 128->128 45x60
           ("regressor 256->256 12x15 B16", 16, 12, 15, 256, 256), ("regressor 64->64 23x30 B16", 16, 23, 30, 64, 64)]
 
 
-def timed(ctx, reps, fn):
+def timed(ctx, reps, fn0):
+    def fn():
+        try:
+            return fn0()
+        except _lib.SS2Error as exc:   # the dbg modes compute on stale shared memory: the fp16 range flag may fire
+            if "fp16 range" not in str(exc):
+                raise
+            return fn0()
     fn()
     ctx.profile_enable(_lib.PROF_CONV, True)
     for _ in range(reps):
@@ -31,9 +38,14 @@ def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "plans"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     ctx = _lib.context()
-    os.environ["SS2_CONV_TEST_SPLIT"] = "1"
+    # SS2_CONV_TEST_F16=3 in the environment: fp16 split planes in and out (conv1 of a BasicBlock), kind::f16 MMAs
+    if not os.environ.get("SS2_CONV_TEST_F16"):
+        os.environ["SS2_CONV_TEST_SPLIT"] = "1"
     g = torch.Generator().manual_seed(0)
+    only = os.environ.get("CONV_BENCH_ONLY")
     for name, B, H, W, Cin, Cout in LAYERS:
+        if only and only not in name:
+            continue
         x = torch.randn(B, H, W, Cin, generator=g).cuda()
         w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
         b = torch.randn(Cout, generator=g)

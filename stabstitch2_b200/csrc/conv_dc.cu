@@ -371,7 +371,8 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
     if (P.TH < 1) return false;
     P.a_rows = (128 * mt_blocks + 2 * P.P + 2 + 7) / 8 * 8;
     a_stage = (size_t)P.a_rows * 128 * nplanes;
-    P.NA = P.nchunk >= 2 ? 2 : 1;
+    // two input stages: the next chunk's (fp16 planes, 64-channel layers: the next TILE's) box loads under the current MMAs
+    P.NA = (P.nchunk >= 2 || f16) ? 2 : 1;
     if ((size_t)P.NA * a_stage + 2 * b_stage + 1024 > budget) P.NA = 1;
     if ((size_t)P.NA * a_stage + 2 * b_stage + 1024 > budget) return false;
     P.NB = (int)((budget - 1024 - (size_t)P.NA * a_stage) / b_stage);
@@ -406,7 +407,7 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
         const double bytes = (double)P.nchunk * ((double)(P.TH + 2) * P.P * 128 * nplanes + 9.0 * b_stage);
         const long ntl = (long)P.n_mtiles * P.n_ntiles;
         double c = (double)((ntl + nsm - 1) / nsm) * (mma + bytes / 40.0);
-        if (P.NA < 2 && P.nchunk >= 2) c *= 1.15;
+        if (P.NA < 2 && (P.nchunk >= 2 || f16)) c *= 1.15;
         if (P.NB < 3) c *= 1.03;
         if (best < 0 || c < best) { best = c; best_tw = tw; best_mt = mtb; }
       }
