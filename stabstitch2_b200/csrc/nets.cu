@@ -456,7 +456,7 @@ static int run_backbone(ss2_ctx* ctx, const Backbone& bb, const float* x_nchw, i
   SS2_TRY(run_block(ctx, bb.l1[0], cur, NB, h, w, &cur, &h, &w, st, &bb.l1[1]));
   SS2_TRY(run_block(ctx, bb.l1[1], cur, NB, h, w, &cur, &h, &w, st, &bb.l2[0]));
   SS2_TRY(run_block(ctx, bb.l2[0], cur, NB, h, w, &cur, &h, &w, st, &bb.l2[1]));
-  SS2_TRY(run_block(ctx, bb.l2[1], cur, NB, h, w, &cur, &h, &w, st));
+  SS2_TRY(run_block(ctx, bb.l2[1], cur, NB, h, w, &cur, &h, &w, st, stage2 ? &bb.l3[0] : nullptr));   // f64 is read through .v
   *f64 = cur.v; *h64 = h; *w64 = w;
   if (stage2) {
     SS2_TRY(run_block(ctx, bb.l3[0], cur, NB, h, w, &cur, &h, &w, st, &bb.l3[1]));
