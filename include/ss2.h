@@ -54,6 +54,11 @@ enum { SS2_TPS_EXACT = 0,    /* all 63 radial terms per pixel (the reference's a
 #define SS2_WINDOW 7
 
 /* ---- lifetime ------------------------------------------------------------------------ */
+/* Numerics of the convolutions (read from the environment here): fp32-grade by default - every fp32 product is three exact
+ * tensor-core products of 11-bit split operands accumulated in fp32; behind the ResNet stem the halves are fp16 planes
+ * (low half scaled by 2^11), which hold |v| <= 65504: an activation beyond that raises a flag and the NEXT entry point of
+ * the context returns SS2_ERR_UNSUPPORTED naming the cause (once).  SS2_F16=0: TF32 split planes everywhere (no range limit);
+ * SS2_TC_PASSES=1: plain TF32 like cuDNN's default; SS2_USE_TC=0: exact fp32 SIMT kernels. */
 int ss2_create(int device, ss2_ctx** out);
 void ss2_destroy(ss2_ctx* ctx);
 const char* ss2_last_error(ss2_ctx* ctx);
