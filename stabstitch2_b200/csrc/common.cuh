@@ -212,24 +212,24 @@ __device__ __forceinline__ void tf32_split(float v, float* hi, float* lo) {
   *hi = __uint_as_float(r);
   *lo = v - *hi;
 }
-// fp16 split of the kind::f16 path: h = fp16(v) (|v| clamped to the fp16 range), l = fp16((v - h) * 2^11): v = h + l / 2048
-// to 2^-22 relative (to 2^-36 absolute below fp16's normal range, where the scaled l recovers what the subnormal h loses)
+// fp16 split of the kind::f16 path: h = fp16(v), l = fp16((v - h) * 2^11): v = h + l / 2048 to 2^-22 relative (to 2^-36
+// absolute below fp16's normal range, where the scaled l recovers what the subnormal h loses).  |v| > 65504 does not fit
+// (h = inf): the writers below raise the context's range flag for such a value and the next entry point fails loudly.
 #define SS2_F16_LO_SCALE 2048.0f
 __device__ __forceinline__ void f16_split(float v, __half* h, __half* l) {
-  const __half hh = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+  const __half hh = __float2half_rn(v);
   *h = hh;
-  *l = __float2half_rn(fminf(fmaxf((v - __half2float(hh)) * SS2_F16_LO_SCALE, -65504.0f), 65504.0f));
+  *l = __float2half_rn((v - __half2float(hh)) * SS2_F16_LO_SCALE);
 }
-// four consecutive channels of the two fp16 planes (8 bytes each)
+// four consecutive channels of the two fp16 planes (8 bytes each), packed conversions (cvt.rn.f16x2.f32)
 __device__ __forceinline__ void store_f16_planes4(__half* h16, __half* l16, size_t o, const float (&v)[4], int* range_flag) {
   if (fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))) > 65504.0f) *range_flag = 1;   // (NaN compares false)
-  __half h[4], l[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) f16_split(v[e], &h[e], &l[e]);
-  *reinterpret_cast<uint2*>(h16 + o) = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
-                                                  (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
-  *reinterpret_cast<uint2*>(l16 + o) = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
-                                                  (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+  const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn((v[0] - f01.x) * SS2_F16_LO_SCALE, (v[1] - f01.y) * SS2_F16_LO_SCALE);
+  const __half2 l23 = __floats2half2_rn((v[2] - f23.x) * SS2_F16_LO_SCALE, (v[3] - f23.y) * SS2_F16_LO_SCALE);
+  *reinterpret_cast<uint2*>(h16 + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  *reinterpret_cast<uint2*>(l16 + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
 }
 __device__ __forceinline__ void store_split4(const ActRef& o, size_t idx, float4 v) {
   *reinterpret_cast<float4*>(o.v + idx) = v;
