@@ -283,3 +283,42 @@ print("ok")
 ''' % (ref, ROOT, os.path.join(ROOT, "stabstitch2_b200", "dropin"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_f16_split_planes_arithmetic():
+    """The arithmetic the fp16 split planes rest on (csrc/common.cuh f16_split), restated in numpy:
+    h = fp16(v), l = fp16((v - h) * 2^11) reproduces v to 2^-22 relative in fp16's normal range and to 2^-36 absolute below it,
+    and three products of the halves, the two correction products accumulated with the factor 2^11 and folded in at the end
+    (D1 + D2 / 2048), reproduce an fp32 dot product to ~2^-21 - the accuracy of the split-TF32 form."""
+    rng = np.random.default_rng(7)
+    mag = 10.0 ** rng.uniform(-9, 4.5, size=200000)
+    v = (rng.standard_normal(200000) * mag).astype(np.float32)
+    v = v[np.abs(v) <= 65504]
+
+    def split(x):
+        h = x.astype(np.float16)
+        l = ((x - h.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)   # the subtraction is exact in fp32
+        return h, l
+
+    h, l = split(v)
+    assert np.isfinite(h.astype(np.float32)).all() and np.isfinite(l.astype(np.float32)).all()
+    rec = h.astype(np.float64) + l.astype(np.float64) / 2048.0
+    err = np.abs(rec - v.astype(np.float64))
+    normal = np.abs(v) >= 2.0 ** -14
+    assert (err[normal] <= np.abs(v[normal]).astype(np.float64) * 2.0 ** -22).all()
+    assert (err[~normal] <= 2.0 ** -36).all()
+    # dot products of K = 576 terms (a 64-channel 3x3 layer), activations and weights of mixed magnitude
+    K, M = 576, 2000
+    a = (rng.standard_normal((M, K)) * 10.0 ** rng.uniform(-3, 1, size=(M, 1))).astype(np.float32)
+    b = (rng.standard_normal((M, K)) / np.sqrt(K)).astype(np.float32)
+    ah, al = split(a)
+    bh, bl = split(b)
+    f64 = lambda x: x.astype(np.float64)  # noqa: E731  (products of 11-bit halves are exact in fp32; the sums are taken in fp64 here)
+    d1 = (f64(ah) * f64(bh)).sum(1)
+    d2 = (f64(ah) * f64(bl)).sum(1) + (f64(al) * f64(bh)).sum(1)
+    got = d1 + d2 / 2048.0
+    ref = (f64(a) * f64(b)).sum(1)
+    scale = (np.abs(f64(a)) * np.abs(f64(b))).sum(1)
+    assert (np.abs(got - ref) <= scale * 2.0 ** -21).all()
+    # without the correction products (plain fp16 operands) the same bound fails by orders of magnitude
+    assert (np.abs(d1 - ref) > scale * 2.0 ** -21).mean() > 0.9
