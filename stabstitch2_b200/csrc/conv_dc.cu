@@ -15,7 +15,9 @@
 //   * weights stream through their own ring (one [64 cout][32 k] hi/lo stage per (chunk, tap)).
 //   * persistent CTAs (one per SM) with two TMEM accumulators: the epilogue of tile i overlaps the MMAs of
 //     tile i + 1.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue.
-// Numerics are those of conv_tc.cu (split TF32, fp32 accumulation in TMEM).
+// Numerics are those of conv_tc.cu: three exact products of 11-bit split operands per fp32 product, fp32 accumulation in
+// TMEM; the operands are TF32 split planes (kind::tf32, K = 8 per MMA) or, template flag F16 - the default behind the stem -
+// fp16 split planes with a 2^11-scaled low half (kind::f16, K = 16 per MMA: half the chunks, stages and instructions).
 #include "tc_common.cuh"
 
 #define DC_THREADS 192
@@ -426,14 +428,14 @@ int conv_dc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
     SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_h16, 9 * L.CinP, L.CoutP, true));
     SS2_TRY(make_weight_map(ctx, &mB_lo, L.wk_l16, 9 * L.CinP, L.CoutP, true));
   } else {
-  SS2_TRY(make_act_map(ctx, &mA_hi, in.hi, L.CinP, W, H, 1, B, P.P, P.TH + 2, 1, 1, 1, 1, 1));
-  SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_hi, 9 * L.CinP, L.CoutP));
-  if (P.npass == 3) {
-    SS2_TRY(make_act_map(ctx, &mA_lo, in.lo, L.CinP, W, H, 1, B, P.P, P.TH + 2, 1, 1, 1, 1, 1));
-    SS2_TRY(make_weight_map(ctx, &mB_lo, L.wk_lo, 9 * L.CinP, L.CoutP));
-  } else {
-    mA_lo = mA_hi; mB_lo = mB_hi;
-  }
+    SS2_TRY(make_act_map(ctx, &mA_hi, in.hi, L.CinP, W, H, 1, B, P.P, P.TH + 2, 1, 1, 1, 1, 1));
+    SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_hi, 9 * L.CinP, L.CoutP));
+    if (P.npass == 3) {
+      SS2_TRY(make_act_map(ctx, &mA_lo, in.lo, L.CinP, W, H, 1, B, P.P, P.TH + 2, 1, 1, 1, 1, 1));
+      SS2_TRY(make_weight_map(ctx, &mB_lo, L.wk_lo, 9 * L.CinP, L.CoutP));
+    } else {
+      mA_lo = mA_hi; mB_lo = mB_hi;
+    }
   }
   static size_t attr_smem_dev[16][8] = {{0}};  // per device: function attributes live in the device's context
   size_t* attr_smem = attr_smem_dev[ctx->device & 15];

@@ -15,6 +15,9 @@
 //   * fp32-grade results ("3xTF32"): activations and weights are stored as hi = rna_tf32(v) and
 //     lo = v - hi; D += Ahi*Bhi + Alo*Bhi + Ahi*Blo (error ~2^-21 relative instead of TF32's
 //     2^-11).  NPASS=1 runs plain TF32 (what cuDNN does for the reference's GPU convolutions).
+//   * F16 (the default behind the stem): the same three products on fp16 split planes, h16 = fp16(v) and
+//     l16 = fp16((v - h16) * 2048), as kind::f16 MMAs (M=128, N=64, K=16: a 128-byte row holds 64 channels); the two
+//     correction products carry the factor 2048 and accumulate in D2, the epilogue takes D1 + D2 / 2048 (common.cuh).
 //   * epilogue: 4 warps tcgen05.ld their 32 TMEM lanes, add bias / residual, ReLU, and store the
 //     row as fp32 plus its (hi, lo) split for the next tensor-core layer.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM lane
@@ -62,10 +65,6 @@ struct TcParams {
   int ncol;  // output columns per N tile (64 for convolutions)
 };
 
-// instruction descriptor: D fp32, A/B tf32, both K-major, N = 64, M = 128
-__host__ __device__ constexpr uint32_t tc_idesc() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
 
 // F16 (with NPASS == 3): the operands are fp16 split planes and the MMAs kind::f16, exactly as in conv_dc.cu: a 128-byte
 // row is 64 channels, K = 16 per instruction, A_l x B_h accumulates into the 2048-scaled D2, the epilogue takes D1 + D2 / 2048.
@@ -366,14 +365,14 @@ int conv_tc_launch(ss2_ctx* ctx, const ConvLayer& L, const ActRef& in, int B, in
     SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_h16, L.KD * L.KH * L.KW * L.CinP, L.CoutP, true));
     SS2_TRY(make_weight_map(ctx, &mB_lo, L.wk_l16, L.KD * L.KH * L.KW * L.CinP, L.CoutP, true));
   } else {
-  SS2_TRY(make_act_map(ctx, &mA_hi, in.hi, L.CinP, W, H, D, B, bw, bh, bd, P.TN, L.sw, L.sh, L.sd));
-  SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_hi, L.KD * L.KH * L.KW * L.CinP, L.CoutP));
-  if (npass == 3) {
-    SS2_TRY(make_act_map(ctx, &mA_lo, in.lo, L.CinP, W, H, D, B, bw, bh, bd, P.TN, L.sw, L.sh, L.sd));
-    SS2_TRY(make_weight_map(ctx, &mB_lo, L.wk_lo, L.KD * L.KH * L.KW * L.CinP, L.CoutP));
-  } else {
-    mA_lo = mA_hi; mB_lo = mB_hi;
-  }
+    SS2_TRY(make_act_map(ctx, &mA_hi, in.hi, L.CinP, W, H, D, B, bw, bh, bd, P.TN, L.sw, L.sh, L.sd));
+    SS2_TRY(make_weight_map(ctx, &mB_hi, L.wk_hi, L.KD * L.KH * L.KW * L.CinP, L.CoutP));
+    if (npass == 3) {
+      SS2_TRY(make_act_map(ctx, &mA_lo, in.lo, L.CinP, W, H, D, B, bw, bh, bd, P.TN, L.sw, L.sh, L.sd));
+      SS2_TRY(make_weight_map(ctx, &mB_lo, L.wk_lo, L.KD * L.KH * L.KW * L.CinP, L.CoutP));
+    } else {
+      mA_lo = mA_hi; mB_lo = mB_hi;
+    }
   }
   dim3 grid(P.nW * P.nH * P.nT * P.nN, L.CoutP / TC_BN);
   const double flops = 2.0 * B * P.Do * P.Ho * P.Wo * (double)L.Cout * L.KD * L.KH * L.KW * L.Cin;
@@ -501,14 +500,14 @@ int conv_tc_corr_launch(ss2_ctx* ctx, const ActRef& n1, const ActRef& n2, int B,
     SS2_TRY(make_act_map(ctx, &mA_lo, n1.l16, C, W, H, 1, B, P.TW, P.TH, 1, 1, 1, 1, 1, true));
     SS2_TRY(make_act_map(ctx, &mB_lo, n2.l16, C, W, H, 1, B, P.bTW, P.bTH, 1, 1, 1, 1, 1, true));
   } else {
-  SS2_TRY(make_act_map(ctx, &mA_hi, n1.hi, C, W, H, 1, B, P.TW, P.TH, 1, 1, 1, 1, 1));
-  SS2_TRY(make_act_map(ctx, &mB_hi, n2.hi, C, W, H, 1, B, P.bTW, P.bTH, 1, 1, 1, 1, 1));
-  if (npass == 3) {
-    SS2_TRY(make_act_map(ctx, &mA_lo, n1.lo, C, W, H, 1, B, P.TW, P.TH, 1, 1, 1, 1, 1));
-    SS2_TRY(make_act_map(ctx, &mB_lo, n2.lo, C, W, H, 1, B, P.bTW, P.bTH, 1, 1, 1, 1, 1));
-  } else {
-    mA_lo = mA_hi; mB_lo = mB_hi;
-  }
+    SS2_TRY(make_act_map(ctx, &mA_hi, n1.hi, C, W, H, 1, B, P.TW, P.TH, 1, 1, 1, 1, 1));
+    SS2_TRY(make_act_map(ctx, &mB_hi, n2.hi, C, W, H, 1, B, P.bTW, P.bTH, 1, 1, 1, 1, 1));
+    if (npass == 3) {
+      SS2_TRY(make_act_map(ctx, &mA_lo, n1.lo, C, W, H, 1, B, P.TW, P.TH, 1, 1, 1, 1, 1));
+      SS2_TRY(make_act_map(ctx, &mB_lo, n2.lo, C, W, H, 1, B, P.bTW, P.bTH, 1, 1, 1, 1, 1));
+    } else {
+      mA_lo = mA_hi; mB_lo = mB_hi;
+    }
   }
   dim3 grid(P.nH * B, cdiv(H, P.bTH));
   ss2_prof_begin(ctx, SS2_PROF_CONV, st);
